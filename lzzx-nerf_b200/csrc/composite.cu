@@ -1,0 +1,425 @@
+// composite.cu — alpha compositing (training forward/backward, inference incremental) for sm_100a.
+//
+// One templated core instantiates the reference's four training variants and five inference variants
+// (raymarching.cu:604-2258): <AMB, NA, UNC> = <ambient mode, #ambient channels, has uncertainty>
+//     plain        <1,1,false>   ambient_sum += a              (:604/:712/:1043)
+//     sigma        <2,1,false>   ambient_sum += w * a          (:1162/:1270/:1387)
+//     uncertainty  <1,1,true>    + uncertainty_sum += w * u    (:1507/:1622/:1754)
+//     triplane     <1,2,true>    two plain ambient channels    (:1878/:2000/:2142)
+//     rgb only     <0,0,false>   composite_rays                (:943)
+//
+// The per-ray recurrence (T *= 1-alpha, early stop on T < T_thresh) is kept SERIAL and in the reference's
+// operation order, so results are bit-identical to the reference kernels on the same GPU (same MUFU.EX2).
+// What changes is data movement: a CTA owns 128 consecutive rows of `rays`; when their sample segments tile
+// one contiguous range (always true for b2n_march_rays_train's deterministic allocation) the CTA stages that
+// range through shared memory with fully coalesced 128 B transactions, threads walk their ray out of shared
+// memory, and the backward writes its per-sample gradients back through the same staging buffer — so HBM
+// sees each algorithmic byte exactly once.  Foreign `rays` orderings (the reference's atomic allocation)
+// take the direct global-memory path of the same template.
+#include "common.cuh"
+
+namespace b2n {
+
+constexpr int CT_THREADS = 128;
+constexpr int CT_CAP = 2048;            // staged samples per CTA (128 rays x 16 steps)
+
+template <int NA, bool UNC> struct Stage {
+    // floats per staged sample: sigma 1, deltas 2, rgb 3, ambient NA, unc
+    static constexpr int FLOATS = 6 + NA + (UNC ? 1 : 0);
+};
+
+// exp(-sigma*delta) exactly as nvcc emits __expf(-s*d) for the reference: (s*d) * -log2(e) -> ex2.approx
+__device__ __forceinline__ float alpha_of(float sigma, float delta) { return __fsub_rn(1.0f, __expf(-__fmul_rn(sigma, delta))); }
+
+// CTA-wide: decide whether the valid segments of this CTA's rows tile [lo, lo+total) in row order.
+// Returns true (uniformly) if so and total <= CT_CAP; fills lo/total.
+__device__ __forceinline__ bool cta_tiling(bool valid, uint32_t off, uint32_t num, uint32_t &lo, uint32_t &total) {
+    __shared__ uint32_t s_w[CT_THREADS / 32];
+    __shared__ uint32_t s_lo;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t cnt = valid ? num : 0u;
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) s_w[warp] = inc;
+    if (threadIdx.x == 0) s_lo = 0xffffffffu;
+    __syncthreads();
+    uint32_t before = inc - cnt, tot = 0;
+#pragma unroll
+    for (int w = 0; w < CT_THREADS / 32; w++) { if (w < (int)warp) before += s_w[w]; tot += s_w[w]; }
+    // the first valid row defines lo (it is the one with before == 0 and cnt > 0)
+    if (valid && before == 0) s_lo = off;        // several rows may have before==0 only if earlier ones have cnt==0 → invalid
+    __syncthreads();
+    lo = s_lo; total = tot;
+    const bool ok = !valid || (off == lo + before);
+    return __syncthreads_and(ok) && tot <= CT_CAP && tot > 0;
+}
+
+// coalesced copy of `count` floats global -> shared (count*4 bytes contiguous, arbitrary 4 B alignment)
+__device__ __forceinline__ void stage_in(float *dst, const float *__restrict__ src, uint32_t count) {
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < count; i += CT_THREADS) dst[i] = __ldcs(src + i);
+}
+__device__ __forceinline__ void stage_out(float *__restrict__ dst, const float *src, uint32_t count) {
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < count; i += CT_THREADS) __stcs(dst + i, src[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// training forward
+// ---------------------------------------------------------------------------------------------------
+template <int AMB, int NA, bool UNC>
+__device__ __forceinline__ void train_fwd_ray(const float *sg, const float *rgb, const float *a0p, const float *a1p, const float *up,
+                                              const float *dl, uint32_t num, float T_thresh,
+                                              float &ws, float &a0, float &a1, float &u, float &d, float &r, float &g, float &b) {
+    float T = 1.0f;
+    for (uint32_t k = 0; k < num; k++) {
+        const float alpha = alpha_of(sg[k], dl[2 * k]);
+        const float w = __fmul_rn(alpha, T);
+        r = __fmaf_rn(w, rgb[3 * k], r);
+        g = __fmaf_rn(w, rgb[3 * k + 1], g);
+        b = __fmaf_rn(w, rgb[3 * k + 2], b);
+        d = __fmaf_rn(w, dl[2 * k + 1], d);
+        ws = __fadd_rn(ws, w);
+        if (NA >= 1) a0 = (AMB == 2) ? __fmaf_rn(w, a0p[k], a0) : __fadd_rn(a0, a0p[k]);
+        if (NA >= 2) a1 = (AMB == 2) ? __fmaf_rn(w, a1p[k], a1) : __fadd_rn(a1, a1p[k]);
+        if (UNC) u = __fmaf_rn(w, up[k], u);
+        T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+        if (T < T_thresh) break;
+    }
+}
+
+template <int AMB, int NA, bool UNC>
+__global__ void __launch_bounds__(CT_THREADS) k_comp_train_fwd(
+        const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ amb0,
+        const float *__restrict__ amb1, const float *__restrict__ unc, const float *__restrict__ deltas,
+        const int32_t *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
+        float *__restrict__ weights_sum, float *__restrict__ amb0_sum, float *__restrict__ amb1_sum,
+        float *__restrict__ unc_sum, float *__restrict__ depth, float *__restrict__ image) {
+    extern __shared__ float sm[];
+    const uint32_t n = blockIdx.x * CT_THREADS + threadIdx.x;
+    uint32_t idx = 0, off = 0, num = 0;
+    if (n < N) { idx = (uint32_t)rays[3 * (size_t)n]; off = (uint32_t)rays[3 * (size_t)n + 1]; num = (uint32_t)rays[3 * (size_t)n + 2]; }
+    const bool valid = (n < N) && !(num == 0 || off + num > M);
+    uint32_t lo, total;
+    const bool staged = cta_tiling(valid, off, num, lo, total);
+    float ws = 0, a0 = 0, a1 = 0, u = 0, d = 0, r = 0, g = 0, b = 0;
+    if (staged) {
+        float *s_sg = sm, *s_dl = s_sg + CT_CAP, *s_rgb = s_dl + 2 * CT_CAP, *s_a0 = s_rgb + 3 * CT_CAP;
+        float *s_a1 = s_a0 + (NA >= 1 ? CT_CAP : 0), *s_u = s_a1 + (NA >= 2 ? CT_CAP : 0);
+        stage_in(s_sg, sigmas + lo, total);
+        stage_in(s_dl, deltas + 2 * (size_t)lo, 2 * total);
+        stage_in(s_rgb, rgbs + 3 * (size_t)lo, 3 * total);
+        if (NA >= 1) stage_in(s_a0, amb0 + lo, total);
+        if (NA >= 2) stage_in(s_a1, amb1 + lo, total);
+        if (UNC) stage_in(s_u, unc + lo, total);
+        __syncthreads();
+        if (valid) {
+            const uint32_t o = off - lo;
+            train_fwd_ray<AMB, NA, UNC>(s_sg + o, s_rgb + 3 * o, s_a0 + o, s_a1 + o, s_u + o, s_dl + 2 * o, num, T_thresh, ws, a0, a1, u, d, r, g, b);
+        }
+    } else if (valid) {
+        train_fwd_ray<AMB, NA, UNC>(sigmas + off, rgbs + 3 * (size_t)off, NA >= 1 ? amb0 + off : nullptr, NA >= 2 ? amb1 + off : nullptr,
+                                    UNC ? unc + off : nullptr, deltas + 2 * (size_t)off, num, T_thresh, ws, a0, a1, u, d, r, g, b);
+    }
+    if (n >= N) return;
+    weights_sum[idx] = ws;
+    if (NA >= 1) amb0_sum[idx] = a0;
+    if (NA >= 2) amb1_sum[idx] = a1;
+    if (UNC) unc_sum[idx] = u;
+    depth[idx] = d;
+    image[3 * (size_t)idx] = r; image[3 * (size_t)idx + 1] = g; image[3 * (size_t)idx + 2] = b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// training backward.  Gradients of samples after the early stop stay 0 (caller pre-zeroes; the staged path
+// rewrites the whole tiled range, zeros included).
+// ---------------------------------------------------------------------------------------------------
+struct RayGrads { float gws, ga0, ga1, gu, gi0, gi1, gi2, wsF, a0F, uF, rF, gF, bF; };
+
+// IN-PLACE capable: gs/grgb/ga0/ga1/gu may alias sg/rgb/a0p/a1p/up (each sample is read before it is written)
+template <int AMB, int NA, bool UNC, bool ZERO_TAIL>
+__device__ __forceinline__ void train_bwd_ray(const float *sg, const float *rgb, const float *a0p, const float *up, const float *dl,
+                                              uint32_t num, float T_thresh, const RayGrads &q,
+                                              float *gs, float *grgb, float *ga0, float *ga1, float *gu) {
+    float T = 1.0f, r = 0, g = 0, b = 0, a = 0, u = 0;
+    uint32_t k = 0;
+    for (; k < num; k++) {
+        const float sigma = sg[k], delta = dl[2 * k];
+        const float c0 = rgb[3 * k], c1 = rgb[3 * k + 1], c2 = rgb[3 * k + 2];
+        const float av = (AMB == 2) ? a0p[k] : 0.0f;
+        const float uv = UNC ? up[k] : 0.0f;
+        const float alpha = alpha_of(sigma, delta);
+        const float w = __fmul_rn(alpha, T);
+        r = __fmaf_rn(w, c0, r); g = __fmaf_rn(w, c1, g); b = __fmaf_rn(w, c2, b);
+        if (AMB == 2) a = __fmaf_rn(w, av, a);
+        if (UNC) u = __fmaf_rn(w, uv, u);
+        T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+        grgb[3 * k] = __fmul_rn(q.gi0, w); grgb[3 * k + 1] = __fmul_rn(q.gi1, w); grgb[3 * k + 2] = __fmul_rn(q.gi2, w);
+        if (NA >= 1) ga0[k] = (AMB == 2) ? __fmul_rn(q.ga0, w) : q.ga0;
+        if (NA >= 2) ga1[k] = q.ga1;
+        if (UNC) gu[k] = __fmul_rn(q.gu, w);
+        float acc = __fmul_rn(q.gi0, __fmaf_rn(T, c0, -__fsub_rn(q.rF, r)));
+        acc = __fmaf_rn(q.gi1, __fmaf_rn(T, c1, -__fsub_rn(q.gF, g)), acc);
+        acc = __fmaf_rn(q.gi2, __fmaf_rn(T, c2, -__fsub_rn(q.bF, b)), acc);
+        if (AMB == 2) acc = __fmaf_rn(q.ga0, __fmaf_rn(T, av, -__fsub_rn(q.a0F, a)), acc);
+        if (UNC) acc = __fmaf_rn(q.gu, __fmaf_rn(T, uv, -__fsub_rn(q.uF, u)), acc);
+        acc = __fmaf_rn(q.gws, __fsub_rn(1.0f, q.wsF), acc);
+        gs[k] = __fmul_rn(delta, acc);
+        if (T < T_thresh) { k++; break; }
+    }
+    if (ZERO_TAIL) {
+        for (; k < num; k++) {
+            gs[k] = 0.0f; grgb[3 * k] = 0.0f; grgb[3 * k + 1] = 0.0f; grgb[3 * k + 2] = 0.0f;
+            if (NA >= 1) ga0[k] = 0.0f;
+            if (NA >= 2) ga1[k] = 0.0f;
+            if (UNC) gu[k] = 0.0f;
+        }
+    }
+}
+
+template <int AMB, int NA, bool UNC>
+__global__ void __launch_bounds__(CT_THREADS) k_comp_train_bwd(
+        const float *__restrict__ g_ws, const float *__restrict__ g_a0, const float *__restrict__ g_a1,
+        const float *__restrict__ g_u, const float *__restrict__ g_img,
+        const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ amb0,
+        const float *__restrict__ unc, const float *__restrict__ deltas, const int32_t *__restrict__ rays,
+        const float *__restrict__ weights_sum, const float *__restrict__ amb0_sum, const float *__restrict__ unc_sum,
+        const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
+        float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs, float *__restrict__ grad_a0,
+        float *__restrict__ grad_a1, float *__restrict__ grad_u) {
+    extern __shared__ float sm[];
+    const uint32_t n = blockIdx.x * CT_THREADS + threadIdx.x;
+    uint32_t idx = 0, off = 0, num = 0;
+    if (n < N) { idx = (uint32_t)rays[3 * (size_t)n]; off = (uint32_t)rays[3 * (size_t)n + 1]; num = (uint32_t)rays[3 * (size_t)n + 2]; }
+    const bool valid = (n < N) && !(num == 0 || off + num > M);
+    uint32_t lo, total;
+    const bool staged = cta_tiling(valid, off, num, lo, total);
+    RayGrads q = {};
+    if (valid) {
+        q.gws = g_ws[idx];
+        if (NA >= 1) q.ga0 = g_a0[idx];
+        if (NA >= 2) q.ga1 = g_a1[idx];
+        if (UNC) { q.gu = g_u[idx]; q.uF = unc_sum[idx]; }
+        if (AMB == 2) q.a0F = amb0_sum[idx];
+        q.gi0 = g_img[3 * (size_t)idx]; q.gi1 = g_img[3 * (size_t)idx + 1]; q.gi2 = g_img[3 * (size_t)idx + 2];
+        q.wsF = weights_sum[idx];
+        q.rF = image[3 * (size_t)idx]; q.gF = image[3 * (size_t)idx + 1]; q.bF = image[3 * (size_t)idx + 2];
+    }
+    if (staged) {
+        // s_a0 doubles as grad_a0 staging, s_a1 is output-only (grad_a1 = per-ray constant), s_u doubles as grad_u
+        float *s_sg = sm, *s_dl = s_sg + CT_CAP, *s_rgb = s_dl + 2 * CT_CAP, *s_a0 = s_rgb + 3 * CT_CAP;
+        float *s_a1 = s_a0 + (NA >= 1 ? CT_CAP : 0), *s_u = s_a1 + (NA >= 2 ? CT_CAP : 0);
+        stage_in(s_sg, sigmas + lo, total);
+        stage_in(s_dl, deltas + 2 * (size_t)lo, 2 * total);
+        stage_in(s_rgb, rgbs + 3 * (size_t)lo, 3 * total);
+        if (AMB == 2) stage_in(s_a0, amb0 + lo, total);
+        if (UNC) stage_in(s_u, unc + lo, total);
+        __syncthreads();
+        if (valid) {
+            const uint32_t o = off - lo;
+            train_bwd_ray<AMB, NA, UNC, true>(s_sg + o, s_rgb + 3 * o, s_a0 + o, s_u + o, s_dl + 2 * o, num, T_thresh, q,
+                                              s_sg + o, s_rgb + 3 * o, s_a0 + o, s_a1 + o, s_u + o);
+        }
+        __syncthreads();
+        stage_out(grad_sigmas + lo, s_sg, total);
+        stage_out(grad_rgbs + 3 * (size_t)lo, s_rgb, 3 * total);
+        if (NA >= 1) stage_out(grad_a0 + lo, s_a0, total);
+        if (NA >= 2) stage_out(grad_a1 + lo, s_a1, total);
+        if (UNC) stage_out(grad_u + lo, s_u, total);
+    } else if (valid) {
+        train_bwd_ray<AMB, NA, UNC, false>(sigmas + off, rgbs + 3 * (size_t)off, AMB == 2 ? amb0 + off : nullptr, UNC ? unc + off : nullptr,
+                                           deltas + 2 * (size_t)off, num, T_thresh, q, grad_sigmas + off, grad_rgbs + 3 * (size_t)off,
+                                           NA >= 1 ? grad_a0 + off : nullptr, NA >= 2 ? grad_a1 + off : nullptr, UNC ? grad_u + off : nullptr);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// inference: incremental, in place (raymarching.cu:943-1029 and variants)
+// ---------------------------------------------------------------------------------------------------
+template <int AMB, int NA, bool UNC>
+__global__ void __launch_bounds__(128) k_comp_infer(
+        uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *__restrict__ rays_alive, float *__restrict__ rays_t,
+        const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
+        const float *__restrict__ amb0, const float *__restrict__ amb1, const float *__restrict__ unc,
+        float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image,
+        float *__restrict__ amb0_sum, float *__restrict__ amb1_sum, float *__restrict__ unc_sum) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int32_t idx = rays_alive[n];
+    const size_t base = (size_t)n * n_step;
+    float t = rays_t[idx], ws = weights_sum[idx], d = depth[idx];
+    float r = image[3 * (size_t)idx], g = image[3 * (size_t)idx + 1], b = image[3 * (size_t)idx + 2];
+    float a0 = NA >= 1 ? amb0_sum[idx] : 0.0f, a1 = NA >= 2 ? amb1_sum[idx] : 0.0f, u = UNC ? unc_sum[idx] : 0.0f;
+    uint32_t step = 0;
+    while (step < n_step) {
+        const size_t i = base + step;
+        const float delta = deltas[2 * i];
+        if (delta == 0.0f) break;
+        const float alpha = alpha_of(sigmas[i], delta);
+        const float T = __fsub_rn(1.0f, ws);
+        const float w = __fmul_rn(alpha, T);
+        ws = __fadd_rn(ws, w);
+        t = deltas[2 * i + 1];
+        d = __fmaf_rn(w, t, d);
+        r = __fmaf_rn(w, rgbs[3 * i], r); g = __fmaf_rn(w, rgbs[3 * i + 1], g); b = __fmaf_rn(w, rgbs[3 * i + 2], b);
+        if (NA >= 1) a0 = (AMB == 2) ? __fmaf_rn(w, amb0[i], a0) : __fadd_rn(a0, amb0[i]);
+        if (NA >= 2) a1 = (AMB == 2) ? __fmaf_rn(w, amb1[i], a1) : __fadd_rn(a1, amb1[i]);
+        if (UNC) u = __fmaf_rn(w, unc[i], u);
+        if (T < T_thresh) break;
+        step++;
+    }
+    if (step < n_step) rays_alive[n] = -1; else rays_t[idx] = t;
+    weights_sum[idx] = ws; depth[idx] = d;
+    image[3 * (size_t)idx] = r; image[3 * (size_t)idx + 1] = g; image[3 * (size_t)idx + 2] = b;
+    if (NA >= 1) amb0_sum[idx] = a0;
+    if (NA >= 2) amb1_sum[idx] = a1;
+    if (UNC) unc_sum[idx] = u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------------
+template <int AMB, int NA, bool UNC>
+static int launch_train_fwd(const char *what, const float *sigmas, const float *rgbs, const float *amb0, const float *amb1, const float *unc,
+                            const float *deltas, const int32_t *rays, uint32_t M, uint32_t N, float T_thresh,
+                            float *ws, float *a0s, float *a1s, float *us, float *depth, float *image, void *stream) {
+    B2N_REQUIRE(sigmas && rgbs && deltas && rays && ws && depth && image, "%s: null pointer", what);
+    B2N_REQUIRE((NA < 1 || (amb0 && a0s)) && (NA < 2 || (amb1 && a1s)) && (!UNC || (unc && us)), "%s: null pointer", what);
+    if (N == 0) return 0;
+    static bool attr_done = false;
+    const size_t smem = sizeof(float) * (size_t)Stage<NA, UNC>::FLOATS * CT_CAP;
+    auto kern = k_comp_train_fwd<AMB, NA, UNC>;
+    if (!attr_done) { B2N_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    kern<<<ceil_div<uint32_t>(N, CT_THREADS), CT_THREADS, smem, as_stream(stream)>>>(sigmas, rgbs, amb0, amb1, unc, deltas, rays, M, N, T_thresh,
+                                                                                     ws, a0s, a1s, us, depth, image);
+    return check_launch(what);
+}
+
+template <int AMB, int NA, bool UNC>
+static int launch_train_bwd(const char *what, const float *g_ws, const float *g_a0, const float *g_a1, const float *g_u, const float *g_img,
+                            const float *sigmas, const float *rgbs, const float *amb0, const float *unc, const float *deltas,
+                            const int32_t *rays, const float *ws, const float *a0s, const float *us, const float *image,
+                            uint32_t M, uint32_t N, float T_thresh, float *gs, float *grgb, float *ga0, float *ga1, float *gu, void *stream) {
+    B2N_REQUIRE(g_ws && g_img && sigmas && rgbs && deltas && rays && ws && image && gs && grgb, "%s: null pointer", what);
+    B2N_REQUIRE((NA < 1 || (g_a0 && ga0)) && (NA < 2 || (g_a1 && ga1)) && (!UNC || (g_u && unc && us && gu)) && (AMB != 2 || (amb0 && a0s)),
+                "%s: null pointer", what);
+    if (N == 0) return 0;
+    static bool attr_done = false;
+    const size_t smem = sizeof(float) * (size_t)Stage<NA, UNC>::FLOATS * CT_CAP;
+    auto kern = k_comp_train_bwd<AMB, NA, UNC>;
+    if (!attr_done) { B2N_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    kern<<<ceil_div<uint32_t>(N, CT_THREADS), CT_THREADS, smem, as_stream(stream)>>>(g_ws, g_a0, g_a1, g_u, g_img, sigmas, rgbs, amb0, unc, deltas, rays,
+                                                                                     ws, a0s, us, image, M, N, T_thresh, gs, grgb, ga0, ga1, gu);
+    return check_launch(what);
+}
+
+template <int AMB, int NA, bool UNC>
+static int launch_infer(const char *what, uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t,
+                        const float *sigmas, const float *rgbs, const float *deltas, const float *amb0, const float *amb1, const float *unc,
+                        float *ws, float *depth, float *image, float *a0s, float *a1s, float *us, void *stream) {
+    B2N_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && ws && depth && image, "%s: null pointer", what);
+    B2N_REQUIRE((NA < 1 || (amb0 && a0s)) && (NA < 2 || (amb1 && a1s)) && (!UNC || (unc && us)), "%s: null pointer", what);
+    if (n_alive == 0) return 0;
+    k_comp_infer<AMB, NA, UNC><<<ceil_div<uint32_t>(n_alive, 128), 128, 0, as_stream(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas,
+                                                                                                 amb0, amb1, unc, ws, depth, image, a0s, a1s, us);
+    return check_launch(what);
+}
+
+}  // namespace b2n
+
+using namespace b2n;
+
+extern "C" {
+
+int b2n_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *ambient, const float *deltas, const int32_t *rays,
+                                     uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *ambient_sum, float *depth, float *image, void *stream) {
+    return launch_train_fwd<1, 1, false>("composite_rays_train_forward", sigmas, rgbs, ambient, nullptr, nullptr, deltas, rays, M, N, T_thresh,
+                                         weights_sum, ambient_sum, nullptr, nullptr, depth, image, stream);
+}
+int b2n_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_ambient_sum, const float *grad_image, const float *sigmas,
+                                      const float *rgbs, const float *ambient, const float *deltas, const int32_t *rays, const float *weights_sum,
+                                      const float *ambient_sum, const float *image, uint32_t M, uint32_t N, float T_thresh,
+                                      float *grad_sigmas, float *grad_rgbs, float *grad_ambient, void *stream) {
+    (void)ambient; (void)ambient_sum;
+    return launch_train_bwd<1, 1, false>("composite_rays_train_backward", grad_weights_sum, grad_ambient_sum, nullptr, nullptr, grad_image, sigmas, rgbs,
+                                         nullptr, nullptr, deltas, rays, weights_sum, nullptr, nullptr, image, M, N, T_thresh,
+                                         grad_sigmas, grad_rgbs, grad_ambient, nullptr, nullptr, stream);
+}
+int b2n_composite_rays_train_sigma_forward(const float *sigmas, const float *rgbs, const float *ambient, const float *deltas, const int32_t *rays,
+                                           uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *ambient_sum, float *depth, float *image, void *stream) {
+    return launch_train_fwd<2, 1, false>("composite_rays_train_sigma_forward", sigmas, rgbs, ambient, nullptr, nullptr, deltas, rays, M, N, T_thresh,
+                                         weights_sum, ambient_sum, nullptr, nullptr, depth, image, stream);
+}
+int b2n_composite_rays_train_sigma_backward(const float *grad_weights_sum, const float *grad_ambient_sum, const float *grad_image, const float *sigmas,
+                                            const float *rgbs, const float *ambient, const float *deltas, const int32_t *rays, const float *weights_sum,
+                                            const float *ambient_sum, const float *image, uint32_t M, uint32_t N, float T_thresh,
+                                            float *grad_sigmas, float *grad_rgbs, float *grad_ambient, void *stream) {
+    return launch_train_bwd<2, 1, false>("composite_rays_train_sigma_backward", grad_weights_sum, grad_ambient_sum, nullptr, nullptr, grad_image, sigmas, rgbs,
+                                         ambient, nullptr, deltas, rays, weights_sum, ambient_sum, nullptr, image, M, N, T_thresh,
+                                         grad_sigmas, grad_rgbs, grad_ambient, nullptr, nullptr, stream);
+}
+int b2n_composite_rays_train_uncertainty_forward(const float *sigmas, const float *rgbs, const float *ambient, const float *uncertainty, const float *deltas,
+                                                 const int32_t *rays, uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *ambient_sum,
+                                                 float *uncertainty_sum, float *depth, float *image, void *stream) {
+    return launch_train_fwd<1, 1, true>("composite_rays_train_uncertainty_forward", sigmas, rgbs, ambient, nullptr, uncertainty, deltas, rays, M, N, T_thresh,
+                                        weights_sum, ambient_sum, nullptr, uncertainty_sum, depth, image, stream);
+}
+int b2n_composite_rays_train_uncertainty_backward(const float *grad_weights_sum, const float *grad_ambient_sum, const float *grad_uncertainty_sum,
+                                                  const float *grad_image, const float *sigmas, const float *rgbs, const float *ambient,
+                                                  const float *uncertainty, const float *deltas, const int32_t *rays, const float *weights_sum,
+                                                  const float *ambient_sum, const float *uncertainty_sum, const float *image, uint32_t M, uint32_t N,
+                                                  float T_thresh, float *grad_sigmas, float *grad_rgbs, float *grad_ambient, float *grad_uncertainty, void *stream) {
+    (void)ambient; (void)ambient_sum;
+    return launch_train_bwd<1, 1, true>("composite_rays_train_uncertainty_backward", grad_weights_sum, grad_ambient_sum, nullptr, grad_uncertainty_sum, grad_image,
+                                        sigmas, rgbs, nullptr, uncertainty, deltas, rays, weights_sum, nullptr, uncertainty_sum, image, M, N, T_thresh,
+                                        grad_sigmas, grad_rgbs, grad_ambient, nullptr, grad_uncertainty, stream);
+}
+int b2n_composite_rays_train_triplane_forward(const float *sigmas, const float *rgbs, const float *amb_aud, const float *amb_eye, const float *uncertainty,
+                                              const float *deltas, const int32_t *rays, uint32_t M, uint32_t N, float T_thresh, float *weights_sum,
+                                              float *amb_aud_sum, float *amb_eye_sum, float *uncertainty_sum, float *depth, float *image, void *stream) {
+    return launch_train_fwd<1, 2, true>("composite_rays_train_triplane_forward", sigmas, rgbs, amb_aud, amb_eye, uncertainty, deltas, rays, M, N, T_thresh,
+                                        weights_sum, amb_aud_sum, amb_eye_sum, uncertainty_sum, depth, image, stream);
+}
+int b2n_composite_rays_train_triplane_backward(const float *grad_weights_sum, const float *grad_amb_aud_sum, const float *grad_amb_eye_sum,
+                                               const float *grad_uncertainty_sum, const float *grad_image, const float *sigmas, const float *rgbs,
+                                               const float *amb_aud, const float *amb_eye, const float *uncertainty, const float *deltas,
+                                               const int32_t *rays, const float *weights_sum, const float *amb_aud_sum, const float *amb_eye_sum,
+                                               const float *uncertainty_sum, const float *image, uint32_t M, uint32_t N, float T_thresh,
+                                               float *grad_sigmas, float *grad_rgbs, float *grad_amb_aud, float *grad_amb_eye, float *grad_uncertainty, void *stream) {
+    (void)amb_aud; (void)amb_eye; (void)amb_aud_sum; (void)amb_eye_sum;
+    return launch_train_bwd<1, 2, true>("composite_rays_train_triplane_backward", grad_weights_sum, grad_amb_aud_sum, grad_amb_eye_sum, grad_uncertainty_sum,
+                                        grad_image, sigmas, rgbs, nullptr, uncertainty, deltas, rays, weights_sum, nullptr, uncertainty_sum, image, M, N,
+                                        T_thresh, grad_sigmas, grad_rgbs, grad_amb_aud, grad_amb_eye, grad_uncertainty, stream);
+}
+
+int b2n_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t, const float *sigmas, const float *rgbs,
+                       const float *deltas, float *weights_sum, float *depth, float *image, void *stream) {
+    return launch_infer<0, 0, false>("composite_rays", n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, nullptr, nullptr, nullptr,
+                                     weights_sum, depth, image, nullptr, nullptr, nullptr, stream);
+}
+int b2n_composite_rays_ambient(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t, const float *sigmas, const float *rgbs,
+                               const float *deltas, const float *ambients, float *weights_sum, float *depth, float *image, float *ambient_sum, void *stream) {
+    return launch_infer<1, 1, false>("composite_rays_ambient", n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, ambients, nullptr, nullptr,
+                                     weights_sum, depth, image, ambient_sum, nullptr, nullptr, stream);
+}
+int b2n_composite_rays_ambient_sigma(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t, const float *sigmas,
+                                     const float *rgbs, const float *deltas, const float *ambients, float *weights_sum, float *depth, float *image,
+                                     float *ambient_sum, void *stream) {
+    return launch_infer<2, 1, false>("composite_rays_ambient_sigma", n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, ambients, nullptr, nullptr,
+                                     weights_sum, depth, image, ambient_sum, nullptr, nullptr, stream);
+}
+int b2n_composite_rays_uncertainty(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t, const float *sigmas,
+                                   const float *rgbs, const float *deltas, const float *ambients, const float *uncertainties, float *weights_sum,
+                                   float *depth, float *image, float *ambient_sum, float *uncertainty_sum, void *stream) {
+    return launch_infer<1, 1, true>("composite_rays_uncertainty", n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, ambients, nullptr,
+                                    uncertainties, weights_sum, depth, image, ambient_sum, nullptr, uncertainty_sum, stream);
+}
+int b2n_composite_rays_triplane(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t, const float *sigmas,
+                                const float *rgbs, const float *deltas, const float *ambs_aud, const float *ambs_eye, const float *uncertainties,
+                                float *weights_sum, float *depth, float *image, float *amb_aud_sum, float *amb_eye_sum, float *uncertainty_sum, void *stream) {
+    return launch_infer<1, 2, true>("composite_rays_triplane", n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, ambs_aud, ambs_eye,
+                                    uncertainties, weights_sum, depth, image, amb_aud_sum, amb_eye_sum, uncertainty_sum, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// dda.cuh — the occupancy-bitfield DDA shared by the training marcher, the inference marcher and the fused
+// frame kernel.  One probe = one iteration of the reference's while-loop body (raymarching.cu:400-441 /
+// :466-517 / :875-928).  Rounding is explicit so the result does not depend on compiler contraction:
+// the FMA placements are those of the reference's sm_100a SASS.
+#pragma once
+#include "common.cuh"
+
+namespace b2n {
+
+struct DdaSample { float x, y, z, dt; };
+
+// raymarching.cu:108-144
+__device__ __forceinline__ void near_far_one(float ox, float oy, float oz, float rdx, float rdy, float rdz,
+                                             float a0, float a1, float a2, float a3, float a4, float a5,
+                                             float min_near, float &tn, float &tf) {
+    const float FMAX = 3.402823466e+38f;
+    float n0 = __fmul_rn(__fsub_rn(a0, ox), rdx), f0 = __fmul_rn(__fsub_rn(a3, ox), rdx), s;
+    if (n0 > f0) { s = n0; n0 = f0; f0 = s; }
+    float n1 = __fmul_rn(__fsub_rn(a1, oy), rdy), f1 = __fmul_rn(__fsub_rn(a4, oy), rdy);
+    if (n1 > f1) { s = n1; n1 = f1; f1 = s; }
+    if (n0 > f1 || n1 > f0) { tn = tf = FMAX; return; }
+    if (n1 > n0) n0 = n1;
+    if (f1 < f0) f0 = f1;
+    float n2 = __fmul_rn(__fsub_rn(a2, oz), rdz), f2 = __fmul_rn(__fsub_rn(a5, oz), rdz);
+    if (n2 > f2) { s = n2; n2 = f2; f2 = s; }
+    if (n0 > f2 || n2 > f0) { tn = tf = FMAX; return; }
+    if (n2 > n0) n0 = n2;
+    if (f2 < f0) f0 = f2;
+    if (n0 < min_near) n0 = min_near;
+    tn = n0; tf = f0;
+}
+
+struct DdaRay {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+    float sx, sy, sz;                 // 0.5 * sign(d)
+    float bound, dt_gamma, dt_min, dt_max, rH, Hf, Hm1f, H3f, ncas_m1, far;
+    uint32_t C;
+
+    __device__ __forceinline__ void init(const float *o, const float *d, float bound_, float dt_gamma_, uint32_t max_steps,
+                                         uint32_t C_, uint32_t H, float far_) {
+        ox = o[0]; oy = o[1]; oz = o[2];
+        dx = d[0]; dy = d[1]; dz = d[2];
+        init_common(bound_, dt_gamma_, max_steps, C_, H, far_);
+    }
+    __device__ __forceinline__ void init_common(float bound_, float dt_gamma_, uint32_t max_steps, uint32_t C_, uint32_t H, float far_) {
+        rdx = 1.0f / dx; rdy = 1.0f / dy; rdz = 1.0f / dz;            // IEEE division (raymarching.cu:378)
+        sx = copysignf(0.5f, dx); sy = copysignf(0.5f, dy); sz = copysignf(0.5f, dz);
+        bound = bound_; dt_gamma = dt_gamma_; C = C_; far = far_;
+        Hf = (float)H; Hm1f = (float)(H - 1); rH = 1.0f / Hf;
+        H3f = (float)(H * H * H);                                      // `const float H3 = H*H*H` (:380)
+        ncas_m1 = __fsub_rn((float)C_, 1.0f);
+        dt_max = __fmul_rn(3.4641015529632568359f, (float)(1 << (C_ - 1))) / Hf;   // 2*SQRT3*(1<<(C-1))/H (:386)
+        dt_min = fminf(dt_max, 3.4641015529632568359f / (float)max_steps);         // (:387)
+    }
+    __device__ __forceinline__ float step_of(float t) const { return clampf(__fmul_rn(t, dt_gamma), dt_min, dt_max); }
+    // t0 += clamp(t0*dt_gamma, dt_min, dt_max) * noise   (:392 / :873)
+    __device__ __forceinline__ float perturb(float t0, float noise) const { return __fmaf_rn(step_of(t0), noise, t0); }
+
+    // mip level of a point / of a step size (raymarching.cu:42-54).  With one cascade the level is 0.
+    __device__ __forceinline__ int level_of(float x, float y, float z, float dt) const {
+        if (C == 1) return 0;
+        int e1, e2;
+        (void)frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e1);
+        (void)frexpf(__fmul_rn(0.5f, __fmul_rn(dt, Hf)), &e2);
+        const int l1 = (int)fminf(ncas_m1, fmaxf(0.0f, (float)e1));
+        const int l2 = (int)fminf(ncas_m1, fmaxf(0.0f, (float)e2));
+        return l1 > l2 ? l1 : l2;
+    }
+
+    // One loop iteration at parameter t.  Occupied: fills s, returns true (caller advances t by s.dt).
+    // Empty: advances t past the voxel exit with the reference's do-while and returns false.
+    __device__ __forceinline__ bool probe(const uint8_t *__restrict__ grid, float &t, DdaSample &s) const {
+        const float x = clampf(__fmaf_rn(t, dx, ox), -bound, bound);
+        const float y = clampf(__fmaf_rn(t, dy, oy), -bound, bound);
+        const float z = clampf(__fmaf_rn(t, dz, oz), -bound, bound);
+        const float dt = step_of(t);
+        const int level = level_of(x, y, z, dt);
+        const float mip_bound = fminf(__int_as_float((127 + level) << 23), bound);     // scalbnf(1, level)
+        const float mip_rbound = 1.0f / mip_bound;
+        // 0.5 * (x * mip_rbound + 1) * H — exact in the reference's double, so one fp32 rounding here
+        const float fx = clampf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(x, mip_rbound, 1.0f)), Hf), 0.0f, Hm1f);
+        const float fy = clampf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(y, mip_rbound, 1.0f)), Hf), 0.0f, Hm1f);
+        const float fz = clampf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(z, mip_rbound, 1.0f)), Hf), 0.0f, Hm1f);
+        const int nx = (int)fx, ny = (int)fy, nz = (int)fz;
+        const uint32_t index = (uint32_t)__fmaf_rn((float)level, H3f, (float)morton_enc((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
+        const uint32_t occ = (__ldg(grid + (index >> 3)) >> (index & 7)) & 1u;
+        if (occ) { s.x = x; s.y = y; s.z = z; s.dt = dt; return true; }
+        // distance to the voxel exit (:431-435)
+        const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), sx), rH), 2.0f, -1.0f), mip_bound, -x), rdx);
+        const float ty = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)ny, 0.5f), sy), rH), 2.0f, -1.0f), mip_bound, -y), rdy);
+        const float tz = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nz, 0.5f), sz), rH), 2.0f, -1.0f), mip_bound, -z), rdz);
+        const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+        do { t = __fadd_rn(t, step_of(t)); } while (t < tt);
+        return false;
+    }
+};
+
+}  // namespace b2n

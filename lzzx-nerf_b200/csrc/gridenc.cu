@@ -1,0 +1,377 @@
+// gridenc.cu — multiresolution hash / tiled grid encoder (forward, table-gradient scatter, input gradient).
+//
+// Semantics: gridencoder/src/gridencoder.cu:35-342 (index function :54-72, interpolation :124-175, input
+// derivative :179-222, table backward :264-312, input backward :317-342).  The per-level scale uses the same
+// ex2.approx + fma as the reference (`exp2f(level*S)*H - 1`), corners are accumulated in the reference's
+// order with one fma each, so fp32 outputs are bit-identical on the same GPU.
+//
+// B200 organisation:
+//   * D == 2 (the tri-plane and torso grids): the two x-neighbours of a cell are adjacent in memory for dense
+//     levels, and for hashed levels too because the first hash prime is 1 and table sizes are powers of two
+//     (idx(x+1,y) == idx(x,y) ^ 1 when x is even).  The kernel detects `i1 == (i0 ^ 1)` and fetches the
+//     aligned pair with ONE vector load (8 B fp32 / 4 B fp16 at C=1), i.e. <=3 loads instead of 4 per level.
+//   * tables (<= 2 MB for the head model) stay L2/L1 resident: table loads use the read-only path with default
+//     caching, the streamed inputs/outputs use evict-first (__ldcs/__stcs) so they do not displace the tables.
+//   * backward: the same pair detection turns two scalar REDs into one `red.global.add.v2.f32` (sm_90+ vector
+//     reduction) — the scatter is bound by the SM's RED issue rate, so halving the instruction count is the lever.
+#include "common.cuh"
+
+namespace b2n {
+
+__constant__ uint32_t c_primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
+
+template <uint32_t D>
+__device__ __forceinline__ uint32_t grid_slot(uint32_t gridtype, bool align_corners, uint32_t hashmap_size, uint32_t resolution, const uint32_t (&pg)[D]) {
+    uint32_t stride = 1, index = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        if (stride <= hashmap_size) {
+            index += pg[d] * stride;
+            stride *= align_corners ? resolution : (resolution + 1);
+        }
+    }
+    if (gridtype == 0 && stride > hashmap_size) {
+        index = 0;
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) index ^= pg[d] * c_primes[d];
+    }
+    return index % hashmap_size;
+}
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+// acc += w * val with the reference's rounding: fp32 = one fma; fp16 (scalar_t = at::Half) = the product is
+// narrowed to half, added in float, narrowed again (c10::Half operator+= semantics)
+template <typename T> __device__ __forceinline__ void acc_corner(float &acc, float w, float val);
+template <> __device__ __forceinline__ void acc_corner<float>(float &acc, float w, float val) { acc = __fmaf_rn(w, val, acc); }
+template <> __device__ __forceinline__ void acc_corner<__half>(float &acc, float w, float val) {
+    const float p = __half2float(__float2half_rn(__fmul_rn(w, val)));
+    acc = __half2float(__float2half_rn(__fadd_rn(acc, p)));
+}
+
+struct LevelGeom { float scale; uint32_t resolution, hashmap_size, table_off; };
+__device__ __forceinline__ LevelGeom level_geom(const int32_t *__restrict__ offsets, uint32_t level, float S, uint32_t H) {
+    LevelGeom g;
+    g.table_off = (uint32_t)offsets[level];
+    g.hashmap_size = (uint32_t)offsets[level + 1] - g.table_off;
+    g.scale = __fmaf_rn(exp2f(__fmul_rn((float)level, S)), (float)H, -1.0f);     // gridencoder.cu:125
+    g.resolution = (uint32_t)ceilf(g.scale) + 1u;                               // :126
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward — one thread per (sample, level); outputs [L,B,C]
+// ---------------------------------------------------------------------------------------------------
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256) k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ table, const int32_t *__restrict__ offsets,
+                                                   T *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, T *__restrict__ dy_dx,
+                                                   uint32_t gridtype, bool align_corners) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    const LevelGeom g = level_geom(offsets, level, S, H);
+    const T *tab = table + (size_t)g.table_off * C;
+    T *out = outputs + ((size_t)level * B + b) * C;
+
+    float in[D];
+    bool oob = false;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) { in[d] = __ldcs(inputs + (size_t)b * D + d); oob |= (in[d] < 0.0f || in[d] > 1.0f); }
+    if (oob) {                                                                   // gridencoder.cu:98-122
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) out[c] = from_f<T>(0.0f);
+        if (dy_dx) {
+            T *dd = dy_dx + (size_t)b * D * L * C + (size_t)level * D * C;
+#pragma unroll
+            for (uint32_t k = 0; k < D * C; k++) dd[k] = from_f<T>(0.0f);
+        }
+        return;
+    }
+    float pos[D];
+    uint32_t pg[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        pos[d] = __fmaf_rn(in[d], g.scale, align_corners ? 0.0f : 0.5f);
+        const float fl = floorf(pos[d]);
+        pg[d] = (uint32_t)fl;
+        pos[d] = __fsub_rn(pos[d], (float)pg[d]);
+    }
+    float res[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) res[c] = 0.0f;
+
+    if constexpr (D == 2 && C == 1) {
+        // paired-corner fast path: corners (0,1) and (2,3) differ only in x
+        const float wx0 = __fsub_rn(1.0f, pos[0]), wx1 = pos[0];
+#pragma unroll
+        for (uint32_t j = 0; j < 2; j++) {
+            const float wy = j ? pos[1] : __fsub_rn(1.0f, pos[1]);
+            const uint32_t p0[2] = {pg[0], pg[1] + j}, p1[2] = {pg[0] + 1, pg[1] + j};
+            const uint32_t i0 = grid_slot<D>(gridtype, align_corners, g.hashmap_size, g.resolution, p0);
+            const uint32_t i1 = grid_slot<D>(gridtype, align_corners, g.hashmap_size, g.resolution, p1);
+            float v0, v1;
+            if (i1 == (i0 ^ 1u) && !(g.table_off & 1u)) {
+                // aligned pair (table offsets are multiples of 8 entries, grid.py:117)
+                if (sizeof(T) == 4) {
+                    const float2 pr = __ldg(reinterpret_cast<const float2 *>(tab) + (i0 >> 1));
+                    v0 = (i0 & 1u) ? pr.y : pr.x; v1 = (i0 & 1u) ? pr.x : pr.y;
+                } else {
+                    const __half2 pr = __ldg(reinterpret_cast<const __half2 *>(tab) + (i0 >> 1));
+                    v0 = __half2float((i0 & 1u) ? pr.y : pr.x); v1 = __half2float((i0 & 1u) ? pr.x : pr.y);
+                }
+            } else {
+                v0 = to_f<T>(__ldg(tab + i0)); v1 = to_f<T>(__ldg(tab + i1));
+            }
+            acc_corner<T>(res[0], __fmul_rn(wx0, wy), v0);
+            acc_corner<T>(res[0], __fmul_rn(wx1, wy), v1);
+        }
+    } else {
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); idx++) {
+            float w = 1.0f;
+            uint32_t pl[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; d++) {
+                if ((idx & (1u << d)) == 0) { w = __fmul_rn(w, __fsub_rn(1.0f, pos[d])); pl[d] = pg[d]; }
+                else                        { w = __fmul_rn(w, pos[d]);                 pl[d] = pg[d] + 1; }
+            }
+            const size_t e = (size_t)grid_slot<D>(gridtype, align_corners, g.hashmap_size, g.resolution, pl) * C;
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) acc_corner<T>(res[c], w, to_f<T>(__ldg(tab + e + c)));
+        }
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) out[c] = from_f<T>(res[c]);
+
+    if (!dy_dx) return;
+    T *dd = dy_dx + (size_t)b * D * L * C + (size_t)level * D * C;               // [B, L, D, C]  (:181)
+#pragma unroll
+    for (uint32_t gd = 0; gd < D; gd++) {
+        float rg[C];
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) rg[c] = 0.0f;
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << (D - 1)); idx++) {
+            float w = g.scale;
+            uint32_t pl[D];
+#pragma unroll
+            for (uint32_t nd = 0; nd + 1 < D; nd++) {
+                const uint32_t d = (nd >= gd) ? nd + 1 : nd;
+                if ((idx & (1u << nd)) == 0) { w = __fmul_rn(w, __fsub_rn(1.0f, pos[d])); pl[d] = pg[d]; }
+                else                         { w = __fmul_rn(w, pos[d]);                 pl[d] = pg[d] + 1; }
+            }
+            pl[gd] = pg[gd];
+            const size_t el = (size_t)grid_slot<D>(gridtype, align_corners, g.hashmap_size, g.resolution, pl) * C;
+            pl[gd] = pg[gd] + 1;
+            const size_t er = (size_t)grid_slot<D>(gridtype, align_corners, g.hashmap_size, g.resolution, pl) * C;
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) {
+                // Half - Half narrows to half in the reference (scalar_t arithmetic)
+                const float diff = to_f<T>(from_f<T>(__fsub_rn(to_f<T>(__ldg(tab + er + c)), to_f<T>(__ldg(tab + el + c)))));
+                acc_corner<T>(rg[c], w, diff);
+            }
+        }
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) dd[gd * C + c] = from_f<T>(rg[c]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward: table gradient scatter — one thread per (sample, level); grad [L,B,C]
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_f32(float *addr, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add_v2_f32(float *addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_h2(__half *addr, __half2 v) {
+    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(addr), "r"(*reinterpret_cast<uint32_t *>(&v)) : "memory");
+}
+
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256) k_grid_bwd(const T *__restrict__ grad, const float *__restrict__ inputs, const int32_t *__restrict__ offsets,
+                                                   T *__restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H,
+                                                   uint32_t gridtype, bool align_corners) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    const LevelGeom g = level_geom(offsets, level, S, H);
+    T *gtab = grad_table + (size_t)g.table_off * C;
+
+    float in[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) { in[d] = __ldcs(inputs + (size_t)b * D + d); if (in[d] < 0.0f || in[d] > 1.0f) return; }
+    float pos[D];
+    uint32_t pg[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        pos[d] = __fmaf_rn(in[d], g.scale, align_corners ? 0.0f : 0.5f);
+        pg[d] = (uint32_t)floorf(pos[d]);
+        pos[d] = __fsub_rn(pos[d], (float)pg[d]);
+    }
+    float gc[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) gc[c] = to_f<T>(grad[((size_t)level * B + b) * C + c]);
+
+    if constexpr (D == 2 && C == 1 && sizeof(T) == 4) {
+        const float wx0 = __fsub_rn(1.0f, pos[0]), wx1 = pos[0];
+#pragma unroll
+        for (uint32_t j = 0; j < 2; j++) {
+            const float wy = j ? pos[1] : __fsub_rn(1.0f, pos[1]);
+            const uint32_t p0[2] = {pg[0], pg[1] + j}, p1[2] = {pg[0] + 1, pg[1] + j};
+            const uint32_t i0 = grid_slot<D>(gridtype, align_corners, g.hashmap_size, g.resolution, p0);
+            const uint32_t i1 = grid_slot<D>(gridtype, align_corners, g.hashmap_size, g.resolution, p1);
+            const float g0 = __fmul_rn(__fmul_rn(wx0, wy), gc[0]), g1 = __fmul_rn(__fmul_rn(wx1, wy), gc[0]);
+            float *base = reinterpret_cast<float *>(gtab);
+            if (i1 == (i0 ^ 1u) && !(g.table_off & 1u)) {
+                if (i0 & 1u) red_add_v2_f32(base + i1, g1, g0); else red_add_v2_f32(base + i0, g0, g1);
+            } else {
+                red_add_f32(base + i0, g0); red_add_f32(base + i1, g1);
+            }
+        }
+    } else {
+#pragma unroll
+    for (uint32_t idx = 0; idx < (1u << D); idx++) {
+        float w = 1.0f;
+        uint32_t pl[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) {
+            if ((idx & (1u << d)) == 0) { w = __fmul_rn(w, __fsub_rn(1.0f, pos[d])); pl[d] = pg[d]; }
+            else                        { w = __fmul_rn(w, pos[d]);                 pl[d] = pg[d] + 1; }
+        }
+        const size_t e = (size_t)grid_slot<D>(gridtype, align_corners, g.hashmap_size, g.resolution, pl) * C;
+        if (sizeof(T) == 4) {
+            float *base = reinterpret_cast<float *>(gtab) + e;
+            if (C >= 2) {
+#pragma unroll
+                for (uint32_t c = 0; c < C; c += 2) red_add_v2_f32(base + c, __fmul_rn(w, gc[c]), __fmul_rn(w, gc[c + 1 < C ? c + 1 : c]));
+            } else {
+                red_add_f32(base, __fmul_rn(w, gc[0]));
+            }
+        } else {
+            __half *base = reinterpret_cast<__half *>(gtab) + e;     // C even (checked on the host): packed half2 reductions (:298-304)
+#pragma unroll
+            for (uint32_t c = 0; c + 1 < C; c += 2)
+                red_add_h2(base + c, __halves2half2(__float2half_rn(__fmul_rn(w, gc[c])), __float2half_rn(__fmul_rn(w, gc[c + 1]))));
+        }
+    }
+    }
+}
+
+// input gradient: grad_inputs[b,d] = sum_l sum_c grad[l,b,c] * dy_dx[b,l,d,c]   (:317-342)
+template <typename T>
+__global__ void __launch_bounds__(256) k_grid_input_bwd(const T *__restrict__ grad, const T *__restrict__ dy_dx, T *__restrict__ grad_inputs,
+                                                         uint32_t B, uint32_t D, uint32_t C, uint32_t L) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * D) return;
+    const uint32_t b = t / D, d = t - b * D;
+    const T *dd = dy_dx + (size_t)b * L * D * C;
+    float r = 0.0f;
+    for (uint32_t l = 0; l < L; l++)
+        for (uint32_t c = 0; c < C; c++)
+            acc_corner<T>(r, to_f<T>(grad[((size_t)l * B + b) * C + c]), to_f<T>(dd[(size_t)l * D * C + d * C + c]));
+    grad_inputs[t] = from_f<T>(r);
+}
+
+template <typename T, uint32_t D>
+static int fwd_dispatch_c(const float *inputs, const T *table, const int32_t *offsets, T *outputs, uint32_t B, uint32_t C, uint32_t L, float S, uint32_t H,
+                          T *dy_dx, uint32_t gridtype, bool ac, cudaStream_t st) {
+    const dim3 grid(ceil_div<uint32_t>(B, 256), L, 1);
+    switch (C) {
+        case 1: k_grid_fwd<T, D, 1><<<grid, 256, 0, st>>>(inputs, table, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac); break;
+        case 2: k_grid_fwd<T, D, 2><<<grid, 256, 0, st>>>(inputs, table, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac); break;
+        case 4: k_grid_fwd<T, D, 4><<<grid, 256, 0, st>>>(inputs, table, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac); break;
+        case 8: k_grid_fwd<T, D, 8><<<grid, 256, 0, st>>>(inputs, table, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac); break;
+        default: set_error("GridEncoding: C must be 1, 2, 4, or 8."); return 2;
+    }
+    return check_launch("grid_encode_forward");
+}
+template <typename T>
+static int fwd_dispatch(const float *inputs, const T *table, const int32_t *offsets, T *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                        uint32_t H, T *dy_dx, uint32_t gridtype, bool ac, cudaStream_t st) {
+    switch (D) {
+        case 1: return fwd_dispatch_c<T, 1>(inputs, table, offsets, outputs, B, C, L, S, H, dy_dx, gridtype, ac, st);
+        case 2: return fwd_dispatch_c<T, 2>(inputs, table, offsets, outputs, B, C, L, S, H, dy_dx, gridtype, ac, st);
+        case 3: return fwd_dispatch_c<T, 3>(inputs, table, offsets, outputs, B, C, L, S, H, dy_dx, gridtype, ac, st);
+        case 4: return fwd_dispatch_c<T, 4>(inputs, table, offsets, outputs, B, C, L, S, H, dy_dx, gridtype, ac, st);
+        case 5: return fwd_dispatch_c<T, 5>(inputs, table, offsets, outputs, B, C, L, S, H, dy_dx, gridtype, ac, st);
+        default: set_error("GridEncoding: D must be 1, 2, 3, 4, or 5"); return 2;
+    }
+}
+template <typename T, uint32_t D>
+static int bwd_dispatch_c(const T *grad, const float *inputs, const int32_t *offsets, T *gtab, uint32_t B, uint32_t C, uint32_t L, float S, uint32_t H,
+                          uint32_t gridtype, bool ac, cudaStream_t st) {
+    const dim3 grid(ceil_div<uint32_t>(B, 256), L, 1);
+    switch (C) {
+        case 1: k_grid_bwd<T, D, 1><<<grid, 256, 0, st>>>(grad, inputs, offsets, gtab, B, L, S, H, gridtype, ac); break;
+        case 2: k_grid_bwd<T, D, 2><<<grid, 256, 0, st>>>(grad, inputs, offsets, gtab, B, L, S, H, gridtype, ac); break;
+        case 4: k_grid_bwd<T, D, 4><<<grid, 256, 0, st>>>(grad, inputs, offsets, gtab, B, L, S, H, gridtype, ac); break;
+        case 8: k_grid_bwd<T, D, 8><<<grid, 256, 0, st>>>(grad, inputs, offsets, gtab, B, L, S, H, gridtype, ac); break;
+        default: set_error("GridEncoding: C must be 1, 2, 4, or 8."); return 2;
+    }
+    return check_launch("grid_encode_backward");
+}
+template <typename T>
+static int bwd_dispatch(const T *grad, const float *inputs, const int32_t *offsets, T *gtab, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                        uint32_t H, uint32_t gridtype, bool ac, cudaStream_t st) {
+    switch (D) {
+        case 1: return bwd_dispatch_c<T, 1>(grad, inputs, offsets, gtab, B, C, L, S, H, gridtype, ac, st);
+        case 2: return bwd_dispatch_c<T, 2>(grad, inputs, offsets, gtab, B, C, L, S, H, gridtype, ac, st);
+        case 3: return bwd_dispatch_c<T, 3>(grad, inputs, offsets, gtab, B, C, L, S, H, gridtype, ac, st);
+        case 4: return bwd_dispatch_c<T, 4>(grad, inputs, offsets, gtab, B, C, L, S, H, gridtype, ac, st);
+        case 5: return bwd_dispatch_c<T, 5>(grad, inputs, offsets, gtab, B, C, L, S, H, gridtype, ac, st);
+        default: set_error("GridEncoding: D must be 1, 2, 3, 4, or 5"); return 2;
+    }
+}
+
+}  // namespace b2n
+
+using namespace b2n;
+
+extern "C" {
+
+int b2n_grid_encode_forward(const float *inputs, const void *embeddings, const int32_t *offsets, void *outputs, uint32_t B, uint32_t D, uint32_t C,
+                            uint32_t L, float S, uint32_t H, void *dy_dx, uint32_t gridtype, int align_corners, b2n_dtype dtype, void *stream) {
+    B2N_REQUIRE(inputs && embeddings && offsets && outputs, "grid_encode_forward: null pointer");
+    B2N_REQUIRE(gridtype <= 1, "grid_encode_forward: gridtype must be 0 (hash) or 1 (tiled)");
+    B2N_REQUIRE(L >= 1 && L <= 65535, "grid_encode_forward: L=%u out of range", L);
+    if (B == 0) return 0;
+    if (dtype == B2N_F32)
+        return fwd_dispatch<float>(inputs, (const float *)embeddings, offsets, (float *)outputs, B, D, C, L, S, H, (float *)dy_dx, gridtype, align_corners != 0, as_stream(stream));
+    if (dtype == B2N_F16)
+        return fwd_dispatch<__half>(inputs, (const __half *)embeddings, offsets, (__half *)outputs, B, D, C, L, S, H, (__half *)dy_dx, gridtype, align_corners != 0, as_stream(stream));
+    set_error("grid_encode_forward: embeddings must be float32 or float16");
+    return 2;
+}
+
+int b2n_grid_encode_backward(const void *grad, const float *inputs, const void *embeddings, const int32_t *offsets, void *grad_embeddings, uint32_t B,
+                             uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, const void *dy_dx, void *grad_inputs, uint32_t gridtype,
+                             int align_corners, b2n_dtype dtype, void *stream) {
+    (void)embeddings;
+    B2N_REQUIRE(grad && inputs && offsets && grad_embeddings, "grid_encode_backward: null pointer");
+    B2N_REQUIRE(gridtype <= 1, "grid_encode_backward: gridtype must be 0 (hash) or 1 (tiled)");
+    B2N_REQUIRE(L >= 1 && L <= 65535, "grid_encode_backward: L=%u out of range", L);
+    B2N_REQUIRE(!(dtype == B2N_F16 && (C & 1)), "grid_encode_backward: float16 tables need an even C (the reference never runs C=1 in half, grid.py:38)");
+    if (B == 0) return 0;
+    int rc;
+    if (dtype == B2N_F32)
+        rc = bwd_dispatch<float>((const float *)grad, inputs, offsets, (float *)grad_embeddings, B, D, C, L, S, H, gridtype, align_corners != 0, as_stream(stream));
+    else if (dtype == B2N_F16)
+        rc = bwd_dispatch<__half>((const __half *)grad, inputs, offsets, (__half *)grad_embeddings, B, D, C, L, S, H, gridtype, align_corners != 0, as_stream(stream));
+    else { set_error("grid_encode_backward: grad must be float32 or float16"); return 2; }
+    if (rc) return rc;
+    if (dy_dx && grad_inputs) {
+        if (dtype == B2N_F32)
+            k_grid_input_bwd<float><<<ceil_div<uint32_t>(B * D, 256), 256, 0, as_stream(stream)>>>((const float *)grad, (const float *)dy_dx, (float *)grad_inputs, B, D, C, L);
+        else
+            k_grid_input_bwd<__half><<<ceil_div<uint32_t>(B * D, 256), 256, 0, as_stream(stream)>>>((const __half *)grad, (const __half *)dy_dx, (__half *)grad_inputs, B, D, C, L);
+        return check_launch("grid_encode_backward(inputs)");
+    }
+    return 0;
+}
+
+}  // extern "C"

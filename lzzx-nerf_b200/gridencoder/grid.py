@@ -1,0 +1,104 @@
+"""Drop-in `gridencoder`: multiresolution hash / tiled grid encoder module (reference: gridencoder/grid.py).
+
+State-dict compatible with the reference: parameter `embeddings [sum(params_in_level), level_dim]`, buffer
+`offsets int32 [num_levels + 1]`, same level sizing (grid.py:111-123) and init range (grid.py:132-134), so a
+reference checkpoint loads unchanged.  The autograd Function keeps the reference's positional signature
+(grid.py:22) and AMP rule (tables run in half only under autocast AND for an even level_dim, grid.py:36-39).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+from torch.amp import custom_bwd, custom_fwd
+
+from .backend import _backend
+
+_gridtype_to_id = {"hash": 0, "tiled": 1}
+
+
+def level_table(input_dim, num_levels, per_level_scale, base_resolution, log2_hashmap_size, align_corners):
+    """Entries per level and their running offsets (grid.py:111-123): dense `(res[+1])^D` capped at 2^log2_hashmap_size,
+    rounded up to a multiple of 8."""
+    cap = 2 ** log2_hashmap_size
+    offsets = [0]
+    for lvl in range(num_levels):
+        res = int(np.ceil(base_resolution * per_level_scale ** lvl))
+        side = res if align_corners else res + 1
+        entries = min(cap, side ** input_dim)
+        offsets.append(offsets[-1] + int(np.ceil(entries / 8) * 8))
+    return offsets
+
+
+class _grid_encode(Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0, align_corners=False):
+        # inputs [B,D] in [0,1] (kept fp32 for precision), embeddings [sO,C], offsets [L+1] -> [B, L*C]
+        inputs = inputs.float().contiguous()
+        B, D = inputs.shape
+        L, C = offsets.shape[0] - 1, embeddings.shape[1]
+        S, H = np.log2(per_level_scale), base_resolution
+        if torch.is_autocast_enabled("cuda") and C % 2 == 0:
+            embeddings = embeddings.to(torch.half)
+        level_major = torch.empty(L, B, C, device=inputs.device, dtype=embeddings.dtype)
+        dy_dx = torch.empty(B, L * D * C, device=inputs.device, dtype=embeddings.dtype) if calc_grad_inputs else None
+        _backend.grid_encode_forward(inputs, embeddings.contiguous(), offsets, level_major, B, D, C, L, S, H, dy_dx, gridtype, align_corners)
+        ctx.save_for_backward(inputs, embeddings, offsets, dy_dx)
+        ctx.geom = (B, D, C, L, S, H, gridtype, align_corners)
+        return level_major.permute(1, 0, 2).reshape(B, L * C)
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, grad):
+        inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
+        B, D, C, L, S, H, gridtype, align_corners = ctx.geom
+        grad = grad.view(B, L, C).permute(1, 0, 2).contiguous()          # [L,B,C], the kernel's layout
+        if grad.dtype != embeddings.dtype:
+            grad = grad.to(embeddings.dtype)
+        grad_embeddings = torch.zeros_like(embeddings)
+        grad_inputs = torch.zeros_like(inputs, dtype=embeddings.dtype) if dy_dx is not None else None
+        _backend.grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H, dy_dx, grad_inputs, gridtype, align_corners)
+        if grad_inputs is not None:
+            grad_inputs = grad_inputs.to(inputs.dtype)
+        return grad_inputs, grad_embeddings, None, None, None, None, None, None
+
+
+grid_encode = _grid_encode.apply
+
+
+class GridEncoder(nn.Module):
+    def __init__(self, input_dim=3, num_levels=16, level_dim=2, per_level_scale=2, base_resolution=16, log2_hashmap_size=19,
+                 desired_resolution=None, gridtype="hash", align_corners=False):
+        super().__init__()
+        if desired_resolution is not None:        # overrides per_level_scale (grid.py:95-96)
+            per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1))
+        self.input_dim, self.num_levels, self.level_dim = input_dim, num_levels, level_dim
+        self.per_level_scale, self.log2_hashmap_size, self.base_resolution = per_level_scale, log2_hashmap_size, base_resolution
+        self.output_dim = num_levels * level_dim
+        self.gridtype, self.gridtype_id, self.align_corners = gridtype, _gridtype_to_id[gridtype], align_corners
+        self.max_params = 2 ** log2_hashmap_size
+        offs = level_table(input_dim, num_levels, per_level_scale, base_resolution, log2_hashmap_size, align_corners)
+        self.register_buffer("offsets", torch.from_numpy(np.array(offs, dtype=np.int32)))
+        self.n_params = offs[-1] * level_dim
+        self.embeddings = nn.Parameter(torch.empty(offs[-1], level_dim))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.embeddings.data.uniform_(-1e-4, 1e-4)
+
+    def __repr__(self):
+        top = int(round(self.base_resolution * self.per_level_scale ** (self.num_levels - 1)))
+        return (f"GridEncoder: input_dim={self.input_dim} num_levels={self.num_levels} level_dim={self.level_dim} "
+                f"resolution={self.base_resolution} -> {top} per_level_scale={self.per_level_scale:.4f} "
+                f"params={tuple(self.embeddings.shape)} gridtype={self.gridtype} align_corners={self.align_corners}")
+
+    def forward(self, inputs, bound=1):
+        # inputs [..., input_dim] in [-bound, bound] -> [..., num_levels * level_dim]
+        unit = (inputs + bound) / (2 * bound)
+        lead = list(unit.shape[:-1])
+        flat = unit.view(-1, self.input_dim)
+        out = grid_encode(flat, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
+                          flat.requires_grad, self.gridtype_id, self.align_corners)
+        return out.view(lead + [self.output_dim])

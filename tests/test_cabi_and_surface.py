@@ -1,0 +1,90 @@
+"""CPU: the C-ABI library loads and exports every symbol include/*.h declares (no compute calls without a GPU), and the
+drop-in packages expose the reference's operator surface (names, positional signatures, state_dict layout)."""
+import ctypes
+import inspect
+import os
+
+import pytest
+import torch
+
+from b2nerf import _lib as L
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(L.LIB_PATH), "build with __graft_entry__.build()"
+    dll = ctypes.CDLL(L.LIB_PATH)
+    protos = L.declared_symbols()
+    assert len(protos) >= 31
+    for name in protos:
+        assert hasattr(dll, name), f"{name} declared in include/*.h but not exported"
+    for must in ("b2n_march_rays_train", "b2n_composite_rays_train_triplane_backward", "b2n_composite_rays_triplane", "b2n_grid_encode_forward",
+                 "b2n_sh_encode_forward", "b2n_freq_encode_backward", "b2n_near_far_from_aabb", "b2n_packbits", "b2n_morton3D"):
+        assert must in protos
+    lib = L.lib()                      # binds argtypes from the header; raises if anything is missing
+    assert lib.raw("b2n_version")() >= 100 and lib.launch_count() == 0
+
+
+def test_header_prototypes_mirror_reference_argument_lists():
+    protos = L.declared_symbols()
+    # raymarching.h:14 march_rays_train(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises)
+    assert protos["b2n_march_rays_train"][2] == ["rays_o", "rays_d", "grid", "bound", "dt_gamma", "max_steps", "N", "C", "H", "M", "nears", "fars",
+                                                "xyzs", "dirs", "deltas", "rays", "counter", "noises", "stream"]
+    assert protos["b2n_composite_rays_triplane"][2] == ["n_alive", "n_step", "T_thresh", "rays_alive", "rays_t", "sigmas", "rgbs", "deltas", "ambs_aud",
+                                                       "ambs_eye", "uncertainties", "weights_sum", "depth", "image", "amb_aud_sum", "amb_eye_sum",
+                                                       "uncertainty_sum", "stream"]
+    assert protos["b2n_grid_encode_forward"][2][:13] == ["inputs", "embeddings", "offsets", "outputs", "B", "D", "C", "L", "S", "H", "dy_dx", "gridtype",
+                                                         "align_corners"]
+
+
+def test_dropin_operator_surface():
+    import raymarching
+    import gridencoder
+    import shencoder
+    import freqencoder
+    from encoding import get_encoder
+    names = ["near_far_from_aabb", "sph_from_ray", "morton3D", "morton3D_invert", "packbits", "morton3D_dilation", "march_rays_train", "composite_rays_train",
+             "march_rays", "composite_rays", "composite_rays_ambient", "composite_rays_train_sigma", "composite_rays_ambient_sigma",
+             "composite_rays_train_uncertainty", "composite_rays_uncertainty", "composite_rays_train_triplane", "composite_rays_triplane"]
+    for n in names:                                          # raymarching.py:48..671
+        assert callable(getattr(raymarching, n)), n
+    from raymarching.backend import _backend as rb
+    for n in ["packbits", "near_far_from_aabb", "sph_from_ray", "morton3D", "morton3D_invert", "morton3D_dilation", "march_rays_train",
+              "march_rays_train_backward", "composite_rays_train_forward", "composite_rays_train_backward", "march_rays", "composite_rays",
+              "composite_rays_ambient", "composite_rays_train_sigma_forward", "composite_rays_train_sigma_backward", "composite_rays_ambient_sigma",
+              "composite_rays_train_uncertainty_forward", "composite_rays_train_uncertainty_backward", "composite_rays_uncertainty",
+              "composite_rays_train_triplane_forward", "composite_rays_train_triplane_backward", "composite_rays_triplane"]:
+        assert callable(getattr(rb, n)), n                   # raymarching/src/bindings.cpp:5-38 (22 functions)
+    sig = inspect.signature(raymarching.raymarching._march_rays_train.forward)
+    assert list(sig.parameters)[1:] == ["rays_o", "rays_d", "bound", "density_bitfield", "C", "H", "nears", "fars", "step_counter", "mean_count",
+                                         "perturb", "align", "force_all_rays", "dt_gamma", "max_steps"]
+    assert sig.parameters["max_steps"].default == 1024 and sig.parameters["mean_count"].default == -1
+    sig = inspect.signature(raymarching.raymarching._march_rays.forward)
+    assert list(sig.parameters)[1:13] == ["n_alive", "n_step", "rays_alive", "rays_t", "rays_o", "rays_d", "bound", "density_bitfield", "C", "H", "near", "far"]
+    sig = inspect.signature(gridencoder.grid._grid_encode.forward)
+    assert list(sig.parameters)[1:] == ["inputs", "embeddings", "offsets", "per_level_scale", "base_resolution", "calc_grad_inputs", "gridtype", "align_corners"]
+    enc, dim = get_encoder("hashgrid", input_dim=2, num_levels=12, level_dim=1, base_resolution=64, log2_hashmap_size=14, desired_resolution=512)
+    assert dim == 12 and tuple(enc.embeddings.shape) == (163584, 1) and enc.offsets.dtype == torch.int32
+    assert float(enc.embeddings.abs().max()) <= 1e-4                      # grid.py:132-134
+    t, tdim = get_encoder("tiledgrid", input_dim=2, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=16, desired_resolution=2048)
+    assert tdim == 32 and t.embeddings.numel() == 1111040                 # network.py:166
+    sh, shd = get_encoder("spherical_harmonics"); fq, fqd = get_encoder("frequency", input_dim=2, multires=8)
+    assert shd == 16 and fqd == 34
+    assert get_encoder("None", input_dim=5)[1] == 5
+    with pytest.raises(NotImplementedError):
+        get_encoder("ash")
+    assert isinstance(shencoder.SHEncoder(degree=8), torch.nn.Module) and isinstance(freqencoder.FreqEncoder(), torch.nn.Module)
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a CUDA device / with CPU tensors — never route to the oracle."""
+    from gridencoder.backend import _backend as gb
+    x = torch.rand(4, 2); emb = torch.rand(8, 1); offs = torch.tensor([0, 8], dtype=torch.int32); out = torch.empty(1, 4, 1)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        gb.grid_encode_forward(x, emb, offs, out, 4, 2, 1, 1, 0.0, 4, None, 0, False)
+    import b2nerf
+    pkg = os.path.dirname(os.path.dirname(b2nerf.__file__))
+    for root, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(root, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f"{fn} imports the test oracle"
