@@ -1,0 +1,67 @@
+/*
+ * b2nerf_fused.h — C ABI of the fused fast path of libb2nerf.so.  No reference counterpart: these entry points run the
+ * same math as nerf_triplane/network.py:252-311 (NeRFNetwork.forward/density) and nerf_triplane/renderer.py:442-561
+ * (run_cuda_for_inference) in a handful of launches instead of ~45 per loop iteration.  Conventions as in b2nerf.h.
+ */
+#ifndef B2NERF_FUSED_H_
+#define B2NERF_FUSED_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Head-model geometry, fixed by network.py:129-152: three D=2 L=12 C=1 hash grids (xy, yz, xz), audio dim 32,
+ * eye dim 1, individual-code dim 4, SH degree 4.  Weights are nn.Linear layout [out,in], fp32, no bias. */
+typedef struct {
+    /* tri-plane tables: each [offsets[12], 1] fp32 (network.py:129-133); offsets shared (grid.py:111-123) */
+    const float   *table_xy, *table_yz, *table_xz;
+    const int32_t *offsets;          /* [13], device */
+    float          S;                /* log2(per_level_scale), grid.py:32 */
+    uint32_t       H;                /* base resolution (64) */
+    float          bound;            /* scene bound (1) */
+    /* MLPs (network.py:141-152) */
+    const float *aud_att_w0, *aud_att_w1;        /* aud_ch_att_net 36->64->32 */
+    const float *eye_att_w0, *eye_att_w1;        /* eye_att_net    36->16->1  */
+    const float *sigma_w0, *sigma_w1, *sigma_w2; /* sigma_net      69->64->64->65 */
+    const float *color_w0, *color_w1;            /* color_net      84->64->3  */
+    const float *unc_w0, *unc_w1;                /* unc_net        36->32->1 (both NULL => testing: unc = log 2) */
+} b2n_head_weights;
+
+typedef struct b2n_model b2n_model;   /* opaque: fp16 weight image in the tensor-core operand layout */
+
+int  b2n_model_create(b2n_model **out, void *stream);
+/* (re)packs the weights on `stream` (two small kernels); the table / offsets pointers are kept, not copied */
+int  b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream);
+void b2n_model_destroy(b2n_model *m);
+
+/* Per-sample network forward = NeRFNetwork.forward (network.py:252-281) on M samples, autocast(fp16) numerics.
+ * xyzs/dirs [M,3]; enc_a [32]; ind_code [4] or NULL; eye [1] or NULL (device).  Outputs (any may be NULL): sigmas [M],
+ * rgbs [M,3], amb_aud [M] (L2 norm of the audio channel attention), amb_eye [M], unc [M] (softplus; log 2 when testing).
+ * n_valid: optional device int32 — only the first min(M, *n_valid) samples are evaluated. */
+int b2n_head_forward(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M,
+                     const float *enc_a, const float *ind_code, const float *eye, const int32_t *n_valid,
+                     float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, void *stream);
+
+/* One whole inference frame = renderer.py:442 (near/far) + :480-545 (march / network / composite loop with compaction)
+ * + :559-561 (background blend, clamp), with NO host synchronisation: alive-ray counts and n_step live in a device-side
+ * control block; the host enqueues a fixed launch sequence (capturable in a CUDA graph).  perturb is off (inference).
+ * rays_o/rays_d [N,3]; bitfield [cascade*grid_size^3/8]; bg_color [N,3] or NULL (=> white); image_out [N,3] fp32;
+ * weights_sum_out [N] or NULL; depth_out [N] or NULL.  workspace: 256-byte aligned device scratch of
+ * b2n_render_frame_workspace_bytes(N) bytes, owned by the caller. */
+typedef struct {
+    float    bound, dt_gamma, min_near, T_thresh, density_scale;
+    uint32_t max_steps, cascade, grid_size;
+    float    aabb[6];
+} b2n_render_cfg;
+uint64_t b2n_render_frame_workspace_bytes(uint32_t N);
+int b2n_render_frame(const b2n_model *m, const b2n_render_cfg *cfg, const float *rays_o, const float *rays_d,
+                     uint32_t N, const uint8_t *bitfield, const float *enc_a, const float *ind_code,
+                     const float *eye, const float *bg_color, void *workspace,
+                     float *image_out, float *weights_sum_out, float *depth_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2NERF_FUSED_H_ */

@@ -1,0 +1,239 @@
+"""Head model of the talking-head NeRF on the B200-native kernels.
+
+`HeadModel` holds exactly the parameters/buffers of the reference's `NeRFNetwork(NeRFRenderer)` head branch
+(nerf_triplane/network.py:97-152, renderer.py:86-160) under the SAME names and shapes, so a reference checkpoint's
+`model` state_dict loads with `strict=False` (torso parameters are ignored):
+    audio_net.*, audio_att_net.*, encoder_{xy,yz,xz}.embeddings / .offsets, sigma_net.net.{0,1,2}.weight,
+    color_net.net.{0,1}.weight, unc_net.net.{0,1}.weight, aud_ch_att_net.net.{0,1}.weight, eye_att_net.net.{0,1}.weight,
+    individual_codes, aabb_train, aabb_infer, density_grid, density_bitfield, step_counter.
+
+Two evaluation paths, same math:
+  * forward_unfused(...)  — the reference's op-by-op graph (network.py:252-311) on the drop-in encoders + torch Linear;
+                            differentiable; used for training through autograd and as the on-GPU parity partner;
+  * forward(...)          — the fused tcgen05 kernel (csrc/fused_head.cu) through the C ABI (inference).
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from gridencoder import GridEncoder
+from shencoder import SHEncoder
+
+from ._lib import lib
+
+
+class MLP(nn.Module):
+    """Bias-free ReLU MLP (network.py:73-94)."""
+
+    def __init__(self, dim_in, dim_out, dim_hidden, num_layers):
+        super().__init__()
+        self.dim_in, self.dim_out, self.dim_hidden, self.num_layers = dim_in, dim_out, dim_hidden, num_layers
+        dims = [dim_in] + [dim_hidden] * (num_layers - 1) + [dim_out]
+        self.net = nn.ModuleList(nn.Linear(dims[i], dims[i + 1], bias=False) for i in range(num_layers))
+
+    def forward(self, x):
+        for i, layer in enumerate(self.net):
+            x = layer(x)
+            if i != self.num_layers - 1:
+                x = F.relu(x, inplace=True)
+        return x
+
+
+class AudioAttNet(nn.Module):
+    """Attention over the 8-frame audio window (network.py:9-36)."""
+
+    def __init__(self, dim_aud=64, seq_len=8):
+        super().__init__()
+        self.seq_len, self.dim_aud = seq_len, dim_aud
+        chans = [dim_aud, 16, 8, 4, 2, 1]
+        layers = []
+        for cin, cout in zip(chans[:-1], chans[1:]):
+            layers += [nn.Conv1d(cin, cout, kernel_size=3, stride=1, padding=1, bias=True), nn.LeakyReLU(0.02, True)]
+        self.attentionConvNet = nn.Sequential(*layers)
+        self.attentionNet = nn.Sequential(nn.Linear(seq_len, seq_len, bias=True), nn.Softmax(dim=1))
+
+    def forward(self, x):                      # x [1, seq_len, dim_aud]
+        y = self.attentionConvNet(x.permute(0, 2, 1))
+        y = self.attentionNet(y.view(1, self.seq_len)).view(1, self.seq_len, 1)
+        return torch.sum(y * x, dim=1)
+
+
+class AudioNet(nn.Module):
+    """Per-frame audio feature extractor (network.py:40-70)."""
+
+    def __init__(self, dim_in=29, dim_aud=64, win_size=16):
+        super().__init__()
+        self.win_size, self.dim_aud = win_size, dim_aud
+        chans = [dim_in, 32, 32, 64, 64]
+        layers = []
+        for cin, cout in zip(chans[:-1], chans[1:]):
+            layers += [nn.Conv1d(cin, cout, kernel_size=3, stride=2, padding=1, bias=True), nn.LeakyReLU(0.02, True)]
+        self.encoder_conv = nn.Sequential(*layers)
+        self.encoder_fc1 = nn.Sequential(nn.Linear(64, 64), nn.LeakyReLU(0.02, True), nn.Linear(64, dim_aud))
+
+    def forward(self, x):
+        half_w = self.win_size // 2
+        x = x[:, :, 8 - half_w:8 + half_w]
+        return self.encoder_fc1(self.encoder_conv(x).squeeze(-1))
+
+
+class _HeadWeightsC(ctypes.Structure):      # mirrors b2n_head_weights (include/b2nerf_fused.h)
+    _fields_ = [("table_xy", ctypes.c_void_p), ("table_yz", ctypes.c_void_p), ("table_xz", ctypes.c_void_p), ("offsets", ctypes.c_void_p),
+                ("S", ctypes.c_float), ("H", ctypes.c_uint32), ("bound", ctypes.c_float),
+                ("aud_att_w0", ctypes.c_void_p), ("aud_att_w1", ctypes.c_void_p), ("eye_att_w0", ctypes.c_void_p), ("eye_att_w1", ctypes.c_void_p),
+                ("sigma_w0", ctypes.c_void_p), ("sigma_w1", ctypes.c_void_p), ("sigma_w2", ctypes.c_void_p),
+                ("color_w0", ctypes.c_void_p), ("color_w1", ctypes.c_void_p), ("unc_w0", ctypes.c_void_p), ("unc_w1", ctypes.c_void_p)]
+
+
+class _RenderCfgC(ctypes.Structure):        # mirrors b2n_render_cfg
+    _fields_ = [("bound", ctypes.c_float), ("dt_gamma", ctypes.c_float), ("min_near", ctypes.c_float), ("T_thresh", ctypes.c_float),
+                ("density_scale", ctypes.c_float), ("max_steps", ctypes.c_uint32), ("cascade", ctypes.c_uint32), ("grid_size", ctypes.c_uint32),
+                ("aabb", ctypes.c_float * 6)]
+
+
+class HeadModel(nn.Module):
+    def __init__(self, bound=1.0, audio_in_dim=1024, audio_dim=32, ind_dim=4, ind_num=10000, att=2, grid_size=128):
+        super().__init__()
+        self.bound, self.audio_dim, self.att, self.grid_size = float(bound), audio_dim, att, grid_size
+        self.cascade = 1 + math.ceil(math.log2(bound))
+        self.audio_in_dim = audio_in_dim
+        self.audio_net = AudioNet(audio_in_dim, audio_dim)
+        if att > 0:
+            self.audio_att_net = AudioAttNet(audio_dim)
+        grid = dict(input_dim=2, num_levels=12, level_dim=1, base_resolution=64, log2_hashmap_size=14, desired_resolution=512 * bound)
+        self.encoder_xy, self.encoder_yz, self.encoder_xz = GridEncoder(**grid), GridEncoder(**grid), GridEncoder(**grid)
+        self.in_dim = 36
+        self.eye_att_net = MLP(self.in_dim, 1, 16, 2)
+        self.sigma_net = MLP(self.in_dim + audio_dim + 1, 1 + 64, 64, 3)
+        self.encoder_dir = SHEncoder(input_dim=3, degree=4)
+        self.color_net = MLP(16 + 64 + ind_dim, 3, 64, 2)
+        self.unc_net = MLP(self.in_dim, 1, 32, 2)
+        self.aud_ch_att_net = MLP(self.in_dim, audio_dim, 64, 2)
+        self.individual_codes = nn.Parameter(torch.randn(ind_num, ind_dim) * 0.1)
+        aabb = torch.tensor([-bound, -bound / 2, -bound, bound, bound / 2, bound], dtype=torch.float32)
+        self.register_buffer("aabb_train", aabb.clone())
+        self.register_buffer("aabb_infer", aabb.clone())
+        self.register_buffer("density_grid", torch.zeros(self.cascade, grid_size ** 3))
+        self.register_buffer("density_bitfield", torch.zeros(self.cascade * grid_size ** 3 // 8, dtype=torch.uint8))
+        self.register_buffer("step_counter", torch.zeros(16, 2, dtype=torch.int32))
+        self.testing = False
+        self.unc_loss = True
+        self._handle = None
+
+    # ---- audio prologue (network.py:226-240) --------------------------------------------------------------------------
+    def encode_audio(self, a):
+        if a is None:
+            return None
+        enc_a = self.audio_net(a)
+        if self.att > 0:
+            enc_a = self.audio_att_net(enc_a.unsqueeze(0))
+        return enc_a
+
+    # ---- reference graph on the drop-in ops (network.py:215-223, 252-311) ---------------------------------------------
+    def encode_x(self, xyz):
+        xy, yz, xz = xyz[:, :-1], xyz[:, 1:], torch.cat([xyz[:, :1], xyz[:, -1:]], dim=-1)
+        return torch.cat([self.encoder_xy(xy, bound=self.bound), self.encoder_yz(yz, bound=self.bound), self.encoder_xz(xz, bound=self.bound)], dim=-1)
+
+    def density(self, x, enc_a, e=None, enc_x=None):
+        if enc_x is None:
+            enc_x = self.encode_x(x)
+        enc_a = enc_a.repeat(enc_x.shape[0], 1)
+        aud_ch_att = self.aud_ch_att_net(enc_x)
+        enc_w = enc_a * aud_ch_att
+        eye_att = torch.sigmoid(self.eye_att_net(enc_x))
+        h = torch.cat([enc_x, enc_w, e * eye_att], dim=-1)
+        h = self.sigma_net(h)
+        return {"sigma": torch.exp(h[..., 0]), "geo_feat": h[..., 1:], "ambient_aud": aud_ch_att.norm(dim=-1, keepdim=True), "ambient_eye": eye_att}
+
+    def forward_unfused(self, x, d, enc_a, c, e):
+        enc_x = self.encode_x(x)
+        r = self.density(x, enc_a, e, enc_x)
+        h = torch.cat([self.encoder_dir(d), r["geo_feat"], c.repeat(x.shape[0], 1)], dim=-1)
+        color = torch.sigmoid(self.color_net(h)) * (1 + 2 * 0.001) - 0.001
+        unc = torch.zeros_like(enc_x) if (self.testing or not self.unc_loss) else self.unc_net(enc_x.detach())
+        unc = torch.log(1 + torch.exp(unc))
+        return r["sigma"], color, r["ambient_aud"], r["ambient_eye"], unc[..., None]
+
+    # ---- fused path -----------------------------------------------------------------------------------------------------
+    def pack(self, with_unc=None):
+        """(Re)pack the MLP weights into the tensor-core operand image; call after every optimizer step / load_state_dict."""
+        L = lib()
+        if self._handle is None:
+            h = ctypes.c_void_p()
+            L.call("b2n_model_create", ctypes.byref(h), None)
+            self._handle = h
+        with_unc = (not self.testing and self.unc_loss) if with_unc is None else with_unc
+        p = lambda t: t.detach().data_ptr()
+        for t in (self.encoder_xy.embeddings, self.sigma_net.net[0].weight):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise RuntimeError("HeadModel.pack: parameters must be contiguous float32 CUDA tensors")
+        w = _HeadWeightsC(p(self.encoder_xy.embeddings), p(self.encoder_yz.embeddings), p(self.encoder_xz.embeddings), p(self.encoder_xy.offsets),
+                          float(math.log2(self.encoder_xy.per_level_scale)), self.encoder_xy.base_resolution, self.bound,
+                          p(self.aud_ch_att_net.net[0].weight), p(self.aud_ch_att_net.net[1].weight), p(self.eye_att_net.net[0].weight),
+                          p(self.eye_att_net.net[1].weight), p(self.sigma_net.net[0].weight), p(self.sigma_net.net[1].weight),
+                          p(self.sigma_net.net[2].weight), p(self.color_net.net[0].weight), p(self.color_net.net[1].weight),
+                          p(self.unc_net.net[0].weight) if with_unc else None, p(self.unc_net.net[1].weight) if with_unc else None)
+        self._packed_weights = w            # keep the struct alive
+        L.call("b2n_model_update", self._handle, ctypes.byref(w), torch.cuda.current_stream().cuda_stream)
+        return self
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            self.pack()
+        return self._handle
+
+    @torch.no_grad()
+    def forward(self, x, d, enc_a, c, e, n_valid=None):
+        """Fused head: returns sigma [M], color [M,3], ambient_aud [M,1], ambient_eye [M,1], uncertainty [M,1,1] (fp32)."""
+        M = x.shape[0]
+        x, d = x.float().contiguous(), d.float().contiguous()
+        dev = x.device
+        sig, rgb = torch.empty(M, device=dev), torch.empty(M, 3, device=dev)
+        aud, eye_o, unc = torch.empty(M, device=dev), torch.empty(M, device=dev), torch.empty(M, device=dev)
+        f = lambda t: None if t is None else t.detach().float().contiguous().view(-1)
+        enc_a, c, e = f(enc_a), f(c), f(e)
+        self._keep = (enc_a, c, e)
+        lib().call("b2n_head_forward", self.handle, x.data_ptr(), d.data_ptr(), M, enc_a.data_ptr(), None if c is None else c.data_ptr(),
+                   None if e is None else e.data_ptr(), None if n_valid is None else n_valid.data_ptr(),
+                   sig.data_ptr(), rgb.data_ptr(), aud.data_ptr(), eye_o.data_ptr(), unc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return sig, rgb, aud[:, None], eye_o[:, None], unc[:, None, None]
+
+    # ---- whole-frame inference (renderer.py:406-570) ----------------------------------------------------------------------
+    @torch.no_grad()
+    def render_frame(self, rays_o, rays_d, enc_a, ind_code=None, eye=None, bg_color=None, dt_gamma=1.0 / 256, max_steps=16, min_near=0.05,
+                     T_thresh=1e-4, density_scale=1.0, out=None):
+        """run_cuda_for_inference without host syncs: returns image [N,3] (clamped, background-blended), weights_sum [N], depth [N]."""
+        rays_o, rays_d = rays_o.float().contiguous().view(-1, 3), rays_d.float().contiguous().view(-1, 3)
+        N, dev = rays_o.shape[0], rays_o.device
+        L = lib()
+        need = int(L.raw("b2n_render_frame_workspace_bytes")(N))
+        if getattr(self, "_ws", None) is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        image = out if out is not None else torch.empty(N, 3, device=dev)
+        ws, depth = torch.empty(N, device=dev), torch.empty(N, device=dev)
+        cfg = _RenderCfgC(self.bound, dt_gamma, min_near, T_thresh, density_scale, max_steps, self.cascade, self.grid_size,
+                          (ctypes.c_float * 6)(*[float(v) for v in self.aabb_infer.tolist()]) if not hasattr(self, "_aabb_host") else self._aabb_host)
+        f = lambda t: None if t is None else t.detach().float().contiguous().view(-1)
+        enc_a, ind_code, eye, bg = f(enc_a), f(ind_code), f(eye), f(bg_color)
+        self._keep = (enc_a, ind_code, eye, bg, cfg)
+        L.call("b2n_render_frame", self.handle, ctypes.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(), N, self.density_bitfield.data_ptr(),
+               enc_a.data_ptr(), None if ind_code is None else ind_code.data_ptr(), None if eye is None else eye.data_ptr(),
+               None if bg is None else bg.data_ptr(), self._ws.data_ptr(), image.data_ptr(), ws.data_ptr(), depth.data_ptr(),
+               torch.cuda.current_stream().cuda_stream)
+        return image, ws, depth
+
+    def cache_host_constants(self):
+        """Read aabb_infer once (a D2H copy) so render_frame never synchronises."""
+        self._aabb_host = (ctypes.c_float * 6)(*[float(v) for v in self.aabb_infer.tolist()])
+        return self
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                lib().raw("b2n_model_destroy")(self._handle)
+        except Exception:
+            pass

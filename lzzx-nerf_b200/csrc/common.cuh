@@ -8,6 +8,7 @@
 #include <atomic>
 
 #include "../../include/b2nerf.h"
+#include "../../include/b2nerf_fused.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "libb2nerf is written for sm_100a (B200) only"

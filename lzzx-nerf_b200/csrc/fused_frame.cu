@@ -1,0 +1,252 @@
+// fused_frame.cu — one inference frame (renderer.py:406-570, run_cuda_for_inference) with no host synchronisation.
+//
+// The reference drives its march / network / composite loop from the host and reads the alive-ray count back every
+// iteration (rays_alive[rays_alive >= 0], renderer.py:542 — 16 D2H syncs per frame).  Here the loop state lives in a
+// small device-side control block per iteration:
+//     ctrl[it] = { n_alive, n_step, step, n_samples, done }
+// and the host enqueues a FIXED sequence of launches (max_steps iterations; kernels of iterations after the loop has
+// ended exit at once), so a frame is capturable in a CUDA graph.  Semantics per iteration are the reference's:
+//     n_step = max(min(N // n_alive, 8), 1)                                   renderer.py:506-513
+//     march_rays(n_alive, n_step, ...) -> network -> composite_rays_triplane  renderer.py:518-534
+//     rays_alive = rays_alive[rays_alive >= 0]   (stable compaction)          renderer.py:542
+//     step += n_step; loop while step < max_steps and n_alive > 0             renderer.py:503
+// Per-ray arithmetic is the same code as the per-op kernels (dda.cuh, composite order), so images match the op-by-op
+// path bit for bit given the same network outputs.
+#include "common.cuh"
+#include "dda.cuh"
+#include "fused_head.cuh"
+
+namespace b2n {
+
+struct FrameCtrl { int32_t n_alive, n_step, step, n_samples, done, pad[3]; };     // 32 B
+
+struct FrameWs {            // carved out of the caller's workspace
+    FrameCtrl *ctrl;        // [max_iters + 1]
+    int32_t *alive[2];      // ping-pong compacted ray ids [N]
+    int32_t *totals;        // per-CTA survivor counts
+    float *nears, *fars, *rays_t, *ws, *depth, *aud_sum, *eye_sum, *unc_sum, *image;   // per ray
+    float *xyzs, *dirs, *deltas, *sigmas, *rgbs, *amb_aud, *amb_eye, *unc;              // per sample (<= N + 128)
+};
+
+constexpr uint32_t FR_THREADS = 128;
+constexpr uint32_t FR_MAX_ITERS = 64;
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t carve(FrameWs *w, uint8_t *base, uint32_t N) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { uint8_t *p = base ? base + off : nullptr; off = align_up(off + bytes, 256); return p; };
+    const size_t Np = (size_t)N + 128;
+    FrameWs t;
+    t.ctrl = (FrameCtrl *)take(sizeof(FrameCtrl) * (FR_MAX_ITERS + 1));
+    t.alive[0] = (int32_t *)take(4 * Np); t.alive[1] = (int32_t *)take(4 * Np);
+    t.totals = (int32_t *)take(4 * (Np / FR_THREADS + 2));
+    float **per_ray[] = {&t.nears, &t.fars, &t.rays_t, &t.ws, &t.depth, &t.aud_sum, &t.eye_sum, &t.unc_sum};
+    for (auto p : per_ray) *p = (float *)take(4 * Np);
+    t.image = (float *)take(12 * Np);
+    t.xyzs = (float *)take(12 * Np); t.dirs = (float *)take(12 * Np); t.deltas = (float *)take(8 * Np);
+    t.sigmas = (float *)take(4 * Np); t.rgbs = (float *)take(12 * Np);
+    t.amb_aud = (float *)take(4 * Np); t.amb_eye = (float *)take(4 * Np); t.unc = (float *)take(4 * Np);
+    if (w) *w = t;
+    return off;
+}
+
+// near/far + state reset + ctrl[0]
+__global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ rays_o, const float *__restrict__ rays_d, uint32_t N, float min_near,
+                                                     float a0, float a1, float a2, float a3, float a4, float a5, uint32_t max_steps, FrameWs w) {
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        const float ox = rays_o[3 * n], oy = rays_o[3 * n + 1], oz = rays_o[3 * n + 2];
+        const float rdx = 1.0f / rays_d[3 * n], rdy = 1.0f / rays_d[3 * n + 1], rdz = 1.0f / rays_d[3 * n + 2];
+        float tn, tf;
+        near_far_one(ox, oy, oz, rdx, rdy, rdz, a0, a1, a2, a3, a4, a5, min_near, tn, tf);
+        w.nears[n] = tn; w.fars[n] = tf; w.rays_t[n] = tn;
+        w.ws[n] = 0.0f; w.depth[n] = 0.0f; w.aud_sum[n] = 0.0f; w.eye_sum[n] = 0.0f; w.unc_sum[n] = 0.0f;
+        w.image[3 * n] = 0.0f; w.image[3 * n + 1] = 0.0f; w.image[3 * n + 2] = 0.0f;
+        w.alive[0][n] = (int32_t)n;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        FrameCtrl c = {};
+        c.n_alive = (int32_t)N; c.n_step = 1; c.step = 0; c.n_samples = (int32_t)N;      // N // N = 1
+        c.done = (N == 0 || max_steps == 0) ? 1 : 0;
+        if (c.done) { c.n_alive = 0; c.n_samples = 0; }
+        w.ctrl[0] = c;
+    }
+}
+
+// march_rays for the compacted alive rays of iteration `it` (raymarching.cu:828-929); fills its unproduced slots with zeros
+__global__ void __launch_bounds__(FR_THREADS) k_frame_march(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+                                                             float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, uint32_t it, FrameWs w) {
+    const FrameCtrl c = w.ctrl[it];
+    const uint32_t n = blockIdx.x * FR_THREADS + threadIdx.x;
+    if (c.done || n >= (uint32_t)c.n_alive) return;
+    const uint32_t n_step = (uint32_t)c.n_step;
+    const int32_t id = w.alive[it & 1][n];
+    DdaRay r;
+    r.init(rays_o + 3 * (size_t)id, rays_d + 3 * (size_t)id, bound, dt_gamma, max_steps, C, H, w.fars[id]);
+    float t = r.perturb(w.rays_t[id], 0.0f);          // noise = 0 (perturb is off at inference): fma(dt, 0, t) == t, kept for op parity
+    float *px = w.xyzs + 3 * (size_t)n * n_step, *pd = w.dirs + 3 * (size_t)n * n_step, *pl = w.deltas + 2 * (size_t)n * n_step;
+    uint32_t step = 0;
+    DdaSample s;
+    while (t < r.far && step < n_step) {
+        if (r.probe(grid, t, s)) {
+            t = __fadd_rn(t, s.dt);
+            px[0] = s.x; px[1] = s.y; px[2] = s.z; pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz; pl[0] = s.dt; pl[1] = t;
+            px += 3; pd += 3; pl += 2; step++;
+        }
+    }
+    for (; step < n_step; step++) {                    // the reference relies on a torch.zeros fill (raymarching.py:384-386)
+        px[0] = 0.0f; px[1] = 0.0f; px[2] = 0.0f; pd[0] = 0.0f; pd[1] = 0.0f; pd[2] = 0.0f; pl[0] = 0.0f; pl[1] = 0.0f;
+        px += 3; pd += 3; pl += 2;
+    }
+}
+
+// composite_rays_triplane (raymarching.cu:2142-2249) + per-CTA survivor count
+__global__ void __launch_bounds__(FR_THREADS) k_frame_composite(float T_thresh, uint32_t it, FrameWs w) {
+    const FrameCtrl c = w.ctrl[it];
+    const uint32_t n = blockIdx.x * FR_THREADS + threadIdx.x;
+    bool survive = false;
+    if (!c.done && n < (uint32_t)c.n_alive) {
+        const uint32_t n_step = (uint32_t)c.n_step;
+        int32_t *alive = w.alive[it & 1];
+        const int32_t idx = alive[n];
+        const size_t base = (size_t)n * n_step;
+        float t = w.rays_t[idx], ws = w.ws[idx], d = w.depth[idx];
+        float r = w.image[3 * (size_t)idx], g = w.image[3 * (size_t)idx + 1], b = w.image[3 * (size_t)idx + 2];
+        float a0 = w.aud_sum[idx], a1 = w.eye_sum[idx], u = w.unc_sum[idx];
+        uint32_t step = 0;
+        while (step < n_step) {
+            const size_t i = base + step;
+            const float delta = w.deltas[2 * i];
+            if (delta == 0.0f) break;
+            const float alpha = __fsub_rn(1.0f, __expf(-__fmul_rn(w.sigmas[i], delta)));
+            const float T = __fsub_rn(1.0f, ws);
+            const float wgt = __fmul_rn(alpha, T);
+            ws = __fadd_rn(ws, wgt);
+            t = w.deltas[2 * i + 1];
+            d = __fmaf_rn(wgt, t, d);
+            r = __fmaf_rn(wgt, w.rgbs[3 * i], r); g = __fmaf_rn(wgt, w.rgbs[3 * i + 1], g); b = __fmaf_rn(wgt, w.rgbs[3 * i + 2], b);
+            a0 = __fadd_rn(a0, w.amb_aud[i]); a1 = __fadd_rn(a1, w.amb_eye[i]);
+            u = __fmaf_rn(wgt, w.unc[i], u);
+            if (T < T_thresh) break;
+            step++;
+        }
+        survive = !(step < n_step);
+        if (survive) w.rays_t[idx] = t; else alive[n] = -1;
+        w.ws[idx] = ws; w.depth[idx] = d;
+        w.image[3 * (size_t)idx] = r; w.image[3 * (size_t)idx + 1] = g; w.image[3 * (size_t)idx + 2] = b;
+        w.aud_sum[idx] = a0; w.eye_sum[idx] = a1; w.unc_sum[idx] = u;
+    }
+    const int cnt = __syncthreads_count(survive);
+    if (threadIdx.x == 0) w.totals[blockIdx.x] = cnt;
+}
+
+// stable compaction of the survivors into the other alive buffer; the last CTA publishes ctrl[it+1]
+__global__ void __launch_bounds__(FR_THREADS) k_frame_compact(uint32_t N, uint32_t max_steps, uint32_t it, FrameWs w) {
+    const FrameCtrl c = w.ctrl[it];
+    __shared__ uint32_t red[FR_THREADS / 32];
+    __shared__ uint32_t s_base;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nblk_live = c.done ? 0u : ((uint32_t)c.n_alive + FR_THREADS - 1) / FR_THREADS;
+    if (blockIdx.x >= nblk_live && !(blockIdx.x == 0)) return;
+    if (c.done) {                                      // propagate the terminal state
+        if (blockIdx.x == 0 && threadIdx.x == 0) { FrameCtrl nx = c; nx.n_alive = 0; nx.n_samples = 0; nx.done = 1; w.ctrl[it + 1] = nx; }
+        return;
+    }
+    uint32_t part = 0;
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += FR_THREADS) part += (uint32_t)w.totals[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t b = 0; for (int q = 0; q < (int)(FR_THREADS / 32); q++) b += red[q]; s_base = b; }
+    __syncthreads();
+    const uint32_t n = blockIdx.x * FR_THREADS + threadIdx.x;
+    const int32_t id = (n < (uint32_t)c.n_alive) ? w.alive[it & 1][n] : -1;
+    const uint32_t keep = id >= 0 ? 1u : 0u;
+    uint32_t inc = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    __syncthreads();
+    if (lane == 31) red[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < (int)(FR_THREADS / 32); q++) { if (q < (int)warp) woff += red[q]; tot += red[q]; }
+    if (keep) w.alive[(it + 1) & 1][s_base + woff + inc - 1] = id;
+    if (blockIdx.x == nblk_live - 1 && threadIdx.x == 0) {
+        FrameCtrl nx = {};
+        nx.n_alive = (int32_t)(s_base + tot);
+        nx.step = c.step + c.n_step;
+        nx.done = (nx.n_alive <= 0 || nx.step >= (int32_t)max_steps) ? 1 : 0;
+        if (nx.done) { nx.n_alive = 0; nx.n_step = 1; nx.n_samples = 0; }
+        else {
+            int32_t ns = (int32_t)N / nx.n_alive;                  // n_step = max(min(N // n_alive, 8), 1)
+            ns = ns < 8 ? ns : 8; ns = ns > 1 ? ns : 1;
+            nx.n_step = ns; nx.n_samples = nx.n_alive * ns;
+        }
+        w.ctrl[it + 1] = nx;
+    }
+}
+
+// image = clamp(image + (1 - weights_sum) * bg, 0, 1)  (renderer.py:559-561)
+__global__ void __launch_bounds__(256) k_frame_finish(uint32_t N, const float *__restrict__ bg, FrameWs w, float *__restrict__ image_out,
+                                                       float *__restrict__ ws_out, float *__restrict__ depth_out) {
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        const float ws = w.ws[n];
+        const float k = __fsub_rn(1.0f, ws);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float b = bg ? bg[3 * (size_t)n + ch] : 1.0f;
+            const float v = __fadd_rn(w.image[3 * (size_t)n + ch], __fmul_rn(k, b));
+            __stcs(image_out + 3 * (size_t)n + ch, fminf(fmaxf(v, 0.0f), 1.0f));
+        }
+        if (ws_out) ws_out[n] = ws;
+        if (depth_out) depth_out[n] = w.depth[n];
+    }
+}
+
+}  // namespace b2n
+
+using namespace b2n;
+
+struct b2n_model;
+namespace b2n { int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code,
+                                          const float *eye, const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud,
+                                          float *amb_eye, float *unc, cudaStream_t st); }
+
+extern "C" {
+
+uint64_t b2n_render_frame_workspace_bytes(uint32_t N) { return (uint64_t)carve(nullptr, nullptr, N); }
+
+int b2n_render_frame(const b2n_model *m, const b2n_render_cfg *cfg, const float *rays_o, const float *rays_d, uint32_t N, const uint8_t *bitfield,
+                     const float *enc_a, const float *ind_code, const float *eye, const float *bg_color, void *workspace,
+                     float *image_out, float *weights_sum_out, float *depth_out, void *stream) {
+    B2N_REQUIRE(m && cfg && rays_o && rays_d && bitfield && enc_a && workspace && image_out, "render_frame: null pointer");
+    B2N_REQUIRE(((uintptr_t)workspace & 255) == 0, "render_frame: workspace must be 256-byte aligned");
+    B2N_REQUIRE(cfg->max_steps <= FR_MAX_ITERS, "render_frame: max_steps=%u exceeds the %u-iteration launch plan", cfg->max_steps, FR_MAX_ITERS);
+    B2N_REQUIRE(cfg->cascade >= 1 && cfg->cascade <= 24 && cfg->grid_size >= 1 && cfg->grid_size <= 1024, "render_frame: bad cascade / grid size");
+    if (N == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    FrameWs w;
+    carve(&w, (uint8_t *)workspace, N);
+    const uint32_t sms = (uint32_t)sm_count();
+    uint32_t g = ceil_div<uint32_t>(N, 256); if (g > sms * 8) g = sms * 8;
+    k_frame_init<<<g, 256, 0, st>>>(rays_o, rays_d, N, cfg->min_near, cfg->aabb[0], cfg->aabb[1], cfg->aabb[2], cfg->aabb[3], cfg->aabb[4], cfg->aabb[5],
+                                    cfg->max_steps, w);
+    if (check_launch("render_frame(init)")) return 1;
+    const uint32_t ctas = ceil_div<uint32_t>(N, FR_THREADS);
+    for (uint32_t it = 0; it < cfg->max_steps; it++) {
+        k_frame_march<<<ctas, FR_THREADS, 0, st>>>(rays_o, rays_d, bitfield, cfg->bound, cfg->dt_gamma, cfg->max_steps, cfg->cascade, cfg->grid_size, it, w);
+        if (check_launch("render_frame(march)")) return 1;
+        if (int rc = head_forward_on_model(m, w.xyzs, w.dirs, N, enc_a, ind_code, eye, &w.ctrl[it].n_samples, cfg->density_scale, w.sigmas, w.rgbs, w.amb_aud,
+                                           w.amb_eye, w.unc, st)) return rc;
+        k_frame_composite<<<ctas, FR_THREADS, 0, st>>>(cfg->T_thresh, it, w);
+        if (check_launch("render_frame(composite)")) return 1;
+        k_frame_compact<<<ctas, FR_THREADS, 0, st>>>(N, cfg->max_steps, it, w);
+        if (check_launch("render_frame(compact)")) return 1;
+    }
+    k_frame_finish<<<g, 256, 0, st>>>(N, bg_color, w, image_out, weights_sum_out, depth_out);
+    return check_launch("render_frame(finish)");
+}
+
+}  // extern "C"

@@ -1,0 +1,461 @@
+// fused_head.cu — the per-sample head network of the talking-head NeRF as ONE persistent tcgen05 kernel.
+//
+// Replaces the ~45-launch chain of nerf_triplane/network.py:252-311 (NeRFNetwork.forward / density):
+//   tri-plane encode (3 x GridEncoder D=2 L=12 C=1, network.py:215-223)  -> 36 features
+//   aud_ch_att_net 36->64->32, eye_att_net 36->16->1, [unc_net 36->32->1]            (network.py:141-152, 283-292)
+//   sigma_net [36 + 32 + 1 = 69] -> 64 -> 64 -> 65, sigma = exp(h0)                   (network.py:298-301)
+//   SH degree 4 of the view direction, color_net [16 + 64 + 4 = 84] -> 64 -> 3         (network.py:267-275)
+// Numerics follow the reference under autocast(fp16): GEMM operands and activations are fp16, accumulation fp32
+// (TMEM), exp / norm / softplus in fp32, sigmoid in fp16.
+//
+// Organisation (B200):
+//   * persistent CTA per SM, 512 threads = 4 warpgroups; each warpgroup owns one 128-sample tile at a time, its own
+//     128 TMEM columns and two 16 KB operand buffers (X, H).  The four tiles desynchronise and overlap gather,
+//     tensor and epilogue work on the SM.
+//   * all weights (fp16, pre-swizzled K-major SWIZZLE_128B image, 70 KB) are brought in once per CTA by one TMA bulk
+//     copy and stay resident; every layer is a tcgen05.mma (M=128 samples, N=16..112, K=16 per instruction) issued by
+//     one thread per warpgroup with the accumulator in TMEM; epilogues read TMEM with tcgen05.ld (thread == sample
+//     row), apply the activation and write the next layer's fp16 operand straight back to shared memory.
+//   * the gather (144 table reads per sample) reads the fp32 tables through L1/L2 with paired corner loads.
+#include "common.cuh"
+#include "gridcore.cuh"
+#include "tc5.cuh"
+#include "fused_head.cuh"
+
+namespace b2n {
+using namespace tc5;
+
+// ---------------------------------------------------------------------------------------------------
+// weight packing: fp32 nn.Linear weights [out,in] -> fp16 SWIZZLE_128B K-major image (+ small fp32 vectors)
+// ---------------------------------------------------------------------------------------------------
+struct PackRegion { const float *src; uint32_t byte_off, rows, src_rows, ld, col0, kvalid, row_shift; };
+struct PackArgs { PackRegion r[12]; uint32_t n; };
+
+__global__ void __launch_bounds__(256) k_pack_head(const __grid_constant__ PackArgs pa, uint8_t *__restrict__ img) {
+    // one thread per 16-byte chunk (8 halves) of the image
+    uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = 0; i < pa.n; i++) {
+        const PackRegion &g = pa.r[i];
+        const uint32_t nchunks = g.rows * 8u;
+        if (chunk < nchunks) {
+            const uint32_t row = chunk >> 3, c = chunk & 7u;
+            // row_shift rotates source rows (used to move sigma_net's density logit from row 0 to row 64)
+            const uint32_t srow = g.row_shift ? (row < g.src_rows ? (row + g.row_shift) % g.src_rows : row) : row;
+            __half h[8];
+#pragma unroll
+            for (uint32_t k = 0; k < 8; k++) {
+                const uint32_t kk = c * 8u + k;
+                const float v = (g.src && row < g.src_rows && kk < g.kvalid) ? g.src[(size_t)srow * g.ld + g.col0 + kk] : 0.0f;
+                h[k] = __float2half_rn(v);
+            }
+            *reinterpret_cast<uint4 *>(img + g.byte_off + sw128_offset(row, c)) = *reinterpret_cast<uint4 *>(h);
+            return;
+        }
+        chunk -= nchunks;
+    }
+}
+
+// small vectors: eye_w1[16], unc_w1[32], color ind part [64][4] — stored as fp32 values already rounded to fp16
+__global__ void k_pack_small(const float *__restrict__ eye_w1, const float *__restrict__ unc_w1, const float *__restrict__ color_w0, float *__restrict__ out) {
+    const uint32_t t = threadIdx.x;
+    auto rh = [](float v) { return __half2float(__float2half_rn(v)); };
+    if (t < 16) out[HS_EYE_W1 + t] = rh(eye_w1[t]);
+    if (t < 32) out[HS_UNC_W1 + t] = unc_w1 ? rh(unc_w1[t]) : 0.0f;
+    for (uint32_t i = t; i < 256; i += blockDim.x) out[HS_IND_W + i] = rh(color_w0[(i >> 2) * 84 + 80 + (i & 3)]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+// write 32 consecutive hidden units (columns k0..k0+31 of this row) as fp16 into a SW128 operand tile
+template <bool RELU>
+__device__ __forceinline__ void store_hidden32(uint8_t *tile, uint32_t row, uint32_t k0, const uint32_t (&acc)[32], const float *bias) {
+#pragma unroll
+    for (uint32_t c = 0; c < 4; c++) {
+        uint32_t w[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+            float a = __uint_as_float(acc[c * 8 + 2 * j]), b = __uint_as_float(acc[c * 8 + 2 * j + 1]);
+            if (bias) { a += bias[k0 + c * 8 + 2 * j]; b += bias[k0 + c * 8 + 2 * j + 1]; }
+            if (RELU) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+            w[j] = pack2(a, b);
+        }
+        *reinterpret_cast<uint4 *>(tile + sw128_offset(row, (k0 >> 3) + c)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// real spherical harmonics, degree 4 (16 terms), fp32 — same polynomials as shencoder.cu:44-67
+__device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.48860251190291987f * y; o[2] = 0.48860251190291987f * z; o[3] = -0.48860251190291987f * x;
+    o[4] = 1.0925484305920792f * xy; o[5] = -1.0925484305920792f * yz; o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    o[7] = -1.0925484305920792f * xz; o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2); o[10] = 2.8906114426405538f * xy * z;
+    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2); o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2); o[14] = 1.4453057213202769f * z * (x2 - y2);
+    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+__device__ __forceinline__ void issue_mma(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr, uint32_t ksteps, uint32_t N, bool accumulate) {
+    const uint32_t idesc = idesc_f16(128, N);
+    for (uint32_t k = 0; k < ksteps; k++)
+        mma_f16_ss(d_tmem, smem_desc_sw128(a_saddr + k * 32u), smem_desc_sw128(b_saddr + k * 32u), idesc, accumulate || k > 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------
+struct HeadSmem {                       // lives after the 1024-aligned weight image and operand tiles
+    float enc_a_h[32];                  // fp16-rounded audio code
+    float eye_w1[16], unc_w1[32], ind_bias[64];
+    Lvl2 lvl[12];
+    float eye_val;
+    uint32_t n_valid;
+    uint32_t tmem_base;
+    uint64_t bar_w;                     // weight image landed
+    uint64_t bar_mma[HG_WGS];           // per-warpgroup MMA completion
+};
+
+__global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_constant__ HeadArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *s_w = base;
+    uint8_t *s_tiles = base + HW_BYTES;
+    HeadSmem &S = *reinterpret_cast<HeadSmem *>(s_tiles + HG_WGS * 2 * HG_TILE_BYTES);
+
+    const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u, warp = tid >> 5;
+    uint8_t *sX = s_tiles + wg * 2 * HG_TILE_BYTES, *sH = sX + HG_TILE_BYTES;
+
+    // ---- one-time setup ------------------------------------------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(&S.bar_w, 1);
+        for (int g = 0; g < HG_WGS; g++) mbar_init(&S.bar_mma[g], 1);
+        fence_mbar_init();
+        mbar_expect_tx(&S.bar_w, HW_BYTES);
+        bulk_g2s(s_w, a.wimg, HW_BYTES, &S.bar_w);
+        S.n_valid = a.n_valid ? (uint32_t)max(0, min((int)a.M, *a.n_valid)) : a.M;
+        S.eye_val = a.eye ? a.eye[0] : 0.0f;
+    }
+    if (warp == 1) tmem_alloc(&S.tmem_base, 512);
+    if (tid >= 64 && tid < 64 + 12) S.lvl[tid - 64] = make_lvl2(a.offsets, tid - 64, a.S, a.H, 0);
+    if (tid >= 128 && tid < 160) S.enc_a_h[tid - 128] = round_h(a.enc_a[tid - 128]);
+    if (tid >= 160 && tid < 176) S.eye_w1[tid - 160] = a.wsmall[HS_EYE_W1 + tid - 160];
+    if (tid >= 192 && tid < 224) S.unc_w1[tid - 192] = a.wsmall[HS_UNC_W1 + tid - 192];
+    if (tid >= 256 && tid < 320) {      // ind-code part of color_net layer 0 folded into a bias (network.py:270)
+        const uint32_t j = tid - 256;
+        float b = 0.0f;
+        if (a.ind_code)
+            for (int q = 0; q < 4; q++) b = fmaf(a.wsmall[HS_IND_W + j * 4 + q], round_h(a.ind_code[q]), b);
+        S.ind_bias[j] = b;
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    mbar_wait(&S.bar_w, 0);
+
+    const uint32_t n_valid = S.n_valid;
+    const uint32_t n_tiles = (n_valid + HG_TILE - 1) / HG_TILE;
+    const uint32_t tmem_wg = S.tmem_base + wg * 128u;                       // this warpgroup's 128 columns
+    const uint32_t tmem_ld = tmem_wg + (((warp & 3u) * 32u) << 16);         // + this warp's lane quarter
+    const uint32_t sX_a = smem_u32(sX), sH_a = smem_u32(sH), sW_a = smem_u32(s_w);
+    uint64_t *bar = &S.bar_mma[wg];
+    uint32_t phase = 0;
+    const uint32_t nA = a.has_unc ? 112u : 80u;
+
+    auto sync_wg = [&]() { bar_sync(1 + wg, 128); };
+    auto mma_done = [&]() { mbar_wait(bar, phase); phase ^= 1u; fence_after_sync(); };
+    // operands written by this warpgroup's threads -> visible to the tensor pipe, then one thread issues
+    auto publish = [&]() { fence_before_sync(); fence_proxy_async(); sync_wg(); };
+
+    for (uint32_t tile = blockIdx.x * HG_WGS + wg; tile < n_tiles; tile += gridDim.x * HG_WGS) {
+        const uint32_t m = tile * HG_TILE + t;
+        const bool live = m < n_valid;
+        // ---- P0: gather 36 tri-plane features -> X (fp16, K padded to 48) ---------------------------------------------
+        float px = 0, py = 0, pz = 0, dxv = 0, dyv = 0, dzv = 1;
+        if (live) {
+            px = __ldcs(a.xyzs + 3 * (size_t)m); py = __ldcs(a.xyzs + 3 * (size_t)m + 1); pz = __ldcs(a.xyzs + 3 * (size_t)m + 2);
+            dxv = __ldcs(a.dirs + 3 * (size_t)m); dyv = __ldcs(a.dirs + 3 * (size_t)m + 1); dzv = __ldcs(a.dirs + 3 * (size_t)m + 2);
+        }
+        {
+            // (x + bound) / (2 bound), fp32, like GridEncoder.forward (grid.py:143)
+            const float two_b = __fmul_rn(2.0f, a.bound);
+            const float ux = __fdiv_rn(__fadd_rn(px, a.bound), two_b), uy = __fdiv_rn(__fadd_rn(py, a.bound), two_b), uz = __fdiv_rn(__fadd_rn(pz, a.bound), two_b);
+            const bool okx = !(ux < 0.0f || ux > 1.0f), oky = !(uy < 0.0f || uy > 1.0f), okz = !(uz < 0.0f || uz > 1.0f);
+#pragma unroll
+            for (uint32_t p = 0; p < 3; p++) {        // split_xyz: xy, yz, xz (network.py:208-212)
+                const float u = (p == 1) ? uy : ux, v = (p == 0) ? uy : uz;
+                const bool ok = live && ((p == 1) ? oky : okx) && ((p == 0) ? oky : okz);
+                const float *tab = a.tab[p];
+                float f[12];
+#pragma unroll
+                for (uint32_t l = 0; l < 12; l++) f[l] = ok ? lvl2_interp(tab, S.lvl[l], u, v) : 0.0f;
+                // features p*12 .. p*12+11 -> halves; 12 halves = 1.5 chunks, handled as 6 packed words at word offset p*6
+#pragma unroll
+                for (uint32_t j = 0; j < 6; j++) {
+                    const uint32_t word = p * 6u + j;                 // 32-bit word index within the row (18 data words)
+                    *reinterpret_cast<uint32_t *>(sX + sw128_offset(t, word >> 2) + (word & 3u) * 4u) = pack2(f[2 * j], f[2 * j + 1]);
+                }
+            }
+            // zero the K padding: words 18..23 (features 36..47)
+#pragma unroll
+            for (uint32_t word = 18; word < 24; word++) *reinterpret_cast<uint32_t *>(sX + sw128_offset(t, word >> 2) + (word & 3u) * 4u) = 0u;
+        }
+        float shv[16];
+        sh4(dxv, dyv, dzv, shv);
+        publish();
+        // ---- P1: [aud hidden | eye hidden | unc hidden] = X * WA[0:nA] --------------------------------------------------
+        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 0, sX_a, sW_a + HW_A, 3, nA, false); mma_commit(bar); }
+        mma_done();
+        float eye_att, unc_out = 0.6931471805599453f;       // testing: log(1 + e^0) (network.py:245,278)
+        {
+            uint32_t acc[32];
+            ld32(tmem_ld + 0, acc); wait_ld(); store_hidden32<true>(sH, t, 0, acc, nullptr);
+            ld32(tmem_ld + 32, acc); wait_ld(); store_hidden32<true>(sH, t, 32, acc, nullptr);
+            uint32_t e16[16];
+            ld16(tmem_ld + 64, e16); wait_ld();
+            float dot = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 16; j++) dot = fmaf(fmaxf(round_h(__uint_as_float(e16[j])), 0.0f), S.eye_w1[j], dot);
+            // sigmoid evaluated on the fp16 logit, result rounded to fp16 (torch.sigmoid on a half tensor)
+            eye_att = round_h(1.0f / (1.0f + expf(-round_h(dot))));
+            if (a.has_unc) {
+                ld32(tmem_ld + 80, acc); wait_ld();
+                float du = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 32; j++) du = fmaf(fmaxf(round_h(__uint_as_float(acc[j])), 0.0f), S.unc_w1[j], du);
+                du = round_h(du);
+                unc_out = logf(1.0f + expf(du));                        // torch.log(1 + torch.exp(.)) in fp32 (network.py:278)
+            }
+        }
+        publish();
+        // ---- P2: att = H * WB ; sigma hidden (enc_x part) = X * WA[112:176] -------------------------------------------
+        if (t == 0) {
+            fence_after_sync();
+            issue_mma(tmem_wg + 0, sH_a, sW_a + HW_B, 4, 32, false);
+            issue_mma(tmem_wg + 64, sX_a, sW_a + HW_A + 112u * 128u, 3, 64, false);
+            mma_commit(bar);
+        }
+        mma_done();
+        float amb_aud;
+        {
+            uint32_t acc[32];
+            ld32(tmem_ld + 0, acc); wait_ld();
+            float n2 = 0.0f;
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const float a0 = round_h(__uint_as_float(acc[2 * j])), a1 = round_h(__uint_as_float(acc[2 * j + 1]));
+                n2 = fmaf(a0, a0, n2); n2 = fmaf(a1, a1, n2);
+                w[j] = pack2(S.enc_a_h[2 * j] * a0, S.enc_a_h[2 * j + 1] * a1);    // enc_w = enc_a * att, fp16 (network.py:285)
+            }
+            amb_aud = sqrtf(n2);                                                    // .norm(dim=-1) in fp32 (network.py:308)
+            // EW operand into X: chunks 0..3 = enc_w, chunk 4 = [e, 0..], chunk 5 = 0   (K = 33 padded to 48)
+#pragma unroll
+            for (uint32_t c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(sX + sw128_offset(t, c)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+            const float e = a.eye ? S.eye_val * eye_att : 0.0f;                     // e = e * eye_att (network.py:291)
+            *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 4)) = make_uint4(pack2(e, 0.0f), 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 5)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        publish();
+        // ---- P3: sigma hidden += [enc_w, e] * WC -------------------------------------------------------------------------
+        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 64, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
+        mma_done();
+        {
+            uint32_t acc[32];
+            ld32(tmem_ld + 64, acc); wait_ld(); store_hidden32<true>(sH, t, 0, acc, nullptr);
+            ld32(tmem_ld + 96, acc); wait_ld(); store_hidden32<true>(sH, t, 32, acc, nullptr);
+        }
+        publish();
+        // ---- P4: sigma layer 1 --------------------------------------------------------------------------------------------
+        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 0, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
+        mma_done();
+        {
+            uint32_t acc[32];
+            ld32(tmem_ld + 0, acc); wait_ld(); store_hidden32<true>(sH, t, 0, acc, nullptr);
+            ld32(tmem_ld + 32, acc); wait_ld(); store_hidden32<true>(sH, t, 32, acc, nullptr);
+        }
+        publish();
+        // ---- P5: sigma layer 2: cols 0..63 = geo_feat, col 64 = density logit (rows rotated at pack time) -----------------
+        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 0, sH_a, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
+        mma_done();
+        float sigma;
+        {
+            uint32_t acc[32];
+            ld32(tmem_ld + 0, acc); wait_ld(); store_hidden32<false>(sH, t, 0, acc, nullptr);
+            ld32(tmem_ld + 32, acc); wait_ld(); store_hidden32<false>(sH, t, 32, acc, nullptr);
+            uint32_t s16[16];
+            ld16(tmem_ld + 64, s16); wait_ld();
+            sigma = expf(round_h(__uint_as_float(s16[0]))) * a.density_scale;       // torch.exp(h[..., 0]) in fp32 (network.py:301)
+            // view-direction SH into X chunks 0,1 (the 16-wide K step of color layer 0)
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) w[j] = pack2(shv[2 * j], shv[2 * j + 1]);
+            *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        publish();
+        // ---- P6: color layer 0 = geo * WF0 + sh * WF1 (+ ind-code bias in the epilogue) -------------------------------------
+        if (t == 0) {
+            fence_after_sync();
+            issue_mma(tmem_wg + 0, sH_a, sW_a + HW_F0, 4, 64, false);
+            issue_mma(tmem_wg + 0, sX_a, sW_a + HW_F1, 1, 64, true);
+            mma_commit(bar);
+        }
+        mma_done();
+        {
+            uint32_t acc[32];
+            ld32(tmem_ld + 0, acc); wait_ld(); store_hidden32<true>(sH, t, 0, acc, S.ind_bias);
+            ld32(tmem_ld + 32, acc); wait_ld(); store_hidden32<true>(sH, t, 32, acc, S.ind_bias);
+        }
+        publish();
+        // ---- P7: color layer 1 (N padded 3 -> 16) -----------------------------------------------------------------------------
+        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 64, sH_a, sW_a + HW_G, 4, 16, false); mma_commit(bar); }
+        mma_done();
+        {
+            uint32_t c16[16];
+            ld16(tmem_ld + 64, c16); wait_ld();
+            if (live) {
+                float rgb[3];
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    // torch.sigmoid(h_color) * (1 + 2*0.001) - 0.001 evaluated on half tensors (network.py:275)
+                    const float s = round_h(1.0f / (1.0f + expf(-round_h(__uint_as_float(c16[j])))));
+                    rgb[j] = round_h(round_h(s * 1.002f) - 0.001f);
+                }
+                if (a.sigmas) __stcs(a.sigmas + m, sigma);
+                if (a.rgbs) { __stcs(a.rgbs + 3 * (size_t)m, rgb[0]); __stcs(a.rgbs + 3 * (size_t)m + 1, rgb[1]); __stcs(a.rgbs + 3 * (size_t)m + 2, rgb[2]); }
+                if (a.amb_aud) __stcs(a.amb_aud + m, amb_aud);
+                if (a.amb_eye) __stcs(a.amb_eye + m, eye_att);
+                if (a.unc) __stcs(a.unc + m, unc_out);
+            }
+        }
+        fence_before_sync();
+        sync_wg();          // all TMEM reads / smem reads of this tile are done before the next tile's gather overwrites X
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(S.tmem_base, 512);
+}
+
+size_t head_smem_bytes() { return 1024 + HW_BYTES + (size_t)HG_WGS * 2 * HG_TILE_BYTES + sizeof(HeadSmem); }
+
+int launch_head_forward(const HeadArgs &a, cudaStream_t st) {
+    static bool attr = false;
+    const size_t smem = head_smem_bytes();
+    if (!attr) { B2N_CUDA(cudaFuncSetAttribute(k_head_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    const uint32_t tiles = ceil_div<uint32_t>(a.M, HG_TILE);
+    uint32_t ctas = ceil_div<uint32_t>(tiles, HG_WGS);
+    const uint32_t sms = (uint32_t)sm_count();
+    if (ctas > sms) ctas = sms;
+    if (ctas == 0) return 0;
+    k_head_forward<<<ctas, HG_THREADS, smem, st>>>(a);
+    return check_launch("head_forward");
+}
+
+}  // namespace b2n
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI: model object (packed weights) + head forward
+// ---------------------------------------------------------------------------------------------------
+using namespace b2n;
+
+struct b2n_model {
+    uint8_t *wimg = nullptr;       // HW_BYTES
+    float *wsmall = nullptr;       // HS_FLOATS
+    b2n_head_weights w = {};
+    bool ready = false;
+};
+
+extern "C" {
+
+int b2n_model_create(b2n_model **out, void *stream) {
+    (void)stream;
+    B2N_REQUIRE(out, "model_create: null pointer");
+    b2n_model *m = new b2n_model();
+    if (cudaMalloc(&m->wimg, HW_BYTES) != cudaSuccess || cudaMalloc(&m->wsmall, sizeof(float) * HS_FLOATS) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (m->wimg) cudaFree(m->wimg);
+        delete m;
+        set_error("model_create: device allocation failed");
+        return 3;
+    }
+    *out = m;
+    return 0;
+}
+
+void b2n_model_destroy(b2n_model *m) {
+    if (!m) return;
+    cudaFree(m->wimg);
+    cudaFree(m->wsmall);
+    delete m;
+}
+
+int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
+    B2N_REQUIRE(m && w, "model_update: null pointer");
+    B2N_REQUIRE(w->table_xy && w->table_yz && w->table_xz && w->offsets, "model_update: null table pointer");
+    B2N_REQUIRE(w->aud_att_w0 && w->aud_att_w1 && w->eye_att_w0 && w->eye_att_w1 && w->sigma_w0 && w->sigma_w1 && w->sigma_w2 && w->color_w0 && w->color_w1,
+                "model_update: null weight pointer");
+    B2N_REQUIRE((w->unc_w0 == nullptr) == (w->unc_w1 == nullptr), "model_update: unc_w0 / unc_w1 must both be given or both be NULL");
+    PackArgs pa = {};
+    uint32_t n = 0;
+    auto add = [&](const float *src, uint32_t off, uint32_t rows, uint32_t src_rows, uint32_t ld, uint32_t col0, uint32_t kvalid, uint32_t shift) {
+        pa.r[n++] = PackRegion{src, off, rows, src_rows, ld, col0, kvalid, shift};
+    };
+    add(w->aud_att_w0, HW_A, 64, 64, 36, 0, 36, 0);
+    add(w->eye_att_w0, HW_A + 64 * 128, 16, 16, 36, 0, 36, 0);
+    add(w->unc_w0, HW_A + 80 * 128, 32, 32, 36, 0, 36, 0);                 // NULL src -> zeros
+    add(w->sigma_w0, HW_A + 112 * 128, 64, 64, 69, 0, 36, 0);
+    add(w->aud_att_w1, HW_B, 32, 32, 64, 0, 64, 0);
+    add(w->sigma_w0, HW_C, 64, 64, 69, 36, 33, 0);
+    add(w->sigma_w1, HW_D, 64, 64, 64, 0, 64, 0);
+    add(w->sigma_w2, HW_E, 80, 65, 64, 0, 64, 1);                          // rotate: rows 0..63 = geo (src 1..64), row 64 = logit (src 0)
+    add(w->color_w0, HW_F0, 64, 64, 84, 16, 64, 0);                        // geo_feat columns 16..79
+    add(w->color_w0, HW_F1, 64, 64, 84, 0, 16, 0);                         // SH columns 0..15
+    add(w->color_w1, HW_G, 16, 3, 64, 0, 64, 0);
+    pa.n = n;
+    cudaStream_t st = as_stream(stream);
+    k_pack_head<<<ceil_div<uint32_t>(HW_BYTES / 16, 256), 256, 0, st>>>(pa, m->wimg);
+    if (check_launch("model_update(pack)")) return 1;
+    k_pack_small<<<1, 256, 0, st>>>(w->eye_att_w1, w->unc_w1, w->color_w0, m->wsmall);
+    if (check_launch("model_update(small)")) return 1;
+    m->w = *w;
+    m->ready = true;
+    return 0;
+}
+
+}  // extern "C"
+
+namespace b2n {
+int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
+                          const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, cudaStream_t st) {
+    B2N_REQUIRE(m && m->ready, "head_forward: model has no weights (call b2n_model_update)");
+    B2N_REQUIRE(xyzs && dirs && enc_a, "head_forward: null pointer");
+    if (M == 0) return 0;
+    HeadArgs a = {};
+    a.xyzs = xyzs; a.dirs = dirs; a.M = M; a.n_valid = n_valid;
+    a.tab[0] = m->w.table_xy; a.tab[1] = m->w.table_yz; a.tab[2] = m->w.table_xz;
+    a.offsets = m->w.offsets; a.S = m->w.S; a.H = m->w.H; a.bound = m->w.bound;
+    a.wimg = m->wimg; a.wsmall = m->wsmall;
+    a.enc_a = enc_a; a.ind_code = ind_code; a.eye = eye;
+    a.sigmas = sigmas; a.rgbs = rgbs; a.amb_aud = amb_aud; a.amb_eye = amb_eye; a.unc = unc;
+    a.has_unc = m->w.unc_w0 != nullptr;
+    a.density_scale = density_scale;
+    return launch_head_forward(a, st);
+}
+}  // namespace b2n
+
+extern "C" {
+
+int b2n_head_forward(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
+                     const int32_t *n_valid, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, void *stream) {
+    return head_forward_on_model(m, xyzs, dirs, M, enc_a, ind_code, eye, n_valid, 1.0f, sigmas, rgbs, amb_aud, amb_eye, unc, as_stream(stream));
+}
+
+}  // extern "C"

@@ -60,7 +60,7 @@ for name in ("head16", "cascade2", "nogamma"):
     # capped buffer: rays whose segment would overflow M are dropped (raymarching.cu:457); which ones depends on the
     # atomic order, so only the invariant totals are stored
     # inference march: first 512 rays, 4 steps each, resuming from nears
-    n_alive, n_step = 512, 4
+    n_alive, n_step = min(256, c["rays_o"].shape[0]), 4
     alive = torch.arange(n_alive, dtype=torch.int32, device="cuda")
     M = n_alive * n_step; M += 128 - M % 128
     ox, od, ol = (torch.zeros(M, k, device="cuda") for k in (3, 3, 2))

@@ -88,3 +88,18 @@ def test_no_cpu_fallback():
             if fn.endswith(".py"):
                 src = open(os.path.join(root, fn)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f"{fn} imports the test oracle"
+
+
+def test_head_model_state_dict_matches_reference_names_and_count():
+    """#parameters = 683 509 for the HuBERT head model (test.ipynb:269) and reference parameter names."""
+    from b2nerf.model import HeadModel
+    m = HeadModel(audio_in_dim=1024)
+    assert sum(p.numel() for p in m.parameters()) == 683509
+    assert sum(p.numel() for p in HeadModel(audio_in_dim=29).parameters()) == 587989
+    sd = m.state_dict()
+    for k, shape in {"encoder_xy.embeddings": (163584, 1), "encoder_yz.offsets": (13,), "sigma_net.net.0.weight": (64, 69), "sigma_net.net.2.weight": (65, 64),
+                     "color_net.net.0.weight": (64, 84), "color_net.net.1.weight": (3, 64), "unc_net.net.1.weight": (1, 32), "aud_ch_att_net.net.1.weight": (32, 64),
+                     "eye_att_net.net.0.weight": (16, 36), "audio_net.encoder_conv.0.weight": (32, 1024, 3), "audio_net.encoder_fc1.2.weight": (32, 64),
+                     "audio_att_net.attentionConvNet.8.weight": (1, 2, 3), "audio_att_net.attentionNet.0.weight": (8, 8), "individual_codes": (10000, 4),
+                     "density_bitfield": (262144,), "density_grid": (1, 2097152), "step_counter": (16, 2), "aabb_infer": (6,)}.items():
+        assert tuple(sd[k].shape) == shape, k
