@@ -141,6 +141,10 @@ int b2n_grid_encode_backward(const void *grad, const float *inputs, const void *
         uint32_t H, const void *dy_dx, void *grad_inputs, uint32_t gridtype, int align_corners,
         b2n_dtype dtype, void *stream);
 
+/* scales_out[l] = exp2f(l*S)*H - 1 for l < L, computed with the kernels' own arithmetic (ex2.approx + fma, as the reference's
+ * gridencoder.cu:125 compiles to): a diagnostic that lets a CPU checker reproduce fp32 encodings bit for bit */
+int b2n_grid_level_scales(float S, uint32_t H, uint32_t L, float *scales_out, void *stream);
+
 /* ---- spherical harmonics (shencoder.h:9-10) ------------------------------------------------------- */
 /* inputs [B,3]; outputs [B,degree^2]; dy_dx [B,3*degree^2] or NULL; degree in 1..8 */
 int b2n_sh_encode_forward(const float *inputs, float *outputs, uint32_t B, uint32_t D, uint32_t degree,

@@ -277,6 +277,12 @@ __global__ void __launch_bounds__(256) k_grid_input_bwd(const T *__restrict__ gr
     grad_inputs[t] = from_f<T>(r);
 }
 
+// per-level scales exactly as the kernels compute them (ex2.approx + fma) — lets a CPU checker use the GPU's bits
+__global__ void k_level_scales(float S, uint32_t H, uint32_t L, float *__restrict__ out) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < L) out[l] = __fmaf_rn(exp2f(__fmul_rn((float)l, S)), (float)H, -1.0f);
+}
+
 template <typename T, uint32_t D>
 static int fwd_dispatch_c(const float *inputs, const T *table, const int32_t *offsets, T *outputs, uint32_t B, uint32_t C, uint32_t L, float S, uint32_t H,
                           T *dy_dx, uint32_t gridtype, bool ac, cudaStream_t st) {
@@ -346,6 +352,13 @@ int b2n_grid_encode_forward(const float *inputs, const void *embeddings, const i
         return fwd_dispatch<__half>(inputs, (const __half *)embeddings, offsets, (__half *)outputs, B, D, C, L, S, H, (__half *)dy_dx, gridtype, align_corners != 0, as_stream(stream));
     set_error("grid_encode_forward: embeddings must be float32 or float16");
     return 2;
+}
+
+int b2n_grid_level_scales(float S, uint32_t H, uint32_t L, float *scales_out, void *stream) {
+    B2N_REQUIRE(scales_out, "grid_level_scales: null pointer");
+    if (L == 0) return 0;
+    k_level_scales<<<ceil_div<uint32_t>(L, 64), 64, 0, as_stream(stream)>>>(S, H, L, scales_out);
+    return check_launch("grid_level_scales");
 }
 
 int b2n_grid_encode_backward(const void *grad, const float *inputs, const void *embeddings, const int32_t *offsets, void *grad_embeddings, uint32_t B,

@@ -30,5 +30,12 @@ def grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, 
          gridtype, int(bool(align_corners)), code, stream_ptr(inputs))
 
 
+def grid_level_scales(S, H, L, device="cuda"):
+    """Per-level scales exp2f(l*S)*H - 1 with the kernels' own arithmetic (diagnostic; not part of the reference surface)."""
+    out = torch.empty(L, dtype=torch.float32, device=device)
+    call("b2n_grid_level_scales", float(S), H, L, out.data_ptr(), stream_ptr(out))
+    return out
+
+
 _backend = types.SimpleNamespace(grid_encode_forward=grid_encode_forward, grid_encode_backward=grid_encode_backward)
 __all__ = ["_backend"]

@@ -138,6 +138,15 @@ for name in cases.GRID_CASES:
     ge.grid_encode_backward(T(c["grad"]), x, emb, offs, gemb, B, D, C, L, c["S"], c["H"], dy, gin, c["gridtype"], c["align_corners"])
     save("grid_" + name, outputs=npy(out), dy_dx=npy(dy), grad_embeddings=npy(gemb), grad_inputs=npy(gin))
 
+# per-level scales as the GPU computes them (through libb2nerf's diagnostic entry point; same ex2.approx + fma as the reference kernel —
+# verified by the bit-exact grid outputs above) so the CPU oracle can reproduce the fp32 encodings bit for bit
+from gridencoder.backend import grid_level_scales  # noqa: E402
+sc = {}
+for name in cases.GRID_CASES:
+    c = cases.grid_case(name)
+    sc[f"S{np.float32(c['S']).view(np.uint32):08x}_H{c['H']}_L{c['L']}"] = npy(grid_level_scales(c["S"], c["H"], c["L"]))
+save("level_scales", **sc)
+
 # ---- SH / freq ----------------------------------------------------------------------------------------------------
 dirs = cases.dirs_case(256, 3); arrs = {}
 raw = (np.random.default_rng(4).standard_normal((64, 3)) * 0.7).astype(np.float32)       # un-normalised inputs: polynomials, not unit-sphere values

@@ -124,7 +124,8 @@ def _loop_reference(m, rays_o, rays_d, enc_a, c, e, fused_net, max_steps=16, dt_
         else:
             with torch.autocast("cuda", dtype=torch.float16):
                 sig, rgb, aa, ae, un = m.forward_unfused(xyzs, dirs, enc_a, c, e)
-        raymarching.composite_rays_triplane(n_alive, n_step, alive, rays_t, sig, rgb, deltas, aa, ae, un, ws, depth, image, s_aud, s_eye, s_unc, T_thresh)
+        with torch.autocast("cuda", dtype=torch.float16):      # the reference renders inside autocast: custom_fwd casts the fp16 outputs to fp32
+            raymarching.composite_rays_triplane(n_alive, n_step, alive, rays_t, sig, rgb, deltas, aa, ae, un, ws, depth, image, s_aud, s_eye, s_unc, T_thresh)
         alive = alive[alive >= 0]
         step += n_step
     image = (image + (1 - ws).unsqueeze(-1) * 1.0).clamp(0, 1)

@@ -54,7 +54,7 @@ def test_morton_packbits_dilation_exact(rm):
     odd = (rng.random((1, 8 * 37)) * 20).astype(np.float32)            # byte count not a multiple of 4: tail path
     assert np.array_equal(npy(rm.packbits(T(odd), 10.0)), oracle.packbits(odd, 10.0))
     into = torch.zeros(37, dtype=torch.uint8, device="cuda")
-    assert rm.packbits(T(odd), 10.0, into) is into and np.array_equal(npy(into), oracle.packbits(odd, 10.0))
+    assert rm.packbits(T(odd), 10.0, into).data_ptr() == into.data_ptr() and np.array_equal(npy(into), oracle.packbits(odd, 10.0))
     g2 = rng.standard_normal((2, 32 ** 3)).astype(np.float32)
     assert np.array_equal(npy(rm.morton3D_dilation(T(g2))), oracle.morton3D_dilation(g2, 2, 32))
 
@@ -317,12 +317,19 @@ def test_grid_encode(ref, name):
     emb, x, offs = T(c["embeddings"]), T(c["inputs"]), T(c["offsets"])
     out = torch.empty(L, B, C, device="cuda", dtype=dt); dy = torch.empty(B, L * D * C, device="cuda", dtype=dt)
     _backend.grid_encode_forward(x, emb, offs, out, B, D, C, L, c["S"], c["H"], dy, c["gridtype"], c["align_corners"])
-    o_out, o_dy = oracle.grid_encode_forward(c["inputs"], c["embeddings"], c["offsets"], c["S"], c["H"], c["gridtype"], c["align_corners"], True, c["half"])
-    # vs CPU oracle: libm exp2f vs ex2.approx can move the level scale by an ulp -> 1e-5 abs on O(1) table values (fp32), 2e-3 for fp16 tables
-    tol = dict(rtol=0, atol=2e-3) if c["half"] else dict(rtol=0, atol=2e-5)
-    np.testing.assert_allclose(npy(out).astype(np.float32), o_out.astype(np.float32), **tol)
+    # the oracle is fed the per-level scales the GPU computes (ex2.approx), so the fp32 encoding must match bit for bit
+    from gridencoder.backend import grid_level_scales
+    oracle.set_level_scales(npy(grid_level_scales(c["S"], c["H"], L)))
+    try:
+        o_out, o_dy = oracle.grid_encode_forward(c["inputs"], c["embeddings"], c["offsets"], c["S"], c["H"], c["gridtype"], c["align_corners"], True, c["half"])
+    finally:
+        oracle.set_level_scales(None)
     scale_top = 2.0 ** (c["S"] * (L - 1)) * c["H"]
-    np.testing.assert_allclose(npy(dy).astype(np.float32), o_dy.astype(np.float32), rtol=0, atol=(8.0 if c["half"] else 2e-4) * scale_top / 64)
+    if c["half"]:      # fp16 tables: half rounding after every corner; tolerance 1e-3-class (north star), derivative scaled by the top-level resolution
+        np.testing.assert_allclose(npy(out).astype(np.float32), o_out.astype(np.float32), rtol=0, atol=2e-3)
+        np.testing.assert_allclose(npy(dy).astype(np.float32), o_dy.astype(np.float32), rtol=2e-2, atol=8.0 * scale_top / 64)
+    else:
+        assert np.array_equal(npy(out), o_out) and np.array_equal(npy(dy), o_dy)
     assert float(out[:, 2].abs().sum()) == 0 and float(out[:, 3].abs().sum()) == 0     # out-of-range rows -> zeros
     gemb = torch.zeros_like(emb); gin = torch.zeros(B, D, device="cuda", dtype=dt)
     _backend.grid_encode_backward(T(c["grad"]), x, emb, offs, gemb, B, D, C, L, c["S"], c["H"], dy, gin, c["gridtype"], c["align_corners"])
@@ -358,8 +365,13 @@ def test_grid_encoder_module_triplane_autograd():
     w = torch.randn_like(y)
     (y * w).sum().backward()
     S = float(np.log2(enc.per_level_scale))
-    o_out, _ = oracle.grid_encode_forward(npy((x + 1) / 2), npy(enc.embeddings), npy(enc.offsets), S, 64)
-    np.testing.assert_allclose(npy(y), o_out.transpose(1, 0, 2).reshape(5000, 12), rtol=0, atol=2e-5)
+    from gridencoder.backend import grid_level_scales
+    oracle.set_level_scales(npy(grid_level_scales(S, 64, 12)))
+    try:
+        o_out, _ = oracle.grid_encode_forward(npy((x + 1) / 2), npy(enc.embeddings), npy(enc.offsets), S, 64)
+    finally:
+        oracle.set_level_scales(None)
+    assert np.array_equal(npy(y), o_out.transpose(1, 0, 2).reshape(5000, 12))
     o_ge, _ = oracle.grid_encode_backward(npy(w).reshape(5000, 12, 1).transpose(1, 0, 2), npy((x + 1) / 2), npy(enc.offsets), 1, S, 64)
     np.testing.assert_allclose(npy(enc.embeddings.grad), o_ge, rtol=1e-4, atol=1e-4)
 
