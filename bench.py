@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native NeRF hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (libb2nerf.so); torchrun launches it for N > 1
+    python bench.py --impl reference --gpus N --steps K ...   # the repo's ops as pure PyTorch on the host cores (CPU arm)
+
+Workload at every N (BASELINE.json configs[1] / configs[3]): one step = one 512x512 talking-head frame per GPU — AudioNet+AudioAttNet,
+near/far, the 16-step occupancy march / tri-plane encode / head MLPs / composite loop, background blend — random-init weights, the
+synthetic head-sized density blob of SURVEY §8d, `max_steps 16, dt_gamma 1/256, bound 1`.  Frames are independent, so N GPUs render
+N frames per step (weak scaling, no data-path collective).
+
+One JSON line on stdout (rank 0).  `value` = frames/s with the rays already in HBM; `e2e` = the same through FrameRenderer.render_host
+with pinned HOST buffers (rays + audio window up, fp32 image down, every frame); `roofline` = the fused tcgen05 head kernel;
+`cpu_baseline` = oracle/torch_port.py on a bounded sample of the same frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "lzzx-nerf_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+HW = 512
+N_RAYS = HW * HW
+POOL = 24                      # distinct frames cycled through: 24 x 6.3 MB of rays = 151 MB > 126 MB L2
+METRIC = "infer_512x512_frames_per_sec"
+MACS_PER_SAMPLE_INFER = 23184  # SURVEY §8a a7 (no unc_net at inference)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        self.cmd = ["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"]
+        self.rows, self.proc = [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_inputs(rank):
+    from b2nerf import scene
+    frames = [scene.frame_rays(frame=rank * 1000 + f) for f in range(POOL)]
+    auds = [scene.audio_window(frame=rank * 1000 + f) for f in range(POOL)]
+    bitfield = scene.bitfield_from_grid(scene.density_grid())
+    return frames, auds, bitfield
+
+
+def build_model(device=None):
+    from b2nerf.model import HeadModel
+    torch.manual_seed(0)
+    m = HeadModel(audio_in_dim=1024)       # random-init weights of the reference architecture (683 509 parameters)
+    m.testing = True
+    return m if device is None else m.to(device)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# CPU arm: the repo's ops as pure PyTorch on the host cores
+# ------------------------------------------------------------------------------------------------------------------------------
+def cpu_frames_per_sec(rows, steps, warmup):
+    """Times oracle/torch_port.render_frame on a `rows`-row band of the 512x512 frame; returns (frames/s equivalent, seconds/step, samples)."""
+    from oracle import torch_port as tp
+    from b2nerf import scene
+    torch.set_num_threads(os.cpu_count())
+    m = build_model()
+    p = tp.params_from_state_dict(m.state_dict())
+    bf = torch.from_numpy(scene.bitfield_from_grid(scene.density_grid()))
+    r0 = (HW - rows) // 2
+    aabb = torch.from_numpy(scene.AABB)
+    times, ns = [], 0
+    with torch.no_grad():
+        for s in range(warmup + steps):
+            o, d = scene.frame_rays(frame=s)
+            o = torch.from_numpy(o).view(HW, HW, 3)[r0:r0 + rows].reshape(-1, 3)
+            d = torch.from_numpy(d).view(HW, HW, 3)[r0:r0 + rows].reshape(-1, 3)
+            auds = torch.from_numpy(scene.audio_window(frame=s))
+            t0 = time.perf_counter()
+            enc_a = m.encode_audio(auds)[0]
+            _, _, _, ns = tp.render_frame(p, o, d, bf, enc_a, m.individual_codes[0].detach(), torch.tensor([0.4]), aabb)
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                times.append(dt)
+    sec = float(np.mean(times))
+    return (rows / HW) / sec, sec, ns
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    rows = 64
+    fps, sec, ns = cpu_frames_per_sec(rows, args.steps, max(args.warmup, 1))
+    cores = os.cpu_count()
+    sample = f"central {rows}-row band of the 512x512 frame ({rows * HW} of {N_RAYS} rays, {ns} samples) per step, pure-PyTorch fp32 port (oracle/torch_port.py)"
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "infer_512x512_frame", "note": "the reference has no CPU path for these ops (SURVEY §8d); this arm is the pure-PyTorch port on host cores"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------------------
+def head_kernel_profile(model, renderer, frames, auds, steps):
+    """Separate instrumented pass (no CUDA graph): CUDA events on the launching stream around every fused-head launch of `steps` frames.
+    Returns (total head ms, launches, total samples evaluated)."""
+    from b2nerf import lib
+    L = lib()
+    stream = torch.cuda.current_stream()
+    dev = renderer.dev
+    N = renderer.N
+    cfg_kw = renderer.kw
+    total_ms, launches, samples = 0.0, 0, 0
+    import raymarching
+    with torch.no_grad():
+        for s in range(steps):
+            o, d = frames[s % POOL]
+            rays_o, rays_d = o, d
+            with torch.autocast("cuda", dtype=torch.float16):
+                enc_a = model.encode_audio(auds[s % POOL]).float()
+            nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, model.aabb_infer, 0.05)
+            ws, depth, image = torch.zeros(N, device=dev), torch.zeros(N, device=dev), torch.zeros(N, 3, device=dev)
+            sa, se, su = torch.zeros(N, device=dev), torch.zeros(N, device=dev), torch.zeros(N, device=dev)
+            alive = torch.arange(N, dtype=torch.int32, device=dev); rays_t = nears.clone()
+            step = 0
+            while step < cfg_kw["max_steps"]:
+                n_alive = alive.shape[0]
+                if n_alive <= 0:
+                    break
+                n_step = max(min(N // n_alive, 8), 1)
+                xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, alive, rays_t, rays_o, rays_d, model.bound, model.density_bitfield, model.cascade,
+                                                            model.grid_size, nears, fars, 128, False, cfg_kw["dt_gamma"], cfg_kw["max_steps"])
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                sig, rgb, aa, ae, un = model(xyzs, dirs, enc_a, renderer.ind_code, renderer.eye)
+                e1.record(stream)
+                raymarching.composite_rays_triplane(n_alive, n_step, alive, rays_t, sig, rgb, deltas, aa, ae, un, ws, depth, image, sa, se, su, cfg_kw["T_thresh"])
+                alive = alive[alive >= 0]
+                e1.synchronize()
+                total_ms += e0.elapsed_time(e1); launches += 1; samples += n_alive * n_step
+                step += n_step
+    return total_ms, launches, samples
+
+
+def run_gpu_arm(args, rank, world, local_rank):
+    from b2nerf import lib
+    from b2nerf.render import FrameRenderer
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    frames_np, auds_np, bitfield = synthetic_inputs(rank)
+    model = build_model(dev)
+    model.density_bitfield.copy_(torch.from_numpy(bitfield).to(dev))
+    r = FrameRenderer(model, N_RAYS, use_graph=not args.no_graph)
+    frames = [(torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)) for o, d in frames_np]
+    auds = [torch.from_numpy(a).to(dev) for a in auds_np]
+    host_o = [torch.from_numpy(o).pin_memory() for o, _ in frames_np]
+    host_d = [torch.from_numpy(d).pin_memory() for _, d in frames_np]
+    host_a = [torch.from_numpy(a).pin_memory() for a in auds_np]
+    out_host = torch.empty(N_RAYS, 3).pin_memory()
+    L = lib()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for s in range(warmup):
+            fn(s)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.launch_count()
+        e0.record()
+        for s in range(steps):
+            fn(warmup + s)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, L.launch_count() - l0
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    dev_ms, launches = timed(lambda s: r.render_device(frames[s % POOL][0], frames[s % POOL][1], auds[s % POOL]), args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    e2e_ms, _ = timed(lambda s: r.render_host(host_o[s % POOL], host_d[s % POOL], host_a[s % POOL], out_host), args.steps, args.warmup)
+    if rank != 0:
+        return
+    img = out_host.numpy()
+    assert np.isfinite(img).all() and 0.0 < float(img.mean()) <= 1.0
+    value = world * args.steps / (dev_ms * 1e-3)
+    e2e = world * args.steps / (e2e_ms * 1e-3)
+    pk, pk_src = peaks()
+    head_ms, head_launches, head_samples = head_kernel_profile(model, r, frames, auds, min(args.steps, 8))
+    flops = 2.0 * MACS_PER_SAMPLE_INFER * head_samples
+    achieved = flops / (head_ms * 1e-3) / 1e12
+    peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "infer_512x512_frame", "rays_per_frame": N_RAYS, "max_steps": 16, "dt_gamma": 1 / 256, "bound": 1,
+                   "params": 683509, "weights": "random-init", "frames_per_gpu_per_step": 1, "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                   "l2": f"inputs cycle through {POOL} distinct frames ({POOL * N_RAYS * 24 / 1e6:.0f} MB of rays) > 126 MB L2", "cuda_graph": not args.no_graph},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": r.h2d_bytes(), "d2h_bytes_per_step": r.d2h_bytes(), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "k_head_forward (fused tri-plane gather + 7 tcgen05 layers)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": pk_src + " (bf16 sustained)",
+                     "how": f"CUDA events on the launching stream around each of {head_launches} head launches of {min(args.steps, 8)} frames "
+                            f"(separate un-graphed pass of the same frames), {head_samples} samples x {2 * MACS_PER_SAMPLE_INFER} FLOP",
+                     "head_ms_per_frame": head_ms / min(args.steps, 8), "samples_per_frame": head_samples / min(args.steps, 8)},
+    }
+    if world == 1 and not args.no_cpu:
+        rows = 32
+        fps, sec, ns = cpu_frames_per_sec(rows, 2, 1)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"central {rows}-row band of one 512x512 frame ({rows * HW} rays, {ns} samples), mean of 2 after 1 warm-up, pure-PyTorch fp32 (oracle/torch_port.py)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b2nerf", choices=["b2nerf", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b2nerf" else args.warmup
+    rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    run_gpu_arm(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
