@@ -52,6 +52,7 @@ class ClockSampler(threading.Thread):
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         self.cmd = ["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"]
         self.rows, self.proc = [], None
+        self.cmd[-1] = "50"
 
     def run(self):
         try:
@@ -60,6 +61,11 @@ class ClockSampler(threading.Thread):
                 self.rows.append([c.strip() for c in line.split(",")])
         except Exception:
             pass
+
+    def wait_first(self, timeout=10.0):
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
 
     def stop(self):
         if self.proc is not None:
@@ -229,7 +235,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.3)
+        sampler.wait_first()
     dev_ms, launches = timed(lambda s: r.render_device(frames[s % POOL][0], frames[s % POOL][1], auds[s % POOL]), args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
     e2e_ms, _ = timed(lambda s: r.render_host(host_o[s % POOL], host_d[s % POOL], host_a[s % POOL], out_host), args.steps, args.warmup)
@@ -251,7 +257,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                    "params": 683509, "weights": "random-init", "frames_per_gpu_per_step": 1, "parallelism": f"frames sharded over {world} GPU(s), no collective",
                    "l2": f"inputs cycle through {POOL} distinct frames ({POOL * N_RAYS * 24 / 1e6:.0f} MB of rays) > 126 MB L2", "cuda_graph": not args.no_graph},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": r.h2d_bytes(), "d2h_bytes_per_step": r.d2h_bytes(), "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) if r.graph is None else int(r.launches_per_frame * args.steps),
         "clocks": clocks,
         "roofline": {"kernel": "k_head_forward (fused tri-plane gather + 7 tcgen05 layers)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": pk_src + " (bf16 sustained)",

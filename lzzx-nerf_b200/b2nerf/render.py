@@ -26,6 +26,7 @@ class FrameRenderer:
         self.ind_code = model.individual_codes[ind_index:ind_index + 1].detach().clone()
         self.image = torch.empty(self.N, 3, device=d)
         self.graph = None
+        self.launches_per_frame = None
         model.cache_host_constants()
         model.pack()
         if use_graph:
@@ -45,9 +46,12 @@ class FrameRenderer:
                 self._device_frame()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
+        from ._lib import lib
         g = torch.cuda.CUDAGraph()
+        n0 = lib().launch_count()
         with torch.cuda.graph(g):
             self._device_frame()
+        self.launches_per_frame = lib().launch_count() - n0      # libb2nerf kernel nodes replayed per frame (torch's audio-net kernels not counted)
         self.graph = g
 
     @torch.no_grad()

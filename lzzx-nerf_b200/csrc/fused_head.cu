@@ -130,6 +130,9 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
     HeadSmem &S = *reinterpret_cast<HeadSmem *>(s_tiles + HG_WGS * 2 * HG_TILE_BYTES);
 
     const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u, warp = tid >> 5;
+    // nothing to do (a loop iteration after the frame finished): leave before touching TMEM / the weight image
+    const uint32_t n_valid_early = a.n_valid ? (uint32_t)max(0, min((int)a.M, __ldg(a.n_valid))) : a.M;
+    if (n_valid_early <= blockIdx.x * HG_WGS * HG_TILE) return;
     uint8_t *sX = s_tiles + wg * 2 * HG_TILE_BYTES, *sH = sX + HG_TILE_BYTES;
 
     // ---- one-time setup ------------------------------------------------------------------------------------------
