@@ -72,20 +72,27 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);
 }
-// write 32 consecutive hidden units (columns k0..k0+31 of this row) as fp16 into a SW128 operand tile
-template <bool RELU>
-__device__ __forceinline__ void store_hidden32(uint8_t *tile, uint32_t row, uint32_t k0, const uint32_t (&acc)[32], const float *bias) {
+// TMEM -> fp16 operand tile: reads `ncols` accumulator columns of this thread's row starting at TMEM address `taddr`, applies
+// (+bias, ReLU) and writes them as halves k0.. of row `row` of a SWIZZLE_128B tile.  Deliberately NOT inlined and rolled over
+// 16-column blocks: the kernel has five of these epilogues and four warpgroups in different phases, so code size (I-cache
+// footprint) matters more than the few loop instructions.
+__device__ __noinline__ void hidden_epilogue(uint32_t taddr, uint32_t ncols, uint8_t *tile, uint32_t row, uint32_t k0, bool relu, const float *bias) {
+#pragma unroll 1
+    for (uint32_t cb = 0; cb < ncols; cb += 16) {
+        uint32_t acc[16];
+        ld16(taddr + cb, acc);
+        wait_ld();
+        uint32_t w[8];
 #pragma unroll
-    for (uint32_t c = 0; c < 4; c++) {
-        uint32_t w[4];
-#pragma unroll
-        for (uint32_t j = 0; j < 4; j++) {
-            float a = __uint_as_float(acc[c * 8 + 2 * j]), b = __uint_as_float(acc[c * 8 + 2 * j + 1]);
-            if (bias) { a += bias[k0 + c * 8 + 2 * j]; b += bias[k0 + c * 8 + 2 * j + 1]; }
-            if (RELU) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+        for (uint32_t j = 0; j < 8; j++) {
+            float a = __uint_as_float(acc[2 * j]), b = __uint_as_float(acc[2 * j + 1]);
+            if (bias) { a += bias[cb + 2 * j]; b += bias[cb + 2 * j + 1]; }
+            if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
             w[j] = pack2(a, b);
         }
-        *reinterpret_cast<uint4 *>(tile + sw128_offset(row, (k0 >> 3) + c)) = make_uint4(w[0], w[1], w[2], w[3]);
+        const uint32_t c0 = (k0 + cb) >> 3;
+        *reinterpret_cast<uint4 *>(tile + sw128_offset(row, c0)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4 *>(tile + sw128_offset(row, c0 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
     }
 }
 
@@ -102,7 +109,7 @@ __device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {
     o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
 
-__device__ __forceinline__ void issue_mma(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr, uint32_t ksteps, uint32_t N, bool accumulate) {
+__device__ __noinline__ void issue_mma(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr, uint32_t ksteps, uint32_t N, bool accumulate) {
     const uint32_t idesc = idesc_f16(128, N);
     for (uint32_t k = 0; k < ksteps; k++)
         mma_f16_ss(d_tmem, smem_desc_sw128(a_saddr + k * 32u), smem_desc_sw128(b_saddr + k * 32u), idesc, accumulate || k > 0);
@@ -190,19 +197,19 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             const float two_b = __fmul_rn(2.0f, a.bound);
             const float ux = __fdiv_rn(__fadd_rn(px, a.bound), two_b), uy = __fdiv_rn(__fadd_rn(py, a.bound), two_b), uz = __fdiv_rn(__fadd_rn(pz, a.bound), two_b);
             const bool okx = !(ux < 0.0f || ux > 1.0f), oky = !(uy < 0.0f || uy > 1.0f), okz = !(uz < 0.0f || uz > 1.0f);
-#pragma unroll
+#pragma unroll 1
             for (uint32_t p = 0; p < 3; p++) {        // split_xyz: xy, yz, xz (network.py:208-212)
                 const float u = (p == 1) ? uy : ux, v = (p == 0) ? uy : uz;
                 const bool ok = live && ((p == 1) ? oky : okx) && ((p == 0) ? oky : okz);
                 const float *tab = a.tab[p];
-                float f[12];
+#pragma unroll 1
+                for (uint32_t l = 0; l < 12; l += 4) {        // 4 levels per trip: 8 pair loads in flight, small code
+                    float f[4];
 #pragma unroll
-                for (uint32_t l = 0; l < 12; l++) f[l] = ok ? lvl2_interp(tab, S.lvl[l], u, v) : 0.0f;
-                // features p*12 .. p*12+11 -> halves; 12 halves = 1.5 chunks, handled as 6 packed words at word offset p*6
-#pragma unroll
-                for (uint32_t j = 0; j < 6; j++) {
-                    const uint32_t word = p * 6u + j;                 // 32-bit word index within the row (18 data words)
-                    *reinterpret_cast<uint32_t *>(sX + sw128_offset(t, word >> 2) + (word & 3u) * 4u) = pack2(f[2 * j], f[2 * j + 1]);
+                    for (uint32_t q = 0; q < 4; q++) f[q] = ok ? lvl2_interp(tab, S.lvl[l + q], u, v) : 0.0f;
+                    const uint32_t word = p * 6u + (l >> 1);          // 32-bit word index within the row (18 data words)
+                    *reinterpret_cast<uint32_t *>(sX + sw128_offset(t, word >> 2) + (word & 3u) * 4u) = pack2(f[0], f[1]);
+                    *reinterpret_cast<uint32_t *>(sX + sw128_offset(t, (word + 1) >> 2) + ((word + 1) & 3u) * 4u) = pack2(f[2], f[3]);
                 }
             }
             // zero the K padding: words 18..23 (features 36..47)
@@ -218,8 +225,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         float eye_att, unc_out = 0.6931471805599453f;       // testing: log(1 + e^0) (network.py:245,278)
         {
             uint32_t acc[32];
-            ld32(tmem_ld + 0, acc); wait_ld(); store_hidden32<true>(sH, t, 0, acc, nullptr);
-            ld32(tmem_ld + 32, acc); wait_ld(); store_hidden32<true>(sH, t, 32, acc, nullptr);
+            hidden_epilogue(tmem_ld + 0, 64, sH, t, 0, true, nullptr);
             uint32_t e16[16];
             ld16(tmem_ld + 64, e16); wait_ld();
             float dot = 0.0f;
@@ -269,29 +275,19 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         // ---- P3: sigma hidden += [enc_w, e] * WC -------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 64, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
         mma_done();
-        {
-            uint32_t acc[32];
-            ld32(tmem_ld + 64, acc); wait_ld(); store_hidden32<true>(sH, t, 0, acc, nullptr);
-            ld32(tmem_ld + 96, acc); wait_ld(); store_hidden32<true>(sH, t, 32, acc, nullptr);
-        }
+        hidden_epilogue(tmem_ld + 64, 64, sH, t, 0, true, nullptr);
         publish();
         // ---- P4: sigma layer 1 --------------------------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 0, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
         mma_done();
-        {
-            uint32_t acc[32];
-            ld32(tmem_ld + 0, acc); wait_ld(); store_hidden32<true>(sH, t, 0, acc, nullptr);
-            ld32(tmem_ld + 32, acc); wait_ld(); store_hidden32<true>(sH, t, 32, acc, nullptr);
-        }
+        hidden_epilogue(tmem_ld + 0, 64, sH, t, 0, true, nullptr);
         publish();
         // ---- P5: sigma layer 2: cols 0..63 = geo_feat, col 64 = density logit (rows rotated at pack time) -----------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 0, sH_a, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
         mma_done();
         float sigma;
         {
-            uint32_t acc[32];
-            ld32(tmem_ld + 0, acc); wait_ld(); store_hidden32<false>(sH, t, 0, acc, nullptr);
-            ld32(tmem_ld + 32, acc); wait_ld(); store_hidden32<false>(sH, t, 32, acc, nullptr);
+            hidden_epilogue(tmem_ld + 0, 64, sH, t, 0, false, nullptr);
             uint32_t s16[16];
             ld16(tmem_ld + 64, s16); wait_ld();
             sigma = expf(round_h(__uint_as_float(s16[0]))) * a.density_scale;       // torch.exp(h[..., 0]) in fp32 (network.py:301)
@@ -311,11 +307,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             mma_commit(bar);
         }
         mma_done();
-        {
-            uint32_t acc[32];
-            ld32(tmem_ld + 0, acc); wait_ld(); store_hidden32<true>(sH, t, 0, acc, S.ind_bias);
-            ld32(tmem_ld + 32, acc); wait_ld(); store_hidden32<true>(sH, t, 32, acc, S.ind_bias);
-        }
+        hidden_epilogue(tmem_ld + 0, 64, sH, t, 0, true, S.ind_bias);
         publish();
         // ---- P7: color layer 1 (N padded 3 -> 16) -----------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 64, sH_a, sW_a + HW_G, 4, 16, false); mma_commit(bar); }

@@ -31,21 +31,20 @@ __device__ __forceinline__ Lvl2 make_lvl2(const int32_t *__restrict__ offsets, u
     return g;
 }
 
+// generic modulo, kept out of line: only tiled levels whose dense index range exceeds a non-power-of-two size get here
+__device__ __noinline__ uint32_t wrap_slow(uint32_t i, uint32_t size) { return i % size; }
 __device__ __forceinline__ uint32_t wrap(uint32_t i, const Lvl2 &g) {
     if (!(g.flags & 4u)) return i;
-    return (g.flags & 2u) ? (i & (g.size - 1u)) : (i % g.size);
+    return (g.flags & 2u) ? (i & (g.size - 1u)) : wrap_slow(i, g.size);
 }
 
-// corner indices for cell (x, y): i00, i10, i01, i11
+// corner indices for cell (x, y): i00, i10, i01, i11   (branch-free select between the hash and the dense/tiled index)
 __device__ __forceinline__ void lvl2_corners(const Lvl2 &g, uint32_t x, uint32_t y, uint32_t &i00, uint32_t &i10, uint32_t &i01, uint32_t &i11) {
-    if (g.flags & 1u) {
-        const uint32_t h0 = y * 2654435761u, h1 = (y + 1u) * 2654435761u;
-        i00 = wrap(x ^ h0, g); i10 = wrap((x + 1u) ^ h0, g); i01 = wrap(x ^ h1, g); i11 = wrap((x + 1u) ^ h1, g);
-    } else {
-        const bool two_d = g.stride <= g.size;        // otherwise only the x term contributes (gridencoder.cu:60)
-        const uint32_t b0 = two_d ? y * g.stride : 0u, b1 = two_d ? (y + 1u) * g.stride : 0u;
-        i00 = wrap(x + b0, g); i10 = wrap(x + 1u + b0, g); i01 = wrap(x + b1, g); i11 = wrap(x + 1u + b1, g);
-    }
+    const bool hashed = g.flags & 1u;
+    const uint32_t mul = hashed ? 2654435761u : ((g.stride <= g.size) ? g.stride : 0u);   // dense: only the x term if stride > size (gridencoder.cu:60)
+    const uint32_t m0 = y * mul, m1 = m0 + mul;
+    i00 = wrap(hashed ? (x ^ m0) : (x + m0), g); i10 = wrap(hashed ? ((x + 1u) ^ m0) : (x + 1u + m0), g);
+    i01 = wrap(hashed ? (x ^ m1) : (x + m1), g); i11 = wrap(hashed ? ((x + 1u) ^ m1) : (x + 1u + m1), g);
 }
 
 struct Cell2 { uint32_t x, y; float fx, fy; };

@@ -128,7 +128,10 @@ def test_march_rays_train_full_batch_and_cap(rm):
     assert ocnt[0] > 200000            # the capped run really dropped rays
     # python-level wrapper: mean_count path pads M to +128 and keeps the buffers
     x2, d2, l2, r2 = rm.march_rays_train(T(o), T(d), 1.0, T(bf), 1, 128, nears, fars, None, int(ocnt[0]), False, 128, False, scene.DT_GAMMA, 16)
-    assert x2.shape[0] == int(ocnt[0]) + (128 - int(ocnt[0]) % 128) and np.array_equal(npy(r2)[:, 2], orays[:, 2])
+    _, _, _, zrays, _ = oracle.march_rays_train(o, d, bf, 1.0, scene.DT_GAMMA, 16, 1, 128, 65536 * 16, npy(nears), npy(fars), np.zeros(65536, np.float32))
+    assert x2.shape[0] == int(ocnt[0]) + (128 - int(ocnt[0]) % 128)
+    keep = zrays[:, 1] + zrays[:, 2] <= x2.shape[0]            # perturb=False -> zero noise; rays past the estimated buffer are dropped but still counted
+    assert np.array_equal(npy(r2), zrays) and keep.sum() > 60000
     x3, _, _, _ = rm.march_rays_train(T(o), T(d), 1.0, T(bf), 1, 128, nears, fars, None, -1, False, 128, False, scene.DT_GAMMA, 16)
     assert x3.shape[0] == x2.shape[0]
 
@@ -208,7 +211,7 @@ def test_composite_train_fwd_bwd(rm, ref, variant, layout, T_thresh):
     if layout == "capped":
         M = m - 1000
     f = cases.sample_fields(m, 21); g = cases.ray_grads(n, 22)
-    dl = np.stack([np.full(m, 0.027063293, np.float32), np.cumsum(np.full(m, 0.027063293, np.float32))], 1).astype(np.float32)
+    dl = np.stack([np.full(m, 0.027063293, np.float32), 2.0 + 3.0 * rng.random(m).astype(np.float32)], 1).astype(np.float32)
     fn_name, _, amb_keys, has_unc = VARIANTS[variant]
     per = [f[k] for k in amb_keys] + ([f["unc"]] if has_unc else [])
     ins = [T(f["sigmas"])[:M].clone().requires_grad_(), T(f["rgbs"])[:M].clone().requires_grad_()] + [T(p)[:M].clone().requires_grad_() for p in per]
@@ -216,10 +219,11 @@ def test_composite_train_fwd_bwd(rm, ref, variant, layout, T_thresh):
     ofw = oracle.composite_rays_train_forward(variant, f["sigmas"][:M], f["rgbs"][:M], [f[k][:M] for k in amb_keys], f["unc"][:M], dl[:M], rays, T_thresh)
     k = len(amb_keys) + int(has_unc)
     ws, sums, depth, image = outs[0], outs[1:1 + k], outs[1 + k], outs[2 + k]
-    # fp32 composite: 1e-5 relative (north star) — the only divergent primitive is ex2.approx vs libm exp2f
-    tol = dict(rtol=1e-5, atol=1e-6)
+    # fp32 composite: 1e-5 relative (north star).  The only divergent primitive is the GPU's ex2.approx inside __expf vs libm: alpha = 1 - exp(-s*d)
+    # carries an ABSOLUTE error of ~1.2e-7 per sample, hence atol = 16 samples x 1.2e-7 x max|per-sample value| (values <= 1, depth t <= 5).
+    tol = dict(rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(npy(ws), ofw["weights_sum"], **tol)
-    np.testing.assert_allclose(npy(depth), ofw["depth"], **tol)
+    np.testing.assert_allclose(npy(depth), ofw["depth"], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(npy(image), ofw["image"], **tol)
     for i in range(len(amb_keys)):
         np.testing.assert_allclose(npy(sums[i]), ofw["amb_sums"][i], **tol)
