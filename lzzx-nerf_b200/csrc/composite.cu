@@ -159,12 +159,14 @@ __device__ __forceinline__ void train_bwd_ray(const float *sg, const float *rgb,
         if (NA >= 1) ga0[k] = (AMB == 2) ? __fmul_rn(q.ga0, w) : q.ga0;
         if (NA >= 2) ga1[k] = q.ga1;
         if (UNC) gu[k] = __fmul_rn(q.gu, w);
-        float acc = __fmul_rn(q.gi0, __fmaf_rn(T, c0, -__fsub_rn(q.rF, r)));
-        acc = __fmaf_rn(q.gi1, __fmaf_rn(T, c1, -__fsub_rn(q.gF, g)), acc);
+        // summation order of the reference's sm_100a SASS (all four variants): round gi1*t1 first, fma the others onto it,
+        // then ADD the loop-invariant gws*(1-ws_final) product
+        float acc = __fmul_rn(q.gi1, __fmaf_rn(T, c1, -__fsub_rn(q.gF, g)));
+        acc = __fmaf_rn(q.gi0, __fmaf_rn(T, c0, -__fsub_rn(q.rF, r)), acc);
         acc = __fmaf_rn(q.gi2, __fmaf_rn(T, c2, -__fsub_rn(q.bF, b)), acc);
         if (AMB == 2) acc = __fmaf_rn(q.ga0, __fmaf_rn(T, av, -__fsub_rn(q.a0F, a)), acc);
         if (UNC) acc = __fmaf_rn(q.gu, __fmaf_rn(T, uv, -__fsub_rn(q.uF, u)), acc);
-        acc = __fmaf_rn(q.gws, __fsub_rn(1.0f, q.wsF), acc);
+        acc = __fadd_rn(__fmul_rn(q.gws, __fsub_rn(1.0f, q.wsF)), acc);
         gs[k] = __fmul_rn(delta, acc);
         if (T < T_thresh) { k++; break; }
     }

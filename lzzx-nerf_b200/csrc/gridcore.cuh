@@ -56,14 +56,16 @@ __device__ __forceinline__ Cell2 lvl2_cell(const Lvl2 &g, float u, float v) {
     return c;
 }
 
-// pair load: when i1 == i0 ^ 1 the two x-neighbours share one aligned 8-byte word (level offsets are multiples of 8)
+// pair load: when i1 == i0 ^ 1 the two x-neighbours share one aligned 8-byte word (level offsets are multiples of 8).
+// Branch-free: the aligned pair around i0 is always fetched with one 8-byte load; the (rare, lane-divergent) other case adds a
+// predicated scalar load instead of a divergent branch (BSSY/BSYNC showed up as 20 % of the stall samples in the first profile).
 __device__ __forceinline__ void lvl2_load_pair(const float *__restrict__ tab, uint32_t i0, uint32_t i1, float &v0, float &v1) {
-    if (i1 == (i0 ^ 1u)) {
-        const float2 pr = __ldg(reinterpret_cast<const float2 *>(tab) + (i0 >> 1));
-        v0 = (i0 & 1u) ? pr.y : pr.x; v1 = (i0 & 1u) ? pr.x : pr.y;
-    } else {
-        v0 = __ldg(tab + i0); v1 = __ldg(tab + i1);
-    }
+    const float2 pr = __ldg(reinterpret_cast<const float2 *>(tab) + (i0 >> 1));
+    const bool paired = (i1 == (i0 ^ 1u));
+    float other = 0.0f;
+    if (!paired) other = __ldg(tab + i1);
+    v0 = (i0 & 1u) ? pr.y : pr.x;
+    v1 = paired ? ((i0 & 1u) ? pr.x : pr.y) : other;
 }
 
 // interpolated feature of one level (inputs u, v already checked to be inside [0,1])

@@ -133,7 +133,8 @@ def test_march_rays_train_full_batch_and_cap(rm):
     keep = zrays[:, 1] + zrays[:, 2] <= x2.shape[0]            # perturb=False -> zero noise; rays past the estimated buffer are dropped but still counted
     assert np.array_equal(npy(r2), zrays) and keep.sum() > 60000
     x3, _, _, _ = rm.march_rays_train(T(o), T(d), 1.0, T(bf), 1, 128, nears, fars, None, -1, False, 128, False, scene.DT_GAMMA, 16)
-    assert x3.shape[0] == x2.shape[0]
+    ztot = int(zrays[:, 2].sum())
+    assert x3.shape[0] == ztot + (128 - ztot % 128)          # warm-up path trims to the produced samples, 128-aligned
 
 
 @pytest.mark.parametrize("name", ["head16", "cascade2", "nogamma"])
@@ -280,6 +281,8 @@ def test_composite_inference_loop(rm, ref, variant):
     for it, n_step in enumerate((1, 2, 4, 8)):
         n_alive = alive.shape[0]
         assert n_alive == o_alive.shape[0]
+        if n_alive == 0:          # renderer.py:509-510 leaves the loop; the reference kernels cannot be launched on an empty grid
+            break
         xyzs, dirs, deltas = rm.march_rays(n_alive, n_step, alive, rays_t, o, d, c["bound"], T(c["bitfield"]), c["C"], c["H"], nears, fars, 128, False,
                                            c["dt_gamma"], c["max_steps"])
         M = xyzs.shape[0]
