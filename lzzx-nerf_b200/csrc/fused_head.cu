@@ -78,22 +78,40 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // footprint) matters more than the few loop instructions.
 __device__ __noinline__ void hidden_epilogue(uint32_t taddr, uint32_t ncols, uint8_t *tile, uint32_t row, uint32_t k0, bool relu, const float *bias) {
 #pragma unroll 1
-    for (uint32_t cb = 0; cb < ncols; cb += 16) {
-        uint32_t acc[16];
-        ld16(taddr + cb, acc);
+    for (uint32_t cb = 0; cb < ncols; cb += 32) {
+        uint32_t acc[32];
+        ld32(taddr + cb, acc);
         wait_ld();
-        uint32_t w[8];
 #pragma unroll
-        for (uint32_t j = 0; j < 8; j++) {
-            float a = __uint_as_float(acc[2 * j]), b = __uint_as_float(acc[2 * j + 1]);
-            if (bias) { a += bias[cb + 2 * j]; b += bias[cb + 2 * j + 1]; }
-            if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-            w[j] = pack2(a, b);
+        for (uint32_t c = 0; c < 4; c++) {
+            uint32_t w[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) {
+                float x0 = __uint_as_float(acc[c * 8 + 2 * j]), x1 = __uint_as_float(acc[c * 8 + 2 * j + 1]);
+                if (bias) { x0 += bias[cb + c * 8 + 2 * j]; x1 += bias[cb + c * 8 + 2 * j + 1]; }
+                __half2 h = __floats2half2_rn(x0, x1);
+                if (relu) h = __hmax2(h, __float2half2_rn(0.0f));          // relu(round(x)) == round(relu(x))
+                w[j] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            *reinterpret_cast<uint4 *>(tile + sw128_offset(row, ((k0 + cb) >> 3) + c)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        const uint32_t c0 = (k0 + cb) >> 3;
-        *reinterpret_cast<uint4 *>(tile + sw128_offset(row, c0)) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4 *>(tile + sw128_offset(row, c0 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
     }
+}
+
+// One level of one plane: 4 corner reads + bilinear blend, arithmetic identical to gridcore.cuh:lvl2_interp / k_grid_fwd<float,2,1>
+// (weights (1-fx|fx)*(1-fy|fy), four fmas in corner order (0,0),(1,0),(0,1),(1,1)).  Index math: dense levels i + j*stride, hashed
+// levels (i ^ j*2654435761) & (size-1) — the level kind is warp-uniform.  (gx, gy) = 1 - (fx, fy).
+__device__ __forceinline__ float plane_feature(const float *__restrict__ tab, const HeadLvl &g, uint32_t i, uint32_t j, float fx, float gx, float fy, float gy) {
+    const uint32_t m0 = j * g.mul, m1 = m0 + g.mul;
+    uint32_t i00, i10, i01, i11;
+    if (g.mask != 0xffffffffu) { i00 = (i ^ m0) & g.mask; i10 = ((i + 1u) ^ m0) & g.mask; i01 = (i ^ m1) & g.mask; i11 = ((i + 1u) ^ m1) & g.mask; }
+    else { i00 = i + m0; i10 = i00 + 1u; i01 = i + m1; i11 = i01 + 1u; }
+    const float v00 = __ldg(tab + i00), v10 = __ldg(tab + i10), v01 = __ldg(tab + i01), v11 = __ldg(tab + i11);
+    float r = __fmaf_rn(__fmul_rn(gx, gy), v00, 0.0f);
+    r = __fmaf_rn(__fmul_rn(fx, gy), v10, r);
+    r = __fmaf_rn(__fmul_rn(gx, fy), v01, r);
+    r = __fmaf_rn(__fmul_rn(fx, fy), v11, r);
+    return r;
 }
 
 // real spherical harmonics, degree 4 (16 terms), fp32 — same polynomials as shencoder.cu:44-67
@@ -121,7 +139,6 @@ __device__ __noinline__ void issue_mma(uint32_t d_tmem, uint32_t a_saddr, uint32
 struct HeadSmem {                       // lives after the 1024-aligned weight image and operand tiles
     float enc_a_h[32];                  // fp16-rounded audio code
     float eye_w1[16], unc_w1[32], ind_bias[64];
-    Lvl2 lvl[12];
     float eye_val;
     uint32_t n_valid;
     uint32_t tmem_base;
@@ -131,7 +148,7 @@ struct HeadSmem {                       // lives after the 1024-aligned weight i
 
 __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_constant__ HeadArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // pointer arithmetic keeps the shared address space visible to the compiler
     uint8_t *s_w = base;
     uint8_t *s_tiles = base + HW_BYTES;
     HeadSmem &S = *reinterpret_cast<HeadSmem *>(s_tiles + HG_WGS * 2 * HG_TILE_BYTES);
@@ -153,7 +170,6 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         S.eye_val = a.eye ? a.eye[0] : 0.0f;
     }
     if (warp == 1) tmem_alloc(&S.tmem_base, 512);
-    if (tid >= 64 && tid < 64 + 12) S.lvl[tid - 64] = make_lvl2(a.offsets, tid - 64, a.S, a.H, 0);
     if (tid >= 128 && tid < 160) S.enc_a_h[tid - 128] = round_h(a.enc_a[tid - 128]);
     if (tid >= 160 && tid < 176) S.eye_w1[tid - 160] = a.wsmall[HS_EYE_W1 + tid - 160];
     if (tid >= 192 && tid < 224) S.unc_w1[tid - 192] = a.wsmall[HS_UNC_W1 + tid - 192];
@@ -193,23 +209,36 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             dxv = __ldcs(a.dirs + 3 * (size_t)m); dyv = __ldcs(a.dirs + 3 * (size_t)m + 1); dzv = __ldcs(a.dirs + 3 * (size_t)m + 2);
         }
         {
-            // (x + bound) / (2 bound), fp32, like GridEncoder.forward (grid.py:143)
+            // (x + bound) / (2 bound), fp32, like GridEncoder.forward (grid.py:143); out-of-range coordinates give zero features
+            // (gridencoder.cu:98-122) — they are clamped for addressing and masked at the end
             const float two_b = __fmul_rn(2.0f, a.bound);
-            const float ux = __fdiv_rn(__fadd_rn(px, a.bound), two_b), uy = __fdiv_rn(__fadd_rn(py, a.bound), two_b), uz = __fdiv_rn(__fadd_rn(pz, a.bound), two_b);
+            float ux = __fdiv_rn(__fadd_rn(px, a.bound), two_b), uy = __fdiv_rn(__fadd_rn(py, a.bound), two_b), uz = __fdiv_rn(__fadd_rn(pz, a.bound), two_b);
             const bool okx = !(ux < 0.0f || ux > 1.0f), oky = !(uy < 0.0f || uy > 1.0f), okz = !(uz < 0.0f || uz > 1.0f);
+            const bool ok_xy = live && okx && oky, ok_yz = live && oky && okz, ok_xz = live && okx && okz;
+            ux = okx ? ux : 0.0f; uy = oky ? uy : 0.0f; uz = okz ? uz : 0.0f;
+            const float *t_xy = a.tab[0], *t_yz = a.tab[1], *t_xz = a.tab[2];
+            // level-major: the cell of x, y and z is computed once per level and shared by the three planes; 12 independent loads in
+            // flight per level; two levels per trip so each plane stores one packed half2 word
 #pragma unroll 1
-            for (uint32_t p = 0; p < 3; p++) {        // split_xyz: xy, yz, xz (network.py:208-212)
-                const float u = (p == 1) ? uy : ux, v = (p == 0) ? uy : uz;
-                const bool ok = live && ((p == 1) ? oky : okx) && ((p == 0) ? oky : okz);
-                const float *tab = a.tab[p];
-#pragma unroll 1
-                for (uint32_t l = 0; l < 12; l += 4) {        // 4 levels per trip: 8 pair loads in flight, small code
-                    float f[4];
+            for (uint32_t l = 0; l < 12; l += 2) {
+                float f[2][3];
 #pragma unroll
-                    for (uint32_t q = 0; q < 4; q++) f[q] = ok ? lvl2_interp(tab, S.lvl[l + q], u, v) : 0.0f;
-                    const uint32_t word = p * 6u + (l >> 1);          // 32-bit word index within the row (18 data words)
-                    *reinterpret_cast<uint32_t *>(sX + sw128_offset(t, word >> 2) + (word & 3u) * 4u) = pack2(f[0], f[1]);
-                    *reinterpret_cast<uint32_t *>(sX + sw128_offset(t, (word + 1) >> 2) + ((word + 1) & 3u) * 4u) = pack2(f[2], f[3]);
+                for (uint32_t q = 0; q < 2; q++) {
+                    const HeadLvl g = a.lvl[l + q];                       // kernel-parameter (constant bank) read, warp-uniform
+                    const float qx = __fmaf_rn(ux, g.scale, 0.5f), qy = __fmaf_rn(uy, g.scale, 0.5f), qz = __fmaf_rn(uz, g.scale, 0.5f);
+                    const uint32_t ix = (uint32_t)floorf(qx), iy = (uint32_t)floorf(qy), iz = (uint32_t)floorf(qz);
+                    const float fx = __fsub_rn(qx, (float)ix), fy = __fsub_rn(qy, (float)iy), fz = __fsub_rn(qz, (float)iz);
+                    const float gx = __fsub_rn(1.0f, fx), gy = __fsub_rn(1.0f, fy), gz = __fsub_rn(1.0f, fz);
+                    f[q][0] = plane_feature(t_xy + g.off, g, ix, iy, fx, gx, fy, gy);   // split_xyz: xy, yz, xz (network.py:208-212)
+                    f[q][1] = plane_feature(t_yz + g.off, g, iy, iz, fy, gy, fz, gz);
+                    f[q][2] = plane_feature(t_xz + g.off, g, ix, iz, fx, gx, fz, gz);
+                }
+                const uint32_t w0 = l >> 1;                                   // 32-bit word of (level l, l+1) inside a plane's 6 words
+#pragma unroll
+                for (uint32_t p = 0; p < 3; p++) {
+                    const bool ok = (p == 0) ? ok_xy : ((p == 1) ? ok_yz : ok_xz);
+                    const uint32_t word = p * 6u + w0;
+                    *reinterpret_cast<uint32_t *>(sX + sw128_offset(t, word >> 2) + (word & 3u) * 4u) = ok ? pack2(f[0][p], f[1][p]) : 0u;
                 }
             }
             // zero the K padding: words 18..23 (features 36..47)
@@ -363,10 +392,47 @@ using namespace b2n;
 
 struct b2n_model {
     uint8_t *wimg = nullptr;       // HW_BYTES
-    float *wsmall = nullptr;       // HS_FLOATS
+    float *wsmall = nullptr;       // HS_FLOATS (+ 12 floats of scratch for the device-computed level scales)
     b2n_head_weights w = {};
+    HeadLvl lvl[12] = {};
+    // geometry the cached lvl[] was derived from (re-derived only when it changes: one small D2H read + sync)
+    const int32_t *geo_offsets = nullptr;
+    float geo_S = 0.0f;
+    uint32_t geo_H = 0;
     bool ready = false;
 };
+
+namespace b2n { __global__ void k_level_scales(float S, uint32_t H, uint32_t L, float *__restrict__ out); }
+
+// Derive the 12 per-level constants.  Reads offsets[13] and the device-computed scales back to the host (synchronises `st`);
+// runs only when the table geometry changes (model creation), never per frame / per training step.
+static int derive_levels(b2n_model *m, const b2n_head_weights *w, cudaStream_t st) {
+    float *d_scales = m->wsmall + HS_FLOATS;
+    k_level_scales<<<1, 64, 0, st>>>(w->S, w->H, 12, d_scales);
+    if (check_launch("model_update(scales)")) return 1;
+    int32_t offs[13];
+    float scales[12];
+    B2N_CUDA(cudaMemcpyAsync(offs, w->offsets, sizeof(offs), cudaMemcpyDeviceToHost, st));
+    B2N_CUDA(cudaMemcpyAsync(scales, d_scales, sizeof(scales), cudaMemcpyDeviceToHost, st));
+    B2N_CUDA(cudaStreamSynchronize(st));
+    for (int l = 0; l < 12; l++) {
+        const uint32_t size = (uint32_t)(offs[l + 1] - offs[l]);
+        const uint32_t res = (uint32_t)ceilf(scales[l]) + 1u, stride = res + 1u;
+        B2N_REQUIRE(offs[l] >= 0 && offs[l + 1] > offs[l], "model_update: offsets must be increasing");
+        const bool dense = (uint64_t)stride * stride <= size;              // gridencoder.cu:54-72 with D = 2, gridtype = hash
+        HeadLvl g;
+        g.scale = scales[l];
+        g.off = (uint32_t)offs[l];
+        if (dense) { g.mul = stride; g.mask = 0xffffffffu; }
+        else {
+            B2N_REQUIRE((size & (size - 1)) == 0, "model_update: hashed level %d has %u entries; the fused kernel needs a power of two (use the per-op path)", l, size);
+            g.mul = 2654435761u; g.mask = size - 1u;
+        }
+        m->lvl[l] = g;
+    }
+    m->geo_offsets = w->offsets; m->geo_S = w->S; m->geo_H = w->H;
+    return 0;
+}
 
 extern "C" {
 
@@ -374,7 +440,7 @@ int b2n_model_create(b2n_model **out, void *stream) {
     (void)stream;
     B2N_REQUIRE(out, "model_create: null pointer");
     b2n_model *m = new b2n_model();
-    if (cudaMalloc(&m->wimg, HW_BYTES) != cudaSuccess || cudaMalloc(&m->wsmall, sizeof(float) * HS_FLOATS) != cudaSuccess) {
+    if (cudaMalloc(&m->wimg, HW_BYTES) != cudaSuccess || cudaMalloc(&m->wsmall, sizeof(float) * (HS_FLOATS + 16)) != cudaSuccess) {
         (void)cudaGetLastError();
         if (m->wimg) cudaFree(m->wimg);
         delete m;
@@ -416,6 +482,8 @@ int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
     add(w->color_w1, HW_G, 16, 3, 64, 0, 64, 0);
     pa.n = n;
     cudaStream_t st = as_stream(stream);
+    if (m->geo_offsets != w->offsets || m->geo_S != w->S || m->geo_H != w->H)
+        if (int rc = derive_levels(m, w, st)) return rc;
     k_pack_head<<<ceil_div<uint32_t>(HW_BYTES / 16, 256), 256, 0, st>>>(pa, m->wimg);
     if (check_launch("model_update(pack)")) return 1;
     k_pack_small<<<1, 256, 0, st>>>(w->eye_att_w1, w->unc_w1, w->color_w0, m->wsmall);
@@ -436,7 +504,8 @@ int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *di
     HeadArgs a = {};
     a.xyzs = xyzs; a.dirs = dirs; a.M = M; a.n_valid = n_valid;
     a.tab[0] = m->w.table_xy; a.tab[1] = m->w.table_yz; a.tab[2] = m->w.table_xz;
-    a.offsets = m->w.offsets; a.S = m->w.S; a.H = m->w.H; a.bound = m->w.bound;
+    for (int l = 0; l < 12; l++) a.lvl[l] = m->lvl[l];
+    a.bound = m->w.bound;
     a.wimg = m->wimg; a.wsmall = m->wsmall;
     a.enc_a = enc_a; a.ind_code = ind_code; a.eye = eye;
     a.sigmas = sigmas; a.rgbs = rgbs; a.amb_aud = amb_aud; a.amb_eye = amb_eye; a.unc = unc;

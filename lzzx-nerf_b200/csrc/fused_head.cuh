@@ -24,14 +24,20 @@ static_assert(HW_B % 1024 == 0 && HW_C % 1024 == 0 && HW_D % 1024 == 0 && HW_E %
 // small fp32 vectors (values pre-rounded to fp16)
 constexpr uint32_t HS_EYE_W1 = 0, HS_UNC_W1 = 16, HS_IND_W = 48, HS_FLOATS = 48 + 256;
 
+// per-level constants of the (shared) tri-plane geometry, precomputed at b2n_model_update
+struct HeadLvl {
+    float scale;        // exp2f(level*S)*H - 1, computed ON THE DEVICE (ex2.approx) so it carries the reference's bits
+    uint32_t mul;       // dense level: row stride (resolution + 1); hashed level: the hash prime 2654435761
+    uint32_t mask;      // hashed level: size - 1 (size is a power of two); dense level: 0xffffffff
+    uint32_t off;       // first table entry of the level
+};
+
 struct HeadArgs {
     const float *xyzs, *dirs;
     uint32_t M;
     const int32_t *n_valid;
     const float *tab[3];
-    const int32_t *offsets;
-    float S;
-    uint32_t H;
+    HeadLvl lvl[12];
     float bound;
     const uint8_t *wimg;
     const float *wsmall;

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) k_grid_input_bwd(const T *__restrict__ gr
 }
 
 // per-level scales exactly as the kernels compute them (ex2.approx + fma) — lets a CPU checker use the GPU's bits
-__global__ void k_level_scales(float S, uint32_t H, uint32_t L, float *__restrict__ out) {
+__global__ void k_level_scales(float S, uint32_t H, uint32_t L, float *__restrict__ out) {   // also used by fused_head.cu
     const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l < L) out[l] = __fmaf_rn(exp2f(__fmul_rn((float)l, S)), (float)H, -1.0f);
 }
