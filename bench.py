@@ -187,6 +187,44 @@ def head_kernel_profile(model, renderer, frames, auds, steps):
     return total_ms, launches, samples
 
 
+def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536):
+    """BASELINE configs[2]/[4]: data-parallel training step, 65 536 rays per GPU, synthetic audio window (AudioNet + AudioAttNet), grid backward,
+    AdamW; gradients all-reduced once per step over the flat buffer when world > 1.  Returns a dict (rays/s over all ranks)."""
+    from b2nerf import scene
+    from b2nerf.train import Trainer
+    model = build_model(dev)
+    model.testing = False
+    model.density_bitfield.copy_(torch.from_numpy(bitfield).to(dev))
+    tr = Trainer(model, fp16=True)
+    batches = []
+    for s in range(4):
+        o, d = scene.train_rays(step=rank * 100 + s, n=n_rays)
+        batches.append((torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev), torch.from_numpy(scene.audio_window(rank * 100 + s)).to(dev),
+                        torch.rand(n_rays, 3, device=dev)))
+    for s in range(warmup):
+        b = batches[s % 4]
+        tr.train_step(b[0], b[1], b[2], b[3], index=s)
+        if s == 15:
+            tr.update_mean_count()            # the reference's warm-up: 16 steps with worst-case buffers, then the mean_count estimate
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        b = batches[s % 4]
+        loss, m_buf = tr.train_step(b[0], b[1], b[2], b[3], index=s)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"metric": "train_rays_per_sec", "value": world * steps * n_rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": n_rays,
+            "samples_per_step_buffer": int(m_buf), "loss": float(loss), "grad_allreduce_bytes": tr.grads.nbytes() if world > 1 else 0,
+            "path": "drop-in ops + torch autograd (MLPs via cuBLAS under autocast fp16), AdamW, flat-buffer NCCL all-reduce"}
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     from b2nerf import lib
     from b2nerf.render import FrameRenderer
@@ -239,6 +277,9 @@ def run_gpu_arm(args, rank, world, local_rank):
     dev_ms, launches = timed(lambda s: r.render_device(frames[s % POOL][0], frames[s % POOL][1], auds[s % POOL]), args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
     e2e_ms, _ = timed(lambda s: r.render_host(host_o[s % POOL], host_d[s % POOL], host_a[s % POOL], out_host), args.steps, args.warmup)
+    train_info = None
+    if not args.no_train:
+        train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(4, min(args.steps, 20)), warmup=max(args.warmup, 18))
     if rank != 0:
         return
     img = out_host.numpy()
@@ -265,6 +306,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                             f"(separate un-graphed pass of the same frames), {head_samples} samples x {2 * MACS_PER_SAMPLE_INFER} FLOP",
                      "head_ms_per_frame": head_ms / min(args.steps, 8), "samples_per_frame": head_samples / min(args.steps, 8)},
     }
+    if not args.no_train:
+        line["train"] = train_info
     if world == 1 and not args.no_cpu:
         rows = 32
         fps, sec, ns = cpu_frames_per_sec(rows, 2, 1)
@@ -281,6 +324,7 @@ def main():
     ap.add_argument("--impl", default="b2nerf", choices=["b2nerf", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2nerf" else args.warmup
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

@@ -229,3 +229,28 @@ def params_from_state_dict(sd, bound=1.0):
     p["H"] = 64
     p["bound"] = bound
     return p
+
+
+def composite_rays_train_triplane_ragged(sigmas, rgbs, aud, eye, unc, deltas, rays, max_steps=16, T_thresh=1e-4):
+    """Variable-length segments (rays [N,3] = (id, offset, count)), differentiable: pads every ray to `max_steps` samples with sigma = 0
+    (alpha = 0, no contribution) and reuses the equal-length formulation.  Outputs are indexed by ray id like the kernel (raymarching.cu:1967-1974)."""
+    n = rays.shape[0]
+    ids, off, cnt = rays[:, 0].long(), rays[:, 1].long(), rays[:, 2].long()
+    k = torch.arange(max_steps)[None, :]
+    valid = k < cnt[:, None]
+    idx = (off[:, None] + k).clamp_max(max(sigmas.shape[0] - 1, 0))
+    pick = lambda a: torch.where(valid, a[idx], torch.zeros(()))
+    s, a0, a1, u = pick(sigmas), pick(aud), pick(eye), pick(unc)
+    dl0, dl1 = pick(deltas[:, 0]), pick(deltas[:, 1])
+    c = torch.where(valid[:, :, None], rgbs[idx], torch.zeros(()))
+    alpha = 1 - torch.exp(-s * dl0)
+    T = torch.cumprod(torch.cat([torch.ones(n, 1), 1 - alpha], dim=1), dim=1)
+    stopped = (T[:, 1:] < T_thresh).long().cumsum(dim=1)
+    live = torch.cat([torch.ones(n, 1, dtype=torch.bool), stopped[:, :-1] == 0], dim=1) & valid
+    w = alpha * T[:, :-1] * live
+    outs = [w.sum(1), (a0 * live).sum(1), (a1 * live).sum(1), (w * u).sum(1), (w * dl1).sum(1), (w[:, :, None] * c).sum(1)]
+    res = []
+    for o in outs:                                   # scatter by ray id
+        z = torch.zeros_like(o)
+        res.append(z.index_copy(0, ids, o))
+    return tuple(res)

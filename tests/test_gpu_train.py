@@ -1,0 +1,86 @@
+"""GPU: the training step (march_rays_train -> head network -> composite_rays_train_triplane -> backward incl. grid_encode backward ->
+AdamW) on the drop-in ops.  Gradients are checked against the pure-PyTorch port on the CPU (fp32 autograd through the same graph)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import torch_port as tp
+from b2nerf import scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(n_rays, seed=0, table_scale=0.5):
+    from b2nerf.model import HeadModel
+    from b2nerf.train import Trainer
+    torch.manual_seed(seed)
+    m = HeadModel(audio_in_dim=29).cuda()             # DeepSpeech-sized audio front-end keeps the CPU comparison light
+    for enc in (m.encoder_xy, m.encoder_yz, m.encoder_xz):
+        enc.embeddings.data.uniform_(-table_scale, table_scale)
+    bf = scene.bitfield_from_grid(scene.density_grid())
+    m.density_bitfield.copy_(torch.from_numpy(bf).cuda())
+    o, d = scene.train_rays(seed, n_rays)
+    auds = torch.from_numpy(scene.audio_window(seed, hubert=False))
+    gt = torch.from_numpy(np.random.default_rng(seed).random((n_rays, 3)).astype(np.float32))
+    return m, Trainer, bf, o, d, auds, gt
+
+
+def test_train_step_gradients_match_cpu_port_fp32():
+    n = 2048
+    m, Trainer, bf, o, d, auds, gt = _setup(n)
+    tr = Trainer(m, fp16=False)
+    rays_o, rays_d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    eye = torch.full((1, 1), 0.4, device="cuda"); bg = torch.ones(1, 3, device="cuda")
+    tr.grads.zero_()
+    out = tr.render_train(rays_o, rays_d, auds.cuda(), 3, eye, bg, perturb=False)
+    loss = tr.loss(out, gt.cuda())
+    loss.backward()
+    tr.grads.check_attached()
+    # ---- CPU: same graph in pure PyTorch (fp32), samples from the C oracle's marcher ----
+    import copy
+    mc = copy.deepcopy(m).cpu()
+    nears, fars = oracle.near_far_from_aabb(o, d, scene.AABB, 0.05)
+    xyzs, dirs, deltas, rays, cnt = oracle.march_rays_train(o, d, bf, 1.0, 1 / 256, 16, 1, 128, n * 16, nears, fars, np.zeros(n, np.float32))
+    tot = int(cnt[0])
+    P = {k: v for k, v in mc.named_parameters()}
+    p = {k: v for k, v in P.items()}
+    p["encoder_xy.offsets"] = mc.encoder_xy.offsets; p["S"] = float(np.log2(mc.encoder_xy.per_level_scale)); p["H"] = 64; p["bound"] = 1.0
+    enc_a = mc.encode_audio(auds)[0]
+    sig, rgb, aa, ae, un = tp.head_forward(p, torch.from_numpy(xyzs[:tot]), torch.from_numpy(dirs[:tot]), enc_a, P["individual_codes"][3], torch.tensor([0.4]), testing=False)
+    ws, s_a, s_e, s_u, dep, img = tp.composite_rays_train_triplane_ragged(sig, rgb, aa.abs(), ae.abs(), un, torch.from_numpy(deltas[:tot]), torch.from_numpy(rays.astype(np.int64)))
+    img = (img + (1 - ws)[:, None]).clamp(0, 1)
+    mse = ((img - gt) ** 2).mean(-1).mean()
+    al = ws.clamp(1e-5, 1 - 1e-5)
+    ent = (-al * torch.log2(al) - (1 - al) * torch.log2(1 - al)).mean()
+    cpu_loss = mse + 1e-3 * ent + 1e-4 * (s_a.mean() + s_e.mean())
+    cpu_loss.backward()
+    assert abs(float(loss) - float(cpu_loss)) < 2e-4 * max(1.0, abs(float(cpu_loss))), (float(loss), float(cpu_loss))
+    worst = {}
+    for name, q in m.named_parameters():
+        g_gpu = q.grad.detach().cpu()
+        g_cpu = P[name].grad if P[name].grad is not None else torch.zeros_like(P[name])
+        denom = float(g_cpu.abs().max()) + 1e-12
+        worst[name] = float((g_gpu - g_cpu).abs().max()) / denom
+    # fp32 on both sides; differences: fma vs separate ops in the interpolation weights, ex2.approx, atomics order -> 2e-3 of the max gradient
+    bad = {k: v for k, v in worst.items() if v > 2e-3}
+    assert not bad, bad
+    assert float(m.encoder_xy.embeddings.grad.abs().sum()) > 0 and float(m.sigma_net.net[0].weight.grad.abs().sum()) > 0
+
+
+def test_train_steps_reduce_loss_fp16_autocast():
+    n = 65536
+    m, Trainer, bf, o, d, auds, gt = _setup(n, table_scale=1e-4)          # reference init
+    tr = Trainer(m, fp16=True)
+    rays_o, rays_d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    target = torch.tensor([0.2, 0.5, 0.7], device="cuda").expand(n, 3).contiguous()
+    losses = []
+    for step in range(24):
+        l, m_buf = tr.train_step(rays_o, rays_d, auds.cuda(), target, index=step % 7)
+        losses.append(float(l))
+        if step == 15:
+            tr.update_mean_count()
+            assert tr.mean_count > 100000          # ~0.33 M samples for 65 536 rays (~5 samples/ray)
+    assert all(np.isfinite(losses))
+    assert np.mean(losses[-4:]) < 0.9 * np.mean(losses[:4]), losses
+    assert m_buf == tr.mean_count + (128 - tr.mean_count % 128)           # steady state: mean_count-sized, 128-aligned buffers
