@@ -43,6 +43,14 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture (profiles/)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "head_kernel_ncu.json")))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -146,21 +154,18 @@ def run_reference_arm(args, rank):
 # ------------------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------------------
-def head_kernel_profile(model, renderer, frames, auds, steps):
-    """Separate instrumented pass (no CUDA graph): CUDA events on the launching stream around every fused-head launch of `steps` frames.
-    Returns (total head ms, launches, total samples evaluated)."""
-    from b2nerf import lib
-    L = lib()
-    stream = torch.cuda.current_stream()
-    dev = renderer.dev
-    N = renderer.N
-    cfg_kw = renderer.kw
-    total_ms, launches, samples = 0.0, 0, 0
+def head_kernel_profile(model, renderer, frames, auds, n_frames, repeats=5):
+    """Separate instrumented pass (no CUDA graph; CUDA events cannot be recorded inside a replayed graph).  For each of `n_frames` frames the
+    reference loop is run once on the per-op kernels; every loop iteration's fused-head launch is then timed in isolation: one CUDA-event pair on the
+    launching stream around `repeats` back-to-back launches of that same call (so no host gap is inside the pair).  Returns (sum of average launch
+    durations in ms, launches, samples evaluated)."""
     import raymarching
+    stream = torch.cuda.current_stream()
+    dev, N, kw = renderer.dev, renderer.N, renderer.kw
+    total_ms, launches, samples = 0.0, 0, 0
     with torch.no_grad():
-        for s in range(steps):
-            o, d = frames[s % POOL]
-            rays_o, rays_d = o, d
+        for s in range(n_frames):
+            rays_o, rays_d = frames[s % POOL]
             with torch.autocast("cuda", dtype=torch.float16):
                 enc_a = model.encode_audio(auds[s % POOL]).float()
             nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, model.aabb_infer, 0.05)
@@ -168,21 +173,26 @@ def head_kernel_profile(model, renderer, frames, auds, steps):
             sa, se, su = torch.zeros(N, device=dev), torch.zeros(N, device=dev), torch.zeros(N, device=dev)
             alive = torch.arange(N, dtype=torch.int32, device=dev); rays_t = nears.clone()
             step = 0
-            while step < cfg_kw["max_steps"]:
+            while step < kw["max_steps"]:
                 n_alive = alive.shape[0]
                 if n_alive <= 0:
                     break
                 n_step = max(min(N // n_alive, 8), 1)
                 xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, alive, rays_t, rays_o, rays_d, model.bound, model.density_bitfield, model.cascade,
-                                                            model.grid_size, nears, fars, 128, False, cfg_kw["dt_gamma"], cfg_kw["max_steps"])
+                                                            model.grid_size, nears, fars, 128, False, kw["dt_gamma"], kw["max_steps"])
+                sig, rgb, aa, ae, un = model(xyzs, dirs, enc_a, renderer.ind_code, renderer.eye)
+                m_eval = n_alive * n_step                   # what b2n_render_frame evaluates (n_valid = n_alive * n_step)
+                nv = torch.tensor([m_eval], dtype=torch.int32, device=dev)
+                torch.cuda.synchronize(dev)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                sig, rgb, aa, ae, un = model(xyzs, dirs, enc_a, renderer.ind_code, renderer.eye)
+                for _ in range(repeats):
+                    model(xyzs, dirs, enc_a, renderer.ind_code, renderer.eye, n_valid=nv, out=(sig, rgb, aa, ae, un))
                 e1.record(stream)
-                raymarching.composite_rays_triplane(n_alive, n_step, alive, rays_t, sig, rgb, deltas, aa, ae, un, ws, depth, image, sa, se, su, cfg_kw["T_thresh"])
-                alive = alive[alive >= 0]
                 e1.synchronize()
-                total_ms += e0.elapsed_time(e1); launches += 1; samples += n_alive * n_step
+                total_ms += e0.elapsed_time(e1) / repeats; launches += 1; samples += m_eval
+                raymarching.composite_rays_triplane(n_alive, n_step, alive, rays_t, sig, rgb, deltas, aa, ae, un, ws, depth, image, sa, se, su, kw["T_thresh"])
+                alive = alive[alive >= 0]
                 step += n_step
     return total_ms, launches, samples
 
@@ -301,9 +311,10 @@ def run_gpu_arm(args, rank, world, local_rank):
         "gpu_launches": int(launches) if r.graph is None else int(r.launches_per_frame * args.steps),
         "clocks": clocks,
         "roofline": {"kernel": "k_head_forward (fused tri-plane gather + 7 tcgen05 layers)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": pk_src + " (bf16 sustained)",
-                     "how": f"CUDA events on the launching stream around each of {head_launches} head launches of {min(args.steps, 8)} frames "
-                            f"(separate un-graphed pass of the same frames), {head_samples} samples x {2 * MACS_PER_SAMPLE_INFER} FLOP",
+                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": pk_src + " (bf16 sustained)",
+                     "how": f"average launch duration from CUDA events on the launching stream (5 back-to-back repeats per launch) for each of the "
+                            f"{head_launches} head launches of {min(args.steps, 8)} frames, separate un-graphed pass of the same frames; "
+                            f"{head_samples} samples x {2 * MACS_PER_SAMPLE_INFER} FLOP",
                      "head_ms_per_frame": head_ms / min(args.steps, 8), "samples_per_frame": head_samples / min(args.steps, 8)},
     }
     if not args.no_train:

@@ -187,13 +187,17 @@ class HeadModel(nn.Module):
         return self._handle
 
     @torch.no_grad()
-    def forward(self, x, d, enc_a, c, e, n_valid=None):
-        """Fused head: returns sigma [M], color [M,3], ambient_aud [M,1], ambient_eye [M,1], uncertainty [M,1,1] (fp32)."""
+    def forward(self, x, d, enc_a, c, e, n_valid=None, out=None):
+        """Fused head: returns sigma [M], color [M,3], ambient_aud [M,1], ambient_eye [M,1], uncertainty [M,1,1] (fp32).
+        `out` may pass a previous return tuple to write into (no allocation)."""
         M = x.shape[0]
         x, d = x.float().contiguous(), d.float().contiguous()
         dev = x.device
-        sig, rgb = torch.empty(M, device=dev), torch.empty(M, 3, device=dev)
-        aud, eye_o, unc = torch.empty(M, device=dev), torch.empty(M, device=dev), torch.empty(M, device=dev)
+        if out is not None:
+            sig, rgb, aud, eye_o, unc = out[0], out[1], out[2].view(-1), out[3].view(-1), out[4].view(-1)
+        else:
+            sig, rgb = torch.empty(M, device=dev), torch.empty(M, 3, device=dev)
+            aud, eye_o, unc = torch.empty(M, device=dev), torch.empty(M, device=dev), torch.empty(M, device=dev)
         f = lambda t: None if t is None else t.detach().float().contiguous().view(-1)
         enc_a, c, e = f(enc_a), f(c), f(e)
         self._keep = (enc_a, c, e)
