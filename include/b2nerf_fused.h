@@ -44,6 +44,19 @@ int b2n_head_forward(const b2n_model *m, const float *xyzs, const float *dirs, u
                      const float *enc_a, const float *ind_code, const float *eye, const int32_t *n_valid,
                      float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, void *stream);
 
+/* Audio prologue = NeRFNetwork.encode_audio with att > 0 (network.py:226-240): AudioNet (network.py:40-70) on each of the 8 frames of the
+ * window, then AudioAttNet (network.py:9-36).  One kernel, one thread-block cluster of 8 CTAs, autocast(fp16) numerics.
+ * Weights are the torch parameters in place (fp32, nn.Conv1d [out,in,3] / nn.Linear [out,in] layouts).
+ * auds [8, dim_in, L] fp32 (HuBERT: dim_in 1024, L 2; DeepSpeech: dim_in 29, L 16); enc_a [32] fp32. */
+typedef struct {
+    const float *conv_w[4], *conv_b[4];          /* audio_net.encoder_conv.{0,2,4,6}   dim_in->32->32->64->64, k3 s2 p1 */
+    const float *fc_w[2], *fc_b[2];              /* audio_net.encoder_fc1.{0,2}        64->64->32 */
+    const float *att_conv_w[5], *att_conv_b[5];  /* audio_att_net.attentionConvNet.{0,2,4,6,8}  32->16->8->4->2->1, k3 s1 p1 */
+    const float *att_fc_w, *att_fc_b;            /* audio_att_net.attentionNet.0       Linear(8, 8) */
+    uint32_t dim_in;
+} b2n_audio_weights;
+int b2n_audio_encode(const b2n_audio_weights *w, const float *auds, uint32_t L, float *enc_a, void *stream);
+
 /* One whole inference frame = renderer.py:442 (near/far) + :480-545 (march / network / composite loop with compaction)
  * + :559-561 (background blend, clamp), with NO host synchronisation: alive-ray counts and n_step live in a device-side
  * control block; the host enqueues a fixed launch sequence (capturable in a CUDA graph).  perturb is off (inference).

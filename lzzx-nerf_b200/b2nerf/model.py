@@ -88,6 +88,12 @@ class _HeadWeightsC(ctypes.Structure):      # mirrors b2n_head_weights (include/
                 ("color_w0", ctypes.c_void_p), ("color_w1", ctypes.c_void_p), ("unc_w0", ctypes.c_void_p), ("unc_w1", ctypes.c_void_p)]
 
 
+class _AudioWeightsC(ctypes.Structure):     # mirrors b2n_audio_weights
+    _fields_ = [("conv_w", ctypes.c_void_p * 4), ("conv_b", ctypes.c_void_p * 4), ("fc_w", ctypes.c_void_p * 2), ("fc_b", ctypes.c_void_p * 2),
+                ("att_conv_w", ctypes.c_void_p * 5), ("att_conv_b", ctypes.c_void_p * 5), ("att_fc_w", ctypes.c_void_p), ("att_fc_b", ctypes.c_void_p),
+                ("dim_in", ctypes.c_uint32)]
+
+
 class _RenderCfgC(ctypes.Structure):        # mirrors b2n_render_cfg
     _fields_ = [("bound", ctypes.c_float), ("dt_gamma", ctypes.c_float), ("min_near", ctypes.c_float), ("T_thresh", ctypes.c_float),
                 ("density_scale", ctypes.c_float), ("max_steps", ctypes.c_uint32), ("cascade", ctypes.c_uint32), ("grid_size", ctypes.c_uint32),
@@ -131,6 +137,28 @@ class HeadModel(nn.Module):
         if self.att > 0:
             enc_a = self.audio_att_net(enc_a.unsqueeze(0))
         return enc_a
+
+    @torch.no_grad()
+    def encode_audio_fused(self, a, out=None):
+        """encode_audio as one cluster kernel (csrc/fused_audio.cu); a [8, dim_in, L] fp32 -> [1, 32] fp32 (inference, att > 0)."""
+        if self.att <= 0:
+            raise RuntimeError("encode_audio_fused needs the attention net (att > 0)")
+        a = a.float().contiguous()
+        if a.dim() != 3 or a.shape[0] != 8 or a.shape[1] != self.audio_in_dim:
+            raise RuntimeError(f"encode_audio_fused: expected auds [8, {self.audio_in_dim}, L], got {tuple(a.shape)}")
+        p = lambda t: t.detach().data_ptr()
+        conv = [self.audio_net.encoder_conv[i] for i in (0, 2, 4, 6)]
+        fc = [self.audio_net.encoder_fc1[i] for i in (0, 2)]
+        att = [self.audio_att_net.attentionConvNet[i] for i in (0, 2, 4, 6, 8)]
+        lin = self.audio_att_net.attentionNet[0]
+        w = _AudioWeightsC((ctypes.c_void_p * 4)(*[p(c.weight) for c in conv]), (ctypes.c_void_p * 4)(*[p(c.bias) for c in conv]),
+                           (ctypes.c_void_p * 2)(*[p(c.weight) for c in fc]), (ctypes.c_void_p * 2)(*[p(c.bias) for c in fc]),
+                           (ctypes.c_void_p * 5)(*[p(c.weight) for c in att]), (ctypes.c_void_p * 5)(*[p(c.bias) for c in att]),
+                           p(lin.weight), p(lin.bias), self.audio_in_dim)
+        enc = out if out is not None else torch.empty(1, 32, device=a.device)
+        self._keep_audio = (a, w)
+        lib().call("b2n_audio_encode", ctypes.byref(w), a.data_ptr(), a.shape[2], enc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return enc
 
     # ---- reference graph on the drop-in ops (network.py:215-223, 252-311) ---------------------------------------------
     def encode_x(self, xyz):

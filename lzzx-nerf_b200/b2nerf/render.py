@@ -13,7 +13,7 @@ from .model import HeadModel
 
 
 class FrameRenderer:
-    def __init__(self, model: HeadModel, n_rays, eye=0.4, ind_index=0, dt_gamma=1.0 / 256, max_steps=16, T_thresh=1e-4, use_graph=True):
+    def __init__(self, model: HeadModel, n_rays, eye=0.4, ind_index=0, dt_gamma=1.0 / 256, max_steps=16, T_thresh=1e-4, use_graph=True, fused_audio=True):
         self.m = model
         self.dev = next(model.parameters()).device
         self.N = int(n_rays)
@@ -25,6 +25,8 @@ class FrameRenderer:
         self.eye = torch.tensor([[float(eye)]], device=d)
         self.ind_code = model.individual_codes[ind_index:ind_index + 1].detach().clone()
         self.image = torch.empty(self.N, 3, device=d)
+        self.enc_a = torch.empty(1, 32, device=d)
+        self.fused_audio = fused_audio and model.att > 0
         self.graph = None
         self.launches_per_frame = None
         model.cache_host_constants()
@@ -33,9 +35,12 @@ class FrameRenderer:
             self._capture()
 
     def _device_frame(self):
-        with torch.autocast("cuda", dtype=torch.float16):
-            enc_a = self.m.encode_audio(self.auds)              # AudioNet + AudioAttNet (network.py:226-240)
-        self.m.render_frame(self.rays_o, self.rays_d, enc_a.float(), self.ind_code, self.eye, out=self.image, **self.kw)
+        if self.fused_audio:
+            enc_a = self.m.encode_audio_fused(self.auds, out=self.enc_a)      # one cluster kernel (csrc/fused_audio.cu)
+        else:
+            with torch.autocast("cuda", dtype=torch.float16):
+                enc_a = self.m.encode_audio(self.auds).float()              # AudioNet + AudioAttNet through torch (network.py:226-240)
+        self.m.render_frame(self.rays_o, self.rays_d, enc_a, self.ind_code, self.eye, out=self.image, **self.kw)
 
     @torch.no_grad()
     def _capture(self):

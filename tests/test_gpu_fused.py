@@ -157,3 +157,26 @@ def test_render_frame_matches_host_loop(hw):
     a_img, a_ws, _, a_trace = _loop_reference(m, rays_o, rays_d, enc_a, c, e, fused_net=False)
     assert float((ws > 0).float().mean()) > 0.2
     assert float((img - a_img).abs().mean()) < 2e-3 and float((ws - a_ws).abs().mean()) < 2e-3
+
+
+@pytest.mark.parametrize("dim_in,L", [(1024, 2), (29, 16), (44, 16)])
+def test_fused_audio_encoder_matches_torch_autocast(dim_in, L):
+    """AudioNet + AudioAttNet as one cluster kernel vs the torch modules under autocast(fp16) (network.py:9-70, 226-240)."""
+    from b2nerf.model import HeadModel
+    torch.manual_seed(3)
+    m = HeadModel(audio_in_dim=dim_in).cuda()
+    for p in list(m.audio_net.parameters()) + list(m.audio_att_net.parameters()):     # livelier than the default init so every layer matters
+        p.data.mul_(2.0)
+    for trial in range(3):
+        auds = torch.randn(8, dim_in, L, device="cuda")
+        got = m.encode_audio_fused(auds)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            ref16 = m.encode_audio(auds).float()
+        with torch.no_grad():
+            ref32 = m.encode_audio(auds)
+        torch.cuda.synchronize()
+        assert got.shape == (1, 32) and torch.isfinite(got).all()
+        scale = float(ref32.abs().max())
+        # fp16 chain of 11 layers: agreement with the autocast graph at the 1e-3 level of the output scale, and as close to fp32 as autocast is
+        assert float((got - ref16).abs().max()) < 4e-3 * scale, (float((got - ref16).abs().max()), scale)
+        assert float((got - ref32).abs().max()) < 2.0 * float((ref16 - ref32).abs().max()) + 2e-3 * scale
