@@ -294,6 +294,14 @@ def run_gpu_arm(args, rank, world, local_rank):
         return
     img = out_host.numpy()
     assert np.isfinite(img).all() and 0.0 < float(img.mean()) <= 1.0
+    if r.loop_graph is not None:        # device-controlled WHILE loop: kernels per frame = fixed + per-iteration x iterations actually executed
+        iters = r.last_iterations()
+        gpu_launches = int((r.kernels_fixed + r.kernels_per_iteration * iters) * args.steps)
+        loop_mode = f"one CUDA graph per frame, WHILE conditional node, {iters} iterations executed in the last frame"
+    elif r.graph is not None:
+        gpu_launches, loop_mode = int(r.launches_per_frame * args.steps), "torch CUDA graph of the fixed 16-iteration sequence"
+    else:
+        gpu_launches, loop_mode = int(launches), "eager launches"
     value = world * args.steps / (dev_ms * 1e-3)
     e2e = world * args.steps / (e2e_ms * 1e-3)
     pk, pk_src = peaks()
@@ -306,9 +314,9 @@ def run_gpu_arm(args, rank, world, local_rank):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": "infer_512x512_frame", "rays_per_frame": N_RAYS, "max_steps": 16, "dt_gamma": 1 / 256, "bound": 1,
                    "params": 683509, "weights": "random-init", "frames_per_gpu_per_step": 1, "parallelism": f"frames sharded over {world} GPU(s), no collective",
-                   "l2": f"inputs cycle through {POOL} distinct frames ({POOL * N_RAYS * 24 / 1e6:.0f} MB of rays) > 126 MB L2", "cuda_graph": not args.no_graph},
+                   "l2": f"inputs cycle through {POOL} distinct frames ({POOL * N_RAYS * 24 / 1e6:.0f} MB of rays) > 126 MB L2", "cuda_graph": not args.no_graph, "loop": loop_mode},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": r.h2d_bytes(), "d2h_bytes_per_step": r.d2h_bytes(), "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches) if r.graph is None else int(r.launches_per_frame * args.steps),
+        "gpu_launches": gpu_launches,
         "clocks": clocks,
         "roofline": {"kernel": "k_head_forward (fused tri-plane gather + 7 tcgen05 layers)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": pk_src + " (bf16 sustained)",

@@ -74,6 +74,22 @@ int b2n_render_frame(const b2n_model *m, const b2n_render_cfg *cfg, const float 
                      const float *eye, const float *bg_color, void *workspace,
                      float *image_out, float *weights_sum_out, float *depth_out, void *stream);
 
+/* The same frame as ONE CUDA graph whose loop is a WHILE conditional node (init -> while (!done) { march, head, composite, compact, advance }
+ * -> finish): only the iterations the reference's host loop would run are executed; one graph launch per frame.  All pointers are baked in
+ * (static buffers, as with any CUDA graph).  If `audio` is non-NULL the graph starts with b2n_audio_encode(audio, auds, audio_L) -> enc_a;
+ * otherwise enc_a is read as is.  Needs CUDA 12.4+ graph conditional nodes; on failure nothing is created and the plain b2n_render_frame
+ * sequence (capturable into an ordinary graph) remains available. */
+typedef struct b2n_frame_graph b2n_frame_graph;
+int b2n_frame_graph_create(b2n_frame_graph **out, const b2n_model *m, const b2n_render_cfg *cfg, const b2n_audio_weights *audio, const float *auds,
+                           uint32_t audio_L, float *enc_a, const float *rays_o, const float *rays_d, uint32_t N, const uint8_t *bitfield,
+                           const float *ind_code, const float *eye, const float *bg_color, void *workspace, float *image_out, float *weights_sum_out,
+                           float *depth_out);
+int b2n_frame_graph_launch(b2n_frame_graph *fg, void *stream);
+int b2n_frame_graph_info(const b2n_frame_graph *fg, uint64_t *kernels_fixed, uint64_t *kernels_per_iteration);
+void b2n_frame_graph_destroy(b2n_frame_graph *fg);
+/* number of loop iterations executed by the last frame rendered into `workspace` (4-byte read-back; synchronises `stream`) */
+int b2n_frame_iterations(const void *workspace, uint32_t N, int32_t *iterations, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

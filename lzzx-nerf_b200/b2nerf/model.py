@@ -138,6 +138,17 @@ class HeadModel(nn.Module):
             enc_a = self.audio_att_net(enc_a.unsqueeze(0))
         return enc_a
 
+    def audio_weights_struct(self):
+        p = lambda t: t.detach().data_ptr()
+        conv = [self.audio_net.encoder_conv[i] for i in (0, 2, 4, 6)]
+        fc = [self.audio_net.encoder_fc1[i] for i in (0, 2)]
+        att = [self.audio_att_net.attentionConvNet[i] for i in (0, 2, 4, 6, 8)]
+        lin = self.audio_att_net.attentionNet[0]
+        return _AudioWeightsC((ctypes.c_void_p * 4)(*[p(c.weight) for c in conv]), (ctypes.c_void_p * 4)(*[p(c.bias) for c in conv]),
+                              (ctypes.c_void_p * 2)(*[p(c.weight) for c in fc]), (ctypes.c_void_p * 2)(*[p(c.bias) for c in fc]),
+                              (ctypes.c_void_p * 5)(*[p(c.weight) for c in att]), (ctypes.c_void_p * 5)(*[p(c.bias) for c in att]),
+                              p(lin.weight), p(lin.bias), self.audio_in_dim)
+
     @torch.no_grad()
     def encode_audio_fused(self, a, out=None):
         """encode_audio as one cluster kernel (csrc/fused_audio.cu); a [8, dim_in, L] fp32 -> [1, 32] fp32 (inference, att > 0)."""
@@ -146,15 +157,7 @@ class HeadModel(nn.Module):
         a = a.float().contiguous()
         if a.dim() != 3 or a.shape[0] != 8 or a.shape[1] != self.audio_in_dim:
             raise RuntimeError(f"encode_audio_fused: expected auds [8, {self.audio_in_dim}, L], got {tuple(a.shape)}")
-        p = lambda t: t.detach().data_ptr()
-        conv = [self.audio_net.encoder_conv[i] for i in (0, 2, 4, 6)]
-        fc = [self.audio_net.encoder_fc1[i] for i in (0, 2)]
-        att = [self.audio_att_net.attentionConvNet[i] for i in (0, 2, 4, 6, 8)]
-        lin = self.audio_att_net.attentionNet[0]
-        w = _AudioWeightsC((ctypes.c_void_p * 4)(*[p(c.weight) for c in conv]), (ctypes.c_void_p * 4)(*[p(c.bias) for c in conv]),
-                           (ctypes.c_void_p * 2)(*[p(c.weight) for c in fc]), (ctypes.c_void_p * 2)(*[p(c.bias) for c in fc]),
-                           (ctypes.c_void_p * 5)(*[p(c.weight) for c in att]), (ctypes.c_void_p * 5)(*[p(c.bias) for c in att]),
-                           p(lin.weight), p(lin.bias), self.audio_in_dim)
+        w = self.audio_weights_struct()
         enc = out if out is not None else torch.empty(1, 32, device=a.device)
         self._keep_audio = (a, w)
         lib().call("b2n_audio_encode", ctypes.byref(w), a.data_ptr(), a.shape[2], enc.data_ptr(), torch.cuda.current_stream().cuda_stream)

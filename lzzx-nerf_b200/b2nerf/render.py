@@ -27,12 +27,19 @@ class FrameRenderer:
         self.image = torch.empty(self.N, 3, device=d)
         self.enc_a = torch.empty(1, 32, device=d)
         self.fused_audio = fused_audio and model.att > 0
-        self.graph = None
+        self.graph = None               # torch.cuda.CUDAGraph of the fixed launch sequence (fallback)
+        self.loop_graph = None          # libb2nerf frame graph with a device-controlled WHILE loop (preferred)
         self.launches_per_frame = None
+        self.ws = torch.empty(self.N, device=d)
+        self.depth = torch.empty(self.N, device=d)
         model.cache_host_constants()
         model.pack()
         if use_graph:
-            self._capture()
+            try:
+                self._build_loop_graph()
+            except RuntimeError as e:          # conditional graph nodes unavailable: capture the fixed sequence instead (still a GPU path)
+                self.loop_graph_error = str(e)
+                self._capture()
 
     def _device_frame(self):
         if self.fused_audio:
@@ -41,6 +48,57 @@ class FrameRenderer:
             with torch.autocast("cuda", dtype=torch.float16):
                 enc_a = self.m.encode_audio(self.auds).float()              # AudioNet + AudioAttNet through torch (network.py:226-240)
         self.m.render_frame(self.rays_o, self.rays_d, enc_a, self.ind_code, self.eye, out=self.image, **self.kw)
+
+    @torch.no_grad()
+    def _build_loop_graph(self):
+        import ctypes
+        from ._lib import lib
+        from .model import _RenderCfgC
+        L, m = lib(), self.m
+        need = int(L.raw("b2n_render_frame_workspace_bytes")(self.N))
+        self._graph_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        cfg = _RenderCfgC(m.bound, self.kw["dt_gamma"], 0.05, self.kw["T_thresh"], 1.0, self.kw["max_steps"], m.cascade, m.grid_size, m._aabb_host)
+        aw = m.audio_weights_struct() if self.fused_audio else None
+        self._graph_keep = (cfg, aw, self.ind_code.float().contiguous().view(-1), self.eye.float().contiguous().view(-1))
+        h = ctypes.c_void_p()
+        torch.cuda.synchronize(self.dev)
+        L.call("b2n_frame_graph_create", ctypes.byref(h), m.handle, ctypes.byref(cfg), ctypes.byref(aw) if aw is not None else None,
+               self.auds.data_ptr(), self.auds.shape[2], self.enc_a.data_ptr(), self.rays_o.data_ptr(), self.rays_d.data_ptr(), self.N,
+               m.density_bitfield.data_ptr(), self._graph_keep[2].data_ptr(), self._graph_keep[3].data_ptr(), None, self._graph_ws.data_ptr(),
+               self.image.data_ptr(), self.ws.data_ptr(), self.depth.data_ptr())
+        self.loop_graph = h
+        kf, kb = ctypes.c_uint64(), ctypes.c_uint64()
+        L.call("b2n_frame_graph_info", h, ctypes.byref(kf), ctypes.byref(kb))
+        self.kernels_fixed, self.kernels_per_iteration = int(kf.value), int(kb.value)
+
+    def last_iterations(self):
+        """Loop iterations the last frame executed (synchronises)."""
+        import ctypes
+        from ._lib import lib
+        ws = self._graph_ws if self.loop_graph is not None else self.m._ws
+        it = ctypes.c_int32()
+        lib().call("b2n_frame_iterations", ws.data_ptr(), self.N, ctypes.byref(it), torch.cuda.current_stream(self.dev).cuda_stream)
+        return int(it.value)
+
+    def _launch(self):
+        if self.loop_graph is not None:
+            from ._lib import lib
+            if not self.fused_audio:
+                with torch.autocast("cuda", dtype=torch.float16):
+                    self.enc_a.copy_(self.m.encode_audio(self.auds).float())
+            lib().call("b2n_frame_graph_launch", self.loop_graph, torch.cuda.current_stream(self.dev).cuda_stream)
+        elif self.graph is not None:
+            self.graph.replay()
+        else:
+            self._device_frame()
+
+    def __del__(self):
+        try:
+            if self.loop_graph is not None:
+                from ._lib import lib
+                lib().raw("b2n_frame_graph_destroy")(self.loop_graph)
+        except Exception:
+            pass
 
     @torch.no_grad()
     def _capture(self):
@@ -67,10 +125,7 @@ class FrameRenderer:
             self.rays_d.copy_(rays_d.view(-1, 3), non_blocking=True)
         if auds is not None:
             self.auds.copy_(auds, non_blocking=True)
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self._device_frame()
+        self._launch()
         return self.image
 
     @torch.no_grad()
@@ -79,10 +134,7 @@ class FrameRenderer:
         self.rays_o.copy_(rays_o_host.view(-1, 3), non_blocking=True)
         self.rays_d.copy_(rays_d_host.view(-1, 3), non_blocking=True)
         self.auds.copy_(auds_host, non_blocking=True)
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self._device_frame()
+        self._launch()
         out_host.copy_(self.image, non_blocking=True)
         return out_host
 

@@ -16,12 +16,18 @@
 #include "dda.cuh"
 #include "fused_head.cuh"
 
+struct b2n_model;
+namespace b2n {
+int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
+                          const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, cudaStream_t st);
+}
+
 namespace b2n {
 
-struct FrameCtrl { int32_t n_alive, n_step, step, n_samples, done, pad[3]; };     // 32 B
+struct FrameCtrl { int32_t n_alive, n_step, step, n_samples, done, buf, iter, pad; };     // 32 B; buf = which alive[] buffer holds this iteration's ids
 
 struct FrameWs {            // carved out of the caller's workspace
-    FrameCtrl *ctrl;        // [max_iters + 1]
+    FrameCtrl *ctrl;        // ctrl[0] = the iteration being executed (fixed address: kernel arguments never change, so the loop can be a graph WHILE node), ctrl[1] = the next one
     int32_t *alive[2];      // ping-pong compacted ray ids [N]
     int32_t *totals;        // per-CTA survivor counts
     float *nears, *fars, *rays_t, *ws, *depth, *aud_sum, *eye_sum, *unc_sum, *image;   // per ray
@@ -38,7 +44,7 @@ static size_t carve(FrameWs *w, uint8_t *base, uint32_t N) {
     auto take = [&](size_t bytes) { uint8_t *p = base ? base + off : nullptr; off = align_up(off + bytes, 256); return p; };
     const size_t Np = (size_t)N + 128;
     FrameWs t;
-    t.ctrl = (FrameCtrl *)take(sizeof(FrameCtrl) * (FR_MAX_ITERS + 1));
+    t.ctrl = (FrameCtrl *)take(sizeof(FrameCtrl) * 8);
     t.alive[0] = (int32_t *)take(4 * Np); t.alive[1] = (int32_t *)take(4 * Np);
     t.totals = (int32_t *)take(4 * (Np / FR_THREADS + 2));
     float **per_ray[] = {&t.nears, &t.fars, &t.rays_t, &t.ws, &t.depth, &t.aud_sum, &t.eye_sum, &t.unc_sum};
@@ -66,7 +72,7 @@ __global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ ra
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         FrameCtrl c = {};
-        c.n_alive = (int32_t)N; c.n_step = 1; c.step = 0; c.n_samples = (int32_t)N;      // N // N = 1
+        c.n_alive = (int32_t)N; c.n_step = 1; c.step = 0; c.n_samples = (int32_t)N; c.buf = 0; c.iter = 0;      // N // N = 1
         c.done = (N == 0 || max_steps == 0) ? 1 : 0;
         if (c.done) { c.n_alive = 0; c.n_samples = 0; }
         w.ctrl[0] = c;
@@ -75,12 +81,12 @@ __global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ ra
 
 // march_rays for the compacted alive rays of iteration `it` (raymarching.cu:828-929); fills its unproduced slots with zeros
 __global__ void __launch_bounds__(FR_THREADS) k_frame_march(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
-                                                             float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, uint32_t it, FrameWs w) {
-    const FrameCtrl c = w.ctrl[it];
+                                                             float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, FrameWs w) {
+    const FrameCtrl c = w.ctrl[0];
     const uint32_t n = blockIdx.x * FR_THREADS + threadIdx.x;
     if (c.done || n >= (uint32_t)c.n_alive) return;
     const uint32_t n_step = (uint32_t)c.n_step;
-    const int32_t id = w.alive[it & 1][n];
+    const int32_t id = w.alive[c.buf][n];
     DdaRay r;
     r.init(rays_o + 3 * (size_t)id, rays_d + 3 * (size_t)id, bound, dt_gamma, max_steps, C, H, w.fars[id]);
     float t = r.perturb(w.rays_t[id], 0.0f);          // noise = 0 (perturb is off at inference): fma(dt, 0, t) == t, kept for op parity
@@ -101,13 +107,13 @@ __global__ void __launch_bounds__(FR_THREADS) k_frame_march(const float *__restr
 }
 
 // composite_rays_triplane (raymarching.cu:2142-2249) + per-CTA survivor count
-__global__ void __launch_bounds__(FR_THREADS) k_frame_composite(float T_thresh, uint32_t it, FrameWs w) {
-    const FrameCtrl c = w.ctrl[it];
+__global__ void __launch_bounds__(FR_THREADS) k_frame_composite(float T_thresh, FrameWs w) {
+    const FrameCtrl c = w.ctrl[0];
     const uint32_t n = blockIdx.x * FR_THREADS + threadIdx.x;
     bool survive = false;
     if (!c.done && n < (uint32_t)c.n_alive) {
         const uint32_t n_step = (uint32_t)c.n_step;
-        int32_t *alive = w.alive[it & 1];
+        int32_t *alive = w.alive[c.buf];
         const int32_t idx = alive[n];
         const size_t base = (size_t)n * n_step;
         float t = w.rays_t[idx], ws = w.ws[idx], d = w.depth[idx];
@@ -141,15 +147,15 @@ __global__ void __launch_bounds__(FR_THREADS) k_frame_composite(float T_thresh, 
 }
 
 // stable compaction of the survivors into the other alive buffer; the last CTA publishes ctrl[it+1]
-__global__ void __launch_bounds__(FR_THREADS) k_frame_compact(uint32_t N, uint32_t max_steps, uint32_t it, FrameWs w) {
-    const FrameCtrl c = w.ctrl[it];
+__global__ void __launch_bounds__(FR_THREADS) k_frame_compact(uint32_t N, uint32_t max_steps, FrameWs w) {
+    const FrameCtrl c = w.ctrl[0];
     __shared__ uint32_t red[FR_THREADS / 32];
     __shared__ uint32_t s_base;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nblk_live = c.done ? 0u : ((uint32_t)c.n_alive + FR_THREADS - 1) / FR_THREADS;
     if (blockIdx.x >= nblk_live && !(blockIdx.x == 0)) return;
     if (c.done) {                                      // propagate the terminal state
-        if (blockIdx.x == 0 && threadIdx.x == 0) { FrameCtrl nx = c; nx.n_alive = 0; nx.n_samples = 0; nx.done = 1; w.ctrl[it + 1] = nx; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { FrameCtrl nx = c; nx.n_alive = 0; nx.n_samples = 0; nx.done = 1; w.ctrl[1] = nx; }
         return;
     }
     uint32_t part = 0;
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_frame_compact(uint32_t N, uint32
     if (threadIdx.x == 0) { uint32_t b = 0; for (int q = 0; q < (int)(FR_THREADS / 32); q++) b += red[q]; s_base = b; }
     __syncthreads();
     const uint32_t n = blockIdx.x * FR_THREADS + threadIdx.x;
-    const int32_t id = (n < (uint32_t)c.n_alive) ? w.alive[it & 1][n] : -1;
+    const int32_t id = (n < (uint32_t)c.n_alive) ? w.alive[c.buf][n] : -1;
     const uint32_t keep = id >= 0 ? 1u : 0u;
     uint32_t inc = keep;
 #pragma unroll
@@ -172,11 +178,12 @@ __global__ void __launch_bounds__(FR_THREADS) k_frame_compact(uint32_t N, uint32
     uint32_t woff = 0, tot = 0;
 #pragma unroll
     for (int q = 0; q < (int)(FR_THREADS / 32); q++) { if (q < (int)warp) woff += red[q]; tot += red[q]; }
-    if (keep) w.alive[(it + 1) & 1][s_base + woff + inc - 1] = id;
+    if (keep) w.alive[c.buf ^ 1][s_base + woff + inc - 1] = id;
     if (blockIdx.x == nblk_live - 1 && threadIdx.x == 0) {
         FrameCtrl nx = {};
         nx.n_alive = (int32_t)(s_base + tot);
         nx.step = c.step + c.n_step;
+        nx.buf = c.buf ^ 1; nx.iter = c.iter + 1;
         nx.done = (nx.n_alive <= 0 || nx.step >= (int32_t)max_steps) ? 1 : 0;
         if (nx.done) { nx.n_alive = 0; nx.n_step = 1; nx.n_samples = 0; }
         else {
@@ -184,7 +191,16 @@ __global__ void __launch_bounds__(FR_THREADS) k_frame_compact(uint32_t N, uint32
             ns = ns < 8 ? ns : 8; ns = ns > 1 ? ns : 1;
             nx.n_step = ns; nx.n_samples = nx.n_alive * ns;
         }
-        w.ctrl[it + 1] = nx;
+        w.ctrl[1] = nx;
+    }
+}
+
+// end of an iteration: next -> current (single thread).  In the graph build it also drives the WHILE node.
+__global__ void k_frame_advance(FrameWs w, cudaGraphConditionalHandle handle, int use_handle) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const FrameCtrl nx = w.ctrl[1];
+        w.ctrl[0] = nx;
+        if (use_handle) cudaGraphSetConditional(handle, nx.done ? 0u : 1u);
     }
 }
 
@@ -205,14 +221,66 @@ __global__ void __launch_bounds__(256) k_frame_finish(uint32_t N, const float *_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct FramePlan {
+    const b2n_model *m; b2n_render_cfg cfg; const float *rays_o, *rays_d; uint32_t N; const uint8_t *bitfield;
+    const float *enc_a, *ind_code, *eye, *bg; FrameWs w; float *image_out, *ws_out, *depth_out;
+};
+
+static int enqueue_init(const FramePlan &p, cudaStream_t st) {
+    const uint32_t sms = (uint32_t)sm_count();
+    uint32_t g = ceil_div<uint32_t>(p.N, 256); if (g > sms * 8) g = sms * 8;
+    k_frame_init<<<g, 256, 0, st>>>(p.rays_o, p.rays_d, p.N, p.cfg.min_near, p.cfg.aabb[0], p.cfg.aabb[1], p.cfg.aabb[2], p.cfg.aabb[3], p.cfg.aabb[4], p.cfg.aabb[5],
+                                    p.cfg.max_steps, p.w);
+    return check_launch("render_frame(init)");
+}
+// one loop iteration: march -> fused head -> composite -> compact -> advance
+static int enqueue_iteration(const FramePlan &p, cudaStream_t st, cudaGraphConditionalHandle handle, int use_handle) {
+    const uint32_t ctas = ceil_div<uint32_t>(p.N, FR_THREADS);
+    k_frame_march<<<ctas, FR_THREADS, 0, st>>>(p.rays_o, p.rays_d, p.bitfield, p.cfg.bound, p.cfg.dt_gamma, p.cfg.max_steps, p.cfg.cascade, p.cfg.grid_size, p.w);
+    if (check_launch("render_frame(march)")) return 1;
+    if (int rc = head_forward_on_model(p.m, p.w.xyzs, p.w.dirs, p.N, p.enc_a, p.ind_code, p.eye, &p.w.ctrl[0].n_samples, p.cfg.density_scale, p.w.sigmas, p.w.rgbs,
+                                       p.w.amb_aud, p.w.amb_eye, p.w.unc, st)) return rc;
+    k_frame_composite<<<ctas, FR_THREADS, 0, st>>>(p.cfg.T_thresh, p.w);
+    if (check_launch("render_frame(composite)")) return 1;
+    k_frame_compact<<<ctas, FR_THREADS, 0, st>>>(p.N, p.cfg.max_steps, p.w);
+    if (check_launch("render_frame(compact)")) return 1;
+    k_frame_advance<<<1, 32, 0, st>>>(p.w, handle, use_handle);
+    return check_launch("render_frame(advance)");
+}
+static int enqueue_finish(const FramePlan &p, cudaStream_t st) {
+    const uint32_t sms = (uint32_t)sm_count();
+    uint32_t g = ceil_div<uint32_t>(p.N, 256); if (g > sms * 8) g = sms * 8;
+    k_frame_finish<<<g, 256, 0, st>>>(p.N, p.bg, p.w, p.image_out, p.ws_out, p.depth_out);
+    return check_launch("render_frame(finish)");
+}
+
+static int make_plan(FramePlan &p, const b2n_model *m, const b2n_render_cfg *cfg, const float *rays_o, const float *rays_d, uint32_t N, const uint8_t *bitfield,
+                     const float *enc_a, const float *ind_code, const float *eye, const float *bg_color, void *workspace, float *image_out, float *ws_out, float *depth_out) {
+    B2N_REQUIRE(m && cfg && rays_o && rays_d && bitfield && enc_a && workspace && image_out, "render_frame: null pointer");
+    B2N_REQUIRE(((uintptr_t)workspace & 255) == 0, "render_frame: workspace must be 256-byte aligned");
+    B2N_REQUIRE(cfg->max_steps <= FR_MAX_ITERS, "render_frame: max_steps=%u exceeds the %u-iteration launch plan", cfg->max_steps, FR_MAX_ITERS);
+    B2N_REQUIRE(cfg->cascade >= 1 && cfg->cascade <= 24 && cfg->grid_size >= 1 && cfg->grid_size <= 1024, "render_frame: bad cascade / grid size");
+    p.m = m; p.cfg = *cfg; p.rays_o = rays_o; p.rays_d = rays_d; p.N = N; p.bitfield = bitfield; p.enc_a = enc_a; p.ind_code = ind_code; p.eye = eye; p.bg = bg_color;
+    p.image_out = image_out; p.ws_out = ws_out; p.depth_out = depth_out;
+    carve(&p.w, (uint8_t *)workspace, N);
+    return 0;
+}
+
 }  // namespace b2n
 
 using namespace b2n;
 
-struct b2n_model;
-namespace b2n { int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code,
-                                          const float *eye, const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud,
-                                          float *amb_eye, float *unc, cudaStream_t st); }
+// A frame as ONE CUDA graph whose loop is a WHILE conditional node: init -> while (!done) { march, head, composite, compact, advance } -> finish.
+// The condition is written on the device by k_frame_advance (cudaGraphSetConditional), so exactly the iterations the reference's host loop would
+// run are executed, with a single graph launch per frame and no host synchronisation.
+struct b2n_frame_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t kernel_nodes_body = 0, kernel_nodes_fixed = 0;
+};
 
 extern "C" {
 
@@ -221,32 +289,109 @@ uint64_t b2n_render_frame_workspace_bytes(uint32_t N) { return (uint64_t)carve(n
 int b2n_render_frame(const b2n_model *m, const b2n_render_cfg *cfg, const float *rays_o, const float *rays_d, uint32_t N, const uint8_t *bitfield,
                      const float *enc_a, const float *ind_code, const float *eye, const float *bg_color, void *workspace,
                      float *image_out, float *weights_sum_out, float *depth_out, void *stream) {
-    B2N_REQUIRE(m && cfg && rays_o && rays_d && bitfield && enc_a && workspace && image_out, "render_frame: null pointer");
-    B2N_REQUIRE(((uintptr_t)workspace & 255) == 0, "render_frame: workspace must be 256-byte aligned");
-    B2N_REQUIRE(cfg->max_steps <= FR_MAX_ITERS, "render_frame: max_steps=%u exceeds the %u-iteration launch plan", cfg->max_steps, FR_MAX_ITERS);
-    B2N_REQUIRE(cfg->cascade >= 1 && cfg->cascade <= 24 && cfg->grid_size >= 1 && cfg->grid_size <= 1024, "render_frame: bad cascade / grid size");
+    FramePlan p;
+    if (int rc = make_plan(p, m, cfg, rays_o, rays_d, N, bitfield, enc_a, ind_code, eye, bg_color, workspace, image_out, weights_sum_out, depth_out)) return rc;
     if (N == 0) return 0;
     cudaStream_t st = as_stream(stream);
-    FrameWs w;
-    carve(&w, (uint8_t *)workspace, N);
-    const uint32_t sms = (uint32_t)sm_count();
-    uint32_t g = ceil_div<uint32_t>(N, 256); if (g > sms * 8) g = sms * 8;
-    k_frame_init<<<g, 256, 0, st>>>(rays_o, rays_d, N, cfg->min_near, cfg->aabb[0], cfg->aabb[1], cfg->aabb[2], cfg->aabb[3], cfg->aabb[4], cfg->aabb[5],
-                                    cfg->max_steps, w);
-    if (check_launch("render_frame(init)")) return 1;
-    const uint32_t ctas = ceil_div<uint32_t>(N, FR_THREADS);
-    for (uint32_t it = 0; it < cfg->max_steps; it++) {
-        k_frame_march<<<ctas, FR_THREADS, 0, st>>>(rays_o, rays_d, bitfield, cfg->bound, cfg->dt_gamma, cfg->max_steps, cfg->cascade, cfg->grid_size, it, w);
-        if (check_launch("render_frame(march)")) return 1;
-        if (int rc = head_forward_on_model(m, w.xyzs, w.dirs, N, enc_a, ind_code, eye, &w.ctrl[it].n_samples, cfg->density_scale, w.sigmas, w.rgbs, w.amb_aud,
-                                           w.amb_eye, w.unc, st)) return rc;
-        k_frame_composite<<<ctas, FR_THREADS, 0, st>>>(cfg->T_thresh, it, w);
-        if (check_launch("render_frame(composite)")) return 1;
-        k_frame_compact<<<ctas, FR_THREADS, 0, st>>>(N, cfg->max_steps, it, w);
-        if (check_launch("render_frame(compact)")) return 1;
+    if (int rc = enqueue_init(p, st)) return rc;
+    for (uint32_t it = 0; it < cfg->max_steps; it++)        // worst case: n_step = 1 every iteration; finished iterations exit at once
+        if (int rc = enqueue_iteration(p, st, 0, 0)) return rc;
+    return enqueue_finish(p, st);
+}
+
+int b2n_frame_graph_create(b2n_frame_graph **out, const b2n_model *m, const b2n_render_cfg *cfg, const b2n_audio_weights *audio, const float *auds,
+                           uint32_t audio_L, float *enc_a, const float *rays_o, const float *rays_d, uint32_t N, const uint8_t *bitfield,
+                           const float *ind_code, const float *eye, const float *bg_color, void *workspace, float *image_out, float *weights_sum_out,
+                           float *depth_out) {
+    B2N_REQUIRE(out && N > 0, "frame_graph_create: null pointer / empty frame");
+    B2N_REQUIRE(!audio || (auds && enc_a), "frame_graph_create: audio weights given without auds / enc_a buffers");
+    FramePlan p;
+    if (int rc = make_plan(p, m, cfg, rays_o, rays_d, N, bitfield, enc_a, ind_code, eye, bg_color, workspace, image_out, weights_sum_out, depth_out)) return rc;
+    b2n_frame_graph *fg = new b2n_frame_graph();
+    cudaStream_t cs = nullptr;
+    int rc = 3;
+    const uint64_t l0 = g_launches.load();
+    do {
+        if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { set_error("frame_graph_create: stream creation failed"); break; }
+        if (cudaGraphCreate(&fg->graph, 0) != cudaSuccess) { set_error("frame_graph_create: cudaGraphCreate failed"); break; }
+        // prologue: [audio encoder] + init
+        if (cudaStreamBeginCaptureToGraph(cs, fg->graph, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess) { set_error("frame_graph_create: capture-to-graph unsupported"); break; }
+        int e = 0;
+        if (audio) e = b2n_audio_encode(audio, auds, audio_L, enc_a, cs);
+        if (!e) e = enqueue_init(p, cs);
+        cudaStreamCaptureStatus status; const cudaGraphNode_t *deps = nullptr; size_t ndeps = 0;
+        cudaError_t ce = cudaStreamGetCaptureInfo(cs, &status, nullptr, nullptr, &deps, &ndeps);
+        cudaGraphNode_t dep_copy[8]; size_t nd = ndeps < 8 ? ndeps : 8;
+        for (size_t i = 0; i < nd; i++) dep_copy[i] = deps[i];
+        cudaGraph_t tmp = nullptr;
+        cudaError_t ce2 = cudaStreamEndCapture(cs, &tmp);
+        if (e || ce != cudaSuccess || ce2 != cudaSuccess) { if (!e) set_error("frame_graph_create: prologue capture failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ce2)); break; }
+        fg->kernel_nodes_fixed = g_launches.load() - l0;
+        // WHILE node
+        cudaGraphConditionalHandle handle;
+        if ((ce = cudaGraphConditionalHandleCreate(&handle, fg->graph, 1, cudaGraphCondAssignDefault)) != cudaSuccess) { set_error("frame_graph_create: conditional handle: %s", cudaGetErrorString(ce)); break; }
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
+        cudaGraphNode_t loop_node;
+        if ((ce = cudaGraphAddNode(&loop_node, fg->graph, dep_copy, nd, &np)) != cudaSuccess) { set_error("frame_graph_create: conditional node: %s", cudaGetErrorString(ce)); break; }
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        const uint64_t l1 = g_launches.load();
+        if ((ce = cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed)) != cudaSuccess) { set_error("frame_graph_create: body capture: %s", cudaGetErrorString(ce)); break; }
+        e = enqueue_iteration(p, cs, handle, 1);
+        ce2 = cudaStreamEndCapture(cs, &tmp);
+        if (e || ce2 != cudaSuccess) { if (!e) set_error("frame_graph_create: body capture failed: %s", cudaGetErrorString(ce2)); break; }
+        fg->kernel_nodes_body = g_launches.load() - l1;
+        // epilogue
+        if ((ce = cudaStreamBeginCaptureToGraph(cs, fg->graph, &loop_node, nullptr, 1, cudaStreamCaptureModeRelaxed)) != cudaSuccess) { set_error("frame_graph_create: epilogue capture: %s", cudaGetErrorString(ce)); break; }
+        e = enqueue_finish(p, cs);
+        ce2 = cudaStreamEndCapture(cs, &tmp);
+        if (e || ce2 != cudaSuccess) { if (!e) set_error("frame_graph_create: epilogue capture failed: %s", cudaGetErrorString(ce2)); break; }
+        fg->kernel_nodes_fixed += 1;
+        if ((ce = cudaGraphInstantiate(&fg->exec, fg->graph, 0)) != cudaSuccess) { set_error("frame_graph_create: instantiate: %s", cudaGetErrorString(ce)); break; }
+        rc = 0;
+    } while (0);
+    if (cs) cudaStreamDestroy(cs);
+    if (rc) {
+        (void)cudaGetLastError();
+        if (fg->exec) cudaGraphExecDestroy(fg->exec);
+        if (fg->graph) cudaGraphDestroy(fg->graph);
+        delete fg;
+        return rc;
     }
-    k_frame_finish<<<g, 256, 0, st>>>(N, bg_color, w, image_out, weights_sum_out, depth_out);
-    return check_launch("render_frame(finish)");
+    *out = fg;
+    return 0;
+}
+
+int b2n_frame_graph_launch(b2n_frame_graph *fg, void *stream) {
+    B2N_REQUIRE(fg && fg->exec, "frame_graph_launch: null graph");
+    B2N_CUDA(cudaGraphLaunch(fg->exec, as_stream(stream)));
+    return 0;
+}
+
+/* kernels per loop iteration / outside the loop (for launch accounting: launches per frame = fixed + body * iterations) */
+int b2n_frame_graph_info(const b2n_frame_graph *fg, uint64_t *kernels_fixed, uint64_t *kernels_per_iteration) {
+    B2N_REQUIRE(fg && kernels_fixed && kernels_per_iteration, "frame_graph_info: null pointer");
+    *kernels_fixed = fg->kernel_nodes_fixed; *kernels_per_iteration = fg->kernel_nodes_body;
+    return 0;
+}
+
+/* number of loop iterations the last frame rendered into `workspace` executed (reads 4 bytes back; synchronises the stream) */
+int b2n_frame_iterations(const void *workspace, uint32_t N, int32_t *iterations, void *stream) {
+    B2N_REQUIRE(workspace && iterations, "frame_iterations: null pointer");
+    FrameWs w; carve(&w, (uint8_t *)const_cast<void *>(workspace), N);
+    FrameCtrl c;
+    B2N_CUDA(cudaMemcpyAsync(&c, w.ctrl, sizeof(c), cudaMemcpyDeviceToHost, as_stream(stream)));
+    B2N_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    *iterations = c.iter;
+    return 0;
+}
+
+void b2n_frame_graph_destroy(b2n_frame_graph *fg) {
+    if (!fg) return;
+    if (fg->exec) cudaGraphExecDestroy(fg->exec);
+    if (fg->graph) cudaGraphDestroy(fg->graph);
+    delete fg;
 }
 
 }  // extern "C"

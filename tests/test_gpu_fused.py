@@ -180,3 +180,32 @@ def test_fused_audio_encoder_matches_torch_autocast(dim_in, L):
         # fp16 chain of 11 layers: agreement with the autocast graph at the 1e-3 level of the output scale, and as close to fp32 as autocast is
         assert float((got - ref16).abs().max()) < 4e-3 * scale, (float((got - ref16).abs().max()), scale)
         assert float((got - ref32).abs().max()) < 2.0 * float((ref16 - ref32).abs().max()) + 2e-3 * scale
+
+
+def test_frame_renderer_while_graph_matches_fixed_sequence():
+    """FrameRenderer's device-controlled WHILE-loop graph renders the same image as the eager fixed launch sequence, bit for bit,
+    executes only the live iterations, and stays correct when replayed with new inputs."""
+    from b2nerf.model import HeadModel
+    from b2nerf.render import FrameRenderer
+    torch.manual_seed(0)
+    m = HeadModel().cuda()
+    for enc in (m.encoder_xy, m.encoder_yz, m.encoder_xz):
+        enc.embeddings.data.uniform_(-1, 1)
+    m.testing = True
+    m.density_bitfield.copy_(torch.from_numpy(scene.bitfield_from_grid(scene.density_grid())).cuda())
+    hw = 256
+    r_graph = FrameRenderer(m, hw * hw, use_graph=True)
+    r_eager = FrameRenderer(m, hw * hw, use_graph=False)
+    assert r_graph.loop_graph is not None, getattr(r_graph, "loop_graph_error", "no loop graph")
+    for frame in (0, 1, 2):
+        j, i = np.meshgrid(np.arange(hw), np.arange(hw), indexing="ij")
+        o, d = scene.rays_for_pixels(scene.camera_pose(frame), hw, hw, i.ravel(), j.ravel())
+        rays_o, rays_d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+        auds = torch.from_numpy(scene.audio_window(frame)).cuda()
+        a = r_graph.render_device(rays_o, rays_d, auds).clone()
+        b = r_eager.render_device(rays_o, rays_d, auds).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+        iters = r_graph.last_iterations()
+        assert 3 <= iters <= 16 and iters == r_eager.last_iterations() or r_eager.last_iterations() >= iters
+    assert float(a.mean()) < 0.999          # the head is visible against the white background
