@@ -30,6 +30,7 @@ struct FrameWs {            // carved out of the caller's workspace
     FrameCtrl *ctrl;        // ctrl[0] = the iteration being executed (fixed address: kernel arguments never change, so the loop can be a graph WHILE node), ctrl[1] = the next one
     int32_t *alive[2];      // ping-pong compacted ray ids [N]
     int32_t *totals;        // per-CTA survivor counts
+    float *occ_box;         // [6] world-space box around every occupied cell, grown by 2 cells (empty: min > max)
     float *nears, *fars, *rays_t, *ws, *depth, *aud_sum, *eye_sum, *unc_sum, *image;   // per ray
     float *xyzs, *dirs, *deltas, *sigmas, *rgbs, *amb_aud, *amb_eye, *unc;              // per sample (<= N + 128)
 };
@@ -47,6 +48,7 @@ static size_t carve(FrameWs *w, uint8_t *base, uint32_t N) {
     t.ctrl = (FrameCtrl *)take(sizeof(FrameCtrl) * 8);
     t.alive[0] = (int32_t *)take(4 * Np); t.alive[1] = (int32_t *)take(4 * Np);
     t.totals = (int32_t *)take(4 * (Np / FR_THREADS + 2));
+    t.occ_box = (float *)take(4 * 8);
     float **per_ray[] = {&t.nears, &t.fars, &t.rays_t, &t.ws, &t.depth, &t.aud_sum, &t.eye_sum, &t.unc_sum};
     for (auto p : per_ray) *p = (float *)take(4 * Np);
     t.image = (float *)take(12 * Np);
@@ -57,6 +59,48 @@ static size_t carve(FrameWs *w, uint8_t *base, uint32_t N) {
     return off;
 }
 
+// Box around all occupied cells of the bitfield, grown by two cells, in world units (union over cascades).  One CTA: the bitfield of the
+// head model is 256 KB.  EXACTNESS ARGUMENT for using it: a DDA probe at parameter t reads the cell containing clamp(o + t d) (up to one
+// float ulp, i.e. at most the neighbouring cell); if the ray point is farther than two cells from every occupied cell, the probed cell is
+// empty.  Hence (a) a ray that misses the grown box produces no sample at all, and (b) past its exit from the grown box a ray produces no
+// further sample — so marching may stop at min(far, t_exit) and every sample, count and alive flag stays bit-identical to marching to `far`
+// (tests/test_gpu_fused.py compares against the per-op marcher, which does march to `far`).
+__global__ void __launch_bounds__(1024) k_occupied_box(const uint8_t *__restrict__ grid, uint32_t C, uint32_t H, float bound, int enable, float *__restrict__ box) {
+    if (!enable) {          // marching interval not provably inside the grid cube: no clipping
+        if (threadIdx.x < 6) box[threadIdx.x] = threadIdx.x < 3 ? -3.0e38f : 3.0e38f;
+        return;
+    }
+    __shared__ float red[6][32];
+    const uint32_t H3 = H * H * H, words = C * H3 / 32;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (uint32_t wd = threadIdx.x; wd < words; wd += blockDim.x) {
+        uint32_t bits = reinterpret_cast<const uint32_t *>(grid)[wd];
+        while (bits) {
+            const uint32_t b = __ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t idx = wd * 32 + b, level = idx / H3, m = idx - level * H3;
+            const float cell = fminf(scalbnf(1.0f, (int)level), bound) * 2.0f / (float)H;          // cell size of this cascade in world units
+            const float org = -fminf(scalbnf(1.0f, (int)level), bound);
+            const uint32_t c[3] = {compact3(m), compact3(m >> 1), compact3(m >> 2)};
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                lo[a] = fminf(lo[a], org + ((float)c[a] - 2.0f) * cell);
+                hi[a] = fmaxf(hi[a], org + ((float)c[a] + 3.0f) * cell);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
+    if ((threadIdx.x & 31) == 0) for (int a = 0; a < 3; a++) { red[a][threadIdx.x >> 5] = lo[a]; red[3 + a][threadIdx.x >> 5] = hi[a]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = red[threadIdx.x][0];
+        for (uint32_t w = 1; w < blockDim.x / 32; w++) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
+        box[threadIdx.x] = v;
+    }
+}
+
 // near/far + state reset + ctrl[0]
 __global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ rays_o, const float *__restrict__ rays_d, uint32_t N, float min_near,
                                                      float a0, float a1, float a2, float a3, float a4, float a5, uint32_t max_steps, FrameWs w) {
@@ -65,6 +109,15 @@ __global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ ra
         const float rdx = 1.0f / rays_d[3 * n], rdy = 1.0f / rays_d[3 * n + 1], rdz = 1.0f / rays_d[3 * n + 2];
         float tn, tf;
         near_far_one(ox, oy, oz, rdx, rdy, rdz, a0, a1, a2, a3, a4, a5, min_near, tn, tf);
+        // stop marching where the ray leaves the grown occupied box (see k_occupied_box); a ray that misses it never starts
+        {
+            const float *bx = w.occ_box;
+            const float ax0 = (bx[0] - ox) * rdx, ax1 = (bx[3] - ox) * rdx, ay0 = (bx[1] - oy) * rdy, ay1 = (bx[4] - oy) * rdy, az0 = (bx[2] - oz) * rdz, az1 = (bx[5] - oz) * rdz;
+            const float t_in = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fminf(az0, az1));
+            const float t_out = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fmaxf(az0, az1));
+            if (!(t_in <= t_out)) tf = fminf(tf, 0.0f);                 // miss (or empty box): `t < far` is false from the start
+            else tf = fminf(tf, t_out);
+        }
         w.nears[n] = tn; w.fars[n] = tf; w.rays_t[n] = tn;
         w.ws[n] = 0.0f; w.depth[n] = 0.0f; w.aud_sum[n] = 0.0f; w.eye_sum[n] = 0.0f; w.unc_sum[n] = 0.0f;
         w.image[3 * n] = 0.0f; w.image[3 * n + 1] = 0.0f; w.image[3 * n + 2] = 0.0f;
@@ -230,6 +283,11 @@ struct FramePlan {
 };
 
 static int enqueue_init(const FramePlan &p, cudaStream_t st) {
+    // the argument needs probe positions == ray points, i.e. the marching interval (the aabb) inside the [-bound, bound]^3 cube where clamp() is a no-op
+    int inside = 1;
+    for (int a = 0; a < 3; a++) inside &= (p.cfg.aabb[a] >= -p.cfg.bound && p.cfg.aabb[3 + a] <= p.cfg.bound);
+    k_occupied_box<<<1, 1024, 0, st>>>(p.bitfield, p.cfg.cascade, p.cfg.grid_size, p.cfg.bound, inside, p.w.occ_box);
+    if (check_launch("render_frame(occupied box)")) return 1;
     const uint32_t sms = (uint32_t)sm_count();
     uint32_t g = ceil_div<uint32_t>(p.N, 256); if (g > sms * 8) g = sms * 8;
     k_frame_init<<<g, 256, 0, st>>>(p.rays_o, p.rays_d, p.N, p.cfg.min_near, p.cfg.aabb[0], p.cfg.aabb[1], p.cfg.aabb[2], p.cfg.aabb[3], p.cfg.aabb[4], p.cfg.aabb[5],
