@@ -19,7 +19,8 @@
 struct b2n_model;
 namespace b2n {
 int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
-                          const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, cudaStream_t st);
+                          const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, cudaStream_t st,
+                          const float *live_deltas = nullptr);
 }
 
 namespace b2n {
@@ -48,7 +49,7 @@ static size_t carve(FrameWs *w, uint8_t *base, uint32_t N) {
     t.ctrl = (FrameCtrl *)take(sizeof(FrameCtrl) * 8);
     t.alive[0] = (int32_t *)take(4 * Np); t.alive[1] = (int32_t *)take(4 * Np);
     t.totals = (int32_t *)take(4 * (Np / FR_THREADS + 2));
-    t.occ_box = (float *)take(4 * 8);
+    t.occ_box = (float *)take(4 * 6 * 128);      // per-CTA partial boxes of k_occupied_box (reduced by every CTA of k_frame_init)
     float **per_ray[] = {&t.nears, &t.fars, &t.rays_t, &t.ws, &t.depth, &t.aud_sum, &t.eye_sum, &t.unc_sum};
     for (auto p : per_ray) *p = (float *)take(4 * Np);
     t.image = (float *)take(12 * Np);
@@ -65,26 +66,27 @@ static size_t carve(FrameWs *w, uint8_t *base, uint32_t N) {
 // empty.  Hence (a) a ray that misses the grown box produces no sample at all, and (b) past its exit from the grown box a ray produces no
 // further sample — so marching may stop at min(far, t_exit) and every sample, count and alive flag stays bit-identical to marching to `far`
 // (tests/test_gpu_fused.py compares against the per-op marcher, which does march to `far`).
-__global__ void __launch_bounds__(1024) k_occupied_box(const uint8_t *__restrict__ grid, uint32_t C, uint32_t H, float bound, int enable, float *__restrict__ box) {
-    if (!enable) {          // marching interval not provably inside the grid cube: no clipping
-        if (threadIdx.x < 6) box[threadIdx.x] = threadIdx.x < 3 ? -3.0e38f : 3.0e38f;
-        return;
-    }
-    __shared__ float red[6][32];
+constexpr uint32_t OCC_PARTS = 128;
+__global__ void __launch_bounds__(256) k_occupied_box(const uint8_t *__restrict__ grid, uint32_t C, uint32_t H, float bound, int enable, float *__restrict__ parts) {
+    __shared__ float red[6][8];
     const uint32_t H3 = H * H * H, words = C * H3 / 32;
     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (uint32_t wd = threadIdx.x; wd < words; wd += blockDim.x) {
-        uint32_t bits = reinterpret_cast<const uint32_t *>(grid)[wd];
-        while (bits) {
-            const uint32_t b = __ffs(bits) - 1; bits &= bits - 1;
-            const uint32_t idx = wd * 32 + b, level = idx / H3, m = idx - level * H3;
-            const float cell = fminf(scalbnf(1.0f, (int)level), bound) * 2.0f / (float)H;          // cell size of this cascade in world units
-            const float org = -fminf(scalbnf(1.0f, (int)level), bound);
-            const uint32_t c[3] = {compact3(m), compact3(m >> 1), compact3(m >> 2)};
+    if (!enable) {          // marching interval not provably inside the grid cube: no clipping
+        lo[0] = lo[1] = lo[2] = -3.0e38f; hi[0] = hi[1] = hi[2] = 3.0e38f;
+    } else {
+        for (uint32_t wd = blockIdx.x * blockDim.x + threadIdx.x; wd < words; wd += gridDim.x * blockDim.x) {
+            uint32_t bits = __ldg(reinterpret_cast<const uint32_t *>(grid) + wd);
+            while (bits) {
+                const uint32_t b = __ffs(bits) - 1; bits &= bits - 1;
+                const uint32_t idx = wd * 32 + b, level = idx / H3, m = idx - level * H3;
+                const float mb = fminf(scalbnf(1.0f, (int)level), bound);
+                const float cell = mb * 2.0f / (float)H;                // cell size of this cascade in world units
+                const uint32_t c[3] = {compact3(m), compact3(m >> 1), compact3(m >> 2)};
 #pragma unroll
-            for (int a = 0; a < 3; a++) {
-                lo[a] = fminf(lo[a], org + ((float)c[a] - 2.0f) * cell);
-                hi[a] = fmaxf(hi[a], org + ((float)c[a] + 3.0f) * cell);
+                for (int a = 0; a < 3; a++) {
+                    lo[a] = fminf(lo[a], -mb + ((float)c[a] - 2.0f) * cell);
+                    hi[a] = fmaxf(hi[a], -mb + ((float)c[a] + 3.0f) * cell);
+                }
             }
         }
     }
@@ -97,13 +99,20 @@ __global__ void __launch_bounds__(1024) k_occupied_box(const uint8_t *__restrict
     if (threadIdx.x < 6) {
         float v = red[threadIdx.x][0];
         for (uint32_t w = 1; w < blockDim.x / 32; w++) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
-        box[threadIdx.x] = v;
+        parts[blockIdx.x * 6 + threadIdx.x] = v;
     }
 }
 
 // near/far + state reset + ctrl[0]
 __global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ rays_o, const float *__restrict__ rays_d, uint32_t N, float min_near,
                                                      float a0, float a1, float a2, float a3, float a4, float a5, uint32_t max_steps, FrameWs w) {
+    __shared__ float bx[6];
+    if (threadIdx.x < 6) {
+        float v = w.occ_box[threadIdx.x];
+        for (uint32_t q = 1; q < OCC_PARTS; q++) v = threadIdx.x < 3 ? fminf(v, w.occ_box[q * 6 + threadIdx.x]) : fmaxf(v, w.occ_box[q * 6 + threadIdx.x]);
+        bx[threadIdx.x] = v;
+    }
+    __syncthreads();
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
         const float ox = rays_o[3 * n], oy = rays_o[3 * n + 1], oz = rays_o[3 * n + 2];
         const float rdx = 1.0f / rays_d[3 * n], rdy = 1.0f / rays_d[3 * n + 1], rdz = 1.0f / rays_d[3 * n + 2];
@@ -111,7 +120,6 @@ __global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ ra
         near_far_one(ox, oy, oz, rdx, rdy, rdz, a0, a1, a2, a3, a4, a5, min_near, tn, tf);
         // stop marching where the ray leaves the grown occupied box (see k_occupied_box); a ray that misses it never starts
         {
-            const float *bx = w.occ_box;
             const float ax0 = (bx[0] - ox) * rdx, ax1 = (bx[3] - ox) * rdx, ay0 = (bx[1] - oy) * rdy, ay1 = (bx[4] - oy) * rdy, az0 = (bx[2] - oz) * rdz, az1 = (bx[5] - oz) * rdz;
             const float t_in = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fminf(az0, az1));
             const float t_out = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fmaxf(az0, az1));
@@ -286,7 +294,7 @@ static int enqueue_init(const FramePlan &p, cudaStream_t st) {
     // the argument needs probe positions == ray points, i.e. the marching interval (the aabb) inside the [-bound, bound]^3 cube where clamp() is a no-op
     int inside = 1;
     for (int a = 0; a < 3; a++) inside &= (p.cfg.aabb[a] >= -p.cfg.bound && p.cfg.aabb[3 + a] <= p.cfg.bound);
-    k_occupied_box<<<1, 1024, 0, st>>>(p.bitfield, p.cfg.cascade, p.cfg.grid_size, p.cfg.bound, inside, p.w.occ_box);
+    k_occupied_box<<<OCC_PARTS, 256, 0, st>>>(p.bitfield, p.cfg.cascade, p.cfg.grid_size, p.cfg.bound, inside, p.w.occ_box);
     if (check_launch("render_frame(occupied box)")) return 1;
     const uint32_t sms = (uint32_t)sm_count();
     uint32_t g = ceil_div<uint32_t>(p.N, 256); if (g > sms * 8) g = sms * 8;
@@ -300,7 +308,7 @@ static int enqueue_iteration(const FramePlan &p, cudaStream_t st, cudaGraphCondi
     k_frame_march<<<ctas, FR_THREADS, 0, st>>>(p.rays_o, p.rays_d, p.bitfield, p.cfg.bound, p.cfg.dt_gamma, p.cfg.max_steps, p.cfg.cascade, p.cfg.grid_size, p.w);
     if (check_launch("render_frame(march)")) return 1;
     if (int rc = head_forward_on_model(p.m, p.w.xyzs, p.w.dirs, p.N, p.enc_a, p.ind_code, p.eye, &p.w.ctrl[0].n_samples, p.cfg.density_scale, p.w.sigmas, p.w.rgbs,
-                                       p.w.amb_aud, p.w.amb_eye, p.w.unc, st)) return rc;
+                                       p.w.amb_aud, p.w.amb_eye, p.w.unc, st, p.w.deltas)) return rc;
     k_frame_composite<<<ctas, FR_THREADS, 0, st>>>(p.cfg.T_thresh, p.w);
     if (check_launch("render_frame(composite)")) return 1;
     k_frame_compact<<<ctas, FR_THREADS, 0, st>>>(p.N, p.cfg.max_steps, p.w);

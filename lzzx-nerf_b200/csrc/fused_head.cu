@@ -76,9 +76,11 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // (+bias, ReLU) and writes them as halves k0.. of row `row` of a SWIZZLE_128B tile.  Deliberately NOT inlined and rolled over
 // 16-column blocks: the kernel has five of these epilogues and four warpgroups in different phases, so code size (I-cache
 // footprint) matters more than the few loop instructions.
-__device__ __noinline__ void hidden_epilogue(uint32_t taddr, uint32_t ncols, uint8_t *tile, uint32_t row, uint32_t k0, bool relu, const float *bias) {
+template <bool RELU, bool BIAS>
+__device__ __noinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, uint32_t row, const float *bias) {
+    const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll 1
-    for (uint32_t cb = 0; cb < ncols; cb += 32) {
+    for (uint32_t cb = 0; cb < 64; cb += 32) {
         uint32_t acc[32];
         ld32(taddr + cb, acc);
         wait_ld();
@@ -88,12 +90,12 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, uint32_t ncols, uin
 #pragma unroll
             for (uint32_t j = 0; j < 4; j++) {
                 float x0 = __uint_as_float(acc[c * 8 + 2 * j]), x1 = __uint_as_float(acc[c * 8 + 2 * j + 1]);
-                if (bias) { x0 += bias[cb + c * 8 + 2 * j]; x1 += bias[cb + c * 8 + 2 * j + 1]; }
+                if (BIAS) { x0 += bias[cb + c * 8 + 2 * j]; x1 += bias[cb + c * 8 + 2 * j + 1]; }
                 __half2 h = __floats2half2_rn(x0, x1);
-                if (relu) h = __hmax2(h, __float2half2_rn(0.0f));          // relu(round(x)) == round(relu(x))
+                if (RELU) h = __hmax2(h, zero);                              // relu(round(x)) == round(relu(x))
                 w[j] = *reinterpret_cast<uint32_t *>(&h);
             }
-            *reinterpret_cast<uint4 *>(tile + sw128_offset(row, ((k0 + cb) >> 3) + c)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(tile + sw128_offset(row, (cb >> 3) + c)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
 }
@@ -141,6 +143,7 @@ struct HeadSmem {                       // lives after the 1024-aligned weight i
     float eye_w1[16], unc_w1[32], ind_bias[64];
     float eye_val;
     uint32_t n_valid;
+    uint32_t tile_live[HG_WGS];
     uint32_t tmem_base;
     uint64_t bar_w;                     // weight image landed
     uint64_t bar_mma[HG_WGS];           // per-warpgroup MMA completion
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         bulk_g2s(s_w, a.wimg, HW_BYTES, &S.bar_w);
         S.n_valid = a.n_valid ? (uint32_t)max(0, min((int)a.M, *a.n_valid)) : a.M;
         S.eye_val = a.eye ? a.eye[0] : 0.0f;
+        for (int g = 0; g < (int)HG_WGS; g++) S.tile_live[g] = 0;
     }
     if (warp == 1) tmem_alloc(&S.tmem_base, 512);
     if (tid >= 128 && tid < 160) S.enc_a_h[tid - 128] = round_h(a.enc_a[tid - 128]);
@@ -201,7 +205,18 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
 
     for (uint32_t tile = blockIdx.x * HG_WGS + wg; tile < n_tiles; tile += gridDim.x * HG_WGS) {
         const uint32_t m = tile * HG_TILE + t;
-        const bool live = m < n_valid;
+        bool live = m < n_valid;
+        if (a.live_deltas) {
+            // frame mode: a row whose march slot was not produced (delta == 0) is ignored by the composite; a tile made only of such
+            // rows (rays outside the head, rays that ran out) is skipped altogether
+            live = live && (__ldg(a.live_deltas + 2 * (size_t)m) != 0.0f);
+            if (__any_sync(0xffffffffu, live)) S.tile_live[wg] = 1;
+            sync_wg();
+            const uint32_t any_live = S.tile_live[wg];
+            sync_wg();
+            if (t == 0) S.tile_live[wg] = 0;
+            if (!any_live) continue;
+        }
         // ---- P0: gather 36 tri-plane features -> X (fp16, K padded to 48) ---------------------------------------------
         float px = 0, py = 0, pz = 0, dxv = 0, dyv = 0, dzv = 1;
         if (live) {
@@ -254,7 +269,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         float eye_att, unc_out = 0.6931471805599453f;       // testing: log(1 + e^0) (network.py:245,278)
         {
             uint32_t acc[32];
-            hidden_epilogue(tmem_ld + 0, 64, sH, t, 0, true, nullptr);
+            hidden_epilogue<true, false>(tmem_ld + 0, sH, t, nullptr);
             uint32_t e16[16];
             ld16(tmem_ld + 64, e16); wait_ld();
             float dot = 0.0f;
@@ -304,19 +319,19 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         // ---- P3: sigma hidden += [enc_w, e] * WC -------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 64, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
         mma_done();
-        hidden_epilogue(tmem_ld + 64, 64, sH, t, 0, true, nullptr);
+        hidden_epilogue<true, false>(tmem_ld + 64, sH, t, nullptr);
         publish();
         // ---- P4: sigma layer 1 --------------------------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 0, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
         mma_done();
-        hidden_epilogue(tmem_ld + 0, 64, sH, t, 0, true, nullptr);
+        hidden_epilogue<true, false>(tmem_ld + 0, sH, t, nullptr);
         publish();
         // ---- P5: sigma layer 2: cols 0..63 = geo_feat, col 64 = density logit (rows rotated at pack time) -----------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 0, sH_a, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
         mma_done();
         float sigma;
         {
-            hidden_epilogue(tmem_ld + 0, 64, sH, t, 0, false, nullptr);
+            hidden_epilogue<false, false>(tmem_ld + 0, sH, t, nullptr);
             uint32_t s16[16];
             ld16(tmem_ld + 64, s16); wait_ld();
             sigma = expf(round_h(__uint_as_float(s16[0]))) * a.density_scale;       // torch.exp(h[..., 0]) in fp32 (network.py:301)
@@ -336,7 +351,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             mma_commit(bar);
         }
         mma_done();
-        hidden_epilogue(tmem_ld + 0, 64, sH, t, 0, true, S.ind_bias);
+        hidden_epilogue<true, true>(tmem_ld + 0, sH, t, S.ind_bias);
         publish();
         // ---- P7: color layer 1 (N padded 3 -> 16) -----------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 64, sH_a, sW_a + HW_G, 4, 16, false); mma_commit(bar); }
@@ -497,7 +512,8 @@ int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
 
 namespace b2n {
 int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
-                          const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, cudaStream_t st) {
+                          const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, cudaStream_t st,
+                          const float *live_deltas) {
     B2N_REQUIRE(m && m->ready, "head_forward: model has no weights (call b2n_model_update)");
     B2N_REQUIRE(xyzs && dirs && enc_a, "head_forward: null pointer");
     if (M == 0) return 0;
@@ -519,7 +535,7 @@ extern "C" {
 
 int b2n_head_forward(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
                      const int32_t *n_valid, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, void *stream) {
-    return head_forward_on_model(m, xyzs, dirs, M, enc_a, ind_code, eye, n_valid, 1.0f, sigmas, rgbs, amb_aud, amb_eye, unc, as_stream(stream));
+    return head_forward_on_model(m, xyzs, dirs, M, enc_a, ind_code, eye, n_valid, 1.0f, sigmas, rgbs, amb_aud, amb_eye, unc, as_stream(stream), nullptr);
 }
 
 }  // extern "C"

@@ -36,6 +36,7 @@ struct HeadArgs {
     const float *xyzs, *dirs;
     uint32_t M;
     const int32_t *n_valid;
+    const float *live_deltas;   // optional deltas[M,2]: rows with deltas[m,0] == 0 are unproduced march slots; tiles made only of such rows are skipped
     const float *tab[3];
     HeadLvl lvl[12];
     float bound;
