@@ -3,12 +3,15 @@
 // The reference drives its march / network / composite loop from the host and reads the alive-ray count back every
 // iteration (rays_alive[rays_alive >= 0], renderer.py:542 — 16 D2H syncs per frame).  Here the loop state lives in a
 // small device-side control block per iteration:
-//     ctrl[it] = { n_alive, n_step, step, n_samples, done }
-// and the host enqueues a FIXED sequence of launches (max_steps iterations; kernels of iterations after the loop has
-// ended exit at once), so a frame is capturable in a CUDA graph.  Semantics per iteration are the reference's:
+//     ctrl = { n_alive, n_step, step, n_samples, done, ... }
+// rewritten in place by the last CTA of each iteration's composite kernel, so the loop body has FIXED kernel arguments: it is
+// either a CUDA-graph WHILE node (b2n_frame_graph_*) or max_steps unrolled copies whose kernels exit at once after the loop
+// has ended (b2n_render_frame).  Three kernels per iteration: march, fused head, composite.  Semantics are the reference's:
 //     n_step = max(min(N // n_alive, 8), 1)                                   renderer.py:506-513
 //     march_rays(n_alive, n_step, ...) -> network -> composite_rays_triplane  renderer.py:518-534
-//     rays_alive = rays_alive[rays_alive >= 0]   (stable compaction)          renderer.py:542
+//     rays_alive = rays_alive[rays_alive >= 0]                                renderer.py:542
+//         (here: survivors are appended to the other alive buffer with one atomic per warp; the list order differs from the
+//          reference's stable compaction, which no per-ray result depends on)
 //     step += n_step; loop while step < max_steps and n_alive > 0             renderer.py:503
 // Per-ray arithmetic is the same code as the per-op kernels (dda.cuh, composite order), so images match the op-by-op
 // path bit for bit given the same network outputs.
@@ -25,12 +28,13 @@ int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *di
 
 namespace b2n {
 
-struct FrameCtrl { int32_t n_alive, n_step, step, n_samples, done, buf, iter, pad; };     // 32 B; buf = which alive[] buffer holds this iteration's ids
+struct FrameCtrl { int32_t n_alive, n_step, step, n_samples, done, buf, iter, n_live; };     // 32 B; buf = which alive[] buffer holds this iteration's ids
 
 struct FrameWs {            // carved out of the caller's workspace
-    FrameCtrl *ctrl;        // ctrl[0] = the iteration being executed (fixed address: kernel arguments never change, so the loop can be a graph WHILE node), ctrl[1] = the next one
-    int32_t *alive[2];      // ping-pong compacted ray ids [N]
-    int32_t *totals;        // per-CTA survivor counts
+    FrameCtrl *ctrl;        // the iteration being executed (fixed address: kernel arguments never change, so the loop can be a graph WHILE node)
+    int32_t *alive[2];      // ping-pong alive ray ids [N]
+    int32_t *alive_mid;     // rays of this iteration that produced samples (input of head / composite)
+    int32_t *counters;      // [0] |alive_mid|, [1] |next alive|, [2],[3] last-block tickets
     float *occ_box;         // [6] world-space box around every occupied cell, grown by 2 cells (empty: min > max)
     float *nears, *fars, *rays_t, *ws, *depth, *aud_sum, *eye_sum, *unc_sum, *image;   // per ray
     float *xyzs, *dirs, *deltas, *sigmas, *rgbs, *amb_aud, *amb_eye, *unc;              // per sample (<= N + 128)
@@ -48,7 +52,8 @@ static size_t carve(FrameWs *w, uint8_t *base, uint32_t N) {
     FrameWs t;
     t.ctrl = (FrameCtrl *)take(sizeof(FrameCtrl) * 8);
     t.alive[0] = (int32_t *)take(4 * Np); t.alive[1] = (int32_t *)take(4 * Np);
-    t.totals = (int32_t *)take(4 * (Np / FR_THREADS + 2));
+    t.alive_mid = (int32_t *)take(4 * Np);
+    t.counters = (int32_t *)take(4 * 8);
     t.occ_box = (float *)take(4 * 6 * 128);      // per-CTA partial boxes of k_occupied_box (reduced by every CTA of k_frame_init)
     float **per_ray[] = {&t.nears, &t.fars, &t.rays_t, &t.ws, &t.depth, &t.aud_sum, &t.eye_sum, &t.unc_sum};
     for (auto p : per_ray) *p = (float *)take(4 * Np);
@@ -107,10 +112,13 @@ __global__ void __launch_bounds__(256) k_occupied_box(const uint8_t *__restrict_
 __global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ rays_o, const float *__restrict__ rays_d, uint32_t N, float min_near,
                                                      float a0, float a1, float a2, float a3, float a4, float a5, uint32_t max_steps, FrameWs w) {
     __shared__ float bx[6];
-    if (threadIdx.x < 6) {
-        float v = w.occ_box[threadIdx.x];
-        for (uint32_t q = 1; q < OCC_PARTS; q++) v = threadIdx.x < 3 ? fminf(v, w.occ_box[q * 6 + threadIdx.x]) : fmaxf(v, w.occ_box[q * 6 + threadIdx.x]);
-        bx[threadIdx.x] = v;
+    if (threadIdx.x < 6 * 32) {                   // warp a reduces component a of the 128 partial boxes
+        const uint32_t a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        float v = a < 3 ? 3.0e38f : -3.0e38f;
+        for (uint32_t q = lane; q < OCC_PARTS; q += 32) v = a < 3 ? fminf(v, w.occ_box[q * 6 + a]) : fmaxf(v, w.occ_box[q * 6 + a]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const float u = __shfl_xor_sync(0xffffffffu, v, o); v = a < 3 ? fminf(v, u) : fmaxf(v, u); }
+        if (lane == 0) bx[a] = v;
     }
     __syncthreads();
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
@@ -133,49 +141,104 @@ __global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ ra
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         FrameCtrl c = {};
-        c.n_alive = (int32_t)N; c.n_step = 1; c.step = 0; c.n_samples = (int32_t)N; c.buf = 0; c.iter = 0;      // N // N = 1
+        c.n_alive = (int32_t)N; c.n_step = 1; c.step = 0; c.n_samples = 0; c.n_live = 0; c.buf = 0; c.iter = 0;      // N // N = 1
+        for (int q = 0; q < 8; q++) w.counters[q] = 0;
         c.done = (N == 0 || max_steps == 0) ? 1 : 0;
         if (c.done) { c.n_alive = 0; c.n_samples = 0; }
         w.ctrl[0] = c;
     }
 }
 
-// march_rays for the compacted alive rays of iteration `it` (raymarching.cu:828-929); fills its unproduced slots with zeros
+// Warp-aggregated append: lanes with `keep` get consecutive slots of a global list (one atomic per warp; a warp's rays stay adjacent,
+// which keeps the table gathers of the head kernel coherent).  The order across warps is arbitrary — per-ray results do not depend on it.
+__device__ __forceinline__ uint32_t warp_append(bool keep, int32_t *counter) {
+    const uint32_t ballot = __ballot_sync(0xffffffffu, keep), lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0 && ballot) base = (uint32_t)atomicAdd(counter, (int32_t)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + __popc(ballot & ((1u << lane) - 1u));
+}
+// true in exactly one thread block of the grid: the one that finishes last (all other blocks' writes are visible to it)
+__device__ __forceinline__ bool last_block_done(int32_t *ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int32_t)gridDim.x - 1);
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// march_rays for the alive rays of this iteration (raymarching.cu:828-929).  Rays that produce no sample at all are finished (the
+// reference's composite would see delta == 0 in their first slot, add nothing and drop them, raymarching.cu:2193, 2235) — they are
+// dropped HERE, so the head network only evaluates slots of rays that still contribute: the surviving ray ids and their n_step slots are
+// written compacted (alive_mid / xyzs / dirs / deltas); slots a ray did not fill are zero (the reference's torch.zeros, raymarching.py:384).
 __global__ void __launch_bounds__(FR_THREADS) k_frame_march(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
                                                              float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, FrameWs w) {
     const FrameCtrl c = w.ctrl[0];
+    if (c.done) return;
     const uint32_t n = blockIdx.x * FR_THREADS + threadIdx.x;
-    if (c.done || n >= (uint32_t)c.n_alive) return;
     const uint32_t n_step = (uint32_t)c.n_step;
-    const int32_t id = w.alive[c.buf][n];
-    DdaRay r;
-    r.init(rays_o + 3 * (size_t)id, rays_d + 3 * (size_t)id, bound, dt_gamma, max_steps, C, H, w.fars[id]);
-    float t = r.perturb(w.rays_t[id], 0.0f);          // noise = 0 (perturb is off at inference): fma(dt, 0, t) == t, kept for op parity
-    float *px = w.xyzs + 3 * (size_t)n * n_step, *pd = w.dirs + 3 * (size_t)n * n_step, *pl = w.deltas + 2 * (size_t)n * n_step;
+    const bool valid = n < (uint32_t)c.n_alive;
+    float ts[8], dts[8];
     uint32_t step = 0;
-    DdaSample s;
-    while (t < r.far && step < n_step) {
-        if (r.probe(grid, t, s)) {
-            t = __fadd_rn(t, s.dt);
-            px[0] = s.x; px[1] = s.y; px[2] = s.z; pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz; pl[0] = s.dt; pl[1] = t;
-            px += 3; pd += 3; pl += 2; step++;
+    int32_t id = 0;
+    DdaRay r;
+    if (valid) {
+        id = w.alive[c.buf][n];
+        r.init(rays_o + 3 * (size_t)id, rays_d + 3 * (size_t)id, bound, dt_gamma, max_steps, C, H, w.fars[id]);
+        float t = r.perturb(w.rays_t[id], 0.0f);      // noise = 0 (perturb is off at inference): fma(dt, 0, t) == t, kept for op parity
+        DdaSample s;
+        while (t < r.far && step < n_step) {
+            if (r.probe(grid, t, s)) {
+#pragma unroll
+                for (uint32_t k = 0; k < 8; k++) if (k == step) { ts[k] = t; dts[k] = s.dt; }
+                t = __fadd_rn(t, s.dt);
+                step++;
+            }
         }
     }
-    for (; step < n_step; step++) {                    // the reference relies on a torch.zeros fill (raymarching.py:384-386)
-        px[0] = 0.0f; px[1] = 0.0f; px[2] = 0.0f; pd[0] = 0.0f; pd[1] = 0.0f; pd[2] = 0.0f; pl[0] = 0.0f; pl[1] = 0.0f;
-        px += 3; pd += 3; pl += 2;
+    const bool has = valid && step > 0;
+    const uint32_t p = warp_append(has, &w.counters[0]);
+    if (has) {
+        w.alive_mid[p] = id;
+        float *px = w.xyzs + 3 * (size_t)p * n_step, *pd = w.dirs + 3 * (size_t)p * n_step, *pl = w.deltas + 2 * (size_t)p * n_step;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) {
+            if (k < n_step) {
+                if (k < step) {
+                    // the sample position is a pure function of t: same expression as DdaRay::probe
+                    px[0] = clampf(__fmaf_rn(ts[k], r.dx, r.ox), -bound, bound); px[1] = clampf(__fmaf_rn(ts[k], r.dy, r.oy), -bound, bound);
+                    px[2] = clampf(__fmaf_rn(ts[k], r.dz, r.oz), -bound, bound);
+                    pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz; pl[0] = dts[k]; pl[1] = __fadd_rn(ts[k], dts[k]);
+                } else { px[0] = 0.0f; px[1] = 0.0f; px[2] = 0.0f; pd[0] = 0.0f; pd[1] = 0.0f; pd[2] = 0.0f; pl[0] = 0.0f; pl[1] = 0.0f; }
+                px += 3; pd += 3; pl += 2;
+            }
+        }
+    }
+    if (last_block_done(&w.counters[2])) {
+        if (threadIdx.x == 0) {
+            const int32_t live = w.counters[0];
+            w.ctrl[0].n_live = live;
+            w.ctrl[0].n_samples = live * (int32_t)n_step;
+            w.counters[2] = 0;
+        }
     }
 }
 
-// composite_rays_triplane (raymarching.cu:2142-2249) + per-CTA survivor count
-__global__ void __launch_bounds__(FR_THREADS) k_frame_composite(float T_thresh, FrameWs w) {
+// composite_rays_triplane (raymarching.cu:2142-2249) over the rays that produced samples; survivors are appended to the next alive list;
+// the last CTA to finish publishes the next iteration's control block (n_step = max(min(N // n_alive, 8), 1), renderer.py:506-513) and,
+// when the loop is a graph WHILE node, its condition.
+__global__ void __launch_bounds__(FR_THREADS) k_frame_composite(float T_thresh, uint32_t N, uint32_t max_steps, FrameWs w, cudaGraphConditionalHandle handle,
+                                                                 int use_handle) {
     const FrameCtrl c = w.ctrl[0];
+    if (c.done) return;
     const uint32_t n = blockIdx.x * FR_THREADS + threadIdx.x;
     bool survive = false;
-    if (!c.done && n < (uint32_t)c.n_alive) {
+    int32_t idx = 0;
+    if (n < (uint32_t)c.n_live) {
         const uint32_t n_step = (uint32_t)c.n_step;
-        int32_t *alive = w.alive[c.buf];
-        const int32_t idx = alive[n];
+        idx = w.alive_mid[n];
         const size_t base = (size_t)n * n_step;
         float t = w.rays_t[idx], ws = w.ws[idx], d = w.depth[idx];
         float r = w.image[3 * (size_t)idx], g = w.image[3 * (size_t)idx + 1], b = w.image[3 * (size_t)idx + 2];
@@ -198,70 +261,30 @@ __global__ void __launch_bounds__(FR_THREADS) k_frame_composite(float T_thresh, 
             step++;
         }
         survive = !(step < n_step);
-        if (survive) w.rays_t[idx] = t; else alive[n] = -1;
+        if (survive) w.rays_t[idx] = t;
         w.ws[idx] = ws; w.depth[idx] = d;
         w.image[3 * (size_t)idx] = r; w.image[3 * (size_t)idx + 1] = g; w.image[3 * (size_t)idx + 2] = b;
         w.aud_sum[idx] = a0; w.eye_sum[idx] = a1; w.unc_sum[idx] = u;
     }
-    const int cnt = __syncthreads_count(survive);
-    if (threadIdx.x == 0) w.totals[blockIdx.x] = cnt;
-}
-
-// stable compaction of the survivors into the other alive buffer; the last CTA publishes ctrl[it+1]
-__global__ void __launch_bounds__(FR_THREADS) k_frame_compact(uint32_t N, uint32_t max_steps, FrameWs w) {
-    const FrameCtrl c = w.ctrl[0];
-    __shared__ uint32_t red[FR_THREADS / 32];
-    __shared__ uint32_t s_base;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nblk_live = c.done ? 0u : ((uint32_t)c.n_alive + FR_THREADS - 1) / FR_THREADS;
-    if (blockIdx.x >= nblk_live && !(blockIdx.x == 0)) return;
-    if (c.done) {                                      // propagate the terminal state
-        if (blockIdx.x == 0 && threadIdx.x == 0) { FrameCtrl nx = c; nx.n_alive = 0; nx.n_samples = 0; nx.done = 1; w.ctrl[1] = nx; }
-        return;
-    }
-    uint32_t part = 0;
-    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += FR_THREADS) part += (uint32_t)w.totals[b];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) red[warp] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) { uint32_t b = 0; for (int q = 0; q < (int)(FR_THREADS / 32); q++) b += red[q]; s_base = b; }
-    __syncthreads();
-    const uint32_t n = blockIdx.x * FR_THREADS + threadIdx.x;
-    const int32_t id = (n < (uint32_t)c.n_alive) ? w.alive[c.buf][n] : -1;
-    const uint32_t keep = id >= 0 ? 1u : 0u;
-    uint32_t inc = keep;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-    __syncthreads();
-    if (lane == 31) red[warp] = inc;
-    __syncthreads();
-    uint32_t woff = 0, tot = 0;
-#pragma unroll
-    for (int q = 0; q < (int)(FR_THREADS / 32); q++) { if (q < (int)warp) woff += red[q]; tot += red[q]; }
-    if (keep) w.alive[c.buf ^ 1][s_base + woff + inc - 1] = id;
-    if (blockIdx.x == nblk_live - 1 && threadIdx.x == 0) {
-        FrameCtrl nx = {};
-        nx.n_alive = (int32_t)(s_base + tot);
-        nx.step = c.step + c.n_step;
-        nx.buf = c.buf ^ 1; nx.iter = c.iter + 1;
-        nx.done = (nx.n_alive <= 0 || nx.step >= (int32_t)max_steps) ? 1 : 0;
-        if (nx.done) { nx.n_alive = 0; nx.n_step = 1; nx.n_samples = 0; }
-        else {
-            int32_t ns = (int32_t)N / nx.n_alive;                  // n_step = max(min(N // n_alive, 8), 1)
-            ns = ns < 8 ? ns : 8; ns = ns > 1 ? ns : 1;
-            nx.n_step = ns; nx.n_samples = nx.n_alive * ns;
+    const uint32_t p = warp_append(survive, &w.counters[1]);
+    if (survive) w.alive[c.buf ^ 1][p] = idx;
+    if (last_block_done(&w.counters[3])) {
+        if (threadIdx.x == 0) {
+            FrameCtrl nx = {};
+            nx.n_alive = w.counters[1];
+            nx.step = c.step + c.n_step;
+            nx.buf = c.buf ^ 1; nx.iter = c.iter + 1;
+            nx.done = (nx.n_alive <= 0 || nx.step >= (int32_t)max_steps) ? 1 : 0;
+            if (nx.done) { nx.n_alive = 0; nx.n_step = 1; }
+            else {
+                int32_t ns = (int32_t)N / nx.n_alive;
+                ns = ns < 8 ? ns : 8; ns = ns > 1 ? ns : 1;
+                nx.n_step = ns;
+            }
+            w.ctrl[0] = nx;            // every other CTA has finished, so nobody still reads the old block
+            w.counters[0] = 0; w.counters[1] = 0; w.counters[3] = 0;
+            if (use_handle) cudaGraphSetConditional(handle, nx.done ? 0u : 1u);
         }
-        w.ctrl[1] = nx;
-    }
-}
-
-// end of an iteration: next -> current (single thread).  In the graph build it also drives the WHILE node.
-__global__ void k_frame_advance(FrameWs w, cudaGraphConditionalHandle handle, int use_handle) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const FrameCtrl nx = w.ctrl[1];
-        w.ctrl[0] = nx;
-        if (use_handle) cudaGraphSetConditional(handle, nx.done ? 0u : 1u);
     }
 }
 
@@ -302,19 +325,15 @@ static int enqueue_init(const FramePlan &p, cudaStream_t st) {
                                     p.cfg.max_steps, p.w);
     return check_launch("render_frame(init)");
 }
-// one loop iteration: march -> fused head -> composite -> compact -> advance
+// one loop iteration: march (+ drop rays without samples) -> fused head -> composite (+ survivor list, next control block)
 static int enqueue_iteration(const FramePlan &p, cudaStream_t st, cudaGraphConditionalHandle handle, int use_handle) {
     const uint32_t ctas = ceil_div<uint32_t>(p.N, FR_THREADS);
     k_frame_march<<<ctas, FR_THREADS, 0, st>>>(p.rays_o, p.rays_d, p.bitfield, p.cfg.bound, p.cfg.dt_gamma, p.cfg.max_steps, p.cfg.cascade, p.cfg.grid_size, p.w);
     if (check_launch("render_frame(march)")) return 1;
     if (int rc = head_forward_on_model(p.m, p.w.xyzs, p.w.dirs, p.N, p.enc_a, p.ind_code, p.eye, &p.w.ctrl[0].n_samples, p.cfg.density_scale, p.w.sigmas, p.w.rgbs,
                                        p.w.amb_aud, p.w.amb_eye, p.w.unc, st, p.w.deltas)) return rc;
-    k_frame_composite<<<ctas, FR_THREADS, 0, st>>>(p.cfg.T_thresh, p.w);
-    if (check_launch("render_frame(composite)")) return 1;
-    k_frame_compact<<<ctas, FR_THREADS, 0, st>>>(p.N, p.cfg.max_steps, p.w);
-    if (check_launch("render_frame(compact)")) return 1;
-    k_frame_advance<<<1, 32, 0, st>>>(p.w, handle, use_handle);
-    return check_launch("render_frame(advance)");
+    k_frame_composite<<<ctas, FR_THREADS, 0, st>>>(p.cfg.T_thresh, p.N, p.cfg.max_steps, p.w, handle, use_handle);
+    return check_launch("render_frame(composite)");
 }
 static int enqueue_finish(const FramePlan &p, cudaStream_t st) {
     const uint32_t sms = (uint32_t)sm_count();
@@ -339,8 +358,8 @@ static int make_plan(FramePlan &p, const b2n_model *m, const b2n_render_cfg *cfg
 
 using namespace b2n;
 
-// A frame as ONE CUDA graph whose loop is a WHILE conditional node: init -> while (!done) { march, head, composite, compact, advance } -> finish.
-// The condition is written on the device by k_frame_advance (cudaGraphSetConditional), so exactly the iterations the reference's host loop would
+// A frame as ONE CUDA graph whose loop is a WHILE conditional node: init -> while (!done) { march, head, composite } -> finish.
+// The condition is written on the device by the last CTA of k_frame_composite (cudaGraphSetConditional), so exactly the iterations the reference's host loop would
 // run are executed, with a single graph launch per frame and no host synchronisation.
 struct b2n_frame_graph {
     cudaGraph_t graph = nullptr;
