@@ -237,7 +237,7 @@ def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536
 
 def run_gpu_arm(args, rank, world, local_rank):
     from b2nerf import lib
-    from b2nerf.render import FrameRenderer
+    from b2nerf.render import FramePipeline
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -246,13 +246,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     frames_np, auds_np, bitfield = synthetic_inputs(rank)
     model = build_model(dev)
     model.density_bitfield.copy_(torch.from_numpy(bitfield).to(dev))
-    r = FrameRenderer(model, N_RAYS, use_graph=not args.no_graph)
+    pipe = FramePipeline(model, N_RAYS, depth=1 if args.no_graph else max(1, args.in_flight), use_graph=not args.no_graph)
+    r = pipe.slots[0]
     frames = [(torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)) for o, d in frames_np]
     auds = [torch.from_numpy(a).to(dev) for a in auds_np]
     host_o = [torch.from_numpy(o).pin_memory() for o, _ in frames_np]
     host_d = [torch.from_numpy(d).pin_memory() for _, d in frames_np]
     host_a = [torch.from_numpy(a).pin_memory() for a in auds_np]
-    out_host = torch.empty(N_RAYS, 3).pin_memory()
+    out_hosts = [torch.empty(N_RAYS, 3).pin_memory() for _ in range(pipe.depth)]
+    out_host = out_hosts[0]
     L = lib()
 
     def barrier():
@@ -270,6 +272,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         e0.record()
         for s in range(steps):
             fn(warmup + s)
+        pipe.drain()                     # the timing stream waits for every frame in flight
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -284,9 +287,9 @@ def run_gpu_arm(args, rank, world, local_rank):
     if sampler:
         sampler.start()
         sampler.wait_first()
-    dev_ms, launches = timed(lambda s: r.render_device(frames[s % POOL][0], frames[s % POOL][1], auds[s % POOL]), args.steps, args.warmup)
+    dev_ms, launches = timed(lambda s: pipe.submit_device(frames[s % POOL][0], frames[s % POOL][1], auds[s % POOL]), args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
-    e2e_ms, _ = timed(lambda s: r.render_host(host_o[s % POOL], host_d[s % POOL], host_a[s % POOL], out_host), args.steps, args.warmup)
+    e2e_ms, _ = timed(lambda s: pipe.submit_host(host_o[s % POOL], host_d[s % POOL], host_a[s % POOL], out_hosts[s % pipe.depth]), args.steps, args.warmup)
     train_info = None
     if not args.no_train:
         train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(4, min(args.steps, 20)), warmup=max(args.warmup, 18))
@@ -313,7 +316,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": "infer_512x512_frame", "rays_per_frame": N_RAYS, "max_steps": 16, "dt_gamma": 1 / 256, "bound": 1,
-                   "params": 683509, "weights": "random-init", "frames_per_gpu_per_step": 1, "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                   "params": 683509, "weights": "random-init", "frames_per_gpu_per_step": 1, "frames_in_flight_per_gpu": pipe.depth, "parallelism": f"frames sharded over {world} GPU(s), no collective",
                    "l2": f"inputs cycle through {POOL} distinct frames ({POOL * N_RAYS * 24 / 1e6:.0f} MB of rays) > 126 MB L2", "cuda_graph": not args.no_graph, "loop": loop_mode},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": r.h2d_bytes(), "d2h_bytes_per_step": r.d2h_bytes(), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": gpu_launches,
@@ -342,6 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b2nerf", choices=["b2nerf", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=2, help="frames in flight per GPU (independent frames on separate streams; 1 = strictly one after another)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     args = ap.parse_args()

@@ -143,3 +143,46 @@ class FrameRenderer:
 
     def d2h_bytes(self):
         return self.image.numel() * 4
+
+
+class FramePipeline:
+    """`depth` frames in flight on one GPU: frame k runs on renderer/stream k % depth, so the host<->device copies and the kernel
+    tails / dependent-launch gaps of one frame overlap the next frame's work (frames are independent — the reference's test loop,
+    TrainerUtil.py:408-460, renders them one after another).  Results are returned in submission order by `drain()` / the per-slot
+    events; the per-frame arithmetic is exactly FrameRenderer's."""
+
+    def __init__(self, model: HeadModel, n_rays, depth=2, **kw):
+        self.depth = int(depth)
+        self.slots = [FrameRenderer(model, n_rays, **kw) for _ in range(self.depth)]
+        self.dev = self.slots[0].dev
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.depth)]
+        self.done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.k = 0
+
+    def _slot(self):
+        i = self.k % self.depth
+        self.k += 1
+        self.streams[i].wait_stream(torch.cuda.current_stream(self.dev))      # inputs produced on the caller's stream are ready
+        return i
+
+    def submit_device(self, rays_o, rays_d, auds):
+        """Enqueue one frame whose inputs are on the device; returns (slot index, the slot's static image buffer)."""
+        i = self._slot()
+        with torch.cuda.stream(self.streams[i]):
+            img = self.slots[i].render_device(rays_o, rays_d, auds)
+            self.done[i].record()
+        return i, img
+
+    def submit_host(self, rays_o_host, rays_d_host, auds_host, out_host):
+        """Enqueue one frame with pinned host inputs / output (out_host must stay untouched until the slot's event or drain())."""
+        i = self._slot()
+        with torch.cuda.stream(self.streams[i]):
+            self.slots[i].render_host(rays_o_host, rays_d_host, auds_host, out_host)
+            self.done[i].record()
+        return i
+
+    def drain(self):
+        """Make the caller's stream wait for every frame in flight."""
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.streams:
+            cur.wait_stream(s)

@@ -12,20 +12,25 @@
 // operation order, so results are bit-identical to the reference kernels on the same GPU (same MUFU.EX2).
 // What changes is data movement: a CTA owns 128 consecutive rows of `rays`; when their sample segments tile
 // one contiguous range (always true for b2n_march_rays_train's deterministic allocation) the CTA stages that
-// range through shared memory with fully coalesced 128 B transactions, threads walk their ray out of shared
-// memory, and the backward writes its per-sample gradients back through the same staging buffer — so HBM
-// sees each algorithmic byte exactly once.  Foreign `rays` orderings (the reference's atomic allocation)
+// range through shared memory with TMA bulk copies (cp.async.bulk: one thread puts the CTA's whole 70 KB in
+// flight, three CTAs per SM keep > 200 KB outstanding per SM — the latency x bandwidth product HBM3e needs),
+// threads walk their ray out of shared memory, and the backward writes its per-sample gradients back through
+// the same staging buffer with bulk stores — so HBM sees each algorithmic byte exactly once.  Foreign `rays` orderings (the reference's atomic allocation)
 // take the direct global-memory path of the same template.
 #include "common.cuh"
+#include "tc5.cuh"
 
 namespace b2n {
 
 constexpr int CT_THREADS = 128;
 constexpr int CT_CAP = 2048;            // staged samples per CTA (128 rays x 16 steps)
 
+constexpr int CT_PAD = 4;               // floats of slack per staged array (a span keeps its source's 16-byte phase)
+
 template <int NA, bool UNC> struct Stage {
     // floats per staged sample: sigma 1, deltas 2, rgb 3, ambient NA, unc
     static constexpr int FLOATS = 6 + NA + (UNC ? 1 : 0);
+    static constexpr size_t BYTES = sizeof(float) * ((size_t)FLOATS * CT_CAP + 6 * CT_PAD);
 };
 
 // exp(-sigma*delta) exactly as nvcc emits __expf(-s*d) for the reference: (s*d) * -log2(e) -> ex2.approx
@@ -55,14 +60,43 @@ __device__ __forceinline__ bool cta_tiling(bool valid, uint32_t off, uint32_t nu
     return __syncthreads_and(ok) && tot <= CT_CAP && tot > 0;
 }
 
-// coalesced copy of `count` floats global -> shared (count*4 bytes contiguous, arbitrary 4 B alignment)
-__device__ __forceinline__ void stage_in(float *dst, const float *__restrict__ src, uint32_t count) {
-#pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < count; i += CT_THREADS) dst[i] = __ldcs(src + i);
+// A staged span: `count` floats of global memory mirrored in shared memory AT THE SAME 16-BYTE PHASE, so its interior moves as one TMA
+// bulk copy (16 B granules) and at most 3 floats at either end go through ordinary loads / stores.
+struct Span {
+    float *s;                   // s[i] mirrors g[i]
+    uint32_t head, body, count; // floats before the first 16 B boundary; bulk floats (multiple of 4); total
+};
+__device__ __forceinline__ uint32_t phase_of(const float *g) { return ((uint32_t)(uintptr_t)g >> 2) & 3u; }
+__device__ __forceinline__ Span span_of(float *s_base, const float *g, uint32_t count) {
+    const uint32_t phase = phase_of(g);
+    Span sp;
+    sp.s = s_base + phase;
+    sp.count = count;
+    sp.head = min(count, (4u - phase) & 3u);
+    sp.body = (count - sp.head) & ~3u;
+    return sp;
 }
+// global -> shared.  Every thread calls it; thread 0 issues the bulk copy (completion on `bar`, whose expect_tx already counts body * 4).
+__device__ __forceinline__ void span_load(const Span &sp, const float *__restrict__ g, uint64_t *bar) {
+    const uint32_t edge = sp.head + sp.body, t = threadIdx.x - 32u;
+    if (threadIdx.x < sp.head) sp.s[threadIdx.x] = __ldcs(g + threadIdx.x);
+    if (t < sp.count - edge) sp.s[edge + t] = __ldcs(g + edge + t);
+    if (threadIdx.x == 0 && sp.body) tc5::bulk_g2s(sp.s + sp.head, g + sp.head, sp.body * 4u, bar);
+}
+// shared -> global (same phase required: phase_of(g) == phase of sp.s); thread 0 issues the bulk store
+__device__ __forceinline__ void span_store(const Span &sp, float *__restrict__ g) {
+    const uint32_t edge = sp.head + sp.body, t = threadIdx.x - 32u;
+    if (threadIdx.x < sp.head) __stcs(g + threadIdx.x, sp.s[threadIdx.x]);
+    if (t < sp.count - edge) __stcs(g + edge + t, sp.s[edge + t]);
+    if (threadIdx.x == 0 && sp.body) tc5::bulk_s2g(g + sp.head, sp.s + sp.head, sp.body * 4u);
+}
+// out-of-phase destination: plain coalesced stores
 __device__ __forceinline__ void stage_out(float *__restrict__ dst, const float *src, uint32_t count) {
 #pragma unroll 4
     for (uint32_t i = threadIdx.x; i < count; i += CT_THREADS) __stcs(dst + i, src[i]);
+}
+__device__ __forceinline__ void span_store_any(const Span &sp, float *__restrict__ g) {      // uniform branch per CTA
+    if (phase_of(g) == (uint32_t)(sp.s - (float *)((uintptr_t)sp.s & ~(uintptr_t)15))) span_store(sp, g); else stage_out(g, sp.s, sp.count);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -96,27 +130,36 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_fwd(
         const int32_t *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
         float *__restrict__ weights_sum, float *__restrict__ amb0_sum, float *__restrict__ amb1_sum,
         float *__restrict__ unc_sum, float *__restrict__ depth, float *__restrict__ image) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const uint32_t n = blockIdx.x * CT_THREADS + threadIdx.x;
     uint32_t idx = 0, off = 0, num = 0;
     if (n < N) { idx = (uint32_t)rays[3 * (size_t)n]; off = (uint32_t)rays[3 * (size_t)n + 1]; num = (uint32_t)rays[3 * (size_t)n + 2]; }
     const bool valid = (n < N) && !(num == 0 || off + num > M);
+    __shared__ __align__(8) uint64_t s_bar;
+    if (threadIdx.x == 0) { tc5::mbar_init(&s_bar, 1); tc5::fence_mbar_init(); }
     uint32_t lo, total;
-    const bool staged = cta_tiling(valid, off, num, lo, total);
+    const bool staged = cta_tiling(valid, off, num, lo, total);       // (its barriers also publish the mbarrier init)
     float ws = 0, a0 = 0, a1 = 0, u = 0, d = 0, r = 0, g = 0, b = 0;
     if (staged) {
-        float *s_sg = sm, *s_dl = s_sg + CT_CAP, *s_rgb = s_dl + 2 * CT_CAP, *s_a0 = s_rgb + 3 * CT_CAP;
-        float *s_a1 = s_a0 + (NA >= 1 ? CT_CAP : 0), *s_u = s_a1 + (NA >= 2 ? CT_CAP : 0);
-        stage_in(s_sg, sigmas + lo, total);
-        stage_in(s_dl, deltas + 2 * (size_t)lo, 2 * total);
-        stage_in(s_rgb, rgbs + 3 * (size_t)lo, 3 * total);
-        if (NA >= 1) stage_in(s_a0, amb0 + lo, total);
-        if (NA >= 2) stage_in(s_a1, amb1 + lo, total);
-        if (UNC) stage_in(s_u, unc + lo, total);
-        __syncthreads();
+        float *b_sg = sm, *b_dl = b_sg + CT_CAP + CT_PAD, *b_rgb = b_dl + 2 * CT_CAP + CT_PAD, *b_a0 = b_rgb + 3 * CT_CAP + CT_PAD;
+        float *b_a1 = b_a0 + (NA >= 1 ? CT_CAP + CT_PAD : 0), *b_u = b_a1 + (NA >= 2 ? CT_CAP + CT_PAD : 0);
+        const Span p_sg = span_of(b_sg, sigmas + lo, total), p_dl = span_of(b_dl, deltas + 2 * (size_t)lo, 2 * total);
+        const Span p_rgb = span_of(b_rgb, rgbs + 3 * (size_t)lo, 3 * total);
+        const Span p_a0 = NA >= 1 ? span_of(b_a0, amb0 + lo, total) : Span{b_a0, 0, 0, 0};
+        const Span p_a1 = NA >= 2 ? span_of(b_a1, amb1 + lo, total) : Span{b_a1, 0, 0, 0};
+        const Span p_u = UNC ? span_of(b_u, unc + lo, total) : Span{b_u, 0, 0, 0};
+        if (threadIdx.x == 0) tc5::mbar_expect_tx(&s_bar, 4u * (p_sg.body + p_dl.body + p_rgb.body + p_a0.body + p_a1.body + p_u.body));
+        span_load(p_sg, sigmas + lo, &s_bar);
+        span_load(p_dl, deltas + 2 * (size_t)lo, &s_bar);
+        span_load(p_rgb, rgbs + 3 * (size_t)lo, &s_bar);
+        if (NA >= 1) span_load(p_a0, amb0 + lo, &s_bar);
+        if (NA >= 2) span_load(p_a1, amb1 + lo, &s_bar);
+        if (UNC) span_load(p_u, unc + lo, &s_bar);
+        __syncthreads();                       // edge floats
+        tc5::mbar_wait(&s_bar, 0);             // bulk interior
         if (valid) {
             const uint32_t o = off - lo;
-            train_fwd_ray<AMB, NA, UNC>(s_sg + o, s_rgb + 3 * o, s_a0 + o, s_a1 + o, s_u + o, s_dl + 2 * o, num, T_thresh, ws, a0, a1, u, d, r, g, b);
+            train_fwd_ray<AMB, NA, UNC>(p_sg.s + o, p_rgb.s + 3 * o, p_a0.s + o, p_a1.s + o, p_u.s + o, p_dl.s + 2 * o, num, T_thresh, ws, a0, a1, u, d, r, g, b);
         }
     } else if (valid) {
         train_fwd_ray<AMB, NA, UNC>(sigmas + off, rgbs + 3 * (size_t)off, NA >= 1 ? amb0 + off : nullptr, NA >= 2 ? amb1 + off : nullptr,
@@ -190,11 +233,13 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_bwd(
         const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
         float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs, float *__restrict__ grad_a0,
         float *__restrict__ grad_a1, float *__restrict__ grad_u) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const uint32_t n = blockIdx.x * CT_THREADS + threadIdx.x;
     uint32_t idx = 0, off = 0, num = 0;
     if (n < N) { idx = (uint32_t)rays[3 * (size_t)n]; off = (uint32_t)rays[3 * (size_t)n + 1]; num = (uint32_t)rays[3 * (size_t)n + 2]; }
     const bool valid = (n < N) && !(num == 0 || off + num > M);
+    __shared__ __align__(8) uint64_t s_bar;
+    if (threadIdx.x == 0) { tc5::mbar_init(&s_bar, 1); tc5::fence_mbar_init(); }
     uint32_t lo, total;
     const bool staged = cta_tiling(valid, off, num, lo, total);
     RayGrads q = {};
@@ -209,26 +254,35 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_bwd(
         q.rF = image[3 * (size_t)idx]; q.gF = image[3 * (size_t)idx + 1]; q.bF = image[3 * (size_t)idx + 2];
     }
     if (staged) {
-        // s_a0 doubles as grad_a0 staging, s_a1 is output-only (grad_a1 = per-ray constant), s_u doubles as grad_u
-        float *s_sg = sm, *s_dl = s_sg + CT_CAP, *s_rgb = s_dl + 2 * CT_CAP, *s_a0 = s_rgb + 3 * CT_CAP;
-        float *s_a1 = s_a0 + (NA >= 1 ? CT_CAP : 0), *s_u = s_a1 + (NA >= 2 ? CT_CAP : 0);
-        stage_in(s_sg, sigmas + lo, total);
-        stage_in(s_dl, deltas + 2 * (size_t)lo, 2 * total);
-        stage_in(s_rgb, rgbs + 3 * (size_t)lo, 3 * total);
-        if (AMB == 2) stage_in(s_a0, amb0 + lo, total);
-        if (UNC) stage_in(s_u, unc + lo, total);
+        // the a0 span doubles as grad_a0 staging (input only when AMB == 2), a1 is output-only (grad_a1 = per-ray constant), u doubles as grad_u
+        float *b_sg = sm, *b_dl = b_sg + CT_CAP + CT_PAD, *b_rgb = b_dl + 2 * CT_CAP + CT_PAD, *b_a0 = b_rgb + 3 * CT_CAP + CT_PAD;
+        float *b_a1 = b_a0 + (NA >= 1 ? CT_CAP + CT_PAD : 0), *b_u = b_a1 + (NA >= 2 ? CT_CAP + CT_PAD : 0);
+        const Span p_sg = span_of(b_sg, sigmas + lo, total), p_dl = span_of(b_dl, deltas + 2 * (size_t)lo, 2 * total);
+        const Span p_rgb = span_of(b_rgb, rgbs + 3 * (size_t)lo, 3 * total);
+        const Span p_a0 = NA >= 1 ? span_of(b_a0, AMB == 2 ? amb0 + lo : grad_a0 + lo, total) : Span{b_a0, 0, 0, 0};
+        const Span p_a1 = NA >= 2 ? span_of(b_a1, grad_a1 + lo, total) : Span{b_a1, 0, 0, 0};
+        const Span p_u = UNC ? span_of(b_u, unc + lo, total) : Span{b_u, 0, 0, 0};
+        if (threadIdx.x == 0) tc5::mbar_expect_tx(&s_bar, 4u * (p_sg.body + p_dl.body + p_rgb.body + (AMB == 2 ? p_a0.body : 0u) + p_u.body));
+        span_load(p_sg, sigmas + lo, &s_bar);
+        span_load(p_dl, deltas + 2 * (size_t)lo, &s_bar);
+        span_load(p_rgb, rgbs + 3 * (size_t)lo, &s_bar);
+        if (AMB == 2) span_load(p_a0, amb0 + lo, &s_bar);
+        if (UNC) span_load(p_u, unc + lo, &s_bar);
         __syncthreads();
+        tc5::mbar_wait(&s_bar, 0);
         if (valid) {
             const uint32_t o = off - lo;
-            train_bwd_ray<AMB, NA, UNC, true>(s_sg + o, s_rgb + 3 * o, s_a0 + o, s_u + o, s_dl + 2 * o, num, T_thresh, q,
-                                              s_sg + o, s_rgb + 3 * o, s_a0 + o, s_a1 + o, s_u + o);
+            train_bwd_ray<AMB, NA, UNC, true>(p_sg.s + o, p_rgb.s + 3 * o, p_a0.s + o, p_u.s + o, p_dl.s + 2 * o, num, T_thresh, q,
+                                              p_sg.s + o, p_rgb.s + 3 * o, p_a0.s + o, p_a1.s + o, p_u.s + o);
         }
+        tc5::fence_proxy_async();              // this thread's shared-memory writes -> visible to the bulk-store (async) proxy
         __syncthreads();
-        stage_out(grad_sigmas + lo, s_sg, total);
-        stage_out(grad_rgbs + 3 * (size_t)lo, s_rgb, 3 * total);
-        if (NA >= 1) stage_out(grad_a0 + lo, s_a0, total);
-        if (NA >= 2) stage_out(grad_a1 + lo, s_a1, total);
-        if (UNC) stage_out(grad_u + lo, s_u, total);
+        span_store_any(p_sg, grad_sigmas + lo);
+        span_store_any(p_rgb, grad_rgbs + 3 * (size_t)lo);
+        if (NA >= 1) span_store_any(p_a0, grad_a0 + lo);
+        if (NA >= 2) span_store_any(p_a1, grad_a1 + lo);
+        if (UNC) span_store_any(p_u, grad_u + lo);
+        if (threadIdx.x == 0) { tc5::bulk_commit(); tc5::bulk_wait_read0(); }     // shared memory must outlive the bulk reads
     } else if (valid) {
         train_bwd_ray<AMB, NA, UNC, false>(sigmas + off, rgbs + 3 * (size_t)off, AMB == 2 ? amb0 + off : nullptr, UNC ? unc + off : nullptr,
                                            deltas + 2 * (size_t)off, num, T_thresh, q, grad_sigmas + off, grad_rgbs + 3 * (size_t)off,
@@ -290,7 +344,7 @@ static int launch_train_fwd(const char *what, const float *sigmas, const float *
     B2N_REQUIRE((NA < 1 || (amb0 && a0s)) && (NA < 2 || (amb1 && a1s)) && (!UNC || (unc && us)), "%s: null pointer", what);
     if (N == 0) return 0;
     static bool attr_done = false;
-    const size_t smem = sizeof(float) * (size_t)Stage<NA, UNC>::FLOATS * CT_CAP;
+    const size_t smem = Stage<NA, UNC>::BYTES;
     auto kern = k_comp_train_fwd<AMB, NA, UNC>;
     if (!attr_done) { B2N_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
     kern<<<ceil_div<uint32_t>(N, CT_THREADS), CT_THREADS, smem, as_stream(stream)>>>(sigmas, rgbs, amb0, amb1, unc, deltas, rays, M, N, T_thresh,
@@ -308,7 +362,7 @@ static int launch_train_bwd(const char *what, const float *g_ws, const float *g_
                 "%s: null pointer", what);
     if (N == 0) return 0;
     static bool attr_done = false;
-    const size_t smem = sizeof(float) * (size_t)Stage<NA, UNC>::FLOATS * CT_CAP;
+    const size_t smem = Stage<NA, UNC>::BYTES;
     auto kern = k_comp_train_bwd<AMB, NA, UNC>;
     if (!attr_done) { B2N_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
     kern<<<ceil_div<uint32_t>(N, CT_THREADS), CT_THREADS, smem, as_stream(stream)>>>(g_ws, g_a0, g_a1, g_u, g_img, sigmas, rgbs, amb0, unc, deltas, rays,
