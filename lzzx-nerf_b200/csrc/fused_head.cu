@@ -72,13 +72,18 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);
 }
-// TMEM -> fp16 operand tile: reads `ncols` accumulator columns of this thread's row starting at TMEM address `taddr`, applies
-// (+bias, ReLU) and writes them as halves k0.. of row `row` of a SWIZZLE_128B tile.  Deliberately NOT inlined and rolled over
-// 16-column blocks: the kernel has five of these epilogues and four warpgroups in different phases, so code size (I-cache
+// two fp32 -> packed fp16 with ReLU folded into the conversion (cvt.rn.relu: relu(round(x)) == round(relu(x))); lo goes to bits [0,16)
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// TMEM -> fp16 operand tile: reads 64 accumulator columns of this thread's row starting at TMEM address `taddr`, applies
+// (+bias, ReLU) and writes them as halves 0..63 of row `row` of a SWIZZLE_128B tile.  Deliberately NOT inlined and rolled over
+// 32-column blocks: the kernel has five of these epilogues and three warpgroups in different phases, so code size (I-cache
 // footprint) matters more than the few loop instructions.
 template <bool RELU, bool BIAS>
 __device__ __noinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, uint32_t row, const float *bias) {
-    const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll 1
     for (uint32_t cb = 0; cb < 64; cb += 32) {
         uint32_t acc[32];
@@ -91,29 +96,64 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, uint
             for (uint32_t j = 0; j < 4; j++) {
                 float x0 = __uint_as_float(acc[c * 8 + 2 * j]), x1 = __uint_as_float(acc[c * 8 + 2 * j + 1]);
                 if (BIAS) { x0 += bias[cb + c * 8 + 2 * j]; x1 += bias[cb + c * 8 + 2 * j + 1]; }
-                __half2 h = __floats2half2_rn(x0, x1);
-                if (RELU) h = __hmax2(h, zero);                              // relu(round(x)) == round(relu(x))
-                w[j] = *reinterpret_cast<uint32_t *>(&h);
+                w[j] = RELU ? pack2_relu(x0, x1) : pack2(x0, x1);
             }
             *reinterpret_cast<uint4 *>(tile + sw128_offset(row, (cb >> 3) + c)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
 }
 
-// One level of one plane: 4 corner reads + bilinear blend, arithmetic identical to gridcore.cuh:lvl2_interp / k_grid_fwd<float,2,1>
-// (weights (1-fx|fx)*(1-fy|fy), four fmas in corner order (0,0),(1,0),(0,1),(1,1)).  Index math: dense levels i + j*stride, hashed
-// levels (i ^ j*2654435761) & (size-1) — the level kind is warp-uniform.  (gx, gy) = 1 - (fx, fy).
-__device__ __forceinline__ float plane_feature(const float *__restrict__ tab, const HeadLvl &g, uint32_t i, uint32_t j, float fx, float gx, float fy, float gy) {
-    const uint32_t m0 = j * g.mul, m1 = m0 + g.mul;
-    uint32_t i00, i10, i01, i11;
-    if (g.mask != 0xffffffffu) { i00 = (i ^ m0) & g.mask; i10 = ((i + 1u) ^ m0) & g.mask; i01 = (i ^ m1) & g.mask; i11 = ((i + 1u) ^ m1) & g.mask; }
-    else { i00 = i + m0; i10 = i00 + 1u; i01 = i + m1; i11 = i01 + 1u; }
-    const float v00 = __ldg(tab + i00), v10 = __ldg(tab + i10), v01 = __ldg(tab + i01), v11 = __ldg(tab + i11);
+// bilinear blend in the arithmetic of gridcore.cuh:lvl2_interp / k_grid_fwd<float,2,1>: weights (1-fx|fx)*(1-fy|fy), four fmas in corner
+// order (0,0),(1,0),(0,1),(1,1).  (gx, gy) = 1 - (fx, fy).
+__device__ __forceinline__ float blend4(float v00, float v10, float v01, float v11, float fx, float gx, float fy, float gy) {
     float r = __fmaf_rn(__fmul_rn(gx, gy), v00, 0.0f);
     r = __fmaf_rn(__fmul_rn(fx, gy), v10, r);
     r = __fmaf_rn(__fmul_rn(gx, fy), v01, r);
     r = __fmaf_rn(__fmul_rn(fx, fy), v11, r);
     return r;
+}
+// One plane of a DENSE level: entry (i, j) sits at i + j * stride, so the four corners are two adjacent pairs (two address computations).
+__device__ __forceinline__ float plane_dense(const float *__restrict__ lvl_tab, uint32_t stride, uint32_t i, uint32_t j, float fx, float gx, float fy, float gy) {
+    const float *p0 = lvl_tab + (j * stride + i), *p1 = p0 + stride;
+    return blend4(__ldg(p0), __ldg(p0 + 1), __ldg(p1), __ldg(p1 + 1), fx, gx, fy, gy);
+}
+// One plane of a HASHED level: index (i ^ j * 2654435761) & (size - 1)  (gridencoder.cu:54-72 with D = 2; size is a power of two)
+__device__ __forceinline__ float plane_hashed(const float *__restrict__ lvl_tab, uint32_t prime, uint32_t mask, uint32_t i, uint32_t j, float fx, float gx, float fy, float gy) {
+    const uint32_t m0 = j * prime, m1 = m0 + prime, i1 = i + 1u;
+    return blend4(__ldg(lvl_tab + ((i ^ m0) & mask)), __ldg(lvl_tab + ((i1 ^ m0) & mask)), __ldg(lvl_tab + ((i ^ m1) & mask)), __ldg(lvl_tab + ((i1 ^ m1) & mask)),
+                  fx, gx, fy, gy);
+}
+
+// Levels (2k, 2k+1) of the three planes for one sample -> three packed half2 words of the sample's row of an X tile.  The cell of x, y and z
+// is computed once per level and shared by the planes; 12 independent loads in flight per level.  NOT inlined: the tile loop calls it from
+// six places (one trip between every MMA issue and its completion wait).  `ok`: bit p set = plane p in range (else the features are 0,
+// gridencoder.cu:98-122);  `lv` points at the pair's constants in shared memory;  `row` = the sample's row base in the tile, r7 = row & 7.
+__device__ __noinline__ void gather_pair(const float *__restrict__ t_xy, const float *__restrict__ t_yz, const float *__restrict__ t_xz, const HeadLvl *lv,
+                                         float ux, float uy, float uz, uint32_t ok, uint8_t *row, uint32_t r7, uint32_t w0) {
+    float f[2][3];
+#pragma unroll
+    for (uint32_t q = 0; q < 2; q++) {
+        const HeadLvl g = lv[q];                                   // warp-uniform shared-memory read
+        const float qx = __fmaf_rn(ux, g.scale, 0.5f), qy = __fmaf_rn(uy, g.scale, 0.5f), qz = __fmaf_rn(uz, g.scale, 0.5f);
+        const uint32_t ix = (uint32_t)floorf(qx), iy = (uint32_t)floorf(qy), iz = (uint32_t)floorf(qz);
+        const float fx = __fsub_rn(qx, (float)ix), fy = __fsub_rn(qy, (float)iy), fz = __fsub_rn(qz, (float)iz);
+        const float gx = __fsub_rn(1.0f, fx), gy = __fsub_rn(1.0f, fy), gz = __fsub_rn(1.0f, fz);
+        const float *b_xy = t_xy + g.off, *b_yz = t_yz + g.off, *b_xz = t_xz + g.off;
+        if (g.mask == 0xffffffffu) {                                // the level kind is uniform over the grid
+            f[q][0] = plane_dense(b_xy, g.mul, ix, iy, fx, gx, fy, gy);     // split_xyz: xy, yz, xz (network.py:208-212)
+            f[q][1] = plane_dense(b_yz, g.mul, iy, iz, fy, gy, fz, gz);
+            f[q][2] = plane_dense(b_xz, g.mul, ix, iz, fx, gx, fz, gz);
+        } else {
+            f[q][0] = plane_hashed(b_xy, g.mul, g.mask, ix, iy, fx, gx, fy, gy);
+            f[q][1] = plane_hashed(b_yz, g.mul, g.mask, iy, iz, fy, gy, fz, gz);
+            f[q][2] = plane_hashed(b_xz, g.mul, g.mask, ix, iz, fx, gx, fz, gz);
+        }
+    }
+#pragma unroll
+    for (uint32_t p = 0; p < 3; p++) {
+        const uint32_t word = p * 6u + w0;                          // 32-bit word of (level 2k, 2k+1) inside plane p's 6 words
+        *reinterpret_cast<uint32_t *>(row + (((word >> 2) ^ r7) << 4) + (word & 3u) * 4u) = ((ok >> p) & 1u) ? pack2(f[0][p], f[1][p]) : 0u;
+    }
 }
 
 // real spherical harmonics, degree 4 (16 terms), fp32 — same polynomials as shencoder.cu:44-67
@@ -139,39 +179,41 @@ __device__ __noinline__ void issue_mma(uint32_t d_tmem, uint32_t a_saddr, uint32
 // the kernel
 // ---------------------------------------------------------------------------------------------------
 struct HeadSmem {                       // lives after the 1024-aligned weight image and operand tiles
+    HeadLvl lvl[12];
     float enc_a_h[32];                  // fp16-rounded audio code
     float eye_w1[16], unc_w1[32], ind_bias[64];
     float eye_val;
     uint32_t n_valid;
-    uint32_t tile_live[HG_WGS];
     uint32_t tmem_base;
     uint64_t bar_w;                     // weight image landed
     uint64_t bar_mma[HG_WGS];           // per-warpgroup MMA completion
 };
+
+// normalised grid coordinates of a sample + which planes are in range
+struct SampleCoord { float ux, uy, uz; uint32_t ok; };
 
 __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_constant__ HeadArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // pointer arithmetic keeps the shared address space visible to the compiler
     uint8_t *s_w = base;
     uint8_t *s_tiles = base + HW_BYTES;
-    HeadSmem &S = *reinterpret_cast<HeadSmem *>(s_tiles + HG_WGS * 2 * HG_TILE_BYTES);
+    HeadSmem &S = *reinterpret_cast<HeadSmem *>(s_tiles + HG_WGS * 3 * HG_TILE_BYTES);
 
     const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u, warp = tid >> 5;
     // nothing to do (a loop iteration after the frame finished): leave before touching TMEM / the weight image
     const uint32_t n_valid_early = a.n_valid ? (uint32_t)max(0, min((int)a.M, __ldg(a.n_valid))) : a.M;
     if (n_valid_early <= blockIdx.x * HG_WGS * HG_TILE) return;
-    uint8_t *sX = s_tiles + wg * 2 * HG_TILE_BYTES, *sH = sX + HG_TILE_BYTES;
+    uint8_t *sXb = s_tiles + wg * 3 * HG_TILE_BYTES, *sH = sXb + 2 * HG_TILE_BYTES;      // X[0], X[1], H
 
     // ---- one-time setup ------------------------------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(&S.bar_w, 1);
-        for (int g = 0; g < HG_WGS; g++) mbar_init(&S.bar_mma[g], 1);
+        for (int g = 0; g < (int)HG_WGS; g++) mbar_init(&S.bar_mma[g], 1);
         fence_mbar_init();
         mbar_expect_tx(&S.bar_w, HW_BYTES);
         bulk_g2s(s_w, a.wimg, HW_BYTES, &S.bar_w);
         S.n_valid = a.n_valid ? (uint32_t)max(0, min((int)a.M, *a.n_valid)) : a.M;
         S.eye_val = a.eye ? a.eye[0] : 0.0f;
-        for (int g = 0; g < (int)HG_WGS; g++) S.tile_live[g] = 0;
     }
     if (warp == 1) tmem_alloc(&S.tmem_base, 512);
     if (tid >= 128 && tid < 160) S.enc_a_h[tid - 128] = round_h(a.enc_a[tid - 128]);
@@ -184,6 +226,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             for (int q = 0; q < 4; q++) b = fmaf(a.wsmall[HS_IND_W + j * 4 + q], round_h(a.ind_code[q]), b);
         S.ind_bias[j] = b;
     }
+    if (tid >= 320 && tid < 332) S.lvl[tid - 320] = a.lvl[tid - 320];
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -191,114 +234,110 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
 
     const uint32_t n_valid = S.n_valid;
     const uint32_t n_tiles = (n_valid + HG_TILE - 1) / HG_TILE;
-    const uint32_t tmem_wg = S.tmem_base + wg * 128u;                       // this warpgroup's 128 columns
+    const uint32_t tmem_wg = S.tmem_base + wg * HG_TMEM_COLS;               // this warpgroup's columns
     const uint32_t tmem_ld = tmem_wg + (((warp & 3u) * 32u) << 16);         // + this warp's lane quarter
-    const uint32_t sX_a = smem_u32(sX), sH_a = smem_u32(sH), sW_a = smem_u32(s_w);
+    const uint32_t sH_a = smem_u32(sH), sW_a = smem_u32(s_w);
     uint64_t *bar = &S.bar_mma[wg];
     uint32_t phase = 0;
-    const uint32_t nA = a.has_unc ? 112u : 80u;
+    const float *t_xy = a.tab[0], *t_yz = a.tab[1], *t_xz = a.tab[2];
+    const uint32_t r7 = t & 7u;
+    const uint32_t row_off = (t >> 3) * 1024u + r7 * 128u;                  // this sample's row inside a tile
 
     auto sync_wg = [&]() { bar_sync(1 + wg, 128); };
     auto mma_done = [&]() { mbar_wait(bar, phase); phase ^= 1u; fence_after_sync(); };
     // operands written by this warpgroup's threads -> visible to the tensor pipe, then one thread issues
     auto publish = [&]() { fence_before_sync(); fence_proxy_async(); sync_wg(); };
-
-    for (uint32_t tile = blockIdx.x * HG_WGS + wg; tile < n_tiles; tile += gridDim.x * HG_WGS) {
-        const uint32_t m = tile * HG_TILE + t;
+    auto row_live = [&](uint32_t m) {
         bool live = m < n_valid;
-        if (a.live_deltas) {
-            // frame mode: a row whose march slot was not produced (delta == 0) is ignored by the composite; a tile made only of such
-            // rows (rays outside the head, rays that ran out) is skipped altogether
-            live = live && (__ldg(a.live_deltas + 2 * (size_t)m) != 0.0f);
-            if (__any_sync(0xffffffffu, live)) S.tile_live[wg] = 1;
-            sync_wg();
-            const uint32_t any_live = S.tile_live[wg];
-            sync_wg();
-            if (t == 0) S.tile_live[wg] = 0;
-            if (!any_live) continue;
-        }
-        // ---- P0: gather 36 tri-plane features -> X (fp16, K padded to 48) ---------------------------------------------
-        float px = 0, py = 0, pz = 0, dxv = 0, dyv = 0, dzv = 1;
-        if (live) {
-            px = __ldcs(a.xyzs + 3 * (size_t)m); py = __ldcs(a.xyzs + 3 * (size_t)m + 1); pz = __ldcs(a.xyzs + 3 * (size_t)m + 2);
-            dxv = __ldcs(a.dirs + 3 * (size_t)m); dyv = __ldcs(a.dirs + 3 * (size_t)m + 1); dzv = __ldcs(a.dirs + 3 * (size_t)m + 2);
-        }
-        {
-            // (x + bound) / (2 bound), fp32, like GridEncoder.forward (grid.py:143); out-of-range coordinates give zero features
-            // (gridencoder.cu:98-122) — they are clamped for addressing and masked at the end
+        // frame mode: a row whose march slot was not produced (delta == 0) is ignored by the composite
+        if (live && a.live_deltas) live = __ldg(a.live_deltas + 2 * (size_t)m) != 0.0f;
+        return live;
+    };
+    // (x + bound) / (2 bound), fp32, like GridEncoder.forward (grid.py:143); out-of-range coordinates give zero features
+    // (gridencoder.cu:98-122) — they are clamped for addressing and masked when stored
+    auto load_coord = [&](uint32_t m, bool live) {
+        float px = 0, py = 0, pz = 0;
+        if (live) { px = __ldcs(a.xyzs + 3 * (size_t)m); py = __ldcs(a.xyzs + 3 * (size_t)m + 1); pz = __ldcs(a.xyzs + 3 * (size_t)m + 2); }
+        float ux, uy, uz;
+        if (a.inv_two_bound != 0.0f) {       // 2 * bound is a power of two: the division is an exact scaling
+            ux = __fmul_rn(__fadd_rn(px, a.bound), a.inv_two_bound); uy = __fmul_rn(__fadd_rn(py, a.bound), a.inv_two_bound); uz = __fmul_rn(__fadd_rn(pz, a.bound), a.inv_two_bound);
+        } else {
             const float two_b = __fmul_rn(2.0f, a.bound);
-            float ux = __fdiv_rn(__fadd_rn(px, a.bound), two_b), uy = __fdiv_rn(__fadd_rn(py, a.bound), two_b), uz = __fdiv_rn(__fadd_rn(pz, a.bound), two_b);
-            const bool okx = !(ux < 0.0f || ux > 1.0f), oky = !(uy < 0.0f || uy > 1.0f), okz = !(uz < 0.0f || uz > 1.0f);
-            const bool ok_xy = live && okx && oky, ok_yz = live && oky && okz, ok_xz = live && okx && okz;
-            ux = okx ? ux : 0.0f; uy = oky ? uy : 0.0f; uz = okz ? uz : 0.0f;
-            const float *t_xy = a.tab[0], *t_yz = a.tab[1], *t_xz = a.tab[2];
-            // level-major: the cell of x, y and z is computed once per level and shared by the three planes; 12 independent loads in
-            // flight per level; two levels per trip so each plane stores one packed half2 word
-#pragma unroll 1
-            for (uint32_t l = 0; l < 12; l += 2) {
-                float f[2][3];
-#pragma unroll
-                for (uint32_t q = 0; q < 2; q++) {
-                    const HeadLvl g = a.lvl[l + q];                       // kernel-parameter (constant bank) read, warp-uniform
-                    const float qx = __fmaf_rn(ux, g.scale, 0.5f), qy = __fmaf_rn(uy, g.scale, 0.5f), qz = __fmaf_rn(uz, g.scale, 0.5f);
-                    const uint32_t ix = (uint32_t)floorf(qx), iy = (uint32_t)floorf(qy), iz = (uint32_t)floorf(qz);
-                    const float fx = __fsub_rn(qx, (float)ix), fy = __fsub_rn(qy, (float)iy), fz = __fsub_rn(qz, (float)iz);
-                    const float gx = __fsub_rn(1.0f, fx), gy = __fsub_rn(1.0f, fy), gz = __fsub_rn(1.0f, fz);
-                    f[q][0] = plane_feature(t_xy + g.off, g, ix, iy, fx, gx, fy, gy);   // split_xyz: xy, yz, xz (network.py:208-212)
-                    f[q][1] = plane_feature(t_yz + g.off, g, iy, iz, fy, gy, fz, gz);
-                    f[q][2] = plane_feature(t_xz + g.off, g, ix, iz, fx, gx, fz, gz);
-                }
-                const uint32_t w0 = l >> 1;                                   // 32-bit word of (level l, l+1) inside a plane's 6 words
-#pragma unroll
-                for (uint32_t p = 0; p < 3; p++) {
-                    const bool ok = (p == 0) ? ok_xy : ((p == 1) ? ok_yz : ok_xz);
-                    const uint32_t word = p * 6u + w0;
-                    *reinterpret_cast<uint32_t *>(sX + sw128_offset(t, word >> 2) + (word & 3u) * 4u) = ok ? pack2(f[0][p], f[1][p]) : 0u;
-                }
-            }
-            // zero the K padding: words 18..23 (features 36..47)
-#pragma unroll
-            for (uint32_t word = 18; word < 24; word++) *reinterpret_cast<uint32_t *>(sX + sw128_offset(t, word >> 2) + (word & 3u) * 4u) = 0u;
+            ux = __fdiv_rn(__fadd_rn(px, a.bound), two_b); uy = __fdiv_rn(__fadd_rn(py, a.bound), two_b); uz = __fdiv_rn(__fadd_rn(pz, a.bound), two_b);
         }
-        float shv[16];
-        sh4(dxv, dyv, dzv, shv);
+        const bool okx = !(ux < 0.0f || ux > 1.0f), oky = !(uy < 0.0f || uy > 1.0f), okz = !(uz < 0.0f || uz > 1.0f);
+        SampleCoord c;
+        c.ux = okx ? ux : 0.0f; c.uy = oky ? uy : 0.0f; c.uz = okz ? uz : 0.0f;
+        c.ok = live ? ((okx && oky ? 1u : 0u) | (oky && okz ? 2u : 0u) | (okx && okz ? 4u : 0u)) : 0u;
+        return c;
+    };
+    auto gather_trip = [&](const SampleCoord &c, uint8_t *tile, uint32_t k) {     // levels 2k, 2k+1 of the three planes -> X tile
+        gather_pair(t_xy, t_yz, t_xz, &S.lvl[2 * k], c.ux, c.uy, c.uz, c.ok, tile + row_off, r7, k);
+    };
+    auto zero_k_padding = [&](uint8_t *tile) {        // words 18..23 (features 36..47) of the row
+        *reinterpret_cast<uint2 *>(tile + row_off + ((4u ^ r7) << 4) + 8u) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint4 *>(tile + row_off + ((5u ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+    };
+
+    const uint32_t tile_stride = gridDim.x * HG_WGS;
+    uint32_t tile = blockIdx.x * HG_WGS + wg;
+    uint32_t buf = 0;
+    // ---- pipeline prologue: the first tile's features (later tiles are gathered underneath the previous tile's MMA phases) -------
+    if (tile < n_tiles) {
+        const uint32_t m0 = tile * HG_TILE + t;
+        const SampleCoord c = load_coord(m0, row_live(m0));
+#pragma unroll 1
+        for (uint32_t k = 0; k < 6; k++) gather_trip(c, sXb, k);
+        zero_k_padding(sXb);
+    }
+    for (; tile < n_tiles; tile += tile_stride) {
+        uint8_t *sX = sXb + buf * HG_TILE_BYTES, *sXn = sXb + (buf ^ 1u) * HG_TILE_BYTES;
+        const uint32_t sX_a = smem_u32(sX);
+        const uint32_t m = tile * HG_TILE + t;
+        const bool live = row_live(m);
+        float dxv = 0, dyv = 0, dzv = 1;
+        if (live) { dxv = __ldcs(a.dirs + 3 * (size_t)m); dyv = __ldcs(a.dirs + 3 * (size_t)m + 1); dzv = __ldcs(a.dirs + 3 * (size_t)m + 2); }
+        const bool has_next = tile + tile_stride < n_tiles;                  // uniform over the warpgroup
+        SampleCoord cn = {0.0f, 0.0f, 0.0f, 0u};
+        if (has_next) { const uint32_t mn = (tile + tile_stride) * HG_TILE + t; cn = load_coord(mn, row_live(mn)); }
         publish();
-        // ---- P1: [aud hidden | eye hidden | unc hidden] = X * WA[0:nA] --------------------------------------------------
-        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 0, sX_a, sW_a + HW_A, 3, nA, false); mma_commit(bar); }
+        // ---- P1: [aud hidden | eye hidden | sigma hidden (enc_x part)] = X * WA -------------------------------------------
+        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sX_a, sW_a + HW_A, 3, 144, false); mma_commit(bar); }
+        if (has_next) gather_trip(cn, sXn, 0);
         mma_done();
         float eye_att, unc_out = 0.6931471805599453f;       // testing: log(1 + e^0) (network.py:245,278)
         {
-            uint32_t acc[32];
-            hidden_epilogue<true, false>(tmem_ld + 0, sH, t, nullptr);
+            hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr);
             uint32_t e16[16];
-            ld16(tmem_ld + 64, e16); wait_ld();
+            ld16(tmem_ld + TC_EYE, e16); wait_ld();
             float dot = 0.0f;
 #pragma unroll
             for (int j = 0; j < 16; j++) dot = fmaf(fmaxf(round_h(__uint_as_float(e16[j])), 0.0f), S.eye_w1[j], dot);
             // sigmoid evaluated on the fp16 logit, result rounded to fp16 (torch.sigmoid on a half tensor)
             eye_att = round_h(1.0f / (1.0f + expf(-round_h(dot))));
+        }
+        publish();
+        // ---- P2: att = H * WB ; [unc hidden = X * WU] --------------------------------------------------------------------------
+        if (t == 0) {
+            fence_after_sync();
+            issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_B, 4, 32, false);
+            if (a.has_unc) issue_mma(tmem_wg + TC_A + 32, sX_a, sW_a + HW_U, 3, 32, false);
+            mma_commit(bar);
+        }
+        if (has_next) gather_trip(cn, sXn, 1);
+        mma_done();
+        float amb_aud;
+        {
+            uint32_t acc[32];
             if (a.has_unc) {
-                ld32(tmem_ld + 80, acc); wait_ld();
+                ld32(tmem_ld + TC_A + 32, acc); wait_ld();
                 float du = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 32; j++) du = fmaf(fmaxf(round_h(__uint_as_float(acc[j])), 0.0f), S.unc_w1[j], du);
                 du = round_h(du);
                 unc_out = logf(1.0f + expf(du));                        // torch.log(1 + torch.exp(.)) in fp32 (network.py:278)
             }
-        }
-        publish();
-        // ---- P2: att = H * WB ; sigma hidden (enc_x part) = X * WA[112:176] -------------------------------------------
-        if (t == 0) {
-            fence_after_sync();
-            issue_mma(tmem_wg + 0, sH_a, sW_a + HW_B, 4, 32, false);
-            issue_mma(tmem_wg + 64, sX_a, sW_a + HW_A + 112u * 128u, 3, 64, false);
-            mma_commit(bar);
-        }
-        mma_done();
-        float amb_aud;
-        {
-            uint32_t acc[32];
-            ld32(tmem_ld + 0, acc); wait_ld();
+            ld32(tmem_ld + TC_A, acc); wait_ld();
             float n2 = 0.0f;
             uint32_t w[16];
 #pragma unroll
@@ -308,7 +347,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
                 w[j] = pack2(S.enc_a_h[2 * j] * a0, S.enc_a_h[2 * j + 1] * a1);    // enc_w = enc_a * att, fp16 (network.py:285)
             }
             amb_aud = sqrtf(n2);                                                    // .norm(dim=-1) in fp32 (network.py:308)
-            // EW operand into X: chunks 0..3 = enc_w, chunk 4 = [e, 0..], chunk 5 = 0   (K = 33 padded to 48)
+            // EW operand into X (the features are consumed): chunks 0..3 = enc_w, chunk 4 = [e, 0..], chunk 5 = 0   (K = 33 padded to 48)
 #pragma unroll
             for (uint32_t c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(sX + sw128_offset(t, c)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
             const float e = a.eye ? S.eye_val * eye_att : 0.0f;                     // e = e * eye_att (network.py:291)
@@ -317,25 +356,30 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         }
         publish();
         // ---- P3: sigma hidden += [enc_w, e] * WC -------------------------------------------------------------------------
-        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 64, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
+        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
+        if (has_next) gather_trip(cn, sXn, 2);
         mma_done();
-        hidden_epilogue<true, false>(tmem_ld + 64, sH, t, nullptr);
+        hidden_epilogue<true, false>(tmem_ld + TC_S, sH, t, nullptr);
         publish();
         // ---- P4: sigma layer 1 --------------------------------------------------------------------------------------------
-        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 0, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
+        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
+        if (has_next) gather_trip(cn, sXn, 3);
         mma_done();
-        hidden_epilogue<true, false>(tmem_ld + 0, sH, t, nullptr);
+        hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr);
         publish();
         // ---- P5: sigma layer 2: cols 0..63 = geo_feat, col 64 = density logit (rows rotated at pack time) -----------------
-        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 0, sH_a, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
+        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
+        if (has_next) gather_trip(cn, sXn, 4);
         mma_done();
         float sigma;
         {
-            hidden_epilogue<false, false>(tmem_ld + 0, sH, t, nullptr);
+            hidden_epilogue<false, false>(tmem_ld + TC_A, sH, t, nullptr);
             uint32_t s16[16];
-            ld16(tmem_ld + 64, s16); wait_ld();
+            ld16(tmem_ld + TC_A + 64, s16); wait_ld();
             sigma = expf(round_h(__uint_as_float(s16[0]))) * a.density_scale;       // torch.exp(h[..., 0]) in fp32 (network.py:301)
             // view-direction SH into X chunks 0,1 (the 16-wide K step of color layer 0)
+            float shv[16];
+            sh4(dxv, dyv, dzv, shv);
             uint32_t w[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) w[j] = pack2(shv[2 * j], shv[2 * j + 1]);
@@ -346,19 +390,21 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         // ---- P6: color layer 0 = geo * WF0 + sh * WF1 (+ ind-code bias in the epilogue) -------------------------------------
         if (t == 0) {
             fence_after_sync();
-            issue_mma(tmem_wg + 0, sH_a, sW_a + HW_F0, 4, 64, false);
-            issue_mma(tmem_wg + 0, sX_a, sW_a + HW_F1, 1, 64, true);
+            issue_mma(tmem_wg + TC_S, sH_a, sW_a + HW_F0, 4, 64, false);
+            issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_F1, 1, 64, true);
             mma_commit(bar);
         }
+        if (has_next) gather_trip(cn, sXn, 5);
         mma_done();
-        hidden_epilogue<true, true>(tmem_ld + 0, sH, t, S.ind_bias);
+        hidden_epilogue<true, true>(tmem_ld + TC_S, sH, t, S.ind_bias);
         publish();
         // ---- P7: color layer 1 (N padded 3 -> 16) -----------------------------------------------------------------------------
-        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + 64, sH_a, sW_a + HW_G, 4, 16, false); mma_commit(bar); }
+        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_G, 4, 16, false); mma_commit(bar); }
+        if (has_next) zero_k_padding(sXn);
         mma_done();
         {
             uint32_t c16[16];
-            ld16(tmem_ld + 64, c16); wait_ld();
+            ld16(tmem_ld + TC_A, c16); wait_ld();
             if (live) {
                 float rgb[3];
 #pragma unroll
@@ -374,8 +420,8 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
                 if (a.unc) __stcs(a.unc + m, unc_out);
             }
         }
-        fence_before_sync();
-        sync_wg();          // all TMEM reads / smem reads of this tile are done before the next tile's gather overwrites X
+        buf ^= 1u;
+        // the next tile's publish() orders this tile's TMEM reads (fence::before_thread_sync + warpgroup barrier) before its first MMA
     }
 
     fence_before_sync();
@@ -383,7 +429,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
     if (warp == 1) tmem_dealloc(S.tmem_base, 512);
 }
 
-size_t head_smem_bytes() { return 1024 + HW_BYTES + (size_t)HG_WGS * 2 * HG_TILE_BYTES + sizeof(HeadSmem); }
+size_t head_smem_bytes() { return 1024 + HW_BYTES + (size_t)HG_WGS * 3 * HG_TILE_BYTES + sizeof(HeadSmem); }
 
 int launch_head_forward(const HeadArgs &a, cudaStream_t st) {
     static bool attr = false;
@@ -486,8 +532,8 @@ int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
     };
     add(w->aud_att_w0, HW_A, 64, 64, 36, 0, 36, 0);
     add(w->eye_att_w0, HW_A + 64 * 128, 16, 16, 36, 0, 36, 0);
-    add(w->unc_w0, HW_A + 80 * 128, 32, 32, 36, 0, 36, 0);                 // NULL src -> zeros
-    add(w->sigma_w0, HW_A + 112 * 128, 64, 64, 69, 0, 36, 0);
+    add(w->sigma_w0, HW_A + 80 * 128, 64, 64, 69, 0, 36, 0);
+    add(w->unc_w0, HW_U, 32, 32, 36, 0, 36, 0);                            // NULL src -> zeros
     add(w->aud_att_w1, HW_B, 32, 32, 64, 0, 64, 0);
     add(w->sigma_w0, HW_C, 64, 64, 69, 36, 33, 0);
     add(w->sigma_w1, HW_D, 64, 64, 64, 0, 64, 0);
@@ -522,6 +568,11 @@ int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *di
     a.tab[0] = m->w.table_xy; a.tab[1] = m->w.table_yz; a.tab[2] = m->w.table_xz;
     for (int l = 0; l < 12; l++) a.lvl[l] = m->lvl[l];
     a.bound = m->w.bound;
+    {   // (x + b) / (2b) == (x + b) * (1 / 2b) exactly when 2b is a power of two
+        int ex = 0;
+        const float two_b = 2.0f * a.bound;
+        a.inv_two_bound = (two_b > 0.0f && frexpf(two_b, &ex) == 0.5f) ? 1.0f / two_b : 0.0f;
+    }
     a.wimg = m->wimg; a.wsmall = m->wsmall;
     a.enc_a = enc_a; a.ind_code = ind_code; a.eye = eye;
     a.sigmas = sigmas; a.rgbs = rgbs; a.amb_aud = amb_aud; a.amb_eye = amb_eye; a.unc = unc;

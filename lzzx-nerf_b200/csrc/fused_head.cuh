@@ -5,13 +5,19 @@
 namespace b2n {
 
 constexpr uint32_t HG_TILE = 128;                  // samples per tile = UMMA M
-constexpr uint32_t HG_WGS = 4;                     // warpgroups (tiles in flight) per CTA
+constexpr uint32_t HG_WGS = 3;                     // warpgroups (tiles in flight) per CTA; each owns two X tiles (double-buffered gather) and one H tile
+constexpr uint32_t HG_TMEM_COLS = 160;             // TMEM columns per warpgroup (3 x 160 of the 512 allocated)
+// accumulator columns inside a warpgroup's TMEM slice
+constexpr uint32_t TC_A = 0;                       // 64: aud hidden (P1) | att 32 + unc hidden 32 (P2) | sigma layer 1 (P4) | geo 64 + logit (P5, 80 wide) | rgb (P7)
+constexpr uint32_t TC_EYE = 64;                    // 16: eye hidden (P1)
+constexpr uint32_t TC_S = 80;                      // 64: sigma hidden, accumulated by P1 and P3 | color hidden (P6)
 constexpr uint32_t HG_THREADS = HG_WGS * 128;
 constexpr uint32_t HG_TILE_BYTES = HG_TILE * 128;  // one SWIZZLE_128B K-atom of an A operand: 128 rows x 128 B
 
 // fp16 weight image, every region a SWIZZLE_128B K-major atom [rows x 128 B]; offsets are multiples of 1024
-constexpr uint32_t HW_A = 0;                        // 176 rows: aud_att0 (64) | eye_att0 (16) | unc0 (32) | sigma0[:, :36] (64)
-constexpr uint32_t HW_B = HW_A + 176 * 128;         //  32 rows: aud_att1
+constexpr uint32_t HW_A = 0;                        // 144 rows: aud_att0 (64) | eye_att0 (16) | sigma0[:, :36] (64)  — one N = 144 MMA
+constexpr uint32_t HW_U = HW_A + 144 * 128;         //  32 rows: unc0
+constexpr uint32_t HW_B = HW_U + 32 * 128;          //  32 rows: aud_att1
 constexpr uint32_t HW_C = HW_B + 32 * 128;          //  64 rows: sigma0[:, 36:69]  (enc_w 32, eye 1)
 constexpr uint32_t HW_D = HW_C + 64 * 128;          //  64 rows: sigma1
 constexpr uint32_t HW_E = HW_D + 64 * 128;          //  80 rows: sigma2, rows rotated: 0..63 geo_feat, 64 density logit
@@ -19,7 +25,7 @@ constexpr uint32_t HW_F0 = HW_E + 80 * 128;         //  64 rows: color0[:, 16:80
 constexpr uint32_t HW_F1 = HW_F0 + 64 * 128;        //  64 rows: color0[:, 0:16]  (SH)
 constexpr uint32_t HW_G = HW_F1 + 64 * 128;         //  16 rows: color1 (3 valid)
 constexpr uint32_t HW_BYTES = HW_G + 16 * 128;      // 71 680 B
-static_assert(HW_B % 1024 == 0 && HW_C % 1024 == 0 && HW_D % 1024 == 0 && HW_E % 1024 == 0 && HW_F0 % 1024 == 0 && HW_F1 % 1024 == 0 && HW_G % 1024 == 0, "atoms must be 1024 B aligned");
+static_assert(HW_U % 1024 == 0 && HW_B % 1024 == 0 && HW_C % 1024 == 0 && HW_D % 1024 == 0 && HW_E % 1024 == 0 && HW_F0 % 1024 == 0 && HW_F1 % 1024 == 0 && HW_G % 1024 == 0, "atoms must be 1024 B aligned");
 
 // small fp32 vectors (values pre-rounded to fp16)
 constexpr uint32_t HS_EYE_W1 = 0, HS_UNC_W1 = 16, HS_IND_W = 48, HS_FLOATS = 48 + 256;
@@ -40,6 +46,7 @@ struct HeadArgs {
     const float *tab[3];
     HeadLvl lvl[12];
     float bound;
+    float inv_two_bound;        // 1 / (2 bound) when 2 bound is a power of two (exact), else 0 -> divide
     const uint8_t *wimg;
     const float *wsmall;
     const float *enc_a, *ind_code, *eye;
