@@ -79,11 +79,10 @@ __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
     return r;
 }
 // TMEM -> fp16 operand tile: reads 64 accumulator columns of this thread's row starting at TMEM address `taddr`, applies
-// (+bias, ReLU) and writes them as halves 0..63 of row `row` of a SWIZZLE_128B tile.  Deliberately NOT inlined and rolled over
-// 32-column blocks: the kernel has five of these epilogues and three warpgroups in different phases, so code size (I-cache
-// footprint) matters more than the few loop instructions.
+// (+bias, ReLU) and writes them as halves 0..63 of row `row` of a SWIZZLE_128B tile.  Inlined (the table loads of a gather trip stay in
+// flight across it) but rolled over 32-column blocks to keep the tile loop's code size down.
 template <bool RELU, bool BIAS>
-__device__ __noinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, uint32_t row, const float *bias) {
+__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, uint32_t row, const float *bias) {
 #pragma unroll 1
     for (uint32_t cb = 0; cb < 64; cb += 32) {
         uint32_t acc[32];
@@ -103,55 +102,61 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, uint
     }
 }
 
-// bilinear blend in the arithmetic of gridcore.cuh:lvl2_interp / k_grid_fwd<float,2,1>: weights (1-fx|fx)*(1-fy|fy), four fmas in corner
-// order (0,0),(1,0),(0,1),(1,1).  (gx, gy) = 1 - (fx, fy).
-__device__ __forceinline__ float blend4(float v00, float v10, float v01, float v11, float fx, float gx, float fy, float gy) {
-    float r = __fmaf_rn(__fmul_rn(gx, gy), v00, 0.0f);
-    r = __fmaf_rn(__fmul_rn(fx, gy), v10, r);
-    r = __fmaf_rn(__fmul_rn(gx, fy), v01, r);
-    r = __fmaf_rn(__fmul_rn(fx, fy), v11, r);
-    return r;
-}
-// One plane of a DENSE level: entry (i, j) sits at i + j * stride, so the four corners are two adjacent pairs (two address computations).
-__device__ __forceinline__ float plane_dense(const float *__restrict__ lvl_tab, uint32_t stride, uint32_t i, uint32_t j, float fx, float gx, float fy, float gy) {
-    const float *p0 = lvl_tab + (j * stride + i), *p1 = p0 + stride;
-    return blend4(__ldg(p0), __ldg(p0 + 1), __ldg(p1), __ldg(p1 + 1), fx, gx, fy, gy);
-}
-// One plane of a HASHED level: index (i ^ j * 2654435761) & (size - 1)  (gridencoder.cu:54-72 with D = 2; size is a power of two)
-__device__ __forceinline__ float plane_hashed(const float *__restrict__ lvl_tab, uint32_t prime, uint32_t mask, uint32_t i, uint32_t j, float fx, float gx, float fy, float gy) {
-    const uint32_t m0 = j * prime, m1 = m0 + prime, i1 = i + 1u;
-    return blend4(__ldg(lvl_tab + ((i ^ m0) & mask)), __ldg(lvl_tab + ((i1 ^ m0) & mask)), __ldg(lvl_tab + ((i ^ m1) & mask)), __ldg(lvl_tab + ((i1 ^ m1) & mask)),
-                  fx, gx, fy, gy);
-}
+// ---- tri-plane gather, split in two halves so the table reads of one trip (2 levels x 3 planes x 4 corners = 24 loads per sample) stay
+// in flight underneath an MMA completion wait and its epilogue:  gather_issue() computes the cells and issues the loads, gather_finish()
+// blends and stores.  Arithmetic identical to gridcore.cuh:lvl2_interp / k_grid_fwd<float,2,1>: position fma(u, scale, 0.5), weights
+// (1-fx|fx)*(1-fy|fy), four fmas in corner order (0,0),(1,0),(0,1),(1,1); index i + j*stride on dense levels, (i ^ j*2654435761) & (size-1)
+// on hashed levels (gridencoder.cu:54-72 with D = 2; the level kind is uniform over the grid).
+struct SampleCoord { float ux, uy, uz; uint32_t ok; };      // normalised coordinates; ok bit p = plane p in range (and the row is live)
+struct GatherTrip { float v[2][3][4]; float fx[2], fy[2], fz[2]; };
 
-// Levels (2k, 2k+1) of the three planes for one sample -> three packed half2 words of the sample's row of an X tile.  The cell of x, y and z
-// is computed once per level and shared by the planes; 12 independent loads in flight per level.  NOT inlined: the tile loop calls it from
-// six places (one trip between every MMA issue and its completion wait).  `ok`: bit p set = plane p in range (else the features are 0,
-// gridencoder.cu:98-122);  `lv` points at the pair's constants in shared memory;  `row` = the sample's row base in the tile, r7 = row & 7.
-__device__ __noinline__ void gather_pair(const float *__restrict__ t_xy, const float *__restrict__ t_yz, const float *__restrict__ t_xz, const HeadLvl *lv,
-                                         float ux, float uy, float uz, uint32_t ok, uint8_t *row, uint32_t r7, uint32_t w0) {
-    float f[2][3];
+__device__ __forceinline__ void gather_issue(GatherTrip &G, const float *__restrict__ t_xy, const float *__restrict__ t_yz, const float *__restrict__ t_xz,
+                                             const HeadLvl *lv, const SampleCoord &c) {
 #pragma unroll
     for (uint32_t q = 0; q < 2; q++) {
         const HeadLvl g = lv[q];                                   // warp-uniform shared-memory read
-        const float qx = __fmaf_rn(ux, g.scale, 0.5f), qy = __fmaf_rn(uy, g.scale, 0.5f), qz = __fmaf_rn(uz, g.scale, 0.5f);
+        const float qx = __fmaf_rn(c.ux, g.scale, 0.5f), qy = __fmaf_rn(c.uy, g.scale, 0.5f), qz = __fmaf_rn(c.uz, g.scale, 0.5f);
         const uint32_t ix = (uint32_t)floorf(qx), iy = (uint32_t)floorf(qy), iz = (uint32_t)floorf(qz);
-        const float fx = __fsub_rn(qx, (float)ix), fy = __fsub_rn(qy, (float)iy), fz = __fsub_rn(qz, (float)iz);
-        const float gx = __fsub_rn(1.0f, fx), gy = __fsub_rn(1.0f, fy), gz = __fsub_rn(1.0f, fz);
-        const float *b_xy = t_xy + g.off, *b_yz = t_yz + g.off, *b_xz = t_xz + g.off;
-        if (g.mask == 0xffffffffu) {                                // the level kind is uniform over the grid
-            f[q][0] = plane_dense(b_xy, g.mul, ix, iy, fx, gx, fy, gy);     // split_xyz: xy, yz, xz (network.py:208-212)
-            f[q][1] = plane_dense(b_yz, g.mul, iy, iz, fy, gy, fz, gz);
-            f[q][2] = plane_dense(b_xz, g.mul, ix, iz, fx, gx, fz, gz);
+        G.fx[q] = __fsub_rn(qx, (float)ix); G.fy[q] = __fsub_rn(qy, (float)iy); G.fz[q] = __fsub_rn(qz, (float)iz);
+        // planes (i, j): xy = (ix, iy), yz = (iy, iz), xz = (ix, iz)   (split_xyz, network.py:208-212)
+        const uint32_t my0 = iy * g.mul, my1 = my0 + g.mul, mz0 = iz * g.mul, mz1 = mz0 + g.mul, ix1 = ix + 1u, iy1 = iy + 1u;
+        uint32_t e[3][4];
+        if (g.mask == 0xffffffffu) {
+            e[0][0] = ix + my0; e[0][1] = ix1 + my0; e[0][2] = ix + my1; e[0][3] = ix1 + my1;
+            e[1][0] = iy + mz0; e[1][1] = iy1 + mz0; e[1][2] = iy + mz1; e[1][3] = iy1 + mz1;
+            e[2][0] = ix + mz0; e[2][1] = ix1 + mz0; e[2][2] = ix + mz1; e[2][3] = ix1 + mz1;
         } else {
-            f[q][0] = plane_hashed(b_xy, g.mul, g.mask, ix, iy, fx, gx, fy, gy);
-            f[q][1] = plane_hashed(b_yz, g.mul, g.mask, iy, iz, fy, gy, fz, gz);
-            f[q][2] = plane_hashed(b_xz, g.mul, g.mask, ix, iz, fx, gx, fz, gz);
+            e[0][0] = (ix ^ my0) & g.mask; e[0][1] = (ix1 ^ my0) & g.mask; e[0][2] = (ix ^ my1) & g.mask; e[0][3] = (ix1 ^ my1) & g.mask;
+            e[1][0] = (iy ^ mz0) & g.mask; e[1][1] = (iy1 ^ mz0) & g.mask; e[1][2] = (iy ^ mz1) & g.mask; e[1][3] = (iy1 ^ mz1) & g.mask;
+            e[2][0] = (ix ^ mz0) & g.mask; e[2][1] = (ix1 ^ mz0) & g.mask; e[2][2] = (ix ^ mz1) & g.mask; e[2][3] = (ix1 ^ mz1) & g.mask;
         }
+        const float *b0 = t_xy + g.off, *b1 = t_yz + g.off, *b2 = t_xz + g.off;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) { G.v[q][0][k] = __ldg(b0 + e[0][k]); G.v[q][1][k] = __ldg(b1 + e[1][k]); G.v[q][2][k] = __ldg(b2 + e[2][k]); }
+    }
+}
+__device__ __forceinline__ float blend4(const float (&v)[4], float fx, float gx, float fy, float gy) {
+    float r = __fmaf_rn(__fmul_rn(gx, gy), v[0], 0.0f);
+    r = __fmaf_rn(__fmul_rn(fx, gy), v[1], r);
+    r = __fmaf_rn(__fmul_rn(gx, fy), v[2], r);
+    r = __fmaf_rn(__fmul_rn(fx, fy), v[3], r);
+    return r;
+}
+// blend + store: levels (2k, 2k+1) of plane p are one packed half2 word (word p*6 + k) of the sample's row; out-of-range planes store 0
+// (gridencoder.cu:98-122).  `row` = the sample's row base inside the X tile, r7 = row index & 7 (SWIZZLE_128B chunk permutation).
+__device__ __forceinline__ void gather_finish(const GatherTrip &G, uint32_t ok, uint8_t *row, uint32_t r7, uint32_t k) {
+    float f[2][3];
+#pragma unroll
+    for (uint32_t q = 0; q < 2; q++) {
+        const float fx = G.fx[q], fy = G.fy[q], fz = G.fz[q];
+        const float gx = __fsub_rn(1.0f, fx), gy = __fsub_rn(1.0f, fy), gz = __fsub_rn(1.0f, fz);
+        f[q][0] = blend4(G.v[q][0], fx, gx, fy, gy);
+        f[q][1] = blend4(G.v[q][1], fy, gy, fz, gz);
+        f[q][2] = blend4(G.v[q][2], fx, gx, fz, gz);
     }
 #pragma unroll
     for (uint32_t p = 0; p < 3; p++) {
-        const uint32_t word = p * 6u + w0;                          // 32-bit word of (level 2k, 2k+1) inside plane p's 6 words
+        const uint32_t word = p * 6u + k;
         *reinterpret_cast<uint32_t *>(row + (((word >> 2) ^ r7) << 4) + (word & 3u) * 4u) = ((ok >> p) & 1u) ? pack2(f[0][p], f[1][p]) : 0u;
     }
 }
@@ -188,9 +193,6 @@ struct HeadSmem {                       // lives after the 1024-aligned weight i
     uint64_t bar_w;                     // weight image landed
     uint64_t bar_mma[HG_WGS];           // per-warpgroup MMA completion
 };
-
-// normalised grid coordinates of a sample + which planes are in range
-struct SampleCoord { float ux, uy, uz; uint32_t ok; };
 
 __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_constant__ HeadArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -255,9 +257,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
     };
     // (x + bound) / (2 bound), fp32, like GridEncoder.forward (grid.py:143); out-of-range coordinates give zero features
     // (gridencoder.cu:98-122) — they are clamped for addressing and masked when stored
-    auto load_coord = [&](uint32_t m, bool live) {
-        float px = 0, py = 0, pz = 0;
-        if (live) { px = __ldcs(a.xyzs + 3 * (size_t)m); py = __ldcs(a.xyzs + 3 * (size_t)m + 1); pz = __ldcs(a.xyzs + 3 * (size_t)m + 2); }
+    auto make_coord = [&](float px, float py, float pz, bool live) {
         float ux, uy, uz;
         if (a.inv_two_bound != 0.0f) {       // 2 * bound is a power of two: the division is an exact scaling
             ux = __fmul_rn(__fadd_rn(px, a.bound), a.inv_two_bound); uy = __fmul_rn(__fadd_rn(py, a.bound), a.inv_two_bound); uz = __fmul_rn(__fadd_rn(pz, a.bound), a.inv_two_bound);
@@ -271,9 +271,6 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         c.ok = live ? ((okx && oky ? 1u : 0u) | (oky && okz ? 2u : 0u) | (okx && okz ? 4u : 0u)) : 0u;
         return c;
     };
-    auto gather_trip = [&](const SampleCoord &c, uint8_t *tile, uint32_t k) {     // levels 2k, 2k+1 of the three planes -> X tile
-        gather_pair(t_xy, t_yz, t_xz, &S.lvl[2 * k], c.ux, c.uy, c.uz, c.ok, tile + row_off, r7, k);
-    };
     auto zero_k_padding = [&](uint8_t *tile) {        // words 18..23 (features 36..47) of the row
         *reinterpret_cast<uint2 *>(tile + row_off + ((4u ^ r7) << 4) + 8u) = make_uint2(0u, 0u);
         *reinterpret_cast<uint4 *>(tile + row_off + ((5u ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
@@ -285,9 +282,19 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
     // ---- pipeline prologue: the first tile's features (later tiles are gathered underneath the previous tile's MMA phases) -------
     if (tile < n_tiles) {
         const uint32_t m0 = tile * HG_TILE + t;
-        const SampleCoord c = load_coord(m0, row_live(m0));
+        const bool live0 = row_live(m0);
+        float px = 0, py = 0, pz = 0;
+        if (live0) { px = __ldcs(a.xyzs + 3 * (size_t)m0); py = __ldcs(a.xyzs + 3 * (size_t)m0 + 1); pz = __ldcs(a.xyzs + 3 * (size_t)m0 + 2); }
+        const SampleCoord c = make_coord(px, py, pz, live0);
+        GatherTrip GA, GB;                  // two trips in flight
+        gather_issue(GA, t_xy, t_yz, t_xz, &S.lvl[0], c);
 #pragma unroll 1
-        for (uint32_t k = 0; k < 6; k++) gather_trip(c, sXb, k);
+        for (uint32_t k = 0; k < 6; k += 2) {
+            gather_issue(GB, t_xy, t_yz, t_xz, &S.lvl[2 * k + 2], c);
+            gather_finish(GA, c.ok, sXb + row_off, r7, k);
+            if (k + 2 < 6) gather_issue(GA, t_xy, t_yz, t_xz, &S.lvl[2 * k + 4], c);
+            gather_finish(GB, c.ok, sXb + row_off, r7, k + 1);
+        }
         zero_k_padding(sXb);
     }
     for (; tile < n_tiles; tile += tile_stride) {
@@ -298,12 +305,20 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         float dxv = 0, dyv = 0, dzv = 1;
         if (live) { dxv = __ldcs(a.dirs + 3 * (size_t)m); dyv = __ldcs(a.dirs + 3 * (size_t)m + 1); dzv = __ldcs(a.dirs + 3 * (size_t)m + 2); }
         const bool has_next = tile + tile_stride < n_tiles;                  // uniform over the warpgroup
-        SampleCoord cn = {0.0f, 0.0f, 0.0f, 0u};
-        if (has_next) { const uint32_t mn = (tile + tile_stride) * HG_TILE + t; cn = load_coord(mn, row_live(mn)); }
+        float npx = 0, npy = 0, npz = 0;
+        bool nlive = false;
+        if (has_next) {
+            const uint32_t mn = (tile + tile_stride) * HG_TILE + t;
+            nlive = row_live(mn);
+            if (nlive) { npx = __ldcs(a.xyzs + 3 * (size_t)mn); npy = __ldcs(a.xyzs + 3 * (size_t)mn + 1); npz = __ldcs(a.xyzs + 3 * (size_t)mn + 2); }
+        }
+        uint8_t *rown = sXn + row_off;
+        GatherTrip G;
         publish();
         // ---- P1: [aud hidden | eye hidden | sigma hidden (enc_x part)] = X * WA -------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sX_a, sW_a + HW_A, 3, 144, false); mma_commit(bar); }
-        if (has_next) gather_trip(cn, sXn, 0);
+        const SampleCoord cn = make_coord(npx, npy, npz, nlive);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[0], cn);
         mma_done();
         float eye_att, unc_out = 0.6931471805599453f;       // testing: log(1 + e^0) (network.py:245,278)
         {
@@ -316,6 +331,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             // sigmoid evaluated on the fp16 logit, result rounded to fp16 (torch.sigmoid on a half tensor)
             eye_att = round_h(1.0f / (1.0f + expf(-round_h(dot))));
         }
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 0);
         publish();
         // ---- P2: att = H * WB ; [unc hidden = X * WU] --------------------------------------------------------------------------
         if (t == 0) {
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             if (a.has_unc) issue_mma(tmem_wg + TC_A + 32, sX_a, sW_a + HW_U, 3, 32, false);
             mma_commit(bar);
         }
-        if (has_next) gather_trip(cn, sXn, 1);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[2], cn);
         mma_done();
         float amb_aud;
         {
@@ -354,22 +370,25 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 4)) = make_uint4(pack2(e, 0.0f), 0u, 0u, 0u);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 5)) = make_uint4(0u, 0u, 0u, 0u);
         }
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 1);
         publish();
         // ---- P3: sigma hidden += [enc_w, e] * WC -------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
-        if (has_next) gather_trip(cn, sXn, 2);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[4], cn);
         mma_done();
         hidden_epilogue<true, false>(tmem_ld + TC_S, sH, t, nullptr);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 2);
         publish();
         // ---- P4: sigma layer 1 --------------------------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
-        if (has_next) gather_trip(cn, sXn, 3);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[6], cn);
         mma_done();
         hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 3);
         publish();
         // ---- P5: sigma layer 2: cols 0..63 = geo_feat, col 64 = density logit (rows rotated at pack time) -----------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
-        if (has_next) gather_trip(cn, sXn, 4);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[8], cn);
         mma_done();
         float sigma;
         {
@@ -386,6 +405,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 1)) = make_uint4(w[4], w[5], w[6], w[7]);
         }
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 4);
         publish();
         // ---- P6: color layer 0 = geo * WF0 + sh * WF1 (+ ind-code bias in the epilogue) -------------------------------------
         if (t == 0) {
@@ -394,9 +414,10 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_F1, 1, 64, true);
             mma_commit(bar);
         }
-        if (has_next) gather_trip(cn, sXn, 5);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[10], cn);
         mma_done();
         hidden_epilogue<true, true>(tmem_ld + TC_S, sH, t, S.ind_bias);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 5);
         publish();
         // ---- P7: color layer 1 (N padded 3 -> 16) -----------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_G, 4, 16, false); mma_commit(bar); }

@@ -58,16 +58,22 @@ def test_train_step_gradients_match_cpu_port_fp32():
     cpu_loss = mse + 1e-3 * ent + 1e-4 * (s_a.mean() + s_e.mean())
     cpu_loss.backward()
     assert abs(float(loss) - float(cpu_loss)) < 2e-4 * max(1.0, abs(float(cpu_loss))), (float(loss), float(cpu_loss))
-    worst = {}
+    worst, mean_rel = {}, {}
     for name, q in m.named_parameters():
         g_gpu = q.grad.detach().cpu()
         g_cpu = P[name].grad if P[name].grad is not None else torch.zeros_like(P[name])
         denom = float(g_cpu.abs().max()) + 1e-12
         worst[name] = float((g_gpu - g_cpu).abs().max()) / denom
-    # fp32 on both sides; differences: fma vs separate ops in the interpolation weights, ex2.approx, atomics order -> 2e-3 of the max gradient
-    # audio-net gradients flow through enc_a = a sum over ~10^4 samples of signed terms that largely cancel: looser bound
-    bad = {k: v for k, v in worst.items() if v > (3e-2 if k.startswith("audio") else 3e-3)}
+        mean_rel[name] = float((g_gpu - g_cpu).abs().sum()) / (float(g_cpu.abs().sum()) + 1e-12)
+    # fp32 on both sides; differences: fma vs separate ops in the interpolation weights, ex2.approx, atomics order -> 3e-3 of the max gradient.
+    # Looser bounds where the gradient is a sum of ~10^4 signed per-sample terms that largely cancel, so the fp32 noise floor of the
+    # terms (~1e-8 absolute here) is a larger fraction of the result: the audio nets (through enc_a) and the tables (max |g| ~ 2e-6:
+    # a handful of entries sit at 6e-3..1e-2 of the max while the aggregate error stays below 1e-3, checked separately).
+    tol = lambda k: 3e-2 if k.startswith("audio") else (2e-2 if k.endswith("embeddings") else 3e-3)
+    bad = {k: v for k, v in worst.items() if v > tol(k)}
     assert not bad, bad
+    bad_mean = {k: v for k, v in mean_rel.items() if k.endswith("embeddings") and v > 1e-3}
+    assert not bad_mean, bad_mean
     assert float(m.encoder_xy.embeddings.grad.abs().sum()) > 0 and float(m.sigma_net.net[0].weight.grad.abs().sum()) > 0
 
 
