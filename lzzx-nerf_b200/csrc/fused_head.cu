@@ -174,10 +174,13 @@ __device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {
     o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
 
-__device__ __noinline__ void issue_mma(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr, uint32_t ksteps, uint32_t N, bool accumulate) {
+// One layer = `ksteps` K=16 MMAs into the same accumulator.  A K step advances both K-major SWIZZLE_128B operands by 32 bytes, i.e. +2 in the
+// descriptors' start-address field (the operands are < 256 KB into shared memory, so the field never carries).
+__device__ __forceinline__ void issue_mma(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr, uint32_t ksteps, uint32_t N, bool accumulate) {
     const uint32_t idesc = idesc_f16(128, N);
-    for (uint32_t k = 0; k < ksteps; k++)
-        mma_f16_ss(d_tmem, smem_desc_sw128(a_saddr + k * 32u), smem_desc_sw128(b_saddr + k * 32u), idesc, accumulate || k > 0);
+    uint64_t da = smem_desc_sw128(a_saddr), db = smem_desc_sw128(b_saddr);
+#pragma unroll 1
+    for (uint32_t k = 0; k < ksteps; k++, da += 2, db += 2) mma_f16_ss(d_tmem, da, db, idesc, accumulate || k > 0);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -317,8 +320,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         publish();
         // ---- P1: [aud hidden | eye hidden | sigma hidden (enc_x part)] = X * WA -------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sX_a, sW_a + HW_A, 3, 144, false); mma_commit(bar); }
-        const SampleCoord cn = make_coord(npx, npy, npz, nlive);
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[0], cn);
+        if (has_next) zero_k_padding(sXn);
         mma_done();
         float eye_att, unc_out = 0.6931471805599453f;       // testing: log(1 + e^0) (network.py:245,278)
         {
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             // sigmoid evaluated on the fp16 logit, result rounded to fp16 (torch.sigmoid on a half tensor)
             eye_att = round_h(1.0f / (1.0f + expf(-round_h(dot))));
         }
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 0);
+        const SampleCoord cn = make_coord(npx, npy, npz, nlive);         // the coordinate loads had all of P1 to land
         publish();
         // ---- P2: att = H * WB ; [unc hidden = X * WU] --------------------------------------------------------------------------
         if (t == 0) {
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             if (a.has_unc) issue_mma(tmem_wg + TC_A + 32, sX_a, sW_a + HW_U, 3, 32, false);
             mma_commit(bar);
         }
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[2], cn);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[0], cn);
         mma_done();
         float amb_aud;
         {
@@ -370,25 +372,25 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 4)) = make_uint4(pack2(e, 0.0f), 0u, 0u, 0u);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 5)) = make_uint4(0u, 0u, 0u, 0u);
         }
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 1);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 0);
         publish();
         // ---- P3: sigma hidden += [enc_w, e] * WC -------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[4], cn);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[2], cn);
         mma_done();
         hidden_epilogue<true, false>(tmem_ld + TC_S, sH, t, nullptr);
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 2);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 1);
         publish();
         // ---- P4: sigma layer 1 --------------------------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[6], cn);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[4], cn);
         mma_done();
         hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr);
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 3);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 2);
         publish();
         // ---- P5: sigma layer 2: cols 0..63 = geo_feat, col 64 = density logit (rows rotated at pack time) -----------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[8], cn);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[6], cn);
         mma_done();
         float sigma;
         {
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 1)) = make_uint4(w[4], w[5], w[6], w[7]);
         }
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 4);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 3);
         publish();
         // ---- P6: color layer 0 = geo * WF0 + sh * WF1 (+ ind-code bias in the epilogue) -------------------------------------
         if (t == 0) {
@@ -414,14 +416,14 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_F1, 1, 64, true);
             mma_commit(bar);
         }
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[10], cn);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[8], cn);
         mma_done();
         hidden_epilogue<true, true>(tmem_ld + TC_S, sH, t, S.ind_bias);
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 5);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 4);
         publish();
         // ---- P7: color layer 1 (N padded 3 -> 16) -----------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_G, 4, 16, false); mma_commit(bar); }
-        if (has_next) zero_k_padding(sXn);
+        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[10], cn);
         mma_done();
         {
             uint32_t c16[16];
@@ -441,6 +443,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
                 if (a.unc) __stcs(a.unc + m, unc_out);
             }
         }
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 5);
         buf ^= 1u;
         // the next tile's publish() orders this tile's TMEM reads (fence::before_thread_sync + warpgroup barrier) before its first MMA
     }
