@@ -197,7 +197,7 @@ def head_kernel_profile(model, renderer, frames, auds, n_frames, repeats=5):
     return total_ms, launches, samples
 
 
-def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536):
+def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536, eager=False):
     """BASELINE configs[2]/[4]: data-parallel training step, 65 536 rays per GPU, synthetic audio window (AudioNet + AudioAttNet), grid backward,
     AdamW; gradients all-reduced once per step over the flat buffer when world > 1.  Returns a dict (rays/s over all ranks)."""
     from b2nerf import scene
@@ -216,12 +216,16 @@ def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536
         tr.train_step(b[0], b[1], b[2], b[3], index=s)
         if s == 15:
             tr.update_mean_count()            # the reference's warm-up: 16 steps with worst-case buffers, then the mean_count estimate
+    step_fn = tr.train_step if eager else tr.train_step_graphed
+    for s in range(4):                    # graph capture (if any) + steady state
+        b = batches[s % 4]
+        step_fn(b[0], b[1], b[2], b[3], index=s)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(steps):
         b = batches[s % 4]
-        loss, m_buf = tr.train_step(b[0], b[1], b[2], b[3], index=s)
+        loss, m_buf = step_fn(b[0], b[1], b[2], b[3], index=s)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -232,7 +236,8 @@ def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536
         ms = float(t.item())
     return {"metric": "train_rays_per_sec", "value": world * steps * n_rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": n_rays,
             "samples_per_step_buffer": int(m_buf), "loss": float(loss), "grad_allreduce_bytes": tr.grads.nbytes() if world > 1 else 0,
-            "path": "drop-in ops + torch autograd (MLPs via cuBLAS under autocast fp16), AdamW, flat-buffer NCCL all-reduce"}
+            "path": ("eager: " if eager else "forward + backward + all-reduce replayed from one CUDA graph: ") +
+                    "drop-in ops + torch autograd (MLPs via cuBLAS under autocast fp16), fused AdamW, flat-buffer NCCL all-reduce"}
 
 
 def run_gpu_arm(args, rank, world, local_rank):
@@ -292,7 +297,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     e2e_ms, _ = timed(lambda s: pipe.submit_host(host_o[s % POOL], host_d[s % POOL], host_a[s % POOL], out_hosts[s % pipe.depth]), args.steps, args.warmup)
     train_info = None
     if not args.no_train:
-        train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(4, min(args.steps, 20)), warmup=max(args.warmup, 18))
+        train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(4, min(args.steps, 20)), warmup=max(args.warmup, 18), eager=args.train_eager)
     if rank != 0:
         return
     img = out_host.numpy()
@@ -348,6 +353,7 @@ def main():
     ap.add_argument("--in-flight", type=int, default=4, help="frames in flight per GPU (independent frames on separate streams; 1 = strictly one after another)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
+    ap.add_argument("--train-eager", action="store_true", help="training leg without the CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2nerf" else args.warmup
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

@@ -15,6 +15,8 @@
 //   * backward: the same pair detection turns two scalar REDs into one `red.global.add.v2.f32` (sm_90+ vector
 //     reduction) — the scatter is bound by the SM's RED issue rate, so halving the instruction count is the lever.
 #include "common.cuh"
+#include <mutex>
+#include <cstdlib>
 
 namespace b2n {
 
@@ -262,6 +264,118 @@ __global__ void __launch_bounds__(256) k_grid_bwd(const T *__restrict__ grad, co
     }
 }
 
+// Table backward with the level's gradient table PRIVATISED IN SHARED MEMORY (fp32 tables whose largest level fits, e.g. the 64 KB levels of
+// the tri-plane grids).  The direct scatter above is bound by the L2's reduction rate (~50 fp32 reductions per clock for the whole chip, less
+// when a training batch concentrates on the few thousand cells of the coarse levels: measured 46 G red/s); here CTA (slice, level) accumulates
+// its slice of the batch into a zeroed shared-memory copy of ONE level with shared-memory atomics (hundreds of lane-ops per clock chip-wide),
+// then flushes the non-zero quads with `red.global.add.v4.f32`, so the L2 sees (#slices x level size / 4) vector reductions instead of
+// 2^D x B scalar ones.  Sums are reassociated (as with any atomic scatter); same products as the direct kernel.
+constexpr uint32_t GP_THREADS = 512;
+
+__device__ __forceinline__ void red_add_v4_f32(float *addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(GP_THREADS) k_grid_bwd_priv(const float *__restrict__ grad, const float *__restrict__ inputs, const int32_t *__restrict__ offsets,
+                                                               float *__restrict__ grad_table, uint32_t B, uint32_t S_slices, float S, uint32_t H,
+                                                               uint32_t gridtype, bool align_corners, uint32_t smem_floats) {
+    extern __shared__ __align__(16) float s_tab[];
+    const uint32_t level = blockIdx.y;
+    const LevelGeom g = level_geom(offsets, level, S, H);
+    float *gtab = grad_table + (size_t)g.table_off * C;
+    const uint32_t n = g.hashmap_size * C;
+    const bool priv = n <= smem_floats;                 // a level larger than the launch's shared memory scatters straight to global memory
+    float *acc = priv ? s_tab : gtab;
+    if (priv) {
+        for (uint32_t i = threadIdx.x; i < n; i += GP_THREADS) s_tab[i] = 0.0f;
+        __syncthreads();
+    }
+    const uint32_t per = (B + S_slices - 1) / S_slices;
+    const uint32_t b0 = blockIdx.x * per, b1 = min(B, b0 + per);
+#pragma unroll 2
+    for (uint32_t b = b0 + threadIdx.x; b < b1; b += GP_THREADS) {
+        float in[D];
+        bool oob = false;
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) { in[d] = __ldcs(inputs + (size_t)b * D + d); oob |= (in[d] < 0.0f || in[d] > 1.0f); }
+        if (oob) continue;
+        float pos[D];
+        uint32_t pg[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) {
+            pos[d] = __fmaf_rn(in[d], g.scale, align_corners ? 0.0f : 0.5f);
+            pg[d] = (uint32_t)floorf(pos[d]);
+            pos[d] = __fsub_rn(pos[d], (float)pg[d]);
+        }
+        float gc[C];
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) gc[c] = __ldcs(grad + ((size_t)level * B + b) * C + c);
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); idx++) {
+            float w = 1.0f;
+            uint32_t pl[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; d++) {
+                if ((idx & (1u << d)) == 0) { w = __fmul_rn(w, __fsub_rn(1.0f, pos[d])); pl[d] = pg[d]; }
+                else                        { w = __fmul_rn(w, pos[d]);                 pl[d] = pg[d] + 1; }
+            }
+            const uint32_t e = grid_slot<D>(gridtype, align_corners, g.hashmap_size, g.resolution, pl) * C;
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) atomicAdd(acc + e + c, __fmul_rn(w, gc[c]));
+        }
+    }
+    if (!priv) return;
+    __syncthreads();
+    if (((g.table_off * C) & 3u) == 0 && (n & 3u) == 0) {        // 16-byte aligned level (offsets are multiples of 8 entries, grid.py:117)
+        for (uint32_t i = threadIdx.x; i < n / 4; i += GP_THREADS) {
+            const float4 v = reinterpret_cast<const float4 *>(s_tab)[i];
+            if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) red_add_v4_f32(gtab + 4 * (size_t)i, v);
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < n; i += GP_THREADS) { const float v = s_tab[i]; if (v != 0.0f) red_add_f32(gtab + i, v); }
+    }
+}
+
+// largest level (entries) of the grid described by a device `offsets` array — read back ONCE per (pointer, L) and cached; 0 = unknown (the
+// stream is being captured and the geometry has not been seen yet).  The value only sizes the privatised kernel's shared memory: the kernel
+// re-checks every level against it, so a stale entry costs speed, never correctness.
+static uint32_t largest_level_entries(const int32_t *offsets, uint32_t L, cudaStream_t st) {
+    struct Entry { const int32_t *p; uint32_t L, dev, max_entries; };
+    static Entry cache[16];
+    static uint32_t n_cache = 0;
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    for (uint32_t i = 0; i < n_cache; i++) if (cache[i].p == offsets && cache[i].L == L && cache[i].dev == (uint32_t)dev) return cache[i].max_entries;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone || L > 64) { (void)cudaGetLastError(); return 0; }
+    int32_t h[65];
+    if (cudaMemcpyAsync(h, offsets, sizeof(int32_t) * (L + 1), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    uint32_t mx = 0;
+    for (uint32_t l = 0; l < L; l++) { const uint32_t sz = (uint32_t)(h[l + 1] - h[l]); if (h[l + 1] > h[l] && sz > mx) mx = sz; }
+    Entry &e = cache[n_cache < 16 ? n_cache++ : 15];
+    e.p = offsets; e.L = L; e.dev = (uint32_t)dev; e.max_entries = mx;
+    return mx;
+}
+
+template <uint32_t D, uint32_t C>
+static int launch_bwd_priv(const float *grad, const float *inputs, const int32_t *offsets, float *gtab, uint32_t B, uint32_t L, float S, uint32_t H,
+                           uint32_t gridtype, bool ac, uint32_t smem_floats, cudaStream_t st) {
+    static size_t smem_set = 0;
+    const size_t smem = sizeof(float) * (size_t)smem_floats;
+    auto kern = k_grid_bwd_priv<D, C>;
+    if (smem > 48 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    uint32_t slices = 2u * (uint32_t)sm_count() / L;          // two 512-thread CTAs per SM
+    if (const char *e = getenv("B2N_GRID_BWD_SLICES")) slices = (uint32_t)atoi(e);
+    const uint32_t cap = ceil_div<uint32_t>(B, 2048);           // at least two rounds of the CTA per slice
+    if (slices > cap) slices = cap;
+    if (slices < 1) slices = 1;
+    kern<<<dim3(slices, L, 1), GP_THREADS, smem, st>>>(grad, inputs, offsets, gtab, B, slices, S, H, gridtype, ac, smem_floats);
+    return check_launch("grid_encode_backward");
+}
+
 // input gradient: grad_inputs[b,d] = sum_l sum_c grad[l,b,c] * dy_dx[b,l,d,c]   (:317-342)
 template <typename T>
 __global__ void __launch_bounds__(256) k_grid_input_bwd(const T *__restrict__ grad, const T *__restrict__ dy_dx, T *__restrict__ grad_inputs,
@@ -321,9 +435,26 @@ static int bwd_dispatch_c(const T *grad, const float *inputs, const int32_t *off
     }
     return check_launch("grid_encode_backward");
 }
+// fp32 tables, batches large enough to amortise zero + flush, largest level <= 160 KB: privatised kernel
+static bool bwd_privatised(const float *grad, const float *inputs, const int32_t *offsets, float *gtab, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                           uint32_t H, uint32_t gridtype, bool ac, cudaStream_t st, int &rc) {
+    if (B < 16384 || L > 64 || getenv("B2N_GRID_BWD_DIRECT")) return false;
+    const uint32_t mx = largest_level_entries(offsets, L, st);
+    if (mx == 0 || (size_t)mx * C * sizeof(float) > 160 * 1024) return false;
+    const uint32_t fl = mx * C;
+#define B2N_PRIV(DD, CC) if (D == DD && C == CC) { rc = launch_bwd_priv<DD, CC>(grad, inputs, offsets, gtab, B, L, S, H, gridtype, ac, fl, st); return true; }
+    B2N_PRIV(2, 1) B2N_PRIV(2, 2) B2N_PRIV(2, 4) B2N_PRIV(3, 1) B2N_PRIV(3, 2) B2N_PRIV(3, 4)
+#undef B2N_PRIV
+    return false;
+}
+
 template <typename T>
 static int bwd_dispatch(const T *grad, const float *inputs, const int32_t *offsets, T *gtab, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
                         uint32_t H, uint32_t gridtype, bool ac, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        int rc = 0;
+        if (bwd_privatised((const float *)grad, inputs, offsets, (float *)gtab, B, D, C, L, S, H, gridtype, ac, st, rc)) return rc;
+    }
     switch (D) {
         case 1: return bwd_dispatch_c<T, 1>(grad, inputs, offsets, gtab, B, C, L, S, H, gridtype, ac, st);
         case 2: return bwd_dispatch_c<T, 2>(grad, inputs, offsets, gtab, B, C, L, S, H, gridtype, ac, st);
