@@ -358,6 +358,44 @@ def test_grid_encode(ref, name):
     assert torch.equal(r_gin, gin)
 
 
+@pytest.mark.parametrize("name,B", [("triplane", 40000), ("hash3d", 30000), ("tiled_ac", 20000)])
+def test_grid_backward_privatised_path(name, B, monkeypatch):
+    """Batches >= 16 384 points take the shared-memory privatised table backward (gridenc.cu:k_grid_bwd_priv): same sums as the direct
+    red.global scatter and as the double-accumulated oracle, up to fp32 reassociation; samples are clustered like a training batch
+    (many points per coarse cell) and include out-of-range rows."""
+    from gridencoder.backend import _backend
+    from gridencoder.grid import level_table
+    D, L, C, H, log2T, desired, gridtype, ac, _, half = cases.GRID_CASES[name]
+    assert not half
+    pls = np.exp2(np.log2(desired / H) / (L - 1))
+    offsets = np.array(level_table(D, L, pls, H, log2T, ac), np.int32)
+    rng = np.random.default_rng(99)
+    x = (0.5 + 0.12 * rng.standard_normal((B, D))).astype(np.float32)          # concentrated around the centre; a few rows fall outside [0,1]
+    x[:8] = rng.random((8, D)) * 3 - 1
+    grad = rng.standard_normal((L, B, C)).astype(np.float32)
+    S = float(np.log2(pls))
+    xs, gs, offs = T(x), T(grad), T(offsets)
+    emb = torch.zeros(int(offsets[-1]), C, device="cuda")
+    g_priv, g_direct = torch.zeros_like(emb), torch.zeros_like(emb)
+    _backend.grid_encode_backward(gs, xs, emb, offs, g_priv, B, D, C, L, S, H, None, None, gridtype, ac)
+    monkeypatch.setenv("B2N_GRID_BWD_DIRECT", "1")
+    _backend.grid_encode_backward(gs, xs, emb, offs, g_direct, B, D, C, L, S, H, None, None, gridtype, ac)
+    monkeypatch.delenv("B2N_GRID_BWD_DIRECT")
+    scale = float(g_direct.abs().max())
+    assert scale > 1.0
+    np.testing.assert_allclose(npy(g_priv), npy(g_direct), rtol=0, atol=2e-5 * scale)
+    from gridencoder.backend import grid_level_scales
+    oracle.set_level_scales(npy(grid_level_scales(S, H, L)))
+    try:
+        o_ge, _ = oracle.grid_encode_backward(grad, x, offsets, C, S, H, gridtype, ac, None)
+    finally:
+        oracle.set_level_scales(None)
+    np.testing.assert_allclose(npy(g_priv), o_ge, rtol=0, atol=2e-5 * scale)
+    # accumulation semantics: a second call adds on top (the reference's kernel does atomicAdd into the caller's buffer)
+    _backend.grid_encode_backward(gs, xs, emb, offs, g_priv, B, D, C, L, S, H, None, None, gridtype, ac)
+    np.testing.assert_allclose(npy(g_priv), 2 * o_ge, rtol=0, atol=6e-5 * scale)
+
+
 def test_grid_encoder_module_triplane_autograd():
     """The nn.Module surface on the tri-plane config (network.py:129-133): shapes, state_dict names, grads flow to embeddings."""
     from gridencoder import GridEncoder

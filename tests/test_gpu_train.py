@@ -117,7 +117,7 @@ def test_graphed_step_matches_eager_step():
             ls.append(float(loss))
         losses.append(ls)
         if graphed:
-            assert len(tr._graphs) == 1 and m_buf % Trainer.M_BUCKET == 0
+            assert len(tr._graphs) == 1 and m_buf >= -(-tr.mean_count // Trainer.M_BUCKET) * Trainer.M_BUCKET
     eager, graphed = np.array(losses[0]), np.array(losses[1])
     # same arithmetic; the sample buffer is rounded up to M_BUCKET in graph mode (never truncates more rays than the eager step) and the
     # atomic scatter order differs -> tiny drift that grows over the steps
