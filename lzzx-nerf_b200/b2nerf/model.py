@@ -25,6 +25,35 @@ from shencoder import SHEncoder
 from ._lib import lib
 
 
+class _TallLinear(torch.autograd.Function):
+    """y = x W^T for tall activations (M = 10^5..10^6 samples, fan-in / fan-out <= 128) — the shape of every head-MLP layer in a training step.
+    Forward and input gradient are plain GEMMs; the WEIGHT gradient dY^T X reduces over M, and the library heuristic runs it as one wave of
+    4-6 CTAs (171 us per layer in the step profile, profiles/r1_train_step.md).  Here the reduction is split into S independent slabs (one
+    batched GEMM over [S, out, M/S] x [S, M/S, in]) whose partials are summed in fp32.  Numerics: autocast semantics (fp16 operands, fp32
+    accumulation), the partials are rounded to the operand dtype before the fp32 sum."""
+
+    SLABS = 64
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float16)
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return x @ w.t()
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dy @ w if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            S, M = _TallLinear.SLABS, x.shape[0]
+            part = torch.bmm(dy.view(S, M // S, -1).transpose(1, 2), x.view(S, M // S, -1))       # [S, out, in]
+            dw = part.float().sum(0).to(w.dtype)
+        return dx, dw
+
+
 class MLP(nn.Module):
     """Bias-free ReLU MLP (network.py:73-94)."""
 
@@ -35,8 +64,10 @@ class MLP(nn.Module):
         self.net = nn.ModuleList(nn.Linear(dims[i], dims[i + 1], bias=False) for i in range(num_layers))
 
     def forward(self, x):
+        tall = (x.is_cuda and x.dim() == 2 and x.shape[0] >= 16384 and x.shape[0] % _TallLinear.SLABS == 0 and torch.is_grad_enabled()
+                and any(l.weight.requires_grad for l in self.net))
         for i, layer in enumerate(self.net):
-            x = layer(x)
+            x = _TallLinear.apply(x.contiguous(), layer.weight) if tall else layer(x)
             if i != self.num_layers - 1:
                 x = F.relu(x, inplace=True)
         return x

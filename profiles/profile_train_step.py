@@ -25,15 +25,24 @@ for s in range(20):
     if s == 15: tr.update_mean_count()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+step = tr.train_step if "--eager" in sys.argv else tr.train_step_graphed
+for s in range(4):
+    b = batches[s % 4]; step(*b, index=s)
+torch.cuda.synchronize()
 e0.record()
 for s in range(10):
-    b = batches[s % 4]; tr.train_step(*b, index=s)
+    b = batches[s % 4]; step(*b, index=s)
 e1.record(); torch.cuda.synchronize()
 print("ms/step (events, 10 steps):", e0.elapsed_time(e1) / 10)
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for s in range(5):
-        b = batches[s % 4]; tr.train_step(*b, index=s)
+        b = batches[s % 4]; step(*b, index=s)
     torch.cuda.synchronize()
 ka = prof.key_averages()
 tot = sum(k.device_time_total for k in ka if k.device_type == torch.autograd.DeviceType.CUDA) if False else None
-print(ka.table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+rows = [(k.key, k.self_device_time_total / 5, k.count // 5) for k in ka if k.self_device_time_total > 0]
+rows.sort(key=lambda r: -r[1])
+tot = sum(r[1] for r in rows)
+print(f"device time per step: {tot:.1f} us in {sum(r[2] for r in rows)} kernels")
+for name, us, cnt in rows[:60]:
+    print(f"{us:9.1f} us {100 * us / tot:5.1f}%  x{cnt:<4d} {name[:150]}")
