@@ -90,6 +90,11 @@ void b2n_frame_graph_destroy(b2n_frame_graph *fg);
 /* number of loop iterations executed by the last frame rendered into `workspace` (4-byte read-back; synchronises `stream`) */
 int b2n_frame_iterations(const void *workspace, uint32_t N, int32_t *iterations, void *stream);
 
+/* Weight gradient of a bias-free Linear over a tall activation matrix:  dw[out,in] += dy[M,out]^T x[M,in]  (fp16 operands, row-major,
+ * fp32 accumulation; dw is accumulated into, zero it first).  1 <= out, in <= 128.  Replaces the weight-gradient GEMM that autograd's
+ * LinearBackward runs for every MLP layer of nerf_triplane/network.py:73-94 in a training step (csrc/wgrad.cu). */
+int b2n_linear_wgrad(const void *dy_f16, const void *x_f16, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,9 +28,9 @@ from ._lib import lib
 class _TallLinear(torch.autograd.Function):
     """y = x W^T for tall activations (M = 10^5..10^6 samples, fan-in / fan-out <= 128) — the shape of every head-MLP layer in a training step.
     Forward and input gradient are plain GEMMs; the WEIGHT gradient dY^T X reduces over M, and the library heuristic runs it as one wave of
-    4-6 CTAs (171 us per layer in the step profile, profiles/r1_train_step.md).  Here the reduction is split into S independent slabs (one
-    batched GEMM over [S, out, M/S] x [S, M/S, in]) whose partials are summed in fp32.  Numerics: autocast semantics (fp16 operands, fp32
-    accumulation), the partials are rounded to the operand dtype before the fp32 sum."""
+    4-6 CTAs (170-300 us per layer in the step profile, profiles/r1_train_step.md).  Under autocast (fp16 operands) it is computed by
+    b2n_linear_wgrad (csrc/wgrad.cu: one pass over both activations, fp32 accumulation in tensor memory); in fp32 mode the reduction is
+    split into S slabs with a batched GEMM and the partials are summed."""
 
     SLABS = 64
 
@@ -48,9 +48,16 @@ class _TallLinear(torch.autograd.Function):
         dx = dy @ w if ctx.needs_input_grad[0] else None
         dw = None
         if ctx.needs_input_grad[1]:
-            S, M = _TallLinear.SLABS, x.shape[0]
-            part = torch.bmm(dy.view(S, M // S, -1).transpose(1, 2), x.view(S, M // S, -1))       # [S, out, in]
-            dw = part.float().sum(0).to(w.dtype)
+            M, n_out, n_in = x.shape[0], w.shape[0], w.shape[1]
+            if x.dtype == torch.float16 and dy.dtype == torch.float16 and n_out <= 128 and n_in <= 128:
+                # hand-written kernel (csrc/wgrad.cu): both operands streamed once as MN-major tcgen05 operands, fp32 accumulation in TMEM
+                acc = torch.zeros(n_out, n_in, dtype=torch.float32, device=x.device)
+                lib().call("b2n_linear_wgrad", dy.data_ptr(), x.data_ptr(), M, n_out, n_in, acc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                dw = acc.to(w.dtype)
+            else:
+                S = _TallLinear.SLABS
+                part = torch.bmm(dy.view(S, M // S, -1).transpose(1, 2), x.view(S, M // S, -1))       # [S, out, in]
+                dw = part.float().sum(0).to(w.dtype)
         return dx, dw
 
 

@@ -1,0 +1,145 @@
+// wgrad.cu — weight gradient of a bias-free Linear over a tall activation matrix:  dW[out,in] += dY[M,out]^T · X[M,in]
+// (fp16 operands, fp32 accumulation), M = 10^5..10^6 samples, out / in <= 128 — the shape of every head-MLP layer in a training step
+// (nerf_triplane/network.py:73-94 through autograd's LinearBackward).
+//
+// The reduction runs over the SAMPLE dimension, which is the slow (row) dimension of both operands in memory, so both are "MN-major"
+// tensor-core operands: a 128-sample chunk of dY / X is copied row by row into shared memory in the canonical SWIZZLE_128B MN-major layout
+// (128-byte rows of 64 features for one sample, 8-sample groups of 1024 B, 64-feature column blocks 16 KB apart) and fed to tcgen05.mma
+// with a_major = b_major = MN — no transposition anywhere.  One CTA per SM walks its share of the chunks with two operand buffers (the
+// loads of chunk c+1 overlap the MMAs of chunk c), accumulates the whole out x in product in TMEM (M = 128 lanes, N = in columns) and
+// adds it once to the fp32 result with red.global — so the library's one-wave split (4-6 CTAs, 170-300 us per layer measured) becomes an
+// HBM-bound stream over the activations.
+#include "common.cuh"
+#include "tc5.cuh"
+
+namespace b2n {
+using namespace tc5;
+
+constexpr uint32_t WG_THREADS = 256;
+constexpr uint32_t WG_CHUNK = 128;                       // samples per chunk = 8 MMA K-steps
+constexpr uint32_t WG_BLOCK_BYTES = WG_CHUNK * 128;      // one 64-feature column block of a chunk: 128 sample rows x 128 B
+constexpr uint32_t WG_OPERAND_BYTES = 2 * WG_BLOCK_BYTES;   // up to 128 features
+constexpr uint32_t WG_SMEM = 4 * WG_OPERAND_BYTES + 1024 + 64;
+
+// MN-major SWIZZLE_128B descriptor: LBO = distance between 64-element column blocks, SBO = distance between 8-row (K) groups
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(WG_BLOCK_BYTES >> 4) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// byte offset of element (sample k, feature j) inside an operand buffer
+__device__ __forceinline__ uint32_t mn_offset(uint32_t k, uint32_t j) {
+    return (j >> 6) * WG_BLOCK_BYTES + (k >> 3) * 1024u + (k & 7u) * 128u + ((((j & 63u) >> 3) ^ (k & 7u)) << 4) + (j & 7u) * 2u;
+}
+
+// copy rows [row0, row0+128) of a row-major fp16 matrix [M, width] into an operand buffer; V = halves per access (V | width, pointer 2V-aligned)
+template <uint32_t V>
+__device__ __forceinline__ void load_chunk(uint8_t *buf, const __half *__restrict__ src, uint32_t row0, uint32_t M, uint32_t width) {
+    const uint32_t nv = width / V, total = WG_CHUNK * nv;
+    for (uint32_t idx = threadIdx.x; idx < total; idx += WG_THREADS) {
+        const uint32_t k = idx / nv, j = (idx - k * nv) * V;
+        const uint32_t row = row0 + k;
+        uint8_t *dst = buf + mn_offset(k, j);
+        const __half *p = src + (size_t)row * width + j;
+        if (V == 8) *reinterpret_cast<uint4 *>(dst) = row < M ? __ldcs(reinterpret_cast<const uint4 *>(p)) : make_uint4(0, 0, 0, 0);
+        else if (V == 4) *reinterpret_cast<uint2 *>(dst) = row < M ? __ldcs(reinterpret_cast<const uint2 *>(p)) : make_uint2(0, 0);
+        else if (V == 2) *reinterpret_cast<uint32_t *>(dst) = row < M ? __ldcs(reinterpret_cast<const uint32_t *>(p)) : 0u;
+        else *reinterpret_cast<uint16_t *>(dst) = row < M ? __ldcs(reinterpret_cast<const uint16_t *>(p)) : (uint16_t)0;
+    }
+}
+__device__ __forceinline__ void load_chunk_any(uint32_t v, uint8_t *buf, const __half *src, uint32_t row0, uint32_t M, uint32_t width) {
+    if (v == 8) load_chunk<8>(buf, src, row0, M, width);
+    else if (v == 4) load_chunk<4>(buf, src, row0, M, width);
+    else if (v == 2) load_chunk<2>(buf, src, row0, M, width);
+    else load_chunk<1>(buf, src, row0, M, width);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) k_linear_wgrad(const __half *__restrict__ dy, const __half *__restrict__ x, uint32_t M, uint32_t out_dim,
+                                                                 uint32_t in_dim, uint32_t va, uint32_t vb, float *__restrict__ dw) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + 4 * WG_OPERAND_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t n_chunks = (M + WG_CHUNK - 1) / WG_CHUNK;
+    const uint32_t n_pad = (in_dim + 15u) & ~15u;                      // MMA N
+
+    // padding features (j >= width) are never written by the loads: zero everything once
+    for (uint32_t i = tid; i < 4 * WG_OPERAND_BYTES / 16; i += WG_THREADS) reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = idesc_f16(128, n_pad) | (1u << 15) | (1u << 16);       // A and B MN-major
+
+    uint32_t it = 0;
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x, it++) {
+        const uint32_t b = it & 1u;
+        if (it >= 2) mbar_wait(&bars[b], ((it >> 1) - 1u) & 1u);            // the MMAs that read this buffer two chunks ago are done
+        uint8_t *sA = base + b * WG_OPERAND_BYTES, *sB = base + (2u + b) * WG_OPERAND_BYTES;      // two buffers per operand
+        load_chunk_any(va, sA, dy, c * WG_CHUNK, M, out_dim);
+        load_chunk_any(vb, sB, x, c * WG_CHUNK, M, in_dim);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            uint64_t da = smem_desc_mn_sw128(smem_u32(sA)), db = smem_desc_mn_sw128(smem_u32(sB));
+#pragma unroll 1
+            for (uint32_t k = 0; k < WG_CHUNK / 16; k++, da += 2048u >> 4, db += 2048u >> 4) mma_f16_ss(tmem, da, db, idesc, it > 0 || k > 0);
+            mma_commit(&bars[b]);
+        }
+    }
+    if (it > 0) {
+        const uint32_t last = it - 1;
+        mbar_wait(&bars[last & 1u], (last >> 1) & 1u);                      // a commit covers every MMA issued before it
+        fence_after_sync();
+        if (warp < 4) {
+            const uint32_t o = tid;                                         // TMEM lane = output row
+            const uint32_t taddr = tmem + ((warp * 32u) << 16);
+            for (uint32_t cb = 0; cb < n_pad; cb += 16) {
+                uint32_t acc[16];
+                ld16(taddr + cb, acc);
+                wait_ld();
+                if (o < out_dim) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 16; j++)
+                        if (cb + j < in_dim) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dw + (size_t)o * in_dim + cb + j), "f"(__uint_as_float(acc[j])) : "memory");
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+static uint32_t vec_width(const void *p, uint32_t width) {
+    for (uint32_t v = 8; v > 1; v >>= 1)
+        if (width % v == 0 && ((uintptr_t)p % (2 * v)) == 0) return v;
+    return 1;
+}
+
+}  // namespace b2n
+
+using namespace b2n;
+
+extern "C" int b2n_linear_wgrad(const void *dy, const void *x, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, void *stream) {
+    B2N_REQUIRE(dy && x && dw, "linear_wgrad: null pointer");
+    B2N_REQUIRE(out_dim >= 1 && out_dim <= 128 && in_dim >= 1 && in_dim <= 128, "linear_wgrad: out=%u / in=%u unsupported (1..128)", out_dim, in_dim);
+    B2N_REQUIRE(((uintptr_t)dy & 1) == 0 && ((uintptr_t)x & 1) == 0, "linear_wgrad: operands must be 2-byte aligned");
+    if (M == 0) return 0;
+    static bool attr = false;
+    if (!attr) { B2N_CUDA(cudaFuncSetAttribute(k_linear_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM)); attr = true; }
+    const uint32_t n_chunks = ceil_div<uint32_t>(M, WG_CHUNK);
+    uint32_t ctas = (uint32_t)sm_count();
+    if (ctas > n_chunks) ctas = n_chunks;
+    k_linear_wgrad<<<ctas, WG_THREADS, WG_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, vec_width(dy, out_dim),
+                                                                    vec_width(x, in_dim), dw);
+    return check_launch("linear_wgrad");
+}

@@ -209,3 +209,26 @@ def test_frame_renderer_while_graph_matches_fixed_sequence():
         iters = r_graph.last_iterations()
         assert 3 <= iters <= 16 and iters == r_eager.last_iterations() or r_eager.last_iterations() >= iters
     assert float(a.mean()) < 0.999          # the head is visible against the white background
+
+
+@pytest.mark.parametrize("n_out,n_in", [(64, 36), (32, 64), (16, 36), (1, 16), (64, 69), (65, 64), (64, 84), (3, 64), (128, 128), (32, 32)])
+@pytest.mark.parametrize("M", [128, 1000, 40064])
+def test_linear_wgrad_matches_fp32_matmul(n_out, n_in, M):
+    """b2n_linear_wgrad: dW += dY^T X over M samples (fp16 operands as MN-major tcgen05 operands, fp32 accumulation) vs torch in fp32.
+    Products of two halves are exact in fp32, so the only difference is the summation order: 1e-4 of the result scale."""
+    from b2nerf._lib import lib
+    g = torch.Generator(device="cuda").manual_seed(M * 1000 + n_out * 7 + n_in)
+    dy = torch.randn(M, n_out, device="cuda", generator=g).half()
+    x = torch.randn(M, n_in, device="cuda", generator=g).half()
+    dw = torch.full((n_out, n_in), 0.5, device="cuda")              # accumulates on top of the caller's buffer
+    lib().call("b2n_linear_wgrad", dy.data_ptr(), x.data_ptr(), M, n_out, n_in, dw.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    ref = dy.float().t() @ x.float() + 0.5
+    scale = float(ref.abs().max())
+    assert float((dw - ref).abs().max()) <= 1e-4 * scale + 1e-3, float((dw - ref).abs().max())
+    # a 2-byte-aligned (odd element offset) view of the operands takes the narrow-access path
+    if M == 1000:
+        buf = torch.zeros(M * n_in + 1, device="cuda", dtype=torch.float16)
+        xo = buf[1:].view(M, n_in); xo.copy_(x)
+        dw2 = torch.zeros(n_out, n_in, device="cuda")
+        lib().call("b2n_linear_wgrad", dy.data_ptr(), xo.data_ptr(), M, n_out, n_in, dw2.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert float((dw2 - (ref - 0.5)).abs().max()) <= 1e-4 * scale + 1e-3
