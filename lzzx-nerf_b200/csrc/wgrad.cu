@@ -3,9 +3,9 @@
 // (nerf_triplane/network.py:73-94 through autograd's LinearBackward).
 //
 // The reduction runs over the SAMPLE dimension, which is the slow (row) dimension of both operands in memory, so both are "MN-major"
-// tensor-core operands: a 128-sample chunk of dY / X is copied row by row into shared memory in the canonical SWIZZLE_128B MN-major layout
-// (128-byte rows of 64 features for one sample, 8-sample groups of 1024 B, 64-feature column blocks 16 KB apart) and fed to tcgen05.mma
-// with a_major = b_major = MN — no transposition anywhere.  One CTA per SM walks its share of the chunks with two operand buffers (the
+// tensor-core operands: a 64-sample chunk of dY / X is copied row by row into shared memory in the canonical SWIZZLE_128B MN-major layout
+// (128-byte rows of 64 features for one sample, 8-sample groups of 1024 B, 64-feature column blocks 8 KB apart) and fed to tcgen05.mma
+// with a_major = b_major = MN — no transposition anywhere.  Two CTAs per SM walk their share of the chunks with two operand buffers each (the
 // loads of chunk c+1 overlap the MMAs of chunk c), accumulates the whole out x in product in TMEM (M = 128 lanes, N = in columns) and
 // adds it once to the fp32 result with red.global — so the library's one-wave split (4-6 CTAs, 170-300 us per layer measured) becomes an
 // HBM-bound stream over the activations.
@@ -16,8 +16,8 @@ namespace b2n {
 using namespace tc5;
 
 constexpr uint32_t WG_THREADS = 256;
-constexpr uint32_t WG_CHUNK = 128;                       // samples per chunk = 8 MMA K-steps
-constexpr uint32_t WG_BLOCK_BYTES = WG_CHUNK * 128;      // one 64-feature column block of a chunk: 128 sample rows x 128 B
+constexpr uint32_t WG_CHUNK = 64;                        // samples per chunk = 4 MMA K-steps
+constexpr uint32_t WG_BLOCK_BYTES = WG_CHUNK * 128;      // one 64-feature column block of a chunk: 64 sample rows x 128 B
 constexpr uint32_t WG_OPERAND_BYTES = 2 * WG_BLOCK_BYTES;   // up to 128 features
 constexpr uint32_t WG_SMEM = 4 * WG_OPERAND_BYTES + 1024 + 64;
 
@@ -36,19 +36,33 @@ __device__ __forceinline__ uint32_t mn_offset(uint32_t k, uint32_t j) {
     return (j >> 6) * WG_BLOCK_BYTES + (k >> 3) * 1024u + (k & 7u) * 128u + ((((j & 63u) >> 3) ^ (k & 7u)) << 4) + (j & 7u) * 2u;
 }
 
-// copy rows [row0, row0+128) of a row-major fp16 matrix [M, width] into an operand buffer; V = halves per access (V | width, pointer 2V-aligned)
+// copy rows [row0, row0 + WG_CHUNK) of a row-major fp16 matrix [M, width] into an operand buffer; V = halves per access (V | width, pointer
+// 2V-aligned).  Loads are issued in batches of 4 per thread before the first store, so a CTA keeps its whole chunk in flight.
+template <uint32_t V> struct VecOf;
+template <> struct VecOf<8> { typedef uint4 type; };
+template <> struct VecOf<4> { typedef uint2 type; };
+template <> struct VecOf<2> { typedef uint32_t type; };
+template <> struct VecOf<1> { typedef uint16_t type; };
+
 template <uint32_t V>
 __device__ __forceinline__ void load_chunk(uint8_t *buf, const __half *__restrict__ src, uint32_t row0, uint32_t M, uint32_t width) {
+    typedef typename VecOf<V>::type vec_t;
     const uint32_t nv = width / V, total = WG_CHUNK * nv;
-    for (uint32_t idx = threadIdx.x; idx < total; idx += WG_THREADS) {
-        const uint32_t k = idx / nv, j = (idx - k * nv) * V;
-        const uint32_t row = row0 + k;
-        uint8_t *dst = buf + mn_offset(k, j);
-        const __half *p = src + (size_t)row * width + j;
-        if (V == 8) *reinterpret_cast<uint4 *>(dst) = row < M ? __ldcs(reinterpret_cast<const uint4 *>(p)) : make_uint4(0, 0, 0, 0);
-        else if (V == 4) *reinterpret_cast<uint2 *>(dst) = row < M ? __ldcs(reinterpret_cast<const uint2 *>(p)) : make_uint2(0, 0);
-        else if (V == 2) *reinterpret_cast<uint32_t *>(dst) = row < M ? __ldcs(reinterpret_cast<const uint32_t *>(p)) : 0u;
-        else *reinterpret_cast<uint16_t *>(dst) = row < M ? __ldcs(reinterpret_cast<const uint16_t *>(p)) : (uint16_t)0;
+    for (uint32_t i0 = threadIdx.x; i0 < total; i0 += 4 * WG_THREADS) {
+        vec_t v[4];
+        uint32_t off[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+            const uint32_t idx = i0 + u * WG_THREADS;
+            const uint32_t k = idx / nv, j = (idx - k * nv) * V;
+            const uint32_t row = row0 + k;
+            off[u] = idx < total ? mn_offset(k, j) : 0xffffffffu;
+            v[u] = vec_t();
+            if (idx < total && row < M) v[u] = __ldcs(reinterpret_cast<const vec_t *>(src + (size_t)row * width + j));
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++)
+            if (off[u] != 0xffffffffu) *reinterpret_cast<vec_t *>(buf + off[u]) = v[u];
     }
 }
 __device__ __forceinline__ void load_chunk_any(uint32_t v, uint8_t *buf, const __half *src, uint32_t row0, uint32_t M, uint32_t width) {
@@ -58,7 +72,7 @@ __device__ __forceinline__ void load_chunk_any(uint32_t v, uint8_t *buf, const _
     else load_chunk<1>(buf, src, row0, M, width);
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1) k_linear_wgrad(const __half *__restrict__ dy, const __half *__restrict__ x, uint32_t M, uint32_t out_dim,
+__global__ void __launch_bounds__(WG_THREADS, 2) k_linear_wgrad(const __half *__restrict__ dy, const __half *__restrict__ x, uint32_t M, uint32_t out_dim,
                                                                  uint32_t in_dim, uint32_t va, uint32_t vb, float *__restrict__ dw) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -67,6 +81,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_linear_wgrad(const __half *__
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t n_chunks = (M + WG_CHUNK - 1) / WG_CHUNK;
     const uint32_t n_pad = (in_dim + 15u) & ~15u;                      // MMA N
+    const bool vec4 = (in_dim & 3u) == 0 && ((uintptr_t)dw & 15u) == 0;
 
     // padding features (j >= width) are never written by the loads: zero everything once
     for (uint32_t i = tid; i < 4 * WG_OPERAND_BYTES / 16; i += WG_THREADS) reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
@@ -107,9 +122,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_linear_wgrad(const __half *__
                 ld16(taddr + cb, acc);
                 wait_ld();
                 if (o < out_dim) {
+                    float *row = dw + (size_t)o * in_dim + cb;
+                    if (vec4) {                                          // in_dim % 4 == 0 and dw 16-byte aligned: one vector reduction per 4 columns
 #pragma unroll
-                    for (uint32_t j = 0; j < 16; j++)
-                        if (cb + j < in_dim) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dw + (size_t)o * in_dim + cb + j), "f"(__uint_as_float(acc[j])) : "memory");
+                        for (uint32_t j = 0; j < 16; j += 4)
+                            if (cb + j < in_dim)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + j), "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
+                                             "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3])) : "memory");
+                    } else {
+#pragma unroll
+                        for (uint32_t j = 0; j < 16; j++)
+                            if (cb + j < in_dim) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(row + j), "f"(__uint_as_float(acc[j])) : "memory");
+                    }
                 }
             }
         }
@@ -137,7 +161,7 @@ extern "C" int b2n_linear_wgrad(const void *dy, const void *x, uint32_t M, uint3
     static bool attr = false;
     if (!attr) { B2N_CUDA(cudaFuncSetAttribute(k_linear_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM)); attr = true; }
     const uint32_t n_chunks = ceil_div<uint32_t>(M, WG_CHUNK);
-    uint32_t ctas = (uint32_t)sm_count();
+    uint32_t ctas = 2u * (uint32_t)sm_count();            // 64 KB of operand buffers per CTA: two resident CTAs per SM
     if (ctas > n_chunks) ctas = n_chunks;
     k_linear_wgrad<<<ctas, WG_THREADS, WG_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, vec_width(dy, out_dim),
                                                                     vec_width(x, in_dim), dw);
