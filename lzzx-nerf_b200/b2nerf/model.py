@@ -70,8 +70,10 @@ class MLP(nn.Module):
         dims = [dim_in] + [dim_hidden] * (num_layers - 1) + [dim_out]
         self.net = nn.ModuleList(nn.Linear(dims[i], dims[i + 1], bias=False) for i in range(num_layers))
 
+    tall_linear = True       # class switch: False = plain nn.Linear everywhere (the reference's MLP, used by profiles/reference_on_b200.py)
+
     def forward(self, x):
-        tall = (x.is_cuda and x.dim() == 2 and x.shape[0] >= 16384 and x.shape[0] % _TallLinear.SLABS == 0 and torch.is_grad_enabled()
+        tall = (MLP.tall_linear and x.is_cuda and x.dim() == 2 and x.shape[0] >= 16384 and x.shape[0] % _TallLinear.SLABS == 0 and torch.is_grad_enabled()
                 and any(l.weight.requires_grad for l in self.net))
         for i, layer in enumerate(self.net):
             x = _TallLinear.apply(x.contiguous(), layer.weight) if tall else layer(x)

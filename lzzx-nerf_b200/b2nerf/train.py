@@ -20,14 +20,14 @@ from .model import HeadModel
 
 
 class Trainer:
-    def __init__(self, model: HeadModel, lr=1e-2, lr_net=1e-3, fp16=True, max_steps=16, dt_gamma=1.0 / 256, min_near=0.05, lambda_amb=1e-4):
+    def __init__(self, model: HeadModel, lr=1e-2, lr_net=1e-3, fp16=True, max_steps=16, dt_gamma=1.0 / 256, min_near=0.05, lambda_amb=1e-4, fused_optimizer=True):
         self.m = model
         self.fp16, self.max_steps, self.dt_gamma, self.min_near, self.lambda_amb = fp16, max_steps, dt_gamma, min_near, lambda_amb
         enc = [model.encoder_xy.embeddings, model.encoder_yz.embeddings, model.encoder_xz.embeddings]
         enc_ids = {id(p) for p in enc}
         net = [p for p in model.parameters() if id(p) not in enc_ids]
         # AdamW(betas=(0.0, 0.99), eps=1e-8) with lr for the tables and lr_net for the networks (train.py:274, network.py:315-357)
-        on_gpu = enc[0].is_cuda
+        on_gpu = enc[0].is_cuda and fused_optimizer
         self.opt = torch.optim.AdamW([{"params": enc, "lr": lr}, {"params": net, "lr": lr_net, "weight_decay": 0}], betas=(0.0, 0.99), eps=1e-8,
                                      fused=on_gpu, capturable=on_gpu)       # multi-tensor kernels; inf/nan skip + unscale happen on the device
         self.grads = FlatGradBuffer(list(model.parameters()))
