@@ -95,6 +95,14 @@ int b2n_frame_iterations(const void *workspace, uint32_t N, int32_t *iterations,
  * LinearBackward runs for every MLP layer of nerf_triplane/network.py:73-94 in a training step (csrc/wgrad.cu). */
 int b2n_linear_wgrad(const void *dy_f16, const void *x_f16, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, void *stream);
 
+/* AdamW over one flat fp32 parameter buffer (parameters, gradients and both moments contiguous; two hyper-parameter groups split at
+ * n_group0).  Replaces torch.optim.AdamW + the GradScaler unscale pass of the reference's optimizer step (TrainerUtil.py:1040-1056,
+ * train.py:274).  `step` is a 1-element device counter (incremented unless found_inf), `grad_scale` / `found_inf` are the GradScaler's
+ * device scalars (NULL = no scaling / never skip): the gradient is divided by grad_scale and the whole step is skipped when found_inf != 0. */
+int b2n_adamw_flat(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, uint32_t n, uint32_t n_group0, float lr0,
+                   float weight_decay0, float lr1, float weight_decay1, float beta1, float beta2, float eps, float *step,
+                   const float *grad_scale, const float *found_inf, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

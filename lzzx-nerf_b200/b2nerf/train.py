@@ -27,10 +27,16 @@ class Trainer:
         enc_ids = {id(p) for p in enc}
         net = [p for p in model.parameters() if id(p) not in enc_ids]
         # AdamW(betas=(0.0, 0.99), eps=1e-8) with lr for the tables and lr_net for the networks (train.py:274, network.py:315-357)
-        on_gpu = enc[0].is_cuda and fused_optimizer
-        self.opt = torch.optim.AdamW([{"params": enc, "lr": lr}, {"params": net, "lr": lr_net, "weight_decay": 0}], betas=(0.0, 0.99), eps=1e-8,
-                                     fused=on_gpu, capturable=on_gpu)       # multi-tensor kernels; inf/nan skip + unscale happen on the device
-        self.grads = FlatGradBuffer(list(model.parameters()))
+        if enc[0].is_cuda and fused_optimizer:
+            from .optim import FlatAdamW
+            self.opt = FlatAdamW(enc, net, lr, lr_net, weight_decay0=0.01, weight_decay1=0.0, betas=(0.0, 0.99), eps=1e-8)    # one kernel, no sync
+        else:
+            self.opt = torch.optim.AdamW([{"params": enc, "lr": lr}, {"params": net, "lr": lr_net, "weight_decay": 0}], betas=(0.0, 0.99), eps=1e-8)
+        self.grads = FlatGradBuffer(enc + net)           # same parameter order as the optimizer's flat buffers
+        if hasattr(self.opt, "attach_grads"):
+            self.opt.attach_grads(self.grads.flat)
+            if getattr(model, "_handle", None) is not None:
+                model.pack()                              # the parameter storage moved: refresh the pointers baked into the packed model
         self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
         self.local_step = 0
         self.mean_count = 0

@@ -124,3 +124,36 @@ def test_graphed_step_matches_eager_step():
     assert np.allclose(eager, graphed, rtol=2e-2, atol=2e-3), (eager, graphed)
     for (k, p), (_, q) in zip(m.named_parameters(), m2.named_parameters()):
         assert torch.isfinite(q).all(), k
+
+
+def test_flat_adamw_matches_torch_adamw():
+    """FlatAdamW (one kernel over a flat buffer, csrc/optim.cu) vs torch.optim.AdamW with the reference's groups / betas, incl. a GradScaler
+    step that is skipped because of an overflow."""
+    from b2nerf.optim import FlatAdamW
+    torch.manual_seed(0)
+    shapes0, shapes1 = [(1000, 1), (333, 1)], [(64, 36), (3, 64), (7,)]
+    mk = lambda shapes: [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    a0, a1 = mk(shapes0), mk(shapes1)
+    b0, b1 = [torch.nn.Parameter(p.detach().clone()) for p in a0], [torch.nn.Parameter(p.detach().clone()) for p in a1]
+    ref = torch.optim.AdamW([{"params": b0, "lr": 1e-2}, {"params": b1, "lr": 1e-3, "weight_decay": 0}], betas=(0.0, 0.99), eps=1e-8)
+    opt = FlatAdamW(a0, a1, 1e-2, 1e-3, weight_decay0=0.01, weight_decay1=0.0, betas=(0.0, 0.99), eps=1e-8)
+    flat_g = torch.zeros(opt.n, device="cuda")
+    off = 0
+    for p in a0 + a1:
+        p.grad = flat_g[off:off + p.numel()].view_as(p); off += p.numel()
+    opt.attach_grads(flat_g)
+    sa, sb = torch.amp.GradScaler("cuda", init_scale=1024.0), torch.amp.GradScaler("cuda", init_scale=1024.0)
+    for step in range(6):
+        gs = [torch.randn_like(p) for p in a0 + a1]
+        if step == 3:
+            gs[1][5] = float("inf")                       # overflow: both must skip this step and halve the scale
+        for p, q, g in zip(a0 + a1, b0 + b1, gs):
+            p.grad.copy_(g * sa.get_scale()); q.grad = g * sb.get_scale()
+        # GradScaler bookkeeping needs a scaled loss to have been produced
+        sa.scale(torch.zeros((), device="cuda")); sb.scale(torch.zeros((), device="cuda"))
+        sa.step(opt); sa.update()
+        sb.step(ref); sb.update()
+        assert sa.get_scale() == sb.get_scale()
+    assert float(opt.step_count) == 5.0
+    for p, q in zip(a0 + a1, b0 + b1):
+        assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), float((p - q).abs().max())
