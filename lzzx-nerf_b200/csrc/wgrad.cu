@@ -11,6 +11,7 @@
 // HBM-bound stream over the activations.
 #include "common.cuh"
 #include "tc5.cuh"
+#include <cstdlib>
 
 namespace b2n {
 using namespace tc5;
@@ -36,9 +37,9 @@ __device__ __forceinline__ uint32_t mn_offset(uint32_t k, uint32_t j) {
     return (j >> 6) * WG_BLOCK_BYTES + (k >> 3) * 1024u + (k & 7u) * 128u + ((((j & 63u) >> 3) ^ (k & 7u)) << 4) + (j & 7u) * 2u;
 }
 
-// A 64-row chunk of a row-major fp16 matrix [M, width] held in registers between its global loads and its shared-memory stores, so the
-// loads of chunk c+1 are in flight while chunk c is stored, published and multiplied.  V = halves per access (V | width, pointer 2V-aligned);
-// a thread owns accesses tid, tid + 256, ... (at most 32 / V of them for width <= 128).
+// copy rows [row0, row0 + WG_CHUNK) of a row-major fp16 matrix [M, width] into an operand buffer.  V = halves per access (V | width, pointer
+// 2V-aligned).  Threads are laid out as (row, access-in-row) with a power-of-two number of threads per row, so there is no division in the
+// loop; loads are issued in batches of 4 rows per thread before the first store.
 template <uint32_t V> struct VecOf;
 template <> struct VecOf<8> { typedef uint4 type; };
 template <> struct VecOf<4> { typedef uint2 type; };
@@ -46,64 +47,34 @@ template <> struct VecOf<2> { typedef uint32_t type; };
 template <> struct VecOf<1> { typedef uint16_t type; };
 
 template <uint32_t V>
-struct ChunkRegs {
+__device__ __forceinline__ void load_chunk(uint8_t *buf, const __half *__restrict__ src, uint32_t row0, uint32_t M, uint32_t width) {
     typedef typename VecOf<V>::type vec_t;
-    static constexpr uint32_t N = 32 / V;
-    vec_t v[N];
-
-    __device__ __forceinline__ void issue(const __half *__restrict__ src, uint32_t row0, uint32_t M, uint32_t width) {
-        const uint32_t nv = width / V, total = WG_CHUNK * nv;
+    const uint32_t nv = width / V;                                   // accesses per row (<= 128)
+    const uint32_t lg = 32u - __clz(nv - 1u | 0u) ;                  // ceil(log2(nv)) for nv >= 2; nv == 1 -> __clz(0) = 32 -> 0
+    const uint32_t tpr = 1u << lg;                                    // threads per row
+    const uint32_t col = threadIdx.x & (tpr - 1u), r0 = threadIdx.x >> lg, rstep = WG_THREADS >> lg;
+    if (col >= nv) return;
+    const uint32_t j = col * V;
+    for (uint32_t k0 = r0; k0 < WG_CHUNK; k0 += 4 * rstep) {
+        vec_t v[4];
 #pragma unroll
-        for (uint32_t u = 0; u < N; u++) {
-            const uint32_t idx = threadIdx.x + u * WG_THREADS;
+        for (uint32_t u = 0; u < 4; u++) {
+            const uint32_t k = k0 + u * rstep;
             v[u] = vec_t();
-            if (idx < total) {
-                const uint32_t k = idx / nv, j = (idx - k * nv) * V;
-                if (row0 + k < M) v[u] = __ldcs(reinterpret_cast<const vec_t *>(src + (size_t)(row0 + k) * width + j));
-            }
+            if (k < WG_CHUNK && row0 + k < M) v[u] = __ldcs(reinterpret_cast<const vec_t *>(src + (size_t)(row0 + k) * width + j));
         }
-    }
-    __device__ __forceinline__ void store(uint8_t *buf, uint32_t width) const {
-        const uint32_t nv = width / V, total = WG_CHUNK * nv;
 #pragma unroll
-        for (uint32_t u = 0; u < N; u++) {
-            const uint32_t idx = threadIdx.x + u * WG_THREADS;
-            if (idx < total) {
-                const uint32_t k = idx / nv, j = (idx - k * nv) * V;
-                *reinterpret_cast<vec_t *>(buf + mn_offset(k, j)) = v[u];
-            }
+        for (uint32_t u = 0; u < 4; u++) {
+            const uint32_t k = k0 + u * rstep;
+            if (k < WG_CHUNK) *reinterpret_cast<vec_t *>(buf + mn_offset(k, j)) = v[u];
         }
     }
-};
-
-// the chunk loop of one CTA for a given pair of access widths
-template <uint32_t VA, uint32_t VB>
-__device__ __forceinline__ uint32_t chunk_loop(uint8_t *base, uint64_t *bars, uint32_t tmem, uint32_t idesc, const __half *__restrict__ dy,
-                                               const __half *__restrict__ x, uint32_t M, uint32_t out_dim, uint32_t in_dim, uint32_t n_chunks) {
-    ChunkRegs<VA> ra;
-    ChunkRegs<VB> rb;
-    uint32_t it = 0;
-    uint32_t c = blockIdx.x;
-    if (c < n_chunks) { ra.issue(dy, c * WG_CHUNK, M, out_dim); rb.issue(x, c * WG_CHUNK, M, in_dim); }
-    for (; c < n_chunks; c += gridDim.x, it++) {
-        const uint32_t b = it & 1u;
-        if (it >= 2) mbar_wait(&bars[b], ((it >> 1) - 1u) & 1u);            // the MMAs that read this buffer two chunks ago are done
-        uint8_t *sA = base + b * WG_OPERAND_BYTES, *sB = base + (2u + b) * WG_OPERAND_BYTES;      // two buffers per operand
-        ra.store(sA, out_dim);
-        rb.store(sB, in_dim);
-        const uint32_t cn = c + gridDim.x;
-        if (cn < n_chunks) { ra.issue(dy, cn * WG_CHUNK, M, out_dim); rb.issue(x, cn * WG_CHUNK, M, in_dim); }
-        fence_proxy_async();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            fence_after_sync();
-            uint64_t da = smem_desc_mn_sw128(smem_u32(sA)), db = smem_desc_mn_sw128(smem_u32(sB));
-#pragma unroll 1
-            for (uint32_t k = 0; k < WG_CHUNK / 16; k++, da += 2048u >> 4, db += 2048u >> 4) mma_f16_ss(tmem, da, db, idesc, it > 0 || k > 0);
-            mma_commit(&bars[b]);
-        }
-    }
-    return it;
+}
+__device__ __noinline__ void load_chunk_any(uint32_t v, uint8_t *buf, const __half *src, uint32_t row0, uint32_t M, uint32_t width) {
+    if (v == 8) load_chunk<8>(buf, src, row0, M, width);
+    else if (v == 4) load_chunk<4>(buf, src, row0, M, width);
+    else if (v == 2) load_chunk<2>(buf, src, row0, M, width);
+    else load_chunk<1>(buf, src, row0, M, width);
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 2) k_linear_wgrad(const __half *__restrict__ dy, const __half *__restrict__ x, uint32_t M, uint32_t out_dim,
@@ -128,15 +99,22 @@ __global__ void __launch_bounds__(WG_THREADS, 2) k_linear_wgrad(const __half *__
     const uint32_t idesc = idesc_f16(128, n_pad) | (1u << 15) | (1u << 16);       // A and B MN-major
 
     uint32_t it = 0;
-#define B2N_WG_CASE(A, B) case (A) * 16 + (B): it = chunk_loop<A, B>(base, bars, tmem, idesc, dy, x, M, out_dim, in_dim, n_chunks); break;
-    switch (va * 16 + vb) {
-        B2N_WG_CASE(8, 8) B2N_WG_CASE(8, 4) B2N_WG_CASE(8, 2) B2N_WG_CASE(8, 1)
-        B2N_WG_CASE(4, 8) B2N_WG_CASE(4, 4) B2N_WG_CASE(4, 2) B2N_WG_CASE(4, 1)
-        B2N_WG_CASE(2, 8) B2N_WG_CASE(2, 4) B2N_WG_CASE(2, 2) B2N_WG_CASE(2, 1)
-        B2N_WG_CASE(1, 8) B2N_WG_CASE(1, 4) B2N_WG_CASE(1, 2) B2N_WG_CASE(1, 1)
-        default: break;
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x, it++) {
+        const uint32_t b = it & 1u;
+        if (it >= 2) mbar_wait(&bars[b], ((it >> 1) - 1u) & 1u);            // the MMAs that read this buffer two chunks ago are done
+        uint8_t *sA = base + b * WG_OPERAND_BYTES, *sB = base + (2u + b) * WG_OPERAND_BYTES;      // two buffers per operand
+        load_chunk_any(va, sA, dy, c * WG_CHUNK, M, out_dim);
+        load_chunk_any(vb, sB, x, c * WG_CHUNK, M, in_dim);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            uint64_t da = smem_desc_mn_sw128(smem_u32(sA)), db = smem_desc_mn_sw128(smem_u32(sB));
+#pragma unroll 1
+            for (uint32_t k = 0; k < WG_CHUNK / 16; k++, da += 2048u >> 4, db += 2048u >> 4) mma_f16_ss(tmem, da, db, idesc, it > 0 || k > 0);
+            mma_commit(&bars[b]);
+        }
     }
-#undef B2N_WG_CASE
     if (it > 0) {
         const uint32_t last = it - 1;
         mbar_wait(&bars[last & 1u], (last >> 1) & 1u);                      // a commit covers every MMA issued before it
@@ -185,10 +163,12 @@ extern "C" int b2n_linear_wgrad(const void *dy, const void *x, uint32_t M, uint3
     B2N_REQUIRE(out_dim >= 1 && out_dim <= 128 && in_dim >= 1 && in_dim <= 128, "linear_wgrad: out=%u / in=%u unsupported (1..128)", out_dim, in_dim);
     B2N_REQUIRE(((uintptr_t)dy & 1) == 0 && ((uintptr_t)x & 1) == 0, "linear_wgrad: operands must be 2-byte aligned");
     if (M == 0) return 0;
+    uint32_t ctas_per_sm = 2;
     static bool attr = false;
     if (!attr) { B2N_CUDA(cudaFuncSetAttribute(k_linear_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM)); attr = true; }
+    if (const char *g = getenv("B2N_WGRAD_CTAS_PER_SM")) ctas_per_sm = (uint32_t)atoi(g);
     const uint32_t n_chunks = ceil_div<uint32_t>(M, WG_CHUNK);
-    uint32_t ctas = 2u * (uint32_t)sm_count();            // 64 KB of operand buffers per CTA: two resident CTAs per SM
+    uint32_t ctas = ctas_per_sm * (uint32_t)sm_count();            // 64 KB of operand buffers per CTA: two resident CTAs per SM
     if (ctas > n_chunks) ctas = n_chunks;
     k_linear_wgrad<<<ctas, WG_THREADS, WG_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, vec_width(dy, out_dim),
                                                                     vec_width(x, in_dim), dw);
