@@ -70,14 +70,53 @@ __device__ __forceinline__ void load_chunk(uint8_t *buf, const __half *__restric
         }
     }
 }
+// Odd widths (69, 65, 3, 1: rows are not even 4-byte aligned) with a 16-byte aligned matrix: a chunk starts at a multiple of 64 rows, i.e. at a
+// multiple of 128 * width bytes, so the chunk is read as a FLAT stream of aligned 16-byte vectors and only the shared-memory side is
+// element-wise (8 two-byte stores per vector, row/column advanced incrementally: one division per vector).
+__device__ __forceinline__ void load_chunk_flat(uint8_t *buf, const __half *__restrict__ src, uint32_t row0, uint32_t M, uint32_t width) {
+    const uint32_t nvec = WG_CHUNK * width / 8u;                     // 64 * width halves = 8 * width vectors
+    const size_t e0 = (size_t)row0 * width, e_end = (size_t)M * width;
+    for (uint32_t v0 = threadIdx.x; v0 < nvec; v0 += 2 * WG_THREADS) {
+        uint4 q[2];
+#pragma unroll
+        for (uint32_t u = 0; u < 2; u++) {
+            const uint32_t vi = v0 + u * WG_THREADS;
+            q[u] = make_uint4(0, 0, 0, 0);
+            if (vi < nvec) {
+                const size_t e = e0 + (size_t)vi * 8u;
+                if (e + 8u <= e_end) q[u] = __ldcs(reinterpret_cast<const uint4 *>(src + e));
+                else {                                                // last rows of the matrix: element-wise, zero beyond the end
+                    __half h[8];
+#pragma unroll
+                    for (uint32_t t = 0; t < 8; t++) h[t] = e + t < e_end ? src[e + t] : __float2half_rn(0.0f);
+                    q[u] = *reinterpret_cast<uint4 *>(h);
+                }
+            }
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 2; u++) {
+            const uint32_t vi = v0 + u * WG_THREADS;
+            if (vi < nvec) {
+                uint32_t k = vi * 8u / width, j = vi * 8u - k * width;
+                const uint16_t *h = reinterpret_cast<const uint16_t *>(&q[u]);
+#pragma unroll
+                for (uint32_t t = 0; t < 8; t++) {
+                    *reinterpret_cast<uint16_t *>(buf + mn_offset(k, j)) = h[t];
+                    if (++j == width) { j = 0; k++; }
+                }
+            }
+        }
+    }
+}
 __device__ __noinline__ void load_chunk_any(uint32_t v, uint8_t *buf, const __half *src, uint32_t row0, uint32_t M, uint32_t width) {
-    if (v == 8) load_chunk<8>(buf, src, row0, M, width);
+    if (v == 0) load_chunk_flat(buf, src, row0, M, width);
+    else if (v == 8) load_chunk<8>(buf, src, row0, M, width);
     else if (v == 4) load_chunk<4>(buf, src, row0, M, width);
     else if (v == 2) load_chunk<2>(buf, src, row0, M, width);
     else load_chunk<1>(buf, src, row0, M, width);
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 2) k_linear_wgrad(const __half *__restrict__ dy, const __half *__restrict__ x, uint32_t M, uint32_t out_dim,
+__global__ void __launch_bounds__(WG_THREADS, 3) k_linear_wgrad(const __half *__restrict__ dy, const __half *__restrict__ x, uint32_t M, uint32_t out_dim,
                                                                  uint32_t in_dim, uint32_t va, uint32_t vb, float *__restrict__ dw) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -148,10 +187,11 @@ __global__ void __launch_bounds__(WG_THREADS, 2) k_linear_wgrad(const __half *__
     if (warp == 1) tmem_dealloc(tmem, 128);
 }
 
+// halves per global access: 8/4/2 when rows allow it, 0 = flat 16-byte stream (odd width, 16-byte aligned matrix), 1 = element-wise
 static uint32_t vec_width(const void *p, uint32_t width) {
     for (uint32_t v = 8; v > 1; v >>= 1)
         if (width % v == 0 && ((uintptr_t)p % (2 * v)) == 0) return v;
-    return 1;
+    return ((uintptr_t)p % 16) == 0 ? 0 : 1;
 }
 
 }  // namespace b2n
@@ -163,12 +203,12 @@ extern "C" int b2n_linear_wgrad(const void *dy, const void *x, uint32_t M, uint3
     B2N_REQUIRE(out_dim >= 1 && out_dim <= 128 && in_dim >= 1 && in_dim <= 128, "linear_wgrad: out=%u / in=%u unsupported (1..128)", out_dim, in_dim);
     B2N_REQUIRE(((uintptr_t)dy & 1) == 0 && ((uintptr_t)x & 1) == 0, "linear_wgrad: operands must be 2-byte aligned");
     if (M == 0) return 0;
-    uint32_t ctas_per_sm = 2;
+    uint32_t ctas_per_sm = 3;           // 66 KB of operand buffers + 34 registers: three resident CTAs per SM hide the per-chunk load latency
     static bool attr = false;
     if (!attr) { B2N_CUDA(cudaFuncSetAttribute(k_linear_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM)); attr = true; }
     if (const char *g = getenv("B2N_WGRAD_CTAS_PER_SM")) ctas_per_sm = (uint32_t)atoi(g);
     const uint32_t n_chunks = ceil_div<uint32_t>(M, WG_CHUNK);
-    uint32_t ctas = ctas_per_sm * (uint32_t)sm_count();            // 64 KB of operand buffers per CTA: two resident CTAs per SM
+    uint32_t ctas = ctas_per_sm * (uint32_t)sm_count();
     if (ctas > n_chunks) ctas = n_chunks;
     k_linear_wgrad<<<ctas, WG_THREADS, WG_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, vec_width(dy, out_dim),
                                                                     vec_width(x, in_dim), dw);
