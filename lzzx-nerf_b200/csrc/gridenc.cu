@@ -293,36 +293,49 @@ __global__ void __launch_bounds__(GP_THREADS) k_grid_bwd_priv(const float *__res
     }
     const uint32_t per = (B + S_slices - 1) / S_slices;
     const uint32_t b0 = blockIdx.x * per, b1 = min(B, b0 + per);
-#pragma unroll 2
-    for (uint32_t b = b0 + threadIdx.x; b < b1; b += GP_THREADS) {
-        float in[D];
-        bool oob = false;
+    constexpr uint32_t U = 4;                        // samples in flight per thread: all their loads are issued before the first atomic
+    for (uint32_t bb = b0 + threadIdx.x; bb < b1; bb += U * GP_THREADS) {
+        float in[U][D], gc[U][C];
 #pragma unroll
-        for (uint32_t d = 0; d < D; d++) { in[d] = __ldcs(inputs + (size_t)b * D + d); oob |= (in[d] < 0.0f || in[d] > 1.0f); }
-        if (oob) continue;
-        float pos[D];
-        uint32_t pg[D];
+        for (uint32_t u = 0; u < U; u++) {
+            const uint32_t b = bb + u * GP_THREADS;
+            if (b < b1) {
 #pragma unroll
-        for (uint32_t d = 0; d < D; d++) {
-            pos[d] = __fmaf_rn(in[d], g.scale, align_corners ? 0.0f : 0.5f);
-            pg[d] = (uint32_t)floorf(pos[d]);
-            pos[d] = __fsub_rn(pos[d], (float)pg[d]);
+                for (uint32_t d = 0; d < D; d++) in[u][d] = __ldcs(inputs + (size_t)b * D + d);
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++) gc[u][c] = __ldcs(grad + ((size_t)level * B + b) * C + c);
+            } else {
+#pragma unroll
+                for (uint32_t d = 0; d < D; d++) in[u][d] = -1.0f;       // out of range -> skipped below
+            }
         }
-        float gc[C];
 #pragma unroll
-        for (uint32_t c = 0; c < C; c++) gc[c] = __ldcs(grad + ((size_t)level * B + b) * C + c);
+        for (uint32_t u = 0; u < U; u++) {
+            bool oob = false;
 #pragma unroll
-        for (uint32_t idx = 0; idx < (1u << D); idx++) {
-            float w = 1.0f;
-            uint32_t pl[D];
+            for (uint32_t d = 0; d < D; d++) oob |= (in[u][d] < 0.0f || in[u][d] > 1.0f);
+            if (oob) continue;
+            float pos[D];
+            uint32_t pg[D];
 #pragma unroll
             for (uint32_t d = 0; d < D; d++) {
-                if ((idx & (1u << d)) == 0) { w = __fmul_rn(w, __fsub_rn(1.0f, pos[d])); pl[d] = pg[d]; }
-                else                        { w = __fmul_rn(w, pos[d]);                 pl[d] = pg[d] + 1; }
+                pos[d] = __fmaf_rn(in[u][d], g.scale, align_corners ? 0.0f : 0.5f);
+                pg[d] = (uint32_t)floorf(pos[d]);
+                pos[d] = __fsub_rn(pos[d], (float)pg[d]);
             }
-            const uint32_t e = grid_slot<D>(gridtype, align_corners, g.hashmap_size, g.resolution, pl) * C;
 #pragma unroll
-            for (uint32_t c = 0; c < C; c++) atomicAdd(acc + e + c, __fmul_rn(w, gc[c]));
+            for (uint32_t idx = 0; idx < (1u << D); idx++) {
+                float w = 1.0f;
+                uint32_t pl[D];
+#pragma unroll
+                for (uint32_t d = 0; d < D; d++) {
+                    if ((idx & (1u << d)) == 0) { w = __fmul_rn(w, __fsub_rn(1.0f, pos[d])); pl[d] = pg[d]; }
+                    else                        { w = __fmul_rn(w, pos[d]);                 pl[d] = pg[d] + 1; }
+                }
+                const uint32_t e = grid_slot<D>(gridtype, align_corners, g.hashmap_size, g.resolution, pl) * C;
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++) atomicAdd(acc + e + c, __fmul_rn(w, gc[u][c]));
+            }
         }
     }
     if (!priv) return;
@@ -367,7 +380,7 @@ static int launch_bwd_priv(const float *grad, const float *inputs, const int32_t
     const size_t smem = sizeof(float) * (size_t)smem_floats;
     auto kern = k_grid_bwd_priv<D, C>;
     if (smem > 48 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
-    uint32_t slices = 2u * (uint32_t)sm_count() / L;          // two 512-thread CTAs per SM
+    uint32_t slices = 3u * (uint32_t)sm_count() / L;          // three 512-thread CTAs per SM (64 KB of shared memory each for the tri-plane levels)
     if (const char *e = getenv("B2N_GRID_BWD_SLICES")) slices = (uint32_t)atoi(e);
     const uint32_t cap = ceil_div<uint32_t>(B, 2048);           // at least two rounds of the CTA per slice
     if (slices > cap) slices = cap;
