@@ -90,6 +90,28 @@ void b2n_frame_graph_destroy(b2n_frame_graph *fg);
 /* number of loop iterations executed by the last frame rendered into `workspace` (4-byte read-back; synchronises `stream`) */
 int b2n_frame_iterations(const void *workspace, uint32_t N, int32_t *iterations, void *stream);
 
+/* ---- training: fused head forward that also keeps the activations the backward needs ------------------------------------------------
+ * All buffers fp16, row-major, row pitches padded to a multiple of 8 halves (16 bytes) with zero padding, so they are consumed directly as
+ * operands of b2n_linear_wgrad and of b2n_head_backward.  Every row 0..M-1 is written. */
+typedef struct {
+    void *x36;    /* [M,40]  tri-plane features enc_x (36) + 4 zeros                      (network.py:215-223) */
+    void *ha;     /* [M,64]  relu(aud_ch_att_net.net.0(enc_x)) */
+    void *he;     /* [M,16]  relu(eye_att_net.net.0(enc_x)) */
+    void *hu;     /* [M,32]  relu(unc_net.net.0(enc_x)); NULL when unc_net is not evaluated */
+    void *att;    /* [M,32]  aud_ch_att_net output */
+    void *s_in;   /* [M,72]  sigma_net input [enc_x 36 | enc_a * att 32 | eye * eye_att 1 | 0 0 0]   (network.py:293-298) */
+    void *h1;     /* [M,64]  relu(sigma_net.net.0) */
+    void *h2;     /* [M,64]  relu(sigma_net.net.1) */
+    void *c_in;   /* [M,88]  color_net input [sh 16 | geo_feat 64 | ind_code 4 | 0 0 0 0]            (network.py:267-270) */
+    void *hc;     /* [M,64]  relu(color_net.net.0) */
+    void *misc;   /* [M,8]   sigmoid(rgb logits) x3, eye_att, unc logit, 0 0 0 */
+} b2n_head_saved;
+
+/* b2n_head_forward on all M rows + the saved activations (training forward of NeRFNetwork.forward, network.py:252-311). */
+int b2n_head_forward_train(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code,
+                           const float *eye, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc,
+                           const b2n_head_saved *saved, void *stream);
+
 /* Weight gradient of a bias-free Linear over a tall activation matrix:  dw[out,in] += dy[M,out]^T x[M,in]  (fp16 operands, row-major,
  * fp32 accumulation; dw is accumulated into, zero it first).  1 <= out, in <= 128.  Replaces the weight-gradient GEMM that autograd's
  * LinearBackward runs for every MLP layer of nerf_triplane/network.py:73-94 in a training step (csrc/wgrad.cu). */

@@ -25,6 +25,11 @@ from shencoder import SHEncoder
 from ._lib import lib
 
 
+class _HeadSavedC(ctypes.Structure):
+    """b2n_head_saved (include/b2nerf_fused.h)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("x36", "ha", "he", "hu", "att", "s_in", "h1", "h2", "c_in", "hc", "misc")]
+
+
 class _TallLinear(torch.autograd.Function):
     """y = x W^T for tall activations (M = 10^5..10^6 samples, fan-in / fan-out <= 128) — the shape of every head-MLP layer in a training step.
     Forward and input gradient are plain GEMMs; the WEIGHT gradient dY^T X reduces over M, and the library heuristic runs it as one wave of
@@ -276,6 +281,28 @@ class HeadModel(nn.Module):
                    None if e is None else e.data_ptr(), None if n_valid is None else n_valid.data_ptr(),
                    sig.data_ptr(), rgb.data_ptr(), aud.data_ptr(), eye_o.data_ptr(), unc.data_ptr(), torch.cuda.current_stream().cuda_stream)
         return sig, rgb, aud[:, None], eye_o[:, None], unc[:, None, None]
+
+    # ---- training forward with saved activations (csrc/fused_head.cu, SAVE instantiation) --------------------------------
+    SAVED_WIDTHS = dict(x36=40, ha=64, he=16, hu=32, att=32, s_in=72, h1=64, h2=64, c_in=88, hc=64, misc=8)
+
+    @torch.no_grad()
+    def forward_train_fused(self, x, d, enc_a, c, e):
+        """Fused head on ALL rows of x (no n_valid), keeping the fp16 activations the backward needs.  Call pack() after every weight update.
+        Returns (sigma [M], rgb [M,3], ambient_aud [M], ambient_eye [M], unc [M], saved: dict of fp16 [M, width] tensors)."""
+        M, dev = x.shape[0], x.device
+        x, d = x.float().contiguous(), d.float().contiguous()
+        with_unc = (not self.testing) and self.unc_loss
+        saved = {k: torch.empty(M, w, dtype=torch.float16, device=dev) for k, w in self.SAVED_WIDTHS.items() if k != "hu" or with_unc}
+        sv = _HeadSavedC(*[saved[k].data_ptr() if k in saved else None for k, _ in _HeadSavedC._fields_])
+        sig, rgb = torch.empty(M, device=dev), torch.empty(M, 3, device=dev)
+        aud, eye_o, unc = torch.empty(M, device=dev), torch.empty(M, device=dev), torch.empty(M, device=dev)
+        f = lambda t: None if t is None else t.detach().float().contiguous().view(-1)
+        enc_a, c, e = f(enc_a), f(c), f(e)
+        self._keep_train = (enc_a, c, e, sv)
+        lib().call("b2n_head_forward_train", self.handle, x.data_ptr(), d.data_ptr(), M, enc_a.data_ptr(), None if c is None else c.data_ptr(),
+                   None if e is None else e.data_ptr(), sig.data_ptr(), rgb.data_ptr(), aud.data_ptr(), eye_o.data_ptr(), unc.data_ptr(),
+                   ctypes.byref(sv), torch.cuda.current_stream().cuda_stream)
+        return sig, rgb, aud, eye_o, unc, saved
 
     # ---- whole-frame inference (renderer.py:406-570) ----------------------------------------------------------------------
     @torch.no_grad()

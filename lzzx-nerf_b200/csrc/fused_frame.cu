@@ -23,7 +23,7 @@ struct b2n_model;
 namespace b2n {
 int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
                           const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, cudaStream_t st,
-                          const float *live_deltas = nullptr);
+                          const float *live_deltas = nullptr, const b2n_head_saved *saved = nullptr);
 }
 
 namespace b2n {

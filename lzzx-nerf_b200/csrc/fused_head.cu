@@ -82,7 +82,7 @@ __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
 // (+bias, ReLU) and writes them as halves 0..63 of row `row` of a SWIZZLE_128B tile.  Inlined (the table loads of a gather trip stay in
 // flight across it) but rolled over 32-column blocks to keep the tile loop's code size down.
 template <bool RELU, bool BIAS>
-__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, uint32_t row, const float *bias) {
+__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, uint32_t row, const float *bias, uint4 *save = nullptr) {
 #pragma unroll 1
     for (uint32_t cb = 0; cb < 64; cb += 32) {
         uint32_t acc[32];
@@ -98,6 +98,7 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, u
                 w[j] = RELU ? pack2_relu(x0, x1) : pack2(x0, x1);
             }
             *reinterpret_cast<uint4 *>(tile + sw128_offset(row, (cb >> 3) + c)) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (save) save[(cb >> 3) + c] = make_uint4(w[0], w[1], w[2], w[3]);      // training: the same fp16 row, kept for the backward
         }
     }
 }
@@ -144,7 +145,8 @@ __device__ __forceinline__ float blend4(const float (&v)[4], float fx, float gx,
 }
 // blend + store: levels (2k, 2k+1) of plane p are one packed half2 word (word p*6 + k) of the sample's row; out-of-range planes store 0
 // (gridencoder.cu:98-122).  `row` = the sample's row base inside the X tile, r7 = row index & 7 (SWIZZLE_128B chunk permutation).
-__device__ __forceinline__ void gather_finish(const GatherTrip &G, uint32_t ok, uint8_t *row, uint32_t r7, uint32_t k) {
+__device__ __forceinline__ void gather_finish(const GatherTrip &G, uint32_t ok, uint8_t *row, uint32_t r7, uint32_t k, uint32_t *save_a = nullptr,
+                                              uint32_t *save_b = nullptr) {
     float f[2][3];
 #pragma unroll
     for (uint32_t q = 0; q < 2; q++) {
@@ -157,7 +159,9 @@ __device__ __forceinline__ void gather_finish(const GatherTrip &G, uint32_t ok, 
 #pragma unroll
     for (uint32_t p = 0; p < 3; p++) {
         const uint32_t word = p * 6u + k;
-        *reinterpret_cast<uint32_t *>(row + (((word >> 2) ^ r7) << 4) + (word & 3u) * 4u) = ((ok >> p) & 1u) ? pack2(f[0][p], f[1][p]) : 0u;
+        const uint32_t v = ((ok >> p) & 1u) ? pack2(f[0][p], f[1][p]) : 0u;
+        *reinterpret_cast<uint32_t *>(row + (((word >> 2) ^ r7) << 4) + (word & 3u) * 4u) = v;
+        if (save_a) { save_a[word] = v; save_b[word] = v; }               // training: enc_x also goes to the x36 and sigma-input rows
     }
 }
 
@@ -190,6 +194,7 @@ struct HeadSmem {                       // lives after the 1024-aligned weight i
     HeadLvl lvl[12];
     float enc_a_h[32];                  // fp16-rounded audio code
     float eye_w1[16], unc_w1[32], ind_bias[64];
+    float ind_h[4];                     // fp16-rounded individual code (training: part of the saved color_net input)
     float eye_val;
     uint32_t n_valid;
     uint32_t tmem_base;
@@ -197,6 +202,7 @@ struct HeadSmem {                       // lives after the 1024-aligned weight i
     uint64_t bar_mma[HG_WGS];           // per-warpgroup MMA completion
 };
 
+template <bool SAVE>
 __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_constant__ HeadArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // pointer arithmetic keeps the shared address space visible to the compiler
@@ -232,6 +238,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         S.ind_bias[j] = b;
     }
     if (tid >= 320 && tid < 332) S.lvl[tid - 320] = a.lvl[tid - 320];
+    if (tid >= 332 && tid < 336) S.ind_h[tid - 332] = a.ind_code ? round_h(a.ind_code[tid - 332]) : 0.0f;
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -290,15 +297,18 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         if (live0) { px = __ldcs(a.xyzs + 3 * (size_t)m0); py = __ldcs(a.xyzs + 3 * (size_t)m0 + 1); pz = __ldcs(a.xyzs + 3 * (size_t)m0 + 2); }
         const SampleCoord c = make_coord(px, py, pz, live0);
         GatherTrip GA, GB;                  // two trips in flight
+        uint32_t *xs = SAVE && live0 ? reinterpret_cast<uint32_t *>(a.sv.x36) + (size_t)m0 * 20 : nullptr;
+        uint32_t *ss = SAVE && live0 ? reinterpret_cast<uint32_t *>(a.sv.s_in) + (size_t)m0 * 36 : nullptr;
         gather_issue(GA, t_xy, t_yz, t_xz, &S.lvl[0], c);
 #pragma unroll 1
         for (uint32_t k = 0; k < 6; k += 2) {
             gather_issue(GB, t_xy, t_yz, t_xz, &S.lvl[2 * k + 2], c);
-            gather_finish(GA, c.ok, sXb + row_off, r7, k);
+            gather_finish(GA, c.ok, sXb + row_off, r7, k, xs, ss);
             if (k + 2 < 6) gather_issue(GA, t_xy, t_yz, t_xz, &S.lvl[2 * k + 4], c);
-            gather_finish(GB, c.ok, sXb + row_off, r7, k + 1);
+            gather_finish(GB, c.ok, sXb + row_off, r7, k + 1, xs, ss);
         }
         zero_k_padding(sXb);
+        if (xs) { xs[18] = 0u; xs[19] = 0u; }
     }
     for (; tile < n_tiles; tile += tile_stride) {
         uint8_t *sX = sXb + buf * HG_TILE_BYTES, *sXn = sXb + (buf ^ 1u) * HG_TILE_BYTES;
@@ -317,6 +327,17 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         }
         uint8_t *rown = sXn + row_off;
         GatherTrip G;
+        // training: rows of the saved activations for this tile's sample (m) and for the next tile's sample (features only)
+        const bool sv_on = SAVE && live;
+        uint32_t *xsn = nullptr, *ssn = nullptr;
+        if (SAVE && nlive) {
+            const size_t mn = (size_t)(tile + tile_stride) * HG_TILE + t;
+            xsn = reinterpret_cast<uint32_t *>(a.sv.x36) + mn * 20; ssn = reinterpret_cast<uint32_t *>(a.sv.s_in) + mn * 36;
+            xsn[18] = 0u; xsn[19] = 0u;
+        }
+        uint32_t *s_in_w = sv_on ? reinterpret_cast<uint32_t *>(a.sv.s_in) + (size_t)m * 36 : nullptr;
+        uint4 *c_in_q = sv_on ? reinterpret_cast<uint4 *>(a.sv.c_in) + (size_t)m * 11 : nullptr;
+        float unc_logit = 0.0f;
         publish();
         // ---- P1: [aud hidden | eye hidden | sigma hidden (enc_x part)] = X * WA -------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sX_a, sW_a + HW_A, 3, 144, false); mma_commit(bar); }
@@ -324,12 +345,19 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         mma_done();
         float eye_att, unc_out = 0.6931471805599453f;       // testing: log(1 + e^0) (network.py:245,278)
         {
-            hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr);
+            hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr, sv_on ? reinterpret_cast<uint4 *>(a.sv.ha) + (size_t)m * 8 : nullptr);
             uint32_t e16[16];
             ld16(tmem_ld + TC_EYE, e16); wait_ld();
             float dot = 0.0f;
 #pragma unroll
             for (int j = 0; j < 16; j++) dot = fmaf(fmaxf(round_h(__uint_as_float(e16[j])), 0.0f), S.eye_w1[j], dot);
+            if (sv_on) {
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) w[j] = pack2_relu(__uint_as_float(e16[2 * j]), __uint_as_float(e16[2 * j + 1]));
+                uint4 *q = reinterpret_cast<uint4 *>(a.sv.he) + (size_t)m * 2;
+                q[0] = make_uint4(w[0], w[1], w[2], w[3]); q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
             // sigmoid evaluated on the fp16 logit, result rounded to fp16 (torch.sigmoid on a half tensor)
             eye_att = round_h(1.0f / (1.0f + expf(-round_h(dot))));
         }
@@ -353,7 +381,15 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 32; j++) du = fmaf(fmaxf(round_h(__uint_as_float(acc[j])), 0.0f), S.unc_w1[j], du);
                 du = round_h(du);
+                unc_logit = du;
                 unc_out = logf(1.0f + expf(du));                        // torch.log(1 + torch.exp(.)) in fp32 (network.py:278)
+                if (sv_on && a.sv.hu) {
+                    uint4 *q = reinterpret_cast<uint4 *>(a.sv.hu) + (size_t)m * 4;
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        q[c] = make_uint4(pack2_relu(__uint_as_float(acc[8 * c]), __uint_as_float(acc[8 * c + 1])), pack2_relu(__uint_as_float(acc[8 * c + 2]), __uint_as_float(acc[8 * c + 3])),
+                                          pack2_relu(__uint_as_float(acc[8 * c + 4]), __uint_as_float(acc[8 * c + 5])), pack2_relu(__uint_as_float(acc[8 * c + 6]), __uint_as_float(acc[8 * c + 7])));
+                }
             }
             ld32(tmem_ld + TC_A, acc); wait_ld();
             float n2 = 0.0f;
@@ -371,22 +407,33 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             const float e = a.eye ? S.eye_val * eye_att : 0.0f;                     // e = e * eye_att (network.py:291)
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 4)) = make_uint4(pack2(e, 0.0f), 0u, 0u, 0u);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 5)) = make_uint4(0u, 0u, 0u, 0u);
+            if (sv_on) {
+                uint4 *q = reinterpret_cast<uint4 *>(a.sv.att) + (size_t)m * 4;
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    q[c] = make_uint4(pack2(__uint_as_float(acc[8 * c]), __uint_as_float(acc[8 * c + 1])), pack2(__uint_as_float(acc[8 * c + 2]), __uint_as_float(acc[8 * c + 3])),
+                                      pack2(__uint_as_float(acc[8 * c + 4]), __uint_as_float(acc[8 * c + 5])), pack2(__uint_as_float(acc[8 * c + 6]), __uint_as_float(acc[8 * c + 7])));
+                uint2 *sw = reinterpret_cast<uint2 *>(s_in_w + 18);                  // halves 36..67 = enc_w, 68 = e, 69..71 = 0 (8-byte aligned)
+#pragma unroll
+                for (int j = 0; j < 8; j++) sw[j] = make_uint2(w[2 * j], w[2 * j + 1]);
+                sw[8] = make_uint2(pack2(e, 0.0f), 0u);
+            }
         }
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 0);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 0, xsn, ssn);
         publish();
         // ---- P3: sigma hidden += [enc_w, e] * WC -------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
         if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[2], cn);
         mma_done();
-        hidden_epilogue<true, false>(tmem_ld + TC_S, sH, t, nullptr);
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 1);
+        hidden_epilogue<true, false>(tmem_ld + TC_S, sH, t, nullptr, sv_on ? reinterpret_cast<uint4 *>(a.sv.h1) + (size_t)m * 8 : nullptr);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 1, xsn, ssn);
         publish();
         // ---- P4: sigma layer 1 --------------------------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
         if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[4], cn);
         mma_done();
-        hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr);
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 2);
+        hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr, sv_on ? reinterpret_cast<uint4 *>(a.sv.h2) + (size_t)m * 8 : nullptr);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 2, xsn, ssn);
         publish();
         // ---- P5: sigma layer 2: cols 0..63 = geo_feat, col 64 = density logit (rows rotated at pack time) -----------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
@@ -394,7 +441,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         mma_done();
         float sigma;
         {
-            hidden_epilogue<false, false>(tmem_ld + TC_A, sH, t, nullptr);
+            hidden_epilogue<false, false>(tmem_ld + TC_A, sH, t, nullptr, sv_on ? c_in_q + 2 : nullptr);      // geo_feat = halves 16..79 of the color input
             uint32_t s16[16];
             ld16(tmem_ld + TC_A + 64, s16); wait_ld();
             sigma = expf(round_h(__uint_as_float(s16[0]))) * a.density_scale;       // torch.exp(h[..., 0]) in fp32 (network.py:301)
@@ -406,8 +453,12 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             for (int j = 0; j < 8; j++) w[j] = pack2(shv[2 * j], shv[2 * j + 1]);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+            if (sv_on) {
+                c_in_q[0] = make_uint4(w[0], w[1], w[2], w[3]); c_in_q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                c_in_q[10] = make_uint4(pack2(S.ind_h[0], S.ind_h[1]), pack2(S.ind_h[2], S.ind_h[3]), 0u, 0u);
+            }
         }
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 3);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 3, xsn, ssn);
         publish();
         // ---- P6: color layer 0 = geo * WF0 + sh * WF1 (+ ind-code bias in the epilogue) -------------------------------------
         if (t == 0) {
@@ -418,8 +469,8 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         }
         if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[8], cn);
         mma_done();
-        hidden_epilogue<true, true>(tmem_ld + TC_S, sH, t, S.ind_bias);
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 4);
+        hidden_epilogue<true, true>(tmem_ld + TC_S, sH, t, S.ind_bias, sv_on ? reinterpret_cast<uint4 *>(a.sv.hc) + (size_t)m * 8 : nullptr);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 4, xsn, ssn);
         publish();
         // ---- P7: color layer 1 (N padded 3 -> 16) -----------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_G, 4, 16, false); mma_commit(bar); }
@@ -429,13 +480,15 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             uint32_t c16[16];
             ld16(tmem_ld + TC_A, c16); wait_ld();
             if (live) {
-                float rgb[3];
+                float rgb[3], sg[3];
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
                     // torch.sigmoid(h_color) * (1 + 2*0.001) - 0.001 evaluated on half tensors (network.py:275)
                     const float s = round_h(1.0f / (1.0f + expf(-round_h(__uint_as_float(c16[j])))));
+                    sg[j] = s;
                     rgb[j] = round_h(round_h(s * 1.002f) - 0.001f);
                 }
+                if (SAVE) reinterpret_cast<uint4 *>(a.sv.misc)[m] = make_uint4(pack2(sg[0], sg[1]), pack2(sg[2], eye_att), pack2(unc_logit, 0.0f), 0u);
                 if (a.sigmas) __stcs(a.sigmas + m, sigma);
                 if (a.rgbs) { __stcs(a.rgbs + 3 * (size_t)m, rgb[0]); __stcs(a.rgbs + 3 * (size_t)m + 1, rgb[1]); __stcs(a.rgbs + 3 * (size_t)m + 2, rgb[2]); }
                 if (a.amb_aud) __stcs(a.amb_aud + m, amb_aud);
@@ -443,7 +496,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
                 if (a.unc) __stcs(a.unc + m, unc_out);
             }
         }
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 5);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 5, xsn, ssn);
         buf ^= 1u;
         // the next tile's publish() orders this tile's TMEM reads (fence::before_thread_sync + warpgroup barrier) before its first MMA
     }
@@ -455,16 +508,21 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
 
 size_t head_smem_bytes() { return 1024 + HW_BYTES + (size_t)HG_WGS * 3 * HG_TILE_BYTES + sizeof(HeadSmem); }
 
-int launch_head_forward(const HeadArgs &a, cudaStream_t st) {
+int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save) {
     static bool attr = false;
     const size_t smem = head_smem_bytes();
-    if (!attr) { B2N_CUDA(cudaFuncSetAttribute(k_head_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    if (!attr) {
+        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
     const uint32_t tiles = ceil_div<uint32_t>(a.M, HG_TILE);
     uint32_t ctas = ceil_div<uint32_t>(tiles, HG_WGS);
     const uint32_t sms = (uint32_t)sm_count();
     if (ctas > sms) ctas = sms;
     if (ctas == 0) return 0;
-    k_head_forward<<<ctas, HG_THREADS, smem, st>>>(a);
+    if (save) k_head_forward<true><<<ctas, HG_THREADS, smem, st>>>(a);
+    else k_head_forward<false><<<ctas, HG_THREADS, smem, st>>>(a);
     return check_launch("head_forward");
 }
 
@@ -583,7 +641,7 @@ int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
 namespace b2n {
 int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
                           const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, cudaStream_t st,
-                          const float *live_deltas) {
+                          const float *live_deltas, const b2n_head_saved *saved) {
     B2N_REQUIRE(m && m->ready, "head_forward: model has no weights (call b2n_model_update)");
     B2N_REQUIRE(xyzs && dirs && enc_a, "head_forward: null pointer");
     if (M == 0) return 0;
@@ -602,15 +660,27 @@ int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *di
     a.sigmas = sigmas; a.rgbs = rgbs; a.amb_aud = amb_aud; a.amb_eye = amb_eye; a.unc = unc;
     a.has_unc = m->w.unc_w0 != nullptr;
     a.density_scale = density_scale;
-    return launch_head_forward(a, st);
+    if (saved) {
+        B2N_REQUIRE(!a.has_unc || saved->hu, "head_forward_train: unc_net is packed but saved->hu is NULL");
+        a.sv = *saved;
+    }
+    return launch_head_forward(a, st, saved != nullptr);
 }
 }  // namespace b2n
 
 extern "C" {
 
+int b2n_head_forward_train(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
+                           float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, const b2n_head_saved *saved, void *stream) {
+    B2N_REQUIRE(saved, "head_forward_train: null pointer");
+    B2N_REQUIRE(saved->x36 && saved->ha && saved->he && saved->att && saved->s_in && saved->h1 && saved->h2 && saved->c_in && saved->hc && saved->misc,
+                "head_forward_train: null activation buffer");
+    return head_forward_on_model(m, xyzs, dirs, M, enc_a, ind_code, eye, nullptr, 1.0f, sigmas, rgbs, amb_aud, amb_eye, unc, as_stream(stream), nullptr, saved);
+}
+
 int b2n_head_forward(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
                      const int32_t *n_valid, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, void *stream) {
-    return head_forward_on_model(m, xyzs, dirs, M, enc_a, ind_code, eye, n_valid, 1.0f, sigmas, rgbs, amb_aud, amb_eye, unc, as_stream(stream), nullptr);
+    return head_forward_on_model(m, xyzs, dirs, M, enc_a, ind_code, eye, n_valid, 1.0f, sigmas, rgbs, amb_aud, amb_eye, unc, as_stream(stream), nullptr, nullptr);
 }
 
 }  // extern "C"

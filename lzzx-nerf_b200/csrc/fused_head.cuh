@@ -1,6 +1,7 @@
 // fused_head.cuh — shared constants / argument block of the fused head kernel (fused_head.cu) and its callers.
 #pragma once
 #include "common.cuh"
+#include "../../include/b2nerf_fused.h"
 
 namespace b2n {
 
@@ -52,10 +53,11 @@ struct HeadArgs {
     const float *enc_a, *ind_code, *eye;
     float *sigmas, *rgbs, *amb_aud, *amb_eye, *unc;
     int has_unc;
+    b2n_head_saved sv;          // training forward: where the activations go (used by the SAVE instantiation only)
     float density_scale;
 };
 
 size_t head_smem_bytes();
-int launch_head_forward(const HeadArgs &a, cudaStream_t st);
+int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save = false);
 
 }  // namespace b2n

@@ -232,3 +232,38 @@ def test_linear_wgrad_matches_fp32_matmul(n_out, n_in, M):
         dw2 = torch.zeros(n_out, n_in, device="cuda")
         lib().call("b2n_linear_wgrad", dy.data_ptr(), xo.data_ptr(), M, n_out, n_in, dw2.data_ptr(), torch.cuda.current_stream().cuda_stream)
         assert float((dw2 - (ref - 0.5)).abs().max()) <= 1e-4 * scale + 1e-3
+
+
+def test_head_forward_train_saves_the_reference_activations():
+    """b2n_head_forward_train: same outputs as the inference kernel, and the saved fp16 activations equal the intermediate tensors of the
+    reference graph under autocast (network.py:252-311) up to fp16 rounding of different accumulation orders."""
+    m = _model()
+    m.testing = False                      # unc_net is evaluated (network.py:276-278)
+    m.pack()
+    M = 4096 + 77                          # not a multiple of the 128-sample tile
+    x, d = _samples(M, 9)
+    enc_a = torch.randn(1, 32, device="cuda") * 0.5
+    c, e = m.individual_codes[2:3].detach(), torch.tensor([[0.37]], device="cuda")
+    sig, rgb, aud, eye_o, unc, sv = m.forward_train_fused(x, d, enc_a, c, e)
+    o_sig, o_rgb, o_aud, o_eye, o_unc = m(x, d, enc_a, c, e)
+    assert torch.equal(sig, o_sig) and torch.equal(rgb, o_rgb) and torch.equal(aud, o_aud.view(-1)) and torch.equal(eye_o, o_eye.view(-1)) and torch.equal(unc, o_unc.view(-1))
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        enc_x = m.encode_x(x)
+        ha = torch.relu(m.aud_ch_att_net.net[0](enc_x)); att = m.aud_ch_att_net.net[1](ha)
+        he = torch.relu(m.eye_att_net.net[0](enc_x)); eye_att = torch.sigmoid(m.eye_att_net.net[1](he))
+        hu = torch.relu(m.unc_net.net[0](enc_x)); ul = m.unc_net.net[1](hu)
+        s_in = torch.cat([enc_x, enc_a.repeat(M, 1) * att, e * eye_att], dim=-1)
+        h1 = torch.relu(m.sigma_net.net[0](s_in)); h2 = torch.relu(m.sigma_net.net[1](h1)); o = m.sigma_net.net[2](h2)
+        c_in = torch.cat([m.encoder_dir(d), o[..., 1:], c.repeat(M, 1)], dim=-1)
+        hc = torch.relu(m.color_net.net[0](c_in)); s3 = torch.sigmoid(m.color_net.net[1](hc))
+    def close(name, got, want, atol):
+        got, want = got.float(), want.float()
+        err = float((got - want).abs().max())
+        assert err <= atol, (name, err)
+    close("x36", sv["x36"][:, :36], enc_x, 2e-3)
+    assert float(sv["x36"][:, 36:].abs().max()) == 0 and float(sv["s_in"][:, 69:].abs().max()) == 0 and float(sv["c_in"][:, 84:].abs().max()) == 0
+    close("ha", sv["ha"], ha, 1e-2); close("he", sv["he"], he, 1e-2); close("hu", sv["hu"], hu, 1e-2); close("att", sv["att"], att, 1e-2)
+    close("s_in", sv["s_in"][:, :69], s_in, 1e-2)
+    close("h1", sv["h1"], h1, 2e-2); close("h2", sv["h2"], h2, 2e-2)
+    close("c_in", sv["c_in"][:, :84], c_in, 3e-2); close("hc", sv["hc"], hc, 3e-2)
+    close("misc rgb", sv["misc"][:, :3], s3, 1e-2); close("misc eye", sv["misc"][:, 3:4], eye_att, 5e-3); close("misc unc", sv["misc"][:, 4:5], ul, 1e-2)
