@@ -112,6 +112,32 @@ int b2n_head_forward_train(const b2n_model *m, const float *xyzs, const float *d
                            const float *eye, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc,
                            const b2n_head_saved *saved, void *stream);
 
+/* fp16 per-sample gradients produced by b2n_head_backward (same row pitches / zero padding as b2n_head_saved): each is the "dY" operand of one
+ * b2n_linear_wgrad call whose "X" operand is a saved activation. */
+typedef struct {
+    void *d_rl;       /* [M,8]   d rgb logits (3)                                   dW color_net.1  = d_rl^T  hc   */
+    void *d_hc;       /* [M,64]  d color hidden (pre-ReLU)                          dW color_net.0  = d_hc^T  c_in */
+    void *d_o;        /* [M,72]  d sigma_net output, ROTATED [geo_feat 64 | density logit | 0 x7]   dW sigma_net.2 (rows rotated) = d_o^T h2 */
+    void *d_h2;       /* [M,64]                                                     dW sigma_net.1  = d_h2^T  h1   */
+    void *d_h1;       /* [M,64]                                                     dW sigma_net.0  = d_h1^T  s_in */
+    void *d_ew;       /* [M,32]  d (enc_a * att): d enc_a = sum_m d_ew * att */
+    void *d_att;      /* [M,32]                                                     dW aud_att.1    = d_att^T ha   */
+    void *d_ha;       /* [M,64]                                                     dW aud_att.0    = d_ha^T  x36  */
+    void *d_el;       /* [M,8]   d eye logit (col 0), d e (col 1)                    dW eye_att.1    = d_el^T  he   */
+    void *d_he;       /* [M,16]                                                     dW eye_att.0    = d_he^T  x36  */
+    void *d_ul;       /* [M,8]   d unc logit (col 0); NULL without unc_net           dW unc_net.1    = d_ul^T  hu   */
+    void *d_hu;       /* [M,32]  NULL without unc_net                                dW unc_net.0    = d_hu^T  x36  */
+    void *d_ci;       /* [M,8]   d of the ind-code columns of the color input (4): d ind_code = sum_m d_ci */
+    float *d_planes;  /* fp32 [3][12][M]: d enc_x in the layout of grid_encode_backward's `grad` ([L,B,1] per plane: xy, yz, xz) */
+} b2n_head_grads;
+
+/* Backward-data pass of the head network (network.py:252-311 through autograd) in one kernel: consumes the gradients of the five outputs
+ * (any may be NULL = zero) and the activations kept by b2n_head_forward_train, produces b2n_head_grads.  `sigmas` / `amb_aud` are the
+ * forward's outputs. */
+int b2n_head_backward(const b2n_model *m, uint32_t M, const float *enc_a, const float *eye, const b2n_head_saved *saved, const float *sigmas,
+                      const float *amb_aud, const float *g_sigma, const float *g_rgb, const float *g_aud, const float *g_eye, const float *g_unc,
+                      const b2n_head_grads *grads, void *stream);
+
 /* Weight gradient of a bias-free Linear over a tall activation matrix:  dw[out,in] += dy[M,out]^T x[M,in]  (fp16 operands, row-major,
  * fp32 accumulation; dw is accumulated into, zero it first).  1 <= out, in <= 128.  Replaces the weight-gradient GEMM that autograd's
  * LinearBackward runs for every MLP layer of nerf_triplane/network.py:73-94 in a training step (csrc/wgrad.cu). */

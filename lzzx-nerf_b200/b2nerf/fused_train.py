@@ -1,0 +1,106 @@
+"""Training path of the head network on the fused kernels: forward = k_head_forward<SAVE> (csrc/fused_head.cu), backward = k_head_backward
+(csrc/fused_head_bwd.cu) + one b2n_linear_wgrad per weight matrix (csrc/wgrad.cu) + the grid backward fed in its own layout.
+
+Replaces, inside autograd, the graph NeRFNetwork.forward builds under autocast (network.py:215-311): three GridEncoder calls, eleven
+nn.Linear (+ two for unc_net), SHEncoder, cat / repeat / relu / sigmoid / exp / norm — ~500 kernels per step in the reference-style path
+(profiles/r1_train_step.md).  Numerics: autocast semantics (fp16 operands and activations, fp32 accumulation)."""
+import ctypes
+import math
+
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from gridencoder.backend import _backend as _grid_backend
+
+from ._lib import lib
+
+
+class _GradsC(ctypes.Structure):
+    """b2n_head_grads (include/b2nerf_fused.h)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("d_rl", "d_hc", "d_o", "d_h2", "d_h1", "d_ew", "d_att", "d_ha", "d_el", "d_he", "d_ul", "d_hu", "d_ci", "d_planes")]
+
+
+GRAD_WIDTHS = dict(d_rl=8, d_hc=64, d_o=72, d_h2=64, d_h1=64, d_ew=32, d_att=32, d_ha=64, d_el=8, d_he=16, d_ul=8, d_hu=32, d_ci=8)
+
+
+def head_parameters(model):
+    """The parameters the fused Function differentiates, in the order its backward returns their gradients."""
+    return [model.encoder_xy.embeddings, model.encoder_yz.embeddings, model.encoder_xz.embeddings,
+            model.aud_ch_att_net.net[0].weight, model.aud_ch_att_net.net[1].weight, model.eye_att_net.net[0].weight, model.eye_att_net.net[1].weight,
+            model.sigma_net.net[0].weight, model.sigma_net.net[1].weight, model.sigma_net.net[2].weight,
+            model.color_net.net[0].weight, model.color_net.net[1].weight, model.unc_net.net[0].weight, model.unc_net.net[1].weight]
+
+
+def _wgrad(dy, x):
+    """fp32 [dy.shape[1], x.shape[1]] = dy^T x over all rows (b2n_linear_wgrad)."""
+    out = torch.zeros(dy.shape[1], x.shape[1], dtype=torch.float32, device=x.device)
+    lib().call("b2n_linear_wgrad", dy.data_ptr(), x.data_ptr(), x.shape[0], dy.shape[1], x.shape[1], out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+class _FusedHead(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, model, x, d, enc_a, ind_code, eye, *params):
+        sig, rgb, aud, eye_att, unc, saved = model.forward_train_fused(x, d, enc_a, ind_code, eye)
+        ctx.model, ctx.saved_acts = model, saved
+        ctx.with_unc = "hu" in saved
+        ctx.save_for_backward(x, enc_a, eye if eye is not None else torch.zeros(1, device=x.device), sig, aud)
+        ctx.has_eye = eye is not None
+        ctx.mark_non_differentiable()
+        return sig, rgb, aud, eye_att, unc
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g_sig, g_rgb, g_aud, g_eye, g_unc):
+        m, sv = ctx.model, ctx.saved_acts
+        x, enc_a, eye, sig, aud = ctx.saved_tensors
+        M, dev = x.shape[0], x.device
+        f32 = lambda t: None if t is None else t.float().contiguous()
+        g_sig, g_rgb, g_aud, g_eye, g_unc = f32(g_sig), f32(g_rgb), f32(g_aud), f32(g_eye), f32(g_unc)
+        gr = {k: torch.empty(M, w, dtype=torch.float16, device=dev) for k, w in GRAD_WIDTHS.items() if ctx.with_unc or k not in ("d_ul", "d_hu")}
+        planes = torch.empty(3, 12, M, dtype=torch.float32, device=dev)
+        gc = _GradsC(*[(gr[k].data_ptr() if k in gr else None) for k, _ in _GradsC._fields_[:-1]], planes.data_ptr())
+        from .model import _HeadSavedC
+        sc = _HeadSavedC(*[sv[k].data_ptr() if k in sv else None for k, _ in _HeadSavedC._fields_])
+        p = lambda t: None if t is None else t.data_ptr()
+        enc_a_flat = enc_a.contiguous().view(-1)
+        lib().call("b2n_head_backward", m.handle, M, enc_a_flat.data_ptr(), eye.data_ptr() if ctx.has_eye else None, ctypes.byref(sc), sig.data_ptr(),
+                   aud.data_ptr(), p(g_sig), p(g_rgb), p(g_aud), p(g_eye), p(g_unc), ctypes.byref(gc), torch.cuda.current_stream().cuda_stream)
+        # weight gradients: one pass over (dY, X) per matrix
+        d_c1 = _wgrad(gr["d_rl"], sv["hc"])[:3]
+        d_c0 = _wgrad(gr["d_hc"], sv["c_in"])[:, :84]
+        rot = _wgrad(gr["d_o"], sv["h2"])                               # rows: geo_feat 0..63, density logit 64
+        d_s2 = torch.cat([rot[64:65], rot[:64]], dim=0)
+        d_s1 = _wgrad(gr["d_h2"], sv["h1"])
+        d_s0 = _wgrad(gr["d_h1"], sv["s_in"])[:, :69]
+        d_a1 = _wgrad(gr["d_att"], sv["ha"])
+        d_a0 = _wgrad(gr["d_ha"], sv["x36"])[:, :36]
+        d_e1 = _wgrad(gr["d_el"], sv["he"])[:1]
+        d_e0 = _wgrad(gr["d_he"], sv["x36"])[:, :36]
+        if ctx.with_unc:
+            d_u1 = _wgrad(gr["d_ul"], sv["hu"])[:1]
+            d_u0 = _wgrad(gr["d_hu"], sv["x36"])[:, :36]
+        else:
+            d_u0 = d_u1 = None
+        # table gradients: d enc_x is already in the grid backward's [L, B, C] layout, one slab per plane (xy, yz, xz: network.py:208-212)
+        u = (x + m.bound) / (2 * m.bound)
+        enc = m.encoder_xy
+        S, H = float(math.log2(enc.per_level_scale)), enc.base_resolution
+        d_tabs = []
+        for pl, cols, e_mod in ((0, [0, 1], m.encoder_xy), (1, [1, 2], m.encoder_yz), (2, [0, 2], m.encoder_xz)):
+            ge = torch.zeros_like(e_mod.embeddings)
+            _grid_backend.grid_encode_backward(planes[pl].view(12, M, 1), u[:, cols].contiguous(), e_mod.embeddings, e_mod.offsets, ge, M, 2, 1, 12, S, H,
+                                               None, None, 0, False)
+            d_tabs.append(ge)
+        d_enc_a = (gr["d_ew"].float() * sv["att"].float()).sum(0).view_as(enc_a)
+        d_ind = gr["d_ci"][:, :4].float().sum(0)
+        c = lambda t: None if t is None else t.contiguous()
+        return (None, None, None, d_enc_a, d_ind, None, d_tabs[0], d_tabs[1], d_tabs[2], c(d_a0), c(d_a1), c(d_e0), c(d_e1), c(d_s0), c(d_s1), c(d_s2),
+                c(d_c0), c(d_c1), c(d_u0), c(d_u1))
+
+
+def fused_head_train(model, x, d, enc_a, ind_code, eye):
+    """Drop-in for HeadModel.forward_unfused in a training step: (sigma [M], color [M,3], ambient_aud [M,1], ambient_eye [M,1], unc [M,1,1])."""
+    sig, rgb, aud, eye_att, unc = _FusedHead.apply(model, x, d, enc_a, ind_code.view(-1), eye, *head_parameters(model))
+    return sig, rgb, aud[:, None], eye_att[:, None], unc[:, None, None]

@@ -20,8 +20,9 @@ from .model import HeadModel
 
 
 class Trainer:
-    def __init__(self, model: HeadModel, lr=1e-2, lr_net=1e-3, fp16=True, max_steps=16, dt_gamma=1.0 / 256, min_near=0.05, lambda_amb=1e-4, fused_optimizer=True):
+    def __init__(self, model: HeadModel, lr=1e-2, lr_net=1e-3, fp16=True, max_steps=16, dt_gamma=1.0 / 256, min_near=0.05, lambda_amb=1e-4, fused_optimizer=True, fused_head=False):
         self.m = model
+        self.fused_head = fused_head
         self.fp16, self.max_steps, self.dt_gamma, self.min_near, self.lambda_amb = fp16, max_steps, dt_gamma, min_near, lambda_amb
         enc = [model.encoder_xy.embeddings, model.encoder_yz.embeddings, model.encoder_xz.embeddings]
         enc_ids = {id(p) for p in enc}
@@ -57,7 +58,12 @@ class Trainer:
         xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, m.bound, m.density_bitfield, m.cascade, m.grid_size, nears, fars, counter,
                                                                 self.mean_count if mean_count is None else mean_count, perturb, 128, False, self.dt_gamma,
                                                                 self.max_steps)
-        sigmas, rgbs, amb_aud, amb_eye, unc = m.forward_unfused(xyzs, dirs, enc_a, ind_code, eye)
+        if self.fused_head:
+            from .fused_train import fused_head_train
+            m.pack()                                   # the optimizer moved the weights: refresh the operand images (three small kernels)
+            sigmas, rgbs, amb_aud, amb_eye, unc = fused_head_train(m, xyzs, dirs, enc_a, ind_code, eye)
+        else:
+            sigmas, rgbs, amb_aud, amb_eye, unc = m.forward_unfused(xyzs, dirs, enc_a, ind_code, eye)
         ws, aud_sum, eye_sum, unc_sum, depth, image = raymarching.composite_rays_train_triplane(
             sigmas, rgbs, amb_aud.abs().sum(-1), amb_eye.abs().sum(-1), unc, deltas, rays)
         image = (image + (1 - ws).unsqueeze(-1) * bg_color).clamp(0, 1)

@@ -28,7 +28,8 @@ using namespace tc5;
 // ---------------------------------------------------------------------------------------------------
 // weight packing: fp32 nn.Linear weights [out,in] -> fp16 SWIZZLE_128B K-major image (+ small fp32 vectors)
 // ---------------------------------------------------------------------------------------------------
-struct PackRegion { const float *src; uint32_t byte_off, rows, src_rows, ld, col0, kvalid, row_shift; };
+struct PackRegion { const float *src; uint32_t byte_off, rows, src_rows, ld, col0, kvalid, row_shift, tr, k0; };
+// tr = 1: transposed region, value(row n, k) = src[(k0 + k) * ld + col0 + n] for n < src_rows, k < kvalid
 struct PackArgs { PackRegion r[12]; uint32_t n; };
 
 __global__ void __launch_bounds__(256) k_pack_head(const __grid_constant__ PackArgs pa, uint8_t *__restrict__ img) {
@@ -45,7 +46,8 @@ __global__ void __launch_bounds__(256) k_pack_head(const __grid_constant__ PackA
 #pragma unroll
             for (uint32_t k = 0; k < 8; k++) {
                 const uint32_t kk = c * 8u + k;
-                const float v = (g.src && row < g.src_rows && kk < g.kvalid) ? g.src[(size_t)srow * g.ld + g.col0 + kk] : 0.0f;
+                float v = 0.0f;
+                if (g.src && row < g.src_rows && kk < g.kvalid) v = g.tr ? g.src[(size_t)(g.k0 + kk) * g.ld + g.col0 + row] : g.src[(size_t)srow * g.ld + g.col0 + kk];
                 h[k] = __float2half_rn(v);
             }
             *reinterpret_cast<uint4 *>(img + g.byte_off + sw128_offset(row, c)) = *reinterpret_cast<uint4 *>(h);
@@ -56,12 +58,14 @@ __global__ void __launch_bounds__(256) k_pack_head(const __grid_constant__ PackA
 }
 
 // small vectors: eye_w1[16], unc_w1[32], color ind part [64][4] — stored as fp32 values already rounded to fp16
-__global__ void k_pack_small(const float *__restrict__ eye_w1, const float *__restrict__ unc_w1, const float *__restrict__ color_w0, float *__restrict__ out) {
+__global__ void k_pack_small(const float *__restrict__ eye_w1, const float *__restrict__ unc_w1, const float *__restrict__ color_w0,
+                             const float *__restrict__ color_w1, float *__restrict__ out) {
     const uint32_t t = threadIdx.x;
     auto rh = [](float v) { return __half2float(__float2half_rn(v)); };
     if (t < 16) out[HS_EYE_W1 + t] = rh(eye_w1[t]);
     if (t < 32) out[HS_UNC_W1 + t] = unc_w1 ? rh(unc_w1[t]) : 0.0f;
     for (uint32_t i = t; i < 256; i += blockDim.x) out[HS_IND_W + i] = rh(color_w0[(i >> 2) * 84 + 80 + (i & 3)]);
+    for (uint32_t i = t; i < 192; i += blockDim.x) out[HS_C1W + i] = rh(color_w1[i]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -533,18 +537,6 @@ int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save) {
 // ---------------------------------------------------------------------------------------------------
 using namespace b2n;
 
-struct b2n_model {
-    uint8_t *wimg = nullptr;       // HW_BYTES
-    float *wsmall = nullptr;       // HS_FLOATS (+ 12 floats of scratch for the device-computed level scales)
-    b2n_head_weights w = {};
-    HeadLvl lvl[12] = {};
-    // geometry the cached lvl[] was derived from (re-derived only when it changes: one small D2H read + sync)
-    const int32_t *geo_offsets = nullptr;
-    float geo_S = 0.0f;
-    uint32_t geo_H = 0;
-    bool ready = false;
-};
-
 namespace b2n { __global__ void k_level_scales(float S, uint32_t H, uint32_t L, float *__restrict__ out); }
 
 // Derive the 12 per-level constants.  Reads offsets[13] and the device-computed scales back to the host (synchronises `st`);
@@ -583,9 +575,11 @@ int b2n_model_create(b2n_model **out, void *stream) {
     (void)stream;
     B2N_REQUIRE(out, "model_create: null pointer");
     b2n_model *m = new b2n_model();
-    if (cudaMalloc(&m->wimg, HW_BYTES) != cudaSuccess || cudaMalloc(&m->wsmall, sizeof(float) * (HS_FLOATS + 16)) != cudaSuccess) {
+    if (cudaMalloc(&m->wimg, HW_BYTES) != cudaSuccess || cudaMalloc(&m->wimg_t, HT_BYTES) != cudaSuccess ||
+        cudaMalloc(&m->wsmall, sizeof(float) * (HS_FLOATS + 16)) != cudaSuccess) {
         (void)cudaGetLastError();
         if (m->wimg) cudaFree(m->wimg);
+        if (m->wimg_t) cudaFree(m->wimg_t);
         delete m;
         set_error("model_create: device allocation failed");
         return 3;
@@ -597,6 +591,7 @@ int b2n_model_create(b2n_model **out, void *stream) {
 void b2n_model_destroy(b2n_model *m) {
     if (!m) return;
     cudaFree(m->wimg);
+    cudaFree(m->wimg_t);
     cudaFree(m->wsmall);
     delete m;
 }
@@ -610,7 +605,7 @@ int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
     PackArgs pa = {};
     uint32_t n = 0;
     auto add = [&](const float *src, uint32_t off, uint32_t rows, uint32_t src_rows, uint32_t ld, uint32_t col0, uint32_t kvalid, uint32_t shift) {
-        pa.r[n++] = PackRegion{src, off, rows, src_rows, ld, col0, kvalid, shift};
+        pa.r[n++] = PackRegion{src, off, rows, src_rows, ld, col0, kvalid, shift, 0, 0};
     };
     add(w->aud_att_w0, HW_A, 64, 64, 36, 0, 36, 0);
     add(w->eye_att_w0, HW_A + 64 * 128, 16, 16, 36, 0, 36, 0);
@@ -629,8 +624,28 @@ int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
         if (int rc = derive_levels(m, w, st)) return rc;
     k_pack_head<<<ceil_div<uint32_t>(HW_BYTES / 16, 256), 256, 0, st>>>(pa, m->wimg);
     if (check_launch("model_update(pack)")) return 1;
-    k_pack_small<<<1, 256, 0, st>>>(w->eye_att_w1, w->unc_w1, w->color_w0, m->wsmall);
+    k_pack_small<<<1, 256, 0, st>>>(w->eye_att_w1, w->unc_w1, w->color_w0, w->color_w1, m->wsmall);
     if (check_launch("model_update(small)")) return 1;
+    {   // transposed image for the backward-data kernel
+        PackArgs pt = {};
+        uint32_t k = 0;
+        auto addt = [&](const float *src, uint32_t off, uint32_t rows, uint32_t nvalid, uint32_t ld, uint32_t col0, uint32_t kvalid, uint32_t k0) {
+            pt.r[k++] = PackRegion{src, off, rows, nvalid, ld, col0, kvalid, 0, 1, k0};
+        };
+        addt(w->color_w0, HT_C0G, 64, 64, 84, 16, 64, 0);
+        addt(w->color_w0, HT_C0I, 16, 4, 84, 80, 64, 0);
+        addt(w->sigma_w2, HT_S2A, 64, 64, 64, 0, 64, 1);
+        addt(w->sigma_w2, HT_S2B, 64, 64, 64, 0, 1, 0);
+        addt(w->sigma_w1, HT_S1, 64, 64, 64, 0, 64, 0);
+        addt(w->sigma_w0, HT_S0X, 48, 36, 69, 0, 64, 0);
+        addt(w->sigma_w0, HT_S0W, 48, 33, 69, 36, 64, 0);
+        addt(w->aud_att_w1, HT_A1, 64, 64, 64, 0, 32, 0);
+        addt(w->aud_att_w0, HT_A0, 48, 36, 36, 0, 64, 0);
+        addt(w->eye_att_w0, HT_E0, 48, 36, 36, 0, 16, 0);
+        pt.n = k;
+        k_pack_head<<<ceil_div<uint32_t>(HT_BYTES / 16, 256), 256, 0, st>>>(pt, m->wimg_t);
+        if (check_launch("model_update(pack transposed)")) return 1;
+    }
     m->w = *w;
     m->ready = true;
     return 0;

@@ -29,7 +29,23 @@ constexpr uint32_t HW_BYTES = HW_G + 16 * 128;      // 71 680 B
 static_assert(HW_U % 1024 == 0 && HW_B % 1024 == 0 && HW_C % 1024 == 0 && HW_D % 1024 == 0 && HW_E % 1024 == 0 && HW_F0 % 1024 == 0 && HW_F1 % 1024 == 0 && HW_G % 1024 == 0, "atoms must be 1024 B aligned");
 
 // small fp32 vectors (values pre-rounded to fp16)
-constexpr uint32_t HS_EYE_W1 = 0, HS_UNC_W1 = 16, HS_IND_W = 48, HS_FLOATS = 48 + 256;
+constexpr uint32_t HS_EYE_W1 = 0, HS_UNC_W1 = 16, HS_IND_W = 48, HS_C1W = 48 + 256, HS_FLOATS = 48 + 256 + 192;     // HS_C1W: color_net.net.1 [3][64] (backward)
+
+// TRANSPOSED fp16 weight image for the backward-data kernel (fused_head_bwd.cu): dX = dY W needs B = W^T as [N = fan-in rows] x [K = fan-out]
+// K-major SWIZZLE_128B atoms
+constexpr uint32_t HT_C0G = 0;                      //  64 rows: color0[:, 16:80]^T   (d geo_feat    <- d color hidden)
+constexpr uint32_t HT_C0I = HT_C0G + 64 * 128;      //  16 rows: color0[:, 80:84]^T   (d ind_code part, 4 valid)
+constexpr uint32_t HT_S2A = HT_C0I + 16 * 128;      //  64 rows: sigma2[1:65, :]^T    (K = geo_feat index)
+constexpr uint32_t HT_S2B = HT_S2A + 64 * 128;      //  64 rows: sigma2[0:1, :]^T     (K = density logit, 1 valid column)
+constexpr uint32_t HT_S1 = HT_S2B + 64 * 128;       //  64 rows: sigma1^T
+constexpr uint32_t HT_S0X = HT_S1 + 64 * 128;       //  48 rows: sigma0[:, 0:36]^T    (d enc_x, 36 valid)
+constexpr uint32_t HT_S0W = HT_S0X + 48 * 128;      //  48 rows: sigma0[:, 36:69]^T   (d [enc_w, e], 33 valid)
+constexpr uint32_t HT_A1 = HT_S0W + 48 * 128;       //  64 rows: aud_att1^T           (K = 32)
+constexpr uint32_t HT_A0 = HT_A1 + 64 * 128;        //  48 rows: aud_att0^T           (36 valid)
+constexpr uint32_t HT_E0 = HT_A0 + 48 * 128;        //  48 rows: eye_att0^T           (36 valid, K = 16)
+constexpr uint32_t HT_BYTES = HT_E0 + 48 * 128;     // 67 584 B
+static_assert(HT_C0I % 1024 == 0 && HT_S2A % 1024 == 0 && HT_S2B % 1024 == 0 && HT_S1 % 1024 == 0 && HT_S0X % 1024 == 0 && HT_S0W % 1024 == 0 &&
+              HT_A1 % 1024 == 0 && HT_A0 % 1024 == 0 && HT_E0 % 1024 == 0, "atoms must be 1024 B aligned");
 
 // per-level constants of the (shared) tri-plane geometry, precomputed at b2n_model_update
 struct HeadLvl {
@@ -56,6 +72,24 @@ struct HeadArgs {
     b2n_head_saved sv;          // training forward: where the activations go (used by the SAVE instantiation only)
     float density_scale;
 };
+
+}  // namespace b2n
+
+// the packed model behind the opaque C handle
+struct b2n_model {
+    uint8_t *wimg = nullptr;       // HW_BYTES   forward operand image
+    uint8_t *wimg_t = nullptr;     // HT_BYTES   transposed image (backward-data)
+    float *wsmall = nullptr;       // HS_FLOATS (+ 16 floats of scratch for the device-computed level scales)
+    b2n_head_weights w = {};
+    b2n::HeadLvl lvl[12] = {};
+    // geometry the cached lvl[] was derived from (re-derived only when it changes: one small D2H read + sync)
+    const int32_t *geo_offsets = nullptr;
+    float geo_S = 0.0f;
+    uint32_t geo_H = 0;
+    bool ready = false;
+};
+
+namespace b2n {
 
 size_t head_smem_bytes();
 int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save = false);

@@ -157,3 +157,60 @@ def test_flat_adamw_matches_torch_adamw():
     assert float(opt.step_count) == 5.0
     for p, q in zip(a0 + a1, b0 + b1):
         assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), float((p - q).abs().max())
+
+
+def test_fused_head_gradients_match_autograd_under_autocast():
+    """fused_head_train (forward with saved activations + backward-data kernel + weight-gradient kernel + grid backward) vs autograd through
+    forward_unfused under autocast(fp16) on the same samples and the same upstream gradients.  Both sides round activations / gradients to fp16
+    between layers in slightly different places: tolerance 4e-2 of each gradient's max (2e-2 typical), outputs 1e-2."""
+    import copy
+    from b2nerf.model import HeadModel, MLP
+    from b2nerf.fused_train import fused_head_train, head_parameters
+    torch.manual_seed(5)
+    m = HeadModel(audio_in_dim=29).cuda()
+    for enc in (m.encoder_xy, m.encoder_yz, m.encoder_xz):
+        enc.embeddings.data.uniform_(-0.5, 0.5)
+    m.testing = False
+    m2 = copy.deepcopy(m)
+    M = 20000 + 37
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = (torch.rand(M, 3, device="cuda", generator=g) * 2 - 1) * torch.tensor([1.0, 0.5, 1.0], device="cuda")
+    d = torch.nn.functional.normalize(torch.randn(M, 3, device="cuda", generator=g), dim=1)
+    enc_a0 = (torch.randn(1, 32, device="cuda", generator=g) * 0.5)
+    eye = torch.tensor([[0.4]], device="cuda")
+    ups = [torch.randn(M, device="cuda", generator=g) * 0.1, torch.randn(M, 3, device="cuda", generator=g), torch.randn(M, 1, device="cuda", generator=g) * 0.1,
+           torch.randn(M, 1, device="cuda", generator=g) * 0.1, torch.randn(M, 1, 1, device="cuda", generator=g) * 0.1]
+    results = []
+    for model, fused in ((m, True), (m2, False)):
+        enc_a = enc_a0.clone().requires_grad_(True)
+        ind = model.individual_codes
+        with torch.autocast("cuda", dtype=torch.float16):
+            if fused:
+                model.pack()
+                outs = fused_head_train(model, x, d, enc_a, ind[3], eye)
+            else:
+                MLP.tall_linear = False
+                try:
+                    outs = model.forward_unfused(x, d, enc_a, ind[3], eye)
+                finally:
+                    MLP.tall_linear = True
+            loss = sum((o.float() * u).sum() for o, u in zip(outs, ups))
+        loss.backward()
+        grads = {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+        grads["enc_a"] = enc_a.grad.detach().float().clone()
+        results.append(([o.detach().float() for o in outs], grads))
+    (o_f, g_f), (o_r, g_r) = results
+    for a, b, name in zip(o_f, o_r, ("sigma", "rgb", "amb_aud", "amb_eye", "unc")):
+        assert a.shape == b.shape, (name, a.shape, b.shape)
+        rel = float((a - b).abs().max()) / (float(b.abs().max()) + 1e-6)
+        assert rel < 1e-2, (name, rel)
+    assert set(g_r) <= set(g_f) | {"audio_net", "audio_att_net"}, set(g_r) - set(g_f)
+    worst = {}
+    for n, gr_ in g_r.items():
+        if n not in g_f:
+            continue
+        denom = float(gr_.abs().max()) + 1e-12
+        worst[n] = float((g_f[n] - gr_).abs().max()) / denom
+    bad = {k: v for k, v in worst.items() if v > 4e-2}
+    assert not bad, (bad, worst)
+    assert len(worst) >= 14, worst
