@@ -197,7 +197,7 @@ def head_kernel_profile(model, renderer, frames, auds, n_frames, repeats=5):
     return total_ms, launches, samples
 
 
-def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536, eager=False):
+def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536, eager=False, fused_head=True):
     """BASELINE configs[2]/[4]: data-parallel training step, 65 536 rays per GPU, synthetic audio window (AudioNet + AudioAttNet), grid backward,
     AdamW; gradients all-reduced once per step over the flat buffer when world > 1.  Returns a dict (rays/s over all ranks)."""
     from b2nerf import scene
@@ -205,7 +205,7 @@ def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536
     model = build_model(dev)
     model.testing = False
     model.density_bitfield.copy_(torch.from_numpy(bitfield).to(dev))
-    tr = Trainer(model, fp16=True)
+    tr = Trainer(model, fp16=True, fused_head=fused_head)
     batches = []
     for s in range(4):
         o, d = scene.train_rays(step=rank * 100 + s, n=n_rays)
@@ -237,7 +237,8 @@ def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536
     return {"metric": "train_rays_per_sec", "value": world * steps * n_rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": n_rays,
             "samples_per_step_buffer": int(m_buf), "loss": float(loss), "grad_allreduce_bytes": tr.grads.nbytes() if world > 1 else 0,
             "path": ("eager: " if eager else "forward + backward + all-reduce replayed from one CUDA graph: ") +
-                    "drop-in ops + torch autograd (MLPs via cuBLAS under autocast fp16), fused AdamW, flat-buffer NCCL all-reduce"}
+                    ("march / composite ops + fused head forward (activations kept) + fused head backward-data + tcgen05 weight-gradient kernel + privatised grid backward"
+                     if fused_head else "drop-in ops + torch autograd (MLPs via cuBLAS under autocast fp16)") + ", flat AdamW, flat-buffer NCCL all-reduce"}
 
 
 def run_gpu_arm(args, rank, world, local_rank):
@@ -297,7 +298,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     e2e_ms, _ = timed(lambda s: pipe.submit_host(host_o[s % POOL], host_d[s % POOL], host_a[s % POOL], out_hosts[s % pipe.depth]), args.steps, args.warmup)
     train_info = None
     if not args.no_train:
-        train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(4, min(args.steps, 20)), warmup=max(args.warmup, 18), eager=args.train_eager)
+        train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(4, min(args.steps, 20)), warmup=max(args.warmup, 18), eager=args.train_eager, fused_head=not args.train_unfused)
     if rank != 0:
         return
     img = out_host.numpy()
@@ -354,6 +355,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     ap.add_argument("--train-eager", action="store_true", help="training leg without the CUDA graph")
+    ap.add_argument("--train-unfused", action="store_true", help="training leg through torch autograd over the per-op kernels instead of the fused head kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2nerf" else args.warmup
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

@@ -14,7 +14,7 @@ from b2nerf.train import Trainer
 dev = torch.device("cuda")
 model = bench.build_model(dev); model.testing = False
 model.density_bitfield.copy_(torch.from_numpy(scene.bitfield_from_grid(scene.density_grid())).to(dev))
-tr = Trainer(model, fp16=True)
+tr = Trainer(model, fp16=True, fused_head="--unfused" not in sys.argv)
 n = 65536
 batches = []
 for s in range(4):
