@@ -88,9 +88,10 @@ class _FusedHead(torch.autograd.Function):
         enc = m.encoder_xy
         S, H = float(math.log2(enc.per_level_scale)), enc.base_resolution
         d_tabs = []
-        for pl, cols, e_mod in ((0, [0, 1], m.encoder_xy), (1, [1, 2], m.encoder_yz), (2, [0, 2], m.encoder_xz)):
+        plane_in = (u[:, 0:2].contiguous(), u[:, 1:3].contiguous(), torch.stack([u[:, 0], u[:, 2]], dim=1))      # no index tensors: graph-capturable
+        for pl, e_mod in ((0, m.encoder_xy), (1, m.encoder_yz), (2, m.encoder_xz)):
             ge = torch.zeros_like(e_mod.embeddings)
-            _grid_backend.grid_encode_backward(planes[pl].view(12, M, 1), u[:, cols].contiguous(), e_mod.embeddings, e_mod.offsets, ge, M, 2, 1, 12, S, H,
+            _grid_backend.grid_encode_backward(planes[pl].view(12, M, 1), plane_in[pl], e_mod.embeddings, e_mod.offsets, ge, M, 2, 1, 12, S, H,
                                                None, None, 0, False)
             d_tabs.append(ge)
         d_enc_a = (gr["d_ew"].float() * sv["att"].float()).sum(0).view_as(enc_a)
