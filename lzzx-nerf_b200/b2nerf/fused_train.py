@@ -20,6 +20,7 @@ class _GradsC(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("d_rl", "d_hc", "d_o", "d_h2", "d_h1", "d_ew", "d_att", "d_ha", "d_el", "d_he", "d_ul", "d_hu", "d_ci", "d_planes")]
 
 
+WGRAD_REPLICAS = 16      # copies of each weight gradient the CTAs reduce into (summed here): un-serialises the same-address reductions in the L2
 GRAD_WIDTHS = dict(d_rl=8, d_hc=64, d_o=72, d_h2=64, d_h1=64, d_ew=32, d_att=32, d_ha=64, d_el=8, d_he=16, d_ul=8, d_hu=32, d_ci=8)
 
 
@@ -33,9 +34,10 @@ def head_parameters(model):
 
 def _wgrad(dy, x):
     """fp32 [dy.shape[1], x.shape[1]] = dy^T x over all rows (b2n_linear_wgrad)."""
-    out = torch.zeros(dy.shape[1], x.shape[1], dtype=torch.float32, device=x.device)
-    lib().call("b2n_linear_wgrad", dy.data_ptr(), x.data_ptr(), x.shape[0], dy.shape[1], x.shape[1], out.data_ptr(), torch.cuda.current_stream().cuda_stream)
-    return out
+    out = torch.zeros(WGRAD_REPLICAS, dy.shape[1], x.shape[1], dtype=torch.float32, device=x.device)
+    lib().call("b2n_linear_wgrad_replicated", dy.data_ptr(), x.data_ptr(), x.shape[0], dy.shape[1], x.shape[1], out.data_ptr(), WGRAD_REPLICAS,
+               torch.cuda.current_stream().cuda_stream)
+    return out.sum(0)
 
 
 class _FusedHead(torch.autograd.Function):
