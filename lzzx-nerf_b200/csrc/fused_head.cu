@@ -92,6 +92,7 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, u
         uint32_t acc[32];
         ld32(taddr + cb, acc);
         wait_ld();
+        uint4 q[4];
 #pragma unroll
         for (uint32_t c = 0; c < 4; c++) {
             uint32_t w[4];
@@ -101,8 +102,12 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, u
                 if (BIAS) { x0 += bias[cb + c * 8 + 2 * j]; x1 += bias[cb + c * 8 + 2 * j + 1]; }
                 w[j] = RELU ? pack2_relu(x0, x1) : pack2(x0, x1);
             }
-            *reinterpret_cast<uint4 *>(tile + sw128_offset(row, (cb >> 3) + c)) = make_uint4(w[0], w[1], w[2], w[3]);
-            if (save) save[(cb >> 3) + c] = make_uint4(w[0], w[1], w[2], w[3]);      // training: the same fp16 row, kept for the backward
+            q[c] = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(tile + sw128_offset(row, (cb >> 3) + c)) = q[c];
+        }
+        if (save) {                                   // training: the same fp16 row, kept for the backward (32-byte stores when the row allows it)
+            if ((reinterpret_cast<uintptr_t>(save) & 31u) == 0) { st256(save + (cb >> 3), q[0], q[1]); st256(save + (cb >> 3) + 2, q[2], q[3]); }
+            else { save[(cb >> 3)] = q[0]; save[(cb >> 3) + 1] = q[1]; save[(cb >> 3) + 2] = q[2]; save[(cb >> 3) + 3] = q[3]; }
         }
     }
 }

@@ -72,6 +72,7 @@ __device__ __forceinline__ void masked_epilogue(uint32_t taddr, uint8_t *tile, u
         uint32_t acc[32];
         ld32(taddr + cb, acc);
         wait_ld();
+        uint4 q[4];
 #pragma unroll
         for (uint32_t c = 0; c < 4; c++) {
             const uint4 a4 = act[(cb >> 3) + c];
@@ -79,16 +80,19 @@ __device__ __forceinline__ void masked_epilogue(uint32_t taddr, uint8_t *tile, u
             uint32_t w[4];
 #pragma unroll
             for (uint32_t j = 0; j < 4; j++) w[j] = pk2_masked(__uint_as_float(acc[c * 8 + 2 * j]), __uint_as_float(acc[c * 8 + 2 * j + 1]), am[j]);
-            const uint4 q = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4 *>(tile + sw128_offset(row, (cb >> 3) + c)) = q;
-            if (save) save[(cb >> 3) + c] = q;
+            q[c] = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(tile + sw128_offset(row, (cb >> 3) + c)) = q[c];
         }
+        if (save) { st256(save + (cb >> 3), q[0], q[1]); st256(save + (cb >> 3) + 2, q[2], q[3]); }      // [M,64] fp16 rows are 128-byte aligned
     }
 }
 __device__ __forceinline__ void load_row8(uint4 (&r)[8], const void *base, size_t m, bool live) {
     const uint4 *p = reinterpret_cast<const uint4 *>(base) + m * 8;
 #pragma unroll
-    for (int i = 0; i < 8; i++) r[i] = live ? __ldcs(p + i) : make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < 8; i += 2) {
+        if (live) ld256(p + i, r[i], r[i + 1]);
+        else { r[i] = make_uint4(0, 0, 0, 0); r[i + 1] = make_uint4(0, 0, 0, 0); }
+    }
 }
 
 __global__ void __launch_bounds__(BW_THREADS, 1) k_head_backward(const __grid_constant__ BwdArgs a) {

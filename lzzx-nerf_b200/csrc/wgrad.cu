@@ -188,6 +188,126 @@ __global__ void __launch_bounds__(WG_THREADS, 3) k_linear_wgrad(const __half *__
     if (warp == 1) tmem_dealloc(tmem, 128);
 }
 
+// ---- pipelined variant for 16-byte aligned operands (every operand of the fused training path: row pitches are multiples of 8 halves) ------
+// One CTA per SM, a ring of WP_STAGES operand stages filled with cp.async (16-byte asynchronous copies, zero-fill past the last row): the
+// copies of chunks c+1 .. c+3 are in flight while chunk c is multiplied, so the per-chunk global-load latency that bounds the simple kernel
+// (one chunk per CTA in flight, ~2 us per chunk) is hidden.
+constexpr uint32_t WP_STAGES = 4;
+constexpr uint32_t WP_STAGE_BYTES = 2 * WG_OPERAND_BYTES;                 // A (<= 128 features) + B (<= 128 features) of one 64-sample chunk
+constexpr uint32_t WP_SMEM = WP_STAGES * WP_STAGE_BYTES + 1024 + 128;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_saddr, const void *src, bool valid) {
+    const uint32_t sz = valid ? 16u : 0u;                                 // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_saddr), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct RowMap { uint32_t col, r0, rstep, nv; };                           // thread -> (16-byte column, first row, row step) of an operand
+__device__ __forceinline__ RowMap row_map(uint32_t width) {
+    RowMap r;
+    r.nv = width / 8u;
+    const uint32_t lg = 32u - __clz(r.nv - 1u);
+    r.col = threadIdx.x & ((1u << lg) - 1u);
+    r.r0 = threadIdx.x >> lg;
+    r.rstep = WG_THREADS >> lg;
+    return r;
+}
+__device__ __forceinline__ void issue_operand(uint32_t s_base, const __half *__restrict__ src, const RowMap &r, uint32_t row0, uint32_t M, uint32_t width) {
+    if (r.col >= r.nv) return;
+    const uint32_t j = r.col * 8u;
+#pragma unroll
+    for (uint32_t u = 0; u < 4; u++) {                                    // <= 4 rows per thread (width <= 128)
+        const uint32_t k = r.r0 + u * r.rstep;
+        if (k < WG_CHUNK) {
+            const uint32_t row = row0 + k;
+            const bool ok = row < M;
+            cp_async16(s_base + mn_offset(k, j), src + (size_t)(ok ? row : 0) * width + j, ok);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) k_linear_wgrad_pipe(const __half *__restrict__ dy, const __half *__restrict__ x, uint32_t M, uint32_t out_dim,
+                                                                      uint32_t in_dim, float *__restrict__ dw, uint32_t replicas) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + WP_STAGES * WP_STAGE_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + WP_STAGES);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t n_chunks = (M + WG_CHUNK - 1) / WG_CHUNK;
+    const uint32_t n_pad = (in_dim + 15u) & ~15u;
+    dw += (size_t)(blockIdx.x % replicas) * out_dim * in_dim;
+    const bool vec4 = (in_dim & 3u) == 0 && ((uintptr_t)dw & 15u) == 0;
+
+    for (uint32_t i = tid; i < WP_STAGES * WP_STAGE_BYTES / 16; i += WG_THREADS) reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { for (uint32_t s = 0; s < WP_STAGES; s++) mbar_init(&bars[s], 1); fence_mbar_init(); }
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = idesc_f16(128, n_pad) | (1u << 15) | (1u << 16);
+    const uint32_t base_a = smem_u32(base);
+    const RowMap ra = row_map(out_dim), rb = row_map(in_dim);
+    const uint32_t my_n = blockIdx.x < n_chunks ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue = [&](uint32_t i) {                                        // chunk i of this CTA -> stage i % WP_STAGES
+        const uint32_t st = base_a + (i % WP_STAGES) * WP_STAGE_BYTES, row0 = (blockIdx.x + i * gridDim.x) * WG_CHUNK;
+        issue_operand(st, dy, ra, row0, M, out_dim);
+        issue_operand(st + WG_OPERAND_BYTES, x, rb, row0, M, in_dim);
+    };
+    for (uint32_t i = 0; i + 1 < WP_STAGES; i++) { if (i < my_n) issue(i); cp_async_commit(); }
+    for (uint32_t i = 0; i < my_n; i++) {
+        cp_async_wait<WP_STAGES - 2>();                                   // this thread's copies of chunk i have landed
+        fence_proxy_async();
+        __syncthreads();                                                  // ... and everybody else's
+        const uint32_t s = i % WP_STAGES;
+        if (tid == 0) {
+            fence_after_sync();
+            uint64_t da = smem_desc_mn_sw128(base_a + s * WP_STAGE_BYTES), db = smem_desc_mn_sw128(base_a + s * WP_STAGE_BYTES + WG_OPERAND_BYTES);
+#pragma unroll 1
+            for (uint32_t k = 0; k < WG_CHUNK / 16; k++, da += 2048u >> 4, db += 2048u >> 4) mma_f16_ss(tmem, da, db, idesc, i > 0 || k > 0);
+            mma_commit(&bars[s]);
+        }
+        const uint32_t nxt = i + WP_STAGES - 1;                           // refills the stage chunk i-1 was multiplied from
+        if (nxt < my_n) {
+            if (i >= 1) mbar_wait(&bars[(i - 1) % WP_STAGES], ((i - 1) / WP_STAGES) & 1u);
+            issue(nxt);
+        }
+        cp_async_commit();
+    }
+    if (my_n > 0) {
+        const uint32_t last = my_n - 1;
+        mbar_wait(&bars[last % WP_STAGES], (last / WP_STAGES) & 1u);
+        fence_after_sync();
+        if (warp < 4) {
+            const uint32_t o = tid;
+            const uint32_t taddr = tmem + ((warp * 32u) << 16);
+            for (uint32_t cb = 0; cb < n_pad; cb += 16) {
+                uint32_t acc[16];
+                ld16(taddr + cb, acc);
+                wait_ld();
+                if (o < out_dim) {
+                    float *row = dw + (size_t)o * in_dim + cb;
+                    if (vec4) {
+#pragma unroll
+                        for (uint32_t j = 0; j < 16; j += 4)
+                            if (cb + j < in_dim)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + j), "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
+                                             "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3])) : "memory");
+                    } else {
+#pragma unroll
+                        for (uint32_t j = 0; j < 16; j++)
+                            if (cb + j < in_dim) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(row + j), "f"(__uint_as_float(acc[j])) : "memory");
+                    }
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
 // halves per global access: 8/4/2 when rows allow it, 0 = flat 16-byte stream (odd width, 16-byte aligned matrix), 1 = element-wise
 static uint32_t vec_width(const void *p, uint32_t width) {
     for (uint32_t v = 8; v > 1; v >>= 1)
@@ -222,7 +342,15 @@ static int wgrad_launch(const void *dy, const void *x, uint32_t M, uint32_t out_
     const uint32_t n_chunks = ceil_div<uint32_t>(M, WG_CHUNK);
     uint32_t ctas = ctas_per_sm * (uint32_t)sm_count();
     if (ctas > n_chunks) ctas = n_chunks;
-    k_linear_wgrad<<<ctas, WG_THREADS, WG_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, vec_width(dy, out_dim),
-                                                                    vec_width(x, in_dim), dw, replicas);
+    const uint32_t va = vec_width(dy, out_dim), vb = vec_width(x, in_dim);
+    if (va == 8 && vb == 8 && !getenv("B2N_WGRAD_SIMPLE")) {              // 16-byte aligned operands: cp.async ring, one CTA per SM
+        static bool attr_p = false;
+        if (!attr_p) { B2N_CUDA(cudaFuncSetAttribute(k_linear_wgrad_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WP_SMEM)); attr_p = true; }
+        uint32_t g = (uint32_t)sm_count();
+        if (g > n_chunks) g = n_chunks;
+        k_linear_wgrad_pipe<<<g, WG_THREADS, WP_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, dw, replicas);
+        return check_launch("linear_wgrad");
+    }
+    k_linear_wgrad<<<ctas, WG_THREADS, WG_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, va, vb, dw, replicas);
     return check_launch("linear_wgrad");
 }

@@ -211,7 +211,8 @@ def test_frame_renderer_while_graph_matches_fixed_sequence():
     assert float(a.mean()) < 0.999          # the head is visible against the white background
 
 
-@pytest.mark.parametrize("n_out,n_in", [(64, 36), (32, 64), (16, 36), (1, 16), (64, 69), (65, 64), (64, 84), (3, 64), (128, 128), (32, 32)])
+@pytest.mark.parametrize("n_out,n_in", [(64, 36), (32, 64), (16, 36), (1, 16), (64, 69), (65, 64), (64, 84), (3, 64), (128, 128), (32, 32),
+                                         (8, 64), (72, 64), (64, 88), (64, 40), (16, 40), (8, 16)])     # padded pitches of the fused path: cp.async ring
 @pytest.mark.parametrize("M", [128, 1000, 40064])
 def test_linear_wgrad_matches_fp32_matmul(n_out, n_in, M):
     """b2n_linear_wgrad: dW += dY^T X over M samples (fp16 operands as MN-major tcgen05 operands, fp32 accumulation) vs torch in fp32.
