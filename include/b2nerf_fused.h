@@ -142,10 +142,10 @@ int b2n_head_backward(const b2n_model *m, uint32_t M, const float *enc_a, const 
  * fp32 accumulation; dw is accumulated into, zero it first).  1 <= out, in <= 128.  Replaces the weight-gradient GEMM that autograd's
  * LinearBackward runs for every MLP layer of nerf_triplane/network.py:73-94 in a training step (csrc/wgrad.cu). */
 int b2n_linear_wgrad(const void *dy_f16, const void *x_f16, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, void *stream);
-/* Same product accumulated into `replicas` copies dw[r][out,in] (CTA b adds its partial to copy b mod replicas; the caller sums the copies):
- * several hundred CTAs reducing into ONE small matrix serialise in the L2 (same-address reductions), which bounds a launch at ~20 us. */
+/* Same product accumulated into `replicas` copies of the result, copy r at dw + r * replica_stride floats (0 = out_dim * in_dim); CTA b adds its
+ * partial to copy b mod replicas and the caller sums the copies: hundreds of CTAs reducing into ONE small matrix serialise in the L2. */
 int b2n_linear_wgrad_replicated(const void *dy_f16, const void *x_f16, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, uint32_t replicas,
-                                void *stream);
+                                uint32_t replica_stride, void *stream);
 
 /* AdamW over one flat fp32 parameter buffer (parameters, gradients and both moments contiguous; two hyper-parameter groups split at
  * n_group0).  Replaces torch.optim.AdamW + the GradScaler unscale pass of the reference's optimizer step (TrainerUtil.py:1040-1056,

@@ -32,12 +32,24 @@ def head_parameters(model):
             model.color_net.net[0].weight, model.color_net.net[1].weight, model.unc_net.net[0].weight, model.unc_net.net[1].weight]
 
 
-def _wgrad(dy, x):
-    """fp32 [dy.shape[1], x.shape[1]] = dy^T x over all rows (b2n_linear_wgrad)."""
-    out = torch.zeros(WGRAD_REPLICAS, dy.shape[1], x.shape[1], dtype=torch.float32, device=x.device)
-    lib().call("b2n_linear_wgrad_replicated", dy.data_ptr(), x.data_ptr(), x.shape[0], dy.shape[1], x.shape[1], out.data_ptr(), WGRAD_REPLICAS,
-               torch.cuda.current_stream().cuda_stream)
-    return out.sum(0)
+def _wgrad_all(pairs):
+    """pairs: [(dY [M,o] fp16, X [M,i] fp16)] -> list of fp32 [o,i] = dY^T X.  All results share one zero-initialised buffer [replicas, total]
+    (ONE fill), every CTA of every launch adds its partial to replica (cta mod replicas), and ONE sum over the replica axis finishes all of them."""
+    dev = pairs[0][0].device
+    sizes = [dy.shape[1] * x.shape[1] for dy, x in pairs]
+    total = sum(sizes)
+    buf = torch.zeros(WGRAD_REPLICAS, total, dtype=torch.float32, device=dev)
+    st, off = torch.cuda.current_stream().cuda_stream, 0
+    for (dy, x), sz in zip(pairs, sizes):
+        lib().call("b2n_linear_wgrad_replicated", dy.data_ptr(), x.data_ptr(), x.shape[0], dy.shape[1], x.shape[1], buf.data_ptr() + 4 * off, WGRAD_REPLICAS,
+                   total, st)
+        off += sz
+    flat = buf.sum(0)
+    outs, off = [], 0
+    for (dy, x), sz in zip(pairs, sizes):
+        outs.append(flat[off:off + sz].view(dy.shape[1], x.shape[1]))
+        off += sz
+    return outs
 
 
 class _FusedHead(torch.autograd.Function):
@@ -70,21 +82,17 @@ class _FusedHead(torch.autograd.Function):
         lib().call("b2n_head_backward", m.handle, M, enc_a_flat.data_ptr(), eye.data_ptr() if ctx.has_eye else None, ctypes.byref(sc), sig.data_ptr(),
                    aud.data_ptr(), p(g_sig), p(g_rgb), p(g_aud), p(g_eye), p(g_unc), ctypes.byref(gc), torch.cuda.current_stream().cuda_stream)
         # weight gradients: one pass over (dY, X) per matrix
-        d_c1 = _wgrad(gr["d_rl"], sv["hc"])[:3]
-        d_c0 = _wgrad(gr["d_hc"], sv["c_in"])[:, :84]
-        rot = _wgrad(gr["d_o"], sv["h2"])                               # rows: geo_feat 0..63, density logit 64
-        d_s2 = torch.cat([rot[64:65], rot[:64]], dim=0)
-        d_s1 = _wgrad(gr["d_h2"], sv["h1"])
-        d_s0 = _wgrad(gr["d_h1"], sv["s_in"])[:, :69]
-        d_a1 = _wgrad(gr["d_att"], sv["ha"])
-        d_a0 = _wgrad(gr["d_ha"], sv["x36"])[:, :36]
-        d_e1 = _wgrad(gr["d_el"], sv["he"])[:1]
-        d_e0 = _wgrad(gr["d_he"], sv["x36"])[:, :36]
+        pairs = [(gr["d_rl"], sv["hc"]), (gr["d_hc"], sv["c_in"]), (gr["d_o"], sv["h2"]), (gr["d_h2"], sv["h1"]), (gr["d_h1"], sv["s_in"]),
+                 (gr["d_att"], sv["ha"]), (gr["d_ha"], sv["x36"]), (gr["d_el"], sv["he"]), (gr["d_he"], sv["x36"])]
         if ctx.with_unc:
-            d_u1 = _wgrad(gr["d_ul"], sv["hu"])[:1]
-            d_u0 = _wgrad(gr["d_hu"], sv["x36"])[:, :36]
-        else:
-            d_u0 = d_u1 = None
+            pairs += [(gr["d_ul"], sv["hu"]), (gr["d_hu"], sv["x36"])]
+        w = _wgrad_all(pairs)
+        d_c1, d_c0 = w[0][:3], w[1][:, :84]
+        d_s2 = torch.cat([w[2][64:65], w[2][:64]], dim=0)                # rows: geo_feat 0..63, density logit 64 -> sigma_net.2's row order
+        d_s1, d_s0 = w[3], w[4][:, :69]
+        d_a1, d_a0 = w[5], w[6][:, :36]
+        d_e1, d_e0 = w[7][:1], w[8][:, :36]
+        d_u1, d_u0 = (w[9][:1], w[10][:, :36]) if ctx.with_unc else (None, None)
         # table gradients: d enc_x is already in the grid backward's [L, B, C] layout, one slab per plane (xy, yz, xz: network.py:208-212)
         u = (x + m.bound) / (2 * m.bound)
         enc = m.encoder_xy

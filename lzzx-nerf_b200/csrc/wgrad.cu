@@ -117,7 +117,7 @@ __device__ __noinline__ void load_chunk_any(uint32_t v, uint8_t *buf, const __ha
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 3) k_linear_wgrad(const __half *__restrict__ dy, const __half *__restrict__ x, uint32_t M, uint32_t out_dim,
-                                                                 uint32_t in_dim, uint32_t va, uint32_t vb, float *__restrict__ dw, uint32_t replicas) {
+                                                                 uint32_t in_dim, uint32_t va, uint32_t vb, float *__restrict__ dw, uint32_t replicas, uint32_t rstride) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + 4 * WG_OPERAND_BYTES);
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(WG_THREADS, 3) k_linear_wgrad(const __half *__
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t n_chunks = (M + WG_CHUNK - 1) / WG_CHUNK;
     const uint32_t n_pad = (in_dim + 15u) & ~15u;                      // MMA N
-    dw += (size_t)(blockIdx.x % replicas) * out_dim * in_dim;          // spread the final reductions over `replicas` copies of the result
+    dw += (size_t)(blockIdx.x % replicas) * rstride;                   // spread the final reductions over `replicas` copies of the result
     const bool vec4 = (in_dim & 3u) == 0 && ((uintptr_t)dw & 15u) == 0;
 
     // padding features (j >= width) are never written by the loads: zero everything once
@@ -228,7 +228,7 @@ __device__ __forceinline__ void issue_operand(uint32_t s_base, const __half *__r
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1) k_linear_wgrad_pipe(const __half *__restrict__ dy, const __half *__restrict__ x, uint32_t M, uint32_t out_dim,
-                                                                      uint32_t in_dim, float *__restrict__ dw, uint32_t replicas) {
+                                                                      uint32_t in_dim, float *__restrict__ dw, uint32_t replicas, uint32_t rstride) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + WP_STAGES * WP_STAGE_BYTES);
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_linear_wgrad_pipe(const __hal
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t n_chunks = (M + WG_CHUNK - 1) / WG_CHUNK;
     const uint32_t n_pad = (in_dim + 15u) & ~15u;
-    dw += (size_t)(blockIdx.x % replicas) * out_dim * in_dim;
+    dw += (size_t)(blockIdx.x % replicas) * rstride;
     const bool vec4 = (in_dim & 3u) == 0 && ((uintptr_t)dw & 15u) == 0;
 
     for (uint32_t i = tid; i < WP_STAGES * WP_STAGE_BYTES / 16; i += WG_THREADS) reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
@@ -319,18 +319,19 @@ static uint32_t vec_width(const void *p, uint32_t width) {
 
 using namespace b2n;
 
-static int wgrad_launch(const void *dy, const void *x, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, uint32_t replicas, void *stream);
+static int wgrad_launch(const void *dy, const void *x, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, uint32_t replicas, uint32_t rstride, void *stream);
 
 extern "C" int b2n_linear_wgrad(const void *dy, const void *x, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, void *stream) {
-    return wgrad_launch(dy, x, M, out_dim, in_dim, dw, 1, stream);
+    return wgrad_launch(dy, x, M, out_dim, in_dim, dw, 1, out_dim * in_dim, stream);
 }
 extern "C" int b2n_linear_wgrad_replicated(const void *dy, const void *x, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, uint32_t replicas,
-                                           void *stream) {
+                                           uint32_t replica_stride, void *stream) {
     B2N_REQUIRE(replicas >= 1 && replicas <= 64, "linear_wgrad_replicated: replicas=%u out of range (1..64)", replicas);
-    return wgrad_launch(dy, x, M, out_dim, in_dim, dw, replicas, stream);
+    B2N_REQUIRE(replica_stride == 0 || replica_stride >= out_dim * in_dim, "linear_wgrad_replicated: replica stride smaller than the matrix");
+    return wgrad_launch(dy, x, M, out_dim, in_dim, dw, replicas, replica_stride ? replica_stride : out_dim * in_dim, stream);
 }
 
-static int wgrad_launch(const void *dy, const void *x, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, uint32_t replicas, void *stream) {
+static int wgrad_launch(const void *dy, const void *x, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, uint32_t replicas, uint32_t rstride, void *stream) {
     B2N_REQUIRE(dy && x && dw, "linear_wgrad: null pointer");
     B2N_REQUIRE(out_dim >= 1 && out_dim <= 128 && in_dim >= 1 && in_dim <= 128, "linear_wgrad: out=%u / in=%u unsupported (1..128)", out_dim, in_dim);
     B2N_REQUIRE(((uintptr_t)dy & 1) == 0 && ((uintptr_t)x & 1) == 0, "linear_wgrad: operands must be 2-byte aligned");
@@ -348,9 +349,9 @@ static int wgrad_launch(const void *dy, const void *x, uint32_t M, uint32_t out_
         if (!attr_p) { B2N_CUDA(cudaFuncSetAttribute(k_linear_wgrad_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WP_SMEM)); attr_p = true; }
         uint32_t g = (uint32_t)sm_count();
         if (g > n_chunks) g = n_chunks;
-        k_linear_wgrad_pipe<<<g, WG_THREADS, WP_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, dw, replicas);
+        k_linear_wgrad_pipe<<<g, WG_THREADS, WP_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, dw, replicas, rstride);
         return check_launch("linear_wgrad");
     }
-    k_linear_wgrad<<<ctas, WG_THREADS, WG_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, va, vb, dw, replicas);
+    k_linear_wgrad<<<ctas, WG_THREADS, WG_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, va, vb, dw, replicas, rstride);
     return check_launch("linear_wgrad");
 }

@@ -29,7 +29,7 @@ for n_out, n_in in layers:
     dy = torch.randn(M, n_out, device="cuda").half(); x = torch.randn(M, n_in, device="cuda").half()
     R = int(os.environ.get("B2N_WG_REPLICAS", "16"))
     dw = torch.zeros(R, n_out, n_in, device="cuda")
-    us = t(lambda: lib().call("b2n_linear_wgrad_replicated", dy.data_ptr(), x.data_ptr(), M, n_out, n_in, dw.data_ptr(), R, st))
+    us = t(lambda: lib().call("b2n_linear_wgrad_replicated", dy.data_ptr(), x.data_ptr(), M, n_out, n_in, dw.data_ptr(), R, 0, st))
     us_lib = t(lambda: dy.t() @ x, reps=5)
     byt = 2 * M * (n_out + n_in)
     rows.append({"out": n_out, "in": n_in, "us": round(us, 1), "library_us": round(us_lib, 1), "GBps": round(byt / us / 1e3, 1), "frac_hbm": round(byt / us / 1e3 / HBM, 3)})
