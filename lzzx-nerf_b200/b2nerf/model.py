@@ -304,6 +304,44 @@ class HeadModel(nn.Module):
                    ctypes.byref(sv), torch.cuda.current_stream().cuda_stream)
         return sig, rgb, aud, eye_o, unc, saved
 
+    # ---- occupancy-grid refresh (renderer.py:699-768, head branch) ---------------------------------------------------------
+    @torch.no_grad()
+    def update_extra_state(self, auds, eye=None, decay=0.95, density_thresh=10.0, density_scale=1.0, fused=True):
+        """NeRFRenderer.update_extra_state for the head: evaluate sigma on the 128^3 Morton-ordered jittered grid of every cascade, dilate,
+        EMA-max into density_grid, re-pack the bitfield (threshold min(mean_density, density_thresh)).  The reference runs `self.density` on
+        128^3 points through the per-op graph; here the 2.1 M points of a cascade go through the fused head kernel in one launch
+        (`fused=False` keeps the reference graph — used by the parity test).  Returns mean_density (one D2H read, like the reference)."""
+        import raymarching
+        dev, G = self.density_grid.device, self.grid_size
+        enc_a = self.encode_audio(auds)
+        if not hasattr(self, "_grid_coords") or self._grid_coords.device != dev:
+            ar = torch.arange(G, dtype=torch.int32, device=dev)
+            xx, yy, zz = torch.meshgrid(ar, ar, ar, indexing="ij")
+            self._grid_coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1).contiguous()        # [G^3, 3]
+            self._grid_indices = raymarching.morton3D(self._grid_coords).long()
+        coords, indices = self._grid_coords, self._grid_indices
+        xyzs = 2 * coords.float() / (G - 1) - 1
+        tmp_grid = torch.zeros_like(self.density_grid)
+        if fused:
+            self.pack()
+        for cas in range(self.cascade):
+            bound = min(2 ** cas, self.bound)
+            half = bound / G
+            cas_xyzs = xyzs * (bound - half)
+            cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half
+            if fused:
+                dirs = torch.zeros_like(cas_xyzs); dirs[:, 2] = 1.0
+                sig = self(cas_xyzs, dirs, enc_a, self.individual_codes[0:1], eye)[0]
+            else:
+                sig = self.density(cas_xyzs, enc_a, eye)["sigma"].reshape(-1).float()
+            tmp_grid[cas, indices] = sig * density_scale
+        tmp_grid = raymarching.morton3D_dilation(tmp_grid)
+        valid = (self.density_grid >= 0) & (tmp_grid >= 0)
+        self.density_grid[valid] = torch.maximum(self.density_grid[valid] * decay, tmp_grid[valid])
+        self.mean_density = float(torch.mean(self.density_grid.clamp(min=0)).item())
+        self.density_bitfield = raymarching.packbits(self.density_grid, min(self.mean_density, density_thresh), self.density_bitfield)
+        return self.mean_density
+
     # ---- whole-frame inference (renderer.py:406-570) ----------------------------------------------------------------------
     @torch.no_grad()
     def render_frame(self, rays_o, rays_d, enc_a, ind_code=None, eye=None, bg_color=None, dt_gamma=1.0 / 256, max_steps=16, min_near=0.05,

@@ -268,3 +268,33 @@ def test_head_forward_train_saves_the_reference_activations():
     close("h1", sv["h1"], h1, 2e-2); close("h2", sv["h2"], h2, 2e-2)
     close("c_in", sv["c_in"][:, :84], c_in, 3e-2); close("hc", sv["hc"], hc, 3e-2)
     close("misc rgb", sv["misc"][:, :3], s3, 1e-2); close("misc eye", sv["misc"][:, 3:4], eye_att, 5e-3); close("misc unc", sv["misc"][:, 4:5], ul, 1e-2)
+
+
+def test_update_extra_state_fused_matches_reference_graph():
+    """HeadModel.update_extra_state (renderer.py:699-768): the fused head kernel on the 128^3 jittered grid vs the reference graph (`density` through
+    the per-op encoders + torch MLPs under autocast) with the same random jitter: same density grid up to fp16 noise, bitfields differ only on
+    cells whose density sits at the threshold."""
+    import copy
+    m = _model(seed=4, table_scale=1.0, testing=True)
+    with torch.no_grad():
+        m.sigma_net.net[2].weight[0] *= 4.0           # spread the densities around the threshold
+    m2 = copy.deepcopy(m)
+    auds = torch.randn(8, m.audio_in_dim, 2, device="cuda")
+    eye = torch.tensor([[0.3]], device="cuda")
+    res = []
+    for model, fused in ((m, True), (m2, False)):
+        torch.manual_seed(11)                          # same jitter on both sides
+        with torch.autocast("cuda", dtype=torch.float16):
+            md = model.update_extra_state(auds, eye, fused=fused, density_thresh=0.5)
+        res.append((md, model.density_grid.clone(), model.density_bitfield.clone()))
+    (md_f, g_f, b_f), (md_r, g_r, b_r) = res
+    assert abs(md_f - md_r) <= 2e-3 * max(md_r, 1e-6), (md_f, md_r)
+    rel = float(((g_f - g_r).abs() / (g_r.abs() + 1e-3)).max())
+    assert rel < 3e-2, rel
+    diff_bits = int(torch.tensor([bin(v).count("1") for v in (b_f ^ b_r).cpu().tolist() if v]).sum()) if bool((b_f ^ b_r).any()) else 0
+    assert diff_bits <= 1e-3 * m.grid_size ** 3, diff_bits
+    assert 0 < int((b_f != 0).sum()) < b_f.numel()
+    # second call applies the EMA decay path
+    with torch.autocast("cuda", dtype=torch.float16):
+        md2 = m.update_extra_state(auds, eye, fused=True, density_thresh=0.5)
+    assert md2 > 0
