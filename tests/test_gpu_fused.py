@@ -287,7 +287,7 @@ def test_update_extra_state_fused_matches_reference_graph():
     for model, fused in ((m, True), (m2, False)):
         torch.manual_seed(11)                          # same jitter on both sides
         with torch.autocast("cuda", dtype=torch.float16):
-            md = model.update_extra_state(auds, eye, fused=fused, density_thresh=0.5)
+            md = model.update_extra_state(auds, eye, fused=fused, density_thresh=1e9)      # threshold = mean density
         res.append((md, model.density_grid.clone(), model.density_bitfield.clone()))
     (md_f, g_f, b_f), (md_r, g_r, b_r) = res
     assert abs(md_f - md_r) <= 2e-3 * max(md_r, 1e-6), (md_f, md_r)
@@ -300,5 +300,5 @@ def test_update_extra_state_fused_matches_reference_graph():
     assert 0.05 < occ < 0.95, occ                      # a non-trivial bitfield
     # second call applies the EMA decay path
     with torch.autocast("cuda", dtype=torch.float16):
-        md2 = m.update_extra_state(auds, eye, fused=True, density_thresh=0.5)
+        md2 = m.update_extra_state(auds, eye, fused=True, density_thresh=1e9)
     assert md2 > 0
