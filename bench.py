@@ -294,8 +294,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         sampler.start()
         sampler.wait_first()
     dev_ms, launches = timed(lambda s: pipe.submit_device(frames[s % POOL][0], frames[s % POOL][1], auds[s % POOL]), args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
     e2e_ms, _ = timed(lambda s: pipe.submit_host(host_o[s % POOL], host_d[s % POOL], host_a[s % POOL], out_hosts[s % pipe.depth]), args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None          # sampled over both timed regions (device-resident and end-to-end)
     train_info = None
     if not args.no_train:
         train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(4, min(args.steps, 20)), warmup=max(args.warmup, 18), eager=args.train_eager, fused_head=not args.train_unfused)
