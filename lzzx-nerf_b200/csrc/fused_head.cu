@@ -112,6 +112,21 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, u
     }
 }
 
+// Training: copy this warp's 32 rows (128 B each) of a SWIZZLE_128B tile to a row-major global array, warp-cooperatively: 8 lanes write the 8
+// chunks of one row, so a store instruction covers 4 full rows (4 cache lines) — a thread storing its own row costs 32 lines per instruction, and
+// with ~1 KB of activations per sample that is what bound the first version of this kernel (lg_throttle / mio_throttle).  The rows were written
+// by this same warp, so a __syncwarp() orders them; the tensor pipe only READS the tile meanwhile.
+__device__ __forceinline__ void warp_rows_out(const uint8_t *tile, uint32_t warp_row0, uint8_t *gtile, uint32_t pitch, uint32_t rows_valid) {
+    __syncwarp();
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; i++) {
+        const uint32_t p = i * 32u + lane, r = warp_row0 + (p >> 3), c = p & 7u;
+        const uint4 v = *reinterpret_cast<const uint4 *>(tile + sw128_offset(r, c));
+        if (r < rows_valid) __stcs(reinterpret_cast<uint4 *>(gtile + (size_t)r * pitch + c * 16u), v);
+    }
+}
+
 // ---- tri-plane gather, split in two halves so the table reads of one trip (2 levels x 3 planes x 4 corners = 24 loads per sample) stay
 // in flight underneath an MMA completion wait and its epilogue:  gather_issue() computes the cells and issues the loads, gather_finish()
 // blends and stores.  Arithmetic identical to gridcore.cuh:lvl2_interp / k_grid_fwd<float,2,1>: position fma(u, scale, 0.5), weights
@@ -344,6 +359,8 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             xsn = reinterpret_cast<uint32_t *>(a.sv.x36) + mn * 20; ssn = reinterpret_cast<uint32_t *>(a.sv.s_in) + mn * 36;
             xsn[18] = 0u; xsn[19] = 0u;
         }
+        const size_t tile_row0 = (size_t)tile * HG_TILE;
+        const uint32_t rows_valid = SAVE ? (uint32_t)min((size_t)HG_TILE, (size_t)a.M - tile_row0) : 0u, wrow0 = (warp & 3u) * 32u;
         uint32_t *s_in_w = sv_on ? reinterpret_cast<uint32_t *>(a.sv.s_in) + (size_t)m * 36 : nullptr;
         uint4 *c_in_q = sv_on ? reinterpret_cast<uint4 *>(a.sv.c_in) + (size_t)m * 11 : nullptr;
         float unc_logit = 0.0f;
@@ -354,7 +371,8 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         mma_done();
         float eye_att, unc_out = 0.6931471805599453f;       // testing: log(1 + e^0) (network.py:245,278)
         {
-            hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr, sv_on ? reinterpret_cast<uint4 *>(a.sv.ha) + (size_t)m * 8 : nullptr);
+            hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr);
+            if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.ha) + tile_row0 * 128, 128, rows_valid);
             uint32_t e16[16];
             ld16(tmem_ld + TC_EYE, e16); wait_ld();
             float dot = 0.0f;
@@ -434,14 +452,16 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
         if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[2], cn);
         mma_done();
-        hidden_epilogue<true, false>(tmem_ld + TC_S, sH, t, nullptr, sv_on ? reinterpret_cast<uint4 *>(a.sv.h1) + (size_t)m * 8 : nullptr);
+        hidden_epilogue<true, false>(tmem_ld + TC_S, sH, t, nullptr);
+        if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.h1) + tile_row0 * 128, 128, rows_valid);
         if (has_next) gather_finish(G, cn.ok, rown, r7, 1, xsn, ssn);
         publish();
         // ---- P4: sigma layer 1 --------------------------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
         if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[4], cn);
         mma_done();
-        hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr, sv_on ? reinterpret_cast<uint4 *>(a.sv.h2) + (size_t)m * 8 : nullptr);
+        hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr);
+        if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.h2) + tile_row0 * 128, 128, rows_valid);
         if (has_next) gather_finish(G, cn.ok, rown, r7, 2, xsn, ssn);
         publish();
         // ---- P5: sigma layer 2: cols 0..63 = geo_feat, col 64 = density logit (rows rotated at pack time) -----------------
@@ -450,7 +470,8 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         mma_done();
         float sigma;
         {
-            hidden_epilogue<false, false>(tmem_ld + TC_A, sH, t, nullptr, sv_on ? c_in_q + 2 : nullptr);      // geo_feat = halves 16..79 of the color input
+            hidden_epilogue<false, false>(tmem_ld + TC_A, sH, t, nullptr);
+            if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.c_in) + tile_row0 * 176 + 32, 176, rows_valid);      // geo_feat = halves 16..79 of the color input
             uint32_t s16[16];
             ld16(tmem_ld + TC_A + 64, s16); wait_ld();
             sigma = expf(round_h(__uint_as_float(s16[0]))) * a.density_scale;       // torch.exp(h[..., 0]) in fp32 (network.py:301)
@@ -478,7 +499,8 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         }
         if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[8], cn);
         mma_done();
-        hidden_epilogue<true, true>(tmem_ld + TC_S, sH, t, S.ind_bias, sv_on ? reinterpret_cast<uint4 *>(a.sv.hc) + (size_t)m * 8 : nullptr);
+        hidden_epilogue<true, true>(tmem_ld + TC_S, sH, t, S.ind_bias);
+        if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.hc) + tile_row0 * 128, 128, rows_valid);
         if (has_next) gather_finish(G, cn.ok, rown, r7, 4, xsn, ssn);
         publish();
         // ---- P7: color layer 1 (N padded 3 -> 16) -----------------------------------------------------------------------------

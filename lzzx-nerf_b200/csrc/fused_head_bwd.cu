@@ -86,6 +86,17 @@ __device__ __forceinline__ void masked_epilogue(uint32_t taddr, uint8_t *tile, u
         if (save) { st256(save + (cb >> 3), q[0], q[1]); st256(save + (cb >> 3) + 2, q[2], q[3]); }      // [M,64] fp16 rows are 128-byte aligned
     }
 }
+// this warp's 32 rows (128 B each) of a SWIZZLE_128B tile -> row-major global array, 8 lanes per row (see fused_head.cu:warp_rows_out)
+__device__ __forceinline__ void warp_rows_out(const uint8_t *tile, uint32_t warp_row0, uint8_t *gtile, uint32_t pitch, uint32_t rows_valid) {
+    __syncwarp();
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; i++) {
+        const uint32_t p = i * 32u + lane, r = warp_row0 + (p >> 3), c = p & 7u;
+        const uint4 v = *reinterpret_cast<const uint4 *>(tile + sw128_offset(r, c));
+        if (r < rows_valid) __stcs(reinterpret_cast<uint4 *>(gtile + (size_t)r * pitch + c * 16u), v);
+    }
+}
 __device__ __forceinline__ void load_row8(uint4 (&r)[8], const void *base, size_t m, bool live) {
     const uint4 *p = reinterpret_cast<const uint4 *>(base) + m * 8;
 #pragma unroll
@@ -135,6 +146,8 @@ __global__ void __launch_bounds__(BW_THREADS, 1) k_head_backward(const __grid_co
     for (uint32_t tile = blockIdx.x * BW_WGS + wg; tile < n_tiles; tile += gridDim.x * BW_WGS) {
         const size_t m = (size_t)tile * HG_TILE + t;
         const bool live = m < a.M;
+        const size_t tile_row0 = (size_t)tile * HG_TILE;
+        const uint32_t rows_valid = (uint32_t)min((size_t)HG_TILE, (size_t)a.M - tile_row0), wrow0 = (warp & 3u) * 32u;
         // ---- per-sample scalars -------------------------------------------------------------------------------------------------
         float g_sig = 0, sig = 0, g_r[3] = {0, 0, 0}, g_aud = 0, nrm = 0, g_eye = 0, g_unc = 0;
         uint4 misc = make_uint4(0, 0, 0, 0);
@@ -170,8 +183,8 @@ __global__ void __launch_bounds__(BW_THREADS, 1) k_head_backward(const __grid_co
                 }
                 const uint4 q = make_uint4(w[0], w[1], w[2], w[3]);
                 *reinterpret_cast<uint4 *>(sP + sw128_offset(t, c)) = q;
-                if (live) reinterpret_cast<uint4 *>(a.g.d_hc)[m * 8 + c] = q;
             }
+            warp_rows_out(sP, wrow0, reinterpret_cast<uint8_t *>(a.g.d_hc) + tile_row0 * 128, 128, rows_valid);
         }
         publish();
         // ---- B2: d geo_feat (64) | d ind-code inputs (4) = d hc . color0[:, 16:84] ------------------------------------------------------
@@ -186,7 +199,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) k_head_backward(const __grid_co
         {
             // d o = [d geo (64) | d logit | 0 ...]: K = 80 operand = atom sP (geo) + atom sQ (logit in column 0); global copy in the same order
             uint4 *save = live ? reinterpret_cast<uint4 *>(a.g.d_o) + m * 9 : nullptr;
-#pragma unroll 1
+#pragma unroll
             for (uint32_t cb = 0; cb < 64; cb += 32) {
                 uint32_t acc[32];
                 ld32(tmem_ld + TB_S + cb, acc);
@@ -198,9 +211,9 @@ __global__ void __launch_bounds__(BW_THREADS, 1) k_head_backward(const __grid_co
                     for (uint32_t j = 0; j < 4; j++) w[j] = pk2(__uint_as_float(acc[c * 8 + 2 * j]), __uint_as_float(acc[c * 8 + 2 * j + 1]));
                     const uint4 q = make_uint4(w[0], w[1], w[2], w[3]);
                     *reinterpret_cast<uint4 *>(sP + sw128_offset(t, (cb >> 3) + c)) = q;
-                    if (save) save[(cb >> 3) + c] = q;
                 }
             }
+            warp_rows_out(sP, wrow0, reinterpret_cast<uint8_t *>(a.g.d_o) + tile_row0 * 144, 144, rows_valid);
             uint32_t i16[16];
             ld16(tmem_ld + TB_S + 64, i16);
             wait_ld();
@@ -222,13 +235,15 @@ __global__ void __launch_bounds__(BW_THREADS, 1) k_head_backward(const __grid_co
             mma_commit(bar);
         }
         mma_done();
-        masked_epilogue(tmem_ld + TB_S, sP, t, act, live ? reinterpret_cast<uint4 *>(a.g.d_h2) + m * 8 : nullptr);
+        masked_epilogue(tmem_ld + TB_S, sP, t, act, nullptr);
+        warp_rows_out(sP, wrow0, reinterpret_cast<uint8_t *>(a.g.d_h2) + tile_row0 * 128, 128, rows_valid);
         load_row8(act, a.sv.h1, m, live);
         publish();
         // ---- B4: d h1 = d h2 . sigma1, masked -----------------------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma_b(tmem_wg + TB_S, sP_a, sW_a + HT_S1, 4, 64, false); mma_commit(bar); }
         mma_done();
-        masked_epilogue(tmem_ld + TB_S, sP, t, act, live ? reinterpret_cast<uint4 *>(a.g.d_h1) + m * 8 : nullptr);
+        masked_epilogue(tmem_ld + TB_S, sP, t, act, nullptr);
+        warp_rows_out(sP, wrow0, reinterpret_cast<uint8_t *>(a.g.d_h1) + tile_row0 * 128, 128, rows_valid);
         publish();
         // ---- B5: d enc_x (TMEM, kept) | d [enc_w (32), e] = d h1 . sigma0 ------------------------------------------------------------
         if (t == 0) {
@@ -317,7 +332,8 @@ __global__ void __launch_bounds__(BW_THREADS, 1) k_head_backward(const __grid_co
         }
         load_row8(act, a.sv.ha, m, live);
         mma_done();
-        masked_epilogue(tmem_ld + TB_S, sP, t, act, live ? reinterpret_cast<uint4 *>(a.g.d_ha) + m * 8 : nullptr);
+        masked_epilogue(tmem_ld + TB_S, sP, t, act, nullptr);
+        warp_rows_out(sP, wrow0, reinterpret_cast<uint8_t *>(a.g.d_ha) + tile_row0 * 128, 128, rows_valid);
         publish();
         // ---- B7: d enc_x += d ha . aud_att0 -> the grid backward's [plane][level][sample] planes ---------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma_b(tmem_wg + TB_X, sP_a, sW_a + HT_A0, 4, 48, true); mma_commit(bar); }
