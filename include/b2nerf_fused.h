@@ -99,7 +99,7 @@ typedef struct {
     void *he;     /* [M,16]  relu(eye_att_net.net.0(enc_x)) */
     void *hu;     /* [M,32]  relu(unc_net.net.0(enc_x)); NULL when unc_net is not evaluated */
     void *att;    /* [M,32]  aud_ch_att_net output */
-    void *s_in;   /* [M,72]  sigma_net input [enc_x 36 | enc_a * att 32 | eye * eye_att 1 | 0 0 0]   (network.py:293-298) */
+    void *s_in;   /* [M,80]  sigma_net input [enc_x 36 | 0 x4 | enc_a * att 32 | eye * eye_att 1 | 0 x7]   (network.py:293-298) */
     void *h1;     /* [M,64]  relu(sigma_net.net.0) */
     void *h2;     /* [M,64]  relu(sigma_net.net.1) */
     void *c_in;   /* [M,88]  color_net input [sh 16 | geo_feat 64 | ind_code 4 | 0 0 0 0]            (network.py:267-270) */

@@ -89,7 +89,7 @@ class _FusedHead(torch.autograd.Function):
         w = _wgrad_all(pairs)
         d_c1, d_c0 = w[0][:3], w[1][:, :84]
         d_s2 = torch.cat([w[2][64:65], w[2][:64]], dim=0)                # rows: geo_feat 0..63, density logit 64 -> sigma_net.2's row order
-        d_s1, d_s0 = w[3], w[4][:, :69]
+        d_s1, d_s0 = w[3], torch.cat([w[4][:, :36], w[4][:, 40:73]], dim=1)      # s_in = [enc_x 36 | pad 4 | enc_w 32 | e | pad 7]
         d_a1, d_a0 = w[5], w[6][:, :36]
         d_e1, d_e0 = w[7][:1], w[8][:, :36]
         d_u1, d_u0 = (w[9][:1], w[10][:, :36]) if ctx.with_unc else (None, None)

@@ -283,7 +283,7 @@ class HeadModel(nn.Module):
         return sig, rgb, aud[:, None], eye_o[:, None], unc[:, None, None]
 
     # ---- training forward with saved activations (csrc/fused_head.cu, SAVE instantiation) --------------------------------
-    SAVED_WIDTHS = dict(x36=40, ha=64, he=16, hu=32, att=32, s_in=72, h1=64, h2=64, c_in=88, hc=64, misc=8)
+    SAVED_WIDTHS = dict(x36=40, ha=64, he=16, hu=32, att=32, s_in=80, h1=64, h2=64, c_in=88, hc=64, misc=8)
 
     @torch.no_grad()
     def forward_train_fused(self, x, d, enc_a, c, e):

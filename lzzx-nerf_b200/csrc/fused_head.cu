@@ -116,15 +116,19 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, u
 // chunks of one row, so a store instruction covers 4 full rows (4 cache lines) — a thread storing its own row costs 32 lines per instruction, and
 // with ~1 KB of activations per sample that is what bound the first version of this kernel (lg_throttle / mio_throttle).  The rows were written
 // by this same warp, so a __syncwarp() orders them; the tensor pipe only READS the tile meanwhile.
-__device__ __forceinline__ void warp_rows_out(const uint8_t *tile, uint32_t warp_row0, uint8_t *gtile, uint32_t pitch, uint32_t rows_valid) {
+template <uint32_t NCH>      // NCH 16-byte chunks per row, starting at chunk `chunk0` of the tile row
+__device__ __forceinline__ void warp_chunks_out(const uint8_t *tile, uint32_t chunk0, uint32_t warp_row0, uint8_t *gtile, uint32_t pitch, uint32_t rows_valid) {
     __syncwarp();
     const uint32_t lane = threadIdx.x & 31u;
 #pragma unroll
-    for (uint32_t i = 0; i < 8; i++) {
-        const uint32_t p = i * 32u + lane, r = warp_row0 + (p >> 3), c = p & 7u;
-        const uint4 v = *reinterpret_cast<const uint4 *>(tile + sw128_offset(r, c));
+    for (uint32_t i = 0; i < NCH; i++) {
+        const uint32_t p = i * 32u + lane, r = warp_row0 + p / NCH, c = p % NCH;
+        const uint4 v = *reinterpret_cast<const uint4 *>(tile + sw128_offset(r, chunk0 + c));
         if (r < rows_valid) __stcs(reinterpret_cast<uint4 *>(gtile + (size_t)r * pitch + c * 16u), v);
     }
+}
+__device__ __forceinline__ void warp_rows_out(const uint8_t *tile, uint32_t warp_row0, uint8_t *gtile, uint32_t pitch, uint32_t rows_valid) {
+    warp_chunks_out<8>(tile, 0, warp_row0, gtile, pitch, rows_valid);
 }
 
 // ---- tri-plane gather, split in two halves so the table reads of one trip (2 levels x 3 planes x 4 corners = 24 loads per sample) stay
@@ -185,7 +189,7 @@ __device__ __forceinline__ void gather_finish(const GatherTrip &G, uint32_t ok, 
         const uint32_t word = p * 6u + k;
         const uint32_t v = ((ok >> p) & 1u) ? pack2(f[0][p], f[1][p]) : 0u;
         *reinterpret_cast<uint32_t *>(row + (((word >> 2) ^ r7) << 4) + (word & 3u) * 4u) = v;
-        if (save_a) { save_a[word] = v; save_b[word] = v; }               // training: enc_x also goes to the x36 and sigma-input rows
+        (void)save_a; (void)save_b;
     }
 }
 
@@ -332,7 +336,13 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             gather_finish(GB, c.ok, sXb + row_off, r7, k + 1, xs, ss);
         }
         zero_k_padding(sXb);
-        if (xs) { xs[18] = 0u; xs[19] = 0u; }
+        (void)xs; (void)ss;
+        if (SAVE) {      // enc_x (36 halves + zero padding = chunks 0..4 of the feature tile) -> x36 rows and the first 80 bytes of the sigma-input rows
+            const size_t tr0 = (size_t)tile * HG_TILE;
+            const uint32_t rv = (uint32_t)min((size_t)HG_TILE, (size_t)a.M - tr0);
+            warp_chunks_out<5>(sXb, 0, (warp & 3u) * 32u, reinterpret_cast<uint8_t *>(a.sv.x36) + tr0 * 80, 80, rv);
+            warp_chunks_out<5>(sXb, 0, (warp & 3u) * 32u, reinterpret_cast<uint8_t *>(a.sv.s_in) + tr0 * 160, 160, rv);
+        }
     }
     for (; tile < n_tiles; tile += tile_stride) {
         uint8_t *sX = sXb + buf * HG_TILE_BYTES, *sXn = sXb + (buf ^ 1u) * HG_TILE_BYTES;
@@ -356,12 +366,11 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         uint32_t *xsn = nullptr, *ssn = nullptr;
         if (SAVE && nlive) {
             const size_t mn = (size_t)(tile + tile_stride) * HG_TILE + t;
-            xsn = reinterpret_cast<uint32_t *>(a.sv.x36) + mn * 20; ssn = reinterpret_cast<uint32_t *>(a.sv.s_in) + mn * 36;
-            xsn[18] = 0u; xsn[19] = 0u;
+            xsn = reinterpret_cast<uint32_t *>(a.sv.x36) + mn * 20; ssn = reinterpret_cast<uint32_t *>(a.sv.s_in) + mn * 40;
         }
         const size_t tile_row0 = (size_t)tile * HG_TILE;
         const uint32_t rows_valid = SAVE ? (uint32_t)min((size_t)HG_TILE, (size_t)a.M - tile_row0) : 0u, wrow0 = (warp & 3u) * 32u;
-        uint32_t *s_in_w = sv_on ? reinterpret_cast<uint32_t *>(a.sv.s_in) + (size_t)m * 36 : nullptr;
+
         uint4 *c_in_q = sv_on ? reinterpret_cast<uint4 *>(a.sv.c_in) + (size_t)m * 11 : nullptr;
         float unc_logit = 0.0f;
         publish();
@@ -382,9 +391,10 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
                 uint32_t w[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) w[j] = pack2_relu(__uint_as_float(e16[2 * j]), __uint_as_float(e16[2 * j + 1]));
-                uint4 *q = reinterpret_cast<uint4 *>(a.sv.he) + (size_t)m * 2;
-                q[0] = make_uint4(w[0], w[1], w[2], w[3]); q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 6)) = make_uint4(w[0], w[1], w[2], w[3]);      // chunks 6, 7 of the feature tile are not operands (K = 48)
+                *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 7)) = make_uint4(w[4], w[5], w[6], w[7]);
             }
+            if (SAVE) warp_chunks_out<2>(sX, 6, wrow0, reinterpret_cast<uint8_t *>(a.sv.he) + tile_row0 * 32, 32, rows_valid);
             // sigmoid evaluated on the fp16 logit, result rounded to fp16 (torch.sigmoid on a half tensor)
             eye_att = round_h(1.0f / (1.0f + expf(-round_h(dot))));
         }
@@ -410,11 +420,10 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
                 du = round_h(du);
                 unc_logit = du;
                 unc_out = logf(1.0f + expf(du));                        // torch.log(1 + torch.exp(.)) in fp32 (network.py:278)
-                if (sv_on && a.sv.hu) {
-                    uint4 *q = reinterpret_cast<uint4 *>(a.sv.hu) + (size_t)m * 4;
+                if (SAVE && a.sv.hu) {
 #pragma unroll
                     for (int c = 0; c < 4; c++)
-                        q[c] = make_uint4(pack2_relu(__uint_as_float(acc[8 * c]), __uint_as_float(acc[8 * c + 1])), pack2_relu(__uint_as_float(acc[8 * c + 2]), __uint_as_float(acc[8 * c + 3])),
+                        *reinterpret_cast<uint4 *>(sH + sw128_offset(t, 4 + c)) = make_uint4(pack2_relu(__uint_as_float(acc[8 * c]), __uint_as_float(acc[8 * c + 1])), pack2_relu(__uint_as_float(acc[8 * c + 2]), __uint_as_float(acc[8 * c + 3])),
                                           pack2_relu(__uint_as_float(acc[8 * c + 4]), __uint_as_float(acc[8 * c + 5])), pack2_relu(__uint_as_float(acc[8 * c + 6]), __uint_as_float(acc[8 * c + 7])));
                 }
             }
@@ -434,16 +443,17 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             const float e = a.eye ? S.eye_val * eye_att : 0.0f;                     // e = e * eye_att (network.py:291)
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 4)) = make_uint4(pack2(e, 0.0f), 0u, 0u, 0u);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 5)) = make_uint4(0u, 0u, 0u, 0u);
-            if (sv_on) {
-                uint4 *q = reinterpret_cast<uint4 *>(a.sv.att) + (size_t)m * 4;
+            if (SAVE) {
+                // the aud hidden tile H is dead (P2 read it): stage att in its chunks 0..3 (unc hidden sits in 4..7), then everything leaves coalesced
 #pragma unroll
                 for (int c = 0; c < 4; c++)
-                    q[c] = make_uint4(pack2(__uint_as_float(acc[8 * c]), __uint_as_float(acc[8 * c + 1])), pack2(__uint_as_float(acc[8 * c + 2]), __uint_as_float(acc[8 * c + 3])),
-                                      pack2(__uint_as_float(acc[8 * c + 4]), __uint_as_float(acc[8 * c + 5])), pack2(__uint_as_float(acc[8 * c + 6]), __uint_as_float(acc[8 * c + 7])));
-                uint2 *sw = reinterpret_cast<uint2 *>(s_in_w + 18);                  // halves 36..67 = enc_w, 68 = e, 69..71 = 0 (8-byte aligned)
-#pragma unroll
-                for (int j = 0; j < 8; j++) sw[j] = make_uint2(w[2 * j], w[2 * j + 1]);
-                sw[8] = make_uint2(pack2(e, 0.0f), 0u);
+                    *reinterpret_cast<uint4 *>(sH + sw128_offset(t, c)) =
+                        make_uint4(pack2(__uint_as_float(acc[8 * c]), __uint_as_float(acc[8 * c + 1])), pack2(__uint_as_float(acc[8 * c + 2]), __uint_as_float(acc[8 * c + 3])),
+                                   pack2(__uint_as_float(acc[8 * c + 4]), __uint_as_float(acc[8 * c + 5])), pack2(__uint_as_float(acc[8 * c + 6]), __uint_as_float(acc[8 * c + 7])));
+                warp_chunks_out<4>(sH, 0, wrow0, reinterpret_cast<uint8_t *>(a.sv.att) + tile_row0 * 64, 64, rows_valid);
+                if (a.sv.hu) warp_chunks_out<4>(sH, 4, wrow0, reinterpret_cast<uint8_t *>(a.sv.hu) + tile_row0 * 64, 64, rows_valid);
+                // [enc_w 32 | e | 0 x7] = chunks 0..4 of X -> bytes 80..159 of the sigma-input rows
+                warp_chunks_out<5>(sX, 0, wrow0, reinterpret_cast<uint8_t *>(a.sv.s_in) + tile_row0 * 160 + 80, 160, rows_valid);
             }
         }
         if (has_next) gather_finish(G, cn.ok, rown, r7, 0, xsn, ssn);
@@ -483,10 +493,8 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             for (int j = 0; j < 8; j++) w[j] = pack2(shv[2 * j], shv[2 * j + 1]);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 1)) = make_uint4(w[4], w[5], w[6], w[7]);
-            if (sv_on) {
-                c_in_q[0] = make_uint4(w[0], w[1], w[2], w[3]); c_in_q[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                c_in_q[10] = make_uint4(pack2(S.ind_h[0], S.ind_h[1]), pack2(S.ind_h[2], S.ind_h[3]), 0u, 0u);
-            }
+            if (SAVE) warp_chunks_out<2>(sX, 0, wrow0, reinterpret_cast<uint8_t *>(a.sv.c_in) + tile_row0 * 176, 176, rows_valid);
+            if (sv_on) c_in_q[10] = make_uint4(pack2(S.ind_h[0], S.ind_h[1]), pack2(S.ind_h[2], S.ind_h[3]), 0u, 0u);
         }
         if (has_next) gather_finish(G, cn.ok, rown, r7, 3, xsn, ssn);
         publish();
@@ -528,6 +536,12 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             }
         }
         if (has_next) gather_finish(G, cn.ok, rown, r7, 5, xsn, ssn);
+        if (SAVE && has_next) {      // the next tile's feature rows are complete (this warp gathered its own 32 rows)
+            const size_t tr0 = (size_t)(tile + tile_stride) * HG_TILE;
+            const uint32_t rv = (uint32_t)min((size_t)HG_TILE, (size_t)a.M - tr0);
+            warp_chunks_out<5>(sXn, 0, wrow0, reinterpret_cast<uint8_t *>(a.sv.x36) + tr0 * 80, 80, rv);
+            warp_chunks_out<5>(sXn, 0, wrow0, reinterpret_cast<uint8_t *>(a.sv.s_in) + tr0 * 160, 160, rv);
+        }
         buf ^= 1u;
         // the next tile's publish() orders this tile's TMEM reads (fence::before_thread_sync + warpgroup barrier) before its first MMA
     }
