@@ -138,6 +138,12 @@ int b2n_head_backward(const b2n_model *m, uint32_t M, const float *enc_a, const 
                       const float *amb_aud, const float *g_sigma, const float *g_rgb, const float *g_aud, const float *g_eye, const float *g_unc,
                       const b2n_head_grads *grads, void *stream);
 
+/* Table gradients of the three tri-plane encoders (network.py:208-223) in one launch: grad_planes = b2n_head_grads.d_planes ([3][L][M] fp32),
+ * xyz [M,3] the sample positions in [-bound, bound]; grad_xy / grad_yz / grad_xz [sO] fp32 are accumulated into (zero them first).  Same sums as
+ * three b2n_grid_encode_backward calls on the xy / yz / xz slices (D = 2, C = 1, hash grid). */
+int b2n_triplane_grid_backward(const float *grad_planes, const float *xyz, const int32_t *offsets, float *grad_xy, float *grad_yz, float *grad_xz,
+                               uint32_t M, uint32_t L, float S, uint32_t H, float bound, void *stream);
+
 /* Weight gradient of a bias-free Linear over a tall activation matrix:  dw[out,in] += dy[M,out]^T x[M,in]  (fp16 operands, row-major,
  * fp32 accumulation; dw is accumulated into, zero it first).  1 <= out, in <= 128.  Replaces the weight-gradient GEMM that autograd's
  * LinearBackward runs for every MLP layer of nerf_triplane/network.py:73-94 in a training step (csrc/wgrad.cu). */

@@ -10,8 +10,6 @@ import math
 import torch
 from torch.amp import custom_bwd, custom_fwd
 
-from gridencoder.backend import _backend as _grid_backend
-
 from ._lib import lib
 
 
@@ -59,6 +57,7 @@ class _FusedHead(torch.autograd.Function):
         sig, rgb, aud, eye_att, unc, saved = model.forward_train_fused(x, d, enc_a, ind_code, eye)
         ctx.model, ctx.saved_acts = model, saved
         ctx.with_unc = "hu" in saved
+        x = x.contiguous()
         ctx.save_for_backward(x, enc_a, eye if eye is not None else torch.zeros(1, device=x.device), sig, aud)
         ctx.has_eye = eye is not None
         ctx.mark_non_differentiable()
@@ -93,17 +92,13 @@ class _FusedHead(torch.autograd.Function):
         d_a1, d_a0 = w[5], w[6][:, :36]
         d_e1, d_e0 = w[7][:1], w[8][:, :36]
         d_u1, d_u0 = (w[9][:1], w[10][:, :36]) if ctx.with_unc else (None, None)
-        # table gradients: d enc_x is already in the grid backward's [L, B, C] layout, one slab per plane (xy, yz, xz: network.py:208-212)
-        u = (x + m.bound) / (2 * m.bound)
+        # table gradients: d enc_x is already in the grid backward's [plane][level][sample] layout; the three planes (xy, yz, xz:
+        # network.py:208-212) go through one launch that takes its plane coordinates straight from xyz
         enc = m.encoder_xy
         S, H = float(math.log2(enc.per_level_scale)), enc.base_resolution
-        d_tabs = []
-        plane_in = (u[:, 0:2].contiguous(), u[:, 1:3].contiguous(), torch.stack([u[:, 0], u[:, 2]], dim=1))      # no index tensors: graph-capturable
-        for pl, e_mod in ((0, m.encoder_xy), (1, m.encoder_yz), (2, m.encoder_xz)):
-            ge = torch.zeros_like(e_mod.embeddings)
-            _grid_backend.grid_encode_backward(planes[pl].view(12, M, 1), plane_in[pl], e_mod.embeddings, e_mod.offsets, ge, M, 2, 1, 12, S, H,
-                                               None, None, 0, False)
-            d_tabs.append(ge)
+        d_tabs = [torch.zeros_like(e_mod.embeddings) for e_mod in (m.encoder_xy, m.encoder_yz, m.encoder_xz)]
+        lib().call("b2n_triplane_grid_backward", planes.data_ptr(), x.data_ptr(), enc.offsets.data_ptr(), d_tabs[0].data_ptr(), d_tabs[1].data_ptr(),
+                   d_tabs[2].data_ptr(), M, 12, S, H, float(m.bound), torch.cuda.current_stream().cuda_stream)
         d_enc_a = (gr["d_ew"].float() * sv["att"].float()).sum(0).view_as(enc_a)
         d_ind = gr["d_ci"][:, :4].float().sum(0)
         c = lambda t: None if t is None else t.contiguous()

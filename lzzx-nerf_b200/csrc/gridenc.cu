@@ -350,6 +350,74 @@ __global__ void __launch_bounds__(GP_THREADS) k_grid_bwd_priv(const float *__res
     }
 }
 
+// Tri-plane table backward for the fused training path: the three planes (xy, yz, xz of network.py:208-212) in ONE launch, plane coordinates
+// taken straight from xyz (no slicing / normalisation kernels), gradients read from the backward-data kernel's [3][L][M] slabs.  Same
+// shared-memory privatisation as k_grid_bwd_priv<2, 1>: CTA (slice, level, plane).
+__global__ void __launch_bounds__(GP_THREADS) k_triplane_bwd_priv(const float *__restrict__ grad, const float *__restrict__ xyz, const int32_t *__restrict__ offsets,
+                                                                   float *__restrict__ gt_xy, float *__restrict__ gt_yz, float *__restrict__ gt_xz, uint32_t M,
+                                                                   uint32_t L, uint32_t S_slices, float S, uint32_t H, float bound, float inv_two_bound,
+                                                                   uint32_t smem_floats) {
+    extern __shared__ __align__(16) float s_tab[];
+    const uint32_t level = blockIdx.y, plane = blockIdx.z;
+    const LevelGeom g = level_geom(offsets, level, S, H);
+    float *gtab = (plane == 0 ? gt_xy : (plane == 1 ? gt_yz : gt_xz)) + g.table_off;
+    const uint32_t ca = plane == 1 ? 1u : 0u, cb = plane == 0 ? 1u : 2u;          // xy = (0,1), yz = (1,2), xz = (0,2)
+    const uint32_t n = g.hashmap_size;
+    const bool priv = n <= smem_floats;
+    float *acc = priv ? s_tab : gtab;
+    if (priv) {
+        for (uint32_t i = threadIdx.x; i < n; i += GP_THREADS) s_tab[i] = 0.0f;
+        __syncthreads();
+    }
+    const float *gl = grad + ((size_t)plane * L + level) * M;
+    const uint32_t per = (M + S_slices - 1) / S_slices;
+    const uint32_t b0 = blockIdx.x * per, b1 = min(M, b0 + per);
+    constexpr uint32_t U = 4;
+    for (uint32_t bb = b0 + threadIdx.x; bb < b1; bb += U * GP_THREADS) {
+        float in[U][2], gc[U];
+#pragma unroll
+        for (uint32_t u = 0; u < U; u++) {
+            const uint32_t b = bb + u * GP_THREADS;
+            if (b < b1) {
+                const float pa = __ldg(xyz + 3 * (size_t)b + ca), pb = __ldg(xyz + 3 * (size_t)b + cb);
+                // (x + bound) / (2 bound) like GridEncoder.forward (grid.py:143); exact scaling when 2 bound is a power of two
+                in[u][0] = inv_two_bound != 0.0f ? __fmul_rn(__fadd_rn(pa, bound), inv_two_bound) : __fdiv_rn(__fadd_rn(pa, bound), __fmul_rn(2.0f, bound));
+                in[u][1] = inv_two_bound != 0.0f ? __fmul_rn(__fadd_rn(pb, bound), inv_two_bound) : __fdiv_rn(__fadd_rn(pb, bound), __fmul_rn(2.0f, bound));
+                gc[u] = __ldcs(gl + b);
+            } else { in[u][0] = -1.0f; in[u][1] = -1.0f; gc[u] = 0.0f; }
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < U; u++) {
+            if (in[u][0] < 0.0f || in[u][0] > 1.0f || in[u][1] < 0.0f || in[u][1] > 1.0f) continue;
+            float pos[2];
+            uint32_t pg[2];
+#pragma unroll
+            for (uint32_t d = 0; d < 2; d++) {
+                pos[d] = __fmaf_rn(in[u][d], g.scale, 0.5f);
+                pg[d] = (uint32_t)floorf(pos[d]);
+                pos[d] = __fsub_rn(pos[d], (float)pg[d]);
+            }
+#pragma unroll
+            for (uint32_t idx = 0; idx < 4; idx++) {
+                const float wx = (idx & 1u) ? pos[0] : __fsub_rn(1.0f, pos[0]), wy = (idx & 2u) ? pos[1] : __fsub_rn(1.0f, pos[1]);
+                const uint32_t pl[2] = {pg[0] + (idx & 1u), pg[1] + ((idx >> 1) & 1u)};
+                const uint32_t e = grid_slot<2>(0, false, g.hashmap_size, g.resolution, pl);
+                atomicAdd(acc + e, __fmul_rn(__fmul_rn(wx, wy), gc[u]));
+            }
+        }
+    }
+    if (!priv) return;
+    __syncthreads();
+    if ((g.table_off & 3u) == 0 && (n & 3u) == 0 && ((uintptr_t)gtab & 15u) == 0) {
+        for (uint32_t i = threadIdx.x; i < n / 4; i += GP_THREADS) {
+            const float4 v = reinterpret_cast<const float4 *>(s_tab)[i];
+            if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) red_add_v4_f32(gtab + 4 * (size_t)i, v);
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < n; i += GP_THREADS) { const float v = s_tab[i]; if (v != 0.0f) red_add_f32(gtab + i, v); }
+    }
+}
+
 // largest level (entries) of the grid described by a device `offsets` array — read back ONCE per (pointer, L) and cached; 0 = unknown (the
 // stream is being captured and the geometry has not been seen yet).  The value only sizes the privatised kernel's shared memory: the kernel
 // re-checks every level against it, so a stale entry costs speed, never correctness.
@@ -496,6 +564,29 @@ int b2n_grid_encode_forward(const float *inputs, const void *embeddings, const i
         return fwd_dispatch<__half>(inputs, (const __half *)embeddings, offsets, (__half *)outputs, B, D, C, L, S, H, (__half *)dy_dx, gridtype, align_corners != 0, as_stream(stream));
     set_error("grid_encode_forward: embeddings must be float32 or float16");
     return 2;
+}
+
+int b2n_triplane_grid_backward(const float *grad_planes, const float *xyz, const int32_t *offsets, float *grad_xy, float *grad_yz, float *grad_xz, uint32_t M,
+                               uint32_t L, float S, uint32_t H, float bound, void *stream) {
+    B2N_REQUIRE(grad_planes && xyz && offsets && grad_xy && grad_yz && grad_xz, "triplane_grid_backward: null pointer");
+    B2N_REQUIRE(L >= 1 && L <= 64 && bound > 0.0f, "triplane_grid_backward: L=%u / bound=%f out of range", L, bound);
+    if (M == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    uint32_t mx = largest_level_entries(offsets, L, st);
+    uint32_t fl = (mx != 0 && (size_t)mx * sizeof(float) <= 160 * 1024) ? mx : 0;       // 0: every level scatters straight to global memory
+    const size_t smem = sizeof(float) * (size_t)fl;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(k_triplane_bwd_priv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    uint32_t slices = 3u * (uint32_t)sm_count() / (3u * L);
+    if (const char *e = getenv("B2N_GRID_BWD_SLICES")) slices = (uint32_t)atoi(e);
+    const uint32_t cap = ceil_div<uint32_t>(M, 2048);
+    if (slices > cap) slices = cap;
+    if (slices < 1) slices = 1;
+    int ex = 0;
+    const float two_b = 2.0f * bound;
+    const float inv = frexpf(two_b, &ex) == 0.5f ? 1.0f / two_b : 0.0f;
+    k_triplane_bwd_priv<<<dim3(slices, L, 3), GP_THREADS, smem, st>>>(grad_planes, xyz, offsets, grad_xy, grad_yz, grad_xz, M, L, slices, S, H, bound, inv, fl);
+    return check_launch("triplane_grid_backward");
 }
 
 int b2n_grid_level_scales(float S, uint32_t H, uint32_t L, float *scales_out, void *stream) {
