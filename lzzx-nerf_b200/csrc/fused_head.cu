@@ -376,7 +376,8 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         publish();
         // ---- P1: [aud hidden | eye hidden | sigma hidden (enc_x part)] = X * WA -------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sX_a, sW_a + HW_A, 3, 144, false); mma_commit(bar); }
-        if (has_next) zero_k_padding(sXn);
+        const SampleCoord cn = make_coord(npx, npy, npz, nlive);
+        if (has_next) { zero_k_padding(sXn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[0], cn); }      // trip 0 in flight under P1
         mma_done();
         float eye_att, unc_out = 0.6931471805599453f;       // testing: log(1 + e^0) (network.py:245,278)
         {
@@ -398,7 +399,6 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             // sigmoid evaluated on the fp16 logit, result rounded to fp16 (torch.sigmoid on a half tensor)
             eye_att = round_h(1.0f / (1.0f + expf(-round_h(dot))));
         }
-        const SampleCoord cn = make_coord(npx, npy, npz, nlive);         // the coordinate loads had all of P1 to land
         publish();
         // ---- P2: att = H * WB ; [unc hidden = X * WU] --------------------------------------------------------------------------
         if (t == 0) {
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             if (a.has_unc) issue_mma(tmem_wg + TC_A + 32, sX_a, sW_a + HW_U, 3, 32, false);
             mma_commit(bar);
         }
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[0], cn);
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 0, xsn, ssn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[2], cn); }      // trip 0 lands (issued a phase ago), trip 1 leaves
         mma_done();
         float amb_aud;
         {
@@ -456,27 +456,24 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
                 warp_chunks_out<5>(sX, 0, wrow0, reinterpret_cast<uint8_t *>(a.sv.s_in) + tile_row0 * 160 + 80, 160, rows_valid);
             }
         }
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 0, xsn, ssn);
         publish();
         // ---- P3: sigma hidden += [enc_w, e] * WC -------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[2], cn);
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 1, xsn, ssn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[4], cn); }      // trip 1 lands (issued a phase ago), trip 2 leaves
         mma_done();
         hidden_epilogue<true, false>(tmem_ld + TC_S, sH, t, nullptr);
         if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.h1) + tile_row0 * 128, 128, rows_valid);
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 1, xsn, ssn);
         publish();
         // ---- P4: sigma layer 1 --------------------------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[4], cn);
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 2, xsn, ssn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[6], cn); }      // trip 2 lands (issued a phase ago), trip 3 leaves
         mma_done();
         hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr);
         if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.h2) + tile_row0 * 128, 128, rows_valid);
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 2, xsn, ssn);
         publish();
         // ---- P5: sigma layer 2: cols 0..63 = geo_feat, col 64 = density logit (rows rotated at pack time) -----------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[6], cn);
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 3, xsn, ssn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[8], cn); }      // trip 3 lands (issued a phase ago), trip 4 leaves
         mma_done();
         float sigma;
         {
@@ -496,7 +493,6 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             if (SAVE) warp_chunks_out<2>(sX, 0, wrow0, reinterpret_cast<uint8_t *>(a.sv.c_in) + tile_row0 * 176, 176, rows_valid);
             if (sv_on) c_in_q[10] = make_uint4(pack2(S.ind_h[0], S.ind_h[1]), pack2(S.ind_h[2], S.ind_h[3]), 0u, 0u);
         }
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 3, xsn, ssn);
         publish();
         // ---- P6: color layer 0 = geo * WF0 + sh * WF1 (+ ind-code bias in the epilogue) -------------------------------------
         if (t == 0) {
@@ -505,15 +501,14 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_F1, 1, 64, true);
             mma_commit(bar);
         }
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[8], cn);
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 4, xsn, ssn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[10], cn); }      // trip 4 lands (issued a phase ago), trip 5 leaves
         mma_done();
         hidden_epilogue<true, true>(tmem_ld + TC_S, sH, t, S.ind_bias);
         if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.hc) + tile_row0 * 128, 128, rows_valid);
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 4, xsn, ssn);
         publish();
         // ---- P7: color layer 1 (N padded 3 -> 16) -----------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_G, 4, 16, false); mma_commit(bar); }
-        if (has_next) gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[10], cn);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 5, xsn, ssn);
         mma_done();
         {
             uint32_t c16[16];
@@ -535,7 +530,6 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
                 if (a.unc) __stcs(a.unc + m, unc_out);
             }
         }
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 5, xsn, ssn);
         if (SAVE && has_next) {      // the next tile's feature rows are complete (this warp gathered its own 32 rows)
             const size_t tr0 = (size_t)(tile + tile_stride) * HG_TILE;
             const uint32_t rv = (uint32_t)min((size_t)HG_TILE, (size_t)a.M - tr0);
