@@ -252,7 +252,9 @@ def run_gpu_arm(args, rank, world, local_rank):
     frames_np, auds_np, bitfield = synthetic_inputs(rank)
     model = build_model(dev)
     model.density_bitfield.copy_(torch.from_numpy(bitfield).to(dev))
-    pipe = FramePipeline(model, N_RAYS, depth=1 if args.no_graph else max(1, args.in_flight), use_graph=not args.no_graph)
+    from b2nerf import scene as _scene
+    pipe = FramePipeline(model, N_RAYS, depth=1 if args.no_graph else max(1, args.in_flight), use_graph=not args.no_graph,
+                         camera=(HW, HW) + tuple(_scene.intrinsics(HW, HW)))
     r = pipe.slots[0]
     frames = [(torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)) for o, d in frames_np]
     auds = [torch.from_numpy(a).to(dev) for a in auds_np]
@@ -296,6 +298,12 @@ def run_gpu_arm(args, rank, world, local_rank):
     dev_ms, launches = timed(lambda s: pipe.submit_device(frames[s % POOL][0], frames[s % POOL][1], auds[s % POOL]), args.steps, args.warmup)
     e2e_ms, _ = timed(lambda s: pipe.submit_host(host_o[s % POOL], host_d[s % POOL], host_a[s % POOL], out_hosts[s % pipe.depth]), args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None          # sampled over both timed regions (device-resident and end-to-end)
+    # the lighter end-to-end variant: pose + audio window up, RGB24 frame down, rays generated / image packed on the device
+    pose_ms = None
+    if r.loop_graph is not None and r.fused_audio:
+        host_p = [torch.from_numpy(_scene.camera_pose(rank * 1000 + f).astype(np.float32)).pin_memory() for f in range(POOL)]
+        out_u8 = [torch.empty(N_RAYS, 3, dtype=torch.uint8).pin_memory() for _ in range(pipe.depth)]
+        pose_ms, _ = timed(lambda s: pipe.submit_host_pose(host_p[s % POOL], host_a[s % POOL], out_u8[s % pipe.depth]), args.steps, args.warmup)
     train_info = None
     if not args.no_train:
         train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(4, min(args.steps, 20)), warmup=max(args.warmup, 18), eager=args.train_eager, fused_head=not args.train_unfused)
@@ -325,6 +333,9 @@ def run_gpu_arm(args, rank, world, local_rank):
                    "params": 683509, "weights": "random-init", "frames_per_gpu_per_step": 1, "frames_in_flight_per_gpu": pipe.depth, "parallelism": f"frames sharded over {world} GPU(s), no collective",
                    "l2": f"inputs cycle through {POOL} distinct frames ({POOL * N_RAYS * 24 / 1e6:.0f} MB of rays) > 126 MB L2", "cuda_graph": not args.no_graph, "loop": loop_mode},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": r.h2d_bytes(), "d2h_bytes_per_step": r.d2h_bytes(), "ms_per_step": e2e_ms / args.steps},
+        "e2e_pose_in_rgb8_out": None if pose_ms is None else {"value": world * args.steps / (pose_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 64 + host_a[0].numel() * 4,
+                                                                "d2h_bytes_per_step": N_RAYS * 3, "ms_per_step": pose_ms / args.steps,
+                                                                "note": "rays from the 4x4 pose and the RGB24 packing run on the device (b2n_frame_io)"},
         "gpu_launches": gpu_launches,
         "clocks": clocks,
         "roofline": {"kernel": "k_head_forward (fused tri-plane gather + 7 tcgen05 layers)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

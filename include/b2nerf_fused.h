@@ -84,6 +84,25 @@ int b2n_frame_graph_create(b2n_frame_graph **out, const b2n_model *m, const b2n_
                            uint32_t audio_L, float *enc_a, const float *rays_o, const float *rays_d, uint32_t N, const uint8_t *bitfield,
                            const float *ind_code, const float *eye, const float *bg_color, void *workspace, float *image_out, float *weights_sum_out,
                            float *depth_out);
+/* Optional device-side frame prologue / epilogue, so that only a pose + the audio window go up and one RGB24 frame comes down:
+ *   pose   : device float[16], row-major 4x4 camera-to-world; when non-NULL the graph starts by filling rays_o / rays_d (which must then be
+ *            writable [H*W,3] buffers, N == H*W) with get_rays' all-pixel branch (nerf_triplane/utils.py:227-312: pixel centres + 0.5,
+ *            direction ((i-cx)/fx, (j-cy)/fy, 1) normalised, rotated by pose[:3,:3], origin pose[:3,3]);
+ *   rgb8_out: device uint8[N*3]; when non-NULL the epilogue also writes (image * 255) truncated to uint8 — the bytes the reference pushes to its
+ *            frame queue (TrainerUtil.py:668). */
+typedef struct {
+    const float *pose;
+    float fx, fy, cx, cy;
+    uint32_t H, W;
+    uint8_t *rgb8_out;
+} b2n_frame_io;
+int b2n_frame_graph_create_io(b2n_frame_graph **out, const b2n_model *m, const b2n_render_cfg *cfg, const b2n_audio_weights *audio, const float *auds,
+                              uint32_t audio_L, float *enc_a, float *rays_o, float *rays_d, uint32_t N, const uint8_t *bitfield,
+                              const float *ind_code, const float *eye, const float *bg_color, void *workspace, float *image_out, float *weights_sum_out,
+                              float *depth_out, const b2n_frame_io *io);
+/* the two stages as plain calls (also usable outside a graph) */
+int b2n_get_rays(const float *pose, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W, float *rays_o, float *rays_d, void *stream);
+int b2n_image_to_rgb8(const float *image, uint32_t n_pixels, uint8_t *rgb8_out, void *stream);
 int b2n_frame_graph_launch(b2n_frame_graph *fg, void *stream);
 int b2n_frame_graph_info(const b2n_frame_graph *fg, uint64_t *kernels_fixed, uint64_t *kernels_per_iteration);
 void b2n_frame_graph_destroy(b2n_frame_graph *fg);

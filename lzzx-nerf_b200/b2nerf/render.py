@@ -13,8 +13,12 @@ from .model import HeadModel
 
 
 class FrameRenderer:
-    def __init__(self, model: HeadModel, n_rays, eye=0.4, ind_index=0, dt_gamma=1.0 / 256, max_steps=16, T_thresh=1e-4, use_graph=True, fused_audio=True):
+    def __init__(self, model: HeadModel, n_rays, eye=0.4, ind_index=0, dt_gamma=1.0 / 256, max_steps=16, T_thresh=1e-4, use_graph=True, fused_audio=True,
+                 camera=None):
+        """camera = (H, W, fx, fy, cx, cy): also build the device-side prologue / epilogue (rays from a 4x4 pose, RGB24 output), so that
+        render_host_pose() moves a pose + the audio window up and one uint8 frame down."""
         self.m = model
+        self.camera = camera
         self.dev = next(model.parameters()).device
         self.N = int(n_rays)
         self.kw = dict(dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh)
@@ -32,6 +36,12 @@ class FrameRenderer:
         self.launches_per_frame = None
         self.ws = torch.empty(self.N, device=d)
         self.depth = torch.empty(self.N, device=d)
+        if camera is not None:
+            if int(camera[0]) * int(camera[1]) != self.N:
+                raise RuntimeError("FrameRenderer: camera H*W must equal n_rays")
+            self.pose = torch.eye(4, device=d).contiguous()
+            self.rgb8 = torch.empty(self.N, 3, dtype=torch.uint8, device=d)
+            self.pose_graph = None
         model.cache_host_constants()
         model.pack()
         if use_graph:
@@ -71,6 +81,38 @@ class FrameRenderer:
         L.call("b2n_frame_graph_info", h, ctypes.byref(kf), ctypes.byref(kb))
         self.kernels_fixed, self.kernels_per_iteration = int(kf.value), int(kb.value)
 
+    @torch.no_grad()
+    def _build_pose_graph(self):
+        """Second graph: pose -> rays (k_frame_rays) -> the same frame -> float image + RGB24 (k_frame_finish)."""
+        import ctypes
+        from ._lib import lib
+        L, m = lib(), self.m
+        H, W, fx, fy, cx, cy = self.camera
+        cfg, aw, ind, eye = self._graph_keep
+        io = _FrameIoC(self.pose.data_ptr(), float(fx), float(fy), float(cx), float(cy), int(H), int(W), self.rgb8.data_ptr())
+        self._pose_keep = io
+        h = ctypes.c_void_p()
+        torch.cuda.synchronize(self.dev)
+        L.call("b2n_frame_graph_create_io", ctypes.byref(h), m.handle, ctypes.byref(cfg), ctypes.byref(aw) if aw is not None else None,
+               self.auds.data_ptr(), self.auds.shape[2], self.enc_a.data_ptr(), self.rays_o.data_ptr(), self.rays_d.data_ptr(), self.N,
+               m.density_bitfield.data_ptr(), ind.data_ptr(), eye.data_ptr(), None, self._graph_ws.data_ptr(),
+               self.image.data_ptr(), self.ws.data_ptr(), self.depth.data_ptr(), ctypes.byref(io))
+        self.pose_graph = h
+
+    @torch.no_grad()
+    def render_host_pose(self, pose_host, auds_host, out_u8_host):
+        """Pinned host pose [4,4] + audio window in, pinned uint8 [N,3] frame out: 64 B + the audio window up, N x 3 bytes down per frame."""
+        from ._lib import lib
+        if self.camera is None or self.loop_graph is None or not self.fused_audio:
+            raise RuntimeError("render_host_pose needs FrameRenderer(camera=...), the loop graph and the fused audio encoder")
+        if self.pose_graph is None:
+            self._build_pose_graph()
+        self.pose.copy_(pose_host.view(4, 4), non_blocking=True)
+        self.auds.copy_(auds_host, non_blocking=True)
+        lib().call("b2n_frame_graph_launch", self.pose_graph, torch.cuda.current_stream(self.dev).cuda_stream)
+        out_u8_host.copy_(self.rgb8, non_blocking=True)
+        return out_u8_host
+
     def last_iterations(self):
         """Loop iterations the last frame executed (synchronises)."""
         import ctypes
@@ -97,6 +139,8 @@ class FrameRenderer:
             if self.loop_graph is not None:
                 from ._lib import lib
                 lib().raw("b2n_frame_graph_destroy")(self.loop_graph)
+                if getattr(self, "pose_graph", None) is not None:
+                    lib().raw("b2n_frame_graph_destroy")(self.pose_graph)
         except Exception:
             pass
 
@@ -145,6 +189,15 @@ class FrameRenderer:
         return self.image.numel() * 4
 
 
+import ctypes as _ct
+
+
+class _FrameIoC(_ct.Structure):
+    """b2n_frame_io (include/b2nerf_fused.h)"""
+    _fields_ = [("pose", _ct.c_void_p), ("fx", _ct.c_float), ("fy", _ct.c_float), ("cx", _ct.c_float), ("cy", _ct.c_float), ("H", _ct.c_uint32),
+                ("W", _ct.c_uint32), ("rgb8_out", _ct.c_void_p)]
+
+
 class FramePipeline:
     """`depth` frames in flight on one GPU: frame k runs on renderer/stream k % depth, so the host<->device copies and the kernel
     tails / dependent-launch gaps of one frame overlap the next frame's work (frames are independent — the reference's test loop,
@@ -178,6 +231,14 @@ class FramePipeline:
         i = self._slot()
         with torch.cuda.stream(self.streams[i]):
             self.slots[i].render_host(rays_o_host, rays_d_host, auds_host, out_host)
+            self.done[i].record()
+        return i
+
+    def submit_host_pose(self, pose_host, auds_host, out_u8_host):
+        """Enqueue one frame from a pinned host pose + audio window; the uint8 frame lands in out_u8_host (renderers built with camera=...)."""
+        i = self._slot()
+        with torch.cuda.stream(self.streams[i]):
+            self.slots[i].render_host_pose(pose_host, auds_host, out_u8_host)
             self.done[i].record()
         return i
 

@@ -74,6 +74,12 @@ def rays_for_pixels(pose, H, W, pix_i, pix_j, fovy_deg=FOVY_DEG):
     return np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32)
 
 
+def intrinsics(H=512, W=512, fovy_deg=FOVY_DEG):
+    """(fx, fy, cx, cy) of the synthetic pinhole camera used by rays_for_pixels."""
+    focal = H / (2.0 * math.tan(math.radians(fovy_deg) / 2.0))
+    return focal, focal, W / 2.0, H / 2.0
+
+
 def frame_rays(frame=0, H=512, W=512, seed=0):
     j, i = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
     return rays_for_pixels(camera_pose(frame, seed=seed), H, W, i.ravel(), j.ravel())

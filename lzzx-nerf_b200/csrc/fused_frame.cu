@@ -288,9 +288,32 @@ __global__ void __launch_bounds__(FR_THREADS) k_frame_composite(float T_thresh, 
     }
 }
 
+// get_rays, all-pixel branch (nerf_triplane/utils.py:227-312) for one pose: pixel n = (row j, column i), direction ((i + 0.5 - cx) / fx,
+// (j + 0.5 - cy) / fy, 1) / norm rotated by pose[:3,:3]; origin pose[:3,3].  fp32, one rounding per torch op.
+__global__ void __launch_bounds__(256) k_frame_rays(const float *__restrict__ pose, float fx, float fy, float cx, float cy, uint32_t W, uint32_t N,
+                                                     float *__restrict__ rays_o, float *__restrict__ rays_d) {
+    const float r00 = pose[0], r01 = pose[1], r02 = pose[2], ox = pose[3], r10 = pose[4], r11 = pose[5], r12 = pose[6], oy = pose[7],
+                r20 = pose[8], r21 = pose[9], r22 = pose[10], oz = pose[11];
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        const uint32_t j = n / W, i = n - j * W;
+        const float xs = __fdiv_rn(__fsub_rn(__fadd_rn((float)i, 0.5f), cx), fx), ys = __fdiv_rn(__fsub_rn(__fadd_rn((float)j, 0.5f), cy), fy);
+        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(xs, xs), __fmul_rn(ys, ys)), 1.0f));
+        const float dx = __fdiv_rn(xs, nrm), dy = __fdiv_rn(ys, nrm), dz = __fdiv_rn(1.0f, nrm);
+        // directions @ R^T: d_k = sum_c dir_c * R[k][c]
+        __stcs(rays_d + 3 * (size_t)n, __fmaf_rn(dz, r02, __fmaf_rn(dy, r01, __fmul_rn(dx, r00))));
+        __stcs(rays_d + 3 * (size_t)n + 1, __fmaf_rn(dz, r12, __fmaf_rn(dy, r11, __fmul_rn(dx, r10))));
+        __stcs(rays_d + 3 * (size_t)n + 2, __fmaf_rn(dz, r22, __fmaf_rn(dy, r21, __fmul_rn(dx, r20))));
+        __stcs(rays_o + 3 * (size_t)n, ox); __stcs(rays_o + 3 * (size_t)n + 1, oy); __stcs(rays_o + 3 * (size_t)n + 2, oz);
+    }
+}
+// (image * 255).astype(uint8): truncation (TrainerUtil.py:668); image is already clamped to [0, 1]
+__global__ void __launch_bounds__(256) k_image_rgb8(const float *__restrict__ image, uint32_t n3, uint8_t *__restrict__ out) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n3; k += gridDim.x * blockDim.x) out[k] = (uint8_t)(int)__fmul_rn(image[k], 255.0f);
+}
+
 // image = clamp(image + (1 - weights_sum) * bg, 0, 1)  (renderer.py:559-561)
 __global__ void __launch_bounds__(256) k_frame_finish(uint32_t N, const float *__restrict__ bg, FrameWs w, float *__restrict__ image_out,
-                                                       float *__restrict__ ws_out, float *__restrict__ depth_out) {
+                                                       float *__restrict__ ws_out, float *__restrict__ depth_out, uint8_t *__restrict__ rgb8_out) {
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
         const float ws = w.ws[n];
         const float k = __fsub_rn(1.0f, ws);
@@ -298,7 +321,9 @@ __global__ void __launch_bounds__(256) k_frame_finish(uint32_t N, const float *_
         for (int ch = 0; ch < 3; ch++) {
             const float b = bg ? bg[3 * (size_t)n + ch] : 1.0f;
             const float v = __fadd_rn(w.image[3 * (size_t)n + ch], __fmul_rn(k, b));
-            __stcs(image_out + 3 * (size_t)n + ch, fminf(fmaxf(v, 0.0f), 1.0f));
+            const float c = fminf(fmaxf(v, 0.0f), 1.0f);
+            __stcs(image_out + 3 * (size_t)n + ch, c);
+            if (rgb8_out) rgb8_out[3 * (size_t)n + ch] = (uint8_t)(int)__fmul_rn(c, 255.0f);
         }
         if (ws_out) ws_out[n] = ws;
         if (depth_out) depth_out[n] = w.depth[n];
@@ -311,9 +336,16 @@ __global__ void __launch_bounds__(256) k_frame_finish(uint32_t N, const float *_
 struct FramePlan {
     const b2n_model *m; b2n_render_cfg cfg; const float *rays_o, *rays_d; uint32_t N; const uint8_t *bitfield;
     const float *enc_a, *ind_code, *eye, *bg; FrameWs w; float *image_out, *ws_out, *depth_out;
+    b2n_frame_io io;        // pose == NULL / rgb8_out == NULL: stage not used
 };
 
 static int enqueue_init(const FramePlan &p, cudaStream_t st) {
+    if (p.io.pose) {
+        const uint32_t g0 = ceil_div<uint32_t>(p.N, 256);
+        k_frame_rays<<<g0 < (uint32_t)sm_count() * 8 ? g0 : (uint32_t)sm_count() * 8, 256, 0, st>>>(p.io.pose, p.io.fx, p.io.fy, p.io.cx, p.io.cy, p.io.W, p.N,
+                                                                                                 const_cast<float *>(p.rays_o), const_cast<float *>(p.rays_d));
+        if (check_launch("render_frame(rays)")) return 1;
+    }
     // the argument needs probe positions == ray points, i.e. the marching interval (the aabb) inside the [-bound, bound]^3 cube where clamp() is a no-op
     int inside = 1;
     for (int a = 0; a < 3; a++) inside &= (p.cfg.aabb[a] >= -p.cfg.bound && p.cfg.aabb[3 + a] <= p.cfg.bound);
@@ -338,7 +370,7 @@ static int enqueue_iteration(const FramePlan &p, cudaStream_t st, cudaGraphCondi
 static int enqueue_finish(const FramePlan &p, cudaStream_t st) {
     const uint32_t sms = (uint32_t)sm_count();
     uint32_t g = ceil_div<uint32_t>(p.N, 256); if (g > sms * 8) g = sms * 8;
-    k_frame_finish<<<g, 256, 0, st>>>(p.N, p.bg, p.w, p.image_out, p.ws_out, p.depth_out);
+    k_frame_finish<<<g, 256, 0, st>>>(p.N, p.bg, p.w, p.image_out, p.ws_out, p.depth_out, p.io.rgb8_out);
     return check_launch("render_frame(finish)");
 }
 
@@ -350,6 +382,7 @@ static int make_plan(FramePlan &p, const b2n_model *m, const b2n_render_cfg *cfg
     B2N_REQUIRE(cfg->cascade >= 1 && cfg->cascade <= 24 && cfg->grid_size >= 1 && cfg->grid_size <= 1024, "render_frame: bad cascade / grid size");
     p.m = m; p.cfg = *cfg; p.rays_o = rays_o; p.rays_d = rays_d; p.N = N; p.bitfield = bitfield; p.enc_a = enc_a; p.ind_code = ind_code; p.eye = eye; p.bg = bg_color;
     p.image_out = image_out; p.ws_out = ws_out; p.depth_out = depth_out;
+    p.io = b2n_frame_io{};
     carve(&p.w, (uint8_t *)workspace, N);
     return 0;
 }
@@ -384,14 +417,43 @@ int b2n_render_frame(const b2n_model *m, const b2n_render_cfg *cfg, const float 
     return enqueue_finish(p, st);
 }
 
+int b2n_get_rays(const float *pose, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W, float *rays_o, float *rays_d, void *stream) {
+    B2N_REQUIRE(pose && rays_o && rays_d, "get_rays: null pointer");
+    B2N_REQUIRE(fx != 0.0f && fy != 0.0f, "get_rays: zero focal length");
+    const uint64_t N64 = (uint64_t)H * W;
+    B2N_REQUIRE(N64 <= 0xffffffffull, "get_rays: image too large");
+    if (N64 == 0) return 0;
+    const uint32_t N = (uint32_t)N64, g0 = ceil_div<uint32_t>(N, 256), cap = (uint32_t)sm_count() * 8;
+    k_frame_rays<<<g0 < cap ? g0 : cap, 256, 0, as_stream(stream)>>>(pose, fx, fy, cx, cy, W, N, rays_o, rays_d);
+    return check_launch("get_rays");
+}
+
+int b2n_image_to_rgb8(const float *image, uint32_t n_pixels, uint8_t *rgb8_out, void *stream) {
+    B2N_REQUIRE(image && rgb8_out, "image_to_rgb8: null pointer");
+    if (n_pixels == 0) return 0;
+    const uint32_t n3 = 3u * n_pixels, g0 = ceil_div<uint32_t>(n3, 256), cap = (uint32_t)sm_count() * 8;
+    k_image_rgb8<<<g0 < cap ? g0 : cap, 256, 0, as_stream(stream)>>>(image, n3, rgb8_out);
+    return check_launch("image_to_rgb8");
+}
+
 int b2n_frame_graph_create(b2n_frame_graph **out, const b2n_model *m, const b2n_render_cfg *cfg, const b2n_audio_weights *audio, const float *auds,
                            uint32_t audio_L, float *enc_a, const float *rays_o, const float *rays_d, uint32_t N, const uint8_t *bitfield,
                            const float *ind_code, const float *eye, const float *bg_color, void *workspace, float *image_out, float *weights_sum_out,
                            float *depth_out) {
+    return b2n_frame_graph_create_io(out, m, cfg, audio, auds, audio_L, enc_a, const_cast<float *>(rays_o), const_cast<float *>(rays_d), N, bitfield, ind_code, eye,
+                                     bg_color, workspace, image_out, weights_sum_out, depth_out, nullptr);
+}
+
+int b2n_frame_graph_create_io(b2n_frame_graph **out, const b2n_model *m, const b2n_render_cfg *cfg, const b2n_audio_weights *audio, const float *auds,
+                              uint32_t audio_L, float *enc_a, float *rays_o, float *rays_d, uint32_t N, const uint8_t *bitfield,
+                              const float *ind_code, const float *eye, const float *bg_color, void *workspace, float *image_out, float *weights_sum_out,
+                              float *depth_out, const b2n_frame_io *io) {
     B2N_REQUIRE(out && N > 0, "frame_graph_create: null pointer / empty frame");
+    B2N_REQUIRE(!io || !io->pose || ((uint64_t)io->H * io->W == N && io->fx != 0.0f && io->fy != 0.0f), "frame_graph_create: pose given but H*W != N or zero focal length");
     B2N_REQUIRE(!audio || (auds && enc_a), "frame_graph_create: audio weights given without auds / enc_a buffers");
     FramePlan p;
     if (int rc = make_plan(p, m, cfg, rays_o, rays_d, N, bitfield, enc_a, ind_code, eye, bg_color, workspace, image_out, weights_sum_out, depth_out)) return rc;
+    if (io) p.io = *io;
     b2n_frame_graph *fg = new b2n_frame_graph();
     cudaStream_t cs = nullptr;
     int rc = 3;

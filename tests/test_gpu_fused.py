@@ -303,3 +303,51 @@ def test_update_extra_state_fused_matches_reference_graph():
     with torch.autocast("cuda", dtype=torch.float16):
         md2 = m.update_extra_state(auds, eye, fused=True, density_thresh=1e9)
     assert md2 > 0
+
+
+def test_get_rays_and_rgb8_match_reference_formulas():
+    """b2n_get_rays vs get_rays' all-pixel branch (utils.py:227-312, float64 numpy restatement in scene.rays_for_pixels) and b2n_image_to_rgb8 vs
+    (image * 255).astype(uint8) (TrainerUtil.py:668, bit-exact)."""
+    from b2nerf._lib import lib
+    from b2nerf import scene
+    H, W = 96, 160
+    pose = scene.camera_pose(5).astype(np.float32)
+    fx, fy, cx, cy = scene.intrinsics(H, W)
+    pd = torch.from_numpy(pose).cuda().contiguous()
+    ro, rd = torch.empty(H * W, 3, device="cuda"), torch.empty(H * W, 3, device="cuda")
+    lib().call("b2n_get_rays", pd.data_ptr(), float(fx), float(fy), float(cx), float(cy), H, W, ro.data_ptr(), rd.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    j, i = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    o_ref, d_ref = scene.rays_for_pixels(pose.astype(np.float64), H, W, i.ravel(), j.ravel())
+    # rays_for_pixels uses one focal derived from H: same as intrinsics()
+    assert np.abs(rd.cpu().numpy() - d_ref).max() < 2e-6 and np.array_equal(ro.cpu().numpy(), o_ref)
+    assert abs(float(rd.norm(dim=1).mean()) - 1.0) < 1e-6
+    img = torch.rand(H * W, 3, device="cuda"); img[0] = 1.0; img[1] = 0.0
+    u8 = torch.empty(H * W, 3, dtype=torch.uint8, device="cuda")
+    lib().call("b2n_image_to_rgb8", img.data_ptr(), H * W, u8.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert np.array_equal(u8.cpu().numpy(), (img.cpu().numpy() * 255).astype(np.uint8))
+
+
+def test_pose_in_rgb8_out_frame_equals_rays_in_frame():
+    """FrameRenderer.render_host_pose (pose -> rays on the device -> frame -> RGB24) == the rays-in path fed with b2n_get_rays' rays, bit for bit."""
+    from b2nerf.render import FrameRenderer
+    from b2nerf._lib import lib
+    from b2nerf import scene
+    m = _model(seed=2)
+    m.density_bitfield.copy_(torch.from_numpy(scene.bitfield_from_grid(scene.density_grid())).cuda())
+    H = W = 128
+    cam = (H, W) + tuple(scene.intrinsics(H, W))
+    r = FrameRenderer(m, H * W, camera=cam)
+    pose = torch.from_numpy(scene.camera_pose(3).astype(np.float32)).pin_memory()
+    auds = torch.from_numpy(scene.audio_window(3)).pin_memory()
+    out_u8 = torch.empty(H * W, 3, dtype=torch.uint8).pin_memory()
+    r.render_host_pose(pose, auds, out_u8)
+    torch.cuda.synchronize()
+    img_pose = r.image.clone()
+    ro, rd = torch.empty(H * W, 3, device="cuda"), torch.empty(H * W, 3, device="cuda")
+    lib().call("b2n_get_rays", pose.cuda().data_ptr(), *[float(v) for v in cam[2:]], H, W, ro.data_ptr(), rd.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    out_f = torch.empty(H * W, 3).pin_memory()
+    r.render_host(ro.cpu().pin_memory(), rd.cpu().pin_memory(), auds, out_f)
+    torch.cuda.synchronize()
+    assert torch.equal(r.image, img_pose)
+    assert np.array_equal(out_u8.numpy(), (out_f.numpy() * 255).astype(np.uint8))
+    assert 0.0 < float(img_pose.mean()) < 1.0 and int((out_u8 < 250).sum()) > 100      # the head is in the picture
