@@ -123,7 +123,7 @@ typedef struct {
     void *h2;     /* [M,64]  relu(sigma_net.net.1) */
     void *c_in;   /* [M,88]  color_net input [sh 16 | geo_feat 64 | ind_code 4 | 0 0 0 0]            (network.py:267-270) */
     void *hc;     /* [M,64]  relu(color_net.net.0) */
-    void *misc;   /* [M,8]   sigmoid(rgb logits) x3, eye_att, unc logit, 0 0 0 */
+    void *misc;   /* [M,8]   sigmoid(rgb logits) x3, eye_att, unc logit, 1.0 (ones column: column sums via b2n_linear_wgrad), 0 0 */
 } b2n_head_saved;
 
 /* b2n_head_forward on all M rows + the saved activations (training forward of NeRFNetwork.forward, network.py:252-311). */

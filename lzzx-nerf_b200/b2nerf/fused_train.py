@@ -83,6 +83,9 @@ class _FusedHead(torch.autograd.Function):
         # weight gradients: one pass over (dY, X) per matrix
         pairs = [(gr["d_rl"], sv["hc"]), (gr["d_hc"], sv["c_in"]), (gr["d_o"], sv["h2"]), (gr["d_h2"], sv["h1"]), (gr["d_h1"], sv["s_in"]),
                  (gr["d_att"], sv["ha"]), (gr["d_ha"], sv["x36"]), (gr["d_el"], sv["he"]), (gr["d_he"], sv["x36"])]
+        # two reductions over the samples ride along as products: d enc_a[j] = sum_m d_ew[m,j] att[m,j] = diag(d_ew^T att);
+        # d ind_code[i] = sum_m d_ci[m,i] = (d_ci^T misc)[i, 5]  (misc column 5 is a column of ones)
+        pairs += [(gr["d_ew"], sv["att"]), (gr["d_ci"], sv["misc"])]
         if ctx.with_unc:
             pairs += [(gr["d_ul"], sv["hu"]), (gr["d_hu"], sv["x36"])]
         w = _wgrad_all(pairs)
@@ -91,7 +94,7 @@ class _FusedHead(torch.autograd.Function):
         d_s1, d_s0 = w[3], torch.cat([w[4][:, :36], w[4][:, 40:73]], dim=1)      # s_in = [enc_x 36 | pad 4 | enc_w 32 | e | pad 7]
         d_a1, d_a0 = w[5], w[6][:, :36]
         d_e1, d_e0 = w[7][:1], w[8][:, :36]
-        d_u1, d_u0 = (w[9][:1], w[10][:, :36]) if ctx.with_unc else (None, None)
+        d_u1, d_u0 = (w[11][:1], w[12][:, :36]) if ctx.with_unc else (None, None)
         # table gradients: d enc_x is already in the grid backward's [plane][level][sample] layout; the three planes (xy, yz, xz:
         # network.py:208-212) go through one launch that takes its plane coordinates straight from xyz
         enc = m.encoder_xy
@@ -99,8 +102,8 @@ class _FusedHead(torch.autograd.Function):
         d_tabs = [torch.zeros_like(e_mod.embeddings) for e_mod in (m.encoder_xy, m.encoder_yz, m.encoder_xz)]
         lib().call("b2n_triplane_grid_backward", planes.data_ptr(), x.data_ptr(), enc.offsets.data_ptr(), d_tabs[0].data_ptr(), d_tabs[1].data_ptr(),
                    d_tabs[2].data_ptr(), M, 12, S, H, float(m.bound), torch.cuda.current_stream().cuda_stream)
-        d_enc_a = (gr["d_ew"].float() * sv["att"].float()).sum(0).view_as(enc_a)
-        d_ind = gr["d_ci"][:, :4].float().sum(0)
+        d_enc_a = torch.diagonal(w[9]).reshape(enc_a.shape)
+        d_ind = w[10][:4, 5]
         c = lambda t: None if t is None else t.contiguous()
         return (None, None, None, d_enc_a, d_ind, None, d_tabs[0], d_tabs[1], d_tabs[2], c(d_a0), c(d_a1), c(d_e0), c(d_e1), c(d_s0), c(d_s1), c(d_s2),
                 c(d_c0), c(d_c1), c(d_u0), c(d_u1))

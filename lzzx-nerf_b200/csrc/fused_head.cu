@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
                     sg[j] = s;
                     rgb[j] = round_h(round_h(s * 1.002f) - 0.001f);
                 }
-                if (SAVE) reinterpret_cast<uint4 *>(a.sv.misc)[m] = make_uint4(pack2(sg[0], sg[1]), pack2(sg[2], eye_att), pack2(unc_logit, 0.0f), 0u);
+                if (SAVE) reinterpret_cast<uint4 *>(a.sv.misc)[m] = make_uint4(pack2(sg[0], sg[1]), pack2(sg[2], eye_att), pack2(unc_logit, 1.0f), 0u);      // column 5 = 1: a ones column for column sums through the wgrad kernel
                 if (a.sigmas) __stcs(a.sigmas + m, sigma);
                 if (a.rgbs) { __stcs(a.rgbs + 3 * (size_t)m, rgb[0]); __stcs(a.rgbs + 3 * (size_t)m + 1, rgb[1]); __stcs(a.rgbs + 3 * (size_t)m + 2, rgb[2]); }
                 if (a.amb_aud) __stcs(a.amb_aud + m, amb_aud);

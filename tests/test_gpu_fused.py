@@ -268,6 +268,7 @@ def test_head_forward_train_saves_the_reference_activations():
     close("s_in", torch.cat([sv["s_in"][:, :36], sv["s_in"][:, 40:73]], dim=1), s_in, 1e-2)
     close("h1", sv["h1"], h1, 2e-2); close("h2", sv["h2"], h2, 2e-2)
     close("c_in", sv["c_in"][:, :84], c_in, 3e-2); close("hc", sv["hc"], hc, 3e-2)
+    assert float((sv["misc"][:, 5] - 1).abs().max()) == 0 and float(sv["misc"][:, 6:].abs().max()) == 0
     close("misc rgb", sv["misc"][:, :3], s3, 1e-2); close("misc eye", sv["misc"][:, 3:4], eye_att, 5e-3); close("misc unc", sv["misc"][:, 4:5], ul, 1e-2)
 
 
