@@ -92,21 +92,25 @@ __global__ void __launch_bounds__(256) k_packbits(const float *__restrict__ grid
     }
 }
 
-// raymarching.cu:304-335 — 6-neighbour max in Morton order
-__global__ void __launch_bounds__(256) k_morton3D_dilation(const float *__restrict__ grid, uint32_t C, uint32_t H, float *__restrict__ out) {
+// raymarching.cu:304-335 — 6-neighbour max in Morton order.  Neighbours are found IN Morton space: with X = 0x49249249 the x bits of an index,
+// x + 1 is ((m | ~X) + 1) & X and x - 1 is ((m & X) - 1) & X (carry / borrow ripple through the foreign bits), so no decode / re-encode per
+// neighbour; "x + 1 < H" is a comparison of dilated values (dilation preserves order) against dilate(H).
+__global__ void __launch_bounds__(256) k_morton3D_dilation(const float *__restrict__ grid, uint32_t C, uint32_t H, uint32_t dilH, float *__restrict__ out) {
     const uint32_t H3 = H * H * H, total = C * H3;
+    constexpr uint32_t X = 0x49249249u;
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < total; n += gridDim.x * blockDim.x) {
         const uint32_t c = n / H3, m = n - c * H3;
-        const uint32_t x = compact3(m), y = compact3(m >> 1), z = compact3(m >> 2);
         const float *g = grid + (size_t)c * H3;
-        float r = grid[n];
-        if (x + 1 < H) r = fmaxf(r, g[morton_enc(x + 1, y, z)]);
-        if (x > 0) r = fmaxf(r, g[morton_enc(x - 1, y, z)]);
-        if (y + 1 < H) r = fmaxf(r, g[morton_enc(x, y + 1, z)]);
-        if (y > 0) r = fmaxf(r, g[morton_enc(x, y - 1, z)]);
-        if (z + 1 < H) r = fmaxf(r, g[morton_enc(x, y, z + 1)]);
-        if (z > 0) r = fmaxf(r, g[morton_enc(x, y, z - 1)]);
-        out[n] = r;
+        float r = __ldg(grid + n);
+#pragma unroll
+        for (uint32_t a = 0; a < 3; a++) {
+            const uint32_t A = X << a;                       // bits of this axis
+            const uint32_t ma = m & A, rest = m & ~A;
+            const uint32_t up = ((m | ~A) + (1u << a)) & A;  // axis coordinate + 1 (wraps to 0 past the last bit)
+            if (up != 0 && (uint64_t)up < ((uint64_t)dilH << a)) r = fmaxf(r, __ldg(g + (rest | up)));
+            if (ma != 0) r = fmaxf(r, __ldg(g + (rest | ((ma - (1u << a)) & A))));
+        }
+        __stcs(out + n, r);
     }
 }
 
@@ -319,7 +323,7 @@ int b2n_morton3D_dilation(const float *grid, uint32_t C, uint32_t H, float *grid
     B2N_REQUIRE(grid && grid_dilation, "morton3D_dilation: null pointer");
     B2N_REQUIRE(H >= 1 && H <= 1024, "morton3D_dilation: H=%u out of the 10-bit Morton range", H);
     if (C == 0) return 0;
-    k_morton3D_dilation<<<grid_for(C * H * H * H, 256), 256, 0, as_stream(stream)>>>(grid, C, H, grid_dilation);
+    k_morton3D_dilation<<<grid_for(C * H * H * H, 256), 256, 0, as_stream(stream)>>>(grid, C, H, morton_enc(H, 0, 0), grid_dilation);
     return check_launch("morton3D_dilation");
 }
 
