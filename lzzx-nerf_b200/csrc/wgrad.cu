@@ -227,59 +227,76 @@ __device__ __forceinline__ void issue_operand(uint32_t s_base, const __half *__r
     }
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1) k_linear_wgrad_pipe(const __half *__restrict__ dy, const __half *__restrict__ x, uint32_t M, uint32_t out_dim,
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised: 8 producer warps keep the cp.async ring full (each thread signals "my part of chunk i has landed" on full[stage]), one extra
+// warp issues the MMAs (waits full[stage], commits to empty[stage]); nobody executes a CTA-wide barrier inside the loop.
+constexpr uint32_t WP_THREADS = WG_THREADS + 32;
+
+__global__ void __launch_bounds__(WP_THREADS, 1) k_linear_wgrad_pipe(const __half *__restrict__ dy, const __half *__restrict__ x, uint32_t M, uint32_t out_dim,
                                                                       uint32_t in_dim, float *__restrict__ dw, uint32_t replicas, uint32_t rstride) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(base + WP_STAGES * WP_STAGE_BYTES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + WP_STAGES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + WP_STAGES * WP_STAGE_BYTES), *empty = full + WP_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + WP_STAGES);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const bool producer = tid < WG_THREADS;
     const uint32_t n_chunks = (M + WG_CHUNK - 1) / WG_CHUNK;
     const uint32_t n_pad = (in_dim + 15u) & ~15u;
     dw += (size_t)(blockIdx.x % replicas) * rstride;
     const bool vec4 = (in_dim & 3u) == 0 && ((uintptr_t)dw & 15u) == 0;
 
-    for (uint32_t i = tid; i < WP_STAGES * WP_STAGE_BYTES / 16; i += WG_THREADS) reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) { for (uint32_t s = 0; s < WP_STAGES; s++) mbar_init(&bars[s], 1); fence_mbar_init(); }
-    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    for (uint32_t i = tid; i < WP_STAGES * WP_STAGE_BYTES / 16; i += WP_THREADS) reinterpret_cast<uint4 *>(base)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (uint32_t s = 0; s < WP_STAGES; s++) { mbar_init(&full[s], WG_THREADS); mbar_init(&empty[s], 1); }
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 128);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t idesc = idesc_f16(128, n_pad) | (1u << 15) | (1u << 16);
     const uint32_t base_a = smem_u32(base);
-    const RowMap ra = row_map(out_dim), rb = row_map(in_dim);
     const uint32_t my_n = blockIdx.x < n_chunks ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    auto issue = [&](uint32_t i) {                                        // chunk i of this CTA -> stage i % WP_STAGES
-        const uint32_t st = base_a + (i % WP_STAGES) * WP_STAGE_BYTES, row0 = (blockIdx.x + i * gridDim.x) * WG_CHUNK;
-        issue_operand(st, dy, ra, row0, M, out_dim);
-        issue_operand(st + WG_OPERAND_BYTES, x, rb, row0, M, in_dim);
-    };
-    for (uint32_t i = 0; i + 1 < WP_STAGES; i++) { if (i < my_n) issue(i); cp_async_commit(); }
-    for (uint32_t i = 0; i < my_n; i++) {
-        cp_async_wait<WP_STAGES - 2>();                                   // this thread's copies of chunk i have landed
-        fence_proxy_async();
-        __syncthreads();                                                  // ... and everybody else's
-        const uint32_t s = i % WP_STAGES;
-        if (tid == 0) {
+    constexpr uint32_t AHEAD = WP_STAGES - 1;                             // chunks in flight per producer
+    if (producer) {
+        const RowMap ra = row_map(out_dim), rb = row_map(in_dim);
+        auto issue = [&](uint32_t i) {                                    // chunk i of this CTA -> stage i % WP_STAGES
+            const uint32_t st = base_a + (i % WP_STAGES) * WP_STAGE_BYTES, row0 = (blockIdx.x + i * gridDim.x) * WG_CHUNK;
+            issue_operand(st, dy, ra, row0, M, out_dim);
+            issue_operand(st + WG_OPERAND_BYTES, x, rb, row0, M, in_dim);
+        };
+        for (uint32_t i = 0; i < AHEAD; i++) { if (i < my_n) issue(i); cp_async_commit(); }
+        for (uint32_t i = 0; i < my_n; i++) {
+            cp_async_wait<AHEAD - 1>();                                   // this thread's copies of chunk i have landed
+            fence_proxy_async();                                          // ... and are visible to the tensor pipe (async proxy)
+            mbar_arrive(&full[i % WP_STAGES]);
+            const uint32_t nxt = i + AHEAD;                               // refills the stage chunk nxt - WP_STAGES (= i - 1) was multiplied from
+            if (nxt < my_n) {
+                if (nxt >= WP_STAGES) mbar_wait(&empty[nxt % WP_STAGES], ((nxt / WP_STAGES) - 1u) & 1u);
+                issue(nxt);
+            }
+            cp_async_commit();
+        }
+    } else if (tid == WG_THREADS) {                                       // the MMA thread
+        const uint32_t idesc = idesc_f16(128, n_pad) | (1u << 15) | (1u << 16);
+        for (uint32_t i = 0; i < my_n; i++) {
+            const uint32_t s = i % WP_STAGES;
+            mbar_wait(&full[s], (i / WP_STAGES) & 1u);
             fence_after_sync();
             uint64_t da = smem_desc_mn_sw128(base_a + s * WP_STAGE_BYTES), db = smem_desc_mn_sw128(base_a + s * WP_STAGE_BYTES + WG_OPERAND_BYTES);
 #pragma unroll 1
             for (uint32_t k = 0; k < WG_CHUNK / 16; k++, da += 2048u >> 4, db += 2048u >> 4) mma_f16_ss(tmem, da, db, idesc, i > 0 || k > 0);
-            mma_commit(&bars[s]);
+            mma_commit(&empty[s]);
         }
-        const uint32_t nxt = i + WP_STAGES - 1;                           // refills the stage chunk i-1 was multiplied from
-        if (nxt < my_n) {
-            if (i >= 1) mbar_wait(&bars[(i - 1) % WP_STAGES], ((i - 1) / WP_STAGES) & 1u);
-            issue(nxt);
-        }
-        cp_async_commit();
     }
-    if (my_n > 0) {
+    if (my_n > 0 && warp < 4) {                                           // epilogue warps (TMEM lanes 32 * warp ..): the last commit covers every MMA before it
         const uint32_t last = my_n - 1;
-        mbar_wait(&bars[last % WP_STAGES], (last / WP_STAGES) & 1u);
+        mbar_wait(&empty[last % WP_STAGES], (last / WP_STAGES) & 1u);
         fence_after_sync();
-        if (warp < 4) {
+        {
             const uint32_t o = tid;
             const uint32_t taddr = tmem + ((warp * 32u) << 16);
             for (uint32_t cb = 0; cb < n_pad; cb += 16) {
@@ -305,7 +322,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_linear_wgrad_pipe(const __hal
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 128);
+    if (warp == 8) tmem_dealloc(tmem, 128);
 }
 
 // halves per global access: 8/4/2 when rows allow it, 0 = flat 16-byte stream (odd width, 16-byte aligned matrix), 1 = element-wise
@@ -349,7 +366,7 @@ static int wgrad_launch(const void *dy, const void *x, uint32_t M, uint32_t out_
         if (!attr_p) { B2N_CUDA(cudaFuncSetAttribute(k_linear_wgrad_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WP_SMEM)); attr_p = true; }
         uint32_t g = (uint32_t)sm_count();
         if (g > n_chunks) g = n_chunks;
-        k_linear_wgrad_pipe<<<g, WG_THREADS, WP_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, dw, replicas, rstride);
+        k_linear_wgrad_pipe<<<g, WP_THREADS, WP_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, dw, replicas, rstride);
         return check_launch("linear_wgrad");
     }
     k_linear_wgrad<<<ctas, WG_THREADS, WG_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, va, vb, dw, replicas, rstride);
