@@ -173,8 +173,7 @@ __device__ __forceinline__ float blend4(const float (&v)[4], float fx, float gx,
 }
 // blend + store: levels (2k, 2k+1) of plane p are one packed half2 word (word p*6 + k) of the sample's row; out-of-range planes store 0
 // (gridencoder.cu:98-122).  `row` = the sample's row base inside the X tile, r7 = row index & 7 (SWIZZLE_128B chunk permutation).
-__device__ __forceinline__ void gather_finish(const GatherTrip &G, uint32_t ok, uint8_t *row, uint32_t r7, uint32_t k, uint32_t *save_a = nullptr,
-                                              uint32_t *save_b = nullptr) {
+__device__ __forceinline__ void gather_finish(const GatherTrip &G, uint32_t ok, uint8_t *row, uint32_t r7, uint32_t k) {
     float f[2][3];
 #pragma unroll
     for (uint32_t q = 0; q < 2; q++) {
@@ -189,7 +188,6 @@ __device__ __forceinline__ void gather_finish(const GatherTrip &G, uint32_t ok, 
         const uint32_t word = p * 6u + k;
         const uint32_t v = ((ok >> p) & 1u) ? pack2(f[0][p], f[1][p]) : 0u;
         *reinterpret_cast<uint32_t *>(row + (((word >> 2) ^ r7) << 4) + (word & 3u) * 4u) = v;
-        (void)save_a; (void)save_b;
     }
 }
 
@@ -325,18 +323,15 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         if (live0) { px = __ldcs(a.xyzs + 3 * (size_t)m0); py = __ldcs(a.xyzs + 3 * (size_t)m0 + 1); pz = __ldcs(a.xyzs + 3 * (size_t)m0 + 2); }
         const SampleCoord c = make_coord(px, py, pz, live0);
         GatherTrip GA, GB;                  // two trips in flight
-        uint32_t *xs = SAVE && live0 ? reinterpret_cast<uint32_t *>(a.sv.x36) + (size_t)m0 * 20 : nullptr;
-        uint32_t *ss = SAVE && live0 ? reinterpret_cast<uint32_t *>(a.sv.s_in) + (size_t)m0 * 36 : nullptr;
         gather_issue(GA, t_xy, t_yz, t_xz, &S.lvl[0], c);
 #pragma unroll 1
         for (uint32_t k = 0; k < 6; k += 2) {
             gather_issue(GB, t_xy, t_yz, t_xz, &S.lvl[2 * k + 2], c);
-            gather_finish(GA, c.ok, sXb + row_off, r7, k, xs, ss);
+            gather_finish(GA, c.ok, sXb + row_off, r7, k);
             if (k + 2 < 6) gather_issue(GA, t_xy, t_yz, t_xz, &S.lvl[2 * k + 4], c);
-            gather_finish(GB, c.ok, sXb + row_off, r7, k + 1, xs, ss);
+            gather_finish(GB, c.ok, sXb + row_off, r7, k + 1);
         }
         zero_k_padding(sXb);
-        (void)xs; (void)ss;
         if (SAVE) {      // enc_x (36 halves + zero padding = chunks 0..4 of the feature tile) -> x36 rows and the first 80 bytes of the sigma-input rows
             const size_t tr0 = (size_t)tile * HG_TILE;
             const uint32_t rv = (uint32_t)min((size_t)HG_TILE, (size_t)a.M - tr0);
@@ -363,11 +358,6 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         GatherTrip G;
         // training: rows of the saved activations for this tile's sample (m) and for the next tile's sample (features only)
         const bool sv_on = SAVE && live;
-        uint32_t *xsn = nullptr, *ssn = nullptr;
-        if (SAVE && nlive) {
-            const size_t mn = (size_t)(tile + tile_stride) * HG_TILE + t;
-            xsn = reinterpret_cast<uint32_t *>(a.sv.x36) + mn * 20; ssn = reinterpret_cast<uint32_t *>(a.sv.s_in) + mn * 40;
-        }
         const size_t tile_row0 = (size_t)tile * HG_TILE;
         const uint32_t rows_valid = SAVE ? (uint32_t)min((size_t)HG_TILE, (size_t)a.M - tile_row0) : 0u, wrow0 = (warp & 3u) * 32u;
 
@@ -407,7 +397,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             if (a.has_unc) issue_mma(tmem_wg + TC_A + 32, sX_a, sW_a + HW_U, 3, 32, false);
             mma_commit(bar);
         }
-        if (has_next) { gather_finish(G, cn.ok, rown, r7, 0, xsn, ssn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[2], cn); }      // trip 0 lands (issued a phase ago), trip 1 leaves
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 0); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[2], cn); }      // trip 0 lands (issued a phase ago), trip 1 leaves
         mma_done();
         float amb_aud;
         {
@@ -459,21 +449,21 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         publish();
         // ---- P3: sigma hidden += [enc_w, e] * WC -------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
-        if (has_next) { gather_finish(G, cn.ok, rown, r7, 1, xsn, ssn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[4], cn); }      // trip 1 lands (issued a phase ago), trip 2 leaves
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 1); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[4], cn); }      // trip 1 lands (issued a phase ago), trip 2 leaves
         mma_done();
         hidden_epilogue<true, false>(tmem_ld + TC_S, sH, t, nullptr);
         if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.h1) + tile_row0 * 128, 128, rows_valid);
         publish();
         // ---- P4: sigma layer 1 --------------------------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
-        if (has_next) { gather_finish(G, cn.ok, rown, r7, 2, xsn, ssn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[6], cn); }      // trip 2 lands (issued a phase ago), trip 3 leaves
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 2); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[6], cn); }      // trip 2 lands (issued a phase ago), trip 3 leaves
         mma_done();
         hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr);
         if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.h2) + tile_row0 * 128, 128, rows_valid);
         publish();
         // ---- P5: sigma layer 2: cols 0..63 = geo_feat, col 64 = density logit (rows rotated at pack time) -----------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
-        if (has_next) { gather_finish(G, cn.ok, rown, r7, 3, xsn, ssn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[8], cn); }      // trip 3 lands (issued a phase ago), trip 4 leaves
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 3); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[8], cn); }      // trip 3 lands (issued a phase ago), trip 4 leaves
         mma_done();
         float sigma;
         {
@@ -501,14 +491,14 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_F1, 1, 64, true);
             mma_commit(bar);
         }
-        if (has_next) { gather_finish(G, cn.ok, rown, r7, 4, xsn, ssn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[10], cn); }      // trip 4 lands (issued a phase ago), trip 5 leaves
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 4); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[10], cn); }      // trip 4 lands (issued a phase ago), trip 5 leaves
         mma_done();
         hidden_epilogue<true, true>(tmem_ld + TC_S, sH, t, S.ind_bias);
         if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.hc) + tile_row0 * 128, 128, rows_valid);
         publish();
         // ---- P7: color layer 1 (N padded 3 -> 16) -----------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_G, 4, 16, false); mma_commit(bar); }
-        if (has_next) gather_finish(G, cn.ok, rown, r7, 5, xsn, ssn);
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 5);
         mma_done();
         {
             uint32_t c16[16];
