@@ -180,6 +180,17 @@ int b2n_adamw_flat(float *params, const float *grads, float *exp_avg, float *exp
                    float weight_decay0, float lr1, float weight_decay1, float beta1, float beta2, float eps, float *step,
                    const float *grad_scale, const float *found_inf, void *stream);
 
+/* Training loss of the head branch and its gradient (TrainerUtil.py:238-300 with the background blend of renderer.py:559-561):
+ *   img = clamp(image + (1 - weights_sum) * bg, 0, 1);  loss = mean (img - gt)^2 + lambda_ent * mean H2(clamp(weights_sum, 1e-5, 1 - 1e-5))
+ *         + lambda_amb * (mean aud_sum + mean eye_sum).
+ * image [N,3], weights_sum / aud_sum / eye_sum [N] are composite_rays_train_triplane's outputs; bg_color [3] or [N,3] (bg_per_ray); loss is one device
+ * float (overwritten).  The backward multiplies by the device scalar *grad_loss (autograd's upstream gradient, i.e. the loss scale). */
+int b2n_head_loss_forward(const float *image, const float *weights_sum, const float *aud_sum, const float *eye_sum, const float *gt_rgb,
+                          const float *bg_color, int bg_per_ray, uint32_t N, float lambda_ent, float lambda_amb, float *loss, void *stream);
+int b2n_head_loss_backward(const float *image, const float *weights_sum, const float *gt_rgb, const float *bg_color, int bg_per_ray, uint32_t N,
+                           float lambda_ent, float lambda_amb, const float *grad_loss, float *grad_image, float *grad_weights_sum,
+                           float *grad_aud_sum, float *grad_eye_sum, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,3 +113,36 @@ def fused_head_train(model, x, d, enc_a, ind_code, eye):
     """Drop-in for HeadModel.forward_unfused in a training step: (sigma [M], color [M,3], ambient_aud [M,1], ambient_eye [M,1], unc [M,1,1])."""
     sig, rgb, aud, eye_att, unc = _FusedHead.apply(model, x, d, enc_a, ind_code.view(-1), eye, *head_parameters(model))
     return sig, rgb, aud[:, None], eye_att[:, None], unc[:, None, None]
+
+
+class _FusedLoss(torch.autograd.Function):
+    """Trainer.loss (TrainerUtil.py:238-300) + the background blend (renderer.py:559-561) as two kernels (csrc/loss.cu)."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, image, ws, aud_sum, eye_sum, gt, bg, lambda_ent, lambda_amb):
+        image, ws, aud_sum, eye_sum, gt, bg = (t.contiguous() for t in (image, ws, aud_sum, eye_sum, gt, bg))
+        n = ws.shape[0]
+        per_ray = int(bg.numel() == 3 * n and n > 1)
+        loss = torch.empty((), dtype=torch.float32, device=ws.device)
+        lib().call("b2n_head_loss_forward", image.data_ptr(), ws.data_ptr(), aud_sum.data_ptr(), eye_sum.data_ptr(), gt.data_ptr(), bg.data_ptr(), per_ray, n,
+                   float(lambda_ent), float(lambda_amb), loss.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ctx.save_for_backward(image, ws, gt, bg)
+        ctx.cfg = (per_ray, n, float(lambda_ent), float(lambda_amb))
+        return loss
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        image, ws, gt, bg = ctx.saved_tensors
+        per_ray, n, l_ent, l_amb = ctx.cfg
+        g = g.float().contiguous()
+        d_img, d_ws, d_aud, d_eye = torch.empty_like(image), torch.empty_like(ws), torch.empty_like(ws), torch.empty_like(ws)
+        lib().call("b2n_head_loss_backward", image.data_ptr(), ws.data_ptr(), gt.data_ptr(), bg.data_ptr(), per_ray, n, l_ent, l_amb, g.data_ptr(),
+                   d_img.data_ptr(), d_ws.data_ptr(), d_aud.data_ptr(), d_eye.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return d_img, d_ws, d_aud, d_eye, None, None, None, None
+
+
+def fused_head_loss(image, weights_sum, aud_sum, eye_sum, gt_rgb, bg_color, lambda_ent=1e-3, lambda_amb=1e-4):
+    """`image` is the composite's UN-blended image; returns the scalar loss of Trainer.loss on clamp(image + (1 - ws) * bg, 0, 1)."""
+    return _FusedLoss.apply(image, weights_sum, aud_sum, eye_sum, gt_rgb, bg_color, lambda_ent, lambda_amb)

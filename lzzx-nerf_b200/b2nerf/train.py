@@ -66,11 +66,16 @@ class Trainer:
             sigmas, rgbs, amb_aud, amb_eye, unc = m.forward_unfused(xyzs, dirs, enc_a, ind_code, eye)
         ws, aud_sum, eye_sum, unc_sum, depth, image = raymarching.composite_rays_train_triplane(
             sigmas, rgbs, amb_aud.abs().sum(-1), amb_eye.abs().sum(-1), unc, deltas, rays)
-        image = (image + (1 - ws).unsqueeze(-1) * bg_color).clamp(0, 1)
-        return dict(image=image, weights_sum=ws, ambient_aud=aud_sum, ambient_eye=eye_sum, uncertainty=unc_sum, n_samples_buffer=xyzs.shape[0])
+        raw = image
+        image = None if self.fused_head else (image + (1 - ws).unsqueeze(-1) * bg_color).clamp(0, 1)      # the fused loss blends the background itself
+        return dict(image=image, raw_image=raw, bg_color=bg_color, weights_sum=ws, ambient_aud=aud_sum, ambient_eye=eye_sum, uncertainty=unc_sum,
+                    n_samples_buffer=xyzs.shape[0])
 
     def loss(self, out, gt_rgb):
         # TrainerUtil.py:238-300 (head branch): MSE, entropy of the alpha channel, ambient regularisers
+        if out["image"] is None:
+            from .fused_train import fused_head_loss
+            return fused_head_loss(out["raw_image"], out["weights_sum"], out["ambient_aud"], out["ambient_eye"], gt_rgb, out["bg_color"], 1e-3, self.lambda_amb)
         mse = ((out["image"] - gt_rgb) ** 2).mean(-1).mean()
         alphas = out["weights_sum"].clamp(1e-5, 1 - 1e-5)
         entropy = (-alphas * torch.log2(alphas) - (1 - alphas) * torch.log2(1 - alphas)).mean()

@@ -214,3 +214,28 @@ def test_fused_head_gradients_match_autograd_under_autocast():
     bad = {k: v for k, v in worst.items() if v > 4e-2}
     assert not bad, (bad, worst)
     assert len(worst) >= 14, worst
+
+
+def test_fused_loss_matches_torch_loss_and_gradients():
+    """b2n_head_loss_forward/backward vs Trainer.loss on the blended image through autograd (fp32): value 1e-6, gradients 1e-5 of their max."""
+    from b2nerf.fused_train import fused_head_loss
+    g = torch.Generator(device="cuda").manual_seed(8)
+    n = 65536 + 13
+    image = torch.rand(n, 3, device="cuda", generator=g) * 0.9
+    ws = torch.rand(n, device="cuda", generator=g)
+    ws[:50] = 0.0; ws[50:100] = 1.0                      # both clamp regions of the entropy term
+    image[100:200] = 1.5; image[200:300] = -0.25         # both clamp regions of the colour
+    aud, eye = torch.rand(n, device="cuda", generator=g), torch.rand(n, device="cuda", generator=g)
+    gt = torch.rand(n, 3, device="cuda", generator=g)
+    for bg in (torch.ones(1, 3, device="cuda"), torch.rand(n, 3, device="cuda", generator=g)):
+        a = [t.clone().requires_grad_(True) for t in (image, ws, aud, eye)]
+        b = [t.clone().requires_grad_(True) for t in (image, ws, aud, eye)]
+        lf = fused_head_loss(a[0], a[1], a[2], a[3], gt, bg, 1e-3, 1e-4)
+        img = (b[0] + (1 - b[1]).unsqueeze(-1) * bg).clamp(0, 1)
+        al = b[1].clamp(1e-5, 1 - 1e-5)
+        lt = ((img - gt) ** 2).mean(-1).mean() + 1e-3 * (-al * torch.log2(al) - (1 - al) * torch.log2(1 - al)).mean() + 1e-4 * (b[2].mean() + b[3].mean())
+        assert abs(float(lf) - float(lt)) < 2e-6 * max(1.0, abs(float(lt))), (float(lf), float(lt))
+        (lf * 1024.0).backward(); (lt * 1024.0).backward()
+        for x, y, name in zip(a, b, ("image", "ws", "aud", "eye")):
+            err = float((x.grad - y.grad).abs().max()) / (float(y.grad.abs().max()) + 1e-20)
+            assert err < 2e-5, (name, err)
