@@ -239,3 +239,34 @@ def test_fused_loss_matches_torch_loss_and_gradients():
         for x, y, name in zip(a, b, ("image", "ws", "aud", "eye")):
             err = float((x.grad - y.grad).abs().max()) / (float(y.grad.abs().max()) + 1e-20)
             assert err < 2e-5, (name, err)
+
+
+def test_fused_head_without_unc_net():
+    """unc_loss = False: unc_net is not packed / evaluated (network.py:276-278 else-branch); the fused path must run with the unc buffers absent,
+    give finite gradients for every other parameter and none for unc_net."""
+    from b2nerf.model import HeadModel
+    from b2nerf.fused_train import fused_head_train
+    torch.manual_seed(6)
+    m = HeadModel(audio_in_dim=29).cuda()
+    for enc in (m.encoder_xy, m.encoder_yz, m.encoder_xz):
+        enc.embeddings.data.uniform_(-0.5, 0.5)
+    m.testing, m.unc_loss = False, False
+    M = 16384 + 5
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = (torch.rand(M, 3, device="cuda", generator=g) * 2 - 1) * torch.tensor([1.0, 0.5, 1.0], device="cuda")
+    d = torch.nn.functional.normalize(torch.randn(M, 3, device="cuda", generator=g), dim=1)
+    enc_a = (torch.randn(1, 32, device="cuda", generator=g) * 0.5).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        m.pack()
+        sig, rgb, aud, eye_att, unc = fused_head_train(m, x, d, enc_a, m.individual_codes[1], torch.tensor([[0.2]], device="cuda"))
+        loss = sig.sum() * 1e-3 + rgb.sum() + aud.sum() + eye_att.sum()
+    loss.backward()
+    assert float((unc - 0.6931471805599453).abs().max()) < 1e-6          # log(1 + e^0)
+    for n, p in m.named_parameters():
+        if n.startswith("unc_net") or n.startswith("audio"):
+            assert p.grad is None or float(p.grad.abs().sum()) == 0, n
+        elif n == "individual_codes":
+            assert float(p.grad[1].abs().sum()) > 0 and float(p.grad[0].abs().sum()) == 0
+        else:
+            assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0, n
+    assert torch.isfinite(enc_a.grad).all() and float(enc_a.grad.abs().sum()) > 0
