@@ -56,6 +56,15 @@ typedef struct {
     uint32_t dim_in;
 } b2n_audio_weights;
 int b2n_audio_encode(const b2n_audio_weights *w, const float *auds, uint32_t L, float *enc_a, void *stream);
+/* Backward of b2n_audio_encode (training): d_enc_a [32] -> the gradient of every parameter, accumulated into `g` (same layouts as the weights; zero
+ * them first).  One cluster kernel: recomputes the forward, back-propagates through the attention net on CTA 0 and through the eight AudioNet copies. */
+typedef struct {
+    float *conv_w[4], *conv_b[4];
+    float *fc_w[2], *fc_b[2];
+    float *att_conv_w[5], *att_conv_b[5];
+    float *att_fc_w, *att_fc_b;
+} b2n_audio_grads;
+int b2n_audio_backward(const b2n_audio_weights *w, const float *auds, uint32_t L, const float *d_enc_a, const b2n_audio_grads *g, void *stream);
 
 /* One whole inference frame = renderer.py:442 (near/far) + :480-545 (march / network / composite loop with compaction)
  * + :559-561 (background blend, clamp), with NO host synchronisation: alive-ray counts and n_step live in a device-side

@@ -146,3 +146,55 @@ class _FusedLoss(torch.autograd.Function):
 def fused_head_loss(image, weights_sum, aud_sum, eye_sum, gt_rgb, bg_color, lambda_ent=1e-3, lambda_amb=1e-4):
     """`image` is the composite's UN-blended image; returns the scalar loss of Trainer.loss on clamp(image + (1 - ws) * bg, 0, 1)."""
     return _FusedLoss.apply(image, weights_sum, aud_sum, eye_sum, gt_rgb, bg_color, lambda_ent, lambda_amb)
+
+
+class _AudioGradsC(ctypes.Structure):
+    """b2n_audio_grads (include/b2nerf_fused.h)"""
+    _fields_ = [("conv_w", ctypes.c_void_p * 4), ("conv_b", ctypes.c_void_p * 4), ("fc_w", ctypes.c_void_p * 2), ("fc_b", ctypes.c_void_p * 2),
+                ("att_conv_w", ctypes.c_void_p * 5), ("att_conv_b", ctypes.c_void_p * 5), ("att_fc_w", ctypes.c_void_p), ("att_fc_b", ctypes.c_void_p)]
+
+
+def audio_parameters(model):
+    """AudioNet / AudioAttNet parameters in the order _AudioEncode.backward returns their gradients."""
+    conv = [model.audio_net.encoder_conv[i] for i in (0, 2, 4, 6)]
+    fc = [model.audio_net.encoder_fc1[i] for i in (0, 2)]
+    att = [model.audio_att_net.attentionConvNet[i] for i in (0, 2, 4, 6, 8)]
+    lin = model.audio_att_net.attentionNet[0]
+    return ([c.weight for c in conv] + [c.bias for c in conv] + [c.weight for c in fc] + [c.bias for c in fc] + [c.weight for c in att] + [c.bias for c in att]
+            + [lin.weight, lin.bias])
+
+
+class _AudioEncode(torch.autograd.Function):
+    """encode_audio (network.py:226-240) inside autograd on the two cluster kernels of csrc/fused_audio.cu (~100 cuDNN / elementwise launches per step in
+    the torch path for an 8-frame window)."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, model, auds, *params):
+        auds = auds.contiguous()
+        w = model.audio_weights_struct()
+        enc = torch.empty(1, 32, dtype=torch.float32, device=auds.device)
+        lib().call("b2n_audio_encode", ctypes.byref(w), auds.data_ptr(), auds.shape[2], enc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ctx.model, ctx.auds, ctx.w = model, auds, w
+        return enc
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g_enc):
+        params = audio_parameters(ctx.model)
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=g_enc.device)
+        views, off = [], 0
+        for p in params:
+            views.append(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+        ptr = [v.data_ptr() for v in views]
+        gs = _AudioGradsC((ctypes.c_void_p * 4)(*ptr[0:4]), (ctypes.c_void_p * 4)(*ptr[4:8]), (ctypes.c_void_p * 2)(*ptr[8:10]), (ctypes.c_void_p * 2)(*ptr[10:12]),
+                          (ctypes.c_void_p * 5)(*ptr[12:17]), (ctypes.c_void_p * 5)(*ptr[17:22]), ptr[22], ptr[23])
+        g = g_enc.float().contiguous().view(-1)
+        lib().call("b2n_audio_backward", ctypes.byref(ctx.w), ctx.auds.data_ptr(), ctx.auds.shape[2], g.data_ptr(), ctypes.byref(gs),
+                   torch.cuda.current_stream().cuda_stream)
+        return (None, None) + tuple(views)
+
+
+def fused_encode_audio(model, auds):
+    """Drop-in for HeadModel.encode_audio in a training step (att > 0): [8, dim_in, L] -> [1, 32] with gradients to the audio nets."""
+    return _AudioEncode.apply(model, auds, *audio_parameters(model))

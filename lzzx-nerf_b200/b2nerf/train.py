@@ -49,7 +49,11 @@ class Trainer:
         `index` may be an int or a 1-element device tensor (graph mode); `counter` overrides the step-counter slot."""
         m = self.m
         nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, m.aabb_train, self.min_near)
-        enc_a = m.encode_audio(auds)
+        if self.fused_head and m.att > 0:
+            from .fused_train import fused_encode_audio
+            enc_a = fused_encode_audio(m, auds)            # two cluster kernels instead of the cuDNN graph
+        else:
+            enc_a = m.encode_audio(auds)
         ind_code = m.individual_codes.index_select(0, index)[0] if torch.is_tensor(index) else m.individual_codes[index]
         if counter is None:
             counter = m.step_counter[self.local_step % 16]

@@ -130,6 +130,178 @@ __global__ void __cluster_dims__(AU_FRAMES, 1, 1) __launch_bounds__(AU_THREADS) 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// backward (training): d enc_a [32] -> gradients of every AudioNet / AudioAttNet parameter
+// ---------------------------------------------------------------------------------------------------
+// Same cluster of 8 CTAs.  Every CTA recomputes its frame's forward keeping all activations in shared memory; CTA 0 gathers the eight feature
+// vectors (DSMEM), runs the attention net forward + backward and leaves d features [8, 32] in its shared memory; after a cluster barrier every CTA
+// reads its row and back-propagates through its AudioNet copy, adding its weight-gradient contributions with red.global (8-way contention at
+// most).  Gradients are computed in fp32 from the forward's fp16-rounded operands (autocast would also round the inter-layer gradients to fp16).
+__device__ __forceinline__ float leaky_grad(float a) { return a > 0.0f ? 1.0f : 0.02f; }      // a = LeakyReLU output: same sign as its input
+
+// conv backward.  in_s [ci, li] forward input, out_s [co, lo] forward OUTPUT (post-activation, for the LeakyReLU slope; NULL = no activation),
+// dout_s [co, lo] gradient w.r.t. that output (overwritten with the pre-activation gradient), din_s [ci, li] (NULL = not needed)
+__device__ void conv3_backward(const float *in_s, uint32_t ci, uint32_t li, const float *__restrict__ w, const float *out_s, float *dout_s, uint32_t co, uint32_t stride,
+                               float *__restrict__ gw, float *__restrict__ gb, float *din_s) {
+    const uint32_t lo = (li + 2 - 3) / stride + 1;
+    if (out_s) {
+        for (uint32_t o = threadIdx.x; o < co * lo; o += AU_THREADS) dout_s[o] *= leaky_grad(out_s[o]);
+        __syncthreads();
+    }
+    for (uint32_t r = threadIdx.x; r < co * ci * 3; r += AU_THREADS) {          // d W[c, cin, k] = sum_x dz[c, x] in[cin, x * stride + k - 1]
+        const uint32_t c = r / (ci * 3), rem = r - c * ci * 3, cin = rem / 3, k = rem - cin * 3;
+        float acc = 0.0f;
+        for (uint32_t x = 0; x < lo; x++) {
+            const int xi = (int)(x * stride + k) - 1;
+            if (xi >= 0 && xi < (int)li) acc = fmaf(dout_s[c * lo + x], in_s[cin * li + xi], acc);
+        }
+        if (acc != 0.0f) atomicAdd(gw + r, acc);
+    }
+    for (uint32_t c = threadIdx.x; c < co; c += AU_THREADS) {
+        float acc = 0.0f;
+        for (uint32_t x = 0; x < lo; x++) acc += dout_s[c * lo + x];
+        atomicAdd(gb + c, acc);
+    }
+    if (din_s) {
+        for (uint32_t o = threadIdx.x; o < ci * li; o += AU_THREADS) {            // d in[cin, xi] = sum_c sum_k dz[c, x] W[c, cin, k] with x * stride + k - 1 == xi
+            const uint32_t cin = o / li, xi = o - cin * li;
+            float acc = 0.0f;
+            for (uint32_t k = 0; k < 3; k++) {
+                const int num = (int)xi + 1 - (int)k;
+                if (num < 0 || num % (int)stride != 0) continue;
+                const uint32_t x = (uint32_t)num / stride;
+                if (x >= lo) continue;
+                for (uint32_t c = 0; c < co; c++) acc = fmaf(dout_s[c * lo + x], rh(__ldg(w + ((size_t)c * ci + cin) * 3 + k)), acc);
+            }
+            din_s[o] = acc;
+        }
+    }
+    __syncthreads();
+}
+// linear backward: in_s [ci], out_s [co] post-activation output or NULL, dout_s [co] (overwritten), din_s [ci] or NULL
+__device__ void linear_backward(const float *in_s, uint32_t ci, const float *__restrict__ w, const float *out_s, float *dout_s, uint32_t co, float *__restrict__ gw,
+                                float *__restrict__ gb, float *din_s) {
+    if (out_s) {
+        for (uint32_t o = threadIdx.x; o < co; o += AU_THREADS) dout_s[o] *= leaky_grad(out_s[o]);
+        __syncthreads();
+    }
+    for (uint32_t r = threadIdx.x; r < co * ci; r += AU_THREADS) {
+        const uint32_t o = r / ci, i = r - o * ci;
+        const float v = dout_s[o] * in_s[i];
+        if (v != 0.0f) atomicAdd(gw + r, v);
+    }
+    for (uint32_t o = threadIdx.x; o < co; o += AU_THREADS) atomicAdd(gb + o, dout_s[o]);
+    if (din_s) {
+        for (uint32_t i = threadIdx.x; i < ci; i += AU_THREADS) {
+            float acc = 0.0f;
+            for (uint32_t o = 0; o < co; o++) acc = fmaf(dout_s[o], rh(__ldg(w + (size_t)o * ci + i)), acc);
+            din_s[i] = acc;
+        }
+    }
+    __syncthreads();
+}
+
+struct AudioBwdArgs {
+    b2n_audio_weights w;
+    b2n_audio_grads g;
+    const float *auds;
+    uint32_t L;
+    const float *d_enc_a;       // [32]
+};
+
+__global__ void __cluster_dims__(AU_FRAMES, 1, 1) __launch_bounds__(AU_THREADS) k_audio_backward(const __grid_constant__ AudioBwdArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ float sm[];
+    const uint32_t frame = cluster.block_rank();
+    const uint32_t dim_in = a.w.dim_in, Lw = a.L < 16 ? a.L : 16;
+    uint32_t l1 = (Lw + 2 - 3) / 2 + 1, l2 = (l1 + 2 - 3) / 2 + 1, l3 = (l2 + 2 - 3) / 2 + 1;      // l4 == 1 (checked on the host)
+    // activations of this frame (all kept)                      sizes with Lw = 16: 32*8, 32*4, 64*2, 64, 64, 32
+    float *s_in = sm, *s_a1 = s_in + dim_in * Lw, *s_a2 = s_a1 + 256, *s_a3 = s_a2 + 128, *s_a4 = s_a3 + 128, *s_g1 = s_a4 + 64, *s_ga = s_g1 + 64, *s_gb = s_ga + 512;
+    __shared__ float s_feat[32];
+    __shared__ float s_all[AU_FRAMES * 32];             // CTA 0: features of all frames [8, 32]
+    __shared__ float s_dX[AU_FRAMES * 32];              // CTA 0: d features
+    __shared__ float s_c[5][16 * AU_FRAMES];            // CTA 0: attention conv outputs (post-activation)
+    __shared__ float s_t0[32 * AU_FRAMES];
+    __shared__ float s_y[AU_FRAMES], s_p[AU_FRAMES], s_dy[AU_FRAMES];
+
+    // ---- forward recompute (same arithmetic as k_audio_encode) ----------------------------------------------------------------
+    const float *x = a.auds + (size_t)frame * dim_in * a.L;
+    for (uint32_t i = threadIdx.x; i < dim_in * Lw; i += AU_THREADS) {
+        const uint32_t c = i / Lw, t = i - c * Lw;
+        s_in[i] = rh(__ldg(x + (size_t)c * a.L + t));
+    }
+    __syncthreads();
+    conv3_layer(s_in, dim_in, Lw, a.w.conv_w[0], a.w.conv_b[0], s_a1, 32, 2, true);
+    conv3_layer(s_a1, 32, l1, a.w.conv_w[1], a.w.conv_b[1], s_a2, 32, 2, true);
+    conv3_layer(s_a2, 32, l2, a.w.conv_w[2], a.w.conv_b[2], s_a3, 64, 2, true);
+    conv3_layer(s_a3, 64, l3, a.w.conv_w[3], a.w.conv_b[3], s_a4, 64, 2, true);
+    linear_layer(s_a4, 64, a.w.fc_w[0], a.w.fc_b[0], s_g1, 64, true);
+    linear_layer(s_g1, 64, a.w.fc_w[1], a.w.fc_b[1], s_feat, 32, false);
+    cluster.sync();
+    if (frame == 0) {
+        for (uint32_t i = threadIdx.x; i < AU_FRAMES * 32; i += AU_THREADS) {
+            const float *remote = cluster.map_shared_rank(s_feat, i >> 5);
+            s_all[i] = remote[i & 31];
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < AU_FRAMES * 32; i += AU_THREADS) s_t0[(i & 31) * AU_FRAMES + (i >> 5)] = s_all[i];      // [32 channels, 8 frames]
+        __syncthreads();
+        const uint32_t chans[6] = {32, 16, 8, 4, 2, 1};
+        const float *prev = s_t0;
+#pragma unroll 1
+        for (int l = 0; l < 5; l++) {
+            conv3_layer(prev, chans[l], AU_FRAMES, a.w.att_conv_w[l], a.w.att_conv_b[l], s_c[l], chans[l + 1], 1, true);
+            prev = s_c[l];
+        }
+        linear_layer(s_c[4], AU_FRAMES, a.w.att_fc_w, a.w.att_fc_b, s_y, AU_FRAMES, false);
+        if (threadIdx.x == 0) {
+            float mx = -INFINITY, den = 0.0f;
+            for (int q = 0; q < AU_FRAMES; q++) mx = fmaxf(mx, s_y[q]);
+            for (int q = 0; q < AU_FRAMES; q++) { s_p[q] = expf(s_y[q] - mx); den += s_p[q]; }
+            for (int q = 0; q < AU_FRAMES; q++) s_p[q] /= den;
+            // enc_a[j] = sum_s p[s] X[s, j]:  d p[s] = sum_j d_out[j] X[s, j];  softmax backward: d y = p * (d p - sum p d p)
+            float dp[AU_FRAMES], dot = 0.0f;
+            for (int q = 0; q < AU_FRAMES; q++) {
+                float acc = 0.0f;
+                for (int j = 0; j < 32; j++) acc = fmaf(a.d_enc_a[j], s_all[q * 32 + j], acc);
+                dp[q] = acc; dot = fmaf(s_p[q], acc, dot);
+            }
+            for (int q = 0; q < AU_FRAMES; q++) s_dy[q] = s_p[q] * (dp[q] - dot);
+        }
+        __syncthreads();
+        // ---- attention backward ------------------------------------------------------------------------------------------------
+        float *d_cur = s_ga, *d_nxt = s_gb;                       // gradient w.r.t. the current layer's output / input
+        linear_backward(s_c[4], AU_FRAMES, a.w.att_fc_w, nullptr, s_dy, AU_FRAMES, a.g.att_fc_w, a.g.att_fc_b, d_cur);      // d c5 [1, 8]
+#pragma unroll 1
+        for (int l = 4; l >= 0; l--) {
+            const float *in_l = l == 0 ? s_t0 : s_c[l - 1];
+            conv3_backward(in_l, chans[l], AU_FRAMES, a.w.att_conv_w[l], s_c[l], d_cur, chans[l + 1], 1, a.g.att_conv_w[l], a.g.att_conv_b[l], d_nxt);
+            float *tmp = d_cur; d_cur = d_nxt; d_nxt = tmp;
+        }
+        // d_cur = d t0 [32, 8];  d X[s, j] = p[s] d_out[j] + d t0[j, s]
+        for (uint32_t i = threadIdx.x; i < AU_FRAMES * 32; i += AU_THREADS) {
+            const uint32_t q = i >> 5, j = i & 31;
+            s_dX[i] = fmaf(s_p[q], a.d_enc_a[j], d_cur[j * AU_FRAMES + q]);
+        }
+        __syncthreads();
+    }
+    cluster.sync();                                               // d X is ready in CTA 0
+    {
+        const float *remote = cluster.map_shared_rank(s_dX, 0);
+        if (threadIdx.x < 32) s_ga[threadIdx.x] = remote[frame * 32 + threadIdx.x];      // d feat of this frame
+    }
+    __syncthreads();
+    cluster.sync();                                               // CTA 0 may not exit / reuse its shared memory before every peer has read
+    // ---- AudioNet backward for this frame -------------------------------------------------------------------------------------------
+    float *d_cur = s_ga, *d_nxt = s_gb;
+    linear_backward(s_g1, 64, a.w.fc_w[1], nullptr, d_cur, 32, a.g.fc_w[1], a.g.fc_b[1], d_nxt);                  // -> d g1 [64]
+    linear_backward(s_a4, 64, a.w.fc_w[0], s_g1, d_nxt, 64, a.g.fc_w[0], a.g.fc_b[0], d_cur);                     // -> d a4 [64]
+    conv3_backward(s_a3, 64, l3, a.w.conv_w[3], s_a4, d_cur, 64, 2, a.g.conv_w[3], a.g.conv_b[3], d_nxt);         // -> d a3 [64, l3]
+    conv3_backward(s_a2, 32, l2, a.w.conv_w[2], s_a3, d_nxt, 64, 2, a.g.conv_w[2], a.g.conv_b[2], d_cur);         // -> d a2 [32, l2]
+    conv3_backward(s_a1, 32, l1, a.w.conv_w[1], s_a2, d_cur, 32, 2, a.g.conv_w[1], a.g.conv_b[1], d_nxt);         // -> d a1 [32, l1]
+    conv3_backward(s_in, dim_in, Lw, a.w.conv_w[0], s_a1, d_nxt, 32, 2, a.g.conv_w[0], a.g.conv_b[0], nullptr);
+}
+
 }  // namespace b2n
 
 using namespace b2n;
@@ -151,4 +323,23 @@ extern "C" int b2n_audio_encode(const b2n_audio_weights *w, const float *auds, u
     if (smem > 48 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(k_audio_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
     k_audio_encode<<<AU_FRAMES, AU_THREADS, smem, as_stream(stream)>>>(a);
     return check_launch("audio_encode");
+}
+
+extern "C" int b2n_audio_backward(const b2n_audio_weights *w, const float *auds, uint32_t L, const float *d_enc_a, const b2n_audio_grads *g, void *stream) {
+    B2N_REQUIRE(w && auds && d_enc_a && g, "audio_backward: null pointer");
+    B2N_REQUIRE(w->dim_in >= 1 && w->dim_in <= 4096 && L >= 1, "audio_backward: dim_in=%u / L=%u unsupported", w->dim_in, L);
+    for (int i = 0; i < 4; i++) B2N_REQUIRE(w->conv_w[i] && w->conv_b[i] && g->conv_w[i] && g->conv_b[i], "audio_backward: null conv weight / gradient");
+    for (int i = 0; i < 5; i++) B2N_REQUIRE(w->att_conv_w[i] && w->att_conv_b[i] && g->att_conv_w[i] && g->att_conv_b[i], "audio_backward: null attention conv weight / gradient");
+    B2N_REQUIRE(w->fc_w[0] && w->fc_w[1] && w->fc_b[0] && w->fc_b[1] && w->att_fc_w && w->att_fc_b && g->fc_w[0] && g->fc_w[1] && g->fc_b[0] && g->fc_b[1] &&
+                g->att_fc_w && g->att_fc_b, "audio_backward: null linear weight / gradient");
+    const uint32_t Lw = L < 16 ? L : 16;
+    uint32_t li = Lw;
+    for (int i = 0; i < 4; i++) li = (li + 2 - 3) / 2 + 1;
+    B2N_REQUIRE(li == 1, "audio_backward: window length %u does not reduce to 1 after four stride-2 convolutions", L);
+    AudioBwdArgs a = {*w, *g, auds, L, d_enc_a};
+    const size_t smem = sizeof(float) * ((size_t)w->dim_in * Lw + 256 + 128 + 128 + 64 + 64 + 512 + 512);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(k_audio_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    k_audio_backward<<<AU_FRAMES, AU_THREADS, smem, as_stream(stream)>>>(a);
+    return check_launch("audio_backward");
 }

@@ -270,3 +270,32 @@ def test_fused_head_without_unc_net():
         else:
             assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0, n
     assert torch.isfinite(enc_a.grad).all() and float(enc_a.grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("hubert", [True, False])
+def test_fused_audio_backward_matches_autograd(hubert):
+    """b2n_audio_encode + b2n_audio_backward inside autograd vs encode_audio (torch AudioNet + AudioAttNet) under autocast: output 2e-3, every parameter
+    gradient within 3e-2 of its max (the torch path rounds inter-layer gradients to fp16, the kernel keeps them in fp32)."""
+    import copy
+    from b2nerf.model import HeadModel
+    from b2nerf.fused_train import fused_encode_audio
+    torch.manual_seed(9)
+    m = HeadModel(audio_in_dim=1024 if hubert else 29).cuda()
+    m2 = copy.deepcopy(m)
+    auds = torch.from_numpy(scene.audio_window(4, hubert=hubert)).cuda()
+    up = torch.randn(1, 32, device="cuda")
+    with torch.autocast("cuda", dtype=torch.float16):
+        e1 = fused_encode_audio(m, auds)
+        e2 = m2.encode_audio(auds)
+    (e1.float() * up).sum().backward()
+    (e2.float() * up).sum().backward()
+    assert float((e1.float() - e2.float()).abs().max()) < 2e-3 * max(1.0, float(e2.abs().max()))
+    worst = {}
+    for (n, p), (_, q) in zip(m.named_parameters(), m2.named_parameters()):
+        if not n.startswith("audio"):
+            continue
+        assert p.grad is not None and q.grad is not None, n
+        worst[n] = float((p.grad - q.grad).abs().max()) / (float(q.grad.abs().max()) + 1e-12)
+    assert len(worst) == 24, sorted(worst)
+    bad = {k: v for k, v in worst.items() if v > 3e-2}
+    assert not bad, (bad, worst)
