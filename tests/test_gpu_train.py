@@ -274,30 +274,34 @@ def test_fused_head_without_unc_net():
 
 @pytest.mark.parametrize("hubert", [True, False])
 def test_fused_audio_backward_matches_autograd(hubert):
-    """b2n_audio_encode + b2n_audio_backward inside autograd vs encode_audio (torch AudioNet + AudioAttNet) under autocast: output 2e-3, every parameter
-    gradient within 3e-2 of its max (the torch path rounds inter-layer gradients to fp16, the kernel keeps them in fp32)."""
+    """b2n_audio_encode + b2n_audio_backward inside autograd vs encode_audio (torch AudioNet + AudioAttNet).  Reference = the torch graph in fp32; the
+    kernel (fp16-rounded forward operands like autocast, fp32 gradients) must be as close to it as torch's own autocast path is: AudioNet gradients
+    3e-3 of their max; the attention net's gradients are ill-conditioned (they pass through a softmax over 8 nearly equal logits: 1e-3 in size against
+    1e+3 for the AudioNet, and autocast itself is 2..17 % off the fp32 values), so they are held to 2.5x autocast's own error + 2 %."""
     import copy
     from b2nerf.model import HeadModel
     from b2nerf.fused_train import fused_encode_audio
     torch.manual_seed(9)
     m = HeadModel(audio_in_dim=1024 if hubert else 29).cuda()
-    m2 = copy.deepcopy(m)
+    m2, m3 = copy.deepcopy(m), copy.deepcopy(m)
     auds = torch.from_numpy(scene.audio_window(4, hubert=hubert)).cuda()
     up = torch.randn(1, 32, device="cuda")
     with torch.autocast("cuda", dtype=torch.float16):
         e1 = fused_encode_audio(m, auds)
         e2 = m2.encode_audio(auds)
-    # loss scale as under GradScaler: the attention branch's gradients pass through a softmax (cancellation) and would sit in fp16's subnormal
-    # range in the torch path otherwise
-    (e1.float() * up).sum().mul(4096.0).backward()
-    (e2.float() * up).sum().mul(4096.0).backward()
-    assert float((e1.float() - e2.float()).abs().max()) < 2e-3 * max(1.0, float(e2.abs().max()))
-    worst = {}
-    for (n, p), (_, q) in zip(m.named_parameters(), m2.named_parameters()):
+    e3 = m3.encode_audio(auds)                                   # fp32 reference
+    for e in (e1, e2, e3):
+        (e.float() * up).sum().mul(4096.0).backward()           # loss scale, as under GradScaler
+    assert float((e1.float() - e3).abs().max()) < 2e-3 * max(1.0, float(e3.abs().max()))
+    n_checked = 0
+    for (n, p), (_, q), (_, r) in zip(m.named_parameters(), m2.named_parameters(), m3.named_parameters()):
         if not n.startswith("audio"):
             continue
-        assert p.grad is not None and q.grad is not None, n
-        worst[n] = float((p.grad - q.grad).abs().max()) / (float(q.grad.abs().max()) + 1e-12)
-    assert len(worst) == 24, sorted(worst)
-    bad = {k: v for k, v in worst.items() if v > 3e-2}
-    assert not bad, (bad, worst)
+        mx = float(r.grad.abs().max()) + 1e-12
+        err_fused, err_autocast = float((p.grad - r.grad).abs().max()) / mx, float((q.grad - r.grad).abs().max()) / mx
+        if n.startswith("audio_net"):
+            assert err_fused < 3e-3, (n, err_fused, err_autocast)
+        else:
+            assert err_fused < 2.5 * err_autocast + 2e-2, (n, err_fused, err_autocast)
+        n_checked += 1
+    assert n_checked == 24
