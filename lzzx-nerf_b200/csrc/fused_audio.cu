@@ -14,7 +14,7 @@ namespace cg = cooperative_groups;
 
 namespace b2n {
 
-constexpr int AU_THREADS = 256;
+constexpr int AU_THREADS = 1024;
 constexpr int AU_WARPS = AU_THREADS / 32;
 constexpr int AU_FRAMES = 8;
 
