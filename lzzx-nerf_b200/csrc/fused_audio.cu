@@ -163,17 +163,20 @@ __device__ void conv3_backward(const float *in_s, uint32_t ci, uint32_t li, cons
         atomicAdd(gb + c, acc);
     }
     if (din_s) {
-        for (uint32_t o = threadIdx.x; o < ci * li; o += AU_THREADS) {            // d in[cin, xi] = sum_c sum_k dz[c, x] W[c, cin, k] with x * stride + k - 1 == xi
+        // d in[cin, xi] = sum_c sum_k dz[c, x] W[c, cin, k] with x * stride + k - 1 == xi: one warp per element, lanes split the (c, k) pairs
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (uint32_t o = warp; o < ci * li; o += AU_WARPS) {
             const uint32_t cin = o / li, xi = o - cin * li;
             float acc = 0.0f;
-            for (uint32_t k = 0; k < 3; k++) {
+            for (uint32_t r = lane; r < co * 3; r += 32) {
+                const uint32_t c = r / 3, k = r - c * 3;
                 const int num = (int)xi + 1 - (int)k;
-                if (num < 0 || num % (int)stride != 0) continue;
-                const uint32_t x = (uint32_t)num / stride;
-                if (x >= lo) continue;
-                for (uint32_t c = 0; c < co; c++) acc = fmaf(dout_s[c * lo + x], rh(__ldg(w + ((size_t)c * ci + cin) * 3 + k)), acc);
+                if (num >= 0 && num % (int)stride == 0 && (uint32_t)num / stride < lo)
+                    acc = fmaf(dout_s[c * lo + (uint32_t)num / stride], rh(__ldg(w + ((size_t)c * ci + cin) * 3 + k)), acc);
             }
-            din_s[o] = acc;
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+            if (lane == 0) din_s[o] = acc;
         }
     }
     __syncthreads();
@@ -192,10 +195,13 @@ __device__ void linear_backward(const float *in_s, uint32_t ci, const float *__r
     }
     for (uint32_t o = threadIdx.x; o < co; o += AU_THREADS) atomicAdd(gb + o, dout_s[o]);
     if (din_s) {
-        for (uint32_t i = threadIdx.x; i < ci; i += AU_THREADS) {
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (uint32_t i = warp; i < ci; i += AU_WARPS) {              // one warp per input element, lanes split the outputs
             float acc = 0.0f;
-            for (uint32_t o = 0; o < co; o++) acc = fmaf(dout_s[o], rh(__ldg(w + (size_t)o * ci + i)), acc);
-            din_s[i] = acc;
+            for (uint32_t o = lane; o < co; o += 32) acc = fmaf(dout_s[o], rh(__ldg(w + (size_t)o * ci + i)), acc);
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+            if (lane == 0) din_s[i] = acc;
         }
     }
     __syncthreads();
