@@ -66,47 +66,83 @@ class _FusedHead(torch.autograd.Function):
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, g_sig, g_rgb, g_aud, g_eye, g_unc):
-        m, sv = ctx.model, ctx.saved_acts
-        x, enc_a, eye, sig, aud = ctx.saved_tensors
-        M, dev = x.shape[0], x.device
-        f32 = lambda t: None if t is None else t.float().contiguous()
-        g_sig, g_rgb, g_aud, g_eye, g_unc = f32(g_sig), f32(g_rgb), f32(g_aud), f32(g_eye), f32(g_unc)
-        gr = {k: torch.empty(M, w, dtype=torch.float16, device=dev) for k, w in GRAD_WIDTHS.items() if ctx.with_unc or k not in ("d_ul", "d_hu")}
-        planes = torch.empty(3, 12, M, dtype=torch.float32, device=dev)
-        gc = _GradsC(*[(gr[k].data_ptr() if k in gr else None) for k, _ in _GradsC._fields_[:-1]], planes.data_ptr())
-        from .model import _HeadSavedC
-        sc = _HeadSavedC(*[sv[k].data_ptr() if k in sv else None for k, _ in _HeadSavedC._fields_])
-        p = lambda t: None if t is None else t.data_ptr()
-        enc_a_flat = enc_a.contiguous().view(-1)
-        lib().call("b2n_head_backward", m.handle, M, enc_a_flat.data_ptr(), eye.data_ptr() if ctx.has_eye else None, ctypes.byref(sc), sig.data_ptr(),
-                   aud.data_ptr(), p(g_sig), p(g_rgb), p(g_aud), p(g_eye), p(g_unc), ctypes.byref(gc), torch.cuda.current_stream().cuda_stream)
-        # weight gradients: one pass over (dY, X) per matrix
-        pairs = [(gr["d_rl"], sv["hc"]), (gr["d_hc"], sv["c_in"]), (gr["d_o"], sv["h2"]), (gr["d_h2"], sv["h1"]), (gr["d_h1"], sv["s_in"]),
-                 (gr["d_att"], sv["ha"]), (gr["d_ha"], sv["x36"]), (gr["d_el"], sv["he"]), (gr["d_he"], sv["x36"])]
-        # two reductions over the samples ride along as products: d enc_a[j] = sum_m d_ew[m,j] att[m,j] = diag(d_ew^T att);
-        # d ind_code[i] = sum_m d_ci[m,i] = (d_ci^T misc)[i, 5]  (misc column 5 is a column of ones)
-        pairs += [(gr["d_ew"], sv["att"]), (gr["d_ci"], sv["misc"])]
-        if ctx.with_unc:
-            pairs += [(gr["d_ul"], sv["hu"]), (gr["d_hu"], sv["x36"])]
-        w = _wgrad_all(pairs)
-        d_c1, d_c0 = w[0][:3], w[1][:, :84]
-        d_s2 = torch.cat([w[2][64:65], w[2][:64]], dim=0)                # rows: geo_feat 0..63, density logit 64 -> sigma_net.2's row order
-        d_s1, d_s0 = w[3], torch.cat([w[4][:, :36], w[4][:, 40:73]], dim=1)      # s_in = [enc_x 36 | pad 4 | enc_w 32 | e | pad 7]
-        d_a1, d_a0 = w[5], w[6][:, :36]
-        d_e1, d_e0 = w[7][:1], w[8][:, :36]
-        d_u1, d_u0 = (w[11][:1], w[12][:, :36]) if ctx.with_unc else (None, None)
-        # table gradients: d enc_x is already in the grid backward's [plane][level][sample] layout; the three planes (xy, yz, xz:
-        # network.py:208-212) go through one launch that takes its plane coordinates straight from xyz
-        enc = m.encoder_xy
-        S, H = float(math.log2(enc.per_level_scale)), enc.base_resolution
-        d_tabs = [torch.zeros_like(e_mod.embeddings) for e_mod in (m.encoder_xy, m.encoder_yz, m.encoder_xz)]
-        lib().call("b2n_triplane_grid_backward", planes.data_ptr(), x.data_ptr(), enc.offsets.data_ptr(), d_tabs[0].data_ptr(), d_tabs[1].data_ptr(),
-                   d_tabs[2].data_ptr(), M, 12, S, H, float(m.bound), torch.cuda.current_stream().cuda_stream)
-        d_enc_a = torch.diagonal(w[9]).reshape(enc_a.shape)
-        d_ind = w[10][:4, 5]
-        c = lambda t: None if t is None else t.contiguous()
-        return (None, None, None, d_enc_a, d_ind, None, d_tabs[0], d_tabs[1], d_tabs[2], c(d_a0), c(d_a1), c(d_e0), c(d_e1), c(d_s0), c(d_s1), c(d_s2),
-                c(d_c0), c(d_c1), c(d_u0), c(d_u1))
+        d_enc_a, d_ind, head, _ = _head_backward(ctx, g_sig, g_rgb, g_aud, g_eye, g_unc)
+        return (None, None, None, d_enc_a, d_ind, None, *head)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
+def _head_backward(ctx, g_sig, g_rgb, g_aud, g_eye, g_unc, audio=None):
+    """Shared backward of the fused head.  audio = (weights struct, auds): also back-propagate d enc_a through the audio nets, on a side stream,
+    concurrently with the table-gradient kernel (8 CTAs next to a 148-SM kernel).  Returns (d_enc_a, d_ind, [14 head gradients], [24 audio gradients] | None)."""
+    m, sv = ctx.model, ctx.saved_acts
+    x, enc_a, eye, sig, aud = ctx.saved_tensors
+    M, dev = x.shape[0], x.device
+    f32 = lambda t: None if t is None else t.float().contiguous()
+    g_sig, g_rgb, g_aud, g_eye, g_unc = f32(g_sig), f32(g_rgb), f32(g_aud), f32(g_eye), f32(g_unc)
+    gr = {k: torch.empty(M, w, dtype=torch.float16, device=dev) for k, w in GRAD_WIDTHS.items() if ctx.with_unc or k not in ("d_ul", "d_hu")}
+    planes = torch.empty(3, 12, M, dtype=torch.float32, device=dev)
+    gc = _GradsC(*[(gr[k].data_ptr() if k in gr else None) for k, _ in _GradsC._fields_[:-1]], planes.data_ptr())
+    from .model import _HeadSavedC
+    sc = _HeadSavedC(*[sv[k].data_ptr() if k in sv else None for k, _ in _HeadSavedC._fields_])
+    p = lambda t: None if t is None else t.data_ptr()
+    enc_a_flat = enc_a.contiguous().view(-1)
+    lib().call("b2n_head_backward", m.handle, M, enc_a_flat.data_ptr(), eye.data_ptr() if ctx.has_eye else None, ctypes.byref(sc), sig.data_ptr(),
+               aud.data_ptr(), p(g_sig), p(g_rgb), p(g_aud), p(g_eye), p(g_unc), ctypes.byref(gc), torch.cuda.current_stream().cuda_stream)
+    # weight gradients: one pass over (dY, X) per matrix
+    pairs = [(gr["d_rl"], sv["hc"]), (gr["d_hc"], sv["c_in"]), (gr["d_o"], sv["h2"]), (gr["d_h2"], sv["h1"]), (gr["d_h1"], sv["s_in"]),
+             (gr["d_att"], sv["ha"]), (gr["d_ha"], sv["x36"]), (gr["d_el"], sv["he"]), (gr["d_he"], sv["x36"])]
+    # two reductions over the samples ride along as products: d enc_a[j] = sum_m d_ew[m,j] att[m,j] = diag(d_ew^T att);
+    # d ind_code[i] = sum_m d_ci[m,i] = (d_ci^T misc)[i, 5]  (misc column 5 is a column of ones)
+    pairs += [(gr["d_ew"], sv["att"]), (gr["d_ci"], sv["misc"])]
+    if ctx.with_unc:
+        pairs += [(gr["d_ul"], sv["hu"]), (gr["d_hu"], sv["x36"])]
+    w = _wgrad_all(pairs)
+    d_c1, d_c0 = w[0][:3], w[1][:, :84]
+    d_s2 = torch.cat([w[2][64:65], w[2][:64]], dim=0)                # rows: geo_feat 0..63, density logit 64 -> sigma_net.2's row order
+    d_s1, d_s0 = w[3], torch.cat([w[4][:, :36], w[4][:, 40:73]], dim=1)      # s_in = [enc_x 36 | pad 4 | enc_w 32 | e | pad 7]
+    d_a1, d_a0 = w[5], w[6][:, :36]
+    d_e1, d_e0 = w[7][:1], w[8][:, :36]
+    d_u1, d_u0 = (w[11][:1], w[12][:, :36]) if ctx.with_unc else (None, None)
+    d_enc_a = torch.diagonal(w[9]).reshape(enc_a.shape)
+    d_ind = w[10][:4, 5]
+    audio_grads, side = None, None
+    if audio is not None:
+        aw, auds = audio
+        params = audio_parameters(m)
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(cur)                                  # d enc_a is ready
+        with torch.cuda.stream(side):
+            flat = torch.zeros(sum(p_.numel() for p_ in params), dtype=torch.float32, device=dev)
+            audio_grads, off = [], 0
+            for p_ in params:
+                audio_grads.append(flat[off:off + p_.numel()].view_as(p_)); off += p_.numel()
+            ptr = [v.data_ptr() for v in audio_grads]
+            gs = _AudioGradsC((ctypes.c_void_p * 4)(*ptr[0:4]), (ctypes.c_void_p * 4)(*ptr[4:8]), (ctypes.c_void_p * 2)(*ptr[8:10]), (ctypes.c_void_p * 2)(*ptr[10:12]),
+                              (ctypes.c_void_p * 5)(*ptr[12:17]), (ctypes.c_void_p * 5)(*ptr[17:22]), ptr[22], ptr[23])
+            g_flat = d_enc_a.float().contiguous().view(-1)
+            lib().call("b2n_audio_backward", ctypes.byref(aw), auds.data_ptr(), auds.shape[2], g_flat.data_ptr(), ctypes.byref(gs), side.cuda_stream)
+            flat.record_stream(cur)                            # consumed on the main stream after the join
+    # table gradients: d enc_x is already in the grid backward's [plane][level][sample] layout; the three planes (xy, yz, xz:
+    # network.py:208-212) go through one launch that takes its plane coordinates straight from xyz
+    enc = m.encoder_xy
+    S, H = float(math.log2(enc.per_level_scale)), enc.base_resolution
+    d_tabs = [torch.zeros_like(e_mod.embeddings) for e_mod in (m.encoder_xy, m.encoder_yz, m.encoder_xz)]
+    lib().call("b2n_triplane_grid_backward", planes.data_ptr(), x.data_ptr(), enc.offsets.data_ptr(), d_tabs[0].data_ptr(), d_tabs[1].data_ptr(),
+               d_tabs[2].data_ptr(), M, 12, S, H, float(m.bound), torch.cuda.current_stream().cuda_stream)
+    if side is not None:
+        torch.cuda.current_stream(dev).wait_stream(side)      # join before anybody reads the audio gradients
+    c = lambda t: None if t is None else t.contiguous()
+    return d_enc_a, d_ind, [d_tabs[0], d_tabs[1], d_tabs[2], c(d_a0), c(d_a1), c(d_e0), c(d_e1), c(d_s0), c(d_s1), c(d_s2), c(d_c0), c(d_c1), c(d_u0), c(d_u1)], audio_grads
 
 
 def fused_head_train(model, x, d, enc_a, ind_code, eye):
@@ -193,6 +229,39 @@ class _AudioEncode(torch.autograd.Function):
         lib().call("b2n_audio_backward", ctypes.byref(ctx.w), ctx.auds.data_ptr(), ctx.auds.shape[2], g.data_ptr(), ctypes.byref(gs),
                    torch.cuda.current_stream().cuda_stream)
         return (None, None) + tuple(views)
+
+
+class _FusedHeadAudio(torch.autograd.Function):
+    """encode_audio + NeRFNetwork.forward as ONE autograd node, so that the audio nets' backward (a latency-bound 8-CTA cluster kernel) runs on a side
+    stream next to the table-gradient kernel instead of after it."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, model, x, d, auds, ind_code, eye, n_head, *params):
+        auds = auds.contiguous()
+        aw = model.audio_weights_struct()
+        enc_a = torch.empty(1, 32, dtype=torch.float32, device=auds.device)
+        lib().call("b2n_audio_encode", ctypes.byref(aw), auds.data_ptr(), auds.shape[2], enc_a.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        sig, rgb, aud, eye_att, unc, saved = model.forward_train_fused(x, d, enc_a, ind_code, eye)
+        ctx.model, ctx.saved_acts, ctx.with_unc = model, saved, "hu" in saved
+        ctx.audio = (aw, auds)
+        x = x.contiguous()
+        ctx.save_for_backward(x, enc_a, eye if eye is not None else torch.zeros(1, device=x.device), sig, aud)
+        ctx.has_eye = eye is not None
+        return sig, rgb, aud, eye_att, unc
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g_sig, g_rgb, g_aud, g_eye, g_unc):
+        _, d_ind, head, audio = _head_backward(ctx, g_sig, g_rgb, g_aud, g_eye, g_unc, audio=ctx.audio)
+        return (None, None, None, None, d_ind, None, None, *head, *audio)
+
+
+def fused_head_audio_train(model, x, d, auds, ind_code, eye):
+    """encode_audio(auds) -> forward(x, d, enc_a, ind_code, eye) in a training step, both directions on the fused kernels (att > 0)."""
+    hp = head_parameters(model)
+    sig, rgb, aud, eye_att, unc = _FusedHeadAudio.apply(model, x, d, auds, ind_code.view(-1), eye, len(hp), *hp, *audio_parameters(model))
+    return sig, rgb, aud[:, None], eye_att[:, None], unc[:, None, None]
 
 
 def fused_encode_audio(model, auds):

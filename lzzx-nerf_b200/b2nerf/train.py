@@ -49,11 +49,8 @@ class Trainer:
         `index` may be an int or a 1-element device tensor (graph mode); `counter` overrides the step-counter slot."""
         m = self.m
         nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, m.aabb_train, self.min_near)
-        if self.fused_head and m.att > 0:
-            from .fused_train import fused_encode_audio
-            enc_a = fused_encode_audio(m, auds)            # two cluster kernels instead of the cuDNN graph
-        else:
-            enc_a = m.encode_audio(auds)
+        fused_audio = self.fused_head and m.att > 0
+        enc_a = None if fused_audio else m.encode_audio(auds)       # fused: the audio nets are part of the head's autograd node
         ind_code = m.individual_codes.index_select(0, index)[0] if torch.is_tensor(index) else m.individual_codes[index]
         if counter is None:
             counter = m.step_counter[self.local_step % 16]
@@ -65,7 +62,11 @@ class Trainer:
         if self.fused_head:
             from .fused_train import fused_head_train
             m.pack()                                   # the optimizer moved the weights: refresh the operand images (three small kernels)
-            sigmas, rgbs, amb_aud, amb_eye, unc = fused_head_train(m, xyzs, dirs, enc_a, ind_code, eye)
+            if fused_audio:
+                from .fused_train import fused_head_audio_train
+                sigmas, rgbs, amb_aud, amb_eye, unc = fused_head_audio_train(m, xyzs, dirs, auds, ind_code, eye)
+            else:
+                sigmas, rgbs, amb_aud, amb_eye, unc = fused_head_train(m, xyzs, dirs, enc_a, ind_code, eye)
         else:
             sigmas, rgbs, amb_aud, amb_eye, unc = m.forward_unfused(xyzs, dirs, enc_a, ind_code, eye)
         ws, aud_sum, eye_sum, unc_sum, depth, image = raymarching.composite_rays_train_triplane(

@@ -305,3 +305,43 @@ def test_fused_audio_backward_matches_autograd(hubert):
             assert err_fused < 2.5 * err_autocast + 2e-2, (n, err_fused, err_autocast)
         n_checked += 1
     assert n_checked == 24
+
+
+def test_combined_head_audio_node_equals_separate_nodes():
+    """fused_head_audio_train (one autograd node, audio backward on a side stream next to the table-gradient kernel) gives the gradients of
+    fused_encode_audio -> fused_head_train (two nodes, one stream)."""
+    import copy
+    from b2nerf.model import HeadModel
+    from b2nerf.fused_train import fused_head_train, fused_encode_audio, fused_head_audio_train
+    torch.manual_seed(12)
+    m = HeadModel(audio_in_dim=29).cuda()
+    for enc in (m.encoder_xy, m.encoder_yz, m.encoder_xz):
+        enc.embeddings.data.uniform_(-0.5, 0.5)
+    m.testing = False
+    m2 = copy.deepcopy(m)
+    M = 16384
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.rand(M, 3, device="cuda", generator=g) * 2 - 1) * torch.tensor([1.0, 0.5, 1.0], device="cuda")
+    d = torch.nn.functional.normalize(torch.randn(M, 3, device="cuda", generator=g), dim=1)
+    auds = torch.from_numpy(scene.audio_window(2, hubert=False)).cuda()
+    eye = torch.tensor([[0.3]], device="cuda")
+    outs = []
+    for model, combined in ((m, True), (m2, False)):
+        with torch.autocast("cuda", dtype=torch.float16):
+            model.pack()
+            if combined:
+                o = fused_head_audio_train(model, x, d, auds, model.individual_codes[4], eye)
+            else:
+                o = fused_head_train(model, x, d, fused_encode_audio(model, auds), model.individual_codes[4], eye)
+            loss = (o[0].sum() * 1e-3 + o[1].sum() + o[2].sum() + o[3].sum()) * 64.0
+        loss.backward()
+        outs.append(o)
+    torch.cuda.synchronize()
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    for (n, p), (_, q) in zip(m.named_parameters(), m2.named_parameters()):
+        if q.grad is None:
+            assert p.grad is None or float(p.grad.abs().sum()) == 0, n
+            continue
+        scale = float(q.grad.abs().max()) + 1e-20
+        assert float((p.grad - q.grad).abs().max()) <= 1e-4 * scale, (n, float((p.grad - q.grad).abs().max()) / scale)      # atomics order only
