@@ -237,15 +237,11 @@ class _FusedHeadAudio(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, model, x, d, auds, ind_code, eye, enc_a_ready, *params):
+    def forward(ctx, model, x, d, auds, ind_code, eye, n_head, *params):
         auds = auds.contiguous()
         aw = model.audio_weights_struct()
-        if enc_a_ready is not None:            # launched early on a side stream by start_audio_encode() (overlaps the ray march)
-            enc_a, side = enc_a_ready
-            torch.cuda.current_stream(auds.device).wait_stream(side)
-        else:
-            enc_a = torch.empty(1, 32, dtype=torch.float32, device=auds.device)
-            lib().call("b2n_audio_encode", ctypes.byref(aw), auds.data_ptr(), auds.shape[2], enc_a.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        enc_a = torch.empty(1, 32, dtype=torch.float32, device=auds.device)
+        lib().call("b2n_audio_encode", ctypes.byref(aw), auds.data_ptr(), auds.shape[2], enc_a.data_ptr(), torch.cuda.current_stream().cuda_stream)
         sig, rgb, aud, eye_att, unc, saved = model.forward_train_fused(x, d, enc_a, ind_code, eye)
         ctx.model, ctx.saved_acts, ctx.with_unc = model, saved, "hu" in saved
         ctx.audio = (aw, auds)
@@ -261,26 +257,10 @@ class _FusedHeadAudio(torch.autograd.Function):
         return (None, None, None, None, d_ind, None, None, *head, *audio)
 
 
-def start_audio_encode(model, auds):
-    """Launch the forward audio kernel on the side stream NOW (it only needs auds and the weights) so that it overlaps whatever the caller enqueues
-    next on the main stream (near/far, the ray march); pass the result to fused_head_audio_train(enc_a_ready=...)."""
-    dev = auds.device
-    auds = auds.float().contiguous()
-    cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
-    side.wait_stream(cur)
-    with torch.cuda.stream(side):
-        aw = model.audio_weights_struct()
-        enc_a = torch.empty(1, 32, dtype=torch.float32, device=dev)
-        lib().call("b2n_audio_encode", ctypes.byref(aw), auds.data_ptr(), auds.shape[2], enc_a.data_ptr(), side.cuda_stream)
-        enc_a.record_stream(cur)
-    model._keep_audio_start = (aw, auds)
-    return enc_a, side
-
-
-def fused_head_audio_train(model, x, d, auds, ind_code, eye, enc_a_ready=None):
+def fused_head_audio_train(model, x, d, auds, ind_code, eye):
     """encode_audio(auds) -> forward(x, d, enc_a, ind_code, eye) in a training step, both directions on the fused kernels (att > 0)."""
     hp = head_parameters(model)
-    sig, rgb, aud, eye_att, unc = _FusedHeadAudio.apply(model, x, d, auds, ind_code.view(-1), eye, enc_a_ready, *hp, *audio_parameters(model))
+    sig, rgb, aud, eye_att, unc = _FusedHeadAudio.apply(model, x, d, auds, ind_code.view(-1), eye, len(hp), *hp, *audio_parameters(model))
     return sig, rgb, aud[:, None], eye_att[:, None], unc[:, None, None]
 
 

@@ -48,12 +48,8 @@ class Trainer:
         """run_cuda's training branch (renderer.py:279-304).  Returns dict(image, weights_sum, ambient_aud, ambient_eye, uncertainty, n_samples_buffer).
         `index` may be an int or a 1-element device tensor (graph mode); `counter` overrides the step-counter slot."""
         m = self.m
-        fused_audio = self.fused_head and m.att > 0
-        enc_ready = None
-        if fused_audio:
-            from .fused_train import start_audio_encode
-            enc_ready = start_audio_encode(m, auds)                  # side stream: overlaps near/far + the ray march
         nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, m.aabb_train, self.min_near)
+        fused_audio = self.fused_head and m.att > 0
         enc_a = None if fused_audio else m.encode_audio(auds)       # fused: the audio nets are part of the head's autograd node
         ind_code = m.individual_codes.index_select(0, index)[0] if torch.is_tensor(index) else m.individual_codes[index]
         if counter is None:
@@ -68,7 +64,7 @@ class Trainer:
             m.pack()                                   # the optimizer moved the weights: refresh the operand images (three small kernels)
             if fused_audio:
                 from .fused_train import fused_head_audio_train
-                sigmas, rgbs, amb_aud, amb_eye, unc = fused_head_audio_train(m, xyzs, dirs, auds, ind_code, eye, enc_a_ready=enc_ready)
+                sigmas, rgbs, amb_aud, amb_eye, unc = fused_head_audio_train(m, xyzs, dirs, auds, ind_code, eye)
             else:
                 sigmas, rgbs, amb_aud, amb_eye, unc = fused_head_train(m, xyzs, dirs, enc_a, ind_code, eye)
         else:
