@@ -18,7 +18,6 @@
 //     row), apply the activation and write the next layer's fp16 operand straight back to shared memory.
 //   * the gather (144 table reads per sample) reads the fp32 tables through L1/L2 with paired corner loads.
 #include "common.cuh"
-#include "gridcore.cuh"
 #include "tc5.cuh"
 #include "fused_head.cuh"
 
@@ -84,9 +83,10 @@ __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
 }
 // TMEM -> fp16 operand tile: reads 64 accumulator columns of this thread's row starting at TMEM address `taddr`, applies
 // (+bias, ReLU) and writes them as halves 0..63 of row `row` of a SWIZZLE_128B tile.  Inlined (the table loads of a gather trip stay in
-// flight across it) but rolled over 32-column blocks to keep the tile loop's code size down.
+// flight across it) but rolled over 32-column blocks to keep the tile loop's code size down.  (Training copies the finished rows out with
+// warp_rows_out.)
 template <bool RELU, bool BIAS>
-__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, uint32_t row, const float *bias, uint4 *save = nullptr) {
+__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, uint32_t row, const float *bias) {
 #pragma unroll 1
     for (uint32_t cb = 0; cb < 64; cb += 32) {
         uint32_t acc[32];
@@ -104,10 +104,6 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t *tile, u
             }
             q[c] = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4 *>(tile + sw128_offset(row, (cb >> 3) + c)) = q[c];
-        }
-        if (save) {                                   // training: the same fp16 row, kept for the backward (32-byte stores when the row allows it)
-            if ((reinterpret_cast<uintptr_t>(save) & 31u) == 0) { st256(save + (cb >> 3), q[0], q[1]); st256(save + (cb >> 3) + 2, q[2], q[3]); }
-            else { save[(cb >> 3)] = q[0]; save[(cb >> 3) + 1] = q[1]; save[(cb >> 3) + 2] = q[2]; save[(cb >> 3) + 3] = q[3]; }
         }
     }
 }
@@ -133,7 +129,7 @@ __device__ __forceinline__ void warp_rows_out(const uint8_t *tile, uint32_t warp
 
 // ---- tri-plane gather, split in two halves so the table reads of one trip (2 levels x 3 planes x 4 corners = 24 loads per sample) stay
 // in flight underneath an MMA completion wait and its epilogue:  gather_issue() computes the cells and issues the loads, gather_finish()
-// blends and stores.  Arithmetic identical to gridcore.cuh:lvl2_interp / k_grid_fwd<float,2,1>: position fma(u, scale, 0.5), weights
+// blends and stores.  Arithmetic identical to gridenc.cu:k_grid_fwd<float,2,1>: position fma(u, scale, 0.5), weights
 // (1-fx|fx)*(1-fy|fy), four fmas in corner order (0,0),(1,0),(0,1),(1,1); index i + j*stride on dense levels, (i ^ j*2654435761) & (size-1)
 // on hashed levels (gridencoder.cu:54-72 with D = 2; the level kind is uniform over the grid).
 struct SampleCoord { float ux, uy, uz; uint32_t ok; };      // normalised coordinates; ok bit p = plane p in range (and the row is live)
