@@ -180,6 +180,17 @@ int b2n_linear_wgrad(const void *dy_f16, const void *x_f16, uint32_t M, uint32_t
  * partial to copy b mod replicas and the caller sums the copies: hundreds of CTAs reducing into ONE small matrix serialise in the L2. */
 int b2n_linear_wgrad_replicated(const void *dy_f16, const void *x_f16, uint32_t M, uint32_t out_dim, uint32_t in_dim, float *dw, uint32_t replicas,
                                 uint32_t replica_stride, void *stream);
+/* Up to 16 such products over the same M rows in ONE launch (all weight gradients of a backward): every CTA streams the jobs back to back through one
+ * cp.async ring, two TMEM accumulators alternate so the reduction of job j overlaps the multiplication of job j + 1.  Operands must be 16-byte aligned
+ * with widths that are multiples of 8 (the layouts of b2n_head_saved / b2n_head_grads); dw of job j is accumulated into replica (cta mod replicas) at
+ * dw + r * replica_stride floats. */
+typedef struct {
+    const void *dy;      /* f16 [M, out_dim] */
+    const void *x;       /* f16 [M, in_dim] */
+    float *dw;           /* f32 [replicas][out_dim, in_dim] with replica stride */
+    uint32_t out_dim, in_dim;
+} b2n_wgrad_job;
+int b2n_linear_wgrad_batch(const b2n_wgrad_job *jobs, uint32_t n_jobs, uint32_t M, uint32_t replicas, uint32_t replica_stride, void *stream);
 
 /* AdamW over one flat fp32 parameter buffer (parameters, gradients and both moments contiguous; two hyper-parameter groups split at
  * n_group0).  Replaces torch.optim.AdamW + the GradScaler unscale pass of the reference's optimizer step (TrainerUtil.py:1040-1056,

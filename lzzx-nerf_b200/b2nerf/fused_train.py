@@ -30,18 +30,24 @@ def head_parameters(model):
             model.color_net.net[0].weight, model.color_net.net[1].weight, model.unc_net.net[0].weight, model.unc_net.net[1].weight]
 
 
+class _WgradJobC(ctypes.Structure):
+    """b2n_wgrad_job (include/b2nerf_fused.h)"""
+    _fields_ = [("dy", ctypes.c_void_p), ("x", ctypes.c_void_p), ("dw", ctypes.c_void_p), ("out_dim", ctypes.c_uint32), ("in_dim", ctypes.c_uint32)]
+
+
 def _wgrad_all(pairs):
     """pairs: [(dY [M,o] fp16, X [M,i] fp16)] -> list of fp32 [o,i] = dY^T X.  All results share one zero-initialised buffer [replicas, total]
-    (ONE fill), every CTA of every launch adds its partial to replica (cta mod replicas), and ONE sum over the replica axis finishes all of them."""
+    (ONE fill), ONE launch streams all the products (b2n_linear_wgrad_batch), every CTA adds its partials to replica (cta mod replicas), and ONE sum
+    over the replica axis finishes all of them."""
     dev = pairs[0][0].device
     sizes = [dy.shape[1] * x.shape[1] for dy, x in pairs]
     total = sum(sizes)
     buf = torch.zeros(WGRAD_REPLICAS, total, dtype=torch.float32, device=dev)
-    st, off = torch.cuda.current_stream().cuda_stream, 0
-    for (dy, x), sz in zip(pairs, sizes):
-        lib().call("b2n_linear_wgrad_replicated", dy.data_ptr(), x.data_ptr(), x.shape[0], dy.shape[1], x.shape[1], buf.data_ptr() + 4 * off, WGRAD_REPLICAS,
-                   total, st)
+    jobs, off = (_WgradJobC * len(pairs))(), 0
+    for k, ((dy, x), sz) in enumerate(zip(pairs, sizes)):
+        jobs[k] = _WgradJobC(dy.data_ptr(), x.data_ptr(), buf.data_ptr() + 4 * off, dy.shape[1], x.shape[1])
         off += sz
+    lib().call("b2n_linear_wgrad_batch", jobs, len(pairs), pairs[0][1].shape[0], WGRAD_REPLICAS, total, torch.cuda.current_stream().cuda_stream)
     flat = buf.sum(0)
     outs, off = [], 0
     for (dy, x), sz in zip(pairs, sizes):

@@ -325,6 +325,113 @@ __global__ void __launch_bounds__(WP_THREADS, 1) k_linear_wgrad_pipe(const __hal
     if (warp == 8) tmem_dealloc(tmem, 128);
 }
 
+// ---- all weight gradients of one backward in ONE launch ---------------------------------------------------------------------------------
+// The 11-13 products of a step share M and differ only in their (narrow) operands; launched one by one each pays ~5 us of launch / ramp / tail on
+// 10-25 us of streaming.  Here every CTA walks the jobs back to back through the same cp.async ring: the producers never drain between jobs, the MMA
+// warp alternates between two TMEM accumulators, and four epilogue warps reduce job j into memory while job j + 1 is being multiplied.
+struct WgradJobs { b2n_wgrad_job j[16]; uint32_t n, M, replicas, rstride; };
+constexpr uint32_t WM_THREADS = WG_THREADS + 32 + 128;                    // 8 producer warps, the MMA warp (8), epilogue warps 9..12
+constexpr uint32_t WM_SMEM = WP_STAGES * WP_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(WM_THREADS, 1) k_linear_wgrad_multi(const __grid_constant__ WgradJobs J) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + WP_STAGES * WP_STAGE_BYTES), *empty = full + WP_STAGES, *acc_full = empty + WP_STAGES, *acc_free = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_free + 2);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t n_chunks = (J.M + WG_CHUNK - 1) / WG_CHUNK;
+    if (tid == 0) {
+        for (uint32_t s = 0; s < WP_STAGES; s++) { mbar_init(&full[s], WG_THREADS); mbar_init(&empty[s], 1); }
+        for (uint32_t a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_free[a], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 256);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t base_a = smem_u32(base);
+    const uint32_t my_n = blockIdx.x < n_chunks ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;      // chunks per job for this CTA
+    const uint32_t total = my_n * J.n;
+    constexpr uint32_t AHEAD = WP_STAGES - 1;
+    // stale bytes of a wider previous job may sit beyond a job's operand widths: harmless, D[o, i] only depends on column o of A and column i of B,
+    // and the epilogue writes o < out_dim, i < in_dim only
+    if (tid < WG_THREADS) {
+        auto issue = [&](uint32_t g) {
+            const uint32_t job = g / my_n, i = g - job * my_n;
+            const b2n_wgrad_job &q = J.j[job];
+            const uint32_t st = base_a + (g % WP_STAGES) * WP_STAGE_BYTES, row0 = (blockIdx.x + i * gridDim.x) * WG_CHUNK;
+            issue_operand(st, reinterpret_cast<const __half *>(q.dy), row_map(q.out_dim), row0, J.M, q.out_dim);
+            issue_operand(st + WG_OPERAND_BYTES, reinterpret_cast<const __half *>(q.x), row_map(q.in_dim), row0, J.M, q.in_dim);
+        };
+        for (uint32_t g = 0; g < AHEAD; g++) { if (g < total) issue(g); cp_async_commit(); }
+        for (uint32_t g = 0; g < total; g++) {
+            cp_async_wait<AHEAD - 1>();
+            fence_proxy_async();
+            mbar_arrive(&full[g % WP_STAGES]);
+            const uint32_t nxt = g + AHEAD;
+            if (nxt < total) {
+                if (nxt >= WP_STAGES) mbar_wait(&empty[nxt % WP_STAGES], ((nxt / WP_STAGES) - 1u) & 1u);
+                issue(nxt);
+            }
+            cp_async_commit();
+        }
+    } else if (tid == WG_THREADS) {                                       // the MMA thread
+        uint32_t g = 0;
+        for (uint32_t job = 0; job < J.n; job++) {
+            const uint32_t a = job & 1u, n_pad = (J.j[job].in_dim + 15u) & ~15u;
+            const uint32_t idesc = idesc_f16(128, n_pad) | (1u << 15) | (1u << 16);
+            if (job >= 2) { mbar_wait(&acc_free[a], ((job >> 1) - 1u) & 1u); fence_after_sync(); }      // the epilogue of job - 2 has drained this accumulator
+            for (uint32_t i = 0; i < my_n; i++, g++) {
+                const uint32_t s = g % WP_STAGES;
+                mbar_wait(&full[s], (g / WP_STAGES) & 1u);
+                fence_after_sync();
+                uint64_t da = smem_desc_mn_sw128(base_a + s * WP_STAGE_BYTES), db = smem_desc_mn_sw128(base_a + s * WP_STAGE_BYTES + WG_OPERAND_BYTES);
+#pragma unroll 1
+                for (uint32_t k = 0; k < WG_CHUNK / 16; k++, da += 2048u >> 4, db += 2048u >> 4) mma_f16_ss(tmem + a * 128u, da, db, idesc, i > 0 || k > 0);
+                mma_commit(&empty[s]);
+            }
+            mma_commit(&acc_full[a]);                                     // arrives when every MMA of this job has completed
+        }
+    } else if (tid >= WG_THREADS + 32 && my_n > 0) {                      // epilogue warps: TMEM lane quarter = warp & 3
+        const uint32_t o = (warp & 3u) * 32u + (tid & 31u);
+        for (uint32_t job = 0; job < J.n; job++) {
+            const uint32_t a = job & 1u;
+            const b2n_wgrad_job &q = J.j[job];
+            const uint32_t n_pad = (q.in_dim + 15u) & ~15u;
+            float *dw = q.dw + (size_t)(blockIdx.x % J.replicas) * J.rstride;
+            const bool vec4 = (q.in_dim & 3u) == 0 && ((uintptr_t)dw & 15u) == 0;
+            mbar_wait(&acc_full[a], (job >> 1) & 1u);
+            fence_after_sync();
+            const uint32_t taddr = tmem + a * 128u + (((warp & 3u) * 32u) << 16);
+            for (uint32_t cb = 0; cb < n_pad; cb += 16) {
+                uint32_t acc[16];
+                ld16(taddr + cb, acc);
+                wait_ld();
+                if (o < q.out_dim) {
+                    float *row = dw + (size_t)o * q.in_dim + cb;
+                    if (vec4) {
+#pragma unroll
+                        for (uint32_t jj = 0; jj < 16; jj += 4)
+                            if (cb + jj < q.in_dim)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + jj), "f"(__uint_as_float(acc[jj])), "f"(__uint_as_float(acc[jj + 1])),
+                                             "f"(__uint_as_float(acc[jj + 2])), "f"(__uint_as_float(acc[jj + 3])) : "memory");
+                    } else {
+#pragma unroll
+                        for (uint32_t jj = 0; jj < 16; jj++)
+                            if (cb + jj < q.in_dim) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(row + jj), "f"(__uint_as_float(acc[jj])) : "memory");
+                    }
+                }
+            }
+            fence_before_sync();
+            mbar_arrive(&acc_free[a]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 256);
+}
+
 // halves per global access: 8/4/2 when rows allow it, 0 = flat 16-byte stream (odd width, 16-byte aligned matrix), 1 = element-wise
 static uint32_t vec_width(const void *p, uint32_t width) {
     for (uint32_t v = 8; v > 1; v >>= 1)
@@ -371,4 +478,28 @@ static int wgrad_launch(const void *dy, const void *x, uint32_t M, uint32_t out_
     }
     k_linear_wgrad<<<ctas, WG_THREADS, WG_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, va, vb, dw, replicas, rstride);
     return check_launch("linear_wgrad");
+}
+
+extern "C" int b2n_linear_wgrad_batch(const b2n_wgrad_job *jobs, uint32_t n_jobs, uint32_t M, uint32_t replicas, uint32_t replica_stride, void *stream) {
+    B2N_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= 16, "linear_wgrad_batch: 1..16 jobs");
+    B2N_REQUIRE(replicas >= 1 && replicas <= 64, "linear_wgrad_batch: replicas=%u out of range (1..64)", replicas);
+    if (M == 0) return 0;
+    WgradJobs J = {};
+    J.n = n_jobs; J.M = M; J.replicas = replicas; J.rstride = replica_stride;
+    for (uint32_t i = 0; i < n_jobs; i++) {
+        const b2n_wgrad_job &q = jobs[i];
+        B2N_REQUIRE(q.dy && q.x && q.dw, "linear_wgrad_batch: null pointer in job %u", i);
+        B2N_REQUIRE(q.out_dim >= 8 && q.out_dim <= 128 && q.in_dim >= 8 && q.in_dim <= 128 && q.out_dim % 8 == 0 && q.in_dim % 8 == 0,
+                    "linear_wgrad_batch: job %u: out=%u / in=%u must be multiples of 8 in 8..128 (16-byte rows)", i, q.out_dim, q.in_dim);
+        B2N_REQUIRE(((uintptr_t)q.dy & 15) == 0 && ((uintptr_t)q.x & 15) == 0, "linear_wgrad_batch: job %u: operands must be 16-byte aligned", i);
+        B2N_REQUIRE(replicas == 1 || replica_stride >= q.out_dim * q.in_dim, "linear_wgrad_batch: replica stride smaller than matrix %u", i);
+        J.j[i] = q;
+    }
+    static bool attr = false;
+    if (!attr) { B2N_CUDA(cudaFuncSetAttribute(k_linear_wgrad_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM)); attr = true; }
+    const uint32_t n_chunks = ceil_div<uint32_t>(M, WG_CHUNK);
+    uint32_t g = (uint32_t)sm_count();
+    if (g > n_chunks) g = n_chunks;
+    k_linear_wgrad_multi<<<g, WM_THREADS, WM_SMEM, as_stream(stream)>>>(J);
+    return check_launch("linear_wgrad_batch");
 }

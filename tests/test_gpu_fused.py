@@ -352,3 +352,31 @@ def test_pose_in_rgb8_out_frame_equals_rays_in_frame():
     assert torch.equal(r.image, img_pose)
     assert np.array_equal(out_u8.numpy(), (out_f.numpy() * 255).astype(np.uint8))
     assert 0.0 < float(img_pose.mean()) < 1.0 and int((out_u8 < 250).sum()) > 100      # the head is in the picture
+
+
+def test_linear_wgrad_batch_matches_single_launches():
+    """b2n_linear_wgrad_batch (all products of a backward in one launch, alternating TMEM accumulators) == the per-matrix kernel, in the fused
+    path's shapes, incl. a row count that is not a multiple of the 64-sample chunk and more jobs than accumulators."""
+    import ctypes
+    from b2nerf._lib import lib
+    from b2nerf.fused_train import _WgradJobC
+    M = 20000 + 24
+    shapes = [(8, 64), (64, 88), (72, 64), (64, 64), (64, 80), (32, 64), (64, 40), (8, 16), (16, 40), (32, 32), (8, 8), (8, 32), (32, 40)]
+    g = torch.Generator(device="cuda").manual_seed(21)
+    pairs = [(torch.randn(M, o, device="cuda", generator=g).half(), torch.randn(M, i, device="cuda", generator=g).half()) for o, i in shapes]
+    R = 4
+    total = sum(o * i for o, i in shapes)
+    buf = torch.zeros(R, total, device="cuda")
+    jobs, off = (_WgradJobC * len(pairs))(), 0
+    for k, (dy, x) in enumerate(pairs):
+        jobs[k] = _WgradJobC(dy.data_ptr(), x.data_ptr(), buf.data_ptr() + 4 * off, dy.shape[1], x.shape[1])
+        off += dy.shape[1] * x.shape[1]
+    st = torch.cuda.current_stream().cuda_stream
+    lib().call("b2n_linear_wgrad_batch", jobs, len(pairs), M, R, total, st)
+    flat, off = buf.sum(0), 0
+    for (dy, x), (o, i) in zip(pairs, shapes):
+        ref = dy.float().t() @ x.float()
+        got = flat[off:off + o * i].view(o, i)
+        scale = float(ref.abs().max())
+        assert float((got - ref).abs().max()) <= 1e-4 * scale + 1e-3, ((o, i), float((got - ref).abs().max()), scale)
+        off += o * i
