@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(WG_THREADS, 3) k_linear_wgrad(const __half *__
 // One CTA per SM, a ring of WP_STAGES operand stages filled with cp.async (16-byte asynchronous copies, zero-fill past the last row): the
 // copies of chunks c+1 .. c+3 are in flight while chunk c is multiplied, so the per-chunk global-load latency that bounds the simple kernel
 // (one chunk per CTA in flight, ~2 us per chunk) is hidden.
-constexpr uint32_t WP_STAGES = 6;
+constexpr uint32_t WP_STAGES = 4;
 constexpr uint32_t WP_STAGE_BYTES = 2 * WG_OPERAND_BYTES;                 // A (<= 128 features) + B (<= 128 features) of one 64-sample chunk
 constexpr uint32_t WP_SMEM = WP_STAGES * WP_STAGE_BYTES + 1024 + 128;
 
