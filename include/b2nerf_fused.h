@@ -32,7 +32,10 @@ typedef struct {
 typedef struct b2n_model b2n_model;   /* opaque: fp16 weight image in the tensor-core operand layout */
 
 int  b2n_model_create(b2n_model **out, void *stream);
-/* (re)packs the weights on `stream` (two small kernels); the table / offsets pointers are kept, not copied */
+/* (re)packs the weights AND the tables on `stream` (four small kernels): the MLPs into the fp16 operand images, the three tri-plane tables into
+ * the corner-quad image the fused gather reads (one 16-byte entry per cell = its four corner values, hashed levels de-hashed; 39.6 MB for the
+ * reference geometry).  Call it after every change to weights or tables.  The table / offsets pointers are also kept (not copied) for the backward
+ * kernels.  Environment B2N_HEAD_QUADS=0 (read at b2n_model_create) keeps the gather on the reference-format tables instead. */
 int  b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream);
 void b2n_model_destroy(b2n_model *m);
 

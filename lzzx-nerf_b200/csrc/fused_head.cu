@@ -17,6 +17,7 @@
 //     one thread per warpgroup with the accumulator in TMEM; epilogues read TMEM with tcgen05.ld (thread == sample
 //     row), apply the activation and write the next layer's fp16 operand straight back to shared memory.
 //   * the gather (144 table reads per sample) reads the fp32 tables through L1/L2 with paired corner loads.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc5.cuh"
 #include "fused_head.cuh"
@@ -133,8 +134,13 @@ __device__ __forceinline__ void warp_rows_out(const uint8_t *tile, uint32_t warp
 // (1-fx|fx)*(1-fy|fy), four fmas in corner order (0,0),(1,0),(0,1),(1,1); index i + j*stride on dense levels, (i ^ j*2654435761) & (size-1)
 // on hashed levels (gridencoder.cu:54-72 with D = 2; the level kind is uniform over the grid).
 struct SampleCoord { float ux, uy, uz; uint32_t ok; };      // normalised coordinates; ok bit p = plane p in range (and the row is live)
-struct GatherTrip { float v[2][3][4]; float fx[2], fy[2], fz[2]; };
+struct GatherTrip { float4 v[2][3]; float fx[2], fy[2], fz[2]; };      // v = corners (0,0),(1,0),(0,1),(1,1) of the cell
 
+// QUAD = false: four 4-byte reads per (level, plane) straight from the reference-format tables.
+// QUAD = true : ONE 16-byte read per (level, plane) from the model's corner-quad image (k_pack_quads below): entry (i, j) of a level holds the four
+//               corner values of cell (i, j), hashed levels de-hashed, so the index is i + j * res on every level.  Same values, same blend —
+//               the features are bit-identical; a sample costs 36 LDG.128 instead of 144 LDG.32 (+ their 64-bit address arithmetic and hashing).
+template <bool QUAD>
 __device__ __forceinline__ void gather_issue(GatherTrip &G, const float *__restrict__ t_xy, const float *__restrict__ t_yz, const float *__restrict__ t_xz,
                                              const HeadLvl *lv, const SampleCoord &c) {
 #pragma unroll
@@ -144,6 +150,13 @@ __device__ __forceinline__ void gather_issue(GatherTrip &G, const float *__restr
         const uint32_t ix = (uint32_t)floorf(qx), iy = (uint32_t)floorf(qy), iz = (uint32_t)floorf(qz);
         G.fx[q] = __fsub_rn(qx, (float)ix); G.fy[q] = __fsub_rn(qy, (float)iy); G.fz[q] = __fsub_rn(qz, (float)iz);
         // planes (i, j): xy = (ix, iy), yz = (iy, iz), xz = (ix, iz)   (split_xyz, network.py:208-212)
+        if (QUAD) {
+            const uint32_t my = iy * g.mul + g.off, mz = iz * g.mul + g.off;
+            G.v[q][0] = __ldg(reinterpret_cast<const float4 *>(t_xy) + (ix + my));
+            G.v[q][1] = __ldg(reinterpret_cast<const float4 *>(t_yz) + (iy + mz));
+            G.v[q][2] = __ldg(reinterpret_cast<const float4 *>(t_xz) + (ix + mz));
+            continue;
+        }
         const uint32_t my0 = iy * g.mul, my1 = my0 + g.mul, mz0 = iz * g.mul, mz1 = mz0 + g.mul, ix1 = ix + 1u, iy1 = iy + 1u;
         uint32_t e[3][4];
         if (g.mask == 0xffffffffu) {
@@ -156,15 +169,16 @@ __device__ __forceinline__ void gather_issue(GatherTrip &G, const float *__restr
             e[2][0] = (ix ^ mz0) & g.mask; e[2][1] = (ix1 ^ mz0) & g.mask; e[2][2] = (ix ^ mz1) & g.mask; e[2][3] = (ix1 ^ mz1) & g.mask;
         }
         const float *b0 = t_xy + g.off, *b1 = t_yz + g.off, *b2 = t_xz + g.off;
-#pragma unroll
-        for (uint32_t k = 0; k < 4; k++) { G.v[q][0][k] = __ldg(b0 + e[0][k]); G.v[q][1][k] = __ldg(b1 + e[1][k]); G.v[q][2][k] = __ldg(b2 + e[2][k]); }
+        G.v[q][0] = make_float4(__ldg(b0 + e[0][0]), __ldg(b0 + e[0][1]), __ldg(b0 + e[0][2]), __ldg(b0 + e[0][3]));
+        G.v[q][1] = make_float4(__ldg(b1 + e[1][0]), __ldg(b1 + e[1][1]), __ldg(b1 + e[1][2]), __ldg(b1 + e[1][3]));
+        G.v[q][2] = make_float4(__ldg(b2 + e[2][0]), __ldg(b2 + e[2][1]), __ldg(b2 + e[2][2]), __ldg(b2 + e[2][3]));
     }
 }
-__device__ __forceinline__ float blend4(const float (&v)[4], float fx, float gx, float fy, float gy) {
-    float r = __fmaf_rn(__fmul_rn(gx, gy), v[0], 0.0f);
-    r = __fmaf_rn(__fmul_rn(fx, gy), v[1], r);
-    r = __fmaf_rn(__fmul_rn(gx, fy), v[2], r);
-    r = __fmaf_rn(__fmul_rn(fx, fy), v[3], r);
+__device__ __forceinline__ float blend4(const float4 &v, float fx, float gx, float fy, float gy) {
+    float r = __fmaf_rn(__fmul_rn(gx, gy), v.x, 0.0f);
+    r = __fmaf_rn(__fmul_rn(fx, gy), v.y, r);
+    r = __fmaf_rn(__fmul_rn(gx, fy), v.z, r);
+    r = __fmaf_rn(__fmul_rn(fx, fy), v.w, r);
     return r;
 }
 // blend + store: levels (2k, 2k+1) of plane p are one packed half2 word (word p*6 + k) of the sample's row; out-of-range planes store 0
@@ -224,7 +238,7 @@ struct HeadSmem {                       // lives after the 1024-aligned weight i
     uint64_t bar_mma[HG_WGS];           // per-warpgroup MMA completion
 };
 
-template <bool SAVE>
+template <bool SAVE, bool QUAD>
 __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_constant__ HeadArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // pointer arithmetic keeps the shared address space visible to the compiler
@@ -319,12 +333,12 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         if (live0) { px = __ldcs(a.xyzs + 3 * (size_t)m0); py = __ldcs(a.xyzs + 3 * (size_t)m0 + 1); pz = __ldcs(a.xyzs + 3 * (size_t)m0 + 2); }
         const SampleCoord c = make_coord(px, py, pz, live0);
         GatherTrip GA, GB;                  // two trips in flight
-        gather_issue(GA, t_xy, t_yz, t_xz, &S.lvl[0], c);
+        gather_issue<QUAD>(GA, t_xy, t_yz, t_xz, &S.lvl[0], c);
 #pragma unroll 1
         for (uint32_t k = 0; k < 6; k += 2) {
-            gather_issue(GB, t_xy, t_yz, t_xz, &S.lvl[2 * k + 2], c);
+            gather_issue<QUAD>(GB, t_xy, t_yz, t_xz, &S.lvl[2 * k + 2], c);
             gather_finish(GA, c.ok, sXb + row_off, r7, k);
-            if (k + 2 < 6) gather_issue(GA, t_xy, t_yz, t_xz, &S.lvl[2 * k + 4], c);
+            if (k + 2 < 6) gather_issue<QUAD>(GA, t_xy, t_yz, t_xz, &S.lvl[2 * k + 4], c);
             gather_finish(GB, c.ok, sXb + row_off, r7, k + 1);
         }
         zero_k_padding(sXb);
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         // ---- P1: [aud hidden | eye hidden | sigma hidden (enc_x part)] = X * WA -------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sX_a, sW_a + HW_A, 3, 144, false); mma_commit(bar); }
         const SampleCoord cn = make_coord(npx, npy, npz, nlive);
-        if (has_next) { zero_k_padding(sXn); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[0], cn); }      // trip 0 in flight under P1
+        if (has_next) { zero_k_padding(sXn); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[0], cn); }      // trip 0 in flight under P1
         mma_done();
         float eye_att, unc_out = 0.6931471805599453f;       // testing: log(1 + e^0) (network.py:245,278)
         {
@@ -393,7 +407,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             if (a.has_unc) issue_mma(tmem_wg + TC_A + 32, sX_a, sW_a + HW_U, 3, 32, false);
             mma_commit(bar);
         }
-        if (has_next) { gather_finish(G, cn.ok, rown, r7, 0); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[2], cn); }      // trip 0 lands (issued a phase ago), trip 1 leaves
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 0); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[2], cn); }      // trip 0 lands (issued a phase ago), trip 1 leaves
         mma_done();
         float amb_aud;
         {
@@ -445,21 +459,21 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
         publish();
         // ---- P3: sigma hidden += [enc_w, e] * WC -------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
-        if (has_next) { gather_finish(G, cn.ok, rown, r7, 1); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[4], cn); }      // trip 1 lands (issued a phase ago), trip 2 leaves
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 1); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[4], cn); }      // trip 1 lands (issued a phase ago), trip 2 leaves
         mma_done();
         hidden_epilogue<true, false>(tmem_ld + TC_S, sH, t, nullptr);
         if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.h1) + tile_row0 * 128, 128, rows_valid);
         publish();
         // ---- P4: sigma layer 1 --------------------------------------------------------------------------------------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
-        if (has_next) { gather_finish(G, cn.ok, rown, r7, 2); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[6], cn); }      // trip 2 lands (issued a phase ago), trip 3 leaves
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 2); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[6], cn); }      // trip 2 lands (issued a phase ago), trip 3 leaves
         mma_done();
         hidden_epilogue<true, false>(tmem_ld + TC_A, sH, t, nullptr);
         if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.h2) + tile_row0 * 128, 128, rows_valid);
         publish();
         // ---- P5: sigma layer 2: cols 0..63 = geo_feat, col 64 = density logit (rows rotated at pack time) -----------------
         if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sH_a, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
-        if (has_next) { gather_finish(G, cn.ok, rown, r7, 3); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[8], cn); }      // trip 3 lands (issued a phase ago), trip 4 leaves
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 3); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[8], cn); }      // trip 3 lands (issued a phase ago), trip 4 leaves
         mma_done();
         float sigma;
         {
@@ -487,7 +501,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
             issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_F1, 1, 64, true);
             mma_commit(bar);
         }
-        if (has_next) { gather_finish(G, cn.ok, rown, r7, 4); gather_issue(G, t_xy, t_yz, t_xz, &S.lvl[10], cn); }      // trip 4 lands (issued a phase ago), trip 5 leaves
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 4); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[10], cn); }      // trip 4 lands (issued a phase ago), trip 5 leaves
         mma_done();
         hidden_epilogue<true, true>(tmem_ld + TC_S, sH, t, S.ind_bias);
         if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.hc) + tile_row0 * 128, 128, rows_valid);
@@ -533,12 +547,14 @@ __global__ void __launch_bounds__(HG_THREADS, 1) k_head_forward(const __grid_con
 
 size_t head_smem_bytes() { return 1024 + HW_BYTES + (size_t)HG_WGS * 3 * HG_TILE_BYTES + sizeof(HeadSmem); }
 
-int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save) {
+int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save, bool quad) {
     static bool attr = false;
     const size_t smem = head_smem_bytes();
     if (!attr) {
-        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     const uint32_t tiles = ceil_div<uint32_t>(a.M, HG_TILE);
@@ -546,9 +562,31 @@ int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save) {
     const uint32_t sms = (uint32_t)sm_count();
     if (ctas > sms) ctas = sms;
     if (ctas == 0) return 0;
-    if (save) k_head_forward<true><<<ctas, HG_THREADS, smem, st>>>(a);
-    else k_head_forward<false><<<ctas, HG_THREADS, smem, st>>>(a);
+    if (save) { if (quad) k_head_forward<true, true><<<ctas, HG_THREADS, smem, st>>>(a); else k_head_forward<true, false><<<ctas, HG_THREADS, smem, st>>>(a); }
+    else { if (quad) k_head_forward<false, true><<<ctas, HG_THREADS, smem, st>>>(a); else k_head_forward<false, false><<<ctas, HG_THREADS, smem, st>>>(a); }
     return check_launch("head_forward");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// corner-quad image of the three tables (QUAD gather): quads[plane][qoff(level) + i + j * res] = the four corner values of cell (i, j),
+// read through the reference's index function (gridencoder.cu:54-72, D = 2) — built by b2n_model_update, i.e. after every weight update.
+// ---------------------------------------------------------------------------------------------------
+struct QuadArgs { const float *tab[3]; HeadLvl lvl[12], qlvl[12]; uint32_t cells; float4 *quads; };      // cells = entries per plane
+
+__global__ void __launch_bounds__(256) k_pack_quads(const __grid_constant__ QuadArgs qa) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= qa.cells) return;
+    uint32_t l = 0;
+#pragma unroll
+    for (uint32_t k = 1; k < 12; k++) l += (c >= qa.qlvl[k].off) ? 1u : 0u;
+    const HeadLvl g = qa.lvl[l], q = qa.qlvl[l];
+    const uint32_t r = c - q.off, j = r / q.mul, i = r - j * q.mul;
+    const uint32_t m0 = j * g.mul, m1 = m0 + g.mul;
+    uint32_t e0, e1, e2, e3;
+    if (g.mask == 0xffffffffu) { e0 = i + m0; e1 = i + 1u + m0; e2 = i + m1; e3 = i + 1u + m1; }
+    else { e0 = (i ^ m0) & g.mask; e1 = ((i + 1u) ^ m0) & g.mask; e2 = (i ^ m1) & g.mask; e3 = ((i + 1u) ^ m1) & g.mask; }
+    const float *b = qa.tab[blockIdx.y] + g.off;
+    qa.quads[(size_t)blockIdx.y * qa.cells + c] = make_float4(__ldg(b + e0), __ldg(b + e1), __ldg(b + e2), __ldg(b + e3));
 }
 
 }  // namespace b2n
@@ -568,6 +606,7 @@ static int derive_levels(b2n_model *m, const b2n_head_weights *w, cudaStream_t s
     if (check_launch("model_update(scales)")) return 1;
     int32_t offs[13];
     float scales[12];
+    uint32_t qcells = 0;
     B2N_CUDA(cudaMemcpyAsync(offs, w->offsets, sizeof(offs), cudaMemcpyDeviceToHost, st));
     B2N_CUDA(cudaMemcpyAsync(scales, d_scales, sizeof(scales), cudaMemcpyDeviceToHost, st));
     B2N_CUDA(cudaStreamSynchronize(st));
@@ -585,7 +624,16 @@ static int derive_levels(b2n_model *m, const b2n_head_weights *w, cudaStream_t s
             g.mul = 2654435761u; g.mask = size - 1u;
         }
         m->lvl[l] = g;
+        // quad image: cells (i, j), i, j in [0, res): floor(u * scale + 0.5) <= res - 1 for u in [0, 1]
+        m->qlvl[l] = HeadLvl{scales[l], res, 0u, qcells};
+        qcells += res * res;
     }
+    if (m->use_quads && qcells != m->quad_cells) {
+        if (m->quads) cudaFree(m->quads);
+        m->quads = nullptr;
+        B2N_CUDA(cudaMalloc(&m->quads, (size_t)qcells * 3 * sizeof(float4)));
+    }
+    m->quad_cells = qcells;
     m->geo_offsets = w->offsets; m->geo_S = w->S; m->geo_H = w->H;
     return 0;
 }
@@ -596,6 +644,10 @@ int b2n_model_create(b2n_model **out, void *stream) {
     (void)stream;
     B2N_REQUIRE(out, "model_create: null pointer");
     b2n_model *m = new b2n_model();
+    {   // B2N_HEAD_QUADS=0 keeps the four-reads-per-cell gather on the reference-format tables (A/B measurements)
+        const char *e = getenv("B2N_HEAD_QUADS");
+        m->use_quads = !(e && e[0] == '0');
+    }
     if (cudaMalloc(&m->wimg, HW_BYTES) != cudaSuccess || cudaMalloc(&m->wimg_t, HT_BYTES) != cudaSuccess ||
         cudaMalloc(&m->wsmall, sizeof(float) * (HS_FLOATS + 16)) != cudaSuccess) {
         (void)cudaGetLastError();
@@ -614,6 +666,7 @@ void b2n_model_destroy(b2n_model *m) {
     cudaFree(m->wimg);
     cudaFree(m->wimg_t);
     cudaFree(m->wsmall);
+    if (m->quads) cudaFree(m->quads);
     delete m;
 }
 
@@ -667,6 +720,14 @@ int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
         k_pack_head<<<ceil_div<uint32_t>(HT_BYTES / 16, 256), 256, 0, st>>>(pt, m->wimg_t);
         if (check_launch("model_update(pack transposed)")) return 1;
     }
+    if (m->use_quads) {
+        QuadArgs qa = {};
+        qa.tab[0] = w->table_xy; qa.tab[1] = w->table_yz; qa.tab[2] = w->table_xz;
+        for (int l = 0; l < 12; l++) { qa.lvl[l] = m->lvl[l]; qa.qlvl[l] = m->qlvl[l]; }
+        qa.cells = m->quad_cells; qa.quads = m->quads;
+        k_pack_quads<<<dim3(ceil_div<uint32_t>(m->quad_cells, 256), 3), 256, 0, st>>>(qa);
+        if (check_launch("model_update(quads)")) return 1;
+    }
     m->w = *w;
     m->ready = true;
     return 0;
@@ -683,8 +744,13 @@ int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *di
     if (M == 0) return 0;
     HeadArgs a = {};
     a.xyzs = xyzs; a.dirs = dirs; a.M = M; a.n_valid = n_valid;
-    a.tab[0] = m->w.table_xy; a.tab[1] = m->w.table_yz; a.tab[2] = m->w.table_xz;
-    for (int l = 0; l < 12; l++) a.lvl[l] = m->lvl[l];
+    if (m->use_quads) {
+        for (int p = 0; p < 3; p++) a.tab[p] = reinterpret_cast<const float *>(m->quads + (size_t)p * m->quad_cells);
+        for (int l = 0; l < 12; l++) a.lvl[l] = m->qlvl[l];
+    } else {
+        a.tab[0] = m->w.table_xy; a.tab[1] = m->w.table_yz; a.tab[2] = m->w.table_xz;
+        for (int l = 0; l < 12; l++) a.lvl[l] = m->lvl[l];
+    }
     a.bound = m->w.bound;
     {   // (x + b) / (2b) == (x + b) * (1 / 2b) exactly when 2b is a power of two
         int ex = 0;
@@ -700,7 +766,7 @@ int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *di
         B2N_REQUIRE(!a.has_unc || saved->hu, "head_forward_train: unc_net is packed but saved->hu is NULL");
         a.sv = *saved;
     }
-    return launch_head_forward(a, st, saved != nullptr);
+    return launch_head_forward(a, st, saved != nullptr, m->use_quads);
 }
 }  // namespace b2n
 

@@ -82,6 +82,11 @@ struct b2n_model {
     float *wsmall = nullptr;       // HS_FLOATS (+ 16 floats of scratch for the device-computed level scales)
     b2n_head_weights w = {};
     b2n::HeadLvl lvl[12] = {};
+    // corner-quad image of the tables (fused_head.cu:k_pack_quads): [3][quad_cells] float4, qlvl[l] = {scale, res, -, first cell of the level}
+    float4 *quads = nullptr;
+    uint32_t quad_cells = 0;
+    b2n::HeadLvl qlvl[12] = {};
+    bool use_quads = true;
     // geometry the cached lvl[] was derived from (re-derived only when it changes: one small D2H read + sync)
     const int32_t *geo_offsets = nullptr;
     float geo_S = 0.0f;
@@ -92,6 +97,6 @@ struct b2n_model {
 namespace b2n {
 
 size_t head_smem_bytes();
-int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save = false);
+int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save = false, bool quad = false);
 
 }  // namespace b2n

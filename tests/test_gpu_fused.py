@@ -97,9 +97,32 @@ def test_fused_gather_equals_grid_encoder_bits():
     a = m(x, d, enc_a, c, e)[3].clone()           # eye attention depends on enc_x only
     x2 = x.clone(); x2[:, 0] = -x2[:, 0]           # change x only: planes xy and xz change
     m.encoder_xy.embeddings.data.zero_(); m.encoder_xz.embeddings.data.zero_()
+    m.pack()                                       # the tables are part of the packed model (corner-quad image), like the MLP weights
     b1 = m(x, d, enc_a, c, e)[3].clone(); b2 = m(x2, d, enc_a, c, e)[3].clone()
     torch.cuda.synchronize()
     assert torch.equal(b1, b2) and not torch.equal(a, b1)       # with only the yz plane alive, x is irrelevant
+
+
+@pytest.mark.parametrize("table_scale", [1.0, 1e-4])
+def test_quad_gather_equals_table_gather_bits(table_scale, monkeypatch):
+    """The corner-quad image (one 16-byte read per cell, hashed levels de-hashed; fused_head.cu:k_pack_quads) holds the same values the
+    reference index function (gridencoder.cu:54-72) reaches, so both gather modes give identical outputs, bit for bit — including samples on
+    the faces of the cube (last cell of every level) and out-of-range ones."""
+    import copy
+    m1 = _model(3, table_scale, False)
+    monkeypatch.setenv("B2N_HEAD_QUADS", "0")
+    m0 = copy.deepcopy(m1); m0._handle = None; m0._packed_weights = None
+    m0.pack()                                       # model created with the environment set: gathers from the reference-format tables
+    monkeypatch.delenv("B2N_HEAD_QUADS")
+    m1.pack()
+    x, d = _samples(200003, 11)
+    x[:6] = torch.tensor([[1.0, 1.0, 1.0], [-1.0, -1.0, -1.0], [1.0, -1.0, 0.0], [0.0, 1.0, -1.0], [1.5, 0.2, 0.1], [0.999999, 0.999999, 0.999999]], device="cuda")
+    enc_a = torch.randn(1, 32, device="cuda") * 0.5; c = m1.individual_codes[2:3].detach(); e = torch.tensor([[0.6]], device="cuda")
+    o1 = [t.clone() for t in m1(x, d, enc_a, c, e)]
+    o0 = [t.clone() for t in m0(x, d, enc_a, c, e)]
+    torch.cuda.synchronize()
+    for a, b in zip(o1, o0):
+        assert torch.equal(a, b)
 
 
 def _loop_reference(m, rays_o, rays_d, enc_a, c, e, fused_net, max_steps=16, dt_gamma=1 / 256, T_thresh=1e-4):
