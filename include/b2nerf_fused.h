@@ -195,6 +195,19 @@ typedef struct {
 } b2n_wgrad_job;
 int b2n_linear_wgrad_batch(const b2n_wgrad_job *jobs, uint32_t n_jobs, uint32_t M, uint32_t replicas, uint32_t replica_stride, void *stream);
 
+/* Finishing pass for replicated weight gradients (b2n_linear_wgrad_batch): for every block, dst[i * dst_ld + c] += sum over replicas r of
+ * src[r * replica_stride + src_off + i * src_ld + c], i < rows, c < cols — ONE launch that sums the replicas and accumulates each (padded, possibly
+ * row-rotated or column-sliced) product straight into the storage of the parameter's gradient (what autograd's AccumulateGrad + the slicing / cat
+ * kernels of a LinearBackward graph would do, TrainerUtil.py:1040-1046).  A diagonal is a block with cols = 1 and src_ld = ld + 1. */
+typedef struct {
+    uint32_t src_off, src_ld;     /* first element and row pitch inside one replica (floats) */
+    uint32_t rows, cols;
+    float   *dst;                 /* accumulated into */
+    uint32_t dst_ld;
+    uint32_t reserved;
+} b2n_wgrad_block;
+int b2n_wgrad_scatter(const float *src, uint32_t replicas, uint32_t replica_stride, const b2n_wgrad_block *blocks, uint32_t n_blocks, void *stream);
+
 /* AdamW over one flat fp32 parameter buffer (parameters, gradients and both moments contiguous; two hyper-parameter groups split at
  * n_group0).  Replaces torch.optim.AdamW + the GradScaler unscale pass of the reference's optimizer step (TrainerUtil.py:1040-1056,
  * train.py:274).  `step` is a 1-element device counter (incremented unless found_inf), `grad_scale` / `found_inf` are the GradScaler's

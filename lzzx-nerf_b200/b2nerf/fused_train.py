@@ -56,6 +56,50 @@ def _wgrad_all(pairs):
     return outs
 
 
+class _WgradBlockC(ctypes.Structure):
+    """b2n_wgrad_block (include/b2nerf_fused.h)"""
+    _fields_ = [("src_off", ctypes.c_uint32), ("src_ld", ctypes.c_uint32), ("rows", ctypes.c_uint32), ("cols", ctypes.c_uint32), ("dst", ctypes.c_void_p),
+                ("dst_ld", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+def _wgrad_all_direct(pairs, blocks_of):
+    """Same launch as _wgrad_all, but the replicas are summed AND accumulated into their destinations by one b2n_wgrad_scatter launch.
+    blocks_of(k, off, in_dim, scratch_ptr) -> [(src_off, src_ld, rows, cols, dst_ptr, dst_ld)] for product k.  Returns the 64-float scratch tail
+    (zero-initialised with the replica buffer) that blocks may target."""
+    dev = pairs[0][0].device
+    sizes = [dy.shape[1] * x.shape[1] for dy, x in pairs]
+    total = sum(sizes)
+    buf = torch.zeros(WGRAD_REPLICAS * total + 64, dtype=torch.float32, device=dev)
+    scratch = buf[WGRAD_REPLICAS * total:]
+    jobs, off, blocks = (_WgradJobC * len(pairs))(), 0, []
+    for k, ((dy, x), sz) in enumerate(zip(pairs, sizes)):
+        jobs[k] = _WgradJobC(dy.data_ptr(), x.data_ptr(), buf.data_ptr() + 4 * off, dy.shape[1], x.shape[1])
+        blocks += blocks_of(k, off, x.shape[1], scratch.data_ptr())
+        off += sz
+    st = torch.cuda.current_stream().cuda_stream
+    lib().call("b2n_linear_wgrad_batch", jobs, len(pairs), pairs[0][1].shape[0], WGRAD_REPLICAS, total, st)
+    arr = (_WgradBlockC * len(blocks))(*[_WgradBlockC(so, sl, r, c, dst, dl, 0) for so, sl, r, c, dst, dl in blocks])
+    lib().call("b2n_wgrad_scatter", buf.data_ptr(), WGRAD_REPLICAS, total, arr, len(blocks), st)
+    return scratch
+
+
+def _direct_targets(m, with_unc, audio):
+    """The .grad tensors the fused backward may accumulate into in place (Trainer's flat gradient buffer), or None when the caller asked for
+    ordinary autograd outputs (model._direct_grads unset, or some parameter has no contiguous fp32 .grad yet)."""
+    if not getattr(m, "_direct_grads", False):
+        return None
+    ps = head_parameters(m)
+    if not with_unc:
+        ps = ps[:12]
+    if audio:
+        ps = ps + audio_parameters(m)
+    for p_ in ps:
+        g = p_.grad
+        if g is None or g.dtype != torch.float32 or not g.is_contiguous() or not g.is_cuda:
+            return None
+    return True
+
+
 class _FusedHead(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -111,15 +155,43 @@ def _head_backward(ctx, g_sig, g_rgb, g_aud, g_eye, g_unc, audio=None):
     pairs += [(gr["d_ew"], sv["att"]), (gr["d_ci"], sv["misc"])]
     if ctx.with_unc:
         pairs += [(gr["d_ul"], sv["hu"]), (gr["d_hu"], sv["x36"])]
-    w = _wgrad_all(pairs)
-    d_c1, d_c0 = w[0][:3], w[1][:, :84]
-    d_s2 = torch.cat([w[2][64:65], w[2][:64]], dim=0)                # rows: geo_feat 0..63, density logit 64 -> sigma_net.2's row order
-    d_s1, d_s0 = w[3], torch.cat([w[4][:, :36], w[4][:, 40:73]], dim=1)      # s_in = [enc_x 36 | pad 4 | enc_w 32 | e | pad 7]
-    d_a1, d_a0 = w[5], w[6][:, :36]
-    d_e1, d_e0 = w[7][:1], w[8][:, :36]
-    d_u1, d_u0 = (w[11][:1], w[12][:, :36]) if ctx.with_unc else (None, None)
-    d_enc_a = torch.diagonal(w[9]).reshape(enc_a.shape)
-    d_ind = w[10][:4, 5]
+    direct = _direct_targets(m, ctx.with_unc, audio is not None)
+    if direct:
+        # every product lands in its parameter's .grad (views of the trainer's flat all-reduce buffer) through ONE finishing launch: no sum / slice /
+        # cat / contiguous / AccumulateGrad kernels.  Block = (src_off, src_ld, rows, cols, dst, dst_ld) inside product k (row pitch = its in_dim).
+        G = lambda t: t.grad.data_ptr()
+        net = dict(c1=m.color_net.net[1].weight, c0=m.color_net.net[0].weight, s2=m.sigma_net.net[2].weight, s1=m.sigma_net.net[1].weight,
+                   s0=m.sigma_net.net[0].weight, a1=m.aud_ch_att_net.net[1].weight, a0=m.aud_ch_att_net.net[0].weight, e1=m.eye_att_net.net[1].weight,
+                   e0=m.eye_att_net.net[0].weight, u1=m.unc_net.net[1].weight, u0=m.unc_net.net[0].weight)
+
+        def blocks_of(k, off, ld, scratch):
+            if k == 0: return [(off, ld, 3, 64, G(net["c1"]), 64)]
+            if k == 1: return [(off, ld, 64, 84, G(net["c0"]), 84)]
+            if k == 2: return [(off + 64 * ld, ld, 1, 64, G(net["s2"]), 64), (off, ld, 64, 64, G(net["s2"]) + 4 * 64, 64)]      # logit row 64 -> row 0
+            if k == 3: return [(off, ld, 64, 64, G(net["s1"]), 64)]
+            if k == 4: return [(off, ld, 64, 36, G(net["s0"]), 69), (off + 40, ld, 64, 33, G(net["s0"]) + 4 * 36, 69)]       # s_in = [enc_x 36 | pad 4 | enc_w 32 | e | pad 7]
+            if k == 5: return [(off, ld, 32, 64, G(net["a1"]), 64)]
+            if k == 6: return [(off, ld, 64, 36, G(net["a0"]), 36)]
+            if k == 7: return [(off, ld, 1, 16, G(net["e1"]), 16)]
+            if k == 8: return [(off, ld, 16, 36, G(net["e0"]), 36)]
+            if k == 9: return [(off, ld + 1, 32, 1, scratch, 1)]                       # d enc_a = diag(d_ew^T att)
+            if k == 10: return [(off + 5, ld, 4, 1, scratch + 4 * 32, 1)]              # d ind_code = column 5 of d_ci^T misc
+            if k == 11: return [(off, ld, 1, 32, G(net["u1"]), 32)]
+            return [(off, ld, 32, 36, G(net["u0"]), 36)]
+
+        scratch = _wgrad_all_direct(pairs, blocks_of)
+        d_enc_a, d_ind = scratch[:32].reshape(enc_a.shape), scratch[32:36]
+        d_c1 = d_c0 = d_s2 = d_s1 = d_s0 = d_a1 = d_a0 = d_e1 = d_e0 = d_u1 = d_u0 = None
+    else:
+        w = _wgrad_all(pairs)
+        d_c1, d_c0 = w[0][:3], w[1][:, :84]
+        d_s2 = torch.cat([w[2][64:65], w[2][:64]], dim=0)                # rows: geo_feat 0..63, density logit 64 -> sigma_net.2's row order
+        d_s1, d_s0 = w[3], torch.cat([w[4][:, :36], w[4][:, 40:73]], dim=1)      # s_in = [enc_x 36 | pad 4 | enc_w 32 | e | pad 7]
+        d_a1, d_a0 = w[5], w[6][:, :36]
+        d_e1, d_e0 = w[7][:1], w[8][:, :36]
+        d_u1, d_u0 = (w[11][:1], w[12][:, :36]) if ctx.with_unc else (None, None)
+        d_enc_a = torch.diagonal(w[9]).reshape(enc_a.shape)
+        d_ind = w[10][:4, 5]
     audio_grads, side = None, None
     if audio is not None:
         aw, auds = audio
@@ -128,23 +200,34 @@ def _head_backward(ctx, g_sig, g_rgb, g_aud, g_eye, g_unc, audio=None):
         side = _side_stream(dev)
         side.wait_stream(cur)                                  # d enc_a is ready
         with torch.cuda.stream(side):
-            flat = torch.zeros(sum(p_.numel() for p_ in params), dtype=torch.float32, device=dev)
-            audio_grads, off = [], 0
-            for p_ in params:
-                audio_grads.append(flat[off:off + p_.numel()].view_as(p_)); off += p_.numel()
-            ptr = [v.data_ptr() for v in audio_grads]
+            if direct:                                         # the kernel accumulates (red.global) straight into the parameters' .grad
+                audio_grads, flat = [None] * len(params), None
+                ptr = [p_.grad.data_ptr() for p_ in params]
+            else:
+                flat = torch.zeros(sum(p_.numel() for p_ in params), dtype=torch.float32, device=dev)
+                audio_grads, off = [], 0
+                for p_ in params:
+                    audio_grads.append(flat[off:off + p_.numel()].view_as(p_)); off += p_.numel()
+                ptr = [v.data_ptr() for v in audio_grads]
             gs = _AudioGradsC((ctypes.c_void_p * 4)(*ptr[0:4]), (ctypes.c_void_p * 4)(*ptr[4:8]), (ctypes.c_void_p * 2)(*ptr[8:10]), (ctypes.c_void_p * 2)(*ptr[10:12]),
                               (ctypes.c_void_p * 5)(*ptr[12:17]), (ctypes.c_void_p * 5)(*ptr[17:22]), ptr[22], ptr[23])
             g_flat = d_enc_a.float().contiguous().view(-1)
             lib().call("b2n_audio_backward", ctypes.byref(aw), auds.data_ptr(), auds.shape[2], g_flat.data_ptr(), ctypes.byref(gs), side.cuda_stream)
-            flat.record_stream(cur)                            # consumed on the main stream after the join
+            if flat is not None:
+                flat.record_stream(cur)                        # consumed on the main stream after the join
+            g_flat.record_stream(side)
     # table gradients: d enc_x is already in the grid backward's [plane][level][sample] layout; the three planes (xy, yz, xz:
     # network.py:208-212) go through one launch that takes its plane coordinates straight from xyz
     enc = m.encoder_xy
     S, H = float(math.log2(enc.per_level_scale)), enc.base_resolution
-    d_tabs = [torch.zeros_like(e_mod.embeddings) for e_mod in (m.encoder_xy, m.encoder_yz, m.encoder_xz)]
+    if direct:                                                 # accumulate (red.global) into the tables' .grad
+        d_tabs = [e_mod.embeddings.grad for e_mod in (m.encoder_xy, m.encoder_yz, m.encoder_xz)]
+    else:
+        d_tabs = [torch.zeros_like(e_mod.embeddings) for e_mod in (m.encoder_xy, m.encoder_yz, m.encoder_xz)]
     lib().call("b2n_triplane_grid_backward", planes.data_ptr(), x.data_ptr(), enc.offsets.data_ptr(), d_tabs[0].data_ptr(), d_tabs[1].data_ptr(),
                d_tabs[2].data_ptr(), M, 12, S, H, float(m.bound), torch.cuda.current_stream().cuda_stream)
+    if direct:
+        d_tabs = [None, None, None]
     if side is not None:
         torch.cuda.current_stream(dev).wait_stream(side)      # join before anybody reads the audio gradients
     c = lambda t: None if t is None else t.contiguous()

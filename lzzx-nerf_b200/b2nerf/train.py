@@ -38,6 +38,8 @@ class Trainer:
             self.opt.attach_grads(self.grads.flat)
             if getattr(model, "_handle", None) is not None:
                 model.pack()                              # the parameter storage moved: refresh the pointers baked into the packed model
+        # the fused backward accumulates every gradient straight into these .grad views (fused_train._direct_targets): no per-parameter add kernels
+        model._direct_grads = bool(fused_head and enc[0].is_cuda)
         self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
         self.local_step = 0
         self.mean_count = 0

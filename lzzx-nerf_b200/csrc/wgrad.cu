@@ -503,3 +503,41 @@ extern "C" int b2n_linear_wgrad_batch(const b2n_wgrad_job *jobs, uint32_t n_jobs
     k_linear_wgrad_multi<<<g, WM_THREADS, WM_SMEM, as_stream(stream)>>>(J);
     return check_launch("linear_wgrad_batch");
 }
+
+// ---- finishing pass of the replicated weight gradients: sum the replicas and ACCUMULATE rectangular blocks straight into the parameters' .grad
+// storage (row rotations / column slices of the padded products are expressed as blocks), so no slicing / cat / add kernels follow a backward.
+namespace b2n {
+struct ScatterJobs { b2n_wgrad_block j[32]; uint32_t n, replicas, rstride; };
+__global__ void __launch_bounds__(256) k_wgrad_scatter(const __grid_constant__ ScatterJobs J, const float *__restrict__ src) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t k = 0; k < J.n; k++) {
+        const b2n_wgrad_block &q = J.j[k];
+        const uint32_t n = q.rows * q.cols;
+        if (e < n) {
+            const uint32_t i = e / q.cols, c = e - i * q.cols;
+            const float *p = src + q.src_off + (size_t)i * q.src_ld + c;
+            float a = 0.0f;
+            for (uint32_t r = 0; r < J.replicas; r++) a += __ldg(p + (size_t)r * J.rstride);
+            q.dst[(size_t)i * q.dst_ld + c] += a;
+            return;
+        }
+        e -= n;
+    }
+}
+}  // namespace b2n
+
+extern "C" int b2n_wgrad_scatter(const float *src, uint32_t replicas, uint32_t replica_stride, const b2n_wgrad_block *blocks, uint32_t n_blocks, void *stream) {
+    B2N_REQUIRE(src && blocks, "wgrad_scatter: null pointer");
+    B2N_REQUIRE(n_blocks >= 1 && n_blocks <= 32, "wgrad_scatter: 1..32 blocks");
+    B2N_REQUIRE(replicas >= 1 && replicas <= 64, "wgrad_scatter: replicas=%u out of range (1..64)", replicas);
+    ScatterJobs J = {};
+    J.n = n_blocks; J.replicas = replicas; J.rstride = replica_stride;
+    uint32_t total = 0;
+    for (uint32_t i = 0; i < n_blocks; i++) {
+        B2N_REQUIRE(blocks[i].dst && blocks[i].cols >= 1 && blocks[i].rows >= 1, "wgrad_scatter: block %u is empty", i);
+        J.j[i] = blocks[i];
+        total += blocks[i].rows * blocks[i].cols;
+    }
+    k_wgrad_scatter<<<ceil_div<uint32_t>(total, 256), 256, 0, as_stream(stream)>>>(J, src);
+    return check_launch("wgrad_scatter");
+}

@@ -345,3 +345,46 @@ def test_combined_head_audio_node_equals_separate_nodes():
             continue
         scale = float(q.grad.abs().max()) + 1e-20
         assert float((p.grad - q.grad).abs().max()) <= 1e-4 * scale, (n, float((p.grad - q.grad).abs().max()) / scale)      # atomics order only
+
+
+def test_direct_gradient_accumulation_equals_autograd_outputs():
+    """Trainer mode (model._direct_grads): the fused backward accumulates every product straight into the parameters' .grad views through ONE
+    b2n_wgrad_scatter launch (tables and audio nets by red.global into .grad) — same numbers as returning the gradients through autograd.
+    Also checks that it really accumulates (pre-filled .grad)."""
+    import copy
+    from b2nerf.model import HeadModel
+    from b2nerf.dist import FlatGradBuffer
+    from b2nerf.fused_train import fused_head_audio_train
+    torch.manual_seed(11)
+    m = HeadModel(audio_in_dim=29).cuda()
+    for enc in (m.encoder_xy, m.encoder_yz, m.encoder_xz):
+        enc.embeddings.data.uniform_(-0.5, 0.5)
+    m.testing = False
+    m2 = copy.deepcopy(m)
+    M = 30000 + 11
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = (torch.rand(M, 3, device="cuda", generator=g) * 2 - 1) * torch.tensor([1.0, 0.5, 1.0], device="cuda")
+    d = torch.nn.functional.normalize(torch.randn(M, 3, device="cuda", generator=g), dim=1)
+    auds = torch.randn(8, 29, 16, device="cuda", generator=g)
+    eye = torch.tensor([[0.4]], device="cuda")
+    ups = [torch.randn(M, device="cuda", generator=g) * 0.1, torch.randn(M, 3, device="cuda", generator=g), torch.randn(M, 1, device="cuda", generator=g) * 0.1,
+           torch.randn(M, 1, device="cuda", generator=g) * 0.1, torch.randn(M, 1, 1, device="cuda", generator=g) * 0.1]
+    flats = []
+    for model, direct in ((m, True), (m2, False)):
+        fb = FlatGradBuffer(list(model.parameters()))
+        fb.flat.fill_(0.25)                                   # accumulate, do not overwrite
+        model._direct_grads = direct
+        model.pack()
+        with torch.autocast("cuda", dtype=torch.float16):
+            outs = fused_head_audio_train(model, x, d, auds, model.individual_codes[3], eye)
+            loss = sum((o.float() * u).sum() for o, u in zip(outs, ups))
+        loss.backward()
+        torch.cuda.synchronize()
+        fb.check_attached()
+        flats.append(fb.flat.clone())
+    a, b = flats
+    assert float((b - 0.25).abs().max()) > 1e-3
+    # identical kernels produce the products; only the accumulation order of the fp32 sums differs (replica sum + 0.25 vs 0.25 + replica sum,
+    # atomics order in the tables / audio nets)
+    tol = 2e-5 * float((b - 0.25).abs().max()) + 1e-6
+    assert float((a - b).abs().max()) <= tol, (float((a - b).abs().max()), tol)
