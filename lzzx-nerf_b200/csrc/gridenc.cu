@@ -418,6 +418,142 @@ __global__ void __launch_bounds__(GP_THREADS) k_triplane_bwd_priv(const float *_
     }
 }
 
+// Same job with FIXED-POINT privatisation.  Shared memory has a native atomic add only for 32-bit integers (ATOMS.ADD); a float atomicAdd there is a
+// compare-and-swap loop (LDS + FADD + ATOMS.CAST.SPIN, retried under contention — short_scoreboard 4.6 stalls per issue in the float kernel above).
+// So every contribution t = w * g is converted to a fixed-point integer V = rint(t * 2^(K - e)), 2^e > the largest |g| of the CTA's slice (found by
+// a first pass over the slice), and added as two fire-and-forget integer atomics, V = hi * 2^lo_bits + lo with |lo| <= 2^(lo_bits - 1) (one atomic when hi == 0).  With at
+// most n_max = 4 * slice contributions per slot, lo_bits = 32 - ceil(log2 n_max) and K = min(62 - 2 ceil(log2 n_max), 30) keep both sums inside 32 bits
+// (K = 26 for the 65 536-ray step: every contribution is kept to 2^-26 of the slice's largest gradient, the sums are exact — and so independent of
+// the order of the atomics — where fp32 accumulation rounds each add to 2^-24 of the running sum).  A non-finite gradient poisons the level (NaN),
+// so the GradScaler's overflow check still sees it.
+constexpr uint32_t GF_THREADS = 1024;
+__global__ void __launch_bounds__(GF_THREADS, 1) k_triplane_bwd_fix(const float *__restrict__ grad, const float *__restrict__ xyz, const int32_t *__restrict__ offsets,
+                                                                     float *__restrict__ gt_xy, float *__restrict__ gt_yz, float *__restrict__ gt_xz, uint32_t M,
+                                                                     uint32_t L, uint32_t S_slices, float S, uint32_t H, float bound, float inv_two_bound,
+                                                                     uint32_t smem_entries, int K, uint32_t lo_bits) {
+    extern __shared__ __align__(16) int2 s_acc[];          // .x = hi sum, .y = lo sum (both signed)
+    __shared__ float s_red[GF_THREADS / 32];
+    __shared__ int s_bad;
+    const uint32_t level = blockIdx.y, plane = blockIdx.z;
+    const LevelGeom g = level_geom(offsets, level, S, H);
+    float *gtab = (plane == 0 ? gt_xy : (plane == 1 ? gt_yz : gt_xz)) + g.table_off;
+    const uint32_t ca = plane == 1 ? 1u : 0u, cb = plane == 0 ? 1u : 2u;          // xy = (0,1), yz = (1,2), xz = (0,2)
+    const uint32_t n = g.hashmap_size;
+    // slot of corner (i, j) = grid_slot<2>() with the level's kind resolved once (it is uniform over the CTA): dense levels index i + j * (res + 1)
+    // (always < n: no modulo), hashed levels (i ^ j * 2654435761) mod n — a mask when n is a power of two (grid.py:117 rounds hashed levels to 2^k);
+    // the generic `% n` costs ~25 instructions per corner
+    const uint32_t row_stride = g.resolution + 1u;
+    const bool dense = row_stride <= n && (uint64_t)row_stride * row_stride <= n, pow2 = (n & (n - 1u)) == 0u;
+    const bool generic = !dense && !pow2;
+    const uint32_t jmul_h = dense ? 0u : 2654435761u, mask_h = dense ? 0xffffffffu : n - 1u, jmul_d = dense ? row_stride : 0u;
+    auto slot_of = [&](uint32_t i, uint32_t j) -> uint32_t {
+        if (generic) return (i ^ (j * 2654435761u)) % n;
+        return ((i ^ (j * jmul_h)) & mask_h) + j * jmul_d;              // branch-free for the two kinds the reference geometry has
+    };
+    const float *gl = grad + ((size_t)plane * L + level) * M;
+    const uint32_t per = (M + S_slices - 1) / S_slices;
+    const uint32_t b0 = blockIdx.x * per, b1 = min(M, b0 + per);
+    if (n > smem_entries) {                                 // level too large to privatise: scatter straight to global memory
+        for (uint32_t b = b0 + threadIdx.x; b < b1; b += GF_THREADS) {
+            const float pa = __ldg(xyz + 3 * (size_t)b + ca), pb = __ldg(xyz + 3 * (size_t)b + cb);
+            const float u0 = inv_two_bound != 0.0f ? __fmul_rn(__fadd_rn(pa, bound), inv_two_bound) : __fdiv_rn(__fadd_rn(pa, bound), __fmul_rn(2.0f, bound));
+            const float u1 = inv_two_bound != 0.0f ? __fmul_rn(__fadd_rn(pb, bound), inv_two_bound) : __fdiv_rn(__fadd_rn(pb, bound), __fmul_rn(2.0f, bound));
+            if (u0 < 0.0f || u0 > 1.0f || u1 < 0.0f || u1 > 1.0f) continue;
+            const float gc = __ldcs(gl + b);
+            float p0 = __fmaf_rn(u0, g.scale, 0.5f), p1 = __fmaf_rn(u1, g.scale, 0.5f);
+            const uint32_t i0 = (uint32_t)floorf(p0), i1 = (uint32_t)floorf(p1);
+            p0 = __fsub_rn(p0, (float)i0); p1 = __fsub_rn(p1, (float)i1);
+#pragma unroll
+            for (uint32_t idx = 0; idx < 4; idx++) {
+                const float wx = (idx & 1u) ? p0 : __fsub_rn(1.0f, p0), wy = (idx & 2u) ? p1 : __fsub_rn(1.0f, p1);
+                red_add_f32(gtab + slot_of(i0 + (idx & 1u), i1 + ((idx >> 1) & 1u)), __fmul_rn(__fmul_rn(wx, wy), gc));
+            }
+        }
+        return;
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += GF_THREADS) s_acc[i] = make_int2(0, 0);
+    if (threadIdx.x == 0) s_bad = 0;
+    // ---- pass 1: the largest |g| of the slice (ordinary loads: the second pass finds the values in L1 / L2)
+    float gmax = 0.0f;
+    bool bad = false;
+    for (uint32_t b = b0 + threadIdx.x; b < b1; b += GF_THREADS) {
+        const float v = fabsf(__ldg(gl + b));
+        bad |= !(v <= 3.0e38f);                             // inf or nan
+        gmax = fmaxf(gmax, v);
+    }
+#pragma unroll
+    for (uint32_t o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    if ((threadIdx.x & 31u) == 0) s_red[threadIdx.x >> 5] = gmax;
+    __syncthreads();
+    if (bad) s_bad = 1;
+    gmax = s_red[0];
+#pragma unroll
+    for (uint32_t w = 1; w < GF_THREADS / 32; w++) gmax = fmaxf(gmax, s_red[w]);
+    __syncthreads();
+    if (s_bad) {                                           // uniform
+        if (threadIdx.x == 0) red_add_f32(gtab, __int_as_float(0x7fc00000));
+        return;
+    }
+    if (gmax == 0.0f) return;                               // uniform: nothing to add
+    int e;
+    (void)frexpf(gmax, &e);                                 // gmax < 2^e
+    e = max(e, -100);
+    const float to_fix = ldexpf(1.0f, K - e);
+    const int lo_half = 1 << (lo_bits - 1u);
+    // ---- pass 2: fixed-point scatter
+    constexpr uint32_t U = 4;
+    for (uint32_t bb = b0 + threadIdx.x; bb < b1; bb += U * GF_THREADS) {
+        float in[U][2], gc[U];
+#pragma unroll
+        for (uint32_t u = 0; u < U; u++) {
+            const uint32_t b = bb + u * GF_THREADS;
+            if (b < b1) {
+                const float pa = __ldg(xyz + 3 * (size_t)b + ca), pb = __ldg(xyz + 3 * (size_t)b + cb);
+                in[u][0] = inv_two_bound != 0.0f ? __fmul_rn(__fadd_rn(pa, bound), inv_two_bound) : __fdiv_rn(__fadd_rn(pa, bound), __fmul_rn(2.0f, bound));
+                in[u][1] = inv_two_bound != 0.0f ? __fmul_rn(__fadd_rn(pb, bound), inv_two_bound) : __fdiv_rn(__fadd_rn(pb, bound), __fmul_rn(2.0f, bound));
+                gc[u] = __ldg(gl + b);
+            } else { in[u][0] = -1.0f; in[u][1] = -1.0f; gc[u] = 0.0f; }
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < U; u++) {
+            if (in[u][0] < 0.0f || in[u][0] > 1.0f || in[u][1] < 0.0f || in[u][1] > 1.0f || gc[u] == 0.0f) continue;
+            float pos[2];
+            uint32_t pg[2];
+#pragma unroll
+            for (uint32_t d = 0; d < 2; d++) {
+                pos[d] = __fmaf_rn(in[u][d], g.scale, 0.5f);
+                pg[d] = (uint32_t)floorf(pos[d]);
+                pos[d] = __fsub_rn(pos[d], (float)pg[d]);
+            }
+#pragma unroll
+            for (uint32_t idx = 0; idx < 4; idx++) {
+                const float wx = (idx & 1u) ? pos[0] : __fsub_rn(1.0f, pos[0]), wy = (idx & 2u) ? pos[1] : __fsub_rn(1.0f, pos[1]);
+                const uint32_t slot = slot_of(pg[0] + (idx & 1u), pg[1] + ((idx >> 1) & 1u));
+                const int V = __float2int_rn(__fmul_rn(__fmul_rn(__fmul_rn(wx, wy), gc[u]), to_fix));
+                if (V != 0) {
+                    // V = hi * 2^lo_bits + lo with a SIGNED lo in [-2^(lo_bits-1), 2^(lo_bits-1)): small contributions of either sign have hi == 0
+                    // and cost one atomic
+                    const int hi = (V + lo_half) >> lo_bits, lo = V - (hi << lo_bits);
+                    if (hi != 0) atomicAdd(&s_acc[slot].x, hi);
+                    atomicAdd(&s_acc[slot].y, lo);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const float from_fix = ldexpf(1.0f, e - K);
+    auto value = [&](int2 a) { return __fmul_rn(__ll2float_rn(((long long)a.x << lo_bits) + (long long)a.y), from_fix); };
+    if ((g.table_off & 3u) == 0 && (n & 3u) == 0 && ((uintptr_t)gtab & 15u) == 0) {
+        for (uint32_t i = threadIdx.x; i < n / 4; i += GF_THREADS) {
+            const int4 q0 = reinterpret_cast<const int4 *>(s_acc)[2 * i], q1 = reinterpret_cast<const int4 *>(s_acc)[2 * i + 1];
+            const float4 v = make_float4(value(make_int2(q0.x, q0.y)), value(make_int2(q0.z, q0.w)), value(make_int2(q1.x, q1.y)), value(make_int2(q1.z, q1.w)));
+            if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) red_add_v4_f32(gtab + 4 * (size_t)i, v);
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < n; i += GF_THREADS) { const float v = value(s_acc[i]); if (v != 0.0f) red_add_f32(gtab + i, v); }
+    }
+}
+
 // largest level (entries) of the grid described by a device `offsets` array — read back ONCE per (pointer, L) and cached; 0 = unknown (the
 // stream is being captured and the geometry has not been seen yet).  The value only sizes the privatised kernel's shared memory: the kernel
 // re-checks every level against it, so a stale entry costs speed, never correctness.
@@ -573,6 +709,29 @@ int b2n_triplane_grid_backward(const float *grad_planes, const float *xyz, const
     if (M == 0) return 0;
     cudaStream_t st = as_stream(stream);
     uint32_t mx = largest_level_entries(offsets, L, st);
+    int ex = 0;
+    const float two_b = 2.0f * bound;
+    const float inv = frexpf(two_b, &ex) == 0.5f ? 1.0f / two_b : 0.0f;
+    static const bool fixed_point = !(getenv("B2N_GRID_BWD_FIXED") && getenv("B2N_GRID_BWD_FIXED")[0] == '0');
+    if (fixed_point && mx != 0 && (size_t)mx * sizeof(int2) <= 200 * 1024) {
+        // fixed-point privatisation: 8 bytes per slot, one 1024-thread CTA per SM
+        const size_t smem = sizeof(int2) * (size_t)mx;
+        static size_t smem_set = 0;
+        if (smem > 32 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(k_triplane_bwd_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+        uint32_t slices = 2u * (uint32_t)sm_count() / (3u * L);        // two waves of (slice, level, plane) CTAs
+        if (const char *e = getenv("B2N_GRID_BWD_SLICES")) slices = (uint32_t)atoi(e);
+        const uint32_t cap = ceil_div<uint32_t>(M, 4096);
+        if (slices > cap) slices = cap;
+        if (slices < 1) slices = 1;
+        const uint32_t per = ceil_div<uint32_t>(M, slices);
+        uint32_t nbits = 1;
+        while (nbits < 31 && (1ull << nbits) < 4ull * per) nbits++;       // at most 4 contributions per sample and slot
+        B2N_REQUIRE(nbits <= 24, "triplane_grid_backward: M=%u too large for the fixed-point kernel", M);
+        const int K = min(62 - 2 * (int)nbits, 30);                        // V = rint(t * 2^(K - e)) must also fit an int32
+        k_triplane_bwd_fix<<<dim3(slices, L, 3), GF_THREADS, smem, st>>>(grad_planes, xyz, offsets, grad_xy, grad_yz, grad_xz, M, L, slices, S, H, bound, inv, mx, K,
+                                                                           32u - nbits);
+        return check_launch("triplane_grid_backward");
+    }
     uint32_t fl = (mx != 0 && (size_t)mx * sizeof(float) <= 160 * 1024) ? mx : 0;       // 0: every level scatters straight to global memory
     const size_t smem = sizeof(float) * (size_t)fl;
     static size_t smem_set = 0;
@@ -582,9 +741,6 @@ int b2n_triplane_grid_backward(const float *grad_planes, const float *xyz, const
     const uint32_t cap = ceil_div<uint32_t>(M, 2048);
     if (slices > cap) slices = cap;
     if (slices < 1) slices = 1;
-    int ex = 0;
-    const float two_b = 2.0f * bound;
-    const float inv = frexpf(two_b, &ex) == 0.5f ? 1.0f / two_b : 0.0f;
     k_triplane_bwd_priv<<<dim3(slices, L, 3), GP_THREADS, smem, st>>>(grad_planes, xyz, offsets, grad_xy, grad_yz, grad_xz, M, L, slices, S, H, bound, inv, fl);
     return check_launch("triplane_grid_backward");
 }

@@ -192,7 +192,14 @@ __global__ void __launch_bounds__(WG_THREADS, 3) k_linear_wgrad(const __half *__
 // One CTA per SM, a ring of WP_STAGES operand stages filled with cp.async (16-byte asynchronous copies, zero-fill past the last row): the
 // copies of chunks c+1 .. c+3 are in flight while chunk c is multiplied, so the per-chunk global-load latency that bounds the simple kernel
 // (one chunk per CTA in flight, ~2 us per chunk) is hidden.
-constexpr uint32_t WP_STAGES = 4;
+#ifndef WP_STAGES_N
+#define WP_STAGES_N 4
+#endif
+constexpr uint32_t WP_STAGES = WP_STAGES_N;
+#ifndef WP_AHEAD_N
+#define WP_AHEAD_N (WP_STAGES_N - 1)
+#endif
+constexpr uint32_t WP_AHEAD = WP_AHEAD_N;                              // chunks in flight ahead of the one being multiplied
 constexpr uint32_t WP_STAGE_BYTES = 2 * WG_OPERAND_BYTES;                 // A (<= 128 features) + B (<= 128 features) of one 64-sample chunk
 constexpr uint32_t WP_SMEM = WP_STAGES * WP_STAGE_BYTES + 1024 + 128;
 
@@ -213,13 +220,14 @@ __device__ __forceinline__ RowMap row_map(uint32_t width) {
     r.rstep = WG_THREADS >> lg;
     return r;
 }
-__device__ __forceinline__ void issue_operand(uint32_t s_base, const __half *__restrict__ src, const RowMap &r, uint32_t row0, uint32_t M, uint32_t width) {
+__device__ __forceinline__ void issue_operand(uint32_t s_base, const __half *__restrict__ src, const RowMap &r, uint32_t row0, uint32_t M, uint32_t width,
+                                              uint32_t chunk = WG_CHUNK) {
     if (r.col >= r.nv) return;
     const uint32_t j = r.col * 8u;
 #pragma unroll
-    for (uint32_t u = 0; u < 4; u++) {                                    // <= 4 rows per thread (width <= 128)
+    for (uint32_t u = 0; u < 4; u++) {                                    // <= 4 rows per thread (width <= 128 with 64-row chunks, <= 64 with 128-row chunks)
         const uint32_t k = r.r0 + u * r.rstep;
-        if (k < WG_CHUNK) {
+        if (k < chunk) {
             const uint32_t row = row0 + k;
             const bool ok = row < M;
             cp_async16(s_base + mn_offset(k, j), src + (size_t)(ok ? row : 0) * width + j, ok);
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(WP_THREADS, 1) k_linear_wgrad_pipe(const __hal
     const uint32_t tmem = *tmem_slot;
     const uint32_t base_a = smem_u32(base);
     const uint32_t my_n = blockIdx.x < n_chunks ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    constexpr uint32_t AHEAD = WP_STAGES - 1;                             // chunks in flight per producer
+    constexpr uint32_t AHEAD = WP_AHEAD;                             // chunks in flight per producer
     if (producer) {
         const RowMap ra = row_map(out_dim), rb = row_map(in_dim);
         auto issue = [&](uint32_t i) {                                    // chunk i of this CTA -> stage i % WP_STAGES
@@ -351,18 +359,61 @@ __global__ void __launch_bounds__(WM_THREADS, 1) k_linear_wgrad_multi(const __gr
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const uint32_t base_a = smem_u32(base);
-    const uint32_t my_n = blockIdx.x < n_chunks ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;      // chunks per job for this CTA
-    const uint32_t total = my_n * J.n;
-    constexpr uint32_t AHEAD = WP_STAGES - 1;
+    // Chunk length per job: a stage holds 64 samples of up to 128 features per operand, or — when both operands are at most 64 features wide (one
+    // 128-byte row per sample) — 128 samples in the same 16 KB.  The stream is bound by (load latency / chunks in flight) per chunk, whatever the
+    // chunk's size, so the narrow jobs (10 of the 13 products of a step) take half as many ring trips.
+    auto chunk_of = [&](uint32_t job) { return (J.j[job].out_dim <= 64u && J.j[job].in_dim <= 64u) ? 2u * WG_CHUNK : WG_CHUNK; };
+    auto my_chunks = [&](uint32_t job) {                                  // chunks of this job walked by this CTA: blockIdx.x, + gridDim.x, ...
+        const uint32_t nc = (J.M + chunk_of(job) - 1) / chunk_of(job);
+        return blockIdx.x < nc ? (nc - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    };
+    uint32_t total = 0;
+    for (uint32_t job = 0; job < J.n; job++) total += my_chunks(job);
+    (void)n_chunks;
+    constexpr uint32_t AHEAD = WP_AHEAD;
     // stale bytes of a wider previous job may sit beyond a job's operand widths: harmless, D[o, i] only depends on column o of A and column i of B,
     // and the epilogue writes o < out_dim, i < in_dim only
     if (tid < WG_THREADS) {
+        // Everything about a thread's copies that does not change from chunk to chunk of a job — which rows / 16-byte column it owns, their swizzled
+        // shared-memory offsets, their element offsets inside a chunk — is computed when the issue cursor enters the job; a chunk then costs one
+        // multiply-add and one compare per cp.async (the per-chunk index arithmetic was what bound this kernel: ~260 instructions per warp and chunk).
+        struct Side { const __half *src; uint32_t width, k[4], soff[4], goff[4]; };
+        Side A, B;
+        uint32_t pj = 0, pi = 0, pn = 0, ch = WG_CHUNK;                    // cursor of the next chunk to issue
+        auto setup_side = [&](Side &sd, const void *ptr, uint32_t width) {
+            const RowMap r = row_map(width);
+            sd.src = reinterpret_cast<const __half *>(ptr); sd.width = width;
+            const uint32_t j = r.col * 8u;
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++) {
+                const uint32_t k = r.r0 + u * r.rstep;
+                const bool act = r.col < r.nv && k < ch;
+                sd.k[u] = act ? k : 0xffffffffu;
+                sd.soff[u] = act ? mn_offset(k, j) : 0u;
+                sd.goff[u] = k * width + j;
+            }
+        };
+        auto setup_job = [&]() {
+            ch = chunk_of(pj); pn = my_chunks(pj);
+            setup_side(A, J.j[pj].dy, J.j[pj].out_dim);
+            setup_side(B, J.j[pj].x, J.j[pj].in_dim);
+        };
+        auto issue_side = [&](const Side &sd, uint32_t st, uint32_t row0) {
+            const __half *p0 = sd.src + (size_t)row0 * sd.width;
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++)
+                if (sd.k[u] != 0xffffffffu) {
+                    const bool ok = row0 + sd.k[u] < J.M;
+                    cp_async16(st + sd.soff[u], ok ? p0 + sd.goff[u] : sd.src, ok);
+                }
+        };
+        setup_job();
         auto issue = [&](uint32_t g) {
-            const uint32_t job = g / my_n, i = g - job * my_n;
-            const b2n_wgrad_job &q = J.j[job];
-            const uint32_t st = base_a + (g % WP_STAGES) * WP_STAGE_BYTES, row0 = (blockIdx.x + i * gridDim.x) * WG_CHUNK;
-            issue_operand(st, reinterpret_cast<const __half *>(q.dy), row_map(q.out_dim), row0, J.M, q.out_dim);
-            issue_operand(st + WG_OPERAND_BYTES, reinterpret_cast<const __half *>(q.x), row_map(q.in_dim), row0, J.M, q.in_dim);
+            while (pi >= pn) { pj++; pi = 0; setup_job(); }
+            const uint32_t st = base_a + (g % WP_STAGES) * WP_STAGE_BYTES, row0 = (blockIdx.x + pi * gridDim.x) * ch;
+            issue_side(A, st, row0);
+            issue_side(B, st + WG_OPERAND_BYTES, row0);
+            pi++;
         };
         for (uint32_t g = 0; g < AHEAD; g++) { if (g < total) issue(g); cp_async_commit(); }
         for (uint32_t g = 0; g < total; g++) {
@@ -381,6 +432,7 @@ __global__ void __launch_bounds__(WM_THREADS, 1) k_linear_wgrad_multi(const __gr
         for (uint32_t job = 0; job < J.n; job++) {
             const uint32_t a = job & 1u, n_pad = (J.j[job].in_dim + 15u) & ~15u;
             const uint32_t idesc = idesc_f16(128, n_pad) | (1u << 15) | (1u << 16);
+            const uint32_t my_n = my_chunks(job), ksteps = chunk_of(job) / 16u;
             if (job >= 2) { mbar_wait(&acc_free[a], ((job >> 1) - 1u) & 1u); fence_after_sync(); }      // the epilogue of job - 2 has drained this accumulator
             for (uint32_t i = 0; i < my_n; i++, g++) {
                 const uint32_t s = g % WP_STAGES;
@@ -388,12 +440,12 @@ __global__ void __launch_bounds__(WM_THREADS, 1) k_linear_wgrad_multi(const __gr
                 fence_after_sync();
                 uint64_t da = smem_desc_mn_sw128(base_a + s * WP_STAGE_BYTES), db = smem_desc_mn_sw128(base_a + s * WP_STAGE_BYTES + WG_OPERAND_BYTES);
 #pragma unroll 1
-                for (uint32_t k = 0; k < WG_CHUNK / 16; k++, da += 2048u >> 4, db += 2048u >> 4) mma_f16_ss(tmem + a * 128u, da, db, idesc, i > 0 || k > 0);
+                for (uint32_t k = 0; k < ksteps; k++, da += 2048u >> 4, db += 2048u >> 4) mma_f16_ss(tmem + a * 128u, da, db, idesc, i > 0 || k > 0);
                 mma_commit(&empty[s]);
             }
             mma_commit(&acc_full[a]);                                     // arrives when every MMA of this job has completed
         }
-    } else if (tid >= WG_THREADS + 32 && my_n > 0) {                      // epilogue warps: TMEM lane quarter = warp & 3
+    } else if (tid >= WG_THREADS + 32) {                                  // epilogue warps: TMEM lane quarter = warp & 3
         const uint32_t o = (warp & 3u) * 32u + (tid & 31u);
         for (uint32_t job = 0; job < J.n; job++) {
             const uint32_t a = job & 1u;
@@ -401,10 +453,11 @@ __global__ void __launch_bounds__(WM_THREADS, 1) k_linear_wgrad_multi(const __gr
             const uint32_t n_pad = (q.in_dim + 15u) & ~15u;
             float *dw = q.dw + (size_t)(blockIdx.x % J.replicas) * J.rstride;
             const bool vec4 = (q.in_dim & 3u) == 0 && ((uintptr_t)dw & 15u) == 0;
+            const bool any = my_chunks(job) > 0;                          // no chunk of this job here: the accumulator holds nothing (keep the handshake)
             mbar_wait(&acc_full[a], (job >> 1) & 1u);
             fence_after_sync();
             const uint32_t taddr = tmem + a * 128u + (((warp & 3u) * 32u) << 16);
-            for (uint32_t cb = 0; cb < n_pad; cb += 16) {
+            for (uint32_t cb = 0; any && cb < n_pad; cb += 16) {
                 uint32_t acc[16];
                 ld16(taddr + cb, acc);
                 wait_ld();

@@ -388,3 +388,71 @@ def test_direct_gradient_accumulation_equals_autograd_outputs():
     # atomics order in the tables / audio nets)
     tol = 2e-5 * float((b - 0.25).abs().max()) + 1e-6
     assert float((a - b).abs().max()) <= tol, (float((a - b).abs().max()), tol)
+
+
+def test_triplane_grid_backward_fixed_point_vs_float64():
+    """b2n_triplane_grid_backward (fixed-point shared-memory privatisation, csrc/gridenc.cu:k_triplane_bwd_fix) against the scatter restated in torch
+    with float64 accumulation: index rule of gridencoder.cu:54-72 (D = 2: dense levels i + j * (res + 1), hashed levels (i ^ j * 2654435761) mod
+    size), weights / products formed in fp32 exactly like the kernel.  Gradients span 5 decades; tolerance 1e-5 of each level's largest entry
+    (the fixed-point sums are exact to 2^-26 of the largest gradient of a slice; fp32 atomics would be ~1e-4 here).  A non-finite gradient must
+    poison its table (GradScaler overflow detection)."""
+    import math
+    from b2nerf import lib
+    from b2nerf.model import HeadModel
+    from gridencoder.backend import grid_level_scales
+    torch.manual_seed(4)
+    m = HeadModel().cuda()
+    enc = m.encoder_xy
+    S, H, L = float(math.log2(enc.per_level_scale)), enc.base_resolution, 12
+    offs = enc.offsets.cpu().tolist()
+    M = 150003
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xyz = torch.randn(M, 3, device="cuda", generator=g) * 0.25           # clustered: heavy collisions on the coarse levels
+    xyz[:64] = torch.rand(64, 3, device="cuda", generator=g) * 2.4 - 1.2   # some out of range
+    xyz[64] = torch.tensor([1.0, 1.0, 1.0]); xyz[65] = torch.tensor([-1.0, -1.0, -1.0])
+    xyz = xyz.contiguous()
+    mag = 10.0 ** (torch.rand(3, L, M, device="cuda", generator=g) * 5 - 4)
+    grad = (torch.randn(3, L, M, device="cuda", generator=g) * mag).contiguous()
+    grad[:, :, 100:200] = 0.0
+    tabs = [torch.zeros(offs[-1], 1, device="cuda") for _ in range(3)]
+    st = torch.cuda.current_stream().cuda_stream
+    lib().call("b2n_triplane_grid_backward", grad.data_ptr(), xyz.data_ptr(), enc.offsets.data_ptr(), tabs[0].data_ptr(), tabs[1].data_ptr(), tabs[2].data_ptr(),
+               M, L, S, H, 1.0, st)
+    scales = grid_level_scales(S, H, L)
+    u = (xyz + 1.0) * 0.5                                                  # exact in fp32 for bound = 1
+    planes = ((0, 1), (1, 2), (0, 2))
+    for p, (ca, cb) in enumerate(planes):
+        ref = torch.zeros(offs[-1], dtype=torch.float64, device="cuda")
+        ok = (u[:, ca] >= 0) & (u[:, ca] <= 1) & (u[:, cb] >= 0) & (u[:, cb] <= 1)
+        for l in range(L):
+            sc = scales[l]
+            size = offs[l + 1] - offs[l]
+            res = int(math.ceil(float(sc))) + 1
+            stride = res + 1
+            dense = stride * stride <= size
+            pa = (u[:, ca].double() * sc.double() + 0.5).float(); pb = (u[:, cb].double() * sc.double() + 0.5).float()     # == fmaf in fp32
+            ia, ib = pa.floor(), pb.floor()
+            fa, fb = pa - ia, pb - ib
+            ia, ib = ia.long(), ib.long()
+            for k in range(4):
+                wa = fa if (k & 1) else (1.0 - fa); wb = fb if (k & 2) else (1.0 - fb)
+                ja, jb = ia + (k & 1), ib + ((k >> 1) & 1)
+                if dense:
+                    slot = ja + jb * stride
+                else:
+                    slot = (ja ^ ((jb * 2654435761) & 0xFFFFFFFF)) % size
+                t = ((wa * wb) * grad[p, l]).double()
+                ref.index_add_(0, (slot + offs[l])[ok], t[ok])
+        got = tabs[p].view(-1).double()
+        for l in range(L):
+            a, b = got[offs[l]:offs[l + 1]], ref[offs[l]:offs[l + 1]]
+            tol = 1e-5 * float(b.abs().max())
+            assert float((a - b).abs().max()) <= tol, (p, l, float((a - b).abs().max()), tol)
+    # overflow: an inf in one (plane, level) slab must reach that level's gradient as a non-finite value
+    grad[1, 7, 5000] = float("inf")
+    tabs = [torch.zeros(offs[-1], 1, device="cuda") for _ in range(3)]
+    lib().call("b2n_triplane_grid_backward", grad.data_ptr(), xyz.data_ptr(), enc.offsets.data_ptr(), tabs[0].data_ptr(), tabs[1].data_ptr(), tabs[2].data_ptr(),
+               M, L, S, H, 1.0, st)
+    torch.cuda.synchronize()
+    assert not bool(torch.isfinite(tabs[1][offs[7]:offs[8]]).all())
+    assert bool(torch.isfinite(tabs[0]).all()) and bool(torch.isfinite(tabs[2]).all())
