@@ -71,8 +71,13 @@ class Trainer:
                 sigmas, rgbs, amb_aud, amb_eye, unc = fused_head_train(m, xyzs, dirs, enc_a, ind_code, eye)
         else:
             sigmas, rgbs, amb_aud, amb_eye, unc = m.forward_unfused(xyzs, dirs, enc_a, ind_code, eye)
-        ws, aud_sum, eye_sum, unc_sum, depth, image = raymarching.composite_rays_train_triplane(
-            sigmas, rgbs, amb_aud.abs().sum(-1), amb_eye.abs().sum(-1), unc, deltas, rays)
+        if self.fused_head:
+            # ambient.abs().sum(-1) (renderer.py:294-295) over a trailing dimension of 1 of values that are >= 0 by construction (an L2 norm and a
+            # sigmoid): the identity, forward and backward — skip the eight abs / sum / sign / mul kernels
+            amb_a, amb_e = amb_aud.reshape(-1), amb_eye.reshape(-1)
+        else:
+            amb_a, amb_e = amb_aud.abs().sum(-1), amb_eye.abs().sum(-1)
+        ws, aud_sum, eye_sum, unc_sum, depth, image = raymarching.composite_rays_train_triplane(sigmas, rgbs, amb_a, amb_e, unc, deltas, rays)
         raw = image
         image = None if self.fused_head else (image + (1 - ws).unsqueeze(-1) * bg_color).clamp(0, 1)      # the fused loss blends the background itself
         return dict(image=image, raw_image=raw, bg_color=bg_color, weights_sum=ws, ambient_aud=aud_sum, ambient_eye=eye_sum, uncertainty=unc_sum,

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(WM_THREADS, 1) k_linear_wgrad_multi(const __gr
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t n_chunks = (J.M + WG_CHUNK - 1) / WG_CHUNK;
     if (tid == 0) {
-        for (uint32_t s = 0; s < WP_STAGES; s++) { mbar_init(&full[s], WG_THREADS); mbar_init(&empty[s], 1); }
+        for (uint32_t s = 0; s < WP_STAGES; s++) { mbar_init(&full[s], WG_THREADS / 32); mbar_init(&empty[s], 1); }      // one arrival per producer warp
         for (uint32_t a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_free[a], 128); }
         fence_mbar_init();
     }
@@ -419,7 +419,8 @@ __global__ void __launch_bounds__(WM_THREADS, 1) k_linear_wgrad_multi(const __gr
         for (uint32_t g = 0; g < total; g++) {
             cp_async_wait<AHEAD - 1>();
             fence_proxy_async();
-            mbar_arrive(&full[g % WP_STAGES]);
+            __syncwarp();
+            if ((tid & 31u) == 0) mbar_arrive(&full[g % WP_STAGES]);         // 8 arrivals per chunk instead of 256 on one shared-memory word
             const uint32_t nxt = g + AHEAD;
             if (nxt < total) {
                 if (nxt >= WP_STAGES) mbar_wait(&empty[nxt % WP_STAGES], ((nxt / WP_STAGES) - 1u) & 1u);
