@@ -241,6 +241,54 @@ def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536
                      if fused_head else "drop-in ops + torch autograd (MLPs via cuBLAS under autocast fp16)") + ", flat AdamW, flat-buffer NCCL all-reduce"}
 
 
+def torso_bench(dev, steps=20, warmup=5):
+    """Torso branch of a 512x512 frame (torso is OFF in the headline frame, BASELINE configs[1]): the fused kernel (csrc/fused_torso.cu)
+    next to the reference's op-by-op graph on the drop-in encoders + torch Linear under autocast, same synthetic torso occupancy (a blob over ~1/3 of
+    the image), CUDA events on the launching stream."""
+    import math
+    from b2nerf.torso import TorsoModel, get_bg_coords
+    torch.manual_seed(0)
+    m = TorsoModel().to(dev).eval()
+    m.torso_encoder.embeddings.data.uniform_(-0.5, 0.5)
+    G = m.grid_size
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, G), torch.linspace(-1, 1, G), indexing="ij")
+    m.density_grid_torso.copy_((0.05 * torch.exp(-((xx * 1.2) ** 2 + ((yy - 0.5) * 1.5) ** 2) / 0.3)).reshape(-1).to(dev))
+    m.mean_density_torso = float(m.density_grid_torso.mean())
+    coords = get_bg_coords(HW, HW, dev)
+    pose = torch.eye(4, device=dev)[None].clone(); pose[0, 2, 3] = 3.35
+    hc = m.frame_constants(pose, 0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    # the fused call is replayed from a CUDA graph (pack + frame kernel): eager, the ~100 us of Python / ctypes per call would be what is timed
+    m.run_torso_fused(coords, pose, 0, None, h_const=hc)
+    torch.cuda.synchronize()
+    graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            keep = m.run_torso_fused(coords, pose, 0, None, h_const=hc)
+    torch.cuda.current_stream().wait_stream(side)
+    fused_ms = timed(graph.replay)
+    fused_eager_ms = timed(lambda: m.run_torso_fused(coords, pose, 0, None, h_const=hc))
+    assert bool(torch.isfinite(keep["bg_color"]).all())
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        per_op_ms = timed(lambda: m.run_torso(coords, pose, 0, None))
+        n_on = int(m.run_torso(coords, pose, 0, None)["mask"].sum())
+    macs = 5440                                            # 34*32 + 32*32 + 32*2 + 66*32 + 32*32 + 32*4 per torso pixel (constant inputs folded into a bias)
+    return {"pixels": HW * HW, "torso_pixels": n_on, "fused_ms_per_frame": fused_ms, "fused_eager_call_ms": fused_eager_ms, "per_op_ms_per_frame": per_op_ms,
+            "fused_gflops": 2.0 * macs * n_on / (fused_ms * 1e-3) / 1e9,
+            "note": "k_torso_frame: occupancy test + freq encoding + deform MLP + tiled fp16 grid + torso MLP + blend in one launch (CUDA cores, thread = pixel); "
+                    "per-op = run_torso on the drop-in encoders + torch Linear under autocast (~25 launches)"}
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     from b2nerf import lib
     from b2nerf.render import FramePipeline
@@ -347,6 +395,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     }
     if not args.no_train:
         line["train"] = train_info
+        line["torso"] = torso_bench(dev)
     if world == 1 and not args.no_cpu:
         rows = 32
         fps, sec, ns = cpu_frames_per_sec(rows, 2, 1)

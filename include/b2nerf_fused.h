@@ -227,6 +227,27 @@ int b2n_head_loss_backward(const float *image, const float *weights_sum, const f
                            float lambda_ent, float lambda_amb, const float *grad_loss, float *grad_image, float *grad_weights_sum,
                            float *grad_aud_sum, float *grad_eye_sum, void *stream);
 
+/* ---- torso branch of a frame = NeRFRenderer.run_torso (renderer.py:572-631) + NeRFNetwork.forward_torso (network.py:170-205) as ONE
+ * kernel, inference, autocast(fp16) numerics: 2-D occupancy test (F.grid_sample of density_grid_torso, align_corners=True, > density_thresh), frequency
+ * encoding of the pixel coordinate (degree 8), deform MLP 84->32->32->2, tiled grid D=2 L=16 C=2 (half arithmetic), torso MLP 116->32->32->4,
+ * sigmoid * 1.002 - 0.001, and the blend over the background.  Weights are the torch parameters in place (fp32, nn.Linear [out,in], no bias).
+ *   bg_coords [N,2] in [-1,1] (utils.py:218-223); h_const [50] = [anchor_encoder(wrapped anchors) 42 | individual_codes_torso row 8] (the per-frame
+ *   constant inputs of both MLPs, network.py:179-190); bg_color NULL (white), [3] or [N,3] (bg_per_ray);
+ *   bg_out [N,3] = torso_color * torso_alpha + bg_color * (1 - torso_alpha) — the bg_color the head composite takes (renderer.py:620,559);
+ *   alpha_out [N] / deform_out [N,2] optional (0 outside the occupancy mask). */
+typedef struct {
+    const float *deform_w0, *deform_w1, *deform_w2;   /* torso_deform_net.net.{0,1,2}.weight  [32,84] [32,32] [2,32] */
+    const float *torso_w0, *torso_w1, *torso_w2;      /* torso_net.net.{0,1,2}.weight         [32,116] [32,32] [4,32] */
+    const float *table;                               /* torso_encoder.embeddings [offsets[16], 2] fp32 */
+    const int32_t *offsets;                           /* [17], device */
+    float S;                                          /* log2(per_level_scale) */
+    uint32_t H;                                       /* base resolution (16) */
+    float torso_shrink;                               /* opt.torso_shrink (0.8) */
+} b2n_torso_weights;
+int b2n_torso_forward(const b2n_torso_weights *w, const float *bg_coords, uint32_t N, const float *density_grid_torso, uint32_t grid_size,
+                      float density_thresh, const float *h_const, const float *bg_color, int bg_per_ray, float *bg_out, float *alpha_out,
+                      float *deform_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,141 @@
+"""Torso branch of the talking-head NeRF on the B200-native kernels.
+
+`TorsoModel` holds the torso parameters / buffers of the reference's `NeRFNetwork(NeRFRenderer)` under the SAME names and shapes
+(nerf_triplane/network.py:156-167, renderer.py:123-149), so the torso part of a reference checkpoint loads with `strict=False`:
+    anchor_points [3,4], torso_deform_net.net.{0,1,2}.weight, torso_encoder.embeddings / .offsets, torso_net.net.{0,1,2}.weight,
+    individual_codes_torso [ind_num, 8], density_grid_torso [grid_size^2]  (+ the python float mean_density_torso).
+
+Two evaluation paths, same math (run_torso, renderer.py:572-631 with forward_torso, network.py:170-205):
+  * run_torso(...)        — the reference's op-by-op graph on the drop-in encoders (freqencoder / gridencoder kernels) + torch Linear; the parity partner;
+  * run_torso_fused(...)  — ONE kernel (csrc/fused_torso.cu, b2n_torso_forward) through the C ABI.
+Both return the reference's dict: bg_color [N,3] (torso over background — what the head composite takes as bg_color), torso_alpha [N,1], torso_color = bg_color.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from freqencoder import FreqEncoder
+from gridencoder import GridEncoder
+
+from ._lib import lib
+from .model import MLP
+
+
+class _TorsoWeightsC(ctypes.Structure):     # mirrors b2n_torso_weights (include/b2nerf_fused.h)
+    _fields_ = [("deform_w0", ctypes.c_void_p), ("deform_w1", ctypes.c_void_p), ("deform_w2", ctypes.c_void_p),
+                ("torso_w0", ctypes.c_void_p), ("torso_w1", ctypes.c_void_p), ("torso_w2", ctypes.c_void_p),
+                ("table", ctypes.c_void_p), ("offsets", ctypes.c_void_p), ("S", ctypes.c_float), ("H", ctypes.c_uint32), ("torso_shrink", ctypes.c_float)]
+
+
+def get_bg_coords(H, W, device):
+    """utils.py:218-223: [1, H*W, 2] in [-1, 1] (first coordinate runs over rows)."""
+    X = torch.arange(H, device=device) / (H - 1) * 2 - 1
+    Y = torch.arange(W, device=device) / (W - 1) * 2 - 1
+    xs, ys = torch.meshgrid(X, Y, indexing="ij")
+    return torch.cat([xs.reshape(-1, 1), ys.reshape(-1, 1)], dim=-1).unsqueeze(0)
+
+
+class TorsoModel(nn.Module):
+    def __init__(self, ind_dim_torso=8, ind_num=10000, grid_size=128, torso_shrink=0.8, density_thresh_torso=0.01):
+        super().__init__()
+        self.grid_size, self.torso_shrink, self.density_thresh_torso = grid_size, float(torso_shrink), float(density_thresh_torso)
+        self.individual_dim_torso = ind_dim_torso
+        self.anchor_points = nn.Parameter(torch.tensor([[0.01, 0.01, 0.1, 1], [-0.1, -0.1, 0.1, 1], [0.1, -0.1, 0.1, 1]]))
+        self.torso_deform_encoder = FreqEncoder(input_dim=2, degree=8)          # 34
+        self.anchor_encoder = FreqEncoder(input_dim=6, degree=3)                # 42
+        self.torso_deform_net = MLP(34 + 42 + ind_dim_torso, 2, 32, 3)
+        self.torso_encoder = GridEncoder(input_dim=2, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=16, desired_resolution=2048,
+                                         gridtype="tiled")                    # 32
+        self.torso_net = MLP(32 + 34 + 42 + ind_dim_torso, 4, 32, 3)
+        self.individual_codes_torso = nn.Parameter(torch.randn(ind_num, ind_dim_torso) * 0.1)
+        self.register_buffer("density_grid_torso", torch.zeros(grid_size ** 2))
+        self.mean_density_torso = 0.0
+
+    # ---- per-frame constants ------------------------------------------------------------------------------------------------------------
+    def frame_constants(self, poses, index=0):
+        """[1, 50] = [anchor_encoder(wrapped anchors) | individual code]: the inputs of both MLPs that do not depend on the pixel (network.py:179-190)."""
+        wrapped = self.anchor_points[None, ...] @ poses.permute(0, 2, 1).inverse()
+        wrapped = (wrapped[:, :, :2] / wrapped[:, :, 3, None] / wrapped[:, :, 2, None]).view(1, -1)
+        enc_anchor = self.anchor_encoder(wrapped.float())
+        c = self.individual_codes_torso[index if self.training else 0].view(1, -1)
+        return torch.cat([enc_anchor, c], dim=-1)
+
+    # ---- op-by-op path (the reference graph) ------------------------------------------------------------------------------------------------
+    def forward_torso(self, x, h_const):
+        """network.py:170-205 with [enc_anchor | c] precomputed.  x [M,2] in [-1,1] -> alpha [M,1], color [M,3], dx [M,2]."""
+        x = x * self.torso_shrink
+        enc_x = self.torso_deform_encoder(x)
+        h = torch.cat([enc_x, h_const.repeat(x.shape[0], 1)], dim=-1)
+        dx = self.torso_deform_net(h)
+        x = (x + dx).clamp(-1, 1)
+        x = self.torso_encoder(x, bound=1)
+        h = torch.cat([x, h], dim=-1)
+        h = self.torso_net(h)
+        alpha = torch.sigmoid(h[..., :1]) * (1 + 2 * 0.001) - 0.001
+        color = torch.sigmoid(h[..., 1:]) * (1 + 2 * 0.001) - 0.001
+        return alpha, color, dx
+
+    def density_thresh(self):
+        return min(self.density_thresh_torso, self.mean_density_torso)
+
+    def run_torso(self, bg_coords, poses, index=0, bg_color=None):
+        """renderer.py:572-631 on the drop-in ops (call under torch.autocast like the reference does)."""
+        bg_coords = bg_coords.contiguous().view(-1, 2)
+        N, dev = bg_coords.shape[0], bg_coords.device
+        if bg_color is None:
+            bg_color = 1
+        occupancy = F.grid_sample(self.density_grid_torso.view(1, 1, self.grid_size, self.grid_size), bg_coords.view(1, -1, 1, 2), align_corners=True).view(-1)
+        mask = occupancy > self.density_thresh()
+        torso_alpha, torso_color = torch.zeros([N, 1], device=dev), torch.zeros([N, 3], device=dev)
+        results = {}
+        if mask.any():
+            a, c, deform = self.forward_torso(bg_coords[mask], self.frame_constants(poses, index))
+            torso_alpha[mask] = a.float()
+            torso_color[mask] = c.float()
+            results["deform"] = deform
+        bg_color = torso_color * torso_alpha + bg_color * (1 - torso_alpha)
+        results.update(torso_alpha=torso_alpha, torso_color=bg_color, bg_color=bg_color, mask=mask)
+        return results
+
+    # ---- fused path -------------------------------------------------------------------------------------------------------------------------
+    def weights_struct(self):
+        p = lambda t: t.detach().data_ptr()
+        for t in (self.torso_encoder.embeddings, self.torso_net.net[0].weight, self.torso_deform_net.net[0].weight):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise RuntimeError("TorsoModel: parameters must be contiguous float32 CUDA tensors")
+        d, t, e = self.torso_deform_net.net, self.torso_net.net, self.torso_encoder
+        return _TorsoWeightsC(p(d[0].weight), p(d[1].weight), p(d[2].weight), p(t[0].weight), p(t[1].weight), p(t[2].weight), p(e.embeddings), p(e.offsets),
+                              float(math.log2(e.per_level_scale)), e.base_resolution, self.torso_shrink)
+
+    @torch.no_grad()
+    def run_torso_fused(self, bg_coords, poses, index=0, bg_color=None, h_const=None, want_deform=False):
+        """Same results as run_torso under autocast(fp16), one kernel.  bg_color: None (white), [3] / [1,3] or [N,3]."""
+        bg_coords = bg_coords.contiguous().view(-1, 2)
+        if not (bg_coords.is_cuda and bg_coords.dtype == torch.float32):
+            raise RuntimeError("run_torso_fused: bg_coords must be a float32 CUDA tensor (there is no CPU path)")
+        N, dev = bg_coords.shape[0], bg_coords.device
+        if h_const is None:
+            h_const = self.frame_constants(poses, index)
+        h_const = h_const.float().contiguous().view(-1)
+        per_ray = 0
+        if bg_color is not None:
+            bg_color = torch.as_tensor(bg_color, dtype=torch.float32, device=dev).contiguous()
+            if bg_color.numel() == 1:
+                bg_color = bg_color.expand(3).contiguous()
+            per_ray = int(bg_color.numel() == 3 * N and N > 1)
+            if not per_ray and bg_color.numel() != 3:
+                raise RuntimeError("run_torso_fused: bg_color must have 1, 3 or N*3 elements")
+        out = torch.empty(N, 3, device=dev)
+        alpha = torch.empty(N, device=dev)
+        deform = torch.empty(N, 2, device=dev) if want_deform else None
+        w = self.weights_struct()
+        lib().call("b2n_torso_forward", ctypes.byref(w), bg_coords.data_ptr(), N, self.density_grid_torso.data_ptr(), self.grid_size, float(self.density_thresh()),
+                   h_const.data_ptr(), None if bg_color is None else bg_color.data_ptr(), per_ray, out.data_ptr(), alpha.data_ptr(),
+                   None if deform is None else deform.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        res = dict(torso_alpha=alpha.view(N, 1), torso_color=out, bg_color=out)
+        if deform is not None:
+            res["deform"] = deform
+        return res

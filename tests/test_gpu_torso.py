@@ -1,0 +1,79 @@
+"""GPU: the fused torso kernel (csrc/fused_torso.cu) against the reference graph run_torso / forward_torso (renderer.py:572-631,
+network.py:170-205) evaluated op by op on the drop-in encoders + torch Linear under autocast(fp16) — which is how the reference runs it."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(seed=0, deform_scale=0.02):
+    from b2nerf.torso import TorsoModel
+    torch.manual_seed(seed)
+    m = TorsoModel().cuda().eval()
+    m.torso_encoder.embeddings.data.uniform_(-0.5, 0.5)
+    # keep the deformation small: dx is an fp16 value that moves the lookup in a 2048-cell grid; with |dx| ~ 1e-2 one fp16 ulp of dx (~1e-5) stays far
+    # below the finest cell (1e-3), so the two paths read the same cells
+    m.torso_deform_net.net[2].weight.data.mul_(deform_scale)
+    G = m.grid_size
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, G), torch.linspace(-1, 1, G), indexing="ij")
+    m.density_grid_torso.copy_((0.05 * torch.exp(-((xx * 1.2) ** 2 + ((yy - 0.5) * 1.5) ** 2) / 0.3)).reshape(-1).cuda())      # a torso-sized blob
+    m.mean_density_torso = float(m.density_grid_torso.mean())
+    return m
+
+
+def _pose():
+    th = math.radians(7.0)
+    p = torch.eye(4)
+    p[:3, :3] = torch.tensor([[math.cos(th), 0, math.sin(th)], [0, 1, 0], [-math.sin(th), 0, math.cos(th)]])
+    p[:3, 3] = torch.tensor([0.1, -0.05, 3.35])
+    return p[None].cuda()
+
+
+@pytest.mark.parametrize("hw", [(64, 80), (512, 512)])
+@pytest.mark.parametrize("bg_kind", ["white", "const", "per_ray"])
+def test_fused_torso_matches_autocast_reference(hw, bg_kind):
+    from b2nerf.torso import get_bg_coords
+    m = _model(1)
+    H, W = hw
+    coords = get_bg_coords(H, W, "cuda")
+    N = H * W
+    g = torch.Generator(device="cuda").manual_seed(3)
+    bg = {"white": None, "const": torch.tensor([0.2, 0.5, 0.9], device="cuda"), "per_ray": torch.rand(N, 3, device="cuda", generator=g)}[bg_kind]
+    poses = _pose()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        ref = m.run_torso(coords, poses, 0, bg)
+    out = m.run_torso_fused(coords, poses, 0, bg, want_deform=True)
+    torch.cuda.synchronize()
+    mask = ref["mask"]
+    assert 0.05 < float(mask.float().mean()) < 0.9                       # the blob covers part of the image
+    # occupancy mask: same bilinear arithmetic as F.grid_sample; pixels exactly at the threshold may flip
+    on = out["torso_alpha"].view(-1) != 0
+    flips = int((on & ~mask).sum())                                      # fused says torso where the reference did not
+    assert flips <= max(2, N // 20000), flips
+    a_ref, a_out = ref["torso_alpha"].view(-1), out["torso_alpha"].view(-1)
+    da = (a_ref - a_out).abs()
+    assert float(da.median()) < 3e-4 and float(da.max()) < 1.5e-2, (float(da.median()), float(da.max()))
+    dc = (ref["bg_color"] - out["bg_color"]).abs()
+    assert float(dc.median()) < 3e-4 and float(dc.max()) < 1.5e-2, (float(dc.median()), float(dc.max()))
+    dxr = torch.zeros(N, 2, device="cuda"); dxr[mask] = ref["deform"].float()
+    dd = (dxr - out["deform"]).abs()[mask & on]
+    assert float(dd.max()) < 2e-4, float(dd.max())
+    # outside the mask the background passes through untouched
+    off = ~mask & ~on
+    want = torch.ones(N, 3, device="cuda") if bg is None else (bg.expand(N, 3) if bg.numel() == 3 else bg)
+    assert torch.equal(out["bg_color"][off], want[off])
+
+
+def test_fused_torso_no_cpu_fallback_and_empty_mask():
+    from b2nerf.torso import get_bg_coords
+    m = _model(2)
+    coords = get_bg_coords(32, 32, "cuda")
+    with pytest.raises(RuntimeError):
+        m.run_torso_fused(coords.cpu(), _pose(), 0, None)
+    m.density_grid_torso.zero_(); m.mean_density_torso = 0.0             # threshold 0, occupancy 0: nothing is torso (renderer.py:603-606: strict >)
+    out = m.run_torso_fused(coords, _pose(), 0, None)
+    torch.cuda.synchronize()
+    assert float(out["torso_alpha"].abs().max()) == 0 and torch.equal(out["bg_color"], torch.ones(32 * 32, 3, device="cuda"))
