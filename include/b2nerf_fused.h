@@ -246,7 +246,10 @@ typedef struct {
 } b2n_torso_weights;
 int b2n_torso_forward(const b2n_torso_weights *w, const float *bg_coords, uint32_t N, const float *density_grid_torso, uint32_t grid_size,
                       float density_thresh, const float *h_const, const float *bg_color, int bg_per_ray, float *bg_out, float *alpha_out,
-                      float *deform_out, void *stream);
+                      float *deform_out, void *workspace, void *stream);
+/* workspace: 16-byte aligned device scratch of b2n_torso_workspace_bytes() bytes owned by the caller (packed weight image + tile counter); one per
+ * concurrently running call */
+uint64_t b2n_torso_workspace_bytes(void);
 
 #ifdef __cplusplus
 }

@@ -14,10 +14,13 @@ from .model import HeadModel
 
 class FrameRenderer:
     def __init__(self, model: HeadModel, n_rays, eye=0.4, ind_index=0, dt_gamma=1.0 / 256, max_steps=16, T_thresh=1e-4, use_graph=True, fused_audio=True,
-                 camera=None):
+                 camera=None, torso=None, bg_coords=None):
         """camera = (H, W, fx, fy, cx, cy): also build the device-side prologue / epilogue (rays from a 4x4 pose, RGB24 output), so that
-        render_host_pose() moves a pose + the audio window up and one uint8 frame down."""
+        render_host_pose() moves a pose + the audio window up and one uint8 frame down.
+        torso = a TorsoModel (+ bg_coords [N,2], utils.py:218-223): every frame first runs the fused torso kernel (csrc/fused_torso.cu) over the background into
+        the per-ray bg_color buffer the head frame reads (renderer.py:572-631 then :559-561); set the head pose with set_torso_pose()."""
         self.m = model
+        self.torso = torso
         self.camera = camera
         self.dev = next(model.parameters()).device
         self.N = int(n_rays)
@@ -36,6 +39,17 @@ class FrameRenderer:
         self.launches_per_frame = None
         self.ws = torch.empty(self.N, device=d)
         self.depth = torch.empty(self.N, device=d)
+        self.bg = None
+        if torso is not None:
+            if bg_coords is None or bg_coords.numel() != 2 * self.N:
+                raise RuntimeError("FrameRenderer: torso needs bg_coords [n_rays, 2]")
+            self.bg_coords = bg_coords.to(d).float().contiguous().view(-1, 2)
+            self.bg = torch.ones(self.N, 3, device=d)                       # torso over white; the frame reads it as its per-ray bg_color
+            self.torso_bg_color = None
+            self.torso_h_const = torch.zeros(50, device=d)
+            from ._lib import lib as _lib
+            self.torso_ws = torch.empty(int(_lib().raw("b2n_torso_workspace_bytes")()), dtype=torch.uint8, device=d)
+            self.set_torso_pose(torch.eye(4, device=d)[None])
         if camera is not None:
             if int(camera[0]) * int(camera[1]) != self.N:
                 raise RuntimeError("FrameRenderer: camera H*W must equal n_rays")
@@ -51,13 +65,23 @@ class FrameRenderer:
                 self.loop_graph_error = str(e)
                 self._capture()
 
+    @torch.no_grad()
+    def set_torso_pose(self, poses, index=0):
+        """Head pose [1,4,4] of the coming frames -> the 50 per-frame constant inputs of the torso MLPs (network.py:179-190)."""
+        self.torso_h_const.copy_(self.torso.frame_constants(poses.to(self.dev), index).view(-1))
+
+    def _torso(self):
+        if self.torso is not None:
+            self.torso.run_torso_fused(self.bg_coords, None, 0, self.torso_bg_color, h_const=self.torso_h_const, out=self.bg, workspace=self.torso_ws)
+
     def _device_frame(self):
+        self._torso()
         if self.fused_audio:
             enc_a = self.m.encode_audio_fused(self.auds, out=self.enc_a)      # one cluster kernel (csrc/fused_audio.cu)
         else:
             with torch.autocast("cuda", dtype=torch.float16):
                 enc_a = self.m.encode_audio(self.auds).float()              # AudioNet + AudioAttNet through torch (network.py:226-240)
-        self.m.render_frame(self.rays_o, self.rays_d, enc_a, self.ind_code, self.eye, out=self.image, **self.kw)
+        self.m.render_frame(self.rays_o, self.rays_d, enc_a, self.ind_code, self.eye, bg_color=self.bg, out=self.image, **self.kw)
 
     @torch.no_grad()
     def _build_loop_graph(self):
@@ -74,7 +98,8 @@ class FrameRenderer:
         torch.cuda.synchronize(self.dev)
         L.call("b2n_frame_graph_create", ctypes.byref(h), m.handle, ctypes.byref(cfg), ctypes.byref(aw) if aw is not None else None,
                self.auds.data_ptr(), self.auds.shape[2], self.enc_a.data_ptr(), self.rays_o.data_ptr(), self.rays_d.data_ptr(), self.N,
-               m.density_bitfield.data_ptr(), self._graph_keep[2].data_ptr(), self._graph_keep[3].data_ptr(), None, self._graph_ws.data_ptr(),
+               m.density_bitfield.data_ptr(), self._graph_keep[2].data_ptr(), self._graph_keep[3].data_ptr(), None if self.bg is None else self.bg.data_ptr(),
+               self._graph_ws.data_ptr(),
                self.image.data_ptr(), self.ws.data_ptr(), self.depth.data_ptr())
         self.loop_graph = h
         kf, kb = ctypes.c_uint64(), ctypes.c_uint64()
@@ -95,7 +120,7 @@ class FrameRenderer:
         torch.cuda.synchronize(self.dev)
         L.call("b2n_frame_graph_create_io", ctypes.byref(h), m.handle, ctypes.byref(cfg), ctypes.byref(aw) if aw is not None else None,
                self.auds.data_ptr(), self.auds.shape[2], self.enc_a.data_ptr(), self.rays_o.data_ptr(), self.rays_d.data_ptr(), self.N,
-               m.density_bitfield.data_ptr(), ind.data_ptr(), eye.data_ptr(), None, self._graph_ws.data_ptr(),
+               m.density_bitfield.data_ptr(), ind.data_ptr(), eye.data_ptr(), None if self.bg is None else self.bg.data_ptr(), self._graph_ws.data_ptr(),
                self.image.data_ptr(), self.ws.data_ptr(), self.depth.data_ptr(), ctypes.byref(io))
         self.pose_graph = h
 
@@ -109,6 +134,7 @@ class FrameRenderer:
             self._build_pose_graph()
         self.pose.copy_(pose_host.view(4, 4), non_blocking=True)
         self.auds.copy_(auds_host, non_blocking=True)
+        self._torso()
         lib().call("b2n_frame_graph_launch", self.pose_graph, torch.cuda.current_stream(self.dev).cuda_stream)
         out_u8_host.copy_(self.rgb8, non_blocking=True)
         return out_u8_host
@@ -125,6 +151,7 @@ class FrameRenderer:
     def _launch(self):
         if self.loop_graph is not None:
             from ._lib import lib
+            self._torso()
             if not self.fused_audio:
                 with torch.autocast("cuda", dtype=torch.float16):
                     self.enc_a.copy_(self.m.encode_audio(self.auds).float())

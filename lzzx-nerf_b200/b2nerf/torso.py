@@ -111,8 +111,9 @@ class TorsoModel(nn.Module):
                               float(math.log2(e.per_level_scale)), e.base_resolution, self.torso_shrink)
 
     @torch.no_grad()
-    def run_torso_fused(self, bg_coords, poses, index=0, bg_color=None, h_const=None, want_deform=False):
-        """Same results as run_torso under autocast(fp16), one kernel.  bg_color: None (white), [3] / [1,3] or [N,3]."""
+    def run_torso_fused(self, bg_coords, poses, index=0, bg_color=None, h_const=None, want_deform=False, out=None, workspace=None):
+        """Same results as run_torso under autocast(fp16), one kernel.  bg_color: None (white), [3] / [1,3] or [N,3]; out: optional [N,3] result buffer
+        (FrameRenderer passes the buffer its frame graph reads as bg_color)."""
         bg_coords = bg_coords.contiguous().view(-1, 2)
         if not (bg_coords.is_cuda and bg_coords.dtype == torch.float32):
             raise RuntimeError("run_torso_fused: bg_coords must be a float32 CUDA tensor (there is no CPU path)")
@@ -128,13 +129,17 @@ class TorsoModel(nn.Module):
             per_ray = int(bg_color.numel() == 3 * N and N > 1)
             if not per_ray and bg_color.numel() != 3:
                 raise RuntimeError("run_torso_fused: bg_color must have 1, 3 or N*3 elements")
-        out = torch.empty(N, 3, device=dev)
+        out = torch.empty(N, 3, device=dev) if out is None else out
+        if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == 3 * N):
+            raise RuntimeError("run_torso_fused: out must be a contiguous float32 CUDA tensor [N,3]")
         alpha = torch.empty(N, device=dev)
         deform = torch.empty(N, 2, device=dev) if want_deform else None
         w = self.weights_struct()
+        if workspace is None:          # packed weight image + tile counter; concurrent callers (frames in flight on several streams) pass their own
+            workspace = torch.empty(int(lib().raw("b2n_torso_workspace_bytes")()), dtype=torch.uint8, device=dev)
         lib().call("b2n_torso_forward", ctypes.byref(w), bg_coords.data_ptr(), N, self.density_grid_torso.data_ptr(), self.grid_size, float(self.density_thresh()),
                    h_const.data_ptr(), None if bg_color is None else bg_color.data_ptr(), per_ray, out.data_ptr(), alpha.data_ptr(),
-                   None if deform is None else deform.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                   None if deform is None else deform.data_ptr(), workspace.data_ptr(), torch.cuda.current_stream().cuda_stream)
         res = dict(torso_alpha=alpha.view(N, 1), torso_color=out, bg_color=out)
         if deform is not None:
             res["deform"] = deform

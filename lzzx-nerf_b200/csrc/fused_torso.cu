@@ -264,9 +264,11 @@ __global__ void __launch_bounds__(TS_THREADS) k_torso_frame(const __grid_constan
 
 using namespace b2n;
 
+extern "C" uint64_t b2n_torso_workspace_bytes(void) { return sizeof(float) * (TI_TOTAL + 4); }
+
 extern "C" int b2n_torso_forward(const b2n_torso_weights *w, const float *bg_coords, uint32_t N, const float *density_grid_torso, uint32_t grid_size,
                                  float density_thresh, const float *h_const, const float *bg_color, int bg_per_ray, float *bg_out, float *alpha_out,
-                                 float *deform_out, void *stream) {
+                                 float *deform_out, void *workspace, void *stream) {
     B2N_REQUIRE(w && bg_coords && density_grid_torso && h_const && bg_out, "torso_forward: null pointer");
     B2N_REQUIRE(w->deform_w0 && w->deform_w1 && w->deform_w2 && w->torso_w0 && w->torso_w1 && w->torso_w2 && w->table && w->offsets, "torso_forward: null weight pointer");
     B2N_REQUIRE(grid_size >= 2, "torso_forward: grid_size=%u", grid_size);
@@ -276,10 +278,10 @@ extern "C" int b2n_torso_forward(const b2n_torso_weights *w, const float *bg_coo
     a.bg_coords = bg_coords; a.N = N; a.dgrid = density_grid_torso; a.G = grid_size; a.thresh = density_thresh; a.shrink = w->torso_shrink;
     a.hconst = h_const; a.table = w->table; a.offsets = w->offsets; a.S = w->S; a.H = w->H;
     a.bg_color = bg_color; a.bg_per_ray = bg_per_ray; a.bg_out = bg_out; a.alpha_out = alpha_out; a.deform_out = deform_out;
-    // the weights are re-packed on every call (a 35 KB image in library scratch, one small launch): the caller may have stepped an optimizer in
-    // between.  One image (+ the tile counter) per device: concurrent calls must be ordered on one stream
-    float *img = static_cast<float *>(scratch(sizeof(float) * (TI_TOTAL + 4), 1));
-    B2N_REQUIRE(img, "torso_forward: scratch allocation failed");
+    // the weights are re-packed on every call (a 35 KB image + the tile counter in the caller's workspace, one small launch): the caller may have
+    // stepped an optimizer in between, and concurrent frames on different streams each bring their own workspace
+    B2N_REQUIRE(workspace && ((uintptr_t)workspace & 15) == 0, "torso_forward: workspace must be a 16-byte aligned device buffer of b2n_torso_workspace_bytes()");
+    float *img = static_cast<float *>(workspace);
     k_torso_pack<<<ceil_div<uint32_t>(TI_TOTAL, 256), 256, 0, as_stream(stream)>>>(w->deform_w0, w->deform_w1, w->deform_w2, w->torso_w0, w->torso_w1, w->torso_w2, img, reinterpret_cast<uint32_t *>(img + TI_TOTAL));
     if (check_launch("torso_forward(pack)")) return 1;
     a.img = img; a.tile_counter = reinterpret_cast<uint32_t *>(img + TI_TOTAL);

@@ -103,3 +103,22 @@ def test_head_model_state_dict_matches_reference_names_and_count():
                      "audio_att_net.attentionConvNet.8.weight": (1, 2, 3), "audio_att_net.attentionNet.0.weight": (8, 8), "individual_codes": (10000, 4),
                      "density_bitfield": (262144,), "density_grid": (1, 2097152), "step_counter": (16, 2), "aabb_infer": (6,)}.items():
         assert tuple(sd[k].shape) == shape, k
+
+
+def test_torso_model_state_dict_matches_reference_names_and_count():
+    """Torso branch (network.py:156-167, renderer.py:123-149): reference parameter / buffer names and shapes; the tiled grid D=2 L=16 C=2
+    holds 1 111 040 parameters (network.py:166)."""
+    from b2nerf.torso import TorsoModel, get_bg_coords
+    m = TorsoModel()
+    sd = m.state_dict()
+    for k, shape in {"anchor_points": (3, 4), "torso_deform_net.net.0.weight": (32, 84), "torso_deform_net.net.1.weight": (32, 32), "torso_deform_net.net.2.weight": (2, 32),
+                     "torso_encoder.embeddings": (555520, 2), "torso_encoder.offsets": (17,), "torso_net.net.0.weight": (32, 116), "torso_net.net.2.weight": (4, 32),
+                     "individual_codes_torso": (10000, 8), "density_grid_torso": (128 * 128,)}.items():
+        assert tuple(sd[k].shape) == shape, k
+    assert m.torso_encoder.embeddings.numel() == 1111040
+    assert m.torso_deform_encoder.output_dim == 34 and m.anchor_encoder.output_dim == 42
+    c = get_bg_coords(4, 6, "cpu")                          # utils.py:218-223: first coordinate runs over the rows
+    assert tuple(c.shape) == (1, 24, 2) and float(c[0, 0, 0]) == -1 and float(c[0, 5, 1]) == 1 and float(c[0, 6, 0]) > -1
+    import pytest
+    with pytest.raises(RuntimeError):                        # no CPU path
+        m.run_torso_fused(c, None, 0, None, h_const=__import__("torch").zeros(50))

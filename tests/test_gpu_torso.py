@@ -77,3 +77,39 @@ def test_fused_torso_no_cpu_fallback_and_empty_mask():
     out = m.run_torso_fused(coords, _pose(), 0, None)
     torch.cuda.synchronize()
     assert float(out["torso_alpha"].abs().max()) == 0 and torch.equal(out["bg_color"], torch.ones(32 * 32, 3, device="cuda"))
+
+
+def test_frame_renderer_with_torso_background():
+    """FrameRenderer(torso=...): every frame runs the fused torso kernel into the per-ray bg_color buffer the head frame reads (renderer.py:572-631 then
+    :559-561) — same image, bit for bit, as calling the two stages by hand; the graph path equals the eager path; the torso shows behind the head."""
+    from b2nerf import scene
+    from b2nerf.model import HeadModel
+    from b2nerf.render import FrameRenderer
+    from b2nerf.torso import get_bg_coords
+    torch.manual_seed(0)
+    m = HeadModel().cuda()
+    for enc in (m.encoder_xy, m.encoder_yz, m.encoder_xz):
+        enc.embeddings.data.uniform_(-1, 1)
+    m.testing = True
+    m.density_bitfield.copy_(torch.from_numpy(scene.bitfield_from_grid(scene.density_grid())).cuda())
+    t = _model(4)
+    hw = 128
+    coords = get_bg_coords(hw, hw, "cuda")
+    pose = _pose()
+    r_graph = FrameRenderer(m, hw * hw, use_graph=True, torso=t, bg_coords=coords)
+    r_eager = FrameRenderer(m, hw * hw, use_graph=False, torso=t, bg_coords=coords)
+    r_plain = FrameRenderer(m, hw * hw, use_graph=True)
+    for r in (r_graph, r_eager):
+        r.set_torso_pose(pose)
+    j, i = np.meshgrid(np.arange(hw), np.arange(hw), indexing="ij")
+    o, d = scene.rays_for_pixels(scene.camera_pose(1), hw, hw, i.ravel(), j.ravel())
+    rays_o, rays_d, auds = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(scene.audio_window(1)).cuda()
+    a = r_graph.render_device(rays_o, rays_d, auds).clone()
+    b = r_eager.render_device(rays_o, rays_d, auds).clone()
+    p = r_plain.render_device(rays_o, rays_d, auds).clone()
+    bg = t.run_torso_fused(coords, pose, 0, None)["bg_color"]
+    enc_a = m.encode_audio_fused(auds)
+    c, _, _ = m.render_frame(rays_o, rays_d, enc_a, r_graph.ind_code, r_graph.eye, bg_color=bg)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    assert not torch.equal(a, p) and float((a - p).abs().max()) > 0.05       # the torso changed the background pixels
