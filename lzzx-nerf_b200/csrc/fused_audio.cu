@@ -23,6 +23,9 @@ __device__ __forceinline__ float leaky_h(float v) { return v > 0.0f ? v : rh(0.0
 
 // Conv1d(ci -> co, kernel 3, given stride, padding 1) + bias + LeakyReLU on a [ci, li] activation held in shared memory (values already
 // fp16-rounded).  One warp per output element (co, lo); lanes split the ci*3 reduction; weights [co, ci, 3] are read coalesced.
+// SW = true: w / b point to SHARED memory copies already rounded to fp16 (k_audio_encode stages every small layer at kernel start: a layer then
+// costs shared-memory latency instead of one L2 round trip for its weights plus one for its bias).
+template <bool SW = false>
 __device__ void conv3_layer(const float *in_s, uint32_t ci, uint32_t li, const float *__restrict__ w, const float *__restrict__ b, float *out_s, uint32_t co,
                             uint32_t stride, bool act) {
     const uint32_t lo = (li + 2 - 3) / stride + 1;
@@ -31,15 +34,27 @@ __device__ void conv3_layer(const float *in_s, uint32_t ci, uint32_t li, const f
         const uint32_t c = o / lo, x = o - c * lo;
         const float *wc = w + (size_t)c * ci * 3;
         float acc = 0.0f;
-        for (uint32_t r = lane; r < ci * 3; r += 32) {
-            const uint32_t cin = r / 3, k = r - cin * 3;
-            const int xi = (int)(x * stride + k) - 1;
-            if (xi >= 0 && xi < (int)li) acc = fmaf(rh(__ldg(wc + r)), in_s[cin * li + xi], acc);
+        // weights are fetched eight at a time, unconditionally (the tap test guarded the load before: no two loads of a lane were ever in flight, and
+        // the first convolution of a HuBERT window — 96 dependent L2 round trips per lane — was most of this kernel's 45 us); same summation order
+        const uint32_t n = ci * 3;
+        for (uint32_t r0 = lane; r0 < n; r0 += 32 * 8) {
+            float wv[8];
+#pragma unroll
+            for (uint32_t u = 0; u < 8; u++) { const uint32_t r = r0 + 32 * u; wv[u] = r < n ? (SW ? wc[r] : __ldg(wc + r)) : 0.0f; }
+#pragma unroll
+            for (uint32_t u = 0; u < 8; u++) {
+                const uint32_t r = r0 + 32 * u;
+                if (r < n) {
+                    const uint32_t cin = r / 3, k = r - cin * 3;
+                    const int xi = (int)(x * stride + k) - 1;
+                    if (xi >= 0 && xi < (int)li) acc = fmaf(SW ? wv[u] : rh(wv[u]), in_s[cin * li + xi], acc);
+                }
+            }
         }
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
         if (lane == 0) {
-            float v = rh(acc + rh(__ldg(b + c)));
+            float v = rh(acc + (SW ? b[c] : rh(__ldg(b + c))));
             out_s[c * lo + x] = act ? leaky_h(v) : v;
         }
     }
@@ -47,19 +62,35 @@ __device__ void conv3_layer(const float *in_s, uint32_t ci, uint32_t li, const f
 }
 
 // Linear(ci -> co) + bias (+ LeakyReLU); one warp per output
+template <bool SW = false>
 __device__ void linear_layer(const float *in_s, uint32_t ci, const float *__restrict__ w, const float *__restrict__ b, float *out_s, uint32_t co, bool act) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (uint32_t o = warp; o < co; o += AU_WARPS) {
         float acc = 0.0f;
-        for (uint32_t r = lane; r < ci; r += 32) acc = fmaf(rh(__ldg(w + (size_t)o * ci + r)), in_s[r], acc);
+        for (uint32_t r = lane; r < ci; r += 32) acc = fmaf(SW ? w[(size_t)o * ci + r] : rh(__ldg(w + (size_t)o * ci + r)), in_s[r], acc);
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
         if (lane == 0) {
-            float v = rh(acc + rh(__ldg(b + o)));
+            float v = rh(acc + (SW ? b[o] : rh(__ldg(b + o))));
             out_s[o] = act ? leaky_h(v) : v;
         }
     }
     __syncthreads();
+}
+
+// shared-memory weight cache of k_audio_encode (floats): everything except the first convolution (dim_in x 32 x 3: 393 KB for HuBERT features)
+constexpr uint32_t AW_C1 = 0, AW_C2 = AW_C1 + 32 * 32 * 3, AW_C3 = AW_C2 + 64 * 32 * 3, AW_F0 = AW_C3 + 64 * 64 * 3, AW_F1 = AW_F0 + 64 * 64,
+                   AW_B = AW_F1 + 32 * 64,                      // biases: conv 32, 32, 64, 64, fc 64, 32
+                   AW_AC = AW_B + 288,                         // attention convs 32->16->8->4->2->1
+                   AW_AB = AW_AC + (16 * 32 + 8 * 16 + 4 * 8 + 2 * 4 + 1 * 2) * 3,      // their biases 16, 8, 4, 2, 1 (+1 pad)
+                   AW_AF = AW_AB + 32, AW_AFB = AW_AF + 64, AW_TOTAL = AW_AFB + 8;
+
+__constant__ uint32_t c_att_w_off[5] = {0, 16 * 32 * 3, (16 * 32 + 8 * 16) * 3, (16 * 32 + 8 * 16 + 4 * 8) * 3, (16 * 32 + 8 * 16 + 4 * 8 + 2 * 4) * 3};
+__constant__ uint32_t c_att_b_off[5] = {0, 16, 24, 28, 30};
+
+__device__ __forceinline__ void stage_weights(float *dst, const float *__restrict__ src, uint32_t n) {
+#pragma unroll 8
+    for (uint32_t i = threadIdx.x; i < n; i += AU_THREADS) dst[i] = rh(__ldg(src + i));
 }
 
 struct AudioArgs {
@@ -81,6 +112,23 @@ __global__ void __cluster_dims__(AU_FRAMES, 1, 1) __launch_bounds__(AU_THREADS) 
     __shared__ float s_all[AU_FRAMES * 32];             // CTA 0: all frames [8, 32]
     __shared__ float s_y[AU_FRAMES];
 
+    // every layer but the first convolution: weights and biases into shared memory (fp16-rounded), all loads issued back to back — the ~13 dependent
+    // layers that follow then pay shared-memory latency instead of two L2 round trips each (the kernel is a latency chain; with the batched weight loads of
+    // conv3_layer: 45 -> 33 us in the training step, the backward twin 130 -> 112 us)
+    float *s_w = s_b + 512;
+    stage_weights(s_w + AW_C1, a.w.conv_w[1], 32 * 32 * 3); stage_weights(s_w + AW_C2, a.w.conv_w[2], 64 * 32 * 3); stage_weights(s_w + AW_C3, a.w.conv_w[3], 64 * 64 * 3);
+    stage_weights(s_w + AW_F0, a.w.fc_w[0], 64 * 64); stage_weights(s_w + AW_F1, a.w.fc_w[1], 32 * 64);
+    stage_weights(s_w + AW_B, a.w.conv_b[0], 32); stage_weights(s_w + AW_B + 32, a.w.conv_b[1], 32); stage_weights(s_w + AW_B + 64, a.w.conv_b[2], 64);
+    stage_weights(s_w + AW_B + 128, a.w.conv_b[3], 64); stage_weights(s_w + AW_B + 192, a.w.fc_b[0], 64); stage_weights(s_w + AW_B + 256, a.w.fc_b[1], 32);
+    if (frame == 0) {
+        const uint32_t chans_[6] = {32, 16, 8, 4, 2, 1};
+#pragma unroll
+        for (int l = 0; l < 5; l++) {
+            stage_weights(s_w + AW_AC + c_att_w_off[l], a.w.att_conv_w[l], chans_[l + 1] * chans_[l] * 3);
+            stage_weights(s_w + AW_AB + c_att_b_off[l], a.w.att_conv_b[l], chans_[l + 1]);
+        }
+        stage_weights(s_w + AW_AF, a.w.att_fc_w, 64); stage_weights(s_w + AW_AFB, a.w.att_fc_b, 8);
+    }
     // window slice + fp16 rounding of the input (autocast casts the conv input to half)
     const float *x = a.auds + (size_t)frame * dim_in * a.L;
     for (uint32_t i = threadIdx.x; i < dim_in * Lw; i += AU_THREADS) {
@@ -90,13 +138,13 @@ __global__ void __cluster_dims__(AU_FRAMES, 1, 1) __launch_bounds__(AU_THREADS) 
     __syncthreads();
     // AudioNet.encoder_conv: dim_in -> 32 -> 32 -> 64 -> 64, stride 2 (network.py:45-54)
     uint32_t li = Lw;
-    conv3_layer(s_in, dim_in, li, a.w.conv_w[0], a.w.conv_b[0], s_a, 32, 2, true); li = (li + 2 - 3) / 2 + 1;
-    conv3_layer(s_a, 32, li, a.w.conv_w[1], a.w.conv_b[1], s_b, 32, 2, true);      li = (li + 2 - 3) / 2 + 1;
-    conv3_layer(s_b, 32, li, a.w.conv_w[2], a.w.conv_b[2], s_a, 64, 2, true);      li = (li + 2 - 3) / 2 + 1;
-    conv3_layer(s_a, 64, li, a.w.conv_w[3], a.w.conv_b[3], s_b, 64, 2, true);      li = (li + 2 - 3) / 2 + 1;
+    conv3_layer<false>(s_in, dim_in, li, a.w.conv_w[0], a.w.conv_b[0], s_a, 32, 2, true);                     li = (li + 2 - 3) / 2 + 1;      // weights too large to stage
+    conv3_layer<true>(s_a, 32, li, s_w + AW_C1, s_w + AW_B + 32, s_b, 32, 2, true);                            li = (li + 2 - 3) / 2 + 1;
+    conv3_layer<true>(s_b, 32, li, s_w + AW_C2, s_w + AW_B + 64, s_a, 64, 2, true);                            li = (li + 2 - 3) / 2 + 1;
+    conv3_layer<true>(s_a, 64, li, s_w + AW_C3, s_w + AW_B + 128, s_b, 64, 2, true);                           li = (li + 2 - 3) / 2 + 1;
     // li == 1 here (squeeze(-1), network.py:66); encoder_fc1: 64 -> 64 -> 32 (network.py:55-59)
-    linear_layer(s_b, 64, a.w.fc_w[0], a.w.fc_b[0], s_a, 64, true);
-    linear_layer(s_a, 64, a.w.fc_w[1], a.w.fc_b[1], s_feat, 32, false);
+    linear_layer<true>(s_b, 64, s_w + AW_F0, s_w + AW_B + 192, s_a, 64, true);
+    linear_layer<true>(s_a, 64, s_w + AW_F1, s_w + AW_B + 256, s_feat, 32, false);
     cluster.sync();                                     // every frame's feature vector is in its CTA's shared memory
     if (frame == 0) {
         for (uint32_t i = threadIdx.x; i < AU_FRAMES * 32; i += AU_THREADS) {
@@ -114,10 +162,10 @@ __global__ void __cluster_dims__(AU_FRAMES, 1, 1) __launch_bounds__(AU_THREADS) 
     const uint32_t chans[6] = {32, 16, 8, 4, 2, 1};
 #pragma unroll 1
     for (int l = 0; l < 5; l++) {
-        conv3_layer(t0, chans[l], AU_FRAMES, a.w.att_conv_w[l], a.w.att_conv_b[l], t1, chans[l + 1], 1, true);
+        conv3_layer<true>(t0, chans[l], AU_FRAMES, s_w + AW_AC + c_att_w_off[l], s_w + AW_AB + c_att_b_off[l], t1, chans[l + 1], 1, true);
         float *tmp = t0; t0 = t1; t1 = tmp;
     }
-    linear_layer(t0, AU_FRAMES, a.w.att_fc_w, a.w.att_fc_b, s_y, AU_FRAMES, false);
+    linear_layer<true>(t0, AU_FRAMES, s_w + AW_AF, s_w + AW_AFB, s_y, AU_FRAMES, false);
     if (threadIdx.x < 32) {
         // softmax over the 8 frames in fp32 (autocast runs softmax in float), then the weighted sum in fp32
         float mx = -INFINITY;
@@ -324,7 +372,7 @@ extern "C" int b2n_audio_encode(const b2n_audio_weights *w, const float *auds, u
     for (int i = 0; i < 4; i++) li = (li + 2 - 3) / 2 + 1;
     B2N_REQUIRE(li == 1, "audio_encode: window length %u does not reduce to 1 after four stride-2 convolutions", L);
     AudioArgs a = {*w, auds, L, enc_a};
-    const size_t smem = sizeof(float) * ((size_t)w->dim_in * Lw + 1024);
+    const size_t smem = sizeof(float) * ((size_t)w->dim_in * Lw + 1024 + AW_TOTAL);       // input slice + ping / pong + the weight cache (121 KB)
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(k_audio_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
     k_audio_encode<<<AU_FRAMES, AU_THREADS, smem, as_stream(stream)>>>(a);
