@@ -134,7 +134,9 @@ class _march_rays_train(Function):
         n = rays_o.shape[0]
         use_estimate = (not force_all_rays) and mean_count > 0
         m = _pad_to(mean_count, align) if use_estimate else n * max_steps
-        xyzs, dirs, deltas = rays_o.new_zeros(m, 3), rays_o.new_zeros(m, 3), rays_o.new_zeros(m, 2)
+        # zero-filled like the reference's (raymarching.py:231-233), in ONE allocation / fill: rows past the counter stay zero
+        zbuf = rays_o.new_zeros(m * 8)
+        xyzs, dirs, deltas = zbuf[:3 * m].view(m, 3), zbuf[3 * m:6 * m].view(m, 3), zbuf[6 * m:].view(m, 2)
         rays = torch.empty(n, 3, dtype=torch.int32, device=rays_o.device)
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=rays_o.device)
@@ -168,7 +170,9 @@ class _march_rays(Function):
         rays_o, rays_d = _rays3(rays_o), _rays3(rays_d)
         m = _pad_to(n_alive * n_step, align)
         # zero fill is part of the contract: deltas == 0 marks "ray ended" for the composite (raymarching.cu:982)
-        xyzs, dirs, deltas = rays_o.new_zeros(m, 3), rays_o.new_zeros(m, 3), rays_o.new_zeros(m, 2)
+        # zero-filled like the reference's (raymarching.py:231-233), in ONE allocation / fill: rows past the counter stay zero
+        zbuf = rays_o.new_zeros(m * 8)
+        xyzs, dirs, deltas = zbuf[:3 * m].view(m, 3), zbuf[3 * m:6 * m].view(m, 3), zbuf[6 * m:].view(m, 2)
         noises = torch.rand(n_alive, dtype=rays_o.dtype, device=rays_o.device) if perturb else rays_o.new_zeros(n_alive)
         _backend.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
                             density_bitfield, near, far, xyzs, dirs, deltas, noises)
@@ -218,8 +222,14 @@ def _make_train_composite(tag, extras):
             per_sample, (deltas, rays, weights_sum) = saved[2:2 + k], saved[2 + k:5 + k]
             sums, image = saved[5 + k:5 + 2 * k], saved[5 + 2 * k]
             m, n, t_thresh = ctx.dims
-            g_sigmas, g_rgbs = torch.zeros_like(sigmas), torch.zeros_like(rgbs)
-            g_extra = [torch.zeros_like(t) for t in per_sample]
+            # pre-zeroed gradients (raymarching.py:627-633), one fill for all of them
+            shapes = [sigmas.shape, rgbs.shape] + [t.shape for t in per_sample]
+            sizes = [int(torch.Size(sh).numel()) for sh in shapes]
+            zbuf = sigmas.new_zeros(sum(sizes))
+            views, off = [], 0
+            for sh, sz in zip(shapes, sizes):
+                views.append(zbuf[off:off + sz].view(sh)); off += sz
+            g_sigmas, g_rgbs, g_extra = views[0], views[1], views[2:]
             bwd_fn(grad_weights_sum.contiguous(), *g_sums, grad_image, sigmas, rgbs, *per_sample, deltas, rays,
                    weights_sum, *sums, image, m, n, t_thresh, g_sigmas, g_rgbs, *g_extra)
             return (g_sigmas, g_rgbs, *g_extra, None, None, None)
