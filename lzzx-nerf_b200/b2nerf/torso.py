@@ -144,3 +144,41 @@ class TorsoModel(nn.Module):
         if deform is not None:
             res["deform"] = deform
         return res
+
+    # ---- 2-D occupancy refresh ----------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def update_extra_state(self, pose, index=0, decay=0.95, fused=True, noise=None):
+        """The torso part of NeRFRenderer.update_extra_state (renderer.py:768-809): alpha of the jittered grid_size^2 lattice for one (pose, individual
+        code), 5x5 max-pool dilation, EMA-max into density_grid_torso, mean -> mean_density_torso (one .item(), as in the reference).  fused=True evaluates
+        the lattice with the fused kernel (threshold -inf: every point is evaluated), fused=False through forward_torso under autocast.  `noise` [G*G, 2] in
+        [0, 1) replaces torch.rand_like (tests)."""
+        G, dev = self.grid_size, self.density_grid_torso.device
+        ar = torch.arange(G, dtype=torch.int32, device=dev)
+        xx, yy = torch.meshgrid(ar, ar, indexing="ij")
+        coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1)], dim=-1)                        # [N, 2] in [0, G)
+        indices = (coords[:, 1] * G + coords[:, 0]).long()                                        # NOTE: xy transposed (renderer.py:789)
+        half = 1 / G
+        xys = (2 * coords.float() / (G - 1) - 1) * (1 - half)
+        xys = xys + ((torch.rand_like(xys) if noise is None else noise.to(dev)) * 2 - 1) * half
+        ind_was, self.training = self.training, True                                              # the refresh uses the frame's own code (renderer.py:777)
+        try:
+            h_const = self.frame_constants(pose.to(dev), index)
+        finally:
+            self.training = ind_was
+        if fused:
+            thresh_was, mean_was = self.density_thresh_torso, self.mean_density_torso
+            self.density_thresh_torso = self.mean_density_torso = -1e30                           # occupancy > -inf: evaluate every lattice point
+            try:
+                alphas = self.run_torso_fused(xys.contiguous(), None, 0, None, h_const=h_const)["torso_alpha"].view(-1)
+            finally:
+                self.density_thresh_torso, self.mean_density_torso = thresh_was, mean_was
+        else:
+            with torch.autocast("cuda", dtype=torch.float16, enabled=xys.is_cuda):
+                alphas = self.forward_torso(xys, h_const)[0].squeeze(1).float()
+        tmp = torch.zeros_like(self.density_grid_torso)
+        tmp[indices] = alphas
+        tmp = F.max_pool2d(tmp.view(1, 1, G, G), kernel_size=5, stride=1, padding=2).view(-1)
+        self.density_grid_torso.copy_(torch.maximum(self.density_grid_torso * decay, tmp))
+        self.mean_density_torso = torch.mean(self.density_grid_torso).item()
+        return self.mean_density_torso
+

@@ -113,3 +113,23 @@ def test_frame_renderer_with_torso_background():
     torch.cuda.synchronize()
     assert torch.equal(a, b) and torch.equal(a, c)
     assert not torch.equal(a, p) and float((a - p).abs().max()) > 0.05       # the torso changed the background pixels
+
+
+def test_torso_occupancy_refresh_fused_matches_reference_graph():
+    """TorsoModel.update_extra_state (renderer.py:768-809): the jittered 128^2 lattice through the fused kernel vs through forward_torso under autocast with
+    the same jitter: same density grid up to the fp16 chain (1e-2 of values in [0, 1]), same mean to 1e-3; EMA-max decay applied."""
+    import copy
+    m = _model(5)
+    m.density_grid_torso.fill_(0.02)
+    m2 = copy.deepcopy(m)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    noise = torch.rand(m.grid_size ** 2, 2, device="cuda", generator=g)
+    pose = _pose()
+    a = m.update_extra_state(pose, index=3, fused=True, noise=noise)
+    b = m2.update_extra_state(pose, index=3, fused=False, noise=noise)
+    torch.cuda.synchronize()
+    d = (m.density_grid_torso - m2.density_grid_torso).abs()
+    assert float(d.max()) < 1.5e-2 and float(d.median()) < 5e-4, (float(d.max()), float(d.median()))
+    assert abs(a - b) < 1e-3 and a == m.mean_density_torso
+    assert float(m.density_grid_torso.min()) >= 0.02 * 0.95 - 1e-7            # EMA-max: never below the decayed previous grid
+    assert m.density_thresh_torso == 0.01                                      # the temporary -inf threshold was restored
