@@ -122,3 +122,27 @@ def test_torso_model_state_dict_matches_reference_names_and_count():
     import pytest
     with pytest.raises(RuntimeError):                        # no CPU path
         m.run_torso_fused(c, None, 0, None, h_const=__import__("torch").zeros(50))
+
+
+def test_state_dicts_match_the_reference_network_class():
+    """Checkpoint compatibility pinned on the reference's OWN NeRFNetwork: tests/golden/ref_state_dict_keys.json lists every state_dict entry
+    (name, shape, dtype) of nerf_triplane/network.py:NeRFNetwork instantiated from /root/reference (tests/golden/make_ref_state_dict_keys.py).  HeadModel must
+    hold exactly the head entries; TorsoModel exactly what the torso stage adds."""
+    import json
+    import os
+    import torch
+    from b2nerf.model import HeadModel
+    from b2nerf.torso import TorsoModel
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_state_dict_keys.json")))
+    desc = lambda sd: {k: [list(v.shape), str(v.dtype)] for k, v in sd.items()}
+    for tag, dim in (("head_hubert", 1024), ("head_deepspeech", 29)):
+        assert desc(HeadModel(audio_in_dim=dim).state_dict()) == ref[tag], tag
+        assert sum(p.numel() for p in HeadModel(audio_in_dim=dim).parameters()) == ref[tag + "_n_params"]
+    extra = {k: v for k, v in ref["torso_hubert"].items() if k not in ref["head_hubert"]}
+    assert desc(TorsoModel().state_dict()) == extra
+    assert sum(p.numel() for p in TorsoModel().parameters()) == ref["torso_hubert_n_params"] - ref["head_hubert_n_params"]
+    # a reference-style checkpoint dict loads into both models
+    sd = {k: torch.zeros(s, dtype=getattr(torch, d.split(".")[1])) for k, (s, d) in ref["torso_hubert"].items()}
+    HeadModel(audio_in_dim=1024).load_state_dict(sd, strict=False)
+    missing, unexpected = TorsoModel().load_state_dict(sd, strict=False)
+    assert not missing
