@@ -241,7 +241,7 @@ def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536
                      if fused_head else "drop-in ops + torch autograd (MLPs via cuBLAS under autocast fp16)") + ", flat AdamW, flat-buffer NCCL all-reduce"}
 
 
-def torso_bench(dev, steps=20, warmup=5):
+def torso_bench(dev, steps=20, warmup=5, head=None):
     """Torso branch of a 512x512 frame (torso is OFF in the headline frame, BASELINE configs[1]): the fused kernel (csrc/fused_torso.cu)
     next to the reference's op-by-op graph on the drop-in encoders + torch Linear under autocast, same synthetic torso occupancy (a blob over ~1/3 of
     the image), CUDA events on the launching stream."""
@@ -283,8 +283,28 @@ def torso_bench(dev, steps=20, warmup=5):
         per_op_ms = timed(lambda: m.run_torso(coords, pose, 0, None))
         n_on = int(m.run_torso(coords, pose, 0, None)["mask"].sum())
     macs = 5440                                            # 34*32 + 32*32 + 32*2 + 66*32 + 32*32 + 32*4 per torso pixel (constant inputs folded into a bias)
+    frames_with_torso = None
+    if head is not None:                                   # whole frames with the torso behind the head: FrameRenderer(torso=...) on every pipeline slot
+        model, frames, auds = head
+        from b2nerf.render import FramePipeline
+        pipe = FramePipeline(model, N_RAYS, depth=6, torso=m, bg_coords=coords)
+        for sl in pipe.slots:
+            sl.set_torso_pose(pose)
+        k = [0]
+
+        def one():
+            f = k[0] % len(frames); k[0] += 1
+            pipe.submit_device(frames[f][0], frames[f][1], auds[f])
+
+        for _ in range(12):
+            one()
+        pipe.drain(); torch.cuda.synchronize(); e0.record()
+        for _ in range(60):
+            one()
+        pipe.drain(); e1.record(); torch.cuda.synchronize()
+        frames_with_torso = 60 / (e0.elapsed_time(e1) * 1e-3)
     return {"pixels": HW * HW, "torso_pixels": n_on, "fused_ms_per_frame": fused_ms, "fused_eager_call_ms": fused_eager_ms, "per_op_ms_per_frame": per_op_ms,
-            "fused_gflops": 2.0 * macs * n_on / (fused_ms * 1e-3) / 1e9,
+            "fused_gflops": 2.0 * macs * n_on / (fused_ms * 1e-3) / 1e9, "frames_per_sec_head_plus_torso": frames_with_torso,
             "note": "k_torso_frame: occupancy test + freq encoding + deform MLP + tiled fp16 grid + torso MLP + blend in one launch (CUDA cores, thread = pixel); "
                     "per-op = run_torso on the drop-in encoders + torch Linear under autocast (~25 launches)"}
 
@@ -357,6 +377,12 @@ def run_gpu_arm(args, rank, world, local_rank):
         train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(4, min(args.steps, 20)), warmup=max(args.warmup, 18), eager=args.train_eager, fused_head=not args.train_unfused)
     if rank != 0:
         return
+    torso_info = None
+    if not args.no_train:                                  # a secondary leg: never lose the headline line over it
+        try:
+            torso_info = torso_bench(dev, head=(model, frames, auds))
+        except Exception as e:                             # noqa: BLE001
+            torso_info = {"error": f"{type(e).__name__}: {e}"}
     img = out_host.numpy()
     assert np.isfinite(img).all() and 0.0 < float(img.mean()) <= 1.0
     if r.loop_graph is not None:        # device-controlled WHILE loop: kernels per frame = fixed + per-iteration x iterations actually executed
@@ -395,7 +421,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     }
     if not args.no_train:
         line["train"] = train_info
-        line["torso"] = torso_bench(dev)
+        line["torso"] = torso_info
     if world == 1 and not args.no_cpu:
         rows = 32
         fps, sec, ns = cpu_frames_per_sec(rows, 2, 1)
