@@ -366,6 +366,13 @@ class HeadModel(nn.Module):
                torch.cuda.current_stream().cuda_stream)
         return image, ws, depth
 
+    def load_state_dict(self, *args, **kwargs):
+        """The packed model (operand images + corner-quad image of the tables) is a snapshot: refresh it when new weights arrive."""
+        r = super().load_state_dict(*args, **kwargs)
+        if self._handle is not None and next(self.parameters()).is_cuda:
+            self.pack()
+        return r
+
     def cache_host_constants(self):
         """Read aabb_infer once (a D2H copy) so render_frame never synchronises."""
         self._aabb_host = (ctypes.c_float * 6)(*[float(v) for v in self.aabb_infer.tolist()])

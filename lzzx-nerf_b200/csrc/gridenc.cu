@@ -726,7 +726,11 @@ int b2n_triplane_grid_backward(const float *grad_planes, const float *xyz, const
         const uint32_t per = ceil_div<uint32_t>(M, slices);
         uint32_t nbits = 1;
         while (nbits < 31 && (1ull << nbits) < 4ull * per) nbits++;       // at most 4 contributions per sample and slot
-        B2N_REQUIRE(nbits <= 24, "triplane_grid_backward: M=%u too large for the fixed-point kernel", M);
+        while (nbits > 24) {                                               // huge batches: more slices keep the per-slot sums inside 32 bits
+            slices *= 2;
+            nbits = 1;
+            while (nbits < 31 && (1ull << nbits) < 4ull * ceil_div<uint32_t>(M, slices)) nbits++;
+        }
         const int K = min(62 - 2 * (int)nbits, 30);                        // V = rint(t * 2^(K - e)) must also fit an int32
         k_triplane_bwd_fix<<<dim3(slices, L, 3), GF_THREADS, smem, st>>>(grad_planes, xyz, offsets, grad_xy, grad_yz, grad_xz, M, L, slices, S, H, bound, inv, mx, K,
                                                                            32u - nbits);

@@ -403,3 +403,17 @@ def test_linear_wgrad_batch_matches_single_launches():
         scale = float(ref.abs().max())
         assert float((got - ref).abs().max()) <= 1e-4 * scale + 1e-3, ((o, i), float((got - ref).abs().max()), scale)
         off += o * i
+
+
+def test_load_state_dict_refreshes_the_packed_model():
+    """The packed model (fp16 operand images + corner-quad image) is a snapshot of weights and tables: load_state_dict on a packed HeadModel re-packs it."""
+    a, b = _model(7, 1.0, True), _model(8, 1.0, True)
+    x, d = _samples(5000, 3)
+    enc_a = torch.randn(1, 32, device="cuda") * 0.5; c = a.individual_codes[1:2].detach().clone(); e = torch.tensor([[0.5]], device="cuda")
+    a.pack(); b.pack()
+    before = a(x, d, enc_a, c, e)[1].clone()
+    want = b(x, d, enc_a, c, e)[1].clone()
+    a.load_state_dict(b.state_dict())
+    got = a(x, d, enc_a, c, e)[1].clone()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and not torch.equal(before, want)
