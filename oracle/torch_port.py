@@ -95,6 +95,57 @@ def head_forward(p, x, d, enc_a, c, e, testing=True):
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
+# torso branch: NeRFRenderer.run_torso (renderer.py:572-631) + NeRFNetwork.forward_torso (network.py:170-205), fp32
+# ---------------------------------------------------------------------------------------------------------------------------
+def freq_encode(x, degree):
+    """freqencoder.cu:48-57: [x | sin(2^f x), cos(2^f x) interleaved per frequency]; output index c >= D: col = c // D - 1, d = c % D, f = col // 2."""
+    outs = [x]
+    for f in range(degree):
+        outs += [torch.sin(x * 2.0 ** f), torch.cos(x * 2.0 ** f)]
+    return torch.cat(outs, dim=1)
+
+
+def tiled_grid_encode_2d(u, table, offsets, S, H):
+    """gridencoder.cu:54-72,124-175 with gridtype = tiled, D = 2, C = 2, align_corners = False; fp32.  u [B,2] in [0,1]; table [sO,2] -> [B, 2 L]."""
+    B, L = u.shape[0], len(offsets) - 1
+    out = torch.zeros(B, L, 2, dtype=torch.float32)
+    for lvl in range(L):
+        size = offsets[lvl + 1] - offsets[lvl]
+        scale = float(np.float32(np.exp2(np.float32(lvl) * np.float32(S))) * np.float32(H) - np.float32(1.0))
+        stride = int(math.ceil(scale)) + 2
+        pos = u * scale + 0.5
+        pg = pos.floor()
+        fr = pos - pg
+        x, y = pg[:, 0].long(), pg[:, 1].long()
+        tab = table[offsets[lvl]:offsets[lvl + 1]]
+        for cy in (0, 1):
+            for cx in (0, 1):
+                idx = (x + cx) + ((y + cy) * stride if stride <= size else 0)
+                w = (fr[:, 0] if cx else 1 - fr[:, 0]) * (fr[:, 1] if cy else 1 - fr[:, 1])
+                out[:, lvl] += w[:, None] * tab[idx % size]
+    return out.reshape(B, 2 * L)
+
+
+def torso_forward(p, bg_coords, h_const, density_grid, grid_size, thresh, bg_color=None, shrink=0.8):
+    """p: fp32 CPU tensors under the reference's names (torso_deform_net.net.*.weight, torso_encoder.embeddings / .offsets, torso_net.net.*.weight) + "S", "H";
+    bg_coords [N,2]; h_const [50] = [anchor encoding | individual code].  Returns (bg [N,3], alpha [N], mask [N])."""
+    N = bg_coords.shape[0]
+    occ = torch.nn.functional.grid_sample(density_grid.view(1, 1, grid_size, grid_size), bg_coords.view(1, -1, 1, 2), align_corners=True).view(-1)
+    mask = occ > thresh
+    x = bg_coords * shrink
+    enc = freq_encode(x, 8)
+    h = torch.cat([enc, h_const.view(1, -1).expand(N, -1)], dim=1)
+    dx = _mlp(h, [p[f"torso_deform_net.net.{i}.weight"] for i in range(3)])
+    u = ((x + dx).clamp(-1, 1) + 1) / 2
+    g = tiled_grid_encode_2d(u, p["torso_encoder.embeddings"], p["torso_encoder.offsets"].tolist(), p["S"], p["H"])
+    o = _mlp(torch.cat([g, h], dim=1), [p[f"torso_net.net.{i}.weight"] for i in range(3)])
+    alpha = torch.where(mask, torch.sigmoid(o[:, 0]) * 1.002 - 0.001, torch.zeros(()))
+    color = torch.where(mask[:, None], torch.sigmoid(o[:, 1:]) * 1.002 - 0.001, torch.zeros(()))
+    bg = torch.ones(N, 3) if bg_color is None else bg_color.expand(N, 3)
+    return color * alpha[:, None] + bg * (1 - alpha[:, None]), alpha, mask
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
 # marching / compositing
 # ---------------------------------------------------------------------------------------------------------------------------
 def near_far_from_aabb(o, d, aabb, min_near):

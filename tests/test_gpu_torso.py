@@ -163,3 +163,28 @@ def test_torso_training_step_through_the_per_op_graph():
         scaler.step(opt); scaler.update()
         losses.append(float(loss.detach()))
     assert losses[-1] < losses[0], losses
+
+
+def test_fused_torso_against_the_cpu_port():
+    """The fused torso kernel against the oracle's fp32 CPU restatement of run_torso / forward_torso (oracle/torch_port.py:torso_forward) on a 96x96 image:
+    fp16 operands / activations with fp32 accumulation vs plain fp32 -> agreement at the 1e-2 level, identical occupancy mask up to threshold ties."""
+    import math
+    from oracle import torch_port
+    from b2nerf.torso import get_bg_coords
+    m = _model(9)
+    coords = get_bg_coords(96, 96, "cuda")
+    pose = _pose()
+    hc = m.frame_constants(pose, 0).detach()
+    out = m.run_torso_fused(coords, pose, 0, None, h_const=hc)
+    p = {k: v.detach().float().cpu() for k, v in m.state_dict().items() if v.dtype.is_floating_point}
+    p["torso_encoder.offsets"] = m.torso_encoder.offsets.cpu()
+    p["S"], p["H"] = float(np.float32(math.log2(m.torso_encoder.per_level_scale))), m.torso_encoder.base_resolution
+    bg, alpha, mask = torch_port.torso_forward(p, coords.view(-1, 2).cpu(), hc.view(-1).cpu(), m.density_grid_torso.cpu(), m.grid_size, m.density_thresh(),
+                                               shrink=m.torso_shrink)
+    on = out["torso_alpha"].view(-1).cpu() != 0
+    assert int((on != mask).sum()) <= 2
+    both = on & mask
+    da = (out["torso_alpha"].view(-1).cpu() - alpha).abs()[both]
+    db = (out["bg_color"].cpu() - bg).abs()[both]
+    assert float(da.mean()) < 3e-3 and float(da.max()) < 3e-2, (float(da.mean()), float(da.max()))
+    assert float(db.mean()) < 3e-3 and float(db.max()) < 3e-2, (float(db.mean()), float(db.max()))
