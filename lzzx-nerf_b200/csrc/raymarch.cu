@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_count(
         const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
         float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
         const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
-        int32_t *__restrict__ rays, const int32_t *__restrict__ counter, int32_t *__restrict__ cta_totals) {
+        int32_t *__restrict__ rays, const int32_t *__restrict__ counter, int32_t *__restrict__ cta_totals, float *__restrict__ t_cache) {
     const uint32_t n = blockIdx.x * MT_THREADS + threadIdx.x;
     uint32_t num = 0;
     if (n < N) {
@@ -132,8 +132,10 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_count(
         r.init(rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H, fars[n]);
         float t = r.perturb(nears[n], noises[n]);
         DdaSample s;
+        // t_cache [max_steps][N] (coalesced over rays): the parameter t of every sample, so that the write pass does not walk the bitfield again —
+        // a sample's position and step are functions of (ray, t) alone
         while (t < r.far && num < max_steps) {
-            if (r.probe(grid, t, s)) { num++; t = __fadd_rn(t, s.dt); }
+            if (r.probe(grid, t, s)) { if (t_cache) t_cache[(size_t)num * N + n] = t; num++; t = __fadd_rn(t, s.dt); }
         }
         rays[3 * (size_t)n] = (int32_t)n;
         rays[3 * (size_t)n + 2] = (int32_t)num;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_write(
         float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
         const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
         float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas,
-        int32_t *__restrict__ rays, int32_t *__restrict__ counter, const int32_t *__restrict__ cta_totals) {
+        int32_t *__restrict__ rays, int32_t *__restrict__ counter, const int32_t *__restrict__ cta_totals, const float *__restrict__ t_cache) {
     __shared__ uint32_t red[MT_THREADS / 32];
     __shared__ uint32_t s_base;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -201,8 +203,21 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_write(
     if (num == 0 || off + num > M) return;       // raymarching.cu:456-457
     DdaRay r;
     r.init(rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H, fars[n]);
-    float t = r.perturb(nears[n], noises[n]);
     float *px = xyzs + 3 * (size_t)off, *pd = dirs + 3 * (size_t)off, *pl = deltas + 2 * (size_t)off;
+    if (t_cache) {                               // replay the recorded parameters: same expressions as DdaRay::probe for an occupied cell
+        for (uint32_t k = 0; k < num; k++) {
+            const float tk = __ldcs(t_cache + (size_t)k * N + n);
+            const float dt = r.step_of(tk);
+            px[0] = clampf(__fmaf_rn(tk, r.dx, r.ox), -bound, bound);
+            px[1] = clampf(__fmaf_rn(tk, r.dy, r.oy), -bound, bound);
+            px[2] = clampf(__fmaf_rn(tk, r.dz, r.oz), -bound, bound);
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            pl[0] = dt; pl[1] = __fadd_rn(tk, dt);
+            px += 3; pd += 3; pl += 2;
+        }
+        return;
+    }
+    float t = r.perturb(nears[n], noises[n]);
     uint32_t step = 0;
     DdaSample s;
     while (t < r.far && step < num) {
@@ -338,11 +353,14 @@ int b2n_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t
     const uint32_t ctas = ceil_div<uint32_t>(N, MT_THREADS);
     int32_t *totals = (int32_t *)scratch(sizeof(int32_t) * (size_t)(ctas + 1), 0);
     B2N_REQUIRE(totals, "march_rays_train: scratch allocation failed");
+    // per-sample t cache between the two passes (max_steps x N floats: 4 MB for the 65 536-ray step); large max_steps fall back to re-marching
+    float *t_cache = nullptr;
+    if (max_steps <= 64 && (uint64_t)max_steps * N <= (64ull << 20)) t_cache = (float *)scratch(sizeof(float) * (size_t)max_steps * N, 2);
     k_march_train_count<<<ctas, MT_THREADS, 0, as_stream(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
-                                                                      nears, fars, noises, rays, counter, totals);
+                                                                      nears, fars, noises, rays, counter, totals, t_cache);
     if (check_launch("march_rays_train(count)")) return 1;
     k_march_train_write<<<ctas, MT_THREADS, 0, as_stream(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
-                                                                      nears, fars, noises, xyzs, dirs, deltas, rays, counter, totals);
+                                                                      nears, fars, noises, xyzs, dirs, deltas, rays, counter, totals, t_cache);
     return check_launch("march_rays_train(write)");
 }
 
