@@ -157,7 +157,7 @@ def run_reference_arm(args, rank):
 def head_kernel_profile(model, renderer, frames, auds, n_frames, repeats=5):
     """Separate instrumented pass (no CUDA graph; CUDA events cannot be recorded inside a replayed graph).  For each of `n_frames` frames the
     reference loop is run once on the per-op kernels; every loop iteration's fused-head launch is then timed in isolation: one CUDA-event pair on the
-    launching stream around `repeats` back-to-back launches of that same call (so no host gap is inside the pair).  Returns (sum of average launch
+    launching stream around `repeats` back-to-back launches of that same call, replayed from a CUDA graph (so no host gap is inside the pair).  Returns (sum of average launch
     durations in ms, launches, samples evaluated)."""
     import raymarching
     stream = torch.cuda.current_stream()
@@ -185,11 +185,20 @@ def head_kernel_profile(model, renderer, frames, auds, n_frames, repeats=5):
                 nv = torch.tensor([m_eval], dtype=torch.int32, device=dev)
                 torch.cuda.synchronize(dev)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                # the repeats are replayed from a small CUDA graph: launched one by one from Python, the ~30 us of host time per call would sit inside the
+                # event pair whenever the kernel is shorter than that (the late, small loop iterations) and the host is busy
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(repeats):
+                        model(xyzs, dirs, enc_a, renderer.ind_code, renderer.eye, n_valid=nv, out=(sig, rgb, aa, ae, un))
+                stream = torch.cuda.current_stream()
+                g.replay()                                  # warm replay (graph upload)
+                torch.cuda.synchronize(dev)
                 e0.record(stream)
-                for _ in range(repeats):
-                    model(xyzs, dirs, enc_a, renderer.ind_code, renderer.eye, n_valid=nv, out=(sig, rgb, aa, ae, un))
+                g.replay()
                 e1.record(stream)
                 e1.synchronize()
+                del g
                 total_ms += e0.elapsed_time(e1) / repeats; launches += 1; samples += m_eval
                 raymarching.composite_rays_triplane(n_alive, n_step, alive, rays_t, sig, rgb, deltas, aa, ae, un, ws, depth, image, sa, se, su, kw["T_thresh"])
                 alive = alive[alive >= 0]
