@@ -41,6 +41,10 @@ struct FrameWs {            // carved out of the caller's workspace
 };
 
 constexpr uint32_t FR_THREADS = 128;
+// The march kernel runs NEXT TO another frame's head kernel, whose one CTA per SM leaves 4096 of the 65 536 registers (384 threads x 160) and ~5 KB of shared
+// memory: a 128-thread CTA at 61 -> 64 registers does not fit (8192), a 64-thread CTA does — with 128 threads the march of one frame could only start in the
+// tail of another frame's head launch.  (The composite kernel is 32 registers x 128 threads = 4096: it already fits.)
+constexpr uint32_t FM_THREADS = 64;
 constexpr uint32_t FR_MAX_ITERS = 64;
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -173,11 +177,11 @@ __device__ __forceinline__ bool last_block_done(int32_t *ticket) {
 // reference's composite would see delta == 0 in their first slot, add nothing and drop them, raymarching.cu:2193, 2235) — they are
 // dropped HERE, so the head network only evaluates slots of rays that still contribute: the surviving ray ids and their n_step slots are
 // written compacted (alive_mid / xyzs / dirs / deltas); slots a ray did not fill are zero (the reference's torch.zeros, raymarching.py:384).
-__global__ void __launch_bounds__(FR_THREADS) k_frame_march(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+__global__ void __launch_bounds__(FM_THREADS) k_frame_march(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
                                                              float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, FrameWs w) {
     const FrameCtrl c = w.ctrl[0];
     if (c.done) return;
-    const uint32_t n = blockIdx.x * FR_THREADS + threadIdx.x;
+    const uint32_t n = blockIdx.x * FM_THREADS + threadIdx.x;
     const uint32_t n_step = (uint32_t)c.n_step;
     const bool valid = n < (uint32_t)c.n_alive;
     float ts[8], dts[8];
@@ -360,7 +364,7 @@ static int enqueue_init(const FramePlan &p, cudaStream_t st) {
 // one loop iteration: march (+ drop rays without samples) -> fused head -> composite (+ survivor list, next control block)
 static int enqueue_iteration(const FramePlan &p, cudaStream_t st, cudaGraphConditionalHandle handle, int use_handle) {
     const uint32_t ctas = ceil_div<uint32_t>(p.N, FR_THREADS);
-    k_frame_march<<<ctas, FR_THREADS, 0, st>>>(p.rays_o, p.rays_d, p.bitfield, p.cfg.bound, p.cfg.dt_gamma, p.cfg.max_steps, p.cfg.cascade, p.cfg.grid_size, p.w);
+    k_frame_march<<<ceil_div<uint32_t>(p.N, FM_THREADS), FM_THREADS, 0, st>>>(p.rays_o, p.rays_d, p.bitfield, p.cfg.bound, p.cfg.dt_gamma, p.cfg.max_steps, p.cfg.cascade, p.cfg.grid_size, p.w);
     if (check_launch("render_frame(march)")) return 1;
     if (int rc = head_forward_on_model(p.m, p.w.xyzs, p.w.dirs, p.N, p.enc_a, p.ind_code, p.eye, &p.w.ctrl[0].n_samples, p.cfg.density_scale, p.w.sigmas, p.w.rgbs,
                                        p.w.amb_aud, p.w.amb_eye, p.w.unc, st, p.w.deltas)) return rc;
