@@ -139,7 +139,12 @@ def cpu_frames_per_sec(rows, steps, warmup):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
+    # bounded sample per step: a 64-row band of the frame, shrunk (multiples of 8 rows) when --steps is large so that the whole run stays within ~3 minutes
     rows = 64
+    _, probe_sec, _ = cpu_frames_per_sec(rows, 1, 1)
+    budget = 180.0 / max(1, args.steps + max(args.warmup, 1))
+    if probe_sec > budget:
+        rows = int(max(8, min(64, (64 * budget / probe_sec) // 8 * 8)))
     fps, sec, ns = cpu_frames_per_sec(rows, args.steps, max(args.warmup, 1))
     cores = os.cpu_count()
     sample = f"central {rows}-row band of the 512x512 frame ({rows * HW} of {N_RAYS} rays, {ns} samples) per step, pure-PyTorch fp32 port (oracle/torch_port.py)"
