@@ -60,6 +60,9 @@ class FrameRenderer:
         model.pack()
         if use_graph:
             try:
+                import os
+                if os.environ.get("B2N_FRAME_NO_WHILE") == "1":       # measurement switch: the fixed 16-iteration sequence captured as an ordinary graph
+                    raise RuntimeError("WHILE-node graph disabled by B2N_FRAME_NO_WHILE")
                 self._build_loop_graph()
             except RuntimeError as e:          # conditional graph nodes unavailable: capture the fixed sequence instead (still a GPU path)
                 self.loop_graph_error = str(e)
