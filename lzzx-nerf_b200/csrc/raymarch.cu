@@ -355,7 +355,12 @@ int b2n_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t
     B2N_REQUIRE(totals, "march_rays_train: scratch allocation failed");
     // per-sample t cache between the two passes (max_steps x N floats: 4 MB for the 65 536-ray step); large max_steps fall back to re-marching
     float *t_cache = nullptr;
-    if (max_steps <= 64 && (uint64_t)max_steps * N <= (64ull << 20)) t_cache = (float *)scratch(sizeof(float) * (size_t)max_steps * N, 2);
+    // (at least 16 MB is requested: the grow-only scratch block then keeps its address for every batch up to 262 144 rays x 16 steps, so a CUDA graph that
+    // captured this call is not left pointing at a freed block when a later, larger batch comes along)
+    if (max_steps <= 64 && (uint64_t)max_steps * N <= (64ull << 20)) {
+        const size_t need = sizeof(float) * (size_t)max_steps * N;
+        t_cache = (float *)scratch(need > (16u << 20) ? need : (size_t)(16u << 20), 2);
+    }
     k_march_train_count<<<ctas, MT_THREADS, 0, as_stream(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
                                                                       nears, fars, noises, rays, counter, totals, t_cache);
     if (check_launch("march_rays_train(count)")) return 1;
