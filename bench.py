@@ -4,14 +4,16 @@
     python bench.py --gpus N --steps K --warmup W            # this repo (libb2nerf.so); torchrun launches it for N > 1
     python bench.py --impl reference --gpus N --steps K ...   # the repo's ops as pure PyTorch on the host cores (CPU arm)
 
-Workload at every N (BASELINE.json configs[1] / configs[3]): one step = one 512x512 talking-head frame per GPU — AudioNet+AudioAttNet,
-near/far, the 16-step occupancy march / tri-plane encode / head MLPs / composite loop, background blend — random-init weights, the
-synthetic head-sized density blob of SURVEY §8d, `max_steps 16, dt_gamma 1/256, bound 1`.  Frames are independent, so N GPUs render
-N frames per step (weak scaling, no data-path collective).
+Workload at every N (BASELINE.json configs[1] / configs[3]): one step = one BATCH of FRAMES_PER_STEP 512x512 talking-head frames per GPU (three of the
+reference's inference-loader batches of 32, provider_for_inference.py:727) — per frame: AudioNet+AudioAttNet, near/far, the 16-step occupancy march /
+tri-plane encode / head MLPs / composite loop, background blend — random-init weights, the synthetic head-sized density blob of SURVEY §8d,
+`max_steps 16, dt_gamma 1/256, bound 1`.  Frames are independent, so N GPUs render N batches per step (weak scaling, no data-path collective).  A batch per
+step keeps the timed region of the driver's 20-step run above half a second at every N (a 20-frame region is 7 ms: its max-over-ranks is launch jitter).
 
-One JSON line on stdout (rank 0).  `value` = frames/s with the rays already in HBM; `e2e` = the same through FrameRenderer.render_host
-with pinned HOST buffers (rays + audio window up, fp32 image down, every frame); `roofline` = the fused tcgen05 head kernel;
-`cpu_baseline` = oracle/torch_port.py on a bounded sample of the same frame.
+One JSON line on stdout (rank 0).  `value` = frames/s with the rays already in HBM; `e2e` = the same through FramePipeline.submit_host_pose with pinned HOST
+buffers (4x4 pose + audio window up, RGB24 frame down, every frame); `roofline` = the fused tcgen05 head kernel (isolated timing -> burst peak), `kernels` =
+per-kernel rooflines of the per-op kernels; `cpu_baseline` = oracle/torch_port.py on a bounded, evenly strided sample of the same frame;
+`reference_on_b200` = the unmodified reference model on its own CUDA extensions on this GPU (profiles/reference_on_b200.py), when staged.
 """
 import argparse
 import json
@@ -32,6 +34,8 @@ import torch  # noqa: E402
 HW = 512
 N_RAYS = HW * HW
 POOL = 24                      # distinct frames cycled through: 24 x 6.3 MB of rays = 151 MB > 126 MB L2
+FRAMES_PER_STEP = 96           # one step = 3 inference-loader batches of 32 frames (provider_for_inference.py:727)
+ROW_STRIDE = 8                 # CPU arms: every 8th row of the frame (64 of 512 rows, evenly spread: the sample has the whole frame's samples-per-ray mix)
 METRIC = "infer_512x512_frames_per_sec"
 MACS_PER_SAMPLE_INFER = 23184  # SURVEY §8a a7 (no unc_net at inference)
 
@@ -110,21 +114,22 @@ def build_model(device=None):
 # CPU arm: the repo's ops as pure PyTorch on the host cores
 # ------------------------------------------------------------------------------------------------------------------------------
 def cpu_frames_per_sec(rows, steps, warmup):
-    """Times oracle/torch_port.render_frame on a `rows`-row band of the 512x512 frame; returns (frames/s equivalent, seconds/step, samples)."""
+    """Times oracle/torch_port.render_frame on `rows` rows of the 512x512 frame taken at an even stride over the whole frame (so the sample has the frame's own mix
+    of empty and dense rays); returns (frames/s equivalent, seconds/step, samples)."""
     from oracle import torch_port as tp
     from b2nerf import scene
     torch.set_num_threads(os.cpu_count())
     m = build_model()
     p = tp.params_from_state_dict(m.state_dict())
     bf = torch.from_numpy(scene.bitfield_from_grid(scene.density_grid()))
-    r0 = (HW - rows) // 2
+    sel = torch.arange(rows) * (HW // rows) + (HW // rows) // 2
     aabb = torch.from_numpy(scene.AABB)
     times, ns = [], 0
     with torch.no_grad():
         for s in range(warmup + steps):
             o, d = scene.frame_rays(frame=s)
-            o = torch.from_numpy(o).view(HW, HW, 3)[r0:r0 + rows].reshape(-1, 3)
-            d = torch.from_numpy(d).view(HW, HW, 3)[r0:r0 + rows].reshape(-1, 3)
+            o = torch.from_numpy(o).view(HW, HW, 3)[sel].reshape(-1, 3)
+            d = torch.from_numpy(d).view(HW, HW, 3)[sel].reshape(-1, 3)
             auds = torch.from_numpy(scene.audio_window(frame=s))
             t0 = time.perf_counter()
             enc_a = m.encode_audio(auds)[0]
@@ -139,18 +144,21 @@ def cpu_frames_per_sec(rows, steps, warmup):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    # bounded sample per step: a 64-row band of the frame, shrunk (multiples of 8 rows) when --steps is large so that the whole run stays within ~3 minutes
-    rows = 64
+    # bounded sample per step: every 8th row of the frame (64 rows), thinned further (powers of two) when --steps is large so that the whole run stays within ~3 minutes
+    rows = HW // ROW_STRIDE
     _, probe_sec, _ = cpu_frames_per_sec(rows, 1, 1)
     budget = 180.0 / max(1, args.steps + max(args.warmup, 1))
-    if probe_sec > budget:
-        rows = int(max(8, min(64, (64 * budget / probe_sec) // 8 * 8)))
+    while probe_sec * rows / (HW // ROW_STRIDE) > budget and rows > 8:
+        rows //= 2
     fps, sec, ns = cpu_frames_per_sec(rows, args.steps, max(args.warmup, 1))
     cores = os.cpu_count()
-    sample = f"central {rows}-row band of the 512x512 frame ({rows * HW} of {N_RAYS} rays, {ns} samples) per step, pure-PyTorch fp32 port (oracle/torch_port.py)"
+    sample = (f"{rows} rows of the 512x512 frame at an even stride of {HW // rows} ({rows * HW} of {N_RAYS} rays, {ns} samples, x{HW // rows} extrapolation) per step, "
+              f"pure-PyTorch fp32 port (oracle/torch_port.py)")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "infer_512x512_frame", "note": "the reference has no CPU path for these ops (SURVEY §8d); this arm is the pure-PyTorch port on host cores"},
+            "config": {"workload": "infer_512x512_frame", "sample_rows": rows, "extrapolation_factor": HW // rows,
+                       "note": "the reference has no CPU path for these ops (SURVEY §8d); this arm is the pure-PyTorch port on host cores, timed on an evenly strided "
+                               "subset of the frame's rows and scaled by rows"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -224,22 +232,22 @@ def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536
     for s in range(4):
         o, d = scene.train_rays(step=rank * 100 + s, n=n_rays)
         batches.append((torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev), torch.from_numpy(scene.audio_window(rank * 100 + s)).to(dev),
-                        torch.rand(n_rays, 3, device=dev)))
+                        torch.rand(n_rays, 3, device=dev), torch.rand(n_rays, device=dev) < 0.5))         # rays, audio window, target colours, face mask
     for s in range(warmup):
         b = batches[s % 4]
-        tr.train_step(b[0], b[1], b[2], b[3], index=s)
+        tr.train_step(b[0], b[1], b[2], b[3], index=s, face_mask=b[4])
         if s == 15:
             tr.update_mean_count()            # the reference's warm-up: 16 steps with worst-case buffers, then the mean_count estimate
     step_fn = tr.train_step if eager else tr.train_step_graphed
-    for s in range(4):                    # graph capture (if any) + steady state
+    for s in range(34):                   # graph captures (the plain step and the every-16th-step variant with the smoothness regulariser) + steady state
         b = batches[s % 4]
-        step_fn(b[0], b[1], b[2], b[3], index=s)
+        step_fn(b[0], b[1], b[2], b[3], index=s, face_mask=b[4])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(steps):
         b = batches[s % 4]
-        loss, m_buf = step_fn(b[0], b[1], b[2], b[3], index=s)
+        loss, m_buf = step_fn(b[0], b[1], b[2], b[3], index=s, face_mask=b[4])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -249,7 +257,9 @@ def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return {"metric": "train_rays_per_sec", "value": world * steps * n_rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": n_rays,
-            "samples_per_step_buffer": int(m_buf), "loss": float(loss), "grad_allreduce_bytes": tr.grads.nbytes() if world > 1 else 0,
+            "samples_per_step_buffer": int(m_buf), "loss": float(loss), "grad_allreduce_bytes": tr.grads.nbytes() if world > 1 else 0, "steps_timed": steps,
+            "objective": "TrainerUtil.py:238-363 head branch: uncertainty-weighted MSE + loss_u + static-uncertainty + entropy(1e-4) + masked / ramped ambient terms, "
+                         "smoothness regulariser on every 16th step (two more network passes); AdamW groups of network.py:332-356, LambdaLR stepped every iteration",
             "path": ("eager: " if eager else "forward + backward + all-reduce replayed from one CUDA graph: ") +
                     ("march / composite ops + fused head forward (activations kept) + fused head backward-data + tcgen05 weight-gradient kernel + privatised grid backward"
                      if fused_head else "drop-in ops + torch autograd (MLPs via cuBLAS under autocast fp16)") + ", flat AdamW, flat-buffer NCCL all-reduce"}
@@ -323,6 +333,18 @@ def torso_bench(dev, steps=20, warmup=5, head=None):
                     "per-op = run_torso on the drop-in encoders + torch Linear under autocast (~25 launches)"}
 
 
+def reference_on_b200():
+    """The number to beat: the unmodified reference model on its own CUDA extensions on this GPU, in a separate process (its packages shadow the
+    drop-ins).  Needs oracle/_ref_py + oracle/_ref (staged / built in the build container, shipped with the snapshot)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "reference_on_b200.py"), "--frames", "20", "--steps", "20"], capture_output=True, text=True,
+                           timeout=600)
+        last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+        return json.loads(last[-1]) if last else {"unavailable": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:                                 # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     from b2nerf import lib
     from b2nerf.render import FramePipeline
@@ -354,14 +376,15 @@ def run_gpu_arm(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     def timed(fn, steps, warmup):
-        for s in range(warmup):
+        """`fn(k)` submits frame k; a step is FRAMES_PER_STEP frames."""
+        for s in range(warmup * FRAMES_PER_STEP):
             fn(s)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = L.launch_count()
         e0.record()
-        for s in range(steps):
-            fn(warmup + s)
+        for s in range(steps * FRAMES_PER_STEP):
+            fn(warmup * FRAMES_PER_STEP + s)
         pipe.drain()                     # the timing stream waits for every frame in flight
         e1.record()
         barrier()
@@ -388,7 +411,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         pose_ms, _ = timed(lambda s: pipe.submit_host_pose(host_p[s % POOL], host_a[s % POOL], out_u8[s % pipe.depth]), args.steps, args.warmup)
     train_info = None
     if not args.no_train:
-        train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(4, min(args.steps, 20)), warmup=max(args.warmup, 18), eager=args.train_eager, fused_head=not args.train_unfused)
+        train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(64, args.steps * 32), warmup=max(args.warmup, 18), eager=args.train_eager,
+                                 fused_head=not args.train_unfused)
     if rank != 0:
         return
     torso_info = None
@@ -401,39 +425,42 @@ def run_gpu_arm(args, rank, world, local_rank):
     assert np.isfinite(img).all() and 0.0 < float(img.mean()) <= 1.0
     if r.loop_graph is not None:        # device-controlled WHILE loop: kernels per frame = fixed + per-iteration x iterations actually executed
         iters = r.last_iterations()
-        gpu_launches = int((r.kernels_fixed + r.kernels_per_iteration * iters) * args.steps)
+        gpu_launches = int((r.kernels_fixed + r.kernels_per_iteration * iters) * args.steps * FRAMES_PER_STEP)
         loop_mode = f"one CUDA graph per frame, WHILE conditional node, {iters} iterations executed in the last frame"
     elif r.graph is not None:
-        gpu_launches, loop_mode = int(r.launches_per_frame * args.steps), "torch CUDA graph of the fixed 16-iteration sequence"
+        gpu_launches, loop_mode = int(r.launches_per_frame * args.steps * FRAMES_PER_STEP), "torch CUDA graph of the fixed 16-iteration sequence"
     else:
         gpu_launches, loop_mode = int(launches), "eager launches"
-    value = world * args.steps / (dev_ms * 1e-3)
-    e2e = world * args.steps / (e2e_ms * 1e-3)
-    e2e_rays = {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": r.h2d_bytes(), "d2h_bytes_per_step": r.d2h_bytes(), "ms_per_step": e2e_ms / args.steps,
+    n_frames = args.steps * FRAMES_PER_STEP
+    value = world * n_frames / (dev_ms * 1e-3)
+    e2e = world * n_frames / (e2e_ms * 1e-3)
+    e2e_rays = {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": FRAMES_PER_STEP * r.h2d_bytes(), "d2h_bytes_per_step": FRAMES_PER_STEP * r.d2h_bytes(),
+                "ms_per_step": e2e_ms / args.steps,
                 "api": "FramePipeline.submit_host: pinned rays_o / rays_d / audio window in, pinned float image out"}
     pk, pk_src = peaks()
     head_ms, head_launches, head_samples = head_kernel_profile(model, r, frames, auds, min(args.steps, 8))
     flops = 2.0 * MACS_PER_SAMPLE_INFER * head_samples
     achieved = flops / (head_ms * 1e-3) / 1e12
-    peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
+    peak = float(pk.get("bf16_tflops", pk.get("bf16_tflops_sustained")))          # burst peak: every head launch is timed in isolation
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": "infer_512x512_frame", "rays_per_frame": N_RAYS, "max_steps": 16, "dt_gamma": 1 / 256, "bound": 1,
-                   "params": 683509, "weights": "random-init", "frames_per_gpu_per_step": 1, "frames_in_flight_per_gpu": pipe.depth, "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                   "params": 683509, "weights": "random-init", "frames_per_gpu_per_step": FRAMES_PER_STEP, "timed_region_s": dev_ms * 1e-3, "frames_in_flight_per_gpu": pipe.depth, "parallelism": f"frames sharded over {world} GPU(s), no collective",
                    "l2": f"inputs cycle through {POOL} distinct frames ({POOL * N_RAYS * 24 / 1e6:.0f} MB of rays) > 126 MB L2", "cuda_graph": not args.no_graph, "loop": loop_mode},
         # End to end through the public API with HOST buffers.  The reference's inference call takes a head pose + the audio window (provider_for_inference.py:597-605:
         # poses.to(device), get_rays ON the device) and hands (preds * 255).astype(uint8) bytes to its frame queue (TrainerUtil.py:668): that is the primary `e2e`
         # (FrameRenderer.render_host_pose: 64 B + the audio window up, one RGB24 frame down; rays and the uint8 packing on the device).  The heavier variant that ships
         # the 6.3 MB of precomputed rays up and the float image down is kept next to it — at 8 GPUs it is bound by the host's memory / PCIe root, not by the GPUs.
-        "e2e": e2e_rays if pose_ms is None else {"value": world * args.steps / (pose_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 64 + host_a[0].numel() * 4,
-                                                  "d2h_bytes_per_step": N_RAYS * 3, "ms_per_step": pose_ms / args.steps,
+        "e2e": e2e_rays if pose_ms is None else {"value": world * n_frames / (pose_ms * 1e-3), "unit": "frames/s",
+                                                  "h2d_bytes_per_step": FRAMES_PER_STEP * (64 + host_a[0].numel() * 4),
+                                                  "d2h_bytes_per_step": FRAMES_PER_STEP * N_RAYS * 3, "ms_per_step": pose_ms / args.steps,
                                                   "api": "FramePipeline.submit_host_pose: pinned 4x4 pose + audio window in, pinned RGB24 frame out"},
         "e2e_rays_in_float_out": e2e_rays,
         "gpu_launches": gpu_launches,
         "clocks": clocks,
         "roofline": {"kernel": "k_head_forward (fused tri-plane gather + 7 tcgen05 layers)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": pk_src + " (bf16 sustained)",
+                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": pk_src + " (bf16 burst: the launches are timed alone)",
                      "how": f"average launch duration from CUDA events on the launching stream (5 back-to-back repeats per launch) for each of the "
                             f"{head_launches} head launches of {min(args.steps, 8)} frames, separate un-graphed pass of the same frames; "
                             f"{head_samples} samples x {2 * MACS_PER_SAMPLE_INFER} FLOP",
@@ -442,24 +469,38 @@ def run_gpu_arm(args, rank, world, local_rank):
     if not args.no_train:
         line["train"] = train_info
         line["torso"] = torso_info
+    if world == 1 and not args.no_kernels:
+        try:                                               # per-kernel rooflines of the per-op kernels at sizes > L2 (profiles/kernel_rooflines.py)
+            sys.path.insert(0, os.path.join(ROOT, "profiles"))
+            import kernel_rooflines
+            del model, pipe, frames
+            torch.cuda.empty_cache()
+            line["kernels"] = kernel_rooflines.measure()
+        except Exception as e:                             # noqa: BLE001
+            line["kernels"] = {"error": f"{type(e).__name__}: {e}"}
+    if world == 1 and not args.no_ref_gpu:
+        line["reference_on_b200"] = reference_on_b200()
     if world == 1 and not args.no_cpu:
-        rows = 32
+        rows = HW // ROW_STRIDE                            # the reference arm's sample: every 8th row of the frame
         fps, sec, ns = cpu_frames_per_sec(rows, 2, 1)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"central {rows}-row band of one 512x512 frame ({rows * HW} rays, {ns} samples), mean of 2 after 1 warm-up, pure-PyTorch fp32 (oracle/torch_port.py)"}
+                                "sample": f"{rows} rows of one 512x512 frame at an even stride of {ROW_STRIDE} ({rows * HW} rays, {ns} samples, x{ROW_STRIDE} extrapolation), "
+                                          f"mean of 2 after 1 warm-up, pure-PyTorch fp32 (oracle/torch_port.py)"}
     print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b2nerf", choices=["b2nerf", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--in-flight", type=int, default=5, help="frames in flight per GPU (independent frames on separate streams; 1 = strictly one after another)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline leg (N = 1)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-this-GPU leg (N = 1)")
     ap.add_argument("--train-eager", action="store_true", help="training leg without the CUDA graph")
     ap.add_argument("--train-unfused", action="store_true", help="training leg through torch autograd over the per-op kernels instead of the fused head kernels")
     args = ap.parse_args()

@@ -23,7 +23,10 @@
  *     Argument validation mirrors gridencoder.cu:425-441 (the raymarching entry points of the reference
  *     validate nothing; here null pointers and unsupported shapes are rejected).
  *   - no entry point allocates device memory visible to the caller, synchronises the device, or touches
- *     the host except where documented (b2n_march_rays_train_count reads one int back when asked to).
+ *     the host.  The two marchers need a little scratch (the occupied box of the bitfield, per-CTA totals, a per-sample
+ *     t cache): the entry points with the reference's argument lists take it from a library-internal grow-only block per
+ *     device (calls on one device must then be stream-ordered, as the reference's legacy-stream kernels are); the *_ws
+ *     variants take a caller-owned workspace and are safe on concurrent streams / inside CUDA graphs.
  */
 #ifndef B2NERF_H_
 #define B2NERF_H_
@@ -61,6 +64,12 @@ int b2n_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t
                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                          const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
                          int32_t *rays, int32_t *counter, const float *noises, void *stream);
+/* the same with a caller-owned 16-byte aligned device workspace of b2n_march_rays_train_workspace_bytes(N, max_steps) bytes */
+uint64_t b2n_march_rays_train_workspace_bytes(uint32_t N, uint32_t max_steps);
+int b2n_march_rays_train_ws(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                            const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                            int32_t *rays, int32_t *counter, const float *noises, void *workspace, void *stream);
 int b2n_march_rays_train_backward(const float *grad_xyzs, const float *grad_dirs, const int32_t *rays,
                                   const float *deltas, uint32_t N, uint32_t M, float *grad_rays_o,
                                   float *grad_rays_d, void *stream);
@@ -111,6 +120,12 @@ int b2n_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive,
                    const float *rays_o, const float *rays_d, float bound, float dt_gamma, uint32_t max_steps,
                    uint32_t C, uint32_t H, const uint8_t *grid, const float *nears, const float *fars,
                    float *xyzs, float *dirs, float *deltas, const float *noises, void *stream);
+/* the same with a caller-owned 16-byte aligned device workspace of b2n_march_rays_workspace_bytes() bytes (NULL = no empty-space clipping) */
+uint64_t b2n_march_rays_workspace_bytes(void);
+int b2n_march_rays_ws(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t,
+                      const float *rays_o, const float *rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                      uint32_t C, uint32_t H, const uint8_t *grid, const float *nears, const float *fars,
+                      float *xyzs, float *dirs, float *deltas, const float *noises, void *workspace, void *stream);
 int b2n_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t,
         const float *sigmas, const float *rgbs, const float *deltas,
         float *weights_sum, float *depth, float *image, void *stream);

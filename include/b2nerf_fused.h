@@ -59,6 +59,11 @@ typedef struct {
     uint32_t dim_in;
 } b2n_audio_weights;
 int b2n_audio_encode(const b2n_audio_weights *w, const float *auds, uint32_t L, float *enc_a, void *stream);
+/* The same with the reference's `smooth_lips` option (renderer.py:456-460; the serving config turns it on): lips_state is a device float[33] carried
+ * across consecutive frames — [0..31] the previous frame's smoothed code, [32] a valid flag (zero it to start a sequence).  When valid,
+ * enc_a = lambda * state + (1 - lambda) * enc_a (lambda = 0.35 in the reference); the result is written to enc_a AND back to the state.
+ * lips_state NULL = b2n_audio_encode. */
+int b2n_audio_encode_smooth(const b2n_audio_weights *w, const float *auds, uint32_t L, float *enc_a, float *lips_state, float lambda, void *stream);
 /* Backward of b2n_audio_encode (training): d_enc_a [32] -> the gradient of every parameter, accumulated into `g` (same layouts as the weights; zero
  * them first).  One cluster kernel: recomputes the forward, back-propagates through the attention net on CTA 0 and through the eight AudioNet copies. */
 typedef struct {
@@ -216,16 +221,38 @@ int b2n_adamw_flat(float *params, const float *grads, float *exp_avg, float *exp
                    float weight_decay0, float lr1, float weight_decay1, float beta1, float beta2, float eps, float *step,
                    const float *grad_scale, const float *found_inf, void *stream);
 
-/* Training loss of the head branch and its gradient (TrainerUtil.py:238-300 with the background blend of renderer.py:559-561):
- *   img = clamp(image + (1 - weights_sum) * bg, 0, 1);  loss = mean (img - gt)^2 + lambda_ent * mean H2(clamp(weights_sum, 1e-5, 1 - 1e-5))
- *         + lambda_amb * (mean aud_sum + mean eye_sum).
- * image [N,3], weights_sum / aud_sum / eye_sum [N] are composite_rays_train_triplane's outputs; bg_color [3] or [N,3] (bg_per_ray); loss is one device
- * float (overwritten).  The backward multiplies by the device scalar *grad_loss (autograd's upstream gradient, i.e. the loss scale). */
-int b2n_head_loss_forward(const float *image, const float *weights_sum, const float *aud_sum, const float *eye_sum, const float *gt_rgb,
-                          const float *bg_color, int bg_per_ray, uint32_t N, float lambda_ent, float lambda_amb, float *loss, void *stream);
-int b2n_head_loss_backward(const float *image, const float *weights_sum, const float *gt_rgb, const float *bg_color, int bg_per_ray, uint32_t N,
-                           float lambda_ent, float lambda_amb, const float *grad_loss, float *grad_image, float *grad_weights_sum,
-                           float *grad_aud_sum, float *grad_eye_sum, void *stream);
+/* The same with up to 8 contiguous hyper-parameter groups (network.py:332-356 get_params: tables lr / AdamW's default weight decay 0.01; networks lr_net / wd;
+ * audio_att_net 5 * lr_net / 1e-4), group k covering flat indices [end[k-1], end[k]); the per-step learning rates are whatever the LR scheduler set
+ * (train.py:284-288, LambdaLR stepped every iteration, TrainerUtil.py:1048-1049).  ema: optional fp32 [n] shadow copy updated in the same pass,
+ * shadow -= (1 - ema_decay) * (shadow - param) — torch_ema's ExponentialMovingAverage.update (TrainerUtil.py:98-99, 1055-1056); NULL = no EMA this step. */
+typedef struct {
+    uint32_t n_groups;
+    uint32_t end[8];
+    float lr[8], weight_decay[8];
+} b2n_adam_groups;
+int b2n_adamw_flat_groups(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, uint32_t n, const b2n_adam_groups *groups, float beta1,
+                          float beta2, float eps, float *step, const float *grad_scale, const float *found_inf, float *ema, float ema_decay, void *stream);
+
+/* Training loss of the head branch and its gradient (TrainerUtil.py:238-334 with the background blend of renderer.py:559-561), sf = *step_factor:
+ *   img = clamp(image + (1 - weights_sum) * bg, 0, 1);   mse_n = mean_c (img - gt)^2
+ *   loss = mean_n [ mse_n * (0.2 + 0.8 clamp((1 - sf) + sf N softmax(unc_sum)_n, 0, 10)) + sf face_n (|img - gt| / (2 (unc+1)^2) + log(unc+1)^2 / 2)
+ *                   + 1e-3 sf (1 - face_n) unc_n ]                                          (the three uncertainty terms only when unc_sum != NULL)
+ *          + lambda_ent mean H2(clamp(weights_sum, 1e-5, 1 - 1e-5)) + sf lambda_amb mean(aud_sum (1 - face)) + sf lambda_amb mean(eye_sum inv_max_steps aud_sum face)
+ * image [N,3], weights_sum / aud_sum / eye_sum / unc_sum [N] are composite_rays_train_triplane's outputs; bg_color [3] or [N,3] (bg_per_ray); face_mask [N] bytes
+ * (bool) or NULL (= every ray on the face); step_factor: device scalar (a replayed CUDA graph sees it ramp) or NULL (= step_factor_host).
+ * stats: device float[4] — [0] the loss (overwritten), [1..2] softmax statistics the backward re-uses.  The backward multiplies by the device scalar
+ * *grad_loss (autograd's upstream gradient, i.e. the loss scale); grad_unc_sum may be NULL. */
+typedef struct {
+    const float *image, *weights_sum, *aud_sum, *eye_sum, *unc_sum;
+    const float *gt_rgb, *bg_color;
+    const uint8_t *face_mask;
+    const float *step_factor;
+    float step_factor_host, lambda_ent, lambda_amb, inv_max_steps;
+    int bg_per_ray, amb_aud_loss, amb_eye_loss;
+} b2n_loss_args;
+int b2n_head_loss_forward(const b2n_loss_args *a, uint32_t N, float *stats, void *stream);
+int b2n_head_loss_backward(const b2n_loss_args *a, uint32_t N, const float *stats, const float *grad_loss, float *grad_image, float *grad_weights_sum,
+                           float *grad_aud_sum, float *grad_eye_sum, float *grad_unc_sum, void *stream);
 
 /* ---- torso branch of a frame = NeRFRenderer.run_torso (renderer.py:572-631) + NeRFNetwork.forward_torso (network.py:170-205) as ONE
  * kernel, inference, autocast(fp16) numerics: 2-D occupancy test (F.grid_sample of density_grid_torso, align_corners=True, > density_thresh), frequency
@@ -250,6 +277,23 @@ int b2n_torso_forward(const b2n_torso_weights *w, const float *bg_coords, uint32
 /* workspace: 16-byte aligned device scratch of b2n_torso_workspace_bytes() bytes owned by the caller (packed weight image + tile counter); one per
  * concurrently running call */
 uint64_t b2n_torso_workspace_bytes(void);
+
+/* ---- density-grid maintenance of the head model (csrc/occupancy.cu) ------------------------------------------------
+ * NeRFRenderer.mark_untrained_grid (renderer.py:633-697), called once before training (TrainerUtil.py:475): every cell of density_grid
+ * [cascade, grid_size^3] (Morton order) that none of the B camera poses (device float [B,4,4], camera-to-world) sees gets -1; other cells are left
+ * untouched.  intrinsics as in the reference (fx, fy, cx, cy). */
+int b2n_mark_untrained_grid(const float *poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t cascade, uint32_t grid_size, float bound,
+                            float *density_grid, void *stream);
+/* update_extra_state's query points of cascade `cas` (renderer.py:729-747), written in MORTON order: row m of xyzs [grid_size^3, 3] is the jittered centre
+ * of the cell with Morton index m, so the sigma the head kernel returns for row m IS tmp_grid[cas, m].  rand01 [grid_size^3, 3] in [0,1) is read in the
+ * reference's own point order ((x * G + y) * G + z) — pass torch.rand_like's output to reproduce its jitter; NULL = cell centres. */
+int b2n_density_grid_points(const float *rand01, uint32_t grid_size, uint32_t cas, float bound, float *xyzs, void *stream);
+/* update_extra_state's tail (renderer.py:752-766) in two launches without a host read-back: tmp = morton3D_dilation(sigma * density_scale);
+ * density_grid = max(density_grid * decay, tmp) where both are >= 0; mean_density = mean(clamp(density_grid, 0)); bitfield = packbits(density_grid,
+ * min(mean_density, density_thresh)).  sigma / density_grid [cascade, grid_size^3] fp32 Morton order; stats: 16 bytes of 8-byte aligned device scratch —
+ * after the call ((float *)stats)[2] holds mean_density. */
+int b2n_density_grid_update(const float *sigma, float density_scale, float *density_grid, uint32_t cascade, uint32_t grid_size, float decay,
+                            float density_thresh, uint8_t *bitfield, void *stats, void *stream);
 
 #ifdef __cplusplus
 }

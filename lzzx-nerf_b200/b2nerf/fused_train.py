@@ -240,37 +240,80 @@ def fused_head_train(model, x, d, enc_a, ind_code, eye):
     return sig, rgb, aud[:, None], eye_att[:, None], unc[:, None, None]
 
 
+class _LossArgsC(ctypes.Structure):
+    """b2n_loss_args (include/b2nerf_fused.h)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("image", "weights_sum", "aud_sum", "eye_sum", "unc_sum", "gt_rgb", "bg_color", "face_mask", "step_factor")] + \
+               [(n, ctypes.c_float) for n in ("step_factor_host", "lambda_ent", "lambda_amb", "inv_max_steps")] + \
+               [(n, ctypes.c_int) for n in ("bg_per_ray", "amb_aud_loss", "amb_eye_loss")]
+
+
 class _FusedLoss(torch.autograd.Function):
-    """Trainer.loss (TrainerUtil.py:238-300) + the background blend (renderer.py:559-561) as two kernels (csrc/loss.cu)."""
+    """The head branch's loss (TrainerUtil.py:238-334) + the background blend (renderer.py:559-561) as three kernels (csrc/loss.cu)."""
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, image, ws, aud_sum, eye_sum, gt, bg, lambda_ent, lambda_amb):
+    def forward(ctx, image, ws, aud_sum, eye_sum, unc_sum, gt, bg, face_mask, step_factor, cfg):
         image, ws, aud_sum, eye_sum, gt, bg = (t.contiguous() for t in (image, ws, aud_sum, eye_sum, gt, bg))
+        unc_sum = None if unc_sum is None else unc_sum.contiguous()
         n = ws.shape[0]
         per_ray = int(bg.numel() == 3 * n and n > 1)
-        loss = torch.empty((), dtype=torch.float32, device=ws.device)
-        lib().call("b2n_head_loss_forward", image.data_ptr(), ws.data_ptr(), aud_sum.data_ptr(), eye_sum.data_ptr(), gt.data_ptr(), bg.data_ptr(), per_ray, n,
-                   float(lambda_ent), float(lambda_amb), loss.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        ctx.save_for_backward(image, ws, gt, bg)
-        ctx.cfg = (per_ray, n, float(lambda_ent), float(lambda_amb))
-        return loss
+        if face_mask is not None:
+            face_mask = face_mask.contiguous().view(-1)
+            face_mask = face_mask.view(torch.uint8) if face_mask.dtype == torch.bool else face_mask.to(torch.uint8)
+        sf_dev = step_factor if torch.is_tensor(step_factor) else None
+        p = lambda t: None if t is None else t.data_ptr()
+        args = _LossArgsC(p(image), p(ws), p(aud_sum), p(eye_sum), p(unc_sum), p(gt), p(bg), p(face_mask), p(sf_dev), 0.0 if sf_dev is not None else float(step_factor),
+                          float(cfg["lambda_ent"]), float(cfg["lambda_amb"]), 1.0 / float(cfg["max_steps"]), per_ray, int(cfg["amb_aud_loss"]), int(cfg["amb_eye_loss"]))
+        stats = torch.empty(4, dtype=torch.float32, device=ws.device)
+        lib().call("b2n_head_loss_forward", ctypes.byref(args), n, stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ctx.keep = (args, image, ws, aud_sum, eye_sum, unc_sum, gt, bg, face_mask, sf_dev, stats)
+        ctx.n = n
+        return stats[0]
 
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, g):
-        image, ws, gt, bg = ctx.saved_tensors
-        per_ray, n, l_ent, l_amb = ctx.cfg
+        args, image, ws, aud_sum, eye_sum, unc_sum, gt, bg, face_mask, sf_dev, stats = ctx.keep
         g = g.float().contiguous()
         d_img, d_ws, d_aud, d_eye = torch.empty_like(image), torch.empty_like(ws), torch.empty_like(ws), torch.empty_like(ws)
-        lib().call("b2n_head_loss_backward", image.data_ptr(), ws.data_ptr(), gt.data_ptr(), bg.data_ptr(), per_ray, n, l_ent, l_amb, g.data_ptr(),
-                   d_img.data_ptr(), d_ws.data_ptr(), d_aud.data_ptr(), d_eye.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        return d_img, d_ws, d_aud, d_eye, None, None, None, None
+        d_unc = torch.empty_like(ws) if unc_sum is not None else None
+        lib().call("b2n_head_loss_backward", ctypes.byref(args), ctx.n, stats.data_ptr(), g.data_ptr(), d_img.data_ptr(), d_ws.data_ptr(), d_aud.data_ptr(),
+                   d_eye.data_ptr(), None if d_unc is None else d_unc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return d_img, d_ws, d_aud, d_eye, d_unc, None, None, None, None, None
 
 
-def fused_head_loss(image, weights_sum, aud_sum, eye_sum, gt_rgb, bg_color, lambda_ent=1e-3, lambda_amb=1e-4):
-    """`image` is the composite's UN-blended image; returns the scalar loss of Trainer.loss on clamp(image + (1 - ws) * bg, 0, 1)."""
-    return _FusedLoss.apply(image, weights_sum, aud_sum, eye_sum, gt_rgb, bg_color, lambda_ent, lambda_amb)
+def fused_head_loss(image, weights_sum, aud_sum, eye_sum, gt_rgb, bg_color, unc_sum=None, face_mask=None, step_factor=0.0, lambda_ent=1e-4, lambda_amb=1e-4,
+                    max_steps=16, amb_aud_loss=True, amb_eye_loss=True):
+    """`image` is the composite's UN-blended image; returns the scalar head-branch loss of TrainerUtil.train_step on clamp(image + (1 - ws) * bg, 0, 1).
+    unc_sum=None drops the uncertainty terms (opt.unc_loss = 0); face_mask=None treats every ray as a face ray; step_factor: float or 1-element device tensor."""
+    cfg = dict(lambda_ent=lambda_ent, lambda_amb=lambda_amb, max_steps=max_steps, amb_aud_loss=amb_aud_loss, amb_eye_loss=amb_eye_loss)
+    return _FusedLoss.apply(image, weights_sum, aud_sum, eye_sum, unc_sum, gt_rgb, bg_color, face_mask, step_factor, cfg)
+
+
+def torch_head_loss(image, weights_sum, aud_sum, eye_sum, gt_rgb, unc_sum=None, face_mask=None, step_factor=0.0, lambda_ent=1e-4, lambda_amb=1e-4, max_steps=16,
+                    amb_aud_loss=True, amb_eye_loss=True):
+    """The same loss op by op, in the reference's own order of operations (TrainerUtil.py:238-334) on the blended image; the parity partner of the kernels."""
+    n = weights_sum.shape[0]
+    sf = step_factor.reshape(()) if torch.is_tensor(step_factor) else step_factor          # a device scalar in a replayed CUDA graph
+    face = torch.ones(n, dtype=torch.bool, device=image.device) if face_mask is None else face_mask.view(-1).bool()
+    loss = ((image - gt_rgb) ** 2).mean(-1)
+    if unc_sum is not None:
+        alpha = 0.2
+        unc_weight = torch.softmax(unc_sum, dim=-1) * n
+        loss = loss * (alpha + (1 - alpha) * ((1 - sf) + sf * unc_weight.detach()).clamp(0, 10))
+        beta = unc_sum + 1
+        norm_rgb = torch.norm(image - gt_rgb, dim=-1).detach()
+        loss_u = (norm_rgb / (2 * beta ** 2) + (torch.log(beta) ** 2) / 2) * face
+        loss = loss + sf * loss_u + 1e-3 * sf * (unc_sum * (~face))
+    loss = loss.mean()
+    alphas = weights_sum.clamp(1e-5, 1 - 1e-5)
+    loss = loss + lambda_ent * (-alphas * torch.log2(alphas) - (1 - alphas) * torch.log2(1 - alphas)).mean()
+    lam = sf * lambda_amb
+    if amb_aud_loss:
+        loss = loss + lam * (aud_sum * (~face)).mean()
+    if amb_eye_loss:
+        loss = loss + lam * ((eye_sum / max_steps * aud_sum.detach()) * face).mean()
+    return loss
 
 
 class _AudioGradsC(ctypes.Structure):

@@ -304,16 +304,65 @@ class HeadModel(nn.Module):
                    ctypes.byref(sv), torch.cuda.current_stream().cuda_stream)
         return sig, rgb, aud, eye_o, unc, saved
 
-    # ---- occupancy-grid refresh (renderer.py:699-768, head branch) ---------------------------------------------------------
+    # ---- occupancy-grid maintenance (renderer.py:633-768, head branch) ----------------------------------------------------------
+    @torch.no_grad()
+    def mark_untrained_grid(self, poses, intrinsic, S=64):
+        """NeRFRenderer.mark_untrained_grid (renderer.py:633-697; TrainerUtil.py:475 calls it before the first step): density_grid cells that none of the
+        training cameras `poses` [B,4,4] (c2w; numpy or tensor) with `intrinsic` (fx, fy, cx, cy) sees are set to -1, which freezes them out of every later
+        update_extra_state.  One kernel over the Morton-ordered grid per 1024 poses (csrc/occupancy.cu); `S` is accepted for signature compatibility."""
+        import numpy as np
+        if isinstance(poses, np.ndarray):
+            poses = torch.from_numpy(poses)
+        dev = self.density_grid.device
+        poses = poses.to(dev).float().contiguous().view(-1, 4, 4)
+        fx, fy, cx, cy = (float(v) for v in intrinsic)
+        B = poses.shape[0]
+        if B <= 1024:
+            lib().call("b2n_mark_untrained_grid", poses.data_ptr(), B, fx, fy, cx, cy, self.cascade, self.grid_size, self.bound, self.density_grid.data_ptr(),
+                       torch.cuda.current_stream().cuda_stream)
+            return
+        # more poses than one launch stages in shared memory: a cell is untrained iff EVERY chunk marks it
+        seen = torch.zeros_like(self.density_grid, dtype=torch.bool)
+        for h in range(0, B, 1024):
+            probe = torch.zeros_like(self.density_grid)
+            chunk = poses[h:h + 1024].contiguous()
+            lib().call("b2n_mark_untrained_grid", chunk.data_ptr(), chunk.shape[0], fx, fy, cx, cy, self.cascade, self.grid_size, self.bound, probe.data_ptr(),
+                       torch.cuda.current_stream().cuda_stream)
+            seen |= probe >= 0
+        self.density_grid[~seen] = -1
+
     @torch.no_grad()
     def update_extra_state(self, auds, eye=None, decay=0.95, density_thresh=10.0, density_scale=1.0, fused=True):
-        """NeRFRenderer.update_extra_state for the head: evaluate sigma on the 128^3 Morton-ordered jittered grid of every cascade, dilate,
-        EMA-max into density_grid, re-pack the bitfield (threshold min(mean_density, density_thresh)).  The reference runs `self.density` on
-        128^3 points through the per-op graph; here the 2.1 M points of a cascade go through the fused head kernel in one launch
-        (`fused=False` keeps the reference graph — used by the parity test).  Returns mean_density (one D2H read, like the reference)."""
+        """NeRFRenderer.update_extra_state for the head (renderer.py:699-766): evaluate sigma on the jittered 128^3 lattice of every cascade, dilate,
+        EMA-max into density_grid, re-pack the bitfield (threshold min(mean_density, density_thresh)).
+        fused=True: per cascade ONE point-generation kernel that writes the lattice in Morton order (jitter = torch.rand_like in the reference's
+        point order, so the same seed gives the reference's points) and ONE fused head launch over the 2.1 M points whose sigma output is tmp_grid itself, then
+        dilation + EMA-max + mean in one kernel and packbits against the device-side threshold in another (csrc/occupancy.cu) — the reference runs ~45 kernels
+        per MLP call plus index_put / dilation / masked max / mean / packbits with a host read-back in between.
+        fused=False keeps the reference's op-by-op graph on the drop-in ops (parity partner).  Returns mean_density (one D2H read, like the reference)."""
         import raymarching
         dev, G = self.density_grid.device, self.grid_size
         enc_a = self.encode_audio(auds)
+        st = torch.cuda.current_stream().cuda_stream
+        if fused:
+            self.pack()
+            n = G ** 3
+            sig_all = torch.empty(self.cascade, n, device=dev)
+            xyzs = torch.empty(n, 3, device=dev)
+            if getattr(self, "_grid_dirs", None) is None or self._grid_dirs.device != dev:
+                self._grid_dirs = torch.zeros(n, 3, device=dev); self._grid_dirs[:, 2] = 1.0
+                self._grid_stats = torch.zeros(4, device=dev)
+            f = lambda t: None if t is None else t.detach().float().contiguous().view(-1)
+            enc_f, code_f, eye_f = f(enc_a), f(self.individual_codes[0:1]), f(eye)
+            for cas in range(self.cascade):
+                rnd = torch.rand(n, 3, device=dev)                          # == torch.rand_like(cas_xyzs) of the reference (same shape / dtype / device)
+                lib().call("b2n_density_grid_points", rnd.data_ptr(), G, cas, self.bound, xyzs.data_ptr(), st)
+                lib().call("b2n_head_forward", self.handle, xyzs.data_ptr(), self._grid_dirs.data_ptr(), n, enc_f.data_ptr(), code_f.data_ptr(),
+                           None if eye_f is None else eye_f.data_ptr(), None, sig_all[cas].data_ptr(), None, None, None, None, st)
+            lib().call("b2n_density_grid_update", sig_all.data_ptr(), float(density_scale), self.density_grid.data_ptr(), self.cascade, G, float(decay),
+                       float(density_thresh), self.density_bitfield.data_ptr(), self._grid_stats.data_ptr(), st)
+            self.mean_density = float(self._grid_stats[2].item())
+            return self.mean_density
         if not hasattr(self, "_grid_coords") or self._grid_coords.device != dev:
             ar = torch.arange(G, dtype=torch.int32, device=dev)
             xx, yy, zz = torch.meshgrid(ar, ar, ar, indexing="ij")
@@ -322,18 +371,12 @@ class HeadModel(nn.Module):
         coords, indices = self._grid_coords, self._grid_indices
         xyzs = 2 * coords.float() / (G - 1) - 1
         tmp_grid = torch.zeros_like(self.density_grid)
-        if fused:
-            self.pack()
         for cas in range(self.cascade):
             bound = min(2 ** cas, self.bound)
             half = bound / G
             cas_xyzs = xyzs * (bound - half)
             cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half
-            if fused:
-                dirs = torch.zeros_like(cas_xyzs); dirs[:, 2] = 1.0
-                sig = self(cas_xyzs, dirs, enc_a, self.individual_codes[0:1], eye)[0]
-            else:
-                sig = self.density(cas_xyzs, enc_a, eye)["sigma"].reshape(-1).float()
+            sig = self.density(cas_xyzs, enc_a, eye)["sigma"].reshape(-1).float()
             tmp_grid[cas, indices] = sig * density_scale
         tmp_grid = raymarching.morton3D_dilation(tmp_grid)
         valid = (self.density_grid >= 0) & (tmp_grid >= 0)

@@ -14,8 +14,11 @@ from .model import HeadModel
 
 class FrameRenderer:
     def __init__(self, model: HeadModel, n_rays, eye=0.4, ind_index=0, dt_gamma=1.0 / 256, max_steps=16, T_thresh=1e-4, use_graph=True, fused_audio=True,
-                 camera=None, torso=None, bg_coords=None):
-        """camera = (H, W, fx, fy, cx, cy): also build the device-side prologue / epilogue (rays from a 4x4 pose, RGB24 output), so that
+                 camera=None, torso=None, bg_coords=None, smooth_lips=False, lips_state=None, lips_lambda=0.35):
+        """smooth_lips: the reference's opt.smooth_lips (renderer.py:456-460, on in the serving config HubertInferenceMQ.py): the audio code of frame k is
+        0.35 * (smoothed code of frame k-1) + 0.65 * (its own); the state is a device float[33] (`lips_state`, shared by the slots of a FramePipeline) and the
+        audio kernel runs in frame order in front of the frame graph instead of inside it.  reset_lips() starts a new sequence.
+        camera = (H, W, fx, fy, cx, cy): also build the device-side prologue / epilogue (rays from a 4x4 pose, RGB24 output), so that
         render_host_pose() moves a pose + the audio window up and one uint8 frame down.
         torso = a TorsoModel (+ bg_coords [N,2], utils.py:218-223): every frame first runs the fused torso kernel (csrc/fused_torso.cu) over the background into
         the per-ray bg_color buffer the head frame reads (renderer.py:572-631 then :559-561); set the head pose with set_torso_pose()."""
@@ -34,6 +37,14 @@ class FrameRenderer:
         self.image = torch.empty(self.N, 3, device=d)
         self.enc_a = torch.empty(1, 32, device=d)
         self.fused_audio = fused_audio and model.att > 0
+        self.smooth_lips = bool(smooth_lips)
+        if self.smooth_lips:
+            if not self.fused_audio:
+                raise RuntimeError("FrameRenderer: smooth_lips needs the fused audio encoder (att > 0)")
+            self.lips_state = lips_state if lips_state is not None else torch.zeros(33, device=d)
+            self.lips_lambda = float(lips_lambda)
+            self._audio_w = model.audio_weights_struct()
+        self._audio_done = False        # smooth_lips: a FramePipeline already ran the audio kernel for the coming frame (in frame order, on its audio stream)
         self.graph = None               # torch.cuda.CUDAGraph of the fixed launch sequence (fallback)
         self.loop_graph = None          # libb2nerf frame graph with a device-controlled WHILE loop (preferred)
         self.launches_per_frame = None
@@ -73,13 +84,29 @@ class FrameRenderer:
         """Head pose [1,4,4] of the coming frames -> the 50 per-frame constant inputs of the torso MLPs (network.py:179-190)."""
         self.torso_h_const.copy_(self.torso.frame_constants(poses.to(self.dev), index).view(-1))
 
+    def reset_lips(self):
+        """Start a new frame sequence (the reference's `self.enc_a = None`, renderer.py:151-152)."""
+        if self.smooth_lips:
+            self.lips_state.zero_()
+
+    def encode_audio_smoothed(self):
+        """k_audio_encode + the smooth_lips EMA on the current stream: self.auds -> self.enc_a, lips_state updated in place."""
+        import ctypes
+        from ._lib import lib
+        lib().call("b2n_audio_encode_smooth", ctypes.byref(self._audio_w), self.auds.data_ptr(), self.auds.shape[2], self.enc_a.data_ptr(),
+                   self.lips_state.data_ptr(), self.lips_lambda, torch.cuda.current_stream(self.dev).cuda_stream)
+
     def _torso(self):
         if self.torso is not None:
             self.torso.run_torso_fused(self.bg_coords, None, 0, self.torso_bg_color, h_const=self.torso_h_const, out=self.bg, workspace=self.torso_ws)
 
     def _device_frame(self):
         self._torso()
-        if self.fused_audio:
+        if self.smooth_lips:
+            if not self._audio_done:
+                self.encode_audio_smoothed()
+            enc_a = self.enc_a
+        elif self.fused_audio:
             enc_a = self.m.encode_audio_fused(self.auds, out=self.enc_a)      # one cluster kernel (csrc/fused_audio.cu)
         else:
             with torch.autocast("cuda", dtype=torch.float16):
@@ -95,7 +122,7 @@ class FrameRenderer:
         need = int(L.raw("b2n_render_frame_workspace_bytes")(self.N))
         self._graph_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
         cfg = _RenderCfgC(m.bound, self.kw["dt_gamma"], 0.05, self.kw["T_thresh"], 1.0, self.kw["max_steps"], m.cascade, m.grid_size, m._aabb_host)
-        aw = m.audio_weights_struct() if self.fused_audio else None
+        aw = m.audio_weights_struct() if (self.fused_audio and not self.smooth_lips) else None        # smooth_lips: the audio kernel runs in frame order, in front of the graph
         self._graph_keep = (cfg, aw, self.ind_code.float().contiguous().view(-1), self.eye.float().contiguous().view(-1))
         h = ctypes.c_void_p()
         torch.cuda.synchronize(self.dev)
@@ -136,8 +163,11 @@ class FrameRenderer:
         if self.pose_graph is None:
             self._build_pose_graph()
         self.pose.copy_(pose_host.view(4, 4), non_blocking=True)
-        self.auds.copy_(auds_host, non_blocking=True)
+        if auds_host is not None:
+            self.auds.copy_(auds_host, non_blocking=True)
         self._torso()
+        if self.smooth_lips and not self._audio_done:
+            self.encode_audio_smoothed()
         lib().call("b2n_frame_graph_launch", self.pose_graph, torch.cuda.current_stream(self.dev).cuda_stream)
         out_u8_host.copy_(self.rgb8, non_blocking=True)
         return out_u8_host
@@ -155,6 +185,8 @@ class FrameRenderer:
         if self.loop_graph is not None:
             from ._lib import lib
             self._torso()
+            if self.smooth_lips and not self._audio_done:
+                self.encode_audio_smoothed()
             if not self.fused_audio:
                 with torch.autocast("cuda", dtype=torch.float16):
                     self.enc_a.copy_(self.m.encode_audio(self.auds).float())
@@ -207,7 +239,8 @@ class FrameRenderer:
         """Host (pinned) buffers in and out: 2 x N x 12 B + audio window up, N x 12 B down, per frame."""
         self.rays_o.copy_(rays_o_host.view(-1, 3), non_blocking=True)
         self.rays_d.copy_(rays_d_host.view(-1, 3), non_blocking=True)
-        self.auds.copy_(auds_host, non_blocking=True)
+        if auds_host is not None:
+            self.auds.copy_(auds_host, non_blocking=True)
         self._launch()
         out_host.copy_(self.image, non_blocking=True)
         return out_host
@@ -236,8 +269,14 @@ class FramePipeline:
 
     def __init__(self, model: HeadModel, n_rays, depth=2, **kw):
         self.depth = int(depth)
+        self.smooth = bool(kw.get("smooth_lips", False))
+        if self.smooth and kw.get("lips_state") is None:                 # ONE smoothing state for the whole frame sequence
+            kw["lips_state"] = torch.zeros(33, device=next(model.parameters()).device)
         self.slots = [FrameRenderer(model, n_rays, **kw) for _ in range(self.depth)]
         self.dev = self.slots[0].dev
+        # smooth_lips makes the audio code of frame k depend on frame k-1: the (tiny) audio kernels run in frame order on their own stream, the frames
+        # themselves still overlap on the slot streams
+        self.audio_stream = torch.cuda.Stream(device=self.dev) if self.smooth else None
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.depth)]
         self.done = [torch.cuda.Event() for _ in range(self.depth)]
         self.k = 0
@@ -248,28 +287,48 @@ class FramePipeline:
         self.streams[i].wait_stream(torch.cuda.current_stream(self.dev))      # inputs produced on the caller's stream are ready
         return i
 
+    def _ordered_audio(self, i, auds):
+        """smooth_lips: copy the window and run audio encode + EMA for slot i on the audio stream (frame order), then let the slot's stream wait for it."""
+        sl, a = self.slots[i], self.audio_stream
+        a.wait_stream(torch.cuda.current_stream(self.dev))
+        a.wait_event(self.done[i])                                         # the slot's previous frame no longer reads its auds / enc_a buffers
+        with torch.cuda.stream(a):
+            sl.auds.copy_(auds, non_blocking=True)
+            sl.encode_audio_smoothed()
+        self.streams[i].wait_stream(a)
+        sl._audio_done = True
+
     def submit_device(self, rays_o, rays_d, auds):
         """Enqueue one frame whose inputs are on the device; returns (slot index, the slot's static image buffer)."""
         i = self._slot()
+        if self.smooth:
+            self._ordered_audio(i, auds); auds = None
         with torch.cuda.stream(self.streams[i]):
             img = self.slots[i].render_device(rays_o, rays_d, auds)
             self.done[i].record()
+        self.slots[i]._audio_done = False
         return i, img
 
     def submit_host(self, rays_o_host, rays_d_host, auds_host, out_host):
         """Enqueue one frame with pinned host inputs / output (out_host must stay untouched until the slot's event or drain())."""
         i = self._slot()
+        if self.smooth:
+            self._ordered_audio(i, auds_host); auds_host = None
         with torch.cuda.stream(self.streams[i]):
             self.slots[i].render_host(rays_o_host, rays_d_host, auds_host, out_host)
             self.done[i].record()
+        self.slots[i]._audio_done = False
         return i
 
     def submit_host_pose(self, pose_host, auds_host, out_u8_host):
         """Enqueue one frame from a pinned host pose + audio window; the uint8 frame lands in out_u8_host (renderers built with camera=...)."""
         i = self._slot()
+        if self.smooth:
+            self._ordered_audio(i, auds_host); auds_host = None
         with torch.cuda.stream(self.streams[i]):
             self.slots[i].render_host_pose(pose_host, auds_host, out_u8_host)
             self.done[i].record()
+        self.slots[i]._audio_done = False
         return i
 
     def drain(self):

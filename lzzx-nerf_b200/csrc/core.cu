@@ -27,8 +27,9 @@ int sm_count() {
     return cached[dev];
 }
 
-// Grow-only per-device scratch slots.  Growth happens only when a call needs more than any earlier call
-// (never in steady state, never under stream capture after a warm-up call of the same shape).
+// Grow-only per-device scratch slots for the entry points that keep the reference's argument lists (no workspace parameter).  Growth happens only when a call
+// needs more than any earlier call (never in steady state, never under stream capture after a warm-up call of the same shape).  A slot is shared by every
+// caller on the device: calls that use it must be stream-ordered with each other; concurrent callers use the *_ws entry points with their own workspace.
 struct Slot { void *ptr = nullptr; size_t bytes = 0; };
 static Slot g_slots[64][4];
 static std::mutex g_slot_mu;
@@ -42,7 +43,8 @@ void *scratch(size_t bytes, int slot) {
         size_t want = bytes < 4096 ? 4096 : bytes + bytes / 2;
         void *p = nullptr;
         if (cudaMalloc(&p, want) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
-        if (s.ptr) cudaFree(s.ptr);      // implicit sync: all users of the old block have drained
+        // the old block is RETIRED, not freed: a CUDA graph captured earlier may still replay kernels that point into it, and another stream may still be
+        // running on it.  Blocks grow geometrically, so the retired ones add up to less than twice the live one.
         s.ptr = p; s.bytes = want;
     }
     return s.ptr;

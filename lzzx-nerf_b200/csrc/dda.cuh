@@ -67,6 +67,25 @@ struct DdaRay {
         return l1 > l2 ? l1 : l2;
     }
 
+    // Exact empty-space clipping (see k_occ_box, raymarch.cu).  `box` = the occupied cells of the bitfield grown by two cells, sides that reach the scene cube
+    // opened to infinity.  Every t the reference visits is a point of the orbit t <- t + step_of(t) started at t0 — occupied or empty cell alike (a sample
+    // advances by dt = step_of(t), the empty-cell do-while repeats the same update) — and outside the grown box every probed cell is empty.  So (a) marching
+    // may stop at the box exit, (b) a ray that misses the box has no sample, and (c) the orbit may be run WITHOUT probing (4 dependent flops a step instead of a
+    // ~60-instruction probe) up to the first orbit point inside the box: the probes that follow are made at the reference's own t values, bit for bit.
+    // Returns the clipped far (0 on a miss) and advances t to the first orbit point >= the box entry.
+    __device__ __forceinline__ float clip_to_box(const float *__restrict__ box, float &t) const {
+        const float ax0 = (box[0] - ox) * rdx, ax1 = (box[3] - ox) * rdx, ay0 = (box[1] - oy) * rdy, ay1 = (box[4] - oy) * rdy;
+        const float az0 = (box[2] - oz) * rdz, az1 = (box[5] - oz) * rdz;
+        const float t_in = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fminf(az0, az1));
+        const float t_out = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fmaxf(az0, az1));
+        if (!(t_in <= t_out)) return 0.0f;                   // miss or empty box (an axis-parallel ray lying IN a box plane, 0 * inf = NaN, also lands here: it is two cells from anything occupied)
+        const float f = fminf(far, t_out);
+        // entry: t_in is rounded, so stop one step early (the margin of two cells absorbs it: the skipped points are provably outside the occupied cells + 1 cell)
+        const float t_stop = t_in - dt_max;
+        while (t < t_stop && t < f) t = __fadd_rn(t, step_of(t));
+        return f;
+    }
+
     // One loop iteration at parameter t.  Occupied: fills s, returns true (caller advances t by s.dt).
     // Empty: advances t past the voxel exit with the reference's do-while and returns false.
     __device__ __forceinline__ bool probe(const uint8_t *__restrict__ grid, float &t, DdaSample &s) const {
@@ -94,5 +113,11 @@ struct DdaRay {
         return false;
     }
 };
+
+// Grown occupied box of a bitfield (k_occ_box, raymarch.cu): OCC_PARTS per-CTA partial boxes, then the final [lo xyz | hi xyz] at parts + 6 * OCC_PARTS
+// and a ticket counter behind it.
+constexpr uint32_t OCC_PARTS = 128;
+constexpr uint32_t OCC_BOX_FLOATS = 6 * OCC_PARTS + 6 + 2;
+__global__ void k_occ_box(const uint8_t *__restrict__ grid, uint32_t C, uint32_t H, float bound, float *__restrict__ parts, int finalize);
 
 }  // namespace b2n

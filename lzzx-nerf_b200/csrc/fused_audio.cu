@@ -98,6 +98,8 @@ struct AudioArgs {
     const float *auds;      // [8, dim_in, L]
     uint32_t L;             // samples per frame (the reference slices x[:, :, 8-8:8+8], i.e. min(L, 16))
     float *enc_a;           // [32]
+    float *lips_state;      // optional [33]: the previous frame's (smoothed) enc_a + a valid flag — smooth_lips, renderer.py:456-460
+    float lips_lambda, lips_one_minus;
 };
 
 __global__ void __cluster_dims__(AU_FRAMES, 1, 1) __launch_bounds__(AU_THREADS) k_audio_encode(const __grid_constant__ AudioArgs a) {
@@ -174,6 +176,15 @@ __global__ void __cluster_dims__(AU_FRAMES, 1, 1) __launch_bounds__(AU_THREADS) 
         for (int s = 0; s < AU_FRAMES; s++) { e[s] = expf(s_y[s] - mx); den += e[s]; }
         float acc = 0.0f;
         for (int s = 0; s < AU_FRAMES; s++) acc = fmaf(e[s] / den, s_all[s * 32 + threadIdx.x], acc);
+        if (a.lips_state != nullptr) {
+            // enc_a = lambda * self.enc_a + (1 - lambda) * enc_a; self.enc_a = enc_a  (fp32, two products and a sum like the torch expression)
+            const bool have = a.lips_state[32] != 0.0f;
+            __syncwarp();
+            if (have) acc = __fadd_rn(__fmul_rn(a.lips_lambda, a.lips_state[threadIdx.x]), __fmul_rn(a.lips_one_minus, acc));
+            a.lips_state[threadIdx.x] = acc;
+            __syncwarp();
+            if (threadIdx.x == 0) a.lips_state[32] = 1.0f;
+        }
         a.enc_a[threadIdx.x] = acc;
     }
 }
@@ -361,6 +372,10 @@ __global__ void __cluster_dims__(AU_FRAMES, 1, 1) __launch_bounds__(AU_THREADS) 
 using namespace b2n;
 
 extern "C" int b2n_audio_encode(const b2n_audio_weights *w, const float *auds, uint32_t L, float *enc_a, void *stream) {
+    return b2n_audio_encode_smooth(w, auds, L, enc_a, nullptr, 0.0f, stream);
+}
+
+extern "C" int b2n_audio_encode_smooth(const b2n_audio_weights *w, const float *auds, uint32_t L, float *enc_a, float *lips_state, float lambda, void *stream) {
     B2N_REQUIRE(w && auds && enc_a, "audio_encode: null pointer");
     B2N_REQUIRE(w->dim_in >= 1 && w->dim_in <= 4096 && L >= 1, "audio_encode: dim_in=%u / L=%u unsupported", w->dim_in, L);
     for (int i = 0; i < 4; i++) B2N_REQUIRE(w->conv_w[i] && w->conv_b[i], "audio_encode: null conv weight");
@@ -371,7 +386,7 @@ extern "C" int b2n_audio_encode(const b2n_audio_weights *w, const float *auds, u
     uint32_t li = Lw;
     for (int i = 0; i < 4; i++) li = (li + 2 - 3) / 2 + 1;
     B2N_REQUIRE(li == 1, "audio_encode: window length %u does not reduce to 1 after four stride-2 convolutions", L);
-    AudioArgs a = {*w, auds, L, enc_a};
+    AudioArgs a = {*w, auds, L, enc_a, lips_state, lambda, (float)(1.0 - (double)lambda)};
     const size_t smem = sizeof(float) * ((size_t)w->dim_in * Lw + 1024 + AW_TOTAL);       // input slice + ping / pong + the weight cache (121 KB)
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(k_audio_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }

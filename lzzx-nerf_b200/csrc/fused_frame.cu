@@ -58,7 +58,7 @@ static size_t carve(FrameWs *w, uint8_t *base, uint32_t N) {
     t.alive[0] = (int32_t *)take(4 * Np); t.alive[1] = (int32_t *)take(4 * Np);
     t.alive_mid = (int32_t *)take(4 * Np);
     t.counters = (int32_t *)take(4 * 8);
-    t.occ_box = (float *)take(4 * 6 * 128);      // per-CTA partial boxes of k_occupied_box (reduced by every CTA of k_frame_init)
+    t.occ_box = (float *)take(4 * OCC_BOX_FLOATS);   // per-CTA partial boxes of k_occ_box (reduced by every CTA of k_frame_init)
     float **per_ray[] = {&t.nears, &t.fars, &t.rays_t, &t.ws, &t.depth, &t.aud_sum, &t.eye_sum, &t.unc_sum};
     for (auto p : per_ray) *p = (float *)take(4 * Np);
     t.image = (float *)take(12 * Np);
@@ -69,79 +69,37 @@ static size_t carve(FrameWs *w, uint8_t *base, uint32_t N) {
     return off;
 }
 
-// Box around all occupied cells of the bitfield, grown by two cells, in world units (union over cascades).  One CTA: the bitfield of the
-// head model is 256 KB.  EXACTNESS ARGUMENT for using it: a DDA probe at parameter t reads the cell containing clamp(o + t d) (up to one
-// float ulp, i.e. at most the neighbouring cell); if the ray point is farther than two cells from every occupied cell, the probed cell is
-// empty.  Hence (a) a ray that misses the grown box produces no sample at all, and (b) past its exit from the grown box a ray produces no
-// further sample — so marching may stop at min(far, t_exit) and every sample, count and alive flag stays bit-identical to marching to `far`
-// (tests/test_gpu_fused.py compares against the per-op marcher, which does march to `far`).
-constexpr uint32_t OCC_PARTS = 128;
-__global__ void __launch_bounds__(256) k_occupied_box(const uint8_t *__restrict__ grid, uint32_t C, uint32_t H, float bound, int enable, float *__restrict__ parts) {
-    __shared__ float red[6][8];
-    const uint32_t H3 = H * H * H, words = C * H3 / 32;
-    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    if (!enable) {          // marching interval not provably inside the grid cube: no clipping
-        lo[0] = lo[1] = lo[2] = -3.0e38f; hi[0] = hi[1] = hi[2] = 3.0e38f;
-    } else {
-        for (uint32_t wd = blockIdx.x * blockDim.x + threadIdx.x; wd < words; wd += gridDim.x * blockDim.x) {
-            const uint32_t bits = __ldg(reinterpret_cast<const uint32_t *>(grid) + wd);
-            if (bits) {
-                // a 32-bit word of the Morton-ordered bitfield is a 4 x 4 x 2 block of cells (Morton bits 0,3 -> x, 1,4 -> y, 2 -> z): the block is taken
-                // whole when any of its cells is occupied — a superset of the exact box (the exactness argument only needs a superset), one step per
-                // non-empty word instead of one per set bit (17 -> 3 us per frame)
-                const uint32_t idx = wd * 32, level = idx / H3, m = idx - level * H3;
-                const float mb = fminf(scalbnf(1.0f, (int)level), bound);
-                const float cell = mb * 2.0f / (float)H;                // cell size of this cascade in world units
-                const uint32_t c[3] = {compact3(m), compact3(m >> 1), compact3(m >> 2)};
-                const float ext[3] = {3.0f, 3.0f, 1.0f};
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    lo[a] = fminf(lo[a], -mb + ((float)c[a] - 2.0f) * cell);
-                    hi[a] = fmaxf(hi[a], -mb + ((float)c[a] + ext[a] + 3.0f) * cell);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
-    if ((threadIdx.x & 31) == 0) for (int a = 0; a < 3; a++) { red[a][threadIdx.x >> 5] = lo[a]; red[3 + a][threadIdx.x >> 5] = hi[a]; }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-        float v = red[threadIdx.x][0];
-        for (uint32_t w = 1; w < blockDim.x / 32; w++) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
-        parts[blockIdx.x * 6 + threadIdx.x] = v;
-    }
-}
-
-// near/far + state reset + ctrl[0]
+// near/far + state reset + ctrl[0].  The marching interval of every ray is clipped to the grown occupied box of the bitfield (k_occ_box, raymarch.cu; exactness
+// argument at dda.cuh:clip_to_box): the far end moves to the box exit, a ray that misses the box never starts, and the orbit t <- t + step_of(t) is run without
+// probing up to the box entry, so the first march iteration starts where the samples are instead of walking ~35 empty cells per ray.
 __global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ rays_o, const float *__restrict__ rays_d, uint32_t N, float min_near,
-                                                     float a0, float a1, float a2, float a3, float a4, float a5, uint32_t max_steps, FrameWs w) {
+                                                     float a0, float a1, float a2, float a3, float a4, float a5, uint32_t max_steps, float bound, float dt_gamma,
+                                                     uint32_t C, uint32_t H, int clip, FrameWs w) {
     __shared__ float bx[6];
-    if (threadIdx.x < 6 * 32) {                   // warp a reduces component a of the 128 partial boxes
+    if (threadIdx.x < 6 * 32) {                   // warp a reduces component a of the partial boxes
         const uint32_t a = threadIdx.x >> 5, lane = threadIdx.x & 31;
         float v = a < 3 ? 3.0e38f : -3.0e38f;
         for (uint32_t q = lane; q < OCC_PARTS; q += 32) v = a < 3 ? fminf(v, w.occ_box[q * 6 + a]) : fmaxf(v, w.occ_box[q * 6 + a]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { const float u = __shfl_xor_sync(0xffffffffu, v, o); v = a < 3 ? fminf(v, u) : fmaxf(v, u); }
-        if (lane == 0) bx[a] = v;
+        if (lane == 0) {
+            if (a < 3 && v <= -bound) v = -INFINITY;           // the box reaches the cube face: see k_occ_box
+            if (a >= 3 && v >= bound) v = INFINITY;
+            bx[a] = v;
+        }
     }
     __syncthreads();
+    DdaRay r;
+    r.dx = r.dy = r.dz = 1.0f;
+    r.init_common(bound, dt_gamma, max_steps, C, H, 0.0f);
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
-        const float ox = rays_o[3 * n], oy = rays_o[3 * n + 1], oz = rays_o[3 * n + 2];
-        const float rdx = 1.0f / rays_d[3 * n], rdy = 1.0f / rays_d[3 * n + 1], rdz = 1.0f / rays_d[3 * n + 2];
+        r.ox = rays_o[3 * n]; r.oy = rays_o[3 * n + 1]; r.oz = rays_o[3 * n + 2];
+        r.rdx = 1.0f / rays_d[3 * n]; r.rdy = 1.0f / rays_d[3 * n + 1]; r.rdz = 1.0f / rays_d[3 * n + 2];
         float tn, tf;
-        near_far_one(ox, oy, oz, rdx, rdy, rdz, a0, a1, a2, a3, a4, a5, min_near, tn, tf);
-        // stop marching where the ray leaves the grown occupied box (see k_occupied_box); a ray that misses it never starts
-        {
-            const float ax0 = (bx[0] - ox) * rdx, ax1 = (bx[3] - ox) * rdx, ay0 = (bx[1] - oy) * rdy, ay1 = (bx[4] - oy) * rdy, az0 = (bx[2] - oz) * rdz, az1 = (bx[5] - oz) * rdz;
-            const float t_in = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fminf(az0, az1));
-            const float t_out = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fmaxf(az0, az1));
-            if (!(t_in <= t_out)) tf = fminf(tf, 0.0f);                 // miss (or empty box): `t < far` is false from the start
-            else tf = fminf(tf, t_out);
-        }
-        w.nears[n] = tn; w.fars[n] = tf; w.rays_t[n] = tn;
+        near_far_one(r.ox, r.oy, r.oz, r.rdx, r.rdy, r.rdz, a0, a1, a2, a3, a4, a5, min_near, tn, tf);
+        float t = r.perturb(tn, 0.0f);            // noise = 0 (perturb is off at inference): fma(dt, 0, t) == t, kept for op parity
+        if (clip) { r.far = tf; tf = r.clip_to_box(bx, t); }
+        w.nears[n] = tn; w.fars[n] = tf; w.rays_t[n] = t;
         w.ws[n] = 0.0f; w.depth[n] = 0.0f; w.aud_sum[n] = 0.0f; w.eye_sum[n] = 0.0f; w.unc_sum[n] = 0.0f;
         w.image[3 * n] = 0.0f; w.image[3 * n + 1] = 0.0f; w.image[3 * n + 2] = 0.0f;
         w.alive[0][n] = (int32_t)n;
@@ -194,7 +152,7 @@ __global__ void __launch_bounds__(FM_THREADS) k_frame_march(const float *__restr
     if (valid) {
         id = w.alive[c.buf][n];
         r.init(rays_o + 3 * (size_t)id, rays_d + 3 * (size_t)id, bound, dt_gamma, max_steps, C, H, w.fars[id]);
-        float t = r.perturb(w.rays_t[id], 0.0f);      // noise = 0 (perturb is off at inference): fma(dt, 0, t) == t, kept for op parity
+        float t = w.rays_t[id];
         DdaSample s;
         while (t < r.far && step < n_step) {
             if (r.probe(grid, t, s)) {
@@ -207,19 +165,43 @@ __global__ void __launch_bounds__(FM_THREADS) k_frame_march(const float *__restr
     }
     const bool has = valid && step > 0;
     const uint32_t p = warp_append(has, &w.counters[0]);
-    if (has) {
-        w.alive_mid[p] = id;
-        float *px = w.xyzs + 3 * (size_t)p * n_step, *pd = w.dirs + 3 * (size_t)p * n_step, *pl = w.deltas + 2 * (size_t)p * n_step;
+    // The warp's surviving rays own the contiguous slot range [p0 n_step, (p0 + cnt) n_step): the 8 floats of a slot are staged through a 1 KB per-warp tile
+    // (the kernel must fit beside another frame's head CTA, which leaves ~7 KB of shared memory per SM) and leave as full 128-byte lines instead of
+    // 4-byte stores at a 12 n_step-byte stride.
+    __shared__ float s_stage[FM_THREADS / 32][256];
+    float *sw = s_stage[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, has), cnt = __popc(ballot), rank = __popc(ballot & ((1u << lane) - 1u));
+    if (cnt) {
+        const uint32_t p0 = __shfl_sync(0xffffffffu, p - rank, __ffs(ballot) - 1);
+        if (has) w.alive_mid[p] = id;
+#pragma unroll 1
+        for (uint32_t which = 0; which < 3; which++) {                    // 0: xyzs, 1: dirs, 2: deltas
+            const uint32_t comps = which == 2 ? 2u : 3u;
+            float *dst = which == 0 ? w.xyzs : (which == 1 ? w.dirs : w.deltas);
+            const uint32_t rpr = min(32u, 256u / (n_step * comps));       // rays per staging round (n_step <= 8: at least 10)
+#pragma unroll 1
+            for (uint32_t r0 = 0; r0 < cnt; r0 += rpr) {
+                if (has && rank >= r0 && rank < r0 + rpr) {
+                    float *q = sw + (rank - r0) * n_step * comps;
 #pragma unroll
-        for (uint32_t k = 0; k < 8; k++) {
-            if (k < n_step) {
-                if (k < step) {
-                    // the sample position is a pure function of t: same expression as DdaRay::probe
-                    px[0] = clampf(__fmaf_rn(ts[k], r.dx, r.ox), -bound, bound); px[1] = clampf(__fmaf_rn(ts[k], r.dy, r.oy), -bound, bound);
-                    px[2] = clampf(__fmaf_rn(ts[k], r.dz, r.oz), -bound, bound);
-                    pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz; pl[0] = dts[k]; pl[1] = __fadd_rn(ts[k], dts[k]);
-                } else { px[0] = 0.0f; px[1] = 0.0f; px[2] = 0.0f; pd[0] = 0.0f; pd[1] = 0.0f; pd[2] = 0.0f; pl[0] = 0.0f; pl[1] = 0.0f; }
-                px += 3; pd += 3; pl += 2;
+                    for (uint32_t k = 0; k < 8; k++) {
+                        if (k < n_step) {
+                            const bool f = k < step;
+                            if (which == 0) {      // the sample position is a pure function of t: same expression as DdaRay::probe
+                                q[3 * k] = f ? clampf(__fmaf_rn(ts[k], r.dx, r.ox), -bound, bound) : 0.0f;
+                                q[3 * k + 1] = f ? clampf(__fmaf_rn(ts[k], r.dy, r.oy), -bound, bound) : 0.0f;
+                                q[3 * k + 2] = f ? clampf(__fmaf_rn(ts[k], r.dz, r.oz), -bound, bound) : 0.0f;
+                            } else if (which == 1) { q[3 * k] = f ? r.dx : 0.0f; q[3 * k + 1] = f ? r.dy : 0.0f; q[3 * k + 2] = f ? r.dz : 0.0f; }
+                            else { q[2 * k] = f ? dts[k] : 0.0f; q[2 * k + 1] = f ? __fadd_rn(ts[k], dts[k]) : 0.0f; }
+                        }
+                    }
+                }
+                __syncwarp();
+                const uint32_t nfl = min(rpr, cnt - r0) * n_step * comps;
+                float *g = dst + (size_t)comps * (p0 + r0) * n_step;
+                for (uint32_t e = lane; e < nfl; e += 32) g[e] = sw[e];
+                __syncwarp();
             }
         }
     }
@@ -353,15 +335,17 @@ static int enqueue_init(const FramePlan &p, cudaStream_t st) {
                                                                                                  const_cast<float *>(p.rays_o), const_cast<float *>(p.rays_d));
         if (check_launch("render_frame(rays)")) return 1;
     }
-    // the argument needs probe positions == ray points, i.e. the marching interval (the aabb) inside the [-bound, bound]^3 cube where clamp() is a no-op
-    int inside = 1;
-    for (int a = 0; a < 3; a++) inside &= (p.cfg.aabb[a] >= -p.cfg.bound && p.cfg.aabb[3 + a] <= p.cfg.bound);
-    k_occupied_box<<<OCC_PARTS, 256, 0, st>>>(p.bitfield, p.cfg.cascade, p.cfg.grid_size, p.cfg.bound, inside, p.w.occ_box);
-    if (check_launch("render_frame(occupied box)")) return 1;
+    // exact empty-space clipping needs whole 32-cell words and a power-of-two grid (Morton blocks); otherwise march unclipped
+    const uint32_t H = p.cfg.grid_size;
+    const int clip = (H & (H - 1)) == 0 && H >= 4 && ((uintptr_t)p.bitfield & 3) == 0;
+    if (clip) {
+        k_occ_box<<<OCC_PARTS, 256, 0, st>>>(p.bitfield, p.cfg.cascade, H, p.cfg.bound, p.w.occ_box, 0);
+        if (check_launch("render_frame(occupied box)")) return 1;
+    }
     const uint32_t sms = (uint32_t)sm_count();
     uint32_t g = ceil_div<uint32_t>(p.N, 256); if (g > sms * 8) g = sms * 8;
     k_frame_init<<<g, 256, 0, st>>>(p.rays_o, p.rays_d, p.N, p.cfg.min_near, p.cfg.aabb[0], p.cfg.aabb[1], p.cfg.aabb[2], p.cfg.aabb[3], p.cfg.aabb[4], p.cfg.aabb[5],
-                                    p.cfg.max_steps, p.w);
+                                    p.cfg.max_steps, p.cfg.bound, p.cfg.dt_gamma, p.cfg.cascade, H, clip, p.w);
     return check_launch("render_frame(init)");
 }
 // one loop iteration: march (+ drop rays without samples) -> fused head -> composite (+ survivor list, next control block)

@@ -1,37 +1,46 @@
 // optim.cu — AdamW over ONE flat parameter buffer: the reference steps ~70 tensors through torch's AdamW after a GradScaler
 // unscale pass (TrainerUtil.py:1040-1056, network.py:315-357: tables lr 1e-2 / default weight decay, networks lr 1e-3 / no decay,
 // betas (0, 0.99), eps 1e-8 — train.py:274).  Here parameters, gradients and both moments each live in one contiguous fp32 buffer (the
-// gradient buffer is the one the data-parallel all-reduce uses), split in two hyper-parameter groups at `n0`; one launch does unscale +
-// skip-on-overflow + decoupled weight decay + moment update + parameter update.  The step counter, the loss scale and the overflow flag
+// gradient buffer is the one the data-parallel all-reduce uses), split into contiguous hyper-parameter groups (network.py:332-356: tables lr / AdamW's
+// default decay 0.01, networks lr_net / wd, audio_att_net 5 lr_net / 1e-4); one launch does unscale + skip-on-overflow + decoupled weight decay + moment
+// update + parameter update and, on the steps the trainer asks for it (TrainerUtil.py:1055-1056, every 1000 steps), the weight EMA of torch_ema.  The step counter, the loss scale and the overflow flag
 // stay on the device, so nothing in the optimizer step synchronises or blocks CUDA-graph capture.
 #include "common.cuh"
 
 namespace b2n {
-
-struct AdamGroup { float lr, weight_decay; };
 
 __global__ void k_adamw_step_count(float *step, const float *found_inf) {
     if (found_inf == nullptr || found_inf[0] == 0.0f) step[0] += 1.0f;
 }
 
 __global__ void __launch_bounds__(256) k_adamw_flat(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, uint32_t n,
-                                                    uint32_t n0, AdamGroup g0, AdamGroup g1, float beta1, float beta2, float eps,
-                                                    const float *__restrict__ step, const float *__restrict__ grad_scale, const float *__restrict__ found_inf) {
-    if (found_inf != nullptr && found_inf[0] != 0.0f) return;                 // overflow in this step's gradients: skip (GradScaler semantics)
+                                                    const __grid_constant__ b2n_adam_groups grp, float beta1, float beta2, float eps,
+                                                    const float *__restrict__ step, const float *__restrict__ grad_scale, const float *__restrict__ found_inf,
+                                                    float *__restrict__ ema, float ema_decay) {
+    const float one_minus_decay = 1.0f - ema_decay;
+    if (found_inf != nullptr && found_inf[0] != 0.0f) {                        // overflow in this step's gradients: skip (GradScaler semantics) ...
+        if (ema != nullptr)                                                    // ... but the reference's ema.update() still runs on the unchanged weights
+            for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { const float s = ema[i]; ema[i] = s - one_minus_decay * (s - p[i]); }
+        return;
+    }
     const float t = step[0];                                                   // already incremented by k_adamw_step_count
     const float inv_scale = grad_scale != nullptr ? 1.0f / grad_scale[0] : 1.0f;
     const float bias1 = 1.0f - powf(beta1, t), bias2 = 1.0f - powf(beta2, t);
     const float rsqrt_bias2 = 1.0f / sqrtf(bias2);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const AdamGroup h = i < n0 ? g0 : g1;
+        uint32_t k = 0;
+        while (k + 1 < grp.n_groups && i >= grp.end[k]) k++;                  // <= 8 contiguous hyper-parameter groups
+        const float lr = grp.lr[k], wd = grp.weight_decay[k];
         const float grad = g[i] * inv_scale;
         float w = p[i];
-        w -= h.lr * h.weight_decay * w;                                        // decoupled weight decay
+        w -= lr * wd * w;                                                      // decoupled weight decay
         const float mi = beta1 * m[i] + (1.0f - beta1) * grad;
         const float vi = beta2 * v[i] + (1.0f - beta2) * grad * grad;
         m[i] = mi; v[i] = vi;
         const float denom = sqrtf(vi) * rsqrt_bias2 + eps;
-        p[i] = w - (h.lr / bias1) * (mi / denom);
+        w -= (lr / bias1) * (mi / denom);
+        p[i] = w;
+        if (ema != nullptr) { const float s = ema[i]; ema[i] = s - one_minus_decay * (s - w); }     // torch_ema: shadow -= (1 - decay) (shadow - param)
     }
 }
 
@@ -39,11 +48,13 @@ __global__ void __launch_bounds__(256) k_adamw_flat(float *__restrict__ p, const
 
 using namespace b2n;
 
-extern "C" int b2n_adamw_flat(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, uint32_t n, uint32_t n_group0, float lr0,
-                              float weight_decay0, float lr1, float weight_decay1, float beta1, float beta2, float eps, float *step,
-                              const float *grad_scale, const float *found_inf, void *stream) {
-    B2N_REQUIRE(params && grads && exp_avg && exp_avg_sq && step, "adamw_flat: null pointer");
-    B2N_REQUIRE(n_group0 <= n, "adamw_flat: group boundary %u beyond n=%u", n_group0, n);
+extern "C" int b2n_adamw_flat_groups(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, uint32_t n, const b2n_adam_groups *groups, float beta1,
+                                     float beta2, float eps, float *step, const float *grad_scale, const float *found_inf, float *ema, float ema_decay, void *stream) {
+    B2N_REQUIRE(params && grads && exp_avg && exp_avg_sq && step && groups, "adamw_flat: null pointer");
+    B2N_REQUIRE(groups->n_groups >= 1 && groups->n_groups <= 8, "adamw_flat: %u groups (1..8)", groups->n_groups);
+    for (uint32_t k = 0; k < groups->n_groups; k++)
+        B2N_REQUIRE(groups->end[k] <= n && (k == 0 || groups->end[k] >= groups->end[k - 1]), "adamw_flat: group %u ends at %u (n = %u; ends must ascend)", k, groups->end[k], n);
+    B2N_REQUIRE(groups->end[groups->n_groups - 1] == n, "adamw_flat: the last group must end at n");
     if (n == 0) return 0;
     cudaStream_t st = as_stream(stream);
     k_adamw_step_count<<<1, 1, 0, st>>>(step, found_inf);
@@ -51,7 +62,15 @@ extern "C" int b2n_adamw_flat(float *params, const float *grads, float *exp_avg,
     uint32_t blocks = ceil_div<uint32_t>(n, 256);
     const uint32_t cap = (uint32_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    k_adamw_flat<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, n_group0, AdamGroup{lr0, weight_decay0}, AdamGroup{lr1, weight_decay1}, beta1,
-                                         beta2, eps, step, grad_scale, found_inf);
+    k_adamw_flat<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, *groups, beta1, beta2, eps, step, grad_scale, found_inf, ema, ema_decay);
     return check_launch("adamw_flat");
+}
+
+extern "C" int b2n_adamw_flat(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, uint32_t n, uint32_t n_group0, float lr0,
+                              float weight_decay0, float lr1, float weight_decay1, float beta1, float beta2, float eps, float *step,
+                              const float *grad_scale, const float *found_inf, void *stream) {
+    B2N_REQUIRE(n_group0 <= n, "adamw_flat: group boundary %u beyond n=%u", n_group0, n);
+    b2n_adam_groups g = {};
+    g.n_groups = 2; g.end[0] = n_group0; g.end[1] = n; g.lr[0] = lr0; g.lr[1] = lr1; g.weight_decay[0] = weight_decay0; g.weight_decay[1] = weight_decay1;
+    return b2n_adamw_flat_groups(params, grads, exp_avg, exp_avg_sq, n, &g, beta1, beta2, eps, step, grad_scale, found_inf, nullptr, 0.0f, stream);
 }

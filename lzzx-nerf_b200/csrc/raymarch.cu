@@ -115,27 +115,93 @@ __global__ void __launch_bounds__(256) k_morton3D_dilation(const float *__restri
 }
 
 // ---------------------------------------------------------------------------------------------------
+// grown occupied box (exact empty-space clipping, dda.cuh:clip_to_box)
+// ---------------------------------------------------------------------------------------------------
+// Box around all occupied cells of the bitfield, grown by two cells of the cell's own cascade, in world units (union over cascades).  A 32-bit word of the
+// Morton-ordered bitfield is a 4 x 4 x 2 block of cells (Morton bits 0,3 -> x, 1,4 -> y, 2 -> z); a non-empty word is taken whole (a superset is all the
+// exactness argument needs).  EXACTNESS: a probe at parameter t reads the cell containing clamp(o + t d, -bound, bound) up to one float ulp, i.e. at most the
+// neighbouring cell; a point more than two cells from every occupied cell therefore probes an empty cell.  The clamp maps points outside the scene cube onto
+// its faces, so a side of the box that comes within the cube face is opened to infinity (points beyond that face are not clipped); a side that stays inside
+// the cube is kept by the clamp (clamp(p)_a stays beyond it whenever p_a is).  The last CTA reduces the partial boxes.
+__global__ void __launch_bounds__(256) k_occ_box(const uint8_t *__restrict__ grid, uint32_t C, uint32_t H, float bound, float *__restrict__ parts, int finalize) {
+    __shared__ float red[6][8];
+    __shared__ int s_last;
+    const uint32_t H3 = H * H * H, words = C * H3 / 32;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (uint32_t wd = blockIdx.x * blockDim.x + threadIdx.x; wd < words; wd += gridDim.x * blockDim.x) {
+        const uint32_t bits = __ldg(reinterpret_cast<const uint32_t *>(grid) + wd);
+        if (bits) {
+            const uint32_t idx = wd * 32, level = idx / H3, m = idx - level * H3;
+            const float mb = fminf(scalbnf(1.0f, (int)level), bound);
+            const float cell = mb * 2.0f / (float)H;                // cell size of this cascade in world units
+            const uint32_t c[3] = {compact3(m), compact3(m >> 1), compact3(m >> 2)};
+            const float ext[3] = {3.0f, 3.0f, 1.0f};
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                lo[a] = fminf(lo[a], -mb + ((float)c[a] - 2.0f) * cell);
+                hi[a] = fmaxf(hi[a], -mb + ((float)c[a] + ext[a] + 3.0f) * cell);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
+    if ((threadIdx.x & 31) == 0) for (int a = 0; a < 3; a++) { red[a][threadIdx.x >> 5] = lo[a]; red[3 + a][threadIdx.x >> 5] = hi[a]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = red[threadIdx.x][0];
+        for (uint32_t w = 1; w < blockDim.x / 32; w++) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
+        parts[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+    if (!finalize) return;                        // the consumer reduces the partial boxes itself (k_frame_init)
+    int32_t *ticket = reinterpret_cast<int32_t *>(parts + 6 * OCC_PARTS + 6);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int32_t)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 6 * 32) {                   // warp a reduces component a of the partial boxes
+        const uint32_t a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        float v = a < 3 ? 3.0e38f : -3.0e38f;
+        for (uint32_t q = lane; q < gridDim.x; q += 32) { const float u = __ldcg(parts + q * 6 + a); v = a < 3 ? fminf(v, u) : fmaxf(v, u); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const float u = __shfl_xor_sync(0xffffffffu, v, o); v = a < 3 ? fminf(v, u) : fmaxf(v, u); }
+        if (lane == 0) {
+            if (a < 3 && v <= -bound) v = -INFINITY;           // the box reaches the cube face: beyond it clamp() lands on cells that may be occupied
+            if (a >= 3 && v >= bound) v = INFINITY;
+            parts[6 * OCC_PARTS + a] = v;
+        }
+    }
+    if (threadIdx.x == 0) *ticket = 0;             // re-armed for the next launch on this buffer
+}
+
+// ---------------------------------------------------------------------------------------------------
 // training march — raymarching.cu:353-518
 // ---------------------------------------------------------------------------------------------------
 constexpr int MT_THREADS = 128;
 
-// pass 1: count occupied steps per ray; rays[n] = (n, -, count); per-CTA totals to scratch
+// pass 1: count occupied steps per ray; rays[n] = (n, -, count); per-CTA totals to scratch.
+// t_cache [N][max_steps]: the parameter t of every sample, so that the write pass does not walk the bitfield again — a sample's position and step are
+// functions of (ray, t) alone.
 __global__ void __launch_bounds__(MT_THREADS) k_march_train_count(
         const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
         float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
         const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
-        int32_t *__restrict__ rays, const int32_t *__restrict__ counter, int32_t *__restrict__ cta_totals, float *__restrict__ t_cache) {
+        int32_t *__restrict__ rays, const int32_t *__restrict__ counter, int32_t *__restrict__ cta_totals, float *__restrict__ t_cache,
+        const float *__restrict__ box) {
     const uint32_t n = blockIdx.x * MT_THREADS + threadIdx.x;
     uint32_t num = 0;
     if (n < N) {
         DdaRay r;
         r.init(rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H, fars[n]);
         float t = r.perturb(nears[n], noises[n]);
+        if (box) r.far = r.clip_to_box(box, t);
         DdaSample s;
-        // t_cache [max_steps][N] (coalesced over rays): the parameter t of every sample, so that the write pass does not walk the bitfield again —
-        // a sample's position and step are functions of (ray, t) alone
+        float *tc = t_cache ? t_cache + (size_t)n * max_steps : nullptr;
         while (t < r.far && num < max_steps) {
-            if (r.probe(grid, t, s)) { if (t_cache) t_cache[(size_t)num * N + n] = t; num++; t = __fadd_rn(t, s.dt); }
+            if (r.probe(grid, t, s)) { if (tc) tc[num] = t; num++; t = __fadd_rn(t, s.dt); }
         }
         rays[3 * (size_t)n] = (int32_t)n;
         rays[3 * (size_t)n + 2] = (int32_t)num;
@@ -156,17 +222,11 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_count(
     }
 }
 
-// pass 2: offsets = snapshot + prefix(CTA totals) + in-CTA exclusive scan; re-march and write samples
-__global__ void __launch_bounds__(MT_THREADS) k_march_train_write(
-        const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
-        float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
-        const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
-        float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas,
-        int32_t *__restrict__ rays, int32_t *__restrict__ counter, const int32_t *__restrict__ cta_totals, const float *__restrict__ t_cache) {
-    __shared__ uint32_t red[MT_THREADS / 32];
-    __shared__ uint32_t s_base;
+// Shared prologue of both write kernels: offsets = snapshot + prefix(CTA totals) + in-CTA exclusive scan.  Returns this thread's (offset, count); the last
+// thread of the grid publishes the counters.  s_base = the CTA's first slot.
+__device__ __forceinline__ void march_train_offsets(uint32_t N, const int32_t *__restrict__ rays, int32_t *__restrict__ counter, const int32_t *__restrict__ cta_totals,
+                                                    uint32_t *red, uint32_t &s_base, uint32_t &off, uint32_t &num) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // base = snapshot + sum of totals of CTAs before this one
     uint32_t part = 0;
     for (uint32_t b = threadIdx.x; b < blockIdx.x; b += MT_THREADS) part += (uint32_t)cta_totals[1 + b];
 #pragma unroll
@@ -181,8 +241,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_write(
     }
     __syncthreads();
     const uint32_t n = blockIdx.x * MT_THREADS + threadIdx.x;
-    const uint32_t num = (n < N) ? (uint32_t)rays[3 * (size_t)n + 2] : 0u;
-    // in-CTA exclusive scan of num
+    num = (n < N) ? (uint32_t)rays[3 * (size_t)n + 2] : 0u;
     uint32_t inc = num;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
@@ -192,32 +251,93 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_write(
     uint32_t woff = 0;
 #pragma unroll
     for (int w = 0; w < MT_THREADS / 32; w++) if (w < (int)warp) woff += red[w];
-    const uint32_t off = s_base + woff + inc - num;
+    off = s_base + woff + inc - num;
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == MT_THREADS - 1) {
         // this thread's inclusive prefix is the grand total (threads past N contribute 0)
         atomicAdd(counter, (int32_t)(off + num - (uint32_t)cta_totals[0]));
         atomicAdd(counter + 1, (int32_t)N);
     }
+}
+
+// pass 2 (t_cache present): OUTPUT-centric.  The samples of a CTA's 128 consecutive rays form one contiguous slot range [s_base, s_base + total): thread j
+// produces slot j (its ray found by a search over the CTA's 128 segment starts in shared memory, its t read from the ray's t_cache row), the 8 floats of a
+// slot go through a shared-memory tile and leave as full contiguous lines of xyzs / dirs / deltas — instead of one thread walking its ray with 4-byte
+// stores at a 12-byte stride.  Same expressions as DdaRay::probe for an occupied cell: bit-identical samples.
+constexpr uint32_t MW_TILE = 512;                 // slots staged per round (16 KB of shared memory)
+__global__ void __launch_bounds__(MT_THREADS) k_march_train_emit(
+        const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+        float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas,
+        int32_t *__restrict__ rays, int32_t *__restrict__ counter, const int32_t *__restrict__ cta_totals, const float *__restrict__ t_cache) {
+    __shared__ uint32_t red[MT_THREADS / 32];
+    __shared__ uint32_t s_base, s_keep;
+    __shared__ uint32_t s_start[MT_THREADS + 1];           // first slot (relative to s_base) of every ray of the CTA; [128] = total kept
+    __shared__ float s_ray[MT_THREADS][6];
+    __shared__ float s_xyz[MW_TILE * 3], s_dir[MW_TILE * 3], s_del[MW_TILE * 2];
+    uint32_t off, num;
+    march_train_offsets(N, rays, counter, cta_totals, red, s_base, off, num);
+    const uint32_t n = blockIdx.x * MT_THREADS + threadIdx.x;
+    if (n < N) {
+        rays[3 * (size_t)n + 1] = (int32_t)off;
+#pragma unroll
+        for (int c = 0; c < 3; c++) { s_ray[threadIdx.x][c] = rays_o[3 * (size_t)n + c]; s_ray[threadIdx.x][3 + c] = rays_d[3 * (size_t)n + c]; }
+    }
+    if (threadIdx.x == 0) s_keep = 0xffffffffu;
+    __syncthreads();
+    // rays past the buffer are dropped whole (raymarching.cu:456-457); offsets ascend, so the kept slots are a prefix of the CTA's range
+    const bool dropped = num > 0 && off + num > M;
+    if (dropped) atomicMin(&s_keep, off - s_base);
+    s_start[threadIdx.x] = off - s_base;
+    if (threadIdx.x == MT_THREADS - 1) s_start[MT_THREADS] = off + num - s_base;
+    __syncthreads();
+    const uint32_t total = min(s_start[MT_THREADS], s_keep);
+    DdaRay q;                                              // only the step rule is used
+    q.dx = q.dy = q.dz = 1.0f;
+    q.init_common(bound, dt_gamma, max_steps, C, H, 0.0f);
+    for (uint32_t j0 = 0; j0 < total; j0 += MW_TILE) {
+        const uint32_t cnt = min(MW_TILE, total - j0);
+        for (uint32_t j = threadIdx.x; j < cnt; j += MT_THREADS) {
+            const uint32_t slot = j0 + j;
+            uint32_t lo = 0, hi = MT_THREADS;              // largest r with s_start[r] <= slot (rays without samples share a start with their successor: skipped)
+#pragma unroll
+            for (int it = 0; it < 7; it++) { const uint32_t mid = (lo + hi) >> 1; if (s_start[mid] <= slot) lo = mid; else hi = mid; }
+            const uint32_t k = slot - s_start[lo];
+            const float tk = __ldcs(t_cache + ((size_t)blockIdx.x * MT_THREADS + lo) * max_steps + k);
+            const float dt = q.step_of(tk);
+            const float *ry = s_ray[lo];
+            s_xyz[3 * j] = clampf(__fmaf_rn(tk, ry[3], ry[0]), -bound, bound);
+            s_xyz[3 * j + 1] = clampf(__fmaf_rn(tk, ry[4], ry[1]), -bound, bound);
+            s_xyz[3 * j + 2] = clampf(__fmaf_rn(tk, ry[5], ry[2]), -bound, bound);
+            s_dir[3 * j] = ry[3]; s_dir[3 * j + 1] = ry[4]; s_dir[3 * j + 2] = ry[5];
+            s_del[2 * j] = dt; s_del[2 * j + 1] = __fadd_rn(tk, dt);
+        }
+        __syncthreads();
+        const size_t g0 = (size_t)s_base + j0;
+        for (uint32_t e = threadIdx.x; e < 3 * cnt; e += MT_THREADS) { __stcs(xyzs + 3 * g0 + e, s_xyz[e]); __stcs(dirs + 3 * g0 + e, s_dir[e]); }
+        for (uint32_t e = threadIdx.x; e < 2 * cnt; e += MT_THREADS) __stcs(deltas + 2 * g0 + e, s_del[e]);
+        __syncthreads();
+    }
+}
+
+// pass 2 without a t cache (very large max_steps): re-march and write samples, one thread per ray
+__global__ void __launch_bounds__(MT_THREADS) k_march_train_write(
+        const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+        float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+        const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
+        float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas,
+        int32_t *__restrict__ rays, int32_t *__restrict__ counter, const int32_t *__restrict__ cta_totals, const float *__restrict__ box) {
+    __shared__ uint32_t red[MT_THREADS / 32];
+    __shared__ uint32_t s_base;
+    uint32_t off, num;
+    march_train_offsets(N, rays, counter, cta_totals, red, s_base, off, num);
+    const uint32_t n = blockIdx.x * MT_THREADS + threadIdx.x;
     if (n >= N) return;
     rays[3 * (size_t)n + 1] = (int32_t)off;
     if (num == 0 || off + num > M) return;       // raymarching.cu:456-457
     DdaRay r;
     r.init(rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H, fars[n]);
     float *px = xyzs + 3 * (size_t)off, *pd = dirs + 3 * (size_t)off, *pl = deltas + 2 * (size_t)off;
-    if (t_cache) {                               // replay the recorded parameters: same expressions as DdaRay::probe for an occupied cell
-        for (uint32_t k = 0; k < num; k++) {
-            const float tk = __ldcs(t_cache + (size_t)k * N + n);
-            const float dt = r.step_of(tk);
-            px[0] = clampf(__fmaf_rn(tk, r.dx, r.ox), -bound, bound);
-            px[1] = clampf(__fmaf_rn(tk, r.dy, r.oy), -bound, bound);
-            px[2] = clampf(__fmaf_rn(tk, r.dz, r.oz), -bound, bound);
-            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
-            pl[0] = dt; pl[1] = __fadd_rn(tk, dt);
-            px += 3; pd += 3; pl += 2;
-        }
-        return;
-    }
     float t = r.perturb(nears[n], noises[n]);
+    if (box) r.far = r.clip_to_box(box, t);
     uint32_t step = 0;
     DdaSample s;
     while (t < r.far && step < num) {
@@ -259,18 +379,80 @@ __global__ void __launch_bounds__(128) k_march_train_backward(
 // ---------------------------------------------------------------------------------------------------
 // inference march — raymarching.cu:828-929
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_march_rays(
+// One thread marches one alive ray (the t recurrence is serial), keeping the <= n_step sample parameters in shared memory; the CTA's 128 rays own the
+// contiguous slot range [128 b n_step, 128 (b + 1) n_step), which is then produced slot by slot and written as full lines (unfilled slots as zeros — the
+// "ray ended" sentinel of the composite, raymarching.cu:982; the reference relies on a torch.zeros fill for them).
+constexpr int MI_THREADS = 128;
+constexpr uint32_t MI_MAX_STEP = 8;               // the staged path covers n_step <= 8 (renderer.py:506-513 never asks for more)
+__global__ void __launch_bounds__(MI_THREADS) k_march_rays(
         uint32_t n_alive, uint32_t n_step, const int32_t *__restrict__ rays_alive, const float *__restrict__ rays_t,
         const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, float dt_gamma,
         uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *__restrict__ grid,
         const float *__restrict__ fars, float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas,
-        const float *__restrict__ noises) {
+        const float *__restrict__ noises, const float *__restrict__ box) {
+    __shared__ float s_t[MI_THREADS][MI_MAX_STEP + 1];       // +1: conflict-free rows
+    __shared__ float s_ray[MI_THREADS][6];
+    __shared__ uint32_t s_cnt[MI_THREADS];
+    __shared__ float s_xyz[MI_THREADS * 3], s_dir[MI_THREADS * 3], s_del[MI_THREADS * 2];
+    const uint32_t n = blockIdx.x * MI_THREADS + threadIdx.x;
+    DdaRay r;
+    uint32_t step = 0;
+    if (n < n_alive) {
+        const int32_t id = rays_alive[n];
+        r.init(rays_o + 3 * (size_t)id, rays_d + 3 * (size_t)id, bound, dt_gamma, max_steps, C, H, fars[id]);
+        float t = r.perturb(rays_t[id], noises[n]);
+        if (box) r.far = r.clip_to_box(box, t);
+        DdaSample s;
+        while (t < r.far && step < n_step) {
+            if (r.probe(grid, t, s)) { s_t[threadIdx.x][step] = t; t = __fadd_rn(t, s.dt); step++; }
+        }
+        s_ray[threadIdx.x][0] = r.ox; s_ray[threadIdx.x][1] = r.oy; s_ray[threadIdx.x][2] = r.oz;
+        s_ray[threadIdx.x][3] = r.dx; s_ray[threadIdx.x][4] = r.dy; s_ray[threadIdx.x][5] = r.dz;
+    } else {
+        r.dx = r.dy = r.dz = 1.0f;
+        r.init_common(bound, dt_gamma, max_steps, C, H, 0.0f);
+    }
+    s_cnt[threadIdx.x] = step;
+    __syncthreads();
+    const uint32_t rays_here = min((uint32_t)MI_THREADS, n_alive - blockIdx.x * MI_THREADS);
+    const uint32_t slots = rays_here * n_step;
+    const size_t g0 = (size_t)blockIdx.x * MI_THREADS * n_step;
+    for (uint32_t j0 = 0; j0 < slots; j0 += MI_THREADS) {
+        const uint32_t j = j0 + threadIdx.x;
+        if (j < slots) {
+            const uint32_t ry = j / n_step, k = j - ry * n_step;
+            const bool have = k < s_cnt[ry];
+            const float tk = have ? s_t[ry][k] : 0.0f;
+            const float dt = r.step_of(tk);
+            const float *q = s_ray[ry];
+            s_xyz[3 * threadIdx.x] = have ? clampf(__fmaf_rn(tk, q[3], q[0]), -bound, bound) : 0.0f;
+            s_xyz[3 * threadIdx.x + 1] = have ? clampf(__fmaf_rn(tk, q[4], q[1]), -bound, bound) : 0.0f;
+            s_xyz[3 * threadIdx.x + 2] = have ? clampf(__fmaf_rn(tk, q[5], q[2]), -bound, bound) : 0.0f;
+            s_dir[3 * threadIdx.x] = have ? q[3] : 0.0f; s_dir[3 * threadIdx.x + 1] = have ? q[4] : 0.0f; s_dir[3 * threadIdx.x + 2] = have ? q[5] : 0.0f;
+            s_del[2 * threadIdx.x] = have ? dt : 0.0f; s_del[2 * threadIdx.x + 1] = have ? __fadd_rn(tk, dt) : 0.0f;
+        }
+        __syncthreads();
+        const uint32_t cnt = min((uint32_t)MI_THREADS, slots - j0);
+        for (uint32_t e = threadIdx.x; e < 3 * cnt; e += MI_THREADS) { xyzs[3 * (g0 + j0) + e] = s_xyz[e]; dirs[3 * (g0 + j0) + e] = s_dir[e]; }
+        for (uint32_t e = threadIdx.x; e < 2 * cnt; e += MI_THREADS) deltas[2 * (g0 + j0) + e] = s_del[e];
+        __syncthreads();
+    }
+}
+
+// n_step > 8 (not reachable from renderer.py): the plain thread-per-ray writer
+__global__ void __launch_bounds__(128) k_march_rays_long(
+        uint32_t n_alive, uint32_t n_step, const int32_t *__restrict__ rays_alive, const float *__restrict__ rays_t,
+        const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, float dt_gamma,
+        uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *__restrict__ grid,
+        const float *__restrict__ fars, float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas,
+        const float *__restrict__ noises, const float *__restrict__ box) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n_alive) return;
     const int32_t id = rays_alive[n];
     DdaRay r;
     r.init(rays_o + 3 * (size_t)id, rays_d + 3 * (size_t)id, bound, dt_gamma, max_steps, C, H, fars[id]);
     float t = r.perturb(rays_t[id], noises[n]);
+    if (box) r.far = r.clip_to_box(box, t);
     float *px = xyzs + 3 * (size_t)n * n_step, *pd = dirs + 3 * (size_t)n * n_step, *pl = deltas + 2 * (size_t)n * n_step;
     uint32_t step = 0;
     DdaSample s;
@@ -342,31 +524,61 @@ int b2n_morton3D_dilation(const float *grid, uint32_t C, uint32_t H, float *grid
     return check_launch("morton3D_dilation");
 }
 
+// workspace layout: [box OCC_BOX_FLOATS floats | cta totals (ctas + 1) int32 | t cache N * max_steps floats (only when max_steps <= 64)]
+static inline size_t mt_align(size_t v) { return (v + 255) & ~(size_t)255; }
+static inline bool mt_cached(uint32_t N, uint32_t max_steps) { return max_steps <= 64 && (uint64_t)max_steps * N <= (64ull << 20); }
+
+uint64_t b2n_march_rays_train_workspace_bytes(uint32_t N, uint32_t max_steps) {
+    const uint32_t ctas = ceil_div<uint32_t>(N ? N : 1, MT_THREADS);
+    return mt_align(sizeof(float) * OCC_BOX_FLOATS) + mt_align(sizeof(int32_t) * (size_t)(ctas + 1)) +
+           (mt_cached(N, max_steps) ? mt_align(sizeof(float) * (size_t)max_steps * N) : 0);
+}
+
+int b2n_march_rays_train_ws(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                            uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
+                            const float *fars, float *xyzs, float *dirs, float *deltas, int32_t *rays, int32_t *counter,
+                            const float *noises, void *workspace, void *stream) {
+    B2N_REQUIRE(rays_o && rays_d && grid && nears && fars && rays && counter && noises, "march_rays_train: null pointer");
+    B2N_REQUIRE(M == 0 || (xyzs && dirs && deltas), "march_rays_train: null output with M=%u", M);
+    B2N_REQUIRE(C >= 1 && C <= 24 && H >= 1 && H <= 1024, "march_rays_train: cascade=%u / grid=%u unsupported", C, H);
+    B2N_REQUIRE(workspace && ((uintptr_t)workspace & 15) == 0, "march_rays_train: workspace must be a 16-byte aligned device buffer of b2n_march_rays_train_workspace_bytes()");
+    if (N == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    const uint32_t ctas = ceil_div<uint32_t>(N, MT_THREADS);
+    char *ws = (char *)workspace;
+    float *box = (float *)ws;
+    int32_t *totals = (int32_t *)(ws + mt_align(sizeof(float) * OCC_BOX_FLOATS));
+    // per-sample t cache between the two passes ([N][max_steps] floats: 4 MB for the 65 536-ray step); very large max_steps fall back to re-marching
+    float *t_cache = mt_cached(N, max_steps) ? (float *)((char *)totals + mt_align(sizeof(int32_t) * (size_t)(ctas + 1))) : nullptr;
+    // exact empty-space clipping needs whole 32-cell words and a power-of-two grid (Morton blocks); otherwise march unclipped
+    const bool clip = (H & (H - 1)) == 0 && H >= 4 && ((uintptr_t)grid & 3) == 0;
+    if (clip) {
+        B2N_CUDA(cudaMemsetAsync(box + 6 * OCC_PARTS + 6, 0, 2 * sizeof(float), st));
+        k_occ_box<<<OCC_PARTS, 256, 0, st>>>(grid, C, H, bound, box, 1);
+        if (check_launch("march_rays_train(box)")) return 1;
+    }
+    const float *boxp = clip ? box + 6 * OCC_PARTS : nullptr;
+    k_march_train_count<<<ctas, MT_THREADS, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, totals, t_cache, boxp);
+    if (check_launch("march_rays_train(count)")) return 1;
+    if (t_cache)
+        k_march_train_emit<<<ctas, MT_THREADS, 0, st>>>(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, xyzs, dirs, deltas, rays, counter, totals, t_cache);
+    else
+        k_march_train_write<<<ctas, MT_THREADS, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, noises, xyzs, dirs, deltas, rays,
+                                                         counter, totals, boxp);
+    return check_launch("march_rays_train(write)");
+}
+
+// The reference's argument list (raymarching.h:18): scratch comes from a library-internal grow-only block per device, so calls on ONE device must be
+// stream-ordered with each other (the reference's own kernels all run on the legacy default stream).  Callers that march concurrently on several streams
+// (or capture into CUDA graphs that outlive later, larger calls) use b2n_march_rays_train_ws with their own workspace — the Python drop-in does.
 int b2n_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
                          const float *fars, float *xyzs, float *dirs, float *deltas, int32_t *rays, int32_t *counter,
                          const float *noises, void *stream) {
-    B2N_REQUIRE(rays_o && rays_d && grid && nears && fars && rays && counter && noises, "march_rays_train: null pointer");
-    B2N_REQUIRE(M == 0 || (xyzs && dirs && deltas), "march_rays_train: null output with M=%u", M);
-    B2N_REQUIRE(C >= 1 && C <= 24 && H >= 1 && H <= 1024, "march_rays_train: cascade=%u / grid=%u unsupported", C, H);
     if (N == 0) return 0;
-    const uint32_t ctas = ceil_div<uint32_t>(N, MT_THREADS);
-    int32_t *totals = (int32_t *)scratch(sizeof(int32_t) * (size_t)(ctas + 1), 0);
-    B2N_REQUIRE(totals, "march_rays_train: scratch allocation failed");
-    // per-sample t cache between the two passes (max_steps x N floats: 4 MB for the 65 536-ray step); large max_steps fall back to re-marching
-    float *t_cache = nullptr;
-    // (at least 16 MB is requested: the grow-only scratch block then keeps its address for every batch up to 262 144 rays x 16 steps, so a CUDA graph that
-    // captured this call is not left pointing at a freed block when a later, larger batch comes along)
-    if (max_steps <= 64 && (uint64_t)max_steps * N <= (64ull << 20)) {
-        const size_t need = sizeof(float) * (size_t)max_steps * N;
-        t_cache = (float *)scratch(need > (16u << 20) ? need : (size_t)(16u << 20), 2);
-    }
-    k_march_train_count<<<ctas, MT_THREADS, 0, as_stream(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
-                                                                      nears, fars, noises, rays, counter, totals, t_cache);
-    if (check_launch("march_rays_train(count)")) return 1;
-    k_march_train_write<<<ctas, MT_THREADS, 0, as_stream(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
-                                                                      nears, fars, noises, xyzs, dirs, deltas, rays, counter, totals, t_cache);
-    return check_launch("march_rays_train(write)");
+    void *ws = scratch((size_t)b2n_march_rays_train_workspace_bytes(N, max_steps), 0);
+    B2N_REQUIRE(ws, "march_rays_train: scratch allocation failed");
+    return b2n_march_rays_train_ws(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises, ws, stream);
 }
 
 int b2n_march_rays_train_backward(const float *grad_xyzs, const float *grad_dirs, const int32_t *rays, const float *deltas,
@@ -377,17 +589,43 @@ int b2n_march_rays_train_backward(const float *grad_xyzs, const float *grad_dirs
     return check_launch("march_rays_train_backward");
 }
 
-int b2n_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t, const float *rays_o,
-                   const float *rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
-                   const uint8_t *grid, const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
-                   const float *noises, void *stream) {
+uint64_t b2n_march_rays_workspace_bytes(void) { return mt_align(sizeof(float) * OCC_BOX_FLOATS); }
+
+int b2n_march_rays_ws(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t, const float *rays_o,
+                      const float *rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                      const uint8_t *grid, const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                      const float *noises, void *workspace, void *stream) {
     (void)nears;
     B2N_REQUIRE(rays_alive && rays_t && rays_o && rays_d && grid && fars && xyzs && dirs && deltas && noises, "march_rays: null pointer");
     B2N_REQUIRE(C >= 1 && C <= 24 && H >= 1 && H <= 1024, "march_rays: cascade=%u / grid=%u unsupported", C, H);
     if (n_alive == 0 || n_step == 0) return 0;
-    k_march_rays<<<ceil_div<uint32_t>(n_alive, 128), 128, 0, as_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound,
-                                                                                   dt_gamma, max_steps, C, H, grid, fars, xyzs, dirs, deltas, noises);
+    cudaStream_t st = as_stream(stream);
+    const bool clip = workspace != nullptr && (H & (H - 1)) == 0 && H >= 4 && ((uintptr_t)grid & 3) == 0;
+    float *box = (float *)workspace;
+    if (clip) {
+        B2N_CUDA(cudaMemsetAsync(box + 6 * OCC_PARTS + 6, 0, 2 * sizeof(float), st));
+        k_occ_box<<<OCC_PARTS, 256, 0, st>>>(grid, C, H, bound, box, 1);
+        if (check_launch("march_rays(box)")) return 1;
+    }
+    const float *boxp = clip ? box + 6 * OCC_PARTS : nullptr;
+    if (n_step <= MI_MAX_STEP)
+        k_march_rays<<<ceil_div<uint32_t>(n_alive, MI_THREADS), MI_THREADS, 0, st>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
+                                                                                     grid, fars, xyzs, dirs, deltas, noises, boxp);
+    else
+        k_march_rays_long<<<ceil_div<uint32_t>(n_alive, 128), 128, 0, st>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
+                                                                            fars, xyzs, dirs, deltas, noises, boxp);
     return check_launch("march_rays");
+}
+
+// the reference's argument list (raymarching.h:20): library-internal scratch for the occupied box — see b2n_march_rays_train
+int b2n_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t, const float *rays_o,
+                   const float *rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                   const uint8_t *grid, const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                   const float *noises, void *stream) {
+    void *ws = scratch((size_t)b2n_march_rays_workspace_bytes(), 1);
+    B2N_REQUIRE(ws, "march_rays: scratch allocation failed");
+    return b2n_march_rays_ws(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, noises, ws,
+                             stream);
 }
 
 }  // extern "C"

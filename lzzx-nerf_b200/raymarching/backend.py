@@ -11,6 +11,7 @@ import types
 import torch
 
 from b2nerf.shim import call, dev_ptr, stream_ptr
+from b2nerf._lib import lib
 
 f32, i32, u8 = torch.float32, torch.int32, torch.uint8
 
@@ -45,9 +46,12 @@ def morton3D_dilation(grid, C, H, grid_dilation):
 
 
 def march_rays_train(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises):
-    call("b2n_march_rays_train", _p(rays_o, "rays_o"), _p(rays_d, "rays_d"), _p(grid, "grid", u8), bound, dt_gamma, max_steps,
+    # the marcher's scratch (occupied box, per-CTA totals, per-sample t cache) is a torch allocation of THIS call: stream-ordered by the caching allocator,
+    # so concurrent marches on different streams and CUDA graphs that captured an earlier call never share or lose it
+    ws = torch.empty(int(lib().raw("b2n_march_rays_train_workspace_bytes")(N, max_steps)), dtype=u8, device=rays_o.device)
+    call("b2n_march_rays_train_ws", _p(rays_o, "rays_o"), _p(rays_d, "rays_d"), _p(grid, "grid", u8), bound, dt_gamma, max_steps,
          N, C, H, M, _p(nears, "nears"), _p(fars, "fars"), _p(xyzs, "xyzs"), _p(dirs, "dirs"), _p(deltas, "deltas"),
-         _p(rays, "rays", i32), _p(counter, "counter", i32), _p(noises, "noises"), stream_ptr(rays_o))
+         _p(rays, "rays", i32), _p(counter, "counter", i32), _p(noises, "noises"), ws.data_ptr(), stream_ptr(rays_o))
 
 
 def march_rays_train_backward(grad_xyzs, grad_dirs, rays, deltas, N, M, grad_rays_o, grad_rays_d):
@@ -56,9 +60,10 @@ def march_rays_train_backward(grad_xyzs, grad_dirs, rays, deltas, N, M, grad_ray
 
 
 def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, noises):
-    call("b2n_march_rays", n_alive, n_step, _p(rays_alive, "rays_alive", i32), _p(rays_t, "rays_t"), _p(rays_o, "rays_o"),
+    ws = torch.empty(int(lib().raw("b2n_march_rays_workspace_bytes")()), dtype=u8, device=rays_o.device)      # occupied box of the bitfield (see march_rays_train)
+    call("b2n_march_rays_ws", n_alive, n_step, _p(rays_alive, "rays_alive", i32), _p(rays_t, "rays_t"), _p(rays_o, "rays_o"),
          _p(rays_d, "rays_d"), bound, dt_gamma, max_steps, C, H, _p(grid, "grid", u8), _p(nears, "nears"), _p(fars, "fars"),
-         _p(xyzs, "xyzs"), _p(dirs, "dirs"), _p(deltas, "deltas"), _p(noises, "noises"), stream_ptr(rays_o))
+         _p(xyzs, "xyzs"), _p(dirs, "dirs"), _p(deltas, "deltas"), _p(noises, "noises"), ws.data_ptr(), stream_ptr(rays_o))
 
 
 # ---- composites: (C-ABI suffix, extra per-sample inputs, extra per-ray accumulators) ----------------------------

@@ -90,7 +90,7 @@ def head_forward(p, x, d, enc_a, c, e, testing=True):
     if testing:
         unc = torch.full((x.shape[0],), math.log(2.0))
     else:
-        unc = torch.log(1 + torch.exp(_mlp(enc_x, [p["unc_net.net.0.weight"], p["unc_net.net.1.weight"]])))[:, 0]
+        unc = torch.log(1 + torch.exp(_mlp(enc_x.detach(), [p["unc_net.net.0.weight"], p["unc_net.net.1.weight"]])))[:, 0]      # unc_net(unc_inp.detach()), network.py:247
     return sigma, color, att.norm(dim=1), eye_att[:, 0], unc
 
 

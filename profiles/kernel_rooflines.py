@@ -42,97 +42,103 @@ def timeit(fn, warm=3, reps=10):
     return e0.elapsed_time(e1) / reps * 1e-3
 
 
-rows = []
+def measure():
+    """Runs every measurement; returns {hbm_peak_gbs, peak_source, kernels: [...]}."""
+    rows = []
 
 
-def report(name, alg_bytes, sec, note=""):
-    gbs = alg_bytes / sec / 1e9
-    rows.append({"kernel": name, "alg_bytes": int(alg_bytes), "us": sec * 1e6, "achieved_gbs": gbs, "frac_of_hbm": gbs / HBM, "note": note})
+    def report(name, alg_bytes, sec, note=""):
+        gbs = alg_bytes / sec / 1e9
+        rows.append({"kernel": name, "alg_bytes": int(alg_bytes), "us": sec * 1e6, "achieved_gbs": gbs, "frac_of_hbm": gbs / HBM, "note": note})
 
 
-torch.manual_seed(0)
-# ---- composites: 4 M rays, 0..16 samples each (mean 8) -> 33 M samples, 1.2 GB of per-sample inputs -----------------------------
-N = 4 * 1024 * 1024
-counts = torch.randint(0, 17, (N,), device=dev, dtype=torch.int32)
-offs = torch.cumsum(counts, 0, dtype=torch.int32) - counts
-rays = torch.stack([torch.arange(N, device=dev, dtype=torch.int32), offs, counts], 1).contiguous()
-M = int(counts.sum())
-sig = torch.rand(M, device=dev) * 5; rgb = torch.rand(M, 3, device=dev); aud = torch.rand(M, device=dev); eye = torch.rand(M, device=dev)
-unc = torch.rand(M, device=dev); dl = torch.rand(M, 2, device=dev) * 0.03 + 0.01
-ws, a0, a1, us, dep = (torch.empty(N, device=dev) for _ in range(5)); img = torch.empty(N, 3, device=dev)
-f = lambda: rb.composite_rays_train_triplane_forward(sig, rgb, aud, eye, unc, dl, rays, M, N, 1e-4, ws, a0, a1, us, dep, img)
-report("composite_rays_train_triplane_forward", 36 * M + 44 * N, timeit(f), f"N={N} rays, M={M} samples (tiled layout -> smem-staged path)")
-g_ws, g_a0, g_a1, g_u = (torch.randn(N, device=dev) for _ in range(4)); g_img = torch.randn(N, 3, device=dev)
-gs, ga0, ga1, gu = (torch.zeros(M, device=dev) for _ in range(4)); grgb = torch.zeros(M, 3, device=dev)
-f = lambda: rb.composite_rays_train_triplane_backward(g_ws, g_a0, g_a1, g_u, g_img, sig, rgb, aud, eye, unc, dl, rays, ws, a0, a1, us, img, M, N, 1e-4, gs, grgb, ga0, ga1, gu)
-report("composite_rays_train_triplane_backward", (36 + 28) * M + (12 + 32 + 28) * N, timeit(f), "same rays")
-perm = torch.randperm(N, device=dev)
-rays_sh = rays[perm].contiguous()
-f = lambda: rb.composite_rays_train_triplane_forward(sig, rgb, aud, eye, unc, dl, rays_sh, M, N, 1e-4, ws, a0, a1, us, dep, img)
-report("composite_rays_train_triplane_forward[shuffled rows: direct path]", 36 * M + 44 * N, timeit(f), "rows permuted like the reference's atomic allocation")
-del gs, ga0, ga1, gu, grgb
-# inference composite: 8 M alive rays x 4 steps
-na, ns = 8 * 1024 * 1024, 4
-Mi = na * ns
-alive = torch.arange(na, device=dev, dtype=torch.int32); rays_t = torch.rand(na, device=dev)
-acc = [torch.zeros(na, device=dev) for _ in range(5)]; imgi = torch.zeros(na, 3, device=dev)
-sig_i, rgb_i, dl_i = sig[:Mi], rgb[:Mi], dl[:Mi]
-f = lambda: rb.composite_rays_triplane(na, ns, 1e-4, alive.clone(), rays_t, sig_i, rgb_i, dl_i, aud[:Mi], eye[:Mi], unc[:Mi], acc[0], acc[1], imgi, acc[2], acc[3], acc[4])
-t_clone = timeit(lambda: alive.clone())
-report("composite_rays_triplane", 36 * Mi + (8 + 64) * na, timeit(f) - t_clone, f"n_alive={na}, n_step={ns}")
-del sig, rgb, aud, eye, unc, dl, rays, rays_sh, perm, acc, imgi
-torch.cuda.empty_cache()
+    torch.manual_seed(0)
+    # ---- composites: 4 M rays, 0..16 samples each (mean 8) -> 33 M samples, 1.2 GB of per-sample inputs -----------------------------
+    N = 4 * 1024 * 1024
+    counts = torch.randint(0, 17, (N,), device=dev, dtype=torch.int32)
+    offs = torch.cumsum(counts, 0, dtype=torch.int32) - counts
+    rays = torch.stack([torch.arange(N, device=dev, dtype=torch.int32), offs, counts], 1).contiguous()
+    M = int(counts.sum())
+    sig = torch.rand(M, device=dev) * 5; rgb = torch.rand(M, 3, device=dev); aud = torch.rand(M, device=dev); eye = torch.rand(M, device=dev)
+    unc = torch.rand(M, device=dev); dl = torch.rand(M, 2, device=dev) * 0.03 + 0.01
+    ws, a0, a1, us, dep = (torch.empty(N, device=dev) for _ in range(5)); img = torch.empty(N, 3, device=dev)
+    f = lambda: rb.composite_rays_train_triplane_forward(sig, rgb, aud, eye, unc, dl, rays, M, N, 1e-4, ws, a0, a1, us, dep, img)
+    report("composite_rays_train_triplane_forward", 36 * M + 44 * N, timeit(f), f"N={N} rays, M={M} samples (tiled layout -> smem-staged path)")
+    g_ws, g_a0, g_a1, g_u = (torch.randn(N, device=dev) for _ in range(4)); g_img = torch.randn(N, 3, device=dev)
+    gs, ga0, ga1, gu = (torch.zeros(M, device=dev) for _ in range(4)); grgb = torch.zeros(M, 3, device=dev)
+    f = lambda: rb.composite_rays_train_triplane_backward(g_ws, g_a0, g_a1, g_u, g_img, sig, rgb, aud, eye, unc, dl, rays, ws, a0, a1, us, img, M, N, 1e-4, gs, grgb, ga0, ga1, gu)
+    report("composite_rays_train_triplane_backward", (36 + 28) * M + (12 + 32 + 28) * N, timeit(f), "same rays")
+    perm = torch.randperm(N, device=dev)
+    rays_sh = rays[perm].contiguous()
+    f = lambda: rb.composite_rays_train_triplane_forward(sig, rgb, aud, eye, unc, dl, rays_sh, M, N, 1e-4, ws, a0, a1, us, dep, img)
+    report("composite_rays_train_triplane_forward[shuffled rows: direct path]", 36 * M + 44 * N, timeit(f), "rows permuted like the reference's atomic allocation")
+    del gs, ga0, ga1, gu, grgb
+    # inference composite: 8 M alive rays x 4 steps
+    na, ns = 8 * 1024 * 1024, 4
+    Mi = na * ns
+    alive = torch.arange(na, device=dev, dtype=torch.int32); rays_t = torch.rand(na, device=dev)
+    acc = [torch.zeros(na, device=dev) for _ in range(5)]; imgi = torch.zeros(na, 3, device=dev)
+    sig_i, rgb_i, dl_i = sig[:Mi], rgb[:Mi], dl[:Mi]
+    f = lambda: rb.composite_rays_triplane(na, ns, 1e-4, alive.clone(), rays_t, sig_i, rgb_i, dl_i, aud[:Mi], eye[:Mi], unc[:Mi], acc[0], acc[1], imgi, acc[2], acc[3], acc[4])
+    t_clone = timeit(lambda: alive.clone())
+    report("composite_rays_triplane", 36 * Mi + (8 + 64) * na, timeit(f) - t_clone, f"n_alive={na}, n_step={ns}")
+    del sig, rgb, aud, eye, unc, dl, rays, rays_sh, perm, acc, imgi
+    torch.cuda.empty_cache()
 
-# ---- utils ---------------------------------------------------------------------------------------------------------------------------
-Nr = 32 * 1024 * 1024
-o = torch.randn(Nr, 3, device=dev) * 0.1 + torch.tensor([0.0, 0.0, 3.0], device=dev); d = torch.nn.functional.normalize(torch.randn(Nr, 3, device=dev) * 0.1 + torch.tensor([0.0, 0.0, -1.0], device=dev), dim=1)
-aabb = torch.from_numpy(scene.AABB).to(dev); nears, fars = torch.empty(Nr, device=dev), torch.empty(Nr, device=dev)
-report("near_far_from_aabb", 32 * Nr, timeit(lambda: rb.near_far_from_aabb(o, d, aabb, Nr, 0.05, nears, fars)), f"N={Nr}")
-coords = torch.randint(0, 128, (Nr, 3), device=dev, dtype=torch.int32); idx = torch.empty(Nr, device=dev, dtype=torch.int32)
-report("morton3D", 16 * Nr, timeit(lambda: rb.morton3D(coords, Nr, idx)), f"N={Nr}")
-grid = torch.rand(8, 256 ** 3, device=dev) * 20; bits = torch.empty(8 * 256 ** 3 // 8, device=dev, dtype=torch.uint8)
-report("packbits", 33 * bits.numel(), timeit(lambda: rb.packbits(grid, bits.numel(), 10.0, bits)), "8 cascades x 256^3 cells (537 MB)")
-gd = torch.empty_like(grid)
-report("morton3D_dilation", 8 * grid.numel(), timeit(lambda: rb.morton3D_dilation(grid, 8, 256, gd)), "read 4 B + write 4 B per cell (neighbours from cache)")
-del grid, gd, bits, coords, idx
-torch.cuda.empty_cache()
+    # ---- utils ---------------------------------------------------------------------------------------------------------------------------
+    Nr = 32 * 1024 * 1024
+    o = torch.randn(Nr, 3, device=dev) * 0.1 + torch.tensor([0.0, 0.0, 3.0], device=dev); d = torch.nn.functional.normalize(torch.randn(Nr, 3, device=dev) * 0.1 + torch.tensor([0.0, 0.0, -1.0], device=dev), dim=1)
+    aabb = torch.from_numpy(scene.AABB).to(dev); nears, fars = torch.empty(Nr, device=dev), torch.empty(Nr, device=dev)
+    report("near_far_from_aabb", 32 * Nr, timeit(lambda: rb.near_far_from_aabb(o, d, aabb, Nr, 0.05, nears, fars)), f"N={Nr}")
+    coords = torch.randint(0, 128, (Nr, 3), device=dev, dtype=torch.int32); idx = torch.empty(Nr, device=dev, dtype=torch.int32)
+    report("morton3D", 16 * Nr, timeit(lambda: rb.morton3D(coords, Nr, idx)), f"N={Nr}")
+    grid = torch.rand(8, 256 ** 3, device=dev) * 20; bits = torch.empty(8 * 256 ** 3 // 8, device=dev, dtype=torch.uint8)
+    report("packbits", 33 * bits.numel(), timeit(lambda: rb.packbits(grid, bits.numel(), 10.0, bits)), "8 cascades x 256^3 cells (537 MB)")
+    gd = torch.empty_like(grid)
+    report("morton3D_dilation", 8 * grid.numel(), timeit(lambda: rb.morton3D_dilation(grid, 8, 256, gd)), "read 4 B + write 4 B per cell (neighbours from cache)")
+    del grid, gd, bits, coords, idx
+    torch.cuda.empty_cache()
 
-# ---- march_rays_train: 1 M rays of the synthetic head scene ------------------------------------------------------------------------------
-bf = torch.from_numpy(scene.bitfield_from_grid(scene.density_grid())).to(dev)
-Nm = 1024 * 1024
-oo, dd = [], []
-for s in range(16):
-    a, b = scene.train_rays(s, 65536)
-    oo.append(torch.from_numpy(a)); dd.append(torch.from_numpy(b))
-ro, rd = torch.cat(oo).to(dev), torch.cat(dd).to(dev)
-nears, fars = raymarching.near_far_from_aabb(ro, rd, aabb, 0.05)
-Mm = Nm * 6
-xyzs, dirs, dls = torch.zeros(Mm, 3, device=dev), torch.zeros(Mm, 3, device=dev), torch.zeros(Mm, 2, device=dev)
-rr = torch.empty(Nm, 3, device=dev, dtype=torch.int32); counter = torch.zeros(2, device=dev, dtype=torch.int32); noises = torch.rand(Nm, device=dev)
-
-
-def march():
-    counter.zero_()
-    rb.march_rays_train(ro, rd, bf, 1.0, 1 / 256, 16, Nm, 1, 128, Mm, nears, fars, xyzs, dirs, dls, rr, counter, noises)
+    # ---- march_rays_train: 1 M rays of the synthetic head scene ------------------------------------------------------------------------------
+    bf = torch.from_numpy(scene.bitfield_from_grid(scene.density_grid())).to(dev)
+    Nm = 1024 * 1024
+    oo, dd = [], []
+    for s in range(16):
+        a, b = scene.train_rays(s, 65536)
+        oo.append(torch.from_numpy(a)); dd.append(torch.from_numpy(b))
+    ro, rd = torch.cat(oo).to(dev), torch.cat(dd).to(dev)
+    nears, fars = raymarching.near_far_from_aabb(ro, rd, aabb, 0.05)
+    Mm = Nm * 6
+    xyzs, dirs, dls = torch.zeros(Mm, 3, device=dev), torch.zeros(Mm, 3, device=dev), torch.zeros(Mm, 2, device=dev)
+    rr = torch.empty(Nm, 3, device=dev, dtype=torch.int32); counter = torch.zeros(2, device=dev, dtype=torch.int32); noises = torch.rand(Nm, device=dev)
 
 
-sec = timeit(march)
-tot = int(counter[0])
-report("march_rays_train (count + write)", 52 * Nm + 32 * tot, sec, f"N={Nm} rays -> {tot} samples; includes the two DDA passes; {Nm / sec / 1e6:.1f} M rays/s")
+    def march():
+        counter.zero_()
+        rb.march_rays_train(ro, rd, bf, 1.0, 1 / 256, 16, Nm, 1, 128, Mm, nears, fars, xyzs, dirs, dls, rr, counter, noises)
 
-# ---- grid encode (API kernels), tri-plane config, 8 M points per plane --------------------------------------------------------------------
-from gridencoder import GridEncoder  # noqa: E402
-enc = GridEncoder(input_dim=2, num_levels=12, level_dim=1, base_resolution=64, log2_hashmap_size=14, desired_resolution=512).to(dev)
-enc.embeddings.data.uniform_(-1, 1)
-B = 8 * 1024 * 1024
-x = torch.rand(B, 2, device=dev); out = torch.empty(12, B, 1, device=dev)
-S = float(np.log2(enc.per_level_scale))
-f = lambda: gb.grid_encode_forward(x, enc.embeddings.data, enc.offsets, out, B, 2, 1, 12, S, 64, None, 0, False)
-sec = timeit(f)
-report("grid_encode_forward (one plane, D=2 L=12 C=1 fp32)", (8 + 48) * B, sec, f"B={B}; HBM bytes 8 in + 48 out per point; L2 gather {192 * B / sec / 1e9:.0f} GB/s (192 B/point); random points")
-grad = torch.randn(12, B, 1, device=dev); ge = torch.zeros_like(enc.embeddings.data)
-f = lambda: gb.grid_encode_backward(grad, x, enc.embeddings.data, enc.offsets, ge, B, 2, 1, 12, S, 64, None, None, 0, False)
-sec = timeit(f)
-report("grid_encode_backward (one plane)", (8 + 48) * B, sec, f"B={B}; {48 * B / sec / 1e9:.1f} G table reductions/s (48 per point, pairs issued as red.v2.f32)")
 
-print(json.dumps({"hbm_peak_gbs": HBM, "peak_source": SRC, "kernels": rows}, indent=1))
+    sec = timeit(march)
+    tot = int(counter[0])
+    report("march_rays_train (count + write)", 52 * Nm + 32 * tot, sec, f"N={Nm} rays -> {tot} samples; includes the two DDA passes; {Nm / sec / 1e6:.1f} M rays/s")
+
+    # ---- grid encode (API kernels), tri-plane config, 8 M points per plane --------------------------------------------------------------------
+    from gridencoder import GridEncoder  # noqa: E402
+    enc = GridEncoder(input_dim=2, num_levels=12, level_dim=1, base_resolution=64, log2_hashmap_size=14, desired_resolution=512).to(dev)
+    enc.embeddings.data.uniform_(-1, 1)
+    B = 8 * 1024 * 1024
+    x = torch.rand(B, 2, device=dev); out = torch.empty(12, B, 1, device=dev)
+    S = float(np.log2(enc.per_level_scale))
+    f = lambda: gb.grid_encode_forward(x, enc.embeddings.data, enc.offsets, out, B, 2, 1, 12, S, 64, None, 0, False)
+    sec = timeit(f)
+    report("grid_encode_forward (one plane, D=2 L=12 C=1 fp32)", (8 + 48) * B, sec, f"B={B}; HBM bytes 8 in + 48 out per point; L2 gather {192 * B / sec / 1e9:.0f} GB/s (192 B/point); random points")
+    grad = torch.randn(12, B, 1, device=dev); ge = torch.zeros_like(enc.embeddings.data)
+    f = lambda: gb.grid_encode_backward(grad, x, enc.embeddings.data, enc.offsets, ge, B, 2, 1, 12, S, 64, None, None, 0, False)
+    sec = timeit(f)
+    report("grid_encode_backward (one plane)", (8 + 48) * B, sec, f"B={B}; {48 * B / sec / 1e9:.1f} G table reductions/s (48 per point, pairs issued as red.v2.f32)")
+
+    return {"hbm_peak_gbs": HBM, "peak_source": SRC, "kernels": rows}
+
+
+if __name__ == "__main__":
+    print(json.dumps(measure(), indent=1))

@@ -1,76 +1,65 @@
 #!/usr/bin/env python
-"""The "reference on B200" row of SURVEY §8(d): the reference's OWN CUDA extensions (oracle/_ref/*.so, compiled in place from /root/reference by
-oracle/build_ref_ext.sh) driven the way the reference drives them — host loop with one alive-count read-back per iteration
-(renderer.py:406-570), per-op kernels, torch MLPs under autocast, plain AdamW + GradScaler — on the same synthetic frames / batches as bench.py.
+"""The "reference on B200" row of SURVEY §8(d): the UNMODIFIED reference model code — nerf_triplane/network.py NeRFNetwork + renderer.py
+(run_cuda_for_inference / run_cuda), its op wrappers and its own CUDA extensions — staged by oracle/stage_ref_py.sh + oracle/build_ref_ext.sh (only
+-std=c++17 differs from its own build flags), driven the way the reference drives it:
+  * inference: TrainerUtil.test_step (TrainerUtil.py:408-460): torch.no_grad + autocast(fp16), model.render(...) per frame, host loop with one alive-count
+    read-back per iteration (renderer.py:503-545);
+  * training:  TrainerUtil.train_one_epoch (TrainerUtil.py:1031-1056): autocast, model.render(training), loss, scaler.scale(loss).backward(), scaler.step(AdamW over
+    model.get_params), scaler.update(), loss.item() — the head-branch loss of TrainerUtil.py:238-334 written inline (TrainerUtil itself imports the product's
+    logging / LPIPS / video stack and is not staged).
+Same synthetic scene, frames, batches and random-init weights as bench.py.  TEST / MEASUREMENT INFRASTRUCTURE: nothing of lzzx-nerf_b200/ is on the timed path
+(only b2nerf.scene, numpy input synthesis).
 
-Test infrastructure (it executes oracle/_ref): the drop-in packages' `backend` modules are replaced by the reference's pybind modules BEFORE the
-packages are imported, so the Python above the backend is identical on both sides and only the kernels differ.
-
-    python profiles/reference_on_b200.py > gpurun_out/reference_on_b200.json
+    python profiles/reference_on_b200.py [--frames 20] [--steps 20]     -> one JSON object on stdout
 """
-import glob, importlib.util, json, os, sys, types
+import argparse
+import json
+import os
+import sys
+import types
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "lzzx-nerf_b200"), ROOT):
-    sys.path.insert(0, p)
-import torch
+REF_PY = os.path.join(ROOT, "oracle", "_ref_py")
+if not os.path.isdir(os.path.join(REF_PY, "nerf_triplane")):
+    print(json.dumps({"unavailable": "oracle/_ref_py not staged (oracle/stage_ref_py.sh)"})); sys.exit(0)
+sys.path[:0] = [REF_PY, os.path.join(ROOT, "tests"), os.path.join(ROOT, "lzzx-nerf_b200")]
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
-
-def load_ref(name):
-    hits = glob.glob(os.path.join(ROOT, "oracle", "_ref", name + ".*.so"))
-    if not hits:
-        print(json.dumps({"unavailable": f"oracle/_ref/{name} not built"})); sys.exit(0)
-    spec = importlib.util.spec_from_file_location(name, hits[0])
-    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
-    return mod
-
-
-for pkg, ext in (("raymarching", "_ref_raymarching_face"), ("gridencoder", "_ref_grid_encoder"), ("shencoder", "_ref_sh_encoder"), ("freqencoder", "_ref_freqencoder")):
-    stub = types.ModuleType(pkg + ".backend")
-    stub._backend = load_ref(ext)
-    sys.modules[pkg + ".backend"] = stub
-
-import raymarching  # noqa: E402  (now on the reference kernels)
-import bench  # noqa: E402
+try:
+    for _ in range(32):
+        try:
+            from nerf_triplane.network import NeRFNetwork  # noqa: E402
+            import nerf_triplane.renderer as ref_renderer  # noqa: E402
+            break
+        except ModuleNotFoundError as e:
+            sys.modules[e.name] = types.ModuleType(e.name)
+            for k in [k for k in sys.modules if k.startswith("nerf_triplane")]:
+                del sys.modules[k]
+    import raymarching  # noqa: E402
+    assert raymarching.__file__.startswith(REF_PY)
+except ImportError as e:
+    print(json.dumps({"unavailable": f"reference extensions not built: {e}"})); sys.exit(0)
+import refcases as rc  # noqa: E402
 from b2nerf import scene  # noqa: E402
-from b2nerf.model import MLP  # noqa: E402
-from b2nerf.train import Trainer  # noqa: E402
 
-MLP.tall_linear = False
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=20)
+ap.add_argument("--steps", type=int, default=20)
+args = ap.parse_args()
+torch.backends.cuda.matmul.allow_tf32 = False      # train.py:11-13
+torch.backends.cudnn.allow_tf32 = False
 dev = torch.device("cuda")
-N, POOL = bench.N_RAYS, 8
-model = bench.build_model(dev)
-bitfield = torch.from_numpy(scene.bitfield_from_grid(scene.density_grid())).to(dev)
-model.density_bitfield.copy_(bitfield)
-frames = [tuple(torch.from_numpy(a).to(dev) for a in scene.frame_rays(frame=f)) for f in range(POOL)]
-auds = [torch.from_numpy(scene.audio_window(frame=f)).to(dev) for f in range(POOL)]
-eye = torch.tensor([[0.4]], device=dev)
-ind_code = model.individual_codes[0:1].detach()
+HW, N, POOL = 512, 512 * 512, 8
+T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
-@torch.no_grad()
-def render_frame(rays_o, rays_d, aud, max_steps=16, dt_gamma=1 / 256, T_thresh=1e-4):
-    """run_cuda_for_inference (renderer.py:406-570): per-op kernels, unfused network under autocast, torch mask compaction."""
-    with torch.autocast("cuda", dtype=torch.float16):
-        enc_a = model.encode_audio(aud)
-        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, model.aabb_infer, 0.05)
-        ws, depth, image = torch.zeros(N, device=dev), torch.zeros(N, device=dev), torch.zeros(N, 3, device=dev)
-        sa, se, su = torch.zeros(N, device=dev), torch.zeros(N, device=dev), torch.zeros(N, device=dev)
-        alive = torch.arange(N, dtype=torch.int32, device=dev); rays_t = nears.clone()
-        step, samples = 0, 0
-        while step < max_steps:
-            n_alive = alive.shape[0]
-            if n_alive <= 0:
-                break
-            n_step = max(min(N // n_alive, 8), 1)
-            xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, alive, rays_t, rays_o, rays_d, model.bound, model.density_bitfield, model.cascade,
-                                                        model.grid_size, nears, fars, 128, False, dt_gamma, max_steps)
-            sig, rgb, aa, ae, un = model.forward_unfused(xyzs, dirs, enc_a, ind_code, eye)
-            raymarching.composite_rays_triplane(n_alive, n_step, alive, rays_t, sig, rgb, deltas, aa, ae, un, ws, depth, image, sa, se, su, T_thresh)
-            alive = alive[alive >= 0]            # the reference's per-iteration host synchronisation (renderer.py:542)
-            samples += n_alive * n_step
-            step += n_step
-        image = (image + (1 - ws).unsqueeze(-1)).clamp(0, 1)
-    return image, samples
+def build(training):
+    torch.manual_seed(0)
+    m = NeRFNetwork(rc.ref_opt(False, "hubert")).to(dev)       # the reference's own random init (tables +-1e-4, grid.py:132-134)
+    m.density_bitfield.copy_(T(scene.bitfield_from_grid(scene.density_grid())))
+    m.testing = not training
+    return m.train() if training else m.eval()
 
 
 def timed(fn, steps, warmup):
@@ -85,24 +74,70 @@ def timed(fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
-out = {"what": "reference CUDA extensions (oracle/_ref) + torch MLPs, reference-style host orchestration, same synthetic inputs as bench.py", "gpu": torch.cuda.get_device_name(0)}
-smp = []
-ms = timed(lambda s: smp.append(render_frame(frames[s % POOL][0], frames[s % POOL][1], auds[s % POOL])[1]), 20, 4)
-out["infer_512x512"] = {"frames_per_sec": 1e3 / ms, "ms_per_frame": ms, "sample_slots_per_frame": smp[-1]}
+out = {"what": "unmodified reference model code (oracle/_ref_py) on the reference's own CUDA extensions (oracle/_ref), reference-style host loop; same synthetic "
+               "inputs as bench.py", "gpu": torch.cuda.get_device_name(0)}
+# ---- inference: 512 x 512 frames ----------------------------------------------------------------------------------------------------------
+m = build(False)
+frames = [tuple(T(a) for a in scene.frame_rays(frame=f)) for f in range(POOL)]
+auds = [T(scene.audio_window(frame=f)) for f in range(POOL)]
+eye = torch.tensor([[0.4]], device=dev)
+bgc = torch.zeros(1, N, 2, device=dev)
 
-# training step: eager, per-op reference kernels, nn.Linear MLPs, foreach AdamW, GradScaler (TrainerUtil.py:1040-1056)
-model_t = bench.build_model(dev); model_t.testing = False
-model_t.density_bitfield.copy_(bitfield)
-tr = Trainer(model_t, fp16=True, fused_optimizer=False)
+
+def frame(s):
+    ro, rd = frames[s % POOL]
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        res, _ = m.render(ro[None], rd[None], auds[s % POOL], bgc, None, eye=eye, index=[0], bg_color=None, perturb=False, dt_gamma=1 / 256, max_steps=16, T_thresh=1e-4)
+    return res["image"]
+
+
+ms = timed(frame, args.frames, 4)
+out["infer_512x512"] = {"frames_per_sec": 1e3 / ms, "ms_per_frame": ms, "frames_timed": args.frames}
+
+# ---- training: 65 536 rays per step -------------------------------------------------------------------------------------------------------------
+mt = build(True)
+opt = torch.optim.AdamW(mt.get_params(1e-2, 1e-3), betas=(0, 0.99), eps=1e-8)          # train.py:274
+scaler = torch.amp.GradScaler("cuda")
 n = 65536
 batches = []
 for s in range(4):
     o, d = scene.train_rays(step=s, n=n)
-    batches.append((torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev), torch.from_numpy(scene.audio_window(s)).to(dev), torch.rand(n, 3, device=dev)))
-for s in range(18):
-    b = batches[s % 4]; tr.train_step(*b, index=s)
-    if s == 15:
-        tr.update_mean_count()
-ms = timed(lambda s: tr.train_step(*batches[s % 4], index=s), 20, 2)
-out["train_65536_rays"] = {"rays_per_sec": n / (ms * 1e-3), "ms_per_step": ms, "mean_count": tr.mean_count}
-print(json.dumps(out, indent=1))
+    batches.append((T(o), T(d), T(scene.audio_window(s)), torch.rand(n, 3, device=dev), torch.rand(n, device=dev) < 0.5))
+bgc_t, bg1 = torch.zeros(1, n, 2, device=dev), torch.ones(1, 3, device=dev)
+state = {"global_step": 0}
+
+
+def step(s):
+    ro, rd, au, gt, face = batches[s % 4]
+    opt.zero_grad()
+    sf = min(state["global_step"] / 200000, 1.0)
+    with torch.autocast("cuda", dtype=torch.float16):
+        res, _ = mt.render(ro[None], rd[None], au, bgc_t, None, eye=eye, index=[s % 7], bg_color=bg1, perturb=True, force_all_rays=False, dt_gamma=1 / 256, max_steps=16,
+                           T_thresh=1e-4)
+        pred = res["image"].view(-1, 3)
+        loss = ((pred - gt) ** 2).mean(-1)
+        unc = res["uncertainty"]
+        w = torch.softmax(unc, dim=-1) * n
+        loss = loss * (0.2 + 0.8 * ((1 - sf) + sf * w.detach()).clamp(0, 10))
+        beta = unc + 1
+        loss = loss + sf * ((torch.norm(pred - gt, dim=-1).detach() / (2 * beta ** 2) + torch.log(beta) ** 2 / 2) * face) + 1e-3 * sf * (unc * ~face)
+        loss = loss.mean()
+        al = res["weights_sum"].clamp(1e-5, 1 - 1e-5)
+        loss = loss + 1e-4 * (-al * torch.log2(al) - (1 - al) * torch.log2(1 - al)).mean()
+        lam = sf * 1e-4
+        loss = loss + lam * (res["ambient_aud"].view(-1) * ~face).mean() + lam * ((res["ambient_eye"].view(-1) / 16 * res["ambient_aud"].view(-1).detach()) * face).mean()
+    scaler.scale(loss).backward()
+    scaler.step(opt)
+    scaler.update()
+    state["global_step"] += 1
+    return loss.item()                                  # TrainerUtil.py:1051
+
+
+for s in range(16):                                     # warm-up with worst-case buffers, then the mean_count estimate (update_extra_state's tail, renderer.py:812-815)
+    step(s)
+mt.mean_count = int(mt.step_counter[:16, 0].sum().item() / 16)
+mt.local_step = 0
+ms = timed(step, args.steps, 2)
+out["train_65536_rays"] = {"rays_per_sec": n / (ms * 1e-3), "ms_per_step": ms, "mean_count": mt.mean_count, "steps_timed": args.steps,
+                           "note": "without the every-16th-step smoothness regulariser (TrainerUtil.py:336-363)"}
+print(json.dumps(out))

@@ -32,11 +32,13 @@ def test_train_step_gradients_match_cpu_port_fp32():
     torch.backends.cuda.matmul.allow_tf32 = False
     m, Trainer, bf, o, d, auds, gt = _setup(n)
     tr = Trainer(m, fp16=False)
+    tr.global_step = tr.iters // 2                    # step_factor 0.5: the uncertainty / ambient terms of TrainerUtil.py:256-331 are all active
+    face = torch.from_numpy(np.random.default_rng(5).random(n) < 0.5)
     rays_o, rays_d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
     eye = torch.full((1, 1), 0.4, device="cuda"); bg = torch.ones(1, 3, device="cuda")
     tr.grads.zero_()
     out = tr.render_train(rays_o, rays_d, auds.cuda(), 3, eye, bg, perturb=False)
-    loss = tr.loss(out, gt.cuda())
+    loss = tr.loss(out, gt.cuda(), face.cuda())
     loss.backward()
     tr.grads.check_attached()
     # ---- CPU: same graph in pure PyTorch (fp32), samples from the C oracle's marcher ----
@@ -52,10 +54,8 @@ def test_train_step_gradients_match_cpu_port_fp32():
     sig, rgb, aa, ae, un = tp.head_forward(p, torch.from_numpy(xyzs[:tot]), torch.from_numpy(dirs[:tot]), enc_a, P["individual_codes"][3], torch.tensor([0.4]), testing=False)
     ws, s_a, s_e, s_u, dep, img = tp.composite_rays_train_triplane_ragged(sig, rgb, aa.abs(), ae.abs(), un, torch.from_numpy(deltas[:tot]), torch.from_numpy(rays.astype(np.int64)))
     img = (img + (1 - ws)[:, None]).clamp(0, 1)
-    mse = ((img - gt) ** 2).mean(-1).mean()
-    al = ws.clamp(1e-5, 1 - 1e-5)
-    ent = (-al * torch.log2(al) - (1 - al) * torch.log2(1 - al)).mean()
-    cpu_loss = mse + 1e-3 * ent + 1e-4 * (s_a.mean() + s_e.mean())
+    from b2nerf.fused_train import torch_head_loss      # the reference's loss, op by op (TrainerUtil.py:238-334) — plain torch, runs on the CPU
+    cpu_loss = torch_head_loss(img, ws, s_a, s_e, gt, unc_sum=s_u, face_mask=face, step_factor=0.5, lambda_ent=1e-4, lambda_amb=1e-4, max_steps=16)
     cpu_loss.backward()
     assert abs(float(loss) - float(cpu_loss)) < 2e-4 * max(1.0, abs(float(cpu_loss))), (float(loss), float(cpu_loss))
     worst, mean_rel = {}, {}
@@ -131,17 +131,26 @@ def test_flat_adamw_matches_torch_adamw():
     step that is skipped because of an overflow."""
     from b2nerf.optim import FlatAdamW
     torch.manual_seed(0)
-    shapes0, shapes1 = [(1000, 1), (333, 1)], [(64, 36), (3, 64), (7,)]
+    shapes0, shapes1, shapes2 = [(1000, 1), (333, 1)], [(64, 36), (3, 64), (7,)], [(16, 32, 3), (8,)]
     mk = lambda shapes: [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
-    a0, a1 = mk(shapes0), mk(shapes1)
-    b0, b1 = [torch.nn.Parameter(p.detach().clone()) for p in a0], [torch.nn.Parameter(p.detach().clone()) for p in a1]
-    ref = torch.optim.AdamW([{"params": b0, "lr": 1e-2}, {"params": b1, "lr": 1e-3, "weight_decay": 0}], betas=(0.0, 0.99), eps=1e-8)
-    opt = FlatAdamW(a0, a1, 1e-2, 1e-3, weight_decay0=0.01, weight_decay1=0.0, betas=(0.0, 0.99), eps=1e-8)
+    a0, a1, a2 = mk(shapes0), mk(shapes1), mk(shapes2)
+    b0, b1, b2 = ([torch.nn.Parameter(p.detach().clone()) for p in a] for a in (a0, a1, a2))
+    # network.py:332-356: tables (AdamW's default decay), networks (wd 0), audio_att_net (5 x lr_net, wd 1e-4); train.py:287 LambdaLR stepped every iteration
+    ref = torch.optim.AdamW([{"params": b0, "lr": 1e-2}, {"params": b1, "lr": 1e-3, "weight_decay": 0}, {"params": b2, "lr": 5e-3, "weight_decay": 1e-4}],
+                            betas=(0.0, 0.99), eps=1e-8)
+    opt = FlatAdamW([{"params": a0, "lr": 1e-2, "weight_decay": 0.01}, {"params": a1, "lr": 1e-3, "weight_decay": 0.0}, {"params": a2, "lr": 5e-3, "weight_decay": 1e-4}],
+                    betas=(0.0, 0.99), eps=1e-8, ema_decay=0.95, ema_update_interval=2)
+    sched_a = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 0.5 ** (it / 4))
+    sched_b = torch.optim.lr_scheduler.LambdaLR(ref, lambda it: 0.5 ** (it / 4))
     flat_g = torch.zeros(opt.n, device="cuda")
     off = 0
-    for p in a0 + a1:
+    for p in a0 + a1 + a2:
         p.grad = flat_g[off:off + p.numel()].view_as(p); off += p.numel()
     opt.attach_grads(flat_g)
+    # torch_ema.ExponentialMovingAverage restated (TrainerUtil.py:98-99, 1055-1056): shadow -= (1 - min(decay, (1 + n) / (10 + n))) * (shadow - param)
+    shadow, n_upd = [q.detach().clone() for q in b0 + b1 + b2], 0
+    a0, b0 = a0 + a1 + a2, b0 + b1 + b2
+    a1, b1 = [], []
     sa, sb = torch.amp.GradScaler("cuda", init_scale=1024.0), torch.amp.GradScaler("cuda", init_scale=1024.0)
     for step in range(6):
         gs = [torch.randn_like(p) for p in a0 + a1]
@@ -153,10 +162,25 @@ def test_flat_adamw_matches_torch_adamw():
         sa.scale(torch.zeros((), device="cuda")); sb.scale(torch.zeros((), device="cuda"))
         sa.step(opt); sa.update()
         sb.step(ref); sb.update()
+        sched_a.step(); sched_b.step()
+        if (step + 1) % 2 == 0:                           # EMA every 2nd optimizer call — also on the overflowed step (ema.update() does not know about the skip)
+            n_upd += 1
+            d = min(0.95, (1 + n_upd) / (10 + n_upd))
+            for sh, q in zip(shadow, b0):
+                sh.sub_((1 - d) * (sh - q.detach()))
         assert sa.get_scale() == sb.get_scale()
     assert float(opt.step_count) == 5.0
     for p, q in zip(a0 + a1, b0 + b1):
         assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), float((p - q).abs().max())
+    off = 0
+    for sh in shadow:
+        got = opt.ema[off:off + sh.numel()].view_as(sh); off += sh.numel()
+        assert torch.allclose(got, sh, rtol=2e-5, atol=2e-6), float((got - sh).abs().max())
+    # checkpoint round trip keeps the moments (they live outside Optimizer.state)
+    sd = opt.state_dict()
+    opt.exp_avg.zero_(); opt.step_count.zero_()
+    opt.load_state_dict(sd)
+    assert float(opt.step_count) == 5.0 and float(opt.exp_avg.abs().sum()) > 0
 
 
 def test_fused_head_gradients_match_autograd_under_autocast():
@@ -216,9 +240,11 @@ def test_fused_head_gradients_match_autograd_under_autocast():
     assert len(worst) >= 14, worst
 
 
-def test_fused_loss_matches_torch_loss_and_gradients():
-    """b2n_head_loss_forward/backward vs Trainer.loss on the blended image through autograd (fp32): value 1e-6, gradients 1e-5 of their max."""
-    from b2nerf.fused_train import fused_head_loss
+@pytest.mark.parametrize("with_unc,step_factor", [(False, 0.0), (True, 0.0), (True, 0.37), (True, 1.0)])
+def test_fused_loss_matches_torch_loss_and_gradients(with_unc, step_factor):
+    """b2n_head_loss_forward/backward vs the reference's loss (TrainerUtil.py:238-334: uncertainty-weighted MSE, loss_u, static-uncertainty, entropy 1e-4, masked /
+    ramped ambient terms) written op by op in torch on the blended image, through autograd (fp32): value 2e-6, gradients 2e-5 of their max."""
+    from b2nerf.fused_train import fused_head_loss, torch_head_loss
     g = torch.Generator(device="cuda").manual_seed(8)
     n = 65536 + 13
     image = torch.rand(n, 3, device="cuda", generator=g) * 0.9
@@ -226,17 +252,22 @@ def test_fused_loss_matches_torch_loss_and_gradients():
     ws[:50] = 0.0; ws[50:100] = 1.0                      # both clamp regions of the entropy term
     image[100:200] = 1.5; image[200:300] = -0.25         # both clamp regions of the colour
     aud, eye = torch.rand(n, device="cuda", generator=g), torch.rand(n, device="cuda", generator=g)
+    unc = torch.rand(n, device="cuda", generator=g) * 3.0
+    unc[300:310] = 12.0                                  # a few rays whose softmax weight hits the clamp at 10
+    face = torch.rand(n, device="cuda", generator=g) < 0.4
     gt = torch.rand(n, 3, device="cuda", generator=g)
-    for bg in (torch.ones(1, 3, device="cuda"), torch.rand(n, 3, device="cuda", generator=g)):
-        a = [t.clone().requires_grad_(True) for t in (image, ws, aud, eye)]
-        b = [t.clone().requires_grad_(True) for t in (image, ws, aud, eye)]
-        lf = fused_head_loss(a[0], a[1], a[2], a[3], gt, bg, 1e-3, 1e-4)
+    for bg, sf in ((torch.ones(1, 3, device="cuda"), step_factor), (torch.rand(n, 3, device="cuda", generator=g), torch.tensor([step_factor], device="cuda"))):
+        a = [t.clone().requires_grad_(True) for t in (image, ws, aud, eye, unc)]
+        b = [t.clone().requires_grad_(True) for t in (image, ws, aud, eye, unc)]
+        lf = fused_head_loss(a[0], a[1], a[2], a[3], gt, bg, unc_sum=a[4] if with_unc else None, face_mask=face, step_factor=sf)
         img = (b[0] + (1 - b[1]).unsqueeze(-1) * bg).clamp(0, 1)
-        al = b[1].clamp(1e-5, 1 - 1e-5)
-        lt = ((img - gt) ** 2).mean(-1).mean() + 1e-3 * (-al * torch.log2(al) - (1 - al) * torch.log2(1 - al)).mean() + 1e-4 * (b[2].mean() + b[3].mean())
+        lt = torch_head_loss(img, b[1], b[2], b[3], gt, unc_sum=b[4] if with_unc else None, face_mask=face, step_factor=step_factor)
         assert abs(float(lf) - float(lt)) < 2e-6 * max(1.0, abs(float(lt))), (float(lf), float(lt))
         (lf * 1024.0).backward(); (lt * 1024.0).backward()
-        for x, y, name in zip(a, b, ("image", "ws", "aud", "eye")):
+        for x, y, name in zip(a, b, ("image", "ws", "aud", "eye", "unc")):
+            if y.grad is None:
+                assert x.grad is None or float(x.grad.abs().max()) == 0.0, name
+                continue
             err = float((x.grad - y.grad).abs().max()) / (float(y.grad.abs().max()) + 1e-20)
             assert err < 2e-5, (name, err)
 
