@@ -33,7 +33,7 @@ __device__ __forceinline__ void near_far_one(float ox, float oy, float oz, float
 struct DdaRay {
     float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
     float sx, sy, sz;                 // 0.5 * sign(d)
-    float bound, dt_gamma, dt_min, dt_max, rH, Hf, Hm1f, H3f, ncas_m1, far;
+    float bound, rbound, dt_gamma, dt_min, dt_max, rH, Hf, Hm1f, H3f, ncas_m1, far;
     uint32_t C;
 
     __device__ __forceinline__ void init(const float *o, const float *d, float bound_, float dt_gamma_, uint32_t max_steps,
@@ -45,7 +45,7 @@ struct DdaRay {
     __device__ __forceinline__ void init_common(float bound_, float dt_gamma_, uint32_t max_steps, uint32_t C_, uint32_t H, float far_) {
         rdx = 1.0f / dx; rdy = 1.0f / dy; rdz = 1.0f / dz;            // IEEE division (raymarching.cu:378)
         sx = copysignf(0.5f, dx); sy = copysignf(0.5f, dy); sz = copysignf(0.5f, dz);
-        bound = bound_; dt_gamma = dt_gamma_; C = C_; far = far_;
+        bound = bound_; rbound = 1.0f / bound_; dt_gamma = dt_gamma_; C = C_; far = far_;
         Hf = (float)H; Hm1f = (float)(H - 1); rH = 1.0f / Hf;
         H3f = (float)(H * H * H);                                      // `const float H3 = H*H*H` (:380)
         ncas_m1 = __fsub_rn((float)C_, 1.0f);
@@ -86,6 +86,70 @@ struct DdaRay {
         return f;
     }
 
+    // mip_bound = fminf(scalbnf(1, level), bound) and mip_rbound = 1 / mip_bound (raymarching.cu:412-413) without the division inside the march loop: the
+    // reciprocal of a power of two is that power negated, exactly; the other case is 1 / bound, divided once per ray.
+    __device__ __forceinline__ void mip_of(int level, float &mb, float &rmb) const {
+        const float p2 = __int_as_float((127 + level) << 23);
+        if (p2 <= bound) { mb = p2; rmb = __int_as_float((127 - level) << 23); } else { mb = bound; rmb = rbound; }
+    }
+
+    // The probe split in two, each a pure function of (ray, t) with the arithmetic of probe() below: the bitfield index of the cell at parameter t, and the
+    // empty-cell branch (advance t past the cell's exit).  march<G>() uses them to keep G probes in flight per thread.
+    __device__ __forceinline__ uint32_t cell_of(float t) const {
+        const float x = clampf(__fmaf_rn(t, dx, ox), -bound, bound);
+        const float y = clampf(__fmaf_rn(t, dy, oy), -bound, bound);
+        const float z = clampf(__fmaf_rn(t, dz, oz), -bound, bound);
+        const int level = level_of(x, y, z, step_of(t));
+        float mip_bound, mip_rbound;
+        mip_of(level, mip_bound, mip_rbound);
+        const float fx = clampf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(x, mip_rbound, 1.0f)), Hf), 0.0f, Hm1f);
+        const float fy = clampf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(y, mip_rbound, 1.0f)), Hf), 0.0f, Hm1f);
+        const float fz = clampf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(z, mip_rbound, 1.0f)), Hf), 0.0f, Hm1f);
+        return (uint32_t)__fmaf_rn((float)level, H3f, (float)morton_enc((uint32_t)(int)fx, (uint32_t)(int)fy, (uint32_t)(int)fz));
+    }
+    __device__ __forceinline__ void skip_empty(float &t) const {
+        const float x = clampf(__fmaf_rn(t, dx, ox), -bound, bound);
+        const float y = clampf(__fmaf_rn(t, dy, oy), -bound, bound);
+        const float z = clampf(__fmaf_rn(t, dz, oz), -bound, bound);
+        const int level = level_of(x, y, z, step_of(t));
+        float mip_bound, mip_rbound;
+        mip_of(level, mip_bound, mip_rbound);
+        const int nx = (int)clampf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(x, mip_rbound, 1.0f)), Hf), 0.0f, Hm1f);
+        const int ny = (int)clampf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(y, mip_rbound, 1.0f)), Hf), 0.0f, Hm1f);
+        const int nz = (int)clampf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(z, mip_rbound, 1.0f)), Hf), 0.0f, Hm1f);
+        const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), sx), rH), 2.0f, -1.0f), mip_bound, -x), rdx);
+        const float ty = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)ny, 0.5f), sy), rH), 2.0f, -1.0f), mip_bound, -y), rdy);
+        const float tz = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nz, 0.5f), sz), rH), 2.0f, -1.0f), mip_bound, -z), rdz);
+        const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+        do { t = __fadd_rn(t, step_of(t)); } while (t < tt);
+    }
+
+    // The reference's marching loop (`while (t < far && step < max_n) { probe }`, raymarching.cu:400-441) with G probes in flight per thread.  Every t the loop
+    // visits lies on the orbit t <- t + step_of(t), so the next G - 1 orbit points are computed ahead and their cells fetched together (G independent index
+    // computations and bitfield loads instead of G dependent round trips); the loop is then replayed serially over the fetched bits, and a fetched bit is used
+    // only if the loop really arrives at that t (an empty cell may jump over orbit points: the group is then abandoned and refetched from the true t).  Same
+    // t sequence, same samples, bit for bit; on_sample(k, t, dt) is called for the k-th sample.  Returns the number of samples; t = where the loop stopped.
+    template <int G, typename F>
+    __device__ __forceinline__ uint32_t march(const uint8_t *__restrict__ grid, float &t, uint32_t max_n, F &&on_sample) const {
+        uint32_t num = 0;
+        while (t < far && num < max_n) {
+            float ts[G];
+            uint32_t occ[G];
+            ts[0] = t;
+#pragma unroll
+            for (int j = 1; j < G; j++) ts[j] = __fadd_rn(ts[j - 1], step_of(ts[j - 1]));
+#pragma unroll
+            for (int j = 0; j < G; j++) { const uint32_t idx = cell_of(ts[j]); occ[j] = (__ldg(grid + (idx >> 3)) >> (idx & 7)) & 1u; }
+#pragma unroll
+            for (int j = 0; j < G; j++) {
+                if (ts[j] != t || !(t < far) || num >= max_n) break;
+                if (occ[j]) { const float dt = step_of(t); on_sample(num, t, dt); num++; t = __fadd_rn(t, dt); }
+                else skip_empty(t);
+            }
+        }
+        return num;
+    }
+
     // One loop iteration at parameter t.  Occupied: fills s, returns true (caller advances t by s.dt).
     // Empty: advances t past the voxel exit with the reference's do-while and returns false.
     __device__ __forceinline__ bool probe(const uint8_t *__restrict__ grid, float &t, DdaSample &s) const {
@@ -94,8 +158,8 @@ struct DdaRay {
         const float z = clampf(__fmaf_rn(t, dz, oz), -bound, bound);
         const float dt = step_of(t);
         const int level = level_of(x, y, z, dt);
-        const float mip_bound = fminf(__int_as_float((127 + level) << 23), bound);     // scalbnf(1, level)
-        const float mip_rbound = 1.0f / mip_bound;
+        float mip_bound, mip_rbound;
+        mip_of(level, mip_bound, mip_rbound);
         // 0.5 * (x * mip_rbound + 1) * H — exact in the reference's double, so one fp32 rounding here
         const float fx = clampf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(x, mip_rbound, 1.0f)), Hf), 0.0f, Hm1f);
         const float fy = clampf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(y, mip_rbound, 1.0f)), Hf), 0.0f, Hm1f);

@@ -181,44 +181,84 @@ __global__ void __launch_bounds__(256) k_occ_box(const uint8_t *__restrict__ gri
 // training march — raymarching.cu:353-518
 // ---------------------------------------------------------------------------------------------------
 constexpr int MT_THREADS = 128;
+__host__ __device__ __forceinline__ uint32_t ceil_div_u(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
-// pass 1: count occupied steps per ray; rays[n] = (n, -, count); per-CTA totals to scratch.
+// pass 1: count occupied steps per ray; rays[n] = (n, -, count); totals of every group of 128 rays to scratch.
 // t_cache [N][max_steps]: the parameter t of every sample, so that the write pass does not walk the bitfield again — a sample's position and step are
 // functions of (ray, t) alone.
+// Training rays are RANDOM pixels (provider.py:669): a third of them reach the occupied box, scattered over every warp, so a thread-per-ray march runs every
+// warp for the longest ray at a third of its lanes.  A CTA therefore first clips a tile of 512 rays (cheap, all lanes), compacts the ones that have something to
+// march into a dense list in shared memory, and marches those with full warps and four probes in flight per thread (DdaRay::march); counts go back to ray
+// order through shared memory.
+constexpr int MC_GROUPS = 4;                          // groups of MT_THREADS rays per CTA of the count pass
 __global__ void __launch_bounds__(MT_THREADS) k_march_train_count(
         const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
         float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
         const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
         int32_t *__restrict__ rays, const int32_t *__restrict__ counter, int32_t *__restrict__ cta_totals, float *__restrict__ t_cache,
         const float *__restrict__ box) {
-    const uint32_t n = blockIdx.x * MT_THREADS + threadIdx.x;
-    uint32_t num = 0;
-    if (n < N) {
-        DdaRay r;
-        r.init(rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H, fars[n]);
-        float t = r.perturb(nears[n], noises[n]);
-        if (box) r.far = r.clip_to_box(box, t);
-        DdaSample s;
-        float *tc = t_cache ? t_cache + (size_t)n * max_steps : nullptr;
-        while (t < r.far && num < max_steps) {
-            if (r.probe(grid, t, s)) { if (tc) tc[num] = t; num++; t = __fadd_rn(t, s.dt); }
-        }
-        rays[3 * (size_t)n] = (int32_t)n;
-        rays[3 * (size_t)n + 2] = (int32_t)num;
-    }
-    // CTA total (warp shuffle + smem)
-    __shared__ uint32_t wsum[MT_THREADS / 32];
-    uint32_t v = num;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    constexpr uint32_t TILE = MC_GROUPS * MT_THREADS;
+    __shared__ float s_t0[TILE], s_far[TILE];
+    __shared__ uint16_t s_list[TILE];
+    __shared__ uint16_t s_num[TILE];
+    __shared__ uint32_t s_nlive, s_wcnt[MT_THREADS / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tile0 = blockIdx.x * TILE;
+    if (threadIdx.x == 0) s_nlive = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
+#pragma unroll 1
+    for (uint32_t g = 0; g < MC_GROUPS; g++) {
+        const uint32_t q = g * MT_THREADS + threadIdx.x, n = tile0 + q;
+        bool live = false;
+        if (n < N) {
+            DdaRay r;
+            r.init(rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H, fars[n]);
+            float t = r.perturb(nears[n], noises[n]);
+            if (box) r.far = r.clip_to_box(box, t);
+            live = t < r.far && max_steps > 0;
+            s_t0[q] = t; s_far[q] = r.far;
+        }
+        s_num[q] = 0;
+        const uint32_t ballot = __ballot_sync(0xffffffffu, live);
+        uint32_t base = 0;
+        if (lane == 0 && ballot) base = atomicAdd(&s_nlive, (uint32_t)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (live) s_list[base + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)q;
+    }
+    __syncthreads();
+    const uint32_t n_live = s_nlive;
+#pragma unroll 1
+    for (uint32_t j = threadIdx.x; j < n_live; j += MT_THREADS) {
+        const uint32_t q = s_list[j], m = tile0 + q;
+        DdaRay r;
+        r.init(rays_o + 3 * (size_t)m, rays_d + 3 * (size_t)m, bound, dt_gamma, max_steps, C, H, s_far[q]);
+        float t = s_t0[q];
+        float *tc = t_cache ? t_cache + (size_t)m * max_steps : nullptr;
+        s_num[q] = (uint16_t)r.march<4>(grid, t, max_steps < 65535u ? max_steps : 65535u, [&](uint32_t k, float tk, float) { if (tc) tc[k] = tk; });
+    }
+    __syncthreads();
+    const uint32_t groups = ceil_div_u(N, MT_THREADS);
+#pragma unroll 1
+    for (uint32_t g = 0; g < MC_GROUPS; g++) {
+        const uint32_t q = g * MT_THREADS + threadIdx.x, n = tile0 + q, gi = blockIdx.x * MC_GROUPS + g;
+        if (gi >= groups) break;
+        const uint32_t num = s_num[q];
+        if (n < N) {
+            rays[3 * (size_t)n] = (int32_t)n;
+            rays[3 * (size_t)n + 2] = (int32_t)num;
+        }
+        uint32_t v = num;
 #pragma unroll
-        for (int w = 0; w < MT_THREADS / 32; w++) tot += wsum[w];
-        cta_totals[1 + blockIdx.x] = (int32_t)tot;
-        if (blockIdx.x == 0) cta_totals[0] = counter[0];   // snapshot: offsets start at the counter's current value
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (lane == 0) s_wcnt[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < MT_THREADS / 32; w++) tot += s_wcnt[w];
+            cta_totals[1 + gi] = (int32_t)tot;
+            if (gi == 0) cta_totals[0] = counter[0];   // snapshot: offsets start at the counter's current value
+        }
     }
 }
 
@@ -259,61 +299,59 @@ __device__ __forceinline__ void march_train_offsets(uint32_t N, const int32_t *_
     }
 }
 
-// pass 2 (t_cache present): OUTPUT-centric.  The samples of a CTA's 128 consecutive rays form one contiguous slot range [s_base, s_base + total): thread j
-// produces slot j (its ray found by a search over the CTA's 128 segment starts in shared memory, its t read from the ray's t_cache row), the 8 floats of a
-// slot go through a shared-memory tile and leave as full contiguous lines of xyzs / dirs / deltas — instead of one thread walking its ray with 4-byte
-// stores at a 12-byte stride.  Same expressions as DdaRay::probe for an occupied cell: bit-identical samples.
-constexpr uint32_t MW_TILE = 512;                 // slots staged per round (16 KB of shared memory)
+// pass 2 (t_cache present).  The samples of a CTA's 128 consecutive rays form one contiguous slot range [s_base, s_base + total): every thread turns the
+// cached t values of its ray (one contiguous t_cache row) into samples inside a shared-memory tile laid out like the output, and the tile leaves as full
+// contiguous lines of xyzs / dirs / deltas — instead of one thread walking its ray with 4-byte stores at a 12-byte stride.  Same expressions as DdaRay::probe
+// for an occupied cell: bit-identical samples.
+constexpr uint32_t MW_TILE = 1024;                // slots staged per round (32 KB of shared memory)
 __global__ void __launch_bounds__(MT_THREADS) k_march_train_emit(
         const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
         float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas,
         int32_t *__restrict__ rays, int32_t *__restrict__ counter, const int32_t *__restrict__ cta_totals, const float *__restrict__ t_cache) {
     __shared__ uint32_t red[MT_THREADS / 32];
-    __shared__ uint32_t s_base, s_keep;
-    __shared__ uint32_t s_start[MT_THREADS + 1];           // first slot (relative to s_base) of every ray of the CTA; [128] = total kept
-    __shared__ float s_ray[MT_THREADS][6];
+    __shared__ uint32_t s_base, s_keep, s_total;
     __shared__ float s_xyz[MW_TILE * 3], s_dir[MW_TILE * 3], s_del[MW_TILE * 2];
     uint32_t off, num;
     march_train_offsets(N, rays, counter, cta_totals, red, s_base, off, num);
     const uint32_t n = blockIdx.x * MT_THREADS + threadIdx.x;
+    float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 0.0f};
     if (n < N) {
         rays[3 * (size_t)n + 1] = (int32_t)off;
+        if (num) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) { s_ray[threadIdx.x][c] = rays_o[3 * (size_t)n + c]; s_ray[threadIdx.x][3 + c] = rays_d[3 * (size_t)n + c]; }
+            for (int c = 0; c < 3; c++) { o[c] = rays_o[3 * (size_t)n + c]; d[c] = rays_d[3 * (size_t)n + c]; }
+        }
     }
     if (threadIdx.x == 0) s_keep = 0xffffffffu;
     __syncthreads();
     // rays past the buffer are dropped whole (raymarching.cu:456-457); offsets ascend, so the kept slots are a prefix of the CTA's range
-    const bool dropped = num > 0 && off + num > M;
-    if (dropped) atomicMin(&s_keep, off - s_base);
-    s_start[threadIdx.x] = off - s_base;
-    if (threadIdx.x == MT_THREADS - 1) s_start[MT_THREADS] = off + num - s_base;
+    const uint32_t a = off - s_base;
+    if (num > 0 && off + num > M) atomicMin(&s_keep, a);
+    if (threadIdx.x == MT_THREADS - 1) s_total = a + num;
     __syncthreads();
-    const uint32_t total = min(s_start[MT_THREADS], s_keep);
+    const uint32_t total = min(s_total, s_keep);
     DdaRay q;                                              // only the step rule is used
     q.dx = q.dy = q.dz = 1.0f;
     q.init_common(bound, dt_gamma, max_steps, C, H, 0.0f);
+    const float *tc = t_cache + (size_t)n * max_steps;
     for (uint32_t j0 = 0; j0 < total; j0 += MW_TILE) {
-        const uint32_t cnt = min(MW_TILE, total - j0);
-        for (uint32_t j = threadIdx.x; j < cnt; j += MT_THREADS) {
-            const uint32_t slot = j0 + j;
-            uint32_t lo = 0, hi = MT_THREADS;              // largest r with s_start[r] <= slot (rays without samples share a start with their successor: skipped)
-#pragma unroll
-            for (int it = 0; it < 7; it++) { const uint32_t mid = (lo + hi) >> 1; if (s_start[mid] <= slot) lo = mid; else hi = mid; }
-            const uint32_t k = slot - s_start[lo];
-            const float tk = __ldcs(t_cache + ((size_t)blockIdx.x * MT_THREADS + lo) * max_steps + k);
+        const uint32_t j1 = min(j0 + MW_TILE, total);
+        const uint32_t lo = max(a, j0), hi = min(a + num, j1);
+        for (uint32_t sl = lo; sl < hi; sl++) {
+            const float tk = __ldcs(tc + (sl - a));
             const float dt = q.step_of(tk);
-            const float *ry = s_ray[lo];
-            s_xyz[3 * j] = clampf(__fmaf_rn(tk, ry[3], ry[0]), -bound, bound);
-            s_xyz[3 * j + 1] = clampf(__fmaf_rn(tk, ry[4], ry[1]), -bound, bound);
-            s_xyz[3 * j + 2] = clampf(__fmaf_rn(tk, ry[5], ry[2]), -bound, bound);
-            s_dir[3 * j] = ry[3]; s_dir[3 * j + 1] = ry[4]; s_dir[3 * j + 2] = ry[5];
+            const uint32_t j = sl - j0;
+            s_xyz[3 * j] = clampf(__fmaf_rn(tk, d[0], o[0]), -bound, bound);
+            s_xyz[3 * j + 1] = clampf(__fmaf_rn(tk, d[1], o[1]), -bound, bound);
+            s_xyz[3 * j + 2] = clampf(__fmaf_rn(tk, d[2], o[2]), -bound, bound);
+            s_dir[3 * j] = d[0]; s_dir[3 * j + 1] = d[1]; s_dir[3 * j + 2] = d[2];
             s_del[2 * j] = dt; s_del[2 * j + 1] = __fadd_rn(tk, dt);
         }
         __syncthreads();
+        const uint32_t cnt = j1 - j0;
         const size_t g0 = (size_t)s_base + j0;
-        for (uint32_t e = threadIdx.x; e < 3 * cnt; e += MT_THREADS) { __stcs(xyzs + 3 * g0 + e, s_xyz[e]); __stcs(dirs + 3 * g0 + e, s_dir[e]); }
-        for (uint32_t e = threadIdx.x; e < 2 * cnt; e += MT_THREADS) __stcs(deltas + 2 * g0 + e, s_del[e]);
+        for (uint32_t e = threadIdx.x; e < 3 * cnt; e += MT_THREADS) { xyzs[3 * g0 + e] = s_xyz[e]; dirs[3 * g0 + e] = s_dir[e]; }
+        for (uint32_t e = threadIdx.x; e < 2 * cnt; e += MT_THREADS) deltas[2 * g0 + e] = s_del[e];
         __syncthreads();
     }
 }
@@ -338,17 +376,12 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_write(
     float *px = xyzs + 3 * (size_t)off, *pd = dirs + 3 * (size_t)off, *pl = deltas + 2 * (size_t)off;
     float t = r.perturb(nears[n], noises[n]);
     if (box) r.far = r.clip_to_box(box, t);
-    uint32_t step = 0;
-    DdaSample s;
-    while (t < r.far && step < num) {
-        if (r.probe(grid, t, s)) {
-            t = __fadd_rn(t, s.dt);
-            px[0] = s.x; px[1] = s.y; px[2] = s.z;
-            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
-            pl[0] = s.dt; pl[1] = t;
-            px += 3; pd += 3; pl += 2; step++;
-        }
-    }
+    r.march<4>(grid, t, num, [&](uint32_t k, float tk, float dt) {
+        px[3 * k] = clampf(__fmaf_rn(tk, r.dx, r.ox), -bound, bound); px[3 * k + 1] = clampf(__fmaf_rn(tk, r.dy, r.oy), -bound, bound);
+        px[3 * k + 2] = clampf(__fmaf_rn(tk, r.dz, r.oz), -bound, bound);
+        pd[3 * k] = r.dx; pd[3 * k + 1] = r.dy; pd[3 * k + 2] = r.dz;
+        pl[2 * k] = dt; pl[2 * k + 1] = __fadd_rn(tk, dt);
+    });
 }
 
 // raymarching.cu:536-583 — gradients to ray origins / directions (camera optimisation)
@@ -402,10 +435,7 @@ __global__ void __launch_bounds__(MI_THREADS) k_march_rays(
         r.init(rays_o + 3 * (size_t)id, rays_d + 3 * (size_t)id, bound, dt_gamma, max_steps, C, H, fars[id]);
         float t = r.perturb(rays_t[id], noises[n]);
         if (box) r.far = r.clip_to_box(box, t);
-        DdaSample s;
-        while (t < r.far && step < n_step) {
-            if (r.probe(grid, t, s)) { s_t[threadIdx.x][step] = t; t = __fadd_rn(t, s.dt); step++; }
-        }
+        step = r.march<4>(grid, t, n_step, [&](uint32_t k, float tk, float) { s_t[threadIdx.x][k] = tk; });
         s_ray[threadIdx.x][0] = r.ox; s_ray[threadIdx.x][1] = r.oy; s_ray[threadIdx.x][2] = r.oz;
         s_ray[threadIdx.x][3] = r.dx; s_ray[threadIdx.x][4] = r.dy; s_ray[threadIdx.x][5] = r.dz;
     } else {
@@ -454,17 +484,12 @@ __global__ void __launch_bounds__(128) k_march_rays_long(
     float t = r.perturb(rays_t[id], noises[n]);
     if (box) r.far = r.clip_to_box(box, t);
     float *px = xyzs + 3 * (size_t)n * n_step, *pd = dirs + 3 * (size_t)n * n_step, *pl = deltas + 2 * (size_t)n * n_step;
-    uint32_t step = 0;
-    DdaSample s;
-    while (t < r.far && step < n_step) {
-        if (r.probe(grid, t, s)) {
-            t = __fadd_rn(t, s.dt);
-            px[0] = s.x; px[1] = s.y; px[2] = s.z;
-            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
-            pl[0] = s.dt; pl[1] = t;
-            px += 3; pd += 3; pl += 2; step++;
-        }
-    }
+    r.march<4>(grid, t, n_step, [&](uint32_t k, float tk, float dt) {
+        px[3 * k] = clampf(__fmaf_rn(tk, r.dx, r.ox), -bound, bound); px[3 * k + 1] = clampf(__fmaf_rn(tk, r.dy, r.oy), -bound, bound);
+        px[3 * k + 2] = clampf(__fmaf_rn(tk, r.dz, r.oz), -bound, bound);
+        pd[3 * k] = r.dx; pd[3 * k + 1] = r.dy; pd[3 * k + 2] = r.dz;
+        pl[2 * k] = dt; pl[2 * k + 1] = __fadd_rn(tk, dt);
+    });
 }
 
 static inline int grid_for(uint32_t n, int threads) {
@@ -558,7 +583,7 @@ int b2n_march_rays_train_ws(const float *rays_o, const float *rays_d, const uint
         if (check_launch("march_rays_train(box)")) return 1;
     }
     const float *boxp = clip ? box + 6 * OCC_PARTS : nullptr;
-    k_march_train_count<<<ctas, MT_THREADS, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, totals, t_cache, boxp);
+    k_march_train_count<<<ceil_div<uint32_t>(ctas, MC_GROUPS), MT_THREADS, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, totals, t_cache, boxp);
     if (check_launch("march_rays_train(count)")) return 1;
     if (t_cache)
         k_march_train_emit<<<ctas, MT_THREADS, 0, st>>>(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, xyzs, dirs, deltas, rays, counter, totals, t_cache);

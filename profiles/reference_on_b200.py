@@ -96,7 +96,7 @@ out["infer_512x512"] = {"frames_per_sec": 1e3 / ms, "ms_per_frame": ms, "frames_
 
 # ---- training: 65 536 rays per step -------------------------------------------------------------------------------------------------------------
 mt = build(True)
-opt = torch.optim.AdamW(mt.get_params(1e-2, 1e-3), betas=(0, 0.99), eps=1e-8)          # train.py:274
+opt = torch.optim.AdamW(mt.get_params(1e-2, 1e-3), betas=(0.0, 0.99), eps=1e-8)        # train.py:274 (its integer 0 is rejected by torch 2.11's AdamW: the only edit)
 scaler = torch.amp.GradScaler("cuda")
 n = 65536
 batches = []

@@ -177,7 +177,7 @@ def case_smooth_lips(sz, mode, outdir):
 def case_train(sz, mode, outdir):
     """run_cuda's training branch (renderer.py:279-304, 553-570) + autograd backward of a fixed linear functional of its outputs, under autocast with a
     static loss scale (the reference uses GradScaler): outputs and the gradient of every parameter."""
-    n, scale = sz["n_train"], 1024.0
+    n, scale = sz["n_train"], rc.LOSS_SCALE
     m = build("head_deepspeech", asr="deepspeech", table_scale=0.5).train(); m.testing = False
     ro, rd, auds, eye, bg, w = rc.train_inputs(n)
     ro, rd, auds, eye, bg = (T(a) for a in (ro, rd, auds, eye, bg))
@@ -252,7 +252,7 @@ def case_torso(sz, mode, outdir):
     # training backward (TrainerUtil.py:188-236 torso stage: MSE on torso_color); here a fixed linear functional
     m.train()
     wt = T(r.standard_normal((N, 3)).astype(np.float32))
-    scale = 1024.0
+    scale = rc.LOSS_SCALE
     with torch.autocast("cuda", dtype=torch.float16):
         res = m.render_torso(torch.zeros(1, N, 3, device=dev), None, None, coords, pose, index=[5], bg_color=bg_ray)
         loss = (res["torso_color"] * wt).sum() / N

@@ -23,6 +23,31 @@ SIZES = {
 }
 
 
+LOSS_SCALE = 65536.0           # static loss scale of the backward goldens = GradScaler's initial scale (the reference trains under autocast + GradScaler)
+
+
+def grad_errors(named_ours, golden, take, index_rows=None):
+    """{name: (max error, L1 error)} of our gradients against the golden ones, each RELATIVE TO THE LARGEST GRADIENT OF THE PARAMETER'S NETWORK (audio_net,
+    audio_att_net, sigma_net, ...; a tri-plane table is its own network): under autocast the reference's backward runs in fp16, where the smallest tensors of a
+    network (the first attention convolutions: 1e-9 against 1e-7 for the network) underflow to exactly 0 — an error bar per tensor would compare against that
+    underflow, one per network compares against what the optimizer step of that network sees."""
+    rows = {}
+    for name, gr in named_ours:
+        key = "grad." + name
+        if key not in golden:
+            continue
+        if index_rows and name in index_rows:
+            gr = gr[index_rows[name]]
+        rows[name] = take(golden, key, gr)
+    net_of = lambda n: n.split(".")[0]
+    net_max, net_l1 = {}, {}
+    for name, (o, w) in rows.items():
+        k = net_of(name)
+        net_max[k] = max(net_max.get(k, 0.0), float(w.abs().max()))
+        net_l1[k] = net_l1.get(k, 0.0) + float(w.abs().sum())
+    return {name: (float((o - w).abs().max()) / (net_max[net_of(name)] + 1e-30), float((o - w).abs().sum()) / (net_l1[net_of(name)] + 1e-30)) for name, (o, w) in rows.items()}
+
+
 def ref_opt(torso=False, asr="hubert", smooth_lips=False):
     """The option namespace the reference's NeRFNetwork / NeRFRenderer read (train.py:18-141 defaults with -O)."""
     return types.SimpleNamespace(bound=1, min_near=0.05, density_thresh=10, density_thresh_torso=0.01, exp_eye=True, test_train=False, smooth_lips=smooth_lips,

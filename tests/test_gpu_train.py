@@ -112,12 +112,12 @@ def test_graphed_step_matches_eager_step():
         assert tr.mean_count > 0
         step = tr.train_step_graphed if graphed else tr.train_step
         ls = []
-        for s in range(6):
+        for s in range(6):                                   # global_step 16..21: the first of them carries the smoothness regulariser (its own graph)
             loss, m_buf = step(rays_o, rays_d, a, g, index=1, perturb=False)
             ls.append(float(loss))
         losses.append(ls)
         if graphed:
-            assert len(tr._graphs) == 1 and m_buf >= -(-tr.mean_count // Trainer.M_BUCKET) * Trainer.M_BUCKET
+            assert len(tr._graphs) == 2 and m_buf >= -(-tr.mean_count // Trainer.M_BUCKET) * Trainer.M_BUCKET
     eager, graphed = np.array(losses[0]), np.array(losses[1])
     # same arithmetic; the sample buffer is rounded up to M_BUCKET in graph mode (never truncates more rays than the eager step) and the
     # atomic scatter order differs -> tiny drift that grows over the steps
