@@ -124,6 +124,46 @@ struct DdaRay {
         do { t = __fadd_rn(t, step_of(t)); } while (t < tt);
     }
 
+    // ONE-STEP-PER-CELL rays.  In an empty cell the reference advances `do t += step_of(t) while (t < tt)` with tt = t + min(tx, ty, tz) the exit of the cell.
+    // Along the axis a with the largest |d_a| the exit is at most one cell away: t_a <= cell |1 / d_a|, so min(tx, ty, tz) <= cell * min_a |1 / d_a|.  If that
+    // bound (with 1e-4 of slack for the rounding of the exit arithmetic, which is a few ulps) is <= dt_min <= step_of(t), then tt <= t + step_of(t) — float
+    // addition is monotone — and the do-while runs exactly once: an empty cell advances ONE orbit step, like an occupied one.  With the reference's own step
+    // rule dt_max = cell diagonal this holds for every ray whose direction is not within a fraction of a degree of a cell diagonal (max |d_a| >= 0.5775),
+    // as long as dt_min == dt_max (max_steps <= H / 2^(C-1), the run configuration).  For such a ray the march is a plain walk over the orbit: no exit
+    // arithmetic at all, and nothing data-dependent in the control flow but the sample counter.  `cell` is the coarsest cascade's (the largest) cell.
+    __device__ __forceinline__ bool one_step_per_cell() const {
+        const float mb = fminf(__int_as_float((127 + (int)C - 1) << 23), bound);
+        const float cell = __fmul_rn(__fmul_rn(mb, 2.0f), rH);
+        return __fmul_rn(__fmul_rn(cell, 1.0001f), fminf(fabsf(rdx), fminf(fabsf(rdy), fabsf(rdz)))) <= dt_min;
+    }
+    // march<G> for a one-step-per-cell ray: same t sequence and samples as the reference loop
+    template <int G, typename F>
+    __device__ __forceinline__ uint32_t march_orbit(const uint8_t *__restrict__ grid, float &t, uint32_t max_n, F &&on_sample) const {
+        uint32_t num = 0;
+        while (t < far && num < max_n) {
+            float ts[G];
+            uint32_t occ[G];
+            ts[0] = t;
+#pragma unroll
+            for (int j = 1; j < G; j++) ts[j] = __fadd_rn(ts[j - 1], step_of(ts[j - 1]));
+#pragma unroll
+            for (int j = 0; j < G; j++) { const uint32_t idx = cell_of(ts[j]); occ[j] = (__ldg(grid + (idx >> 3)) >> (idx & 7)) & 1u; }
+#pragma unroll
+            for (int j = 0; j < G; j++) {
+                if (ts[j] < far && num < max_n) {
+                    if (occ[j]) { on_sample(num, ts[j], step_of(ts[j])); num++; }
+                    t = __fadd_rn(ts[j], step_of(ts[j]));
+                }
+            }
+        }
+        return num;
+    }
+    // dispatch: the cheap walk when the ray qualifies, the general loop otherwise
+    template <int G, typename F>
+    __device__ __forceinline__ uint32_t march_auto(const uint8_t *__restrict__ grid, float &t, uint32_t max_n, F &&on_sample) const {
+        return one_step_per_cell() ? march_orbit<G>(grid, t, max_n, on_sample) : march<G>(grid, t, max_n, on_sample);
+    }
+
     // The reference's marching loop (`while (t < far && step < max_n) { probe }`, raymarching.cu:400-441) with G probes in flight per thread.  Every t the loop
     // visits lies on the orbit t <- t + step_of(t), so the next G - 1 orbit points are computed ahead and their cells fetched together (G independent index
     // computations and bitfield loads instead of G dependent round trips); the loop is then replayed serially over the fetched bits, and a fetched bit is used

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(FM_THREADS) k_frame_march(const float *__restr
         id = w.alive[c.buf][n];
         r.init(rays_o + 3 * (size_t)id, rays_d + 3 * (size_t)id, bound, dt_gamma, max_steps, C, H, w.fars[id]);
         float t = w.rays_t[id];
-        step = r.march<4>(grid, t, n_step, [&](uint32_t ks, float tk, float dt) {
+        step = r.march_auto<4>(grid, t, n_step, [&](uint32_t ks, float tk, float dt) {
 #pragma unroll
             for (uint32_t k = 0; k < 8; k++) if (k == ks) { ts[k] = tk; dts[k] = dt; }
         });

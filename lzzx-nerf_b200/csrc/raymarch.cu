@@ -190,13 +190,14 @@ __host__ __device__ __forceinline__ uint32_t ceil_div_u(uint32_t a, uint32_t b) 
 // warp for the longest ray at a third of its lanes.  A CTA therefore first clips a tile of 512 rays (cheap, all lanes), compacts the ones that have something to
 // march into a dense list in shared memory, and marches those with full warps and four probes in flight per thread (DdaRay::march); counts go back to ray
 // order through shared memory.
-constexpr int MC_GROUPS = 4;                          // groups of MT_THREADS rays per CTA of the count pass
+// MC_GROUPS = groups of MT_THREADS rays per CTA: 4 (a 512-ray tile packs the live rays into full warps) when the batch still fills the machine with CTAs, else 1
+template <int MC_GROUPS>
 __global__ void __launch_bounds__(MT_THREADS) k_march_train_count(
         const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
         float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
         const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
         int32_t *__restrict__ rays, const int32_t *__restrict__ counter, int32_t *__restrict__ cta_totals, float *__restrict__ t_cache,
-        const float *__restrict__ box) {
+        const float *__restrict__ box, int32_t *__restrict__ ticket) {
     constexpr uint32_t TILE = MC_GROUPS * MT_THREADS;
     __shared__ float s_t0[TILE], s_far[TILE];
     __shared__ uint16_t s_list[TILE];
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_count(
         r.init(rays_o + 3 * (size_t)m, rays_d + 3 * (size_t)m, bound, dt_gamma, max_steps, C, H, s_far[q]);
         float t = s_t0[q];
         float *tc = t_cache ? t_cache + (size_t)m * max_steps : nullptr;
-        s_num[q] = (uint16_t)r.march<4>(grid, t, max_steps < 65535u ? max_steps : 65535u, [&](uint32_t k, float tk, float) { if (tc) tc[k] = tk; });
+        s_num[q] = (uint16_t)r.march_auto<4>(grid, t, max_steps < 65535u ? max_steps : 65535u, [&](uint32_t k, float tk, float) { if (tc) tc[k] = tk; });
     }
     __syncthreads();
     const uint32_t groups = ceil_div_u(N, MT_THREADS);
@@ -257,9 +258,39 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_count(
 #pragma unroll
             for (int w = 0; w < MT_THREADS / 32; w++) tot += s_wcnt[w];
             cta_totals[1 + gi] = (int32_t)tot;
-            if (gi == 0) cta_totals[0] = counter[0];   // snapshot: offsets start at the counter's current value
         }
     }
+    // the last CTA to finish turns the group totals into slot offsets: prefix[g] = counter snapshot + samples of all groups before g  (prefix = cta_totals + groups + 1)
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int32_t)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    int32_t *prefix = cta_totals + groups + 1;
+    // tiles of 4 x 128 consecutive totals (coalesced), scanned in registers / by shuffles, with a running carry
+    uint32_t carry = (uint32_t)counter[0];                 // snapshot: offsets start at the counter's current value
+    for (uint32_t t0 = 0; t0 < groups; t0 += 4 * MT_THREADS) {
+        uint32_t v[4];
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) { const uint32_t b = t0 + 4 * threadIdx.x + c; v[c] = b < groups ? (uint32_t)__ldcg(cta_totals + 1 + b) : 0u; }
+        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+        uint32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        __syncthreads();
+        if (lane == 31) s_wcnt[warp] = inc;
+        __syncthreads();
+        uint32_t run = carry + inc - mine, tile_total = 0;
+#pragma unroll
+        for (int w = 0; w < MT_THREADS / 32; w++) { if (w < (int)warp) run += s_wcnt[w]; tile_total += s_wcnt[w]; }
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) { const uint32_t b = t0 + 4 * threadIdx.x + c; if (b < groups) prefix[b] = (int32_t)run; run += v[c]; }
+        carry += tile_total;
+    }
+    if (threadIdx.x == 0) prefix[groups] = (int32_t)carry;
+    if (threadIdx.x == 0) { cta_totals[0] = counter[0]; *ticket = 0; }
 }
 
 // Shared prologue of both write kernels: offsets = snapshot + prefix(CTA totals) + in-CTA exclusive scan.  Returns this thread's (offset, count); the last
@@ -267,18 +298,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_count(
 __device__ __forceinline__ void march_train_offsets(uint32_t N, const int32_t *__restrict__ rays, int32_t *__restrict__ counter, const int32_t *__restrict__ cta_totals,
                                                     uint32_t *red, uint32_t &s_base, uint32_t &off, uint32_t &num) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t part = 0;
-    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += MT_THREADS) part += (uint32_t)cta_totals[1 + b];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) red[warp] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t b = (uint32_t)cta_totals[0];
-#pragma unroll
-        for (int w = 0; w < MT_THREADS / 32; w++) b += red[w];
-        s_base = b;
-    }
+    if (threadIdx.x == 0) s_base = (uint32_t)cta_totals[gridDim.x + 1 + blockIdx.x];       // prefix[] behind the totals (k_march_train_count's last CTA)
     __syncthreads();
     const uint32_t n = blockIdx.x * MT_THREADS + threadIdx.x;
     num = (n < N) ? (uint32_t)rays[3 * (size_t)n + 2] : 0u;
@@ -303,14 +323,14 @@ __device__ __forceinline__ void march_train_offsets(uint32_t N, const int32_t *_
 // cached t values of its ray (one contiguous t_cache row) into samples inside a shared-memory tile laid out like the output, and the tile leaves as full
 // contiguous lines of xyzs / dirs / deltas — instead of one thread walking its ray with 4-byte stores at a 12-byte stride.  Same expressions as DdaRay::probe
 // for an occupied cell: bit-identical samples.
-constexpr uint32_t MW_TILE = 1024;                // slots staged per round (32 KB of shared memory)
+constexpr uint32_t MW_TILE = 512;                 // slots staged per round (16 KB of shared memory)
 __global__ void __launch_bounds__(MT_THREADS) k_march_train_emit(
         const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
         float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas,
         int32_t *__restrict__ rays, int32_t *__restrict__ counter, const int32_t *__restrict__ cta_totals, const float *__restrict__ t_cache) {
     __shared__ uint32_t red[MT_THREADS / 32];
     __shared__ uint32_t s_base, s_keep, s_total;
-    __shared__ float s_xyz[MW_TILE * 3], s_dir[MW_TILE * 3], s_del[MW_TILE * 2];
+    __shared__ __align__(16) float s_xyz[MW_TILE * 3 + 4], s_dir[MW_TILE * 3 + 4], s_del[MW_TILE * 2 + 4];
     uint32_t off, num;
     march_train_offsets(N, rays, counter, cta_totals, red, s_base, off, num);
     const uint32_t n = blockIdx.x * MT_THREADS + threadIdx.x;
@@ -334,24 +354,48 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_emit(
     q.dx = q.dy = q.dz = 1.0f;
     q.init_common(bound, dt_gamma, max_steps, C, H, 0.0f);
     const float *tc = t_cache + (size_t)n * max_steps;
+    const bool vec4 = (max_steps & 3u) == 0;               // rows are 16-byte aligned: read them four parameters at a time
+    // the tile keeps the 16-byte phase of its destination, so it leaves as aligned 16-byte stores (a round advances every array by a multiple of 16 bytes)
+    const uint32_t ph_x = (uint32_t)((reinterpret_cast<uintptr_t>(xyzs + 3 * (size_t)s_base) >> 2) & 3), ph_d = (uint32_t)((reinterpret_cast<uintptr_t>(dirs + 3 * (size_t)s_base) >> 2) & 3),
+                   ph_l = (uint32_t)((reinterpret_cast<uintptr_t>(deltas + 2 * (size_t)s_base) >> 2) & 3);
+    auto flush = [&](float *dst, const float *src, uint32_t nfl, uint32_t phase) {      // dst[e] = src[phase + e], e < nfl
+        const uint32_t head = min((4u - phase) & 3u, nfl), nv = (nfl - head) >> 2, tail = nfl - head - 4 * nv;
+        if (threadIdx.x < head) dst[threadIdx.x] = src[phase + threadIdx.x];
+        float4 *d4 = reinterpret_cast<float4 *>(dst + head);
+        const float4 *s4 = reinterpret_cast<const float4 *>(src + phase + head);
+        for (uint32_t v = threadIdx.x; v < nv; v += MT_THREADS) d4[v] = s4[v];
+        if (threadIdx.x < tail) dst[head + 4 * nv + threadIdx.x] = src[phase + head + 4 * nv + threadIdx.x];
+    };
     for (uint32_t j0 = 0; j0 < total; j0 += MW_TILE) {
         const uint32_t j1 = min(j0 + MW_TILE, total);
-        const uint32_t lo = max(a, j0), hi = min(a + num, j1);
-        for (uint32_t sl = lo; sl < hi; sl++) {
-            const float tk = __ldcs(tc + (sl - a));
+        auto put = [&](uint32_t sl, float tk) {
             const float dt = q.step_of(tk);
             const uint32_t j = sl - j0;
-            s_xyz[3 * j] = clampf(__fmaf_rn(tk, d[0], o[0]), -bound, bound);
-            s_xyz[3 * j + 1] = clampf(__fmaf_rn(tk, d[1], o[1]), -bound, bound);
-            s_xyz[3 * j + 2] = clampf(__fmaf_rn(tk, d[2], o[2]), -bound, bound);
-            s_dir[3 * j] = d[0]; s_dir[3 * j + 1] = d[1]; s_dir[3 * j + 2] = d[2];
-            s_del[2 * j] = dt; s_del[2 * j + 1] = __fadd_rn(tk, dt);
+            float *px = s_xyz + ph_x + 3 * j, *pd = s_dir + ph_d + 3 * j, *pl = s_del + ph_l + 2 * j;
+            px[0] = clampf(__fmaf_rn(tk, d[0], o[0]), -bound, bound);
+            px[1] = clampf(__fmaf_rn(tk, d[1], o[1]), -bound, bound);
+            px[2] = clampf(__fmaf_rn(tk, d[2], o[2]), -bound, bound);
+            pd[0] = d[0]; pd[1] = d[1]; pd[2] = d[2];
+            pl[0] = dt; pl[1] = __fadd_rn(tk, dt);
+        };
+        const uint32_t lo = max(a, j0), hi = min(a + num, j1);
+        if (vec4) {
+#pragma unroll 1
+            for (uint32_t k4 = (lo - a) >> 2; lo < hi && 4 * k4 < hi - a; k4++) {
+                const float4 v = __ldcs(reinterpret_cast<const float4 *>(tc) + k4);
+                const float tq[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (uint32_t c = 0; c < 4; c++) { const uint32_t sl = a + 4 * k4 + c; if (sl >= lo && sl < hi) put(sl, tq[c]); }
+            }
+        } else {
+            for (uint32_t sl = lo; sl < hi; sl++) put(sl, __ldcs(tc + (sl - a)));
         }
         __syncthreads();
         const uint32_t cnt = j1 - j0;
         const size_t g0 = (size_t)s_base + j0;
-        for (uint32_t e = threadIdx.x; e < 3 * cnt; e += MT_THREADS) { xyzs[3 * g0 + e] = s_xyz[e]; dirs[3 * g0 + e] = s_dir[e]; }
-        for (uint32_t e = threadIdx.x; e < 2 * cnt; e += MT_THREADS) deltas[2 * g0 + e] = s_del[e];
+        flush(xyzs + 3 * g0, s_xyz, 3 * cnt, ph_x);
+        flush(dirs + 3 * g0, s_dir, 3 * cnt, ph_d);
+        flush(deltas + 2 * g0, s_del, 2 * cnt, ph_l);
         __syncthreads();
     }
 }
@@ -376,7 +420,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_write(
     float *px = xyzs + 3 * (size_t)off, *pd = dirs + 3 * (size_t)off, *pl = deltas + 2 * (size_t)off;
     float t = r.perturb(nears[n], noises[n]);
     if (box) r.far = r.clip_to_box(box, t);
-    r.march<4>(grid, t, num, [&](uint32_t k, float tk, float dt) {
+    r.march_auto<4>(grid, t, num, [&](uint32_t k, float tk, float dt) {
         px[3 * k] = clampf(__fmaf_rn(tk, r.dx, r.ox), -bound, bound); px[3 * k + 1] = clampf(__fmaf_rn(tk, r.dy, r.oy), -bound, bound);
         px[3 * k + 2] = clampf(__fmaf_rn(tk, r.dz, r.oz), -bound, bound);
         pd[3 * k] = r.dx; pd[3 * k + 1] = r.dy; pd[3 * k + 2] = r.dz;
@@ -435,7 +479,7 @@ __global__ void __launch_bounds__(MI_THREADS) k_march_rays(
         r.init(rays_o + 3 * (size_t)id, rays_d + 3 * (size_t)id, bound, dt_gamma, max_steps, C, H, fars[id]);
         float t = r.perturb(rays_t[id], noises[n]);
         if (box) r.far = r.clip_to_box(box, t);
-        step = r.march<4>(grid, t, n_step, [&](uint32_t k, float tk, float) { s_t[threadIdx.x][k] = tk; });
+        step = r.march_auto<4>(grid, t, n_step, [&](uint32_t k, float tk, float) { s_t[threadIdx.x][k] = tk; });
         s_ray[threadIdx.x][0] = r.ox; s_ray[threadIdx.x][1] = r.oy; s_ray[threadIdx.x][2] = r.oz;
         s_ray[threadIdx.x][3] = r.dx; s_ray[threadIdx.x][4] = r.dy; s_ray[threadIdx.x][5] = r.dz;
     } else {
@@ -484,7 +528,7 @@ __global__ void __launch_bounds__(128) k_march_rays_long(
     float t = r.perturb(rays_t[id], noises[n]);
     if (box) r.far = r.clip_to_box(box, t);
     float *px = xyzs + 3 * (size_t)n * n_step, *pd = dirs + 3 * (size_t)n * n_step, *pl = deltas + 2 * (size_t)n * n_step;
-    r.march<4>(grid, t, n_step, [&](uint32_t k, float tk, float dt) {
+    r.march_auto<4>(grid, t, n_step, [&](uint32_t k, float tk, float dt) {
         px[3 * k] = clampf(__fmaf_rn(tk, r.dx, r.ox), -bound, bound); px[3 * k + 1] = clampf(__fmaf_rn(tk, r.dy, r.oy), -bound, bound);
         px[3 * k + 2] = clampf(__fmaf_rn(tk, r.dz, r.oz), -bound, bound);
         pd[3 * k] = r.dx; pd[3 * k + 1] = r.dy; pd[3 * k + 2] = r.dz;
@@ -555,7 +599,7 @@ static inline bool mt_cached(uint32_t N, uint32_t max_steps) { return max_steps 
 
 uint64_t b2n_march_rays_train_workspace_bytes(uint32_t N, uint32_t max_steps) {
     const uint32_t ctas = ceil_div<uint32_t>(N ? N : 1, MT_THREADS);
-    return mt_align(sizeof(float) * OCC_BOX_FLOATS) + mt_align(sizeof(int32_t) * (size_t)(ctas + 1)) +
+    return mt_align(sizeof(float) * OCC_BOX_FLOATS) + mt_align(sizeof(int32_t) * 2 * (size_t)(ctas + 1)) +
            (mt_cached(N, max_steps) ? mt_align(sizeof(float) * (size_t)max_steps * N) : 0);
 }
 
@@ -574,16 +618,20 @@ int b2n_march_rays_train_ws(const float *rays_o, const float *rays_d, const uint
     float *box = (float *)ws;
     int32_t *totals = (int32_t *)(ws + mt_align(sizeof(float) * OCC_BOX_FLOATS));
     // per-sample t cache between the two passes ([N][max_steps] floats: 4 MB for the 65 536-ray step); very large max_steps fall back to re-marching
-    float *t_cache = mt_cached(N, max_steps) ? (float *)((char *)totals + mt_align(sizeof(int32_t) * (size_t)(ctas + 1))) : nullptr;
+    float *t_cache = mt_cached(N, max_steps) ? (float *)((char *)totals + mt_align(sizeof(int32_t) * 2 * (size_t)(ctas + 1))) : nullptr;
     // exact empty-space clipping needs whole 32-cell words and a power-of-two grid (Morton blocks); otherwise march unclipped
     const bool clip = (H & (H - 1)) == 0 && H >= 4 && ((uintptr_t)grid & 3) == 0;
+    B2N_CUDA(cudaMemsetAsync(box + 6 * OCC_PARTS + 6, 0, 2 * sizeof(float), st));       // the two last-CTA tickets (box reduction, offset scan)
     if (clip) {
-        B2N_CUDA(cudaMemsetAsync(box + 6 * OCC_PARTS + 6, 0, 2 * sizeof(float), st));
         k_occ_box<<<OCC_PARTS, 256, 0, st>>>(grid, C, H, bound, box, 1);
         if (check_launch("march_rays_train(box)")) return 1;
     }
     const float *boxp = clip ? box + 6 * OCC_PARTS : nullptr;
-    k_march_train_count<<<ceil_div<uint32_t>(ctas, MC_GROUPS), MT_THREADS, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, totals, t_cache, boxp);
+    int32_t *ticket = reinterpret_cast<int32_t *>(box + 6 * OCC_PARTS + 7);
+    if (ctas >= 8u * (uint32_t)sm_count())
+        k_march_train_count<4><<<ceil_div<uint32_t>(ctas, 4u), MT_THREADS, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, totals, t_cache, boxp, ticket);
+    else
+        k_march_train_count<1><<<ctas, MT_THREADS, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, totals, t_cache, boxp, ticket);
     if (check_launch("march_rays_train(count)")) return 1;
     if (t_cache)
         k_march_train_emit<<<ctas, MT_THREADS, 0, st>>>(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, xyzs, dirs, deltas, rays, counter, totals, t_cache);
