@@ -258,6 +258,8 @@ def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536
         ms = float(t.item())
     return {"metric": "train_rays_per_sec", "value": world * steps * n_rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": n_rays,
             "samples_per_step_buffer": int(m_buf), "loss": float(loss), "grad_allreduce_bytes": tr.grads.nbytes() if world > 1 else 0, "steps_timed": steps,
+            "grad_allreduce": "none (1 GPU)" if world == 1 else ("one two-shot kernel per rank over NVLink peer memory (csrc/peer_allreduce.cu), inside the step's graph"
+                                                              if tr.grads.peer is not None else "ncclAllReduce of the flat buffer inside the step's graph"),
             "objective": "TrainerUtil.py:238-363 head branch: uncertainty-weighted MSE + loss_u + static-uncertainty + entropy(1e-4) + masked / ramped ambient terms, "
                          "smoothness regulariser on every 16th step (two more network passes); AdamW groups of network.py:332-356, LambdaLR stepped every iteration",
             "path": ("eager: " if eager else "forward + backward + all-reduce replayed from one CUDA graph: ") +

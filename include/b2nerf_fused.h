@@ -278,6 +278,23 @@ int b2n_torso_forward(const b2n_torso_weights *w, const float *bg_coords, uint32
  * concurrently running call */
 uint64_t b2n_torso_workspace_bytes(void);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory (csrc/peer_allreduce.cu) ---------------------------------------
+ * One process per GPU on ONE node.  Every rank allocates its flat gradient buffer with b2n_peer_alloc (a cudaMalloc block followed by a flag block, zeroed;
+ * `ipc_handle_out` receives the 64-byte CUDA IPC handle), the ranks exchange the handles (torch.distributed all_gather), and b2n_peer_comm_create opens all of
+ * them (all_handles = world x 64 bytes in rank order).  b2n_peer_allreduce_mean then replaces `ncclAllReduce(sum) / world` on the buffer with one kernel per
+ * rank: barrier, each rank reduces 1/world of the elements over all ranks and writes the mean back into every rank's buffer, barrier — in place, capturable in
+ * a CUDA graph (epochs live in device memory).  Every rank must make the same sequence of calls.  A barrier that sees no progress for ~2 s sets the error word
+ * (b2n_peer_error) instead of hanging. */
+typedef struct b2n_peer_comm b2n_peer_comm;
+int  b2n_peer_alloc(uint64_t bytes, void **dev_ptr, void *ipc_handle_out);
+int  b2n_peer_free(void *dev_ptr);
+int  b2n_peer_comm_create(b2n_peer_comm **out, int rank, int world, void *local_ptr, const void *all_handles, uint64_t bytes);
+/* ranks as streams of ONE process: ptrs[world] are this process's own b2n_peer_alloc blocks (no IPC) */
+int  b2n_peer_comm_create_local(b2n_peer_comm **out, int rank, int world, void *const *ptrs, uint64_t bytes);
+void b2n_peer_comm_destroy(b2n_peer_comm *c);
+int  b2n_peer_allreduce_mean(b2n_peer_comm *c, uint64_t n_floats, void *stream);
+int  b2n_peer_error(b2n_peer_comm *c, int32_t *host_out, void *stream);
+
 /* ---- density-grid maintenance of the head model (csrc/occupancy.cu) ------------------------------------------------
  * NeRFRenderer.mark_untrained_grid (renderer.py:633-697), called once before training (TrainerUtil.py:475): every cell of density_grid
  * [cascade, grid_size^3] (Morton order) that none of the B camera poses (device float [B,4,4], camera-to-world) sees gets -1; other cells are left

@@ -22,9 +22,11 @@ from .model import HeadModel
 class Trainer:
     def __init__(self, model: HeadModel, lr=1e-2, lr_net=1e-3, fp16=True, max_steps=16, dt_gamma=1.0 / 256, min_near=0.05, lambda_amb=1e-4, fused_optimizer=True,
                  fused_head=False, iters=200000, unc_loss=True, amb_aud_loss=True, amb_eye_loss=True, ema_decay=None, ema_update_interval=1000, lr_schedule=True,
-                 overlap_allreduce=True):
+                 peer_allreduce=True):
         """iters: opt.iters (train.py:24) — the denominator of step_factor = min(global_step / iters, 1) that ramps the uncertainty / ambient terms
-        (TrainerUtil.py:236) and of the LambdaLR decay 0.5 ** (iter / iters) (train.py:287-288).  ema_decay: 0.95 in the reference (train.py:296)."""
+        (TrainerUtil.py:236) and of the LambdaLR decay 0.5 ** (iter / iters) (train.py:287-288).  ema_decay: 0.95 in the reference (train.py:296).
+        peer_allreduce: under torch.distributed with one process per GPU, exchange the gradients with the NVLink peer-memory kernel (csrc/peer_allreduce.cu)
+        instead of NCCL; a COLLECTIVE set-up — every rank must construct its Trainer at the same point."""
         self.m = model
         self.fused_head = fused_head
         self.fp16, self.max_steps, self.dt_gamma, self.min_near, self.lambda_amb = fp16, max_steps, dt_gamma, min_near, lambda_amb
@@ -41,9 +43,8 @@ class Trainer:
             self.opt = torch.optim.AdamW(groups, betas=(0.0, 0.99), eps=1e-8)
         self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda it: 0.5 ** (it / self.iters)) if lr_schedule else None
         ordered = [p for g in groups for p in g["params"]]
-        self.grads = FlatGradBuffer(ordered)           # same parameter order as the optimizer's flat buffers
+        self.grads = FlatGradBuffer(ordered, peer=peer_allreduce)           # same parameter order as the optimizer's flat buffers
         self.n_table_grads = sum(p.numel() for p in enc)
-        self.overlap_allreduce = overlap_allreduce
         if hasattr(self.opt, "attach_grads"):
             self.opt.attach_grads(self.grads.flat)
             if getattr(model, "_handle", None) is not None:

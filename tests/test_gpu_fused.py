@@ -417,3 +417,61 @@ def test_load_state_dict_refreshes_the_packed_model():
     got = a(x, d, enc_a, c, e)[1].clone()
     torch.cuda.synchronize()
     assert torch.equal(got, want) and not torch.equal(before, want)
+
+
+@pytest.mark.parametrize("world,n", [(2, 683509), (4, 40001)])
+def test_peer_allreduce_kernel_ranks_as_streams_of_one_process(world, n):
+    """csrc/peer_allreduce.cu on ONE GPU: `world` ranks = `world` buffers + streams of this process (b2n_peer_comm_create_local); every rank's kernel spins on
+    flags the other ranks' kernels store, all co-resident.  Result = the mean, identical bits on every rank, repeated calls (epochs), inf propagation, no timeout.
+    (The IPC / NVLink set-up between processes is covered by tests/test_gpu_multi.py on a 2-GPU box.)"""
+    import ctypes
+    from b2nerf import lib
+    from b2nerf.dist import _DevMem
+    L = lib()
+    # (every rank's CTAs must be resident at once — each rank owns a whole GPU in a real job; on one GPU four full-size launches of 148 CTAs x 101 registers
+    # would queue behind each other and trip the barrier timeout, so the 4-rank case uses a small buffer)
+    nbytes = (n * 4 + 15) // 16 * 16
+    ptrs, handles = [], []
+    for r in range(world):
+        p, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        L.call("b2n_peer_alloc", nbytes, ctypes.byref(p), h)
+        ptrs.append(p)
+    arr = (ctypes.c_void_p * world)(*[p.value for p in ptrs])
+    comms = []
+    for r in range(world):
+        c = ctypes.c_void_p()
+        L.call("b2n_peer_comm_create_local", ctypes.byref(c), r, world, arr, nbytes)
+        comms.append(c)
+    bufs = [torch.as_tensor(_DevMem(p.value, nbytes // 4), device="cuda")[:n] for p in ptrs]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    try:
+        for it in range(6):
+            xs = [torch.randn(n, device="cuda", generator=g) for _ in range(world)]
+            if it == 5:
+                xs[1][7] = float("inf")
+            want = xs[0].clone()
+            for x in xs[1:]:
+                want = want + x
+            want = want * (1.0 / world)
+            for b, x in zip(bufs, xs):
+                b.copy_(x)
+            torch.cuda.synchronize()
+            for r in range(world):
+                L.call("b2n_peer_allreduce_mean", comms[r], n, streams[r].cuda_stream)
+            torch.cuda.synchronize()
+            for b in bufs:
+                assert torch.equal(b, bufs[0])
+            if it < 5:
+                assert torch.equal(bufs[0], want), float((bufs[0] - want).abs().max())      # same summation order (rank 0, 1, ...), same scale
+            else:
+                assert bool(torch.isinf(bufs[0][7])) and bool(torch.isfinite(bufs[0][8]))
+        err = ctypes.c_int32(-1)
+        L.call("b2n_peer_error", comms[0], ctypes.byref(err), torch.cuda.current_stream().cuda_stream)
+        assert err.value == 0
+    finally:
+        del bufs
+        for c in comms:
+            L.raw("b2n_peer_comm_destroy")(c)
+        for p in ptrs:
+            L.call("b2n_peer_free", p)
