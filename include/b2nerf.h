@@ -150,6 +150,11 @@ int b2n_composite_rays_triplane(uint32_t n_alive, uint32_t n_step, float T_thres
 int b2n_grid_encode_forward(const float *inputs, const void *embeddings, const int32_t *offsets, void *outputs,
         uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, void *dy_dx,
         uint32_t gridtype, int align_corners, b2n_dtype dtype, void *stream);
+/* the same values written ROW-MAJOR, outputs [B, L*C] — the layout GridEncoder.forward returns (grid.py:52 gets it from the [L,B,C] result with a transposing
+ * copy): one thread evaluates all levels of a sample, rows leave through a shared-memory tile as contiguous lines.  No dy_dx.  D in 1..3, C in {1,2,4,8}. */
+int b2n_grid_encode_forward_rows(const float *inputs, const void *embeddings, const int32_t *offsets, void *outputs,
+        uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+        b2n_dtype dtype, void *stream);
 /* grad [L,B,C]; grad_embeddings [sO,C] pre-zeroed, accumulated with atomics; grad_inputs [B,D] or NULL */
 int b2n_grid_encode_backward(const void *grad, const float *inputs, const void *embeddings,
         const int32_t *offsets, void *grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,

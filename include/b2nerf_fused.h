@@ -295,6 +295,12 @@ void b2n_peer_comm_destroy(b2n_peer_comm *c);
 int  b2n_peer_allreduce_mean(b2n_peer_comm *c, uint64_t n_floats, void *stream);
 int  b2n_peer_error(b2n_peer_comm *c, int32_t *host_out, void *stream);
 
+/* ---- measurement probes (csrc/peaks.cu; not on the product path): the rate of random L2-resident gathers / reductions, the ceilings the grid encoder's
+ * forward / backward are reported against (profiles/kernel_rooflines.py).  table: n_floats (a power of two) device floats; every thread of `blocks` x 256
+ * issues loads_per_thread (multiple of 8) independent accesses of `vec` floats at pseudo-random aligned positions. */
+int b2n_probe_gather(const float *table, uint32_t n_floats, uint32_t vec, uint32_t loads_per_thread, uint32_t blocks, float *sink, void *stream);
+int b2n_probe_red(float *table, uint32_t n_floats, uint32_t reds_per_thread, uint32_t blocks, void *stream);
+
 /* ---- density-grid maintenance of the head model (csrc/occupancy.cu) ------------------------------------------------
  * NeRFRenderer.mark_untrained_grid (renderer.py:633-697), called once before training (TrainerUtil.py:475): every cell of density_grid
  * [cascade, grid_size^3] (Morton order) that none of the B camera poses (device float [B,4,4], camera-to-world) sees gets -1; other cells are left

@@ -38,7 +38,7 @@ __device__ __forceinline__ float alpha_of(float sigma, float delta) { return __f
 
 // CTA-wide: decide whether the valid segments of this CTA's rows tile [lo, lo+total) in row order.
 // Returns true (uniformly) if so and total <= CT_CAP; fills lo/total.
-__device__ __forceinline__ bool cta_tiling(bool valid, uint32_t off, uint32_t num, uint32_t &lo, uint32_t &total) {
+__device__ __forceinline__ bool cta_tiling(bool valid, uint32_t off, uint32_t num, uint32_t &lo, uint32_t &total, uint32_t &slot) {
     __shared__ uint32_t s_w[CT_THREADS / 32];
     __shared__ uint32_t s_lo;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -55,7 +55,7 @@ __device__ __forceinline__ bool cta_tiling(bool valid, uint32_t off, uint32_t nu
     // the first valid row defines lo (it is the one with before == 0 and cnt > 0)
     if (valid && before == 0) s_lo = off;        // several rows may have before==0 only if earlier ones have cnt==0 → invalid
     __syncthreads();
-    lo = s_lo; total = tot;
+    lo = s_lo; total = tot; slot = before;
     const bool ok = !valid || (off == lo + before);
     return __syncthreads_and(ok) && tot <= CT_CAP && tot > 0;
 }
@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_fwd(
     const bool valid = (n < N) && !(num == 0 || off + num > M);
     __shared__ __align__(8) uint64_t s_bar;
     if (threadIdx.x == 0) { tc5::mbar_init(&s_bar, 1); tc5::fence_mbar_init(); }
-    uint32_t lo, total;
-    const bool staged = cta_tiling(valid, off, num, lo, total);       // (its barriers also publish the mbarrier init)
+    uint32_t lo, total, slot;
+    const bool staged = cta_tiling(valid, off, num, lo, total, slot);       // (its barriers also publish the mbarrier init)
     float ws = 0, a0 = 0, a1 = 0, u = 0, d = 0, r = 0, g = 0, b = 0;
     if (staged) {
         float *b_sg = sm, *b_dl = b_sg + CT_CAP + CT_PAD, *b_rgb = b_dl + 2 * CT_CAP + CT_PAD, *b_a0 = b_rgb + 3 * CT_CAP + CT_PAD;
@@ -161,6 +161,31 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_fwd(
             const uint32_t o = off - lo;
             train_fwd_ray<AMB, NA, UNC>(p_sg.s + o, p_rgb.s + 3 * o, p_a0.s + o, p_a1.s + o, p_u.s + o, p_dl.s + 2 * o, num, T_thresh, ws, a0, a1, u, d, r, g, b);
         }
+    } else if (total > 0 && total <= (uint32_t)CT_CAP) {
+        // Foreign row order (the reference's atomic allocation, raymarching.cu:446-454: consecutive rows own unrelated segments).  A thread walking its ray
+        // straight out of global memory touches one sector per sample and array; instead every warp copies the segments of its 32 rays into the staging
+        // arrays one ray at a time — a segment is contiguous, so a copy is one or two coalesced loads per array — at the slots an exclusive scan of the
+        // counts assigns, and the rays are then walked out of shared memory like in the tiled case.
+        float *b_sg = sm, *b_dl = b_sg + CT_CAP + CT_PAD, *b_rgb = b_dl + 2 * CT_CAP + CT_PAD, *b_a0 = b_rgb + 3 * CT_CAP + CT_PAD;
+        float *b_a1 = b_a0 + (NA >= 1 ? CT_CAP + CT_PAD : 0), *b_u = b_a1 + (NA >= 2 ? CT_CAP + CT_PAD : 0);
+        const uint32_t lane = threadIdx.x & 31u;
+        const uint32_t cnt = valid ? num : 0u;
+#pragma unroll 1
+        for (uint32_t j = 0; j < 32; j++) {
+            const uint32_t nj = __shfl_sync(0xffffffffu, cnt, j);
+            if (nj == 0) continue;
+            const uint32_t oj = __shfl_sync(0xffffffffu, off, j), sj = __shfl_sync(0xffffffffu, slot, j);
+            for (uint32_t e = lane; e < nj; e += 32) {
+                b_sg[sj + e] = __ldcs(sigmas + oj + e);
+                if (NA >= 1) b_a0[sj + e] = __ldcs(amb0 + oj + e);
+                if (NA >= 2) b_a1[sj + e] = __ldcs(amb1 + oj + e);
+                if (UNC) b_u[sj + e] = __ldcs(unc + oj + e);
+            }
+            for (uint32_t e = lane; e < 2 * nj; e += 32) b_dl[2 * sj + e] = __ldcs(deltas + 2 * (size_t)oj + e);
+            for (uint32_t e = lane; e < 3 * nj; e += 32) b_rgb[3 * sj + e] = __ldcs(rgbs + 3 * (size_t)oj + e);
+        }
+        __syncwarp();                          // a warp only reads what it staged itself
+        if (valid) train_fwd_ray<AMB, NA, UNC>(b_sg + slot, b_rgb + 3 * slot, b_a0 + slot, b_a1 + slot, b_u + slot, b_dl + 2 * slot, num, T_thresh, ws, a0, a1, u, d, r, g, b);
     } else if (valid) {
         train_fwd_ray<AMB, NA, UNC>(sigmas + off, rgbs + 3 * (size_t)off, NA >= 1 ? amb0 + off : nullptr, NA >= 2 ? amb1 + off : nullptr,
                                     UNC ? unc + off : nullptr, deltas + 2 * (size_t)off, num, T_thresh, ws, a0, a1, u, d, r, g, b);
@@ -240,8 +265,8 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_bwd(
     const bool valid = (n < N) && !(num == 0 || off + num > M);
     __shared__ __align__(8) uint64_t s_bar;
     if (threadIdx.x == 0) { tc5::mbar_init(&s_bar, 1); tc5::fence_mbar_init(); }
-    uint32_t lo, total;
-    const bool staged = cta_tiling(valid, off, num, lo, total);
+    uint32_t lo, total, slot;
+    const bool staged = cta_tiling(valid, off, num, lo, total, slot);
     RayGrads q = {};
     if (valid) {
         q.gws = g_ws[idx];

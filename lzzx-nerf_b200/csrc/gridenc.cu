@@ -66,36 +66,11 @@ __device__ __forceinline__ LevelGeom level_geom(const int32_t *__restrict__ offs
     return g;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// forward — one thread per (sample, level); outputs [L,B,C]
-// ---------------------------------------------------------------------------------------------------
+// One level of one sample: cell, fractional position and the interpolated C features (gridencoder.cu:124-175); shared by the level-major kernel of the
+// reference layout and the row-major kernel below.
 template <typename T, uint32_t D, uint32_t C>
-__global__ void __launch_bounds__(256) k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ table, const int32_t *__restrict__ offsets,
-                                                   T *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, T *__restrict__ dy_dx,
-                                                   uint32_t gridtype, bool align_corners) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const uint32_t level = blockIdx.y;
-    const LevelGeom g = level_geom(offsets, level, S, H);
-    const T *tab = table + (size_t)g.table_off * C;
-    T *out = outputs + ((size_t)level * B + b) * C;
-
-    float in[D];
-    bool oob = false;
-#pragma unroll
-    for (uint32_t d = 0; d < D; d++) { in[d] = __ldcs(inputs + (size_t)b * D + d); oob |= (in[d] < 0.0f || in[d] > 1.0f); }
-    if (oob) {                                                                   // gridencoder.cu:98-122
-#pragma unroll
-        for (uint32_t c = 0; c < C; c++) out[c] = from_f<T>(0.0f);
-        if (dy_dx) {
-            T *dd = dy_dx + (size_t)b * D * L * C + (size_t)level * D * C;
-#pragma unroll
-            for (uint32_t k = 0; k < D * C; k++) dd[k] = from_f<T>(0.0f);
-        }
-        return;
-    }
-    float pos[D];
-    uint32_t pg[D];
+__device__ __forceinline__ void grid_level_eval(const float (&in)[D], const LevelGeom &g, const T *__restrict__ tab, uint32_t gridtype, bool align_corners,
+                                                float (&res)[C], float (&pos)[D], uint32_t (&pg)[D]) {
 #pragma unroll
     for (uint32_t d = 0; d < D; d++) {
         pos[d] = __fmaf_rn(in[d], g.scale, align_corners ? 0.0f : 0.5f);
@@ -103,7 +78,6 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const float *__restrict__ inpu
         pg[d] = (uint32_t)fl;
         pos[d] = __fsub_rn(pos[d], (float)pg[d]);
     }
-    float res[C];
 #pragma unroll
     for (uint32_t c = 0; c < C; c++) res[c] = 0.0f;
 
@@ -147,6 +121,39 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const float *__restrict__ inpu
             for (uint32_t c = 0; c < C; c++) acc_corner<T>(res[c], w, to_f<T>(__ldg(tab + e + c)));
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward — one thread per (sample, level); outputs [L,B,C]
+// ---------------------------------------------------------------------------------------------------
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256) k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ table, const int32_t *__restrict__ offsets,
+                                                   T *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, T *__restrict__ dy_dx,
+                                                   uint32_t gridtype, bool align_corners) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    const LevelGeom g = level_geom(offsets, level, S, H);
+    const T *tab = table + (size_t)g.table_off * C;
+    T *out = outputs + ((size_t)level * B + b) * C;
+
+    float in[D];
+    bool oob = false;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) { in[d] = __ldcs(inputs + (size_t)b * D + d); oob |= (in[d] < 0.0f || in[d] > 1.0f); }
+    if (oob) {                                                                   // gridencoder.cu:98-122
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) out[c] = from_f<T>(0.0f);
+        if (dy_dx) {
+            T *dd = dy_dx + (size_t)b * D * L * C + (size_t)level * D * C;
+#pragma unroll
+            for (uint32_t k = 0; k < D * C; k++) dd[k] = from_f<T>(0.0f);
+        }
+        return;
+    }
+    float pos[D], res[C];
+    uint32_t pg[D];
+    grid_level_eval<T, D, C>(in, g, tab, gridtype, align_corners, res, pos, pg);
 #pragma unroll
     for (uint32_t c = 0; c < C; c++) out[c] = from_f<T>(res[c]);
 
@@ -181,6 +188,49 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const float *__restrict__ inpu
 #pragma unroll
         for (uint32_t c = 0; c < C; c++) dd[gd * C + c] = from_f<T>(rg[c]);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward, row-major output [B, L*C] — what GridEncoder.forward hands to its caller (grid.py:52 permutes the reference's [L,B,C] with a transposing copy of the
+// whole output).  One thread evaluates ALL levels of its sample (the tables of the head / torso models sit in L1/L2, so the reference's level-major launch that
+// keeps one level's table hot buys nothing on a 126 MB L2); the CTA's 128 rows are staged in shared memory and leave as one contiguous, fully coalesced block.
+// Same per-level arithmetic (grid_level_eval) => same bits as the level-major kernel.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t GR_THREADS = 128;
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(GR_THREADS) k_grid_fwd_rows(const float *__restrict__ inputs, const T *__restrict__ table, const int32_t *__restrict__ offsets,
+                                                               T *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners) {
+    extern __shared__ __align__(16) uint8_t gr_smem[];
+    LevelGeom *s_lvl = reinterpret_cast<LevelGeom *>(gr_smem);
+    T *s_out = reinterpret_cast<T *>(gr_smem + sizeof(LevelGeom) * ((L + 3) & ~3u));
+    const uint32_t LC = L * C, pitch = LC | 1u;                      // odd pitch: conflict-free column writes
+    for (uint32_t l = threadIdx.x; l < L; l += GR_THREADS) s_lvl[l] = level_geom(offsets, l, S, H);
+    __syncthreads();
+    const uint32_t b = blockIdx.x * GR_THREADS + threadIdx.x;
+    if (b < B) {
+        float in[D];
+        bool oob = false;
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) { in[d] = __ldcs(inputs + (size_t)b * D + d); oob |= (in[d] < 0.0f || in[d] > 1.0f); }
+        T *row = s_out + threadIdx.x * pitch;
+        if (oob) {                                                   // gridencoder.cu:98-122
+            for (uint32_t k = 0; k < LC; k++) row[k] = from_f<T>(0.0f);
+        } else {
+#pragma unroll 2
+            for (uint32_t l = 0; l < L; l++) {
+                const LevelGeom g = s_lvl[l];
+                float pos[D], res[C];
+                uint32_t pg[D];
+                grid_level_eval<T, D, C>(in, g, table + (size_t)g.table_off * C, gridtype, align_corners, res, pos, pg);
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++) row[l * C + c] = from_f<T>(res[c]);
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t rows_here = min(GR_THREADS, B - blockIdx.x * GR_THREADS), total = rows_here * LC;
+    T *dst = outputs + (size_t)blockIdx.x * GR_THREADS * LC;
+    for (uint32_t e = threadIdx.x; e < total; e += GR_THREADS) { const uint32_t r = e / LC; dst[e] = s_out[r * pitch + (e - r * LC)]; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -639,6 +689,19 @@ static int fwd_dispatch(const float *inputs, const T *table, const int32_t *offs
         default: set_error("GridEncoding: D must be 1, 2, 3, 4, or 5"); return 2;
     }
 }
+template <typename T>
+static int fwd_rows_dispatch(const float *inputs, const T *table, const int32_t *offsets, T *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                             uint32_t gridtype, bool ac, cudaStream_t st) {
+    const size_t smem = sizeof(LevelGeom) * ((L + 3) & ~3u) + sizeof(T) * GR_THREADS * ((size_t)(L * C) | 1u);
+    if (smem > 48 * 1024) { set_error("grid_encode_forward_rows: L * C = %u too wide for the staged kernel", L * C); return 2; }
+    const uint32_t grid = ceil_div<uint32_t>(B, GR_THREADS);
+#define B2N_ROWS(DD, CC) if (D == DD && C == CC) { k_grid_fwd_rows<T, DD, CC><<<grid, GR_THREADS, smem, st>>>(inputs, table, offsets, outputs, B, L, S, H, gridtype, ac); return check_launch("grid_encode_forward_rows"); }
+    B2N_ROWS(2, 1) B2N_ROWS(2, 2) B2N_ROWS(2, 4) B2N_ROWS(2, 8) B2N_ROWS(3, 1) B2N_ROWS(3, 2) B2N_ROWS(3, 4) B2N_ROWS(3, 8) B2N_ROWS(1, 1) B2N_ROWS(1, 2) B2N_ROWS(1, 4) B2N_ROWS(1, 8)
+#undef B2N_ROWS
+    set_error("grid_encode_forward_rows: D = %u, C = %u not instantiated (D 1..3, C 1, 2, 4, 8)", D, C);
+    return 2;
+}
+
 template <typename T, uint32_t D>
 static int bwd_dispatch_c(const T *grad, const float *inputs, const int32_t *offsets, T *gtab, uint32_t B, uint32_t C, uint32_t L, float S, uint32_t H,
                           uint32_t gridtype, bool ac, cudaStream_t st) {
@@ -699,6 +762,22 @@ int b2n_grid_encode_forward(const float *inputs, const void *embeddings, const i
     if (dtype == B2N_F16)
         return fwd_dispatch<__half>(inputs, (const __half *)embeddings, offsets, (__half *)outputs, B, D, C, L, S, H, (__half *)dy_dx, gridtype, align_corners != 0, as_stream(stream));
     set_error("grid_encode_forward: embeddings must be float32 or float16");
+    return 2;
+}
+
+// GridEncoder.forward's own layout: outputs [B, L*C] row-major, no input derivative (dy_dx) — same values as b2n_grid_encode_forward followed by the reference's
+// permute(1, 0, 2).reshape(B, L*C) (grid.py:52), bit for bit.  D 1..3, C in {1, 2, 4, 8}, L * C small enough for one staged tile (<= ~90 fp32 features).
+int b2n_grid_encode_forward_rows(const float *inputs, const void *embeddings, const int32_t *offsets, void *outputs, uint32_t B, uint32_t D, uint32_t C,
+                                 uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners, b2n_dtype dtype, void *stream) {
+    B2N_REQUIRE(inputs && embeddings && offsets && outputs, "grid_encode_forward_rows: null pointer");
+    B2N_REQUIRE(gridtype <= 1, "grid_encode_forward_rows: gridtype must be 0 (hash) or 1 (tiled)");
+    B2N_REQUIRE(L >= 1 && L <= 1024, "grid_encode_forward_rows: L=%u out of range", L);
+    if (B == 0) return 0;
+    if (dtype == B2N_F32)
+        return fwd_rows_dispatch<float>(inputs, (const float *)embeddings, offsets, (float *)outputs, B, D, C, L, S, H, gridtype, align_corners != 0, as_stream(stream));
+    if (dtype == B2N_F16)
+        return fwd_rows_dispatch<__half>(inputs, (const __half *)embeddings, offsets, (__half *)outputs, B, D, C, L, S, H, gridtype, align_corners != 0, as_stream(stream));
+    set_error("grid_encode_forward_rows: embeddings must be float32 or float16");
     return 2;
 }
 

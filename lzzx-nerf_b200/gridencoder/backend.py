@@ -19,6 +19,16 @@ def grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, 
          dev_ptr(dy_dx, "dy_dx", _flt, optional=True), gridtype, int(bool(align_corners)), code, stream_ptr(inputs))
 
 
+def grid_encode_forward_rows(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, gridtype, align_corners):
+    """Not part of the reference's pybind surface: the forward written straight in GridEncoder.forward's [B, L*C] layout (no permute copy)."""
+    code = float_code(embeddings, "embeddings")
+    if outputs.dtype != embeddings.dtype:
+        raise B2NError("outputs must have the dtype of embeddings")
+    call("b2n_grid_encode_forward_rows", dev_ptr(inputs, "inputs", torch.float32), dev_ptr(embeddings, "embeddings", _flt),
+         dev_ptr(offsets, "offsets", torch.int32), dev_ptr(outputs, "outputs", _flt), B, D, C, L, float(S), H, gridtype, int(bool(align_corners)), code,
+         stream_ptr(inputs))
+
+
 def grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H, dy_dx, grad_inputs, gridtype, align_corners):
     code = float_code(grad, "grad")
     if grad_embeddings.dtype != grad.dtype:
@@ -38,4 +48,5 @@ def grid_level_scales(S, H, L, device="cuda"):
 
 
 _backend = types.SimpleNamespace(grid_encode_forward=grid_encode_forward, grid_encode_backward=grid_encode_backward)
+_rows_ok = lambda D, C, L: D <= 3 and C in (1, 2, 4, 8) and L * C <= 80
 __all__ = ["_backend"]

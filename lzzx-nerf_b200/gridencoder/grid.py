@@ -13,7 +13,7 @@ import torch.nn as nn
 from torch.autograd import Function
 from torch.amp import custom_bwd, custom_fwd
 
-from .backend import _backend
+from .backend import _backend, _rows_ok, grid_encode_forward_rows
 
 _gridtype_to_id = {"hash": 0, "tiled": 1}
 
@@ -42,11 +42,17 @@ class _grid_encode(Function):
         S, H = np.log2(per_level_scale), base_resolution
         if torch.is_autocast_enabled("cuda") and C % 2 == 0:
             embeddings = embeddings.to(torch.half)
+        ctx.geom = (B, D, C, L, S, H, gridtype, align_corners)
+        if not calc_grad_inputs and _rows_ok(D, C, L):
+            # the result in the caller's [B, L*C] layout straight from the kernel: the reference's [L,B,C] output + transposing copy (grid.py:42,52) in one pass
+            out = torch.empty(B, L * C, device=inputs.device, dtype=embeddings.dtype)
+            grid_encode_forward_rows(inputs, embeddings.contiguous(), offsets, out, B, D, C, L, S, H, gridtype, align_corners)
+            ctx.save_for_backward(inputs, embeddings, offsets, None)
+            return out
         level_major = torch.empty(L, B, C, device=inputs.device, dtype=embeddings.dtype)
         dy_dx = torch.empty(B, L * D * C, device=inputs.device, dtype=embeddings.dtype) if calc_grad_inputs else None
         _backend.grid_encode_forward(inputs, embeddings.contiguous(), offsets, level_major, B, D, C, L, S, H, dy_dx, gridtype, align_corners)
         ctx.save_for_backward(inputs, embeddings, offsets, dy_dx)
-        ctx.geom = (B, D, C, L, S, H, gridtype, align_corners)
         return level_major.permute(1, 0, 2).reshape(B, L * C)
 
     @staticmethod

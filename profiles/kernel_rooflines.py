@@ -68,10 +68,20 @@ def measure():
     gs, ga0, ga1, gu = (torch.zeros(M, device=dev) for _ in range(4)); grgb = torch.zeros(M, 3, device=dev)
     f = lambda: rb.composite_rays_train_triplane_backward(g_ws, g_a0, g_a1, g_u, g_img, sig, rgb, aud, eye, unc, dl, rays, ws, a0, a1, us, img, M, N, 1e-4, gs, grgb, ga0, ga1, gu)
     report("composite_rays_train_triplane_backward", (36 + 28) * M + (12 + 32 + 28) * N, timeit(f), "same rays")
+    # foreign row orders.  The reference allocates segments with an atomicAdd per ray (raymarching.cu:446-454), so its rows come out in the order in which warps
+    # reach the atomic: scrambled within a neighbourhood of a few thousand rays, not over the whole batch — "window 4096" models that; the global permutation
+    # is the adversarial case (every segment read and every per-ray output write is a random DRAM access: not an HBM-streaming workload any more)
+    win = (torch.arange(N, device=dev) // 4096) * 4096
+    local = (win.float() + torch.rand(N, device=dev) * 4096).argsort()
+    rays_loc = rays[local].contiguous()
+    f = lambda: rb.composite_rays_train_triplane_forward(sig, rgb, aud, eye, unc, dl, rays_loc, M, N, 1e-4, ws, a0, a1, us, dep, img)
+    report("composite_rays_train_triplane_forward[rows scrambled within windows of 4096: the reference's atomic order]", 36 * M + 44 * N, timeit(f),
+           "per-warp gathered staging (segments copied ray by ray into shared memory)")
     perm = torch.randperm(N, device=dev)
     rays_sh = rays[perm].contiguous()
     f = lambda: rb.composite_rays_train_triplane_forward(sig, rgb, aud, eye, unc, dl, rays_sh, M, N, 1e-4, ws, a0, a1, us, dep, img)
-    report("composite_rays_train_triplane_forward[shuffled rows: direct path]", 36 * M + 44 * N, timeit(f), "rows permuted like the reference's atomic allocation")
+    report("composite_rays_train_triplane_forward[rows globally permuted: adversarial]", 36 * M + 44 * N, timeit(f), "random DRAM accesses per segment and per output row")
+    del rays_loc, local, win
     del gs, ga0, ga1, gu, grgb
     # inference composite: 8 M alive rays x 4 steps
     na, ns = 8 * 1024 * 1024, 4
@@ -122,8 +132,25 @@ def measure():
     tot = int(counter[0])
     report("march_rays_train (count + write)", 52 * Nm + 32 * tot, sec, f"N={Nm} rays -> {tot} samples; includes the two DDA passes; {Nm / sec / 1e6:.1f} M rays/s")
 
+    # ---- ceilings for the grid encoder: random L2-resident gathers / reductions (csrc/peaks.cu), table = one tri-plane table rounded up to a power of two ------
+    from b2nerf import lib
+    L_ = lib()
+    st = torch.cuda.current_stream().cuda_stream
+    ntab = 262144                                          # 1 MB of floats (the 163 584-entry table is 654 KB): L2-resident, 4x an SM's L1
+    probe_tab, sink = torch.rand(ntab, device=dev), torch.zeros(4, device=dev)
+    blocks, per_thread = 148 * 8, 512
+    n_acc = blocks * 256 * per_thread
+    peaks_l2 = {}
+    for vec in (1, 2, 4):
+        sec = timeit(lambda: L_.call("b2n_probe_gather", probe_tab.data_ptr(), ntab, vec, per_thread, blocks, sink.data_ptr(), st))
+        peaks_l2[f"gather_{4 * vec}B_per_s"] = n_acc / sec
+    sec = timeit(lambda: L_.call("b2n_probe_red", probe_tab.data_ptr(), ntab, per_thread, blocks, st))
+    peaks_l2["red_f32_per_s"] = n_acc / sec
+    peaks_l2["how"] = f"{blocks} x 256 threads x {per_thread} independent accesses at pseudo-random positions of a {ntab * 4 // 1024} KB table (csrc/peaks.cu), CUDA events"
+
     # ---- grid encode (API kernels), tri-plane config, 8 M points per plane --------------------------------------------------------------------
     from gridencoder import GridEncoder  # noqa: E402
+    from gridencoder.backend import grid_encode_forward_rows  # noqa: E402
     enc = GridEncoder(input_dim=2, num_levels=12, level_dim=1, base_resolution=64, log2_hashmap_size=14, desired_resolution=512).to(dev)
     enc.embeddings.data.uniform_(-1, 1)
     B = 8 * 1024 * 1024
@@ -131,13 +158,30 @@ def measure():
     S = float(np.log2(enc.per_level_scale))
     f = lambda: gb.grid_encode_forward(x, enc.embeddings.data, enc.offsets, out, B, 2, 1, 12, S, 64, None, 0, False)
     sec = timeit(f)
-    report("grid_encode_forward (one plane, D=2 L=12 C=1 fp32)", (8 + 48) * B, sec, f"B={B}; HBM bytes 8 in + 48 out per point; L2 gather {192 * B / sec / 1e9:.0f} GB/s (192 B/point); random points")
+    # corner reads per point: 12 levels x 2 rows x (one 8-byte pair when the x-neighbours are adjacent, else two 4-byte reads) -> >= 24 gathers
+    report("grid_encode_forward (one plane, D=2 L=12 C=1 fp32, reference layout [L,B,C])", (8 + 48) * B, sec,
+           f"B={B} random points; {24 * B / sec / 1e9:.1f} G paired corner gathers/s = {24 * B / sec / peaks_l2['gather_8B_per_s']:.2f} of the measured random 8-byte gather rate "
+           f"({peaks_l2['gather_8B_per_s'] / 1e9:.1f} G/s); the caller still pays grid.py:52's transposing copy")
+    rows[-1]["frac_of_l2_gather_peak"] = 24 * B / sec / peaks_l2["gather_8B_per_s"]
+    out_rows = torch.empty(B, 12, device=dev)
+    f = lambda: grid_encode_forward_rows(x, enc.embeddings.data, enc.offsets, out_rows, B, 2, 1, 12, S, 64, 0, False)
+    sec_r = timeit(f)
+    perm = timeit(lambda: out.permute(1, 0, 2).reshape(B, 12))
+    report("grid_encode_forward_rows (same, row-major [B, L*C]: what GridEncoder.forward returns)", (8 + 48) * B, sec_r,
+           f"{24 * B / sec_r / 1e9:.1f} G paired corner gathers/s = {24 * B / sec_r / peaks_l2['gather_8B_per_s']:.2f} of the gather ceiling; replaces the level-major kernel "
+           f"({sec * 1e6:.0f} us) + the transposing copy ({perm * 1e6:.0f} us)")
+    rows[-1]["frac_of_l2_gather_peak"] = 24 * B / sec_r / peaks_l2["gather_8B_per_s"]
+    assert torch.equal(out_rows, out.permute(1, 0, 2).reshape(B, 12))
+    del out_rows
     grad = torch.randn(12, B, 1, device=dev); ge = torch.zeros_like(enc.embeddings.data)
     f = lambda: gb.grid_encode_backward(grad, x, enc.embeddings.data, enc.offsets, ge, B, 2, 1, 12, S, 64, None, None, 0, False)
     sec = timeit(f)
-    report("grid_encode_backward (one plane)", (8 + 48) * B, sec, f"B={B}; {48 * B / sec / 1e9:.1f} G table reductions/s (48 per point, pairs issued as red.v2.f32)")
+    report("grid_encode_backward (one plane)", (8 + 48) * B, sec,
+           f"B={B}; {48 * B / sec / 1e9:.1f} G table reductions/s (48 per point; privatised in shared memory, flushed with red.v4) vs {peaks_l2['red_f32_per_s'] / 1e9:.1f} G/s "
+           f"of direct random red.f32 into an L2-resident table = {48 * B / sec / peaks_l2['red_f32_per_s']:.2f}x")
+    rows[-1]["vs_l2_red_peak"] = 48 * B / sec / peaks_l2["red_f32_per_s"]
 
-    return {"hbm_peak_gbs": HBM, "peak_source": SRC, "kernels": rows}
+    return {"hbm_peak_gbs": HBM, "peak_source": SRC, "l2_peaks": peaks_l2, "kernels": rows}
 
 
 if __name__ == "__main__":
