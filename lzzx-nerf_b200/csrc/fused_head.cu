@@ -28,7 +28,8 @@ using namespace tc5;
 // ---------------------------------------------------------------------------------------------------
 // weight packing: fp32 nn.Linear weights [out,in] -> fp16 SWIZZLE_128B K-major image (+ small fp32 vectors)
 // ---------------------------------------------------------------------------------------------------
-struct PackRegion { const float *src; uint32_t byte_off, rows, src_rows, ld, col0, kvalid, row_shift, tr, k0; };
+struct PackRegion { const float *src; uint32_t byte_off, rows, src_rows, ld, col0, kvalid, row_shift, tr, k0, col1, k1_off, k1_valid; };
+// (col1, k1_off, k1_valid): a second run of source columns placed at K positions [k1_off, k1_off + k1_valid) of the same rows (untransposed regions)
 // tr = 1: transposed region, value(row n, k) = src[(k0 + k) * ld + col0 + n] for n < src_rows, k < kvalid
 struct PackArgs { PackRegion r[12]; uint32_t n; };
 
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) k_pack_head(const __grid_constant__ PackA
                 const uint32_t kk = c * 8u + k;
                 float v = 0.0f;
                 if (g.src && row < g.src_rows && kk < g.kvalid) v = g.tr ? g.src[(size_t)(g.k0 + kk) * g.ld + g.col0 + row] : g.src[(size_t)srow * g.ld + g.col0 + kk];
+                else if (g.src && !g.tr && row < g.src_rows && kk >= g.k1_off && kk < g.k1_off + g.k1_valid) v = g.src[(size_t)srow * g.ld + g.col1 + (kk - g.k1_off)];
                 h[k] = __float2half_rn(v);
             }
             *reinterpret_cast<uint4 *>(img + g.byte_off + sw128_offset(row, c)) = *reinterpret_cast<uint4 *>(h);
@@ -228,8 +230,9 @@ __device__ __forceinline__ void issue_mma(uint32_t d_tmem, uint32_t a_saddr, uin
 // ---------------------------------------------------------------------------------------------------
 struct HeadSmem {                       // lives after the 1024-aligned weight image and operand tiles
     HeadLvl lvl[12];
-    float enc_a_h[32];                  // fp16-rounded audio code
-    float eye_w1[16], unc_w1[32], ind_bias[64];
+    __half2 enc_a_h2[16];               // the audio code in fp16, packed in pairs
+    float eye_w1[16], unc_w1[32];
+    uint32_t ind_p[2];                  // fp16-rounded individual code, packed (zeros without a code)
     float ind_h[4];                     // fp16-rounded individual code (training: part of the saved color_net input)
     float eye_val;
     uint32_t n_valid;
@@ -267,15 +270,12 @@ __global__ void __maxnreg__(SAVE ? 168 : 128) k_head_forward(const __grid_consta
         S.eye_val = a.eye ? a.eye[0] : 0.0f;
     }
     if (warp == 1) tmem_alloc(&S.tmem_base, 512);
-    if (tid >= 128 && tid < 160) S.enc_a_h[tid - 128] = round_h(a.enc_a[tid - 128]);
+    if (tid >= 128 && tid < 144) S.enc_a_h2[tid - 128] = __floats2half2_rn(a.enc_a[2 * (tid - 128)], a.enc_a[2 * (tid - 128) + 1]);
     if (tid >= 160 && tid < 176) S.eye_w1[tid - 160] = a.wsmall[HS_EYE_W1 + tid - 160];
     if (tid >= 192 && tid < 224) S.unc_w1[tid - 192] = a.wsmall[HS_UNC_W1 + tid - 192];
-    if (tid >= 256 && tid < 320) {      // ind-code part of color_net layer 0 folded into a bias (network.py:270)
-        const uint32_t j = tid - 256;
-        float b = 0.0f;
-        if (a.ind_code)
-            for (int q = 0; q < 4; q++) b = fmaf(a.wsmall[HS_IND_W + j * 4 + q], round_h(a.ind_code[q]), b);
-        S.ind_bias[j] = b;
+    if (tid == 256) {                   // individual code -> two packed half2 words (K columns 16..19 of P6's second operand)
+        S.ind_p[0] = a.ind_code ? pack2(a.ind_code[0], a.ind_code[1]) : 0u;
+        S.ind_p[1] = a.ind_code ? pack2(a.ind_code[2], a.ind_code[3]) : 0u;
     }
     if (tid >= 320 && tid < 332) S.lvl[tid - 320] = a.lvl[tid - 320];
     if (tid >= 332 && tid < 336) S.ind_h[tid - 332] = a.ind_code ? round_h(a.ind_code[tid - 332]) : 0.0f;
@@ -390,12 +390,14 @@ __global__ void __maxnreg__(SAVE ? 168 : 128) k_head_forward(const __grid_consta
             uint32_t e16[16];
             ld16(tmem_ld + TC_EYE, e16); wait_ld();
             float dot = 0.0f;
+            uint32_t w[8];
 #pragma unroll
-            for (int j = 0; j < 16; j++) dot = fmaf(fmaxf(round_h(__uint_as_float(e16[j])), 0.0f), S.eye_w1[j], dot);
+            for (int j = 0; j < 8; j++) {      // relu(round_h(x)) of a pair in one cvt.rn.relu.f16x2, widened back for the fp32 dot product
+                w[j] = pack2_relu(__uint_as_float(e16[2 * j]), __uint_as_float(e16[2 * j + 1]));
+                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[j]));
+                dot = fmaf(f.x, S.eye_w1[2 * j], dot); dot = fmaf(f.y, S.eye_w1[2 * j + 1], dot);
+            }
             if (sv_on) {
-                uint32_t w[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) w[j] = pack2_relu(__uint_as_float(e16[2 * j]), __uint_as_float(e16[2 * j + 1]));
                 *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 6)) = make_uint4(w[0], w[1], w[2], w[3]);      // chunks 6, 7 of the feature tile are not operands (K = 48)
                 *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 7)) = make_uint4(w[4], w[5], w[6], w[7]);
             }
@@ -436,9 +438,14 @@ __global__ void __maxnreg__(SAVE ? 168 : 128) k_head_forward(const __grid_consta
             uint32_t w[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) {
-                const float a0 = round_h(__uint_as_float(acc[2 * j])), a1 = round_h(__uint_as_float(acc[2 * j + 1]));
-                n2 = fmaf(a0, a0, n2); n2 = fmaf(a1, a1, n2);
-                w[j] = pack2(S.enc_a_h[2 * j] * a0, S.enc_a_h[2 * j + 1] * a1);    // enc_w = enc_a * att, fp16 (network.py:285)
+                const uint32_t ah = pack2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));      // att pair in fp16 (the Linear's output dtype)
+                const __half2 a2 = *reinterpret_cast<const __half2 *>(&ah);
+                const float2 f = __half22float2(a2);
+                n2 = fmaf(f.x, f.x, n2); n2 = fmaf(f.y, f.y, n2);
+                // enc_w = enc_a * att on half tensors (network.py:285): the product of two halves is exact in fp32, so one HMUL2 rounds exactly like
+                // multiplying in fp32 and converting
+                const __half2 p = __hmul2(a2, S.enc_a_h2[j]);
+                w[j] = *reinterpret_cast<const uint32_t *>(&p);
             }
             amb_aud = sqrtf(n2);                                                    // .norm(dim=-1) in fp32 (network.py:308)
             // EW operand into X (the features are consumed): chunks 0..3 = enc_w, chunk 4 = [e, 0..], chunk 5 = 0   (K = 33 padded to 48)
@@ -494,6 +501,10 @@ __global__ void __maxnreg__(SAVE ? 168 : 128) k_head_forward(const __grid_consta
             for (int j = 0; j < 8; j++) w[j] = pack2(shv[2 * j], shv[2 * j + 1]);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+            // the individual code as K columns 16..19 of the same operand (c.repeat(N, 1) concatenated behind the SH terms, network.py:270): its part of the
+            // layer rides on the tensor core as a second K step instead of a 64-term bias add in the epilogue
+            *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 2)) = make_uint4(S.ind_p[0], S.ind_p[1], 0u, 0u);
+            *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 3)) = make_uint4(0u, 0u, 0u, 0u);
             if (SAVE) warp_chunks_out<2>(sX, 0, wrow0, reinterpret_cast<uint8_t *>(a.sv.c_in) + tile_row0 * 176, 176, rows_valid);
             if (sv_on) c_in_q[10] = make_uint4(pack2(S.ind_h[0], S.ind_h[1]), pack2(S.ind_h[2], S.ind_h[3]), 0u, 0u);
         }
@@ -502,12 +513,12 @@ __global__ void __maxnreg__(SAVE ? 168 : 128) k_head_forward(const __grid_consta
         if (t == 0) {
             fence_after_sync();
             issue_mma(tmem_wg + TC_S, sH_a, sW_a + HW_F0, 4, 64, false);
-            issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_F1, 1, 64, true);
+            issue_mma(tmem_wg + TC_S, sX_a, sW_a + HW_F1, 2, 64, true);
             mma_commit(bar);
         }
         if (has_next) { gather_finish(G, cn.ok, rown, r7, 4); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[10], cn); }      // trip 4 lands (issued a phase ago), trip 5 leaves
         mma_done();
-        hidden_epilogue<true, true>(tmem_ld + TC_S, sH, t, S.ind_bias);
+        hidden_epilogue<true, false>(tmem_ld + TC_S, sH, t, nullptr);
         if (SAVE) warp_rows_out(sH, wrow0, reinterpret_cast<uint8_t *>(a.sv.hc) + tile_row0 * 128, 128, rows_valid);
         publish();
         // ---- P7: color layer 1 (N padded 3 -> 16) -----------------------------------------------------------------------------
@@ -683,7 +694,7 @@ int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
     PackArgs pa = {};
     uint32_t n = 0;
     auto add = [&](const float *src, uint32_t off, uint32_t rows, uint32_t src_rows, uint32_t ld, uint32_t col0, uint32_t kvalid, uint32_t shift) {
-        pa.r[n++] = PackRegion{src, off, rows, src_rows, ld, col0, kvalid, shift, 0, 0};
+        pa.r[n++] = PackRegion{src, off, rows, src_rows, ld, col0, kvalid, shift, 0, 0, 0, 0, 0};
     };
     add(w->aud_att_w0, HW_A, 64, 64, 36, 0, 36, 0);
     add(w->eye_att_w0, HW_A + 64 * 128, 16, 16, 36, 0, 36, 0);
@@ -694,7 +705,8 @@ int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
     add(w->sigma_w1, HW_D, 64, 64, 64, 0, 64, 0);
     add(w->sigma_w2, HW_E, 80, 65, 64, 0, 64, 1);                          // rotate: rows 0..63 = geo (src 1..64), row 64 = logit (src 0)
     add(w->color_w0, HW_F0, 64, 64, 84, 16, 64, 0);                        // geo_feat columns 16..79
-    add(w->color_w0, HW_F1, 64, 64, 84, 0, 16, 0);                         // SH columns 0..15
+    add(w->color_w0, HW_F1, 64, 64, 84, 0, 16, 0);                         // SH columns 0..15 at K 0..15 ...
+    pa.r[n - 1].col1 = 80; pa.r[n - 1].k1_off = 16; pa.r[n - 1].k1_valid = 4;   // ... and the individual-code columns 80..83 at K 16..19 (second K step of P6)
     add(w->color_w1, HW_G, 16, 3, 64, 0, 64, 0);
     pa.n = n;
     cudaStream_t st = as_stream(stream);
@@ -708,7 +720,7 @@ int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
         PackArgs pt = {};
         uint32_t k = 0;
         auto addt = [&](const float *src, uint32_t off, uint32_t rows, uint32_t nvalid, uint32_t ld, uint32_t col0, uint32_t kvalid, uint32_t k0) {
-            pt.r[k++] = PackRegion{src, off, rows, nvalid, ld, col0, kvalid, 0, 1, k0};
+            pt.r[k++] = PackRegion{src, off, rows, nvalid, ld, col0, kvalid, 0, 1, k0, 0, 0, 0};
         };
         addt(w->color_w0, HT_C0G, 64, 64, 84, 16, 64, 0);
         addt(w->color_w0, HT_C0I, 16, 4, 84, 80, 64, 0);
