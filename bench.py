@@ -308,6 +308,22 @@ def torso_bench(dev, steps=20, warmup=5, head=None):
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         per_op_ms = timed(lambda: m.run_torso(coords, pose, 0, None))
         n_on = int(m.run_torso(coords, pose, 0, None)["mask"].sum())
+    # torso TRAINING stage (opt.torso: MSE on torso_color, TrainerUtil.py:188-236): forward + backward of one 512x512 frame, fused kernels vs autograd over the op graph
+    target = torch.rand(HW * HW, 3, device=dev)
+    params = [p for p in m.parameters()]
+
+    def train_step(fused):
+        for p in params:
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.float16):
+            res = m.run_torso_train_fused(coords, pose, 5, None) if fused else m.run_torso(coords, pose, 5, None)
+            loss = ((res["torso_color"] - target) ** 2).mean()
+        (loss * 1024.0).backward()
+
+    m.train()
+    train_fused_ms = timed(lambda: train_step(True))
+    train_per_op_ms = timed(lambda: train_step(False))
+    m.eval()
     macs = 5440                                            # 34*32 + 32*32 + 32*2 + 66*32 + 32*32 + 32*4 per torso pixel (constant inputs folded into a bias)
     frames_with_torso = None
     if head is not None:                                   # whole frames with the torso behind the head: FrameRenderer(torso=...) on every pipeline slot
@@ -331,6 +347,7 @@ def torso_bench(dev, steps=20, warmup=5, head=None):
         frames_with_torso = 60 / (e0.elapsed_time(e1) * 1e-3)
     return {"pixels": HW * HW, "torso_pixels": n_on, "fused_ms_per_frame": fused_ms, "fused_eager_call_ms": fused_eager_ms, "per_op_ms_per_frame": per_op_ms,
             "fused_gflops": 2.0 * macs * n_on / (fused_ms * 1e-3) / 1e9, "frames_per_sec_head_plus_torso": frames_with_torso,
+            "train_fwd_bwd_fused_ms": train_fused_ms, "train_fwd_bwd_per_op_autograd_ms": train_per_op_ms,
             "note": "k_torso_frame: occupancy test + freq encoding + deform MLP + tiled fp16 grid + torso MLP + blend in one launch (CUDA cores, thread = pixel); "
                     "per-op = run_torso on the drop-in encoders + torch Linear under autocast (~25 launches)"}
 

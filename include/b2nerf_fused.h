@@ -274,6 +274,19 @@ typedef struct {
 int b2n_torso_forward(const b2n_torso_weights *w, const float *bg_coords, uint32_t N, const float *density_grid_torso, uint32_t grid_size,
                       float density_thresh, const float *h_const, const float *bg_color, int bg_per_ray, float *bg_out, float *alpha_out,
                       float *deform_out, void *workspace, void *stream);
+/* Training backward of the same branch (network.py:170-205 through autograd) in one kernel: recomputes the forward per pixel, back-propagates through
+ * the blend, the sigmoids, torso_net, the tiled grid (table gradients accumulated in fp32 into g_table [sO,2]; gradient of the deformed coordinate through the
+ * grid's dy_dx and the clamp) and torso_deform_net, and writes the fp16 operands of the six weight gradients dW = dY^T X (all N rows; zero rows outside the torso
+ * mask) for b2n_linear_wgrad_batch: torso_net.{2,1,0} = (dy_t2 [N,8], x_t2 [N,32]) (dy_t1, x_t1 [N,32]) (dy_t0 [N,32], x_t0 [N,120] = [grid 32 | enc_x 34 | h_const 50 | 0 x4]);
+ * torso_deform_net.{2,1,0} = (dy_d2 [N,8], x_d2) (dy_d1, x_d1) (dy_d0 [N,32], x_d0 [N,88] = [enc_x 34 | h_const 50 | 0 x4]).  The gradient of h_const is
+ * W_t0[:, 66:116]^T colsum(dy_t0) + W_d0[:, 34:84]^T colsum(dy_d0).  g_out [N,3] = gradient of bg_out; g_alpha [N] or NULL = gradient of alpha_out. */
+typedef struct {
+    void *x_t0, *x_t1, *x_t2, *x_d0, *x_d1, *x_d2;
+    void *dy_t2, *dy_t1, *dy_t0, *dy_d2, *dy_d1, *dy_d0;
+} b2n_torso_operands;
+int b2n_torso_backward(const b2n_torso_weights *w, const float *bg_coords, uint32_t N, const float *density_grid_torso, uint32_t grid_size,
+                       float density_thresh, const float *h_const, const float *bg_color, int bg_per_ray, const float *g_out, const float *g_alpha,
+                       float *g_table, const b2n_torso_operands *ops, void *workspace, void *stream);
 /* workspace: 16-byte aligned device scratch of b2n_torso_workspace_bytes() bytes owned by the caller (packed weight image + tile counter); one per
  * concurrently running call */
 uint64_t b2n_torso_workspace_bytes(void);

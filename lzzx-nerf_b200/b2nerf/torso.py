@@ -38,6 +38,63 @@ def get_bg_coords(H, W, device):
     return torch.cat([xs.reshape(-1, 1), ys.reshape(-1, 1)], dim=-1).unsqueeze(0)
 
 
+class _TorsoOperandsC(ctypes.Structure):    # mirrors b2n_torso_operands (include/b2nerf_fused.h)
+    _fields_ = [(n, ctypes.c_void_p) for n in ("x_t0", "x_t1", "x_t2", "x_d0", "x_d1", "x_d2", "dy_t2", "dy_t1", "dy_t0", "dy_d2", "dy_d1", "dy_d0")]
+
+
+class _FusedTorso(torch.autograd.Function):
+    """forward_torso + run_torso's blend (network.py:170-205, renderer.py:572-631) as one autograd node on csrc/fused_torso.cu."""
+
+    OPERAND_WIDTHS = dict(x_t0=120, x_t1=32, x_t2=32, x_d0=88, x_d1=32, x_d2=32, dy_t2=8, dy_t1=32, dy_t0=32, dy_d2=8, dy_d1=32, dy_d0=32)
+
+    @staticmethod
+    def forward(ctx, model, bg_coords, h_const, bg_color, wd0, wd1, wd2, wt0, wt1, wt2, table):
+        N, dev = bg_coords.shape[0], bg_coords.device
+        per_ray = int(bg_color is not None and bg_color.numel() == 3 * N and N > 1)
+        out, alpha = torch.empty(N, 3, device=dev), torch.empty(N, device=dev)
+        w = model.weights_struct()
+        ws = torch.empty(int(lib().raw("b2n_torso_workspace_bytes")()), dtype=torch.uint8, device=dev)
+        hc = h_const.detach().float().contiguous().view(-1)
+        lib().call("b2n_torso_forward", ctypes.byref(w), bg_coords.data_ptr(), N, model.density_grid_torso.data_ptr(), model.grid_size, float(model.density_thresh()),
+                   hc.data_ptr(), None if bg_color is None else bg_color.data_ptr(), per_ray, out.data_ptr(), alpha.data_ptr(), None, ws.data_ptr(),
+                   torch.cuda.current_stream().cuda_stream)
+        ctx.model, ctx.per_ray, ctx.thresh = model, per_ray, float(model.density_thresh())
+        ctx.save_for_backward(bg_coords, hc, bg_color if bg_color is not None else torch.empty(0, device=dev))
+        ctx.has_bg = bg_color is not None
+        return out, alpha
+
+    @staticmethod
+    def backward(ctx, g_out, g_alpha):
+        from .fused_train import _wgrad_all
+        model = ctx.model
+        bg_coords, hc, bg_color = ctx.saved_tensors
+        N, dev = bg_coords.shape[0], bg_coords.device
+        Np = -(-N // 256) * 256
+        ops = {k: torch.empty(Np, wd, dtype=torch.float16, device=dev) for k, wd in _FusedTorso.OPERAND_WIDTHS.items()}
+        if Np > N:
+            for t in ops.values():
+                t[N:].zero_()
+        oc = _TorsoOperandsC(*[ops[k].data_ptr() for k, _ in _TorsoOperandsC._fields_])
+        table = model.torso_encoder.embeddings
+        g_table = torch.zeros(table.shape, dtype=torch.float32, device=dev)
+        w = model.weights_struct()
+        ws = torch.empty(int(lib().raw("b2n_torso_workspace_bytes")()), dtype=torch.uint8, device=dev)
+        g_out = g_out.float().contiguous()
+        g_alpha = None if g_alpha is None else g_alpha.float().contiguous()
+        lib().call("b2n_torso_backward", ctypes.byref(w), bg_coords.data_ptr(), N, model.density_grid_torso.data_ptr(), model.grid_size, ctx.thresh, hc.data_ptr(),
+                   bg_color.data_ptr() if ctx.has_bg else None, ctx.per_ray, g_out.data_ptr(), None if g_alpha is None else g_alpha.data_ptr(), g_table.data_ptr(),
+                   ctypes.byref(oc), ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        dw = _wgrad_all([(ops["dy_d0"], ops["x_d0"]), (ops["dy_d1"], ops["x_d1"]), (ops["dy_d2"], ops["x_d2"]),
+                         (ops["dy_t0"], ops["x_t0"]), (ops["dy_t1"], ops["x_t1"]), (ops["dy_t2"], ops["x_t2"])])
+        g_wd0, g_wd1, g_wd2 = dw[0][:, :84].contiguous(), dw[1], dw[2][:2].contiguous()
+        g_wt0, g_wt1, g_wt2 = dw[3][:, :116].contiguous(), dw[4], dw[5][:4].contiguous()
+        # the 50 per-frame constant inputs of both first layers: d h_const = W[:, const]^T colsum(dY) (the weights as the kernels see them: rounded to fp16)
+        d, t = model.torso_deform_net.net, model.torso_net.net
+        s_t, s_d = ops["dy_t0"][:N].float().sum(0), ops["dy_d0"][:N].float().sum(0)
+        g_hc = (t[0].weight.detach()[:, 66:116].half().float().t() @ s_t + d[0].weight.detach()[:, 34:84].half().float().t() @ s_d).view(1, -1)
+        return None, None, g_hc, None, g_wd0, g_wd1, g_wd2, g_wt0, g_wt1, g_wt2, g_table
+
+
 class TorsoModel(nn.Module):
     def __init__(self, ind_dim_torso=8, ind_num=10000, grid_size=128, torso_shrink=0.8, density_thresh_torso=0.01):
         super().__init__()
@@ -144,6 +201,26 @@ class TorsoModel(nn.Module):
         if deform is not None:
             res["deform"] = deform
         return res
+
+    # ---- fused training path -------------------------------------------------------------------------------------------------------
+    def run_torso_train_fused(self, bg_coords, poses, index=0, bg_color=None):
+        """run_torso for the torso TRAINING stage (TrainerUtil.py:188-236 with opt.torso) on two kernels + the head's weight-gradient kernel: forward =
+        k_torso_frame, backward = k_torso_backward (recompute + backward-data + table gradients) and ONE b2n_linear_wgrad_batch launch for the six weight
+        matrices, instead of autograd over ~25 forward and ~60 backward launches of the op-by-op graph.  Differentiable w.r.t. every torso parameter
+        (anchor_points and individual_codes_torso through frame_constants).  Returns the reference's dict (bg_color / torso_color [N,3], torso_alpha [N,1])."""
+        bg_coords = bg_coords.contiguous().view(-1, 2).float()
+        h_const = self.frame_constants(poses, index).float()                  # [1, 50], differentiable (anchor encoder + individual code)
+        N, dev = bg_coords.shape[0], bg_coords.device
+        if bg_color is not None:
+            bg_color = torch.as_tensor(bg_color, dtype=torch.float32, device=dev).contiguous()
+            if bg_color.numel() == 1:
+                bg_color = bg_color.expand(3).contiguous()
+            if bg_color.numel() not in (3, 3 * N):
+                raise RuntimeError("run_torso_train_fused: bg_color must have 1, 3 or N*3 elements")
+        d, t = self.torso_deform_net.net, self.torso_net.net
+        out, alpha = _FusedTorso.apply(self, bg_coords, h_const, bg_color, d[0].weight, d[1].weight, d[2].weight, t[0].weight, t[1].weight, t[2].weight,
+                                       self.torso_encoder.embeddings)
+        return dict(torso_alpha=alpha.view(N, 1), torso_color=out, bg_color=out)
 
     # ---- 2-D occupancy refresh ----------------------------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -300,8 +300,10 @@ def test_fused_torso_vs_reference_run_torso(ref):
         assert 0 < int(g[name + ".n_mask"]) < N
 
 
-def test_torso_training_gradients_vs_reference(ref):
-    """The torso stage's backward (network.py:170-205 through autograd): every torso parameter's gradient against the reference's own autograd graph."""
+@pytest.mark.parametrize("fused", [False, True])
+def test_torso_training_gradients_vs_reference(ref, fused):
+    """The torso stage's backward (network.py:170-205 through autograd): every torso parameter's gradient against the reference's own autograd graph — through
+    the op-by-op graph on the drop-in kernels and through the fused forward / backward kernels (csrc/fused_torso.cu + the tcgen05 weight-gradient kernel)."""
     mode, sz, load = ref
     g = load("torso")
     hw = sz["torso_hw"]
@@ -313,7 +315,7 @@ def test_torso_training_gradients_vs_reference(ref):
     wt = T(r.standard_normal((N, 3)).astype(np.float32))
     scale = rc.LOSS_SCALE
     with torch.autocast("cuda", dtype=torch.float16):
-        res = m.run_torso(coords, pose, index=5, bg_color=bg_ray)
+        res = m.run_torso_train_fused(coords, pose, index=5, bg_color=bg_ray) if fused else m.run_torso(coords, pose, index=5, bg_color=bg_ray)
         loss = (res["torso_color"] * wt).sum() / N
     (loss * scale).backward()
     assert abs(float(loss) - float(g["train.loss"])) < 2e-3 * max(1.0, abs(float(g["train.loss"])))
