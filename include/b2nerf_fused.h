@@ -233,6 +233,13 @@ typedef struct {
 int b2n_adamw_flat_groups(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, uint32_t n, const b2n_adam_groups *groups, float beta1,
                           float beta2, float eps, float *step, const float *grad_scale, const float *found_inf, float *ema, float ema_decay, void *stream);
 
+/* The same step with the GradScaler protocol on the device (torch.amp.GradScaler.step + update, TrainerUtil.py:1046-1047): one non-finite check over the flat
+ * gradients, the unscale / overflow skip inside the AdamW kernel, and the scale update behind it.  scaler_state: device float[4] = {scale, growth tracker,
+ * found_inf (written by the call), unused}; `grads` 16-byte aligned. */
+int b2n_adamw_flat_scaled(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, uint32_t n, const b2n_adam_groups *groups, float beta1,
+                          float beta2, float eps, float *step, float *scaler_state, float growth_factor, float backoff_factor, uint32_t growth_interval,
+                          float *ema, float ema_decay, void *stream);
+
 /* Training loss of the head branch and its gradient (TrainerUtil.py:238-334 with the background blend of renderer.py:559-561), sf = *step_factor:
  *   img = clamp(image + (1 - weights_sum) * bg, 0, 1);   mse_n = mean_c (img - gt)^2
  *   loss = mean_n [ mse_n * (0.2 + 0.8 clamp((1 - sf) + sf N softmax(unc_sum)_n, 0, 10)) + sf face_n (|img - gt| / (2 (unc+1)^2) + log(unc+1)^2 / 2)
@@ -240,7 +247,7 @@ int b2n_adamw_flat_groups(float *params, const float *grads, float *exp_avg, flo
  *          + lambda_ent mean H2(clamp(weights_sum, 1e-5, 1 - 1e-5)) + sf lambda_amb mean(aud_sum (1 - face)) + sf lambda_amb mean(eye_sum inv_max_steps aud_sum face)
  * image [N,3], weights_sum / aud_sum / eye_sum / unc_sum [N] are composite_rays_train_triplane's outputs; bg_color [3] or [N,3] (bg_per_ray); face_mask [N] bytes
  * (bool) or NULL (= every ray on the face); step_factor: device scalar (a replayed CUDA graph sees it ramp) or NULL (= step_factor_host).
- * stats: device float[4] — [0] the loss (overwritten), [1..2] softmax statistics the backward re-uses.  The backward multiplies by the device scalar
+ * stats: device float[256] — [0] the loss (overwritten), [4..131] per-CTA softmax statistics the backward re-uses.  The backward multiplies by the device scalar
  * *grad_loss (autograd's upstream gradient, i.e. the loss scale); grad_unc_sum may be NULL. */
 typedef struct {
     const float *image, *weights_sum, *aud_sum, *eye_sum, *unc_sum;

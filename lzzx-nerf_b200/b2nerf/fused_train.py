@@ -264,7 +264,7 @@ class _FusedLoss(torch.autograd.Function):
         p = lambda t: None if t is None else t.data_ptr()
         args = _LossArgsC(p(image), p(ws), p(aud_sum), p(eye_sum), p(unc_sum), p(gt), p(bg), p(face_mask), p(sf_dev), 0.0 if sf_dev is not None else float(step_factor),
                           float(cfg["lambda_ent"]), float(cfg["lambda_amb"]), 1.0 / float(cfg["max_steps"]), per_ray, int(cfg["amb_aud_loss"]), int(cfg["amb_eye_loss"]))
-        stats = torch.empty(4, dtype=torch.float32, device=ws.device)
+        stats = torch.empty(256, dtype=torch.float32, device=ws.device)
         lib().call("b2n_head_loss_forward", ctypes.byref(args), n, stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
         ctx.keep = (args, image, ws, aud_sum, eye_sum, unc_sum, gt, bg, face_mask, sf_dev, stats)
         ctx.n = n

@@ -74,7 +74,9 @@ class FlatAdamW(torch.optim.Optimizer):
         self.flat_grad = flat_grad
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, scaler=None):
+        """scaler: a FlatGradScaler — the whole GradScaler protocol then runs on the device inside this call (b2n_adamw_flat_scaled).  Without it the optimizer
+        follows torch.amp.GradScaler's `_step_supports_amp_scaling` hand-off (grad_scale / found_inf attributes), or steps unscaled."""
         if self.flat_grad is None:
             raise RuntimeError("FlatAdamW: call attach_grads(FlatGradBuffer.flat) first")
         gs = _AdamGroupsC()
@@ -89,6 +91,12 @@ class FlatAdamW(torch.optim.Optimizer):
             # torch_ema: decay = min(decay, (1 + num_updates) / (10 + num_updates)), num_updates counted from 1
             self.ema_updates += 1
             ema, decay = self.ema, min(self.ema_decay, (1 + self.ema_updates) / (10 + self.ema_updates))
+        if scaler is not None:
+            lib().call("b2n_adamw_flat_scaled", self.flat.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.n,
+                       ctypes.byref(gs), float(b1), float(b2), float(self.param_groups[0]["eps"]), self.step_count.data_ptr(), scaler.state.data_ptr(),
+                       float(scaler.growth_factor), float(scaler.backoff_factor), int(scaler.growth_interval), None if ema is None else ema.data_ptr(), float(decay),
+                       torch.cuda.current_stream().cuda_stream)
+            return None
         lib().call("b2n_adamw_flat_groups", self.flat.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.n,
                    ctypes.byref(gs), float(b1), float(b2), float(self.param_groups[0]["eps"]), self.step_count.data_ptr(),
                    None if scale is None else scale.data_ptr(), None if found is None else found.data_ptr(), None if ema is None else ema.data_ptr(),
@@ -125,3 +133,34 @@ class FlatAdamW(torch.optim.Optimizer):
             self.host_steps, self.ema_updates = int(flat["host_steps"]), int(flat["ema_updates"])
             if self.ema is not None and flat["ema"] is not None:
                 self.ema.copy_(flat["ema"])
+
+
+class FlatGradScaler:
+    """torch.amp.GradScaler for a FlatAdamW (same scale / growth / backoff rules and defaults; TrainerUtil.py:1045-1047 scaler.scale(loss).backward();
+    scaler.step(optimizer); scaler.update()), entirely on the device: `state` = [scale, growth tracker, found_inf, -].  step() hands the state to the optimizer's
+    kernel chain (non-finite check over the flat gradient buffer, unscale + skip inside AdamW, scale update), so update() has nothing left to do and nothing ever
+    synchronises."""
+
+    def __init__(self, device, init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, enabled=True):
+        self.enabled = bool(enabled)
+        self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, growth_interval
+        self.state = torch.tensor([init_scale if enabled else 1.0, 0.0, 0.0, 0.0], dtype=torch.float32, device=device)
+
+    def scale(self, loss):
+        return loss * self.state[0] if self.enabled else loss
+
+    def step(self, optimizer):
+        return optimizer.step(scaler=self) if self.enabled else optimizer.step()
+
+    def update(self):
+        return None
+
+    def get_scale(self):
+        return float(self.state[0].item())
+
+    def state_dict(self):
+        return {"state": self.state.clone(), "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor, "growth_interval": self.growth_interval}
+
+    def load_state_dict(self, sd):
+        self.state.copy_(sd["state"])
+        self.growth_factor, self.backoff_factor, self.growth_interval = sd["growth_factor"], sd["backoff_factor"], sd["growth_interval"]

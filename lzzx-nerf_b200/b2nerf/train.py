@@ -51,7 +51,11 @@ class Trainer:
                 model.pack()                              # the parameter storage moved: refresh the pointers baked into the packed model
         # the fused backward accumulates every gradient straight into these .grad views (fused_train._direct_targets): no per-parameter add kernels
         model._direct_grads = bool(fused_head and enc[0].is_cuda)
-        self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
+        if isinstance(self.opt, FlatAdamW):
+            from .optim import FlatGradScaler
+            self.scaler = FlatGradScaler(enc[0].device, enabled=fp16)      # GradScaler's rules, on the device, inside the optimizer's launch chain
+        else:
+            self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
         self.local_step = 0
         self.mean_count = 0
         self._graphs = {}                # M bucket -> (CUDAGraph, static buffers)

@@ -24,30 +24,50 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// stats[1] = max_n u, stats[2] = sum_n exp(u - max): the softmax over the rays of the batch (TrainerUtil.py:262)
-__global__ void __launch_bounds__(1024) k_loss_softmax_stats(const float *__restrict__ u, uint32_t N, float *__restrict__ stats) {
-    __shared__ float s[32];
+// softmax over the rays of the batch (TrainerUtil.py:262), in two levels: LS_BLOCKS CTAs each leave (max, sum exp(u - max)) of their share in
+// stats[4 + 2 b], and every CTA of the loss kernels folds the LS_BLOCKS partials (softmax_fold) — no single-CTA pass over the batch, no extra launch.
+constexpr uint32_t LS_BLOCKS = 64;
+__global__ void __launch_bounds__(256) k_loss_softmax_stats(const float *__restrict__ u, uint32_t N, float *__restrict__ stats) {
+    __shared__ float s[8];
     float mx = -INFINITY;
-    for (uint32_t n = threadIdx.x; n < N; n += blockDim.x) mx = fmaxf(mx, u[n]);
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) mx = fmaxf(mx, u[n]);
     mx = warp_max(mx);
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = mx;
     __syncthreads();
-    mx = warp_max(s[threadIdx.x & 31]);
+    mx = warp_max(s[threadIdx.x & 7]);
     __syncthreads();
     float se = 0.0f;
-    for (uint32_t n = threadIdx.x; n < N; n += blockDim.x) se += expf(u[n] - mx);
+    if (mx > -INFINITY)
+        for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) se += expf(u[n] - mx);
     se = warp_sum(se);
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = se;
     __syncthreads();
-    se = warp_sum(s[threadIdx.x & 31]);
-    if (threadIdx.x == 0) { stats[1] = mx; stats[2] = se; }
+    if (threadIdx.x < 32) {
+        se = warp_sum(threadIdx.x < 8 ? s[threadIdx.x] : 0.0f);
+        if (threadIdx.x == 0) { stats[4 + 2 * blockIdx.x] = mx; stats[5 + 2 * blockIdx.x] = se; }
+    }
+}
+// every thread of the CTA gets (max, sum exp(u - max)) of the whole batch; call from all threads (one barrier)
+__device__ __forceinline__ void softmax_fold(const float *__restrict__ stats, float &mx, float &se) {
+    __shared__ float s_ms[2];
+    if (threadIdx.x < 32) {
+        const float m0 = stats[4 + 2 * threadIdx.x], m1 = stats[4 + 2 * (threadIdx.x + 32)];
+        const float m = warp_max(fmaxf(m0, m1));
+        float v = 0.0f;
+        if (m0 > -INFINITY) v += stats[5 + 2 * threadIdx.x] * expf(m0 - m);
+        if (m1 > -INFINITY) v += stats[5 + 2 * (threadIdx.x + 32)] * expf(m1 - m);
+        v = warp_sum(v);
+        if (threadIdx.x == 0) { s_ms[0] = m; s_ms[1] = v; }
+    }
+    __syncthreads();
+    mx = s_ms[0]; se = s_ms[1];
 }
 
 struct RayTerms { float img[3], pre[3], d[3], mse, w, sf, face; };
 
 __device__ __forceinline__ float step_factor_of(const b2n_loss_args &a) { return a.step_factor ? a.step_factor[0] : a.step_factor_host; }
 
-__device__ __forceinline__ RayTerms ray_terms(const b2n_loss_args &a, uint32_t n, uint32_t N, const float *stats) {
+__device__ __forceinline__ RayTerms ray_terms(const b2n_loss_args &a, uint32_t n, uint32_t N, float sm_max, float sm_sum) {
     RayTerms t;
     const float k = 1.0f - a.weights_sum[n];
     t.mse = 0.0f;
@@ -64,17 +84,18 @@ __device__ __forceinline__ RayTerms ray_terms(const b2n_loss_args &a, uint32_t n
     t.face = a.face_mask ? (a.face_mask[n] ? 1.0f : 0.0f) : 1.0f;
     t.w = 1.0f;
     if (a.unc_sum) {
-        const float uw = expf(a.unc_sum[n] - stats[1]) / stats[2] * (float)N;
+        const float uw = expf(a.unc_sum[n] - sm_max) / sm_sum * (float)N;
         t.w = 0.2f + 0.8f * fminf(fmaxf((1.0f - t.sf) + t.sf * uw, 0.0f), 10.0f);
     }
     return t;
 }
 
 __global__ void __launch_bounds__(256) k_head_loss_fwd(const __grid_constant__ b2n_loss_args a, uint32_t N, float *__restrict__ stats) {
-    float acc = 0.0f;
+    float acc = 0.0f, sm_max = 0.0f, sm_sum = 1.0f;
+    if (a.unc_sum) softmax_fold(stats, sm_max, sm_sum);
     const float inv_n = 1.0f / (float)N;
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
-        const RayTerms t = ray_terms(a, n, N, stats);
+        const RayTerms t = ray_terms(a, n, N, sm_max, sm_sum);
         float l = t.mse * t.w;
         if (a.unc_sum) {
             const float u = a.unc_sum[n], beta = u + 1.0f, lb = logf(beta);
@@ -105,8 +126,10 @@ __global__ void __launch_bounds__(256) k_head_loss_bwd(const __grid_constant__ b
                                                         float *__restrict__ d_image, float *__restrict__ d_ws, float *__restrict__ d_aud, float *__restrict__ d_eye,
                                                         float *__restrict__ d_unc) {
     const float up = g[0] / (float)N;
+    float sm_max = 0.0f, sm_sum = 1.0f;
+    if (a.unc_sum) softmax_fold(stats, sm_max, sm_sum);
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
-        const RayTerms t = ray_terms(a, n, N, stats);
+        const RayTerms t = ray_terms(a, n, N, sm_max, sm_sum);
         float dw = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
@@ -150,7 +173,7 @@ extern "C" int b2n_head_loss_forward(const b2n_loss_args *a, uint32_t N, float *
     cudaStream_t st = as_stream(stream);
     B2N_CUDA(cudaMemsetAsync(stats, 0, sizeof(float), st));
     if (a->unc_sum) {
-        k_loss_softmax_stats<<<1, 1024, 0, st>>>(a->unc_sum, N, stats);
+        k_loss_softmax_stats<<<LS_BLOCKS, 256, 0, st>>>(a->unc_sum, N, stats);
         if (check_launch("head_loss_forward(stats)")) return 1;
     }
     uint32_t g = ceil_div<uint32_t>(N, 256);

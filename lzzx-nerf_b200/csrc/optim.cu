@@ -44,6 +44,28 @@ __global__ void __launch_bounds__(256) k_adamw_flat(float *__restrict__ p, const
     }
 }
 
+// GradScaler on the device (torch.amp.GradScaler's _amp_foreach_non_finite_check_and_unscale_ + _amp_update_scale_, TrainerUtil.py:1046-1047): the non-finite check
+// is ONE pass over the flat gradient buffer instead of a multi-tensor launch over ~60 views, the unscale is folded into the AdamW kernel, and the scale update
+// is a one-thread kernel behind it.  scaler_state: float[4] = {scale, growth tracker, found_inf, -}.
+__global__ void __launch_bounds__(256) k_flat_nonfinite(const float *__restrict__ g, uint32_t n, float *__restrict__ found_inf) {
+    bool bad = false;
+    const uint32_t n4 = n / 4;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + i);
+        bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n - 4 * n4) bad |= !isfinite(g[4 * n4 + threadIdx.x]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) found_inf[0] = 1.0f;
+}
+__global__ void k_scaler_update(float *state, float growth, float backoff, float interval) {
+    if (state[2] != 0.0f) { state[0] *= backoff; state[1] = 0.0f; }
+    else {
+        const float t = state[1] + 1.0f;
+        if (t >= interval) { const float grown = state[0] * growth; if (isfinite(grown)) state[0] = grown; state[1] = 0.0f; }
+        else state[1] = t;
+    }
+}
+
 }  // namespace b2n
 
 using namespace b2n;
@@ -73,4 +95,25 @@ extern "C" int b2n_adamw_flat(float *params, const float *grads, float *exp_avg,
     b2n_adam_groups g = {};
     g.n_groups = 2; g.end[0] = n_group0; g.end[1] = n; g.lr[0] = lr0; g.lr[1] = lr1; g.weight_decay[0] = weight_decay0; g.weight_decay[1] = weight_decay1;
     return b2n_adamw_flat_groups(params, grads, exp_avg, exp_avg_sq, n, &g, beta1, beta2, eps, step, grad_scale, found_inf, nullptr, 0.0f, stream);
+}
+
+// AdamW + the whole GradScaler protocol in four small launches: non-finite check of the (all-reduced) flat gradients -> step counter -> AdamW with the unscale and
+// the overflow skip folded in -> scale update (x backoff on overflow, x growth after `growth_interval` clean steps).  scaler_state: device float[4]
+// {scale, growth tracker, found_inf (written here), unused}.  `grads` must be 16-byte aligned.
+extern "C" int b2n_adamw_flat_scaled(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, uint32_t n, const b2n_adam_groups *groups, float beta1,
+                                     float beta2, float eps, float *step, float *scaler_state, float growth_factor, float backoff_factor, uint32_t growth_interval,
+                                     float *ema, float ema_decay, void *stream) {
+    B2N_REQUIRE(grads && scaler_state, "adamw_flat_scaled: null pointer");
+    B2N_REQUIRE(((uintptr_t)grads & 15) == 0, "adamw_flat_scaled: the gradient buffer must be 16-byte aligned");
+    if (n == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    B2N_CUDA(cudaMemsetAsync(scaler_state + 2, 0, sizeof(float), st));
+    uint32_t blocks = ceil_div<uint32_t>(n / 4 + 1, 256);
+    const uint32_t cap = (uint32_t)sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    k_flat_nonfinite<<<blocks, 256, 0, st>>>(grads, n, scaler_state + 2);
+    if (check_launch("adamw_flat_scaled(check)")) return 1;
+    if (int rc = b2n_adamw_flat_groups(params, grads, exp_avg, exp_avg_sq, n, groups, beta1, beta2, eps, step, scaler_state, scaler_state + 2, ema, ema_decay, stream)) return rc;
+    k_scaler_update<<<1, 1, 0, st>>>(scaler_state, growth_factor, backoff_factor, (float)growth_interval);
+    return check_launch("adamw_flat_scaled(update)");
 }

@@ -487,3 +487,38 @@ def test_triplane_grid_backward_fixed_point_vs_float64():
     torch.cuda.synchronize()
     assert not bool(torch.isfinite(tabs[1][offs[7]:offs[8]]).all())
     assert bool(torch.isfinite(tabs[0]).all()) and bool(torch.isfinite(tabs[2]).all())
+
+
+def test_flat_grad_scaler_matches_torch_grad_scaler():
+    """FlatGradScaler (scale / found-inf / growth tracker on the device, non-finite check + unscale + skip + scale update inside FlatAdamW's launch chain,
+    csrc/optim.cu) against torch.amp.GradScaler + torch.optim.AdamW: same parameters and the same scale after a sequence with two overflows and a growth."""
+    from b2nerf.optim import FlatAdamW, FlatGradScaler
+    torch.manual_seed(1)
+    mk = lambda shapes: [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    a0, a1 = mk([(500, 1), (77, 1)]), mk([(16, 9), (5,)])
+    b0, b1 = ([torch.nn.Parameter(p.detach().clone()) for p in a] for a in (a0, a1))
+    ref = torch.optim.AdamW([{"params": b0, "lr": 1e-2}, {"params": b1, "lr": 1e-3, "weight_decay": 0}], betas=(0.0, 0.99), eps=1e-8)
+    opt = FlatAdamW([{"params": a0, "lr": 1e-2, "weight_decay": 0.01}, {"params": a1, "lr": 1e-3, "weight_decay": 0.0}], betas=(0.0, 0.99), eps=1e-8)
+    flat_g = torch.zeros(opt.n, device="cuda")
+    off = 0
+    for p in a0 + a1:
+        p.grad = flat_g[off:off + p.numel()].view_as(p); off += p.numel()
+    opt.attach_grads(flat_g)
+    sa = FlatGradScaler("cuda", init_scale=1024.0, growth_interval=3)
+    sb = torch.amp.GradScaler("cuda", init_scale=1024.0, growth_interval=3)
+    for step in range(10):
+        gs = [torch.randn_like(p) for p in a0 + a1]
+        if step in (2, 7):
+            gs[step % 3][1] = float("nan") if step == 2 else float("-inf")
+        for p, q, g in zip(a0 + a1, b0 + b1, gs):
+            p.grad.copy_(g * sa.get_scale()); q.grad = g * sb.get_scale()
+        sb.scale(torch.zeros((), device="cuda"))
+        sa.step(opt); sa.update()
+        sb.step(ref); sb.update()
+        assert sa.get_scale() == sb.get_scale(), (step, sa.get_scale(), sb.get_scale())
+    assert float(opt.step_count) == 8.0
+    for p, q in zip(a0 + a1, b0 + b1):
+        assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), float((p - q).abs().max())
+    sd = sa.state_dict()
+    sa.state.zero_(); sa.load_state_dict(sd)
+    assert sa.get_scale() == sb.get_scale()
