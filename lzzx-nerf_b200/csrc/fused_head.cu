@@ -560,6 +560,297 @@ __global__ void __maxnreg__(SAVE ? 168 : 128) k_head_forward(const __grid_consta
     if (warp == 1) tmem_dealloc(S.tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// inference kernel, FOUR tiles in flight per SM: hidden activations live in TENSOR MEMORY
+// ---------------------------------------------------------------------------------------------------
+// k_head_forward above keeps three tiles per SM in flight: each warpgroup needs two feature tiles and one hidden-activation tile in shared memory (48 KB), and
+// 3 x 48 + 70 KB of weights fill the SM.  Its ncu profile is latency-bound with 12 warps (issue slots 39 % busy, tensor pipe 15 %): more tiles in flight is
+// the lever.  Here the hidden activations never touch shared memory: an epilogue reads the fp32 accumulator columns (tcgen05.ld), applies the activation,
+// packs to fp16 and writes the next layer's A operand straight back to tensor memory (tcgen05.st, two halves per 32-bit column, row = lane), and the next
+// layer is a tcgen05.mma whose A operand is read from TMEM.  A warpgroup then owns 32 KB of shared memory (the double-buffered feature tile) and 128 TMEM
+// columns: 4 warpgroups x (32 KB, 128 columns) = 128 KB + 70 KB of weights and all 512 columns.  No swizzled st.shared / address arithmetic in the
+// epilogues, no generic->async proxy fence for the activations.
+// TMEM columns of a warpgroup: A operand [0, 32) | accumulators inside [32, 128):
+//   P1  [aud hidden 64 | eye hidden 16] -> [32, 112)          (features from shared memory)
+//   P2  att 32 -> [32, 64)  = A(aud hidden) x WB ;  sigma hidden (enc_x part) 64 -> [64, 128) = features x WA[80:144]
+//   P3  [64, 128) += A([enc_a * att | e]) x WC                 P4  [32, 96)  = A x WD            P5  [32, 112) = A x WE  (geo 64 | logit)
+//   P6  [32, 96)  = A(geo) x WF0 + [SH | ind code] x WF1       P7  [32, 48)  = A x WG
+// Same arithmetic as k_head_forward<false, QUAD> (same MMAs on the same operands, same epilogue math) — tests compare the two bit for bit.
+constexpr uint32_t H4_WGS = 4, H4_THREADS = H4_WGS * 128, H4_COLS = 128, H4_ACC = 32;
+struct Head4Smem {
+    HeadLvl lvl[12];
+    __half2 enc_a_h2[16];
+    float eye_w1[16];
+    uint32_t ind_p[2];
+    float eye_val;
+    uint32_t n_valid, tmem_base;
+    uint64_t bar_w, bar_mma[H4_WGS];
+};
+
+// 64 accumulator columns of this thread's row -> (ReLU) -> 32 packed fp16 columns of the A operand region
+template <bool RELU>
+__device__ __forceinline__ void hidden_to_tmem(uint32_t t_acc, uint32_t t_a) {
+#pragma unroll 1
+    for (uint32_t cb = 0; cb < 64; cb += 32) {
+        uint32_t acc[32];
+        ld32(t_acc + cb, acc);
+        wait_ld();
+        uint32_t w[16];
+#pragma unroll
+        for (uint32_t j = 0; j < 16; j++) {
+            const float x0 = __uint_as_float(acc[2 * j]), x1 = __uint_as_float(acc[2 * j + 1]);
+            w[j] = RELU ? pack2_relu(x0, x1) : pack2(x0, x1);
+        }
+        st16(t_a + (cb >> 1), w);
+    }
+}
+__device__ __forceinline__ void issue_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_saddr, uint32_t ksteps, uint32_t N, bool accumulate) {
+    const uint32_t idesc = idesc_f16(128, N);
+    uint64_t db = smem_desc_sw128(b_saddr);
+#pragma unroll 1
+    for (uint32_t k = 0; k < ksteps; k++, a_tmem += 8, db += 2) mma_f16_ts(d_tmem, a_tmem, db, idesc, accumulate || k > 0);      // 16 halves = 8 columns per K step
+}
+
+template <bool QUAD>
+__global__ void __launch_bounds__(H4_THREADS, 1) k_head_infer4(const __grid_constant__ HeadArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *s_w = base;
+    uint8_t *s_tiles = base + HW_BYTES;
+    Head4Smem &S = *reinterpret_cast<Head4Smem *>(s_tiles + H4_WGS * 2 * HG_TILE_BYTES);
+    const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u, warp = tid >> 5;
+    const uint32_t n_valid_early = a.n_valid ? (uint32_t)max(0, min((int)a.M, __ldg(a.n_valid))) : a.M;
+    if (n_valid_early <= blockIdx.x * H4_WGS * HG_TILE) return;
+    uint8_t *sXb = s_tiles + wg * 2 * HG_TILE_BYTES;
+
+    if (tid == 0) {
+        mbar_init(&S.bar_w, 1);
+        for (int g = 0; g < (int)H4_WGS; g++) mbar_init(&S.bar_mma[g], 1);
+        fence_mbar_init();
+        mbar_expect_tx(&S.bar_w, HW_BYTES);
+        bulk_g2s(s_w, a.wimg, HW_BYTES, &S.bar_w);
+        S.n_valid = a.n_valid ? (uint32_t)max(0, min((int)a.M, *a.n_valid)) : a.M;
+        S.eye_val = a.eye ? a.eye[0] : 0.0f;
+    }
+    if (warp == 1) tmem_alloc(&S.tmem_base, 512);
+    if (tid >= 128 && tid < 144) S.enc_a_h2[tid - 128] = __floats2half2_rn(a.enc_a[2 * (tid - 128)], a.enc_a[2 * (tid - 128) + 1]);
+    if (tid >= 160 && tid < 176) S.eye_w1[tid - 160] = a.wsmall[HS_EYE_W1 + tid - 160];
+    if (tid == 256) {
+        S.ind_p[0] = a.ind_code ? pack2(a.ind_code[0], a.ind_code[1]) : 0u;
+        S.ind_p[1] = a.ind_code ? pack2(a.ind_code[2], a.ind_code[3]) : 0u;
+    }
+    if (tid >= 320 && tid < 332) S.lvl[tid - 320] = a.lvl[tid - 320];
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    mbar_wait(&S.bar_w, 0);
+
+    const uint32_t n_valid = S.n_valid;
+    const uint32_t n_tiles = (n_valid + HG_TILE - 1) / HG_TILE;
+    const uint32_t tm = S.tmem_base + wg * H4_COLS;                          // this warpgroup's columns: A operand at +0, accumulators from +32
+    const uint32_t lane_off = ((warp & 3u) * 32u) << 16;                    // this warp's lane quarter (tcgen05.ld / st)
+    const uint32_t tA = tm + lane_off, tD = tm + H4_ACC + lane_off;         // per-thread addresses
+    const uint32_t mA = tm, mD = tm + H4_ACC;                               // MMA operand / accumulator addresses (lane 0)
+    const uint32_t sW_a = smem_u32(s_w);
+    uint64_t *bar = &S.bar_mma[wg];
+    uint32_t phase = 0;
+    const float *t_xy = a.tab[0], *t_yz = a.tab[1], *t_xz = a.tab[2];
+    const uint32_t r7 = t & 7u;
+    const uint32_t row_off = (t >> 3) * 1024u + r7 * 128u;
+
+    auto sync_wg = [&]() { bar_sync(1 + wg, 128); };
+    auto mma_done = [&]() { mbar_wait(bar, phase); phase ^= 1u; fence_after_sync(); };
+    // operands written by this warpgroup (shared memory: generic -> async proxy; tensor memory: tcgen05.st completion) -> visible to the tensor pipe
+    auto publish = [&]() { wait_st(); fence_before_sync(); fence_proxy_async(); sync_wg(); };
+    auto row_live = [&](uint32_t m) {
+        bool live = m < n_valid;
+        if (live && a.live_deltas) live = __ldg(a.live_deltas + 2 * (size_t)m) != 0.0f;
+        return live;
+    };
+    auto make_coord = [&](float px, float py, float pz, bool live) {
+        float ux, uy, uz;
+        if (a.inv_two_bound != 0.0f) {
+            ux = __fmul_rn(__fadd_rn(px, a.bound), a.inv_two_bound); uy = __fmul_rn(__fadd_rn(py, a.bound), a.inv_two_bound); uz = __fmul_rn(__fadd_rn(pz, a.bound), a.inv_two_bound);
+        } else {
+            const float two_b = __fmul_rn(2.0f, a.bound);
+            ux = __fdiv_rn(__fadd_rn(px, a.bound), two_b); uy = __fdiv_rn(__fadd_rn(py, a.bound), two_b); uz = __fdiv_rn(__fadd_rn(pz, a.bound), two_b);
+        }
+        const bool okx = !(ux < 0.0f || ux > 1.0f), oky = !(uy < 0.0f || uy > 1.0f), okz = !(uz < 0.0f || uz > 1.0f);
+        SampleCoord c;
+        c.ux = okx ? ux : 0.0f; c.uy = oky ? uy : 0.0f; c.uz = okz ? uz : 0.0f;
+        c.ok = live ? ((okx && oky ? 1u : 0u) | (oky && okz ? 2u : 0u) | (okx && okz ? 4u : 0u)) : 0u;
+        return c;
+    };
+    auto zero_k_padding = [&](uint8_t *tile) {
+        *reinterpret_cast<uint2 *>(tile + row_off + ((4u ^ r7) << 4) + 8u) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint4 *>(tile + row_off + ((5u ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+    };
+
+    const uint32_t tile_stride = gridDim.x * H4_WGS;
+    uint32_t tile = blockIdx.x * H4_WGS + wg;
+    uint32_t buf = 0;
+    if (tile < n_tiles) {
+        const uint32_t m0 = tile * HG_TILE + t;
+        const bool live0 = row_live(m0);
+        float px = 0, py = 0, pz = 0;
+        if (live0) { px = __ldcs(a.xyzs + 3 * (size_t)m0); py = __ldcs(a.xyzs + 3 * (size_t)m0 + 1); pz = __ldcs(a.xyzs + 3 * (size_t)m0 + 2); }
+        const SampleCoord c = make_coord(px, py, pz, live0);
+        GatherTrip GA, GB;
+        gather_issue<QUAD>(GA, t_xy, t_yz, t_xz, &S.lvl[0], c);
+#pragma unroll 1
+        for (uint32_t k = 0; k < 6; k += 2) {
+            gather_issue<QUAD>(GB, t_xy, t_yz, t_xz, &S.lvl[2 * k + 2], c);
+            gather_finish(GA, c.ok, sXb + row_off, r7, k);
+            if (k + 2 < 6) gather_issue<QUAD>(GA, t_xy, t_yz, t_xz, &S.lvl[2 * k + 4], c);
+            gather_finish(GB, c.ok, sXb + row_off, r7, k + 1);
+        }
+        zero_k_padding(sXb);
+    }
+    for (; tile < n_tiles; tile += tile_stride) {
+        uint8_t *sX = sXb + buf * HG_TILE_BYTES, *sXn = sXb + (buf ^ 1u) * HG_TILE_BYTES;
+        const uint32_t sX_a = smem_u32(sX);
+        const uint32_t m = tile * HG_TILE + t;
+        const bool live = row_live(m);
+        float dxv = 0, dyv = 0, dzv = 1;
+        if (live) { dxv = __ldcs(a.dirs + 3 * (size_t)m); dyv = __ldcs(a.dirs + 3 * (size_t)m + 1); dzv = __ldcs(a.dirs + 3 * (size_t)m + 2); }
+        const bool has_next = tile + tile_stride < n_tiles;
+        float npx = 0, npy = 0, npz = 0;
+        bool nlive = false;
+        if (has_next) {
+            const uint32_t mn = (tile + tile_stride) * HG_TILE + t;
+            nlive = row_live(mn);
+            if (nlive) { npx = __ldcs(a.xyzs + 3 * (size_t)mn); npy = __ldcs(a.xyzs + 3 * (size_t)mn + 1); npz = __ldcs(a.xyzs + 3 * (size_t)mn + 2); }
+        }
+        uint8_t *rown = sXn + row_off;
+        GatherTrip G;
+        publish();
+        // ---- P1: [aud hidden 64 | eye hidden 16] = X * WA[0:80] ---------------------------------------------------------------------
+        if (t == 0) { fence_after_sync(); issue_mma(mD, sX_a, sW_a + HW_A, 3, 80, false); mma_commit(bar); }
+        const SampleCoord cn = make_coord(npx, npy, npz, nlive);
+        if (has_next) { zero_k_padding(sXn); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[0], cn); }
+        mma_done();
+        float eye_att;
+        {
+            hidden_to_tmem<true>(tD, tA);
+            uint32_t e16[16];
+            ld16(tD + 64, e16); wait_ld();
+            float dot = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t w = pack2_relu(__uint_as_float(e16[2 * j]), __uint_as_float(e16[2 * j + 1]));
+                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w));
+                dot = fmaf(f.x, S.eye_w1[2 * j], dot); dot = fmaf(f.y, S.eye_w1[2 * j + 1], dot);
+            }
+            eye_att = round_h(1.0f / (1.0f + expf(-round_h(dot))));
+        }
+        publish();
+        // ---- P2: att = A(aud hidden) * WB -> [32, 64) ; sigma hidden (enc_x part) = X * WA[80:144] -> [64, 128) --------------------
+        if (t == 0) {
+            fence_after_sync();
+            issue_mma_ts(mD, mA, sW_a + HW_B, 4, 32, false);
+            issue_mma(mD + 32, sX_a, sW_a + HW_A + 80 * 128, 3, 64, false);
+            mma_commit(bar);
+        }
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 0); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[2], cn); }
+        mma_done();
+        float amb_aud;
+        {
+            uint32_t acc[32];
+            ld32(tD, acc); wait_ld();
+            float n2 = 0.0f;
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t ah = pack2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+                const __half2 a2 = *reinterpret_cast<const __half2 *>(&ah);
+                const float2 f = __half22float2(a2);
+                n2 = fmaf(f.x, f.x, n2); n2 = fmaf(f.y, f.y, n2);
+                const __half2 p = __hmul2(a2, S.enc_a_h2[j]);
+                w[j] = *reinterpret_cast<const uint32_t *>(&p);
+            }
+            amb_aud = sqrtf(n2);
+            // A operand of P3: [enc_w 32 | e | 0 x15] = 24 columns
+            st16(tA, w);
+            const float e = a.eye ? S.eye_val * eye_att : 0.0f;
+            const uint32_t w8[8] = {pack2(e, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            st8(tA + 16, w8);
+        }
+        publish();
+        // ---- P3: sigma hidden += A([enc_w, e]) * WC ------------------------------------------------------------------------------------
+        if (t == 0) { fence_after_sync(); issue_mma_ts(mD + 32, mA, sW_a + HW_C, 3, 64, true); mma_commit(bar); }
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 1); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[4], cn); }
+        mma_done();
+        hidden_to_tmem<true>(tD + 32, tA);
+        publish();
+        // ---- P4: sigma layer 1 -> [32, 96) --------------------------------------------------------------------------------------------
+        if (t == 0) { fence_after_sync(); issue_mma_ts(mD, mA, sW_a + HW_D, 4, 64, false); mma_commit(bar); }
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 2); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[6], cn); }
+        mma_done();
+        hidden_to_tmem<true>(tD, tA);
+        publish();
+        // ---- P5: sigma layer 2 -> [32, 112): cols 0..63 geo_feat, col 64 density logit ------------------------------------------------------
+        if (t == 0) { fence_after_sync(); issue_mma_ts(mD, mA, sW_a + HW_E, 4, 80, false); mma_commit(bar); }
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 3); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[8], cn); }
+        mma_done();
+        float sigma;
+        {
+            hidden_to_tmem<false>(tD, tA);
+            uint32_t s16[16];
+            ld16(tD + 64, s16); wait_ld();
+            sigma = expf(round_h(__uint_as_float(s16[0]))) * a.density_scale;
+            float shv[16];
+            sh4(dxv, dyv, dzv, shv);
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) w[j] = pack2(shv[2 * j], shv[2 * j + 1]);
+            // the feature tile is dead (P2 read it last): [SH 16 | ind code 4 | 0 x12] in its chunks 0..3
+            *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+            *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 2)) = make_uint4(S.ind_p[0], S.ind_p[1], 0u, 0u);
+            *reinterpret_cast<uint4 *>(sX + sw128_offset(t, 3)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        publish();
+        // ---- P6: color layer 0 = A(geo) * WF0 + [SH | ind] * WF1 -> [32, 96) ------------------------------------------------------------
+        if (t == 0) {
+            fence_after_sync();
+            issue_mma_ts(mD, mA, sW_a + HW_F0, 4, 64, false);
+            issue_mma(mD, sX_a, sW_a + HW_F1, 2, 64, true);
+            mma_commit(bar);
+        }
+        if (has_next) { gather_finish(G, cn.ok, rown, r7, 4); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[10], cn); }
+        mma_done();
+        hidden_to_tmem<true>(tD, tA);
+        publish();
+        // ---- P7: color layer 1 (N padded 3 -> 16) -> [32, 48) --------------------------------------------------------------------------------
+        if (t == 0) { fence_after_sync(); issue_mma_ts(mD, mA, sW_a + HW_G, 4, 16, false); mma_commit(bar); }
+        if (has_next) gather_finish(G, cn.ok, rown, r7, 5);
+        mma_done();
+        {
+            uint32_t c16[16];
+            ld16(tD, c16); wait_ld();
+            if (live) {
+                float rgb[3];
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const float s = round_h(1.0f / (1.0f + expf(-round_h(__uint_as_float(c16[j])))));
+                    rgb[j] = round_h(round_h(s * 1.002f) - 0.001f);
+                }
+                if (a.sigmas) __stcs(a.sigmas + m, sigma);
+                if (a.rgbs) { __stcs(a.rgbs + 3 * (size_t)m, rgb[0]); __stcs(a.rgbs + 3 * (size_t)m + 1, rgb[1]); __stcs(a.rgbs + 3 * (size_t)m + 2, rgb[2]); }
+                if (a.amb_aud) __stcs(a.amb_aud + m, amb_aud);
+                if (a.amb_eye) __stcs(a.amb_eye + m, eye_att);
+                if (a.unc) __stcs(a.unc + m, 0.6931471805599453f);       // testing: log(1 + e^0) (network.py:245,278)
+            }
+        }
+        buf ^= 1u;
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(S.tmem_base, 512);
+}
+
+size_t head4_smem_bytes() { return 1024 + HW_BYTES + (size_t)H4_WGS * 2 * HG_TILE_BYTES + sizeof(Head4Smem); }
+
 size_t head_smem_bytes() { return 1024 + HW_BYTES + (size_t)HG_WGS * 3 * HG_TILE_BYTES + sizeof(HeadSmem); }
 
 int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save, bool quad) {
@@ -573,8 +864,21 @@ int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save, bool quad
         attr = true;
     }
     const uint32_t tiles = ceil_div<uint32_t>(a.M, HG_TILE);
-    uint32_t ctas = ceil_div<uint32_t>(tiles, HG_WGS);
     const uint32_t sms = (uint32_t)sm_count();
+    // inference without unc_net: the four-warpgroup kernel with the activations in tensor memory (B2N_HEAD_WG4=0 keeps the three-warpgroup kernel, for A/B)
+    const char *wg4_env = getenv("B2N_HEAD_WG4");
+    const bool wg4 = !(wg4_env && wg4_env[0] == '0');
+    if (!save && !a.has_unc && wg4) {
+        const size_t smem4 = head4_smem_bytes();
+        B2N_CUDA(cudaFuncSetAttribute(k_head_infer4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        B2N_CUDA(cudaFuncSetAttribute(k_head_infer4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        uint32_t c4 = ceil_div<uint32_t>(tiles, H4_WGS);
+        if (c4 > sms) c4 = sms;
+        if (c4 == 0) return 0;
+        if (quad) k_head_infer4<true><<<c4, H4_THREADS, smem4, st>>>(a); else k_head_infer4<false><<<c4, H4_THREADS, smem4, st>>>(a);
+        return check_launch("head_forward(4 warpgroups)");
+    }
+    uint32_t ctas = ceil_div<uint32_t>(tiles, HG_WGS);
     if (ctas > sms) ctas = sms;
     if (ctas == 0) return 0;
     if (save) { if (quad) k_head_forward<true, true><<<ctas, HG_THREADS, smem, st>>>(a); else k_head_forward<true, false><<<ctas, HG_THREADS, smem, st>>>(a); }

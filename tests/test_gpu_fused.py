@@ -475,3 +475,25 @@ def test_peer_allreduce_kernel_ranks_as_streams_of_one_process(world, n):
             L.raw("b2n_peer_comm_destroy")(c)
         for p in ptrs:
             L.call("b2n_peer_free", p)
+
+
+def test_four_warpgroup_tmem_head_kernel_equals_three_warpgroup_kernel(monkeypatch):
+    """k_head_infer4 (4 tiles in flight per SM, hidden activations in tensor memory: tcgen05.st + MMA with the A operand in TMEM) runs the same MMAs on the same
+    operands with the same epilogue arithmetic as k_head_forward (3 tiles, activations through shared memory): every output bit for bit, on a size with ragged
+    last tiles, out-of-range samples and n_valid."""
+    m = _model(5, 1.0, True)
+    x, d = _samples(150003, 21)
+    x[:4] = torch.tensor([[1.0, 1.0, 1.0], [-1.0, -1.0, -1.0], [1.5, 0.2, 0.1], [0.0, 0.0, 0.0]], device="cuda")
+    enc_a = torch.randn(1, 32, device="cuda") * 0.5; c = m.individual_codes[2:3].detach(); e = torch.tensor([[0.6]], device="cuda")
+    m.pack()
+    nv = torch.tensor([140001], dtype=torch.int32, device="cuda")
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("B2N_HEAD_WG4", flag)
+        o = [t.clone() for t in m(x, d, enc_a, c, e)]
+        o2 = [t.clone() for t in m(x, d, enc_a, None, None, n_valid=nv, out=tuple(torch.full_like(t, -3.0) for t in o))]
+        outs.append(o + o2)
+    torch.cuda.synchronize()
+    for a_, b_, name in zip(outs[0], outs[1], ("sigma", "rgb", "aud", "eye", "unc") * 2):
+        assert torch.equal(a_, b_), (name, float((a_ - b_).abs().max()))
+    assert bool(torch.isfinite(outs[0][0]).all()) and float(outs[0][1].std()) > 1e-3
