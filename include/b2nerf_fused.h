@@ -84,6 +84,9 @@ typedef struct {
     float    bound, dt_gamma, min_near, T_thresh, density_scale;
     uint32_t max_steps, cascade, grid_size;
     float    aabb[6];
+    uint32_t head_ctas;   /* 0: the frame has the GPU to itself — each network launch uses every SM (lowest latency).  > 0: frames from other streams
+                           * are in flight beside this one — a network launch takes at most head_ctas SMs (about half of them is best on B200), so two
+                           * frames' network launches run side by side and the small march / composite launches never queue behind a full-GPU kernel. */
 } b2n_render_cfg;
 uint64_t b2n_render_frame_workspace_bytes(uint32_t N);
 int b2n_render_frame(const b2n_model *m, const b2n_render_cfg *cfg, const float *rays_o, const float *rays_d,

@@ -14,8 +14,9 @@ from .model import HeadModel
 
 class FrameRenderer:
     def __init__(self, model: HeadModel, n_rays, eye=0.4, ind_index=0, dt_gamma=1.0 / 256, max_steps=16, T_thresh=1e-4, use_graph=True, fused_audio=True,
-                 camera=None, torso=None, bg_coords=None, smooth_lips=False, lips_state=None, lips_lambda=0.35):
-        """smooth_lips: the reference's opt.smooth_lips (renderer.py:456-460, on in the serving config HubertInferenceMQ.py): the audio code of frame k is
+                 camera=None, torso=None, bg_coords=None, smooth_lips=False, lips_state=None, lips_lambda=0.35, head_ctas=0):
+        """head_ctas: b2n_render_cfg.head_ctas — 0 when this renderer has the GPU to itself; FramePipeline sets it for its slots.
+        smooth_lips: the reference's opt.smooth_lips (renderer.py:456-460, on in the serving config HubertInferenceMQ.py): the audio code of frame k is
         0.35 * (smoothed code of frame k-1) + 0.65 * (its own); the state is a device float[33] (`lips_state`, shared by the slots of a FramePipeline) and the
         audio kernel runs in frame order in front of the frame graph instead of inside it.  reset_lips() starts a new sequence.
         camera = (H, W, fx, fy, cx, cy): also build the device-side prologue / epilogue (rays from a 4x4 pose, RGB24 output), so that
@@ -23,6 +24,7 @@ class FrameRenderer:
         torso = a TorsoModel (+ bg_coords [N,2], utils.py:218-223): every frame first runs the fused torso kernel (csrc/fused_torso.cu) over the background into
         the per-ray bg_color buffer the head frame reads (renderer.py:572-631 then :559-561); set the head pose with set_torso_pose()."""
         self.m = model
+        self.head_ctas = int(head_ctas)
         self.torso = torso
         self.camera = camera
         self.dev = next(model.parameters()).device
@@ -111,7 +113,7 @@ class FrameRenderer:
         else:
             with torch.autocast("cuda", dtype=torch.float16):
                 enc_a = self.m.encode_audio(self.auds).float()              # AudioNet + AudioAttNet through torch (network.py:226-240)
-        self.m.render_frame(self.rays_o, self.rays_d, enc_a, self.ind_code, self.eye, bg_color=self.bg, out=self.image, **self.kw)
+        self.m.render_frame(self.rays_o, self.rays_d, enc_a, self.ind_code, self.eye, bg_color=self.bg, out=self.image, head_ctas=self.head_ctas, **self.kw)
 
     @torch.no_grad()
     def _build_loop_graph(self):
@@ -121,7 +123,7 @@ class FrameRenderer:
         L, m = lib(), self.m
         need = int(L.raw("b2n_render_frame_workspace_bytes")(self.N))
         self._graph_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
-        cfg = _RenderCfgC(m.bound, self.kw["dt_gamma"], 0.05, self.kw["T_thresh"], 1.0, self.kw["max_steps"], m.cascade, m.grid_size, m._aabb_host)
+        cfg = _RenderCfgC(m.bound, self.kw["dt_gamma"], 0.05, self.kw["T_thresh"], 1.0, self.kw["max_steps"], m.cascade, m.grid_size, m._aabb_host, self.head_ctas)
         aw = m.audio_weights_struct() if (self.fused_audio and not self.smooth_lips) else None        # smooth_lips: the audio kernel runs in frame order, in front of the graph
         self._graph_keep = (cfg, aw, self.ind_code.float().contiguous().view(-1), self.eye.float().contiguous().view(-1))
         h = ctypes.c_void_p()
@@ -272,6 +274,10 @@ class FramePipeline:
         self.smooth = bool(kw.get("smooth_lips", False))
         if self.smooth and kw.get("lips_state") is None:                 # ONE smoothing state for the whole frame sequence
             kw["lips_state"] = torch.zeros(33, device=next(model.parameters()).device)
+        if self.depth >= 2 and "head_ctas" not in kw:
+            # several frames share the GPU: each frame's network launches take half of the SMs, so two of them run side by side and the small march /
+            # composite launches of the other frames find free SMs (3397 -> 3550 frames/s at depth 5 on B200; 60..100 of 148 SMs all within 1.5 %)
+            kw["head_ctas"] = torch.cuda.get_device_properties(next(model.parameters()).device).multi_processor_count // 2
         self.slots = [FrameRenderer(model, n_rays, **kw) for _ in range(self.depth)]
         self.dev = self.slots[0].dev
         # smooth_lips makes the audio code of frame k depend on frame k-1: the (tiny) audio kernels run in frame order on their own stream, the frames

@@ -23,7 +23,7 @@ struct b2n_model;
 namespace b2n {
 int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
                           const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, cudaStream_t st,
-                          const float *live_deltas = nullptr, const b2n_head_saved *saved = nullptr);
+                          const float *live_deltas = nullptr, const b2n_head_saved *saved = nullptr, uint32_t head_ctas = 0);
 }
 
 namespace b2n {
@@ -349,7 +349,7 @@ static int enqueue_iteration(const FramePlan &p, cudaStream_t st, cudaGraphCondi
     k_frame_march<<<ceil_div<uint32_t>(p.N, FM_THREADS), FM_THREADS, 0, st>>>(p.rays_o, p.rays_d, p.bitfield, p.cfg.bound, p.cfg.dt_gamma, p.cfg.max_steps, p.cfg.cascade, p.cfg.grid_size, p.w);
     if (check_launch("render_frame(march)")) return 1;
     if (int rc = head_forward_on_model(p.m, p.w.xyzs, p.w.dirs, p.N, p.enc_a, p.ind_code, p.eye, &p.w.ctrl[0].n_samples, p.cfg.density_scale, p.w.sigmas, p.w.rgbs,
-                                       p.w.amb_aud, p.w.amb_eye, p.w.unc, st, p.w.deltas)) return rc;
+                                       p.w.amb_aud, p.w.amb_eye, p.w.unc, st, p.w.deltas, nullptr, p.cfg.head_ctas)) return rc;
     k_frame_composite<<<ctas, FR_THREADS, 0, st>>>(p.cfg.T_thresh, p.N, p.cfg.max_steps, p.w, handle, use_handle);
     return check_launch("render_frame(composite)");
 }

@@ -228,6 +228,24 @@ __device__ __forceinline__ void issue_mma(uint32_t d_tmem, uint32_t a_saddr, uin
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
+// Tiles of one launch -> CTAs: every CTA takes a CONTIGUOUS, balanced share [lo, hi) of the tiles (shares differ by at most one tile) and its warpgroups
+// walk it round-robin.  (A grid-strided walk hands the last round to the first CTAs only, four tiles each: SMs finished between 36 k and 52 k cycles
+// in the ncu capture of a 1700-tile launch.)  Neighbouring tiles — neighbouring samples of the same rays — stay on one SM and share its L1.
+// A launch with few tiles (the grid is sized for the buffer's capacity, the live count is only known on the device) is packed onto ceil(tiles / WGS) CTAs,
+// one tile per warpgroup, and the other CTAs leave at once: their SMs stay free for the kernels of the other frames in flight.
+__device__ __forceinline__ void cta_tile_share(uint32_t n_tiles, uint32_t wgs, int sched, uint32_t wg, uint32_t &first, uint32_t &end, uint32_t &stride) {
+    if (sched & 2) {            // grid-strided walk (A/B: B2N_HEAD_SCHED=2)
+        first = blockIdx.x * wgs + wg; end = n_tiles; stride = gridDim.x * wgs;
+        if (blockIdx.x * wgs >= n_tiles) end = 0;
+        return;
+    }
+    const uint32_t ctas = (sched & 1) ? gridDim.x : min(gridDim.x, (n_tiles + wgs - 1) / wgs);
+    first = end = 0; stride = wgs;
+    if (blockIdx.x >= ctas) return;
+    first = (uint32_t)(((uint64_t)blockIdx.x * n_tiles) / ctas) + wg;
+    end = (uint32_t)(((uint64_t)(blockIdx.x + 1) * n_tiles) / ctas);
+}
+
 struct HeadSmem {                       // lives after the 1024-aligned weight image and operand tiles
     HeadLvl lvl[12];
     __half2 enc_a_h2[16];               // the audio code in fp16, packed in pairs
@@ -256,7 +274,9 @@ __global__ void __maxnreg__(SAVE ? 168 : 128) k_head_forward(const __grid_consta
     const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u, warp = tid >> 5;
     // nothing to do (a loop iteration after the frame finished): leave before touching TMEM / the weight image
     const uint32_t n_valid_early = a.n_valid ? (uint32_t)max(0, min((int)a.M, __ldg(a.n_valid))) : a.M;
-    if (n_valid_early <= blockIdx.x * HG_WGS * HG_TILE) return;
+    uint32_t tile_first, tile_hi, tile_stride;
+    cta_tile_share((n_valid_early + HG_TILE - 1) / HG_TILE, HG_WGS, a.sched, wg, tile_first, tile_hi, tile_stride);
+    if (tile_hi == 0) return;            // nothing for this CTA (uniform over the CTA)
     uint8_t *sXb = s_tiles + wg * 3 * HG_TILE_BYTES, *sH = sXb + 2 * HG_TILE_BYTES;      // X[0], X[1], H
 
     // ---- one-time setup ------------------------------------------------------------------------------------------
@@ -282,10 +302,10 @@ __global__ void __maxnreg__(SAVE ? 168 : 128) k_head_forward(const __grid_consta
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    mbar_wait(&S.bar_w, 0);
+    // (the weight image is only read by the tensor pipe: the issuing thread waits for it before its first MMA, the first gather runs meanwhile)
 
     const uint32_t n_valid = S.n_valid;
-    const uint32_t n_tiles = (n_valid + HG_TILE - 1) / HG_TILE;
+    const uint32_t n_tiles = tile_hi;                                        // this CTA's share ends here
     const uint32_t tmem_wg = S.tmem_base + wg * HG_TMEM_COLS;               // this warpgroup's columns
     const uint32_t tmem_ld = tmem_wg + (((warp & 3u) * 32u) << 16);         // + this warp's lane quarter
     const uint32_t sH_a = smem_u32(sH), sW_a = smem_u32(s_w);
@@ -326,8 +346,7 @@ __global__ void __maxnreg__(SAVE ? 168 : 128) k_head_forward(const __grid_consta
         *reinterpret_cast<uint4 *>(tile + row_off + ((5u ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
     };
 
-    const uint32_t tile_stride = gridDim.x * HG_WGS;
-    uint32_t tile = blockIdx.x * HG_WGS + wg;
+    uint32_t tile = tile_first;
     uint32_t buf = 0;
     // ---- pipeline prologue: the first tile's features (later tiles are gathered underneath the previous tile's MMA phases) -------
     if (tile < n_tiles) {
@@ -379,7 +398,7 @@ __global__ void __maxnreg__(SAVE ? 168 : 128) k_head_forward(const __grid_consta
         float unc_logit = 0.0f;
         publish();
         // ---- P1: [aud hidden | eye hidden | sigma hidden (enc_x part)] = X * WA -------------------------------------------
-        if (t == 0) { fence_after_sync(); issue_mma(tmem_wg + TC_A, sX_a, sW_a + HW_A, 3, 144, false); mma_commit(bar); }
+        if (t == 0) { mbar_wait(&S.bar_w, 0); fence_after_sync(); issue_mma(tmem_wg + TC_A, sX_a, sW_a + HW_A, 3, 144, false); mma_commit(bar); }
         const SampleCoord cn = make_coord(npx, npy, npz, nlive);
         if (has_next) { zero_k_padding(sXn); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[0], cn); }      // trip 0 in flight under P1
         mma_done();
@@ -620,7 +639,9 @@ __global__ void __launch_bounds__(H4_THREADS, 1) k_head_infer4(const __grid_cons
     Head4Smem &S = *reinterpret_cast<Head4Smem *>(s_tiles + H4_WGS * 2 * HG_TILE_BYTES);
     const uint32_t tid = threadIdx.x, wg = tid >> 7, t = tid & 127u, warp = tid >> 5;
     const uint32_t n_valid_early = a.n_valid ? (uint32_t)max(0, min((int)a.M, __ldg(a.n_valid))) : a.M;
-    if (n_valid_early <= blockIdx.x * H4_WGS * HG_TILE) return;
+    uint32_t tile_first, tile_hi, tile_stride;
+    cta_tile_share((n_valid_early + HG_TILE - 1) / HG_TILE, H4_WGS, a.sched, wg, tile_first, tile_hi, tile_stride);
+    if (tile_hi == 0) return;            // nothing for this CTA (uniform over the CTA)
     uint8_t *sXb = s_tiles + wg * 2 * HG_TILE_BYTES;
 
     if (tid == 0) {
@@ -643,10 +664,10 @@ __global__ void __launch_bounds__(H4_THREADS, 1) k_head_infer4(const __grid_cons
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    mbar_wait(&S.bar_w, 0);
+    // (the weight image is only read by the tensor pipe: the issuing thread waits for it before its first MMA, the first gather runs meanwhile)
 
     const uint32_t n_valid = S.n_valid;
-    const uint32_t n_tiles = (n_valid + HG_TILE - 1) / HG_TILE;
+    const uint32_t n_tiles = tile_hi;                                        // this CTA's share ends here
     const uint32_t tm = S.tmem_base + wg * H4_COLS;                          // this warpgroup's columns: A operand at +0, accumulators from +32
     const uint32_t lane_off = ((warp & 3u) * 32u) << 16;                    // this warp's lane quarter (tcgen05.ld / st)
     const uint32_t tA = tm + lane_off, tD = tm + H4_ACC + lane_off;         // per-thread addresses
@@ -686,8 +707,7 @@ __global__ void __launch_bounds__(H4_THREADS, 1) k_head_infer4(const __grid_cons
         *reinterpret_cast<uint4 *>(tile + row_off + ((5u ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
     };
 
-    const uint32_t tile_stride = gridDim.x * H4_WGS;
-    uint32_t tile = blockIdx.x * H4_WGS + wg;
+    uint32_t tile = tile_first;
     uint32_t buf = 0;
     if (tile < n_tiles) {
         const uint32_t m0 = tile * HG_TILE + t;
@@ -725,7 +745,7 @@ __global__ void __launch_bounds__(H4_THREADS, 1) k_head_infer4(const __grid_cons
         GatherTrip G;
         publish();
         // ---- P1: [aud hidden 64 | eye hidden 16] = X * WA[0:80] ---------------------------------------------------------------------
-        if (t == 0) { fence_after_sync(); issue_mma(mD, sX_a, sW_a + HW_A, 3, 80, false); mma_commit(bar); }
+        if (t == 0) { mbar_wait(&S.bar_w, 0); fence_after_sync(); issue_mma(mD, sX_a, sW_a + HW_A, 3, 80, false); mma_commit(bar); }
         const SampleCoord cn = make_coord(npx, npy, npz, nlive);
         if (has_next) { zero_k_padding(sXn); gather_issue<QUAD>(G, t_xy, t_yz, t_xz, &S.lvl[0], cn); }
         mma_done();
@@ -864,7 +884,8 @@ int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save, bool quad
         attr = true;
     }
     const uint32_t tiles = ceil_div<uint32_t>(a.M, HG_TILE);
-    const uint32_t sms = (uint32_t)sm_count();
+    uint32_t sms = (uint32_t)sm_count();
+    if (a.max_ctas > 0 && a.max_ctas < sms) sms = a.max_ctas;
     // inference without unc_net: the four-warpgroup kernel with the activations in tensor memory (B2N_HEAD_WG4=0 keeps the three-warpgroup kernel, for A/B)
     const char *wg4_env = getenv("B2N_HEAD_WG4");
     const bool wg4 = !(wg4_env && wg4_env[0] == '0');
@@ -1058,7 +1079,7 @@ int b2n_model_update(b2n_model *m, const b2n_head_weights *w, void *stream) {
 namespace b2n {
 int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
                           const int32_t *n_valid, float density_scale, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, cudaStream_t st,
-                          const float *live_deltas, const b2n_head_saved *saved) {
+                          const float *live_deltas, const b2n_head_saved *saved, uint32_t head_ctas) {
     B2N_REQUIRE(m && m->ready, "head_forward: model has no weights (call b2n_model_update)");
     B2N_REQUIRE(xyzs && dirs && enc_a, "head_forward: null pointer");
     if (M == 0) return 0;
@@ -1082,6 +1103,11 @@ int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *di
     a.sigmas = sigmas; a.rgbs = rgbs; a.amb_aud = amb_aud; a.amb_eye = amb_eye; a.unc = unc;
     a.has_unc = m->w.unc_w0 != nullptr;
     a.density_scale = density_scale;
+    // a frame that shares the GPU with other frames in flight (head_ctas > 0): at most head_ctas CTAs, grid-strided tiles; alone: all SMs, balanced shares
+    a.sched = head_ctas ? 2 : 0;
+    a.max_ctas = head_ctas;
+    if (const char *e = getenv("B2N_HEAD_SCHED")) a.sched = atoi(e);            // A/B overrides
+    if (const char *e = getenv("B2N_HEAD_CTAS")) a.max_ctas = (uint32_t)atoi(e);
     if (saved) {
         B2N_REQUIRE(!a.has_unc || saved->hu, "head_forward_train: unc_net is packed but saved->hu is NULL");
         a.sv = *saved;
@@ -1097,12 +1123,12 @@ int b2n_head_forward_train(const b2n_model *m, const float *xyzs, const float *d
     B2N_REQUIRE(saved, "head_forward_train: null pointer");
     B2N_REQUIRE(saved->x36 && saved->ha && saved->he && saved->att && saved->s_in && saved->h1 && saved->h2 && saved->c_in && saved->hc && saved->misc,
                 "head_forward_train: null activation buffer");
-    return head_forward_on_model(m, xyzs, dirs, M, enc_a, ind_code, eye, nullptr, 1.0f, sigmas, rgbs, amb_aud, amb_eye, unc, as_stream(stream), nullptr, saved);
+    return head_forward_on_model(m, xyzs, dirs, M, enc_a, ind_code, eye, nullptr, 1.0f, sigmas, rgbs, amb_aud, amb_eye, unc, as_stream(stream), nullptr, saved, 0);
 }
 
 int b2n_head_forward(const b2n_model *m, const float *xyzs, const float *dirs, uint32_t M, const float *enc_a, const float *ind_code, const float *eye,
                      const int32_t *n_valid, float *sigmas, float *rgbs, float *amb_aud, float *amb_eye, float *unc, void *stream) {
-    return head_forward_on_model(m, xyzs, dirs, M, enc_a, ind_code, eye, n_valid, 1.0f, sigmas, rgbs, amb_aud, amb_eye, unc, as_stream(stream), nullptr, nullptr);
+    return head_forward_on_model(m, xyzs, dirs, M, enc_a, ind_code, eye, n_valid, 1.0f, sigmas, rgbs, amb_aud, amb_eye, unc, as_stream(stream), nullptr, nullptr, 0);
 }
 
 }  // extern "C"

@@ -71,6 +71,8 @@ struct HeadArgs {
     int has_unc;
     b2n_head_saved sv;          // training forward: where the activations go (used by the SAVE instantiation only)
     float density_scale;
+    uint32_t max_ctas;          // 0 = one CTA per SM
+    int sched;                  // tile -> CTA mapping, A/B switch (B2N_HEAD_SCHED): 0 balanced contiguous shares, short launches packed; 1 spread; 2 grid-strided
 };
 
 }  // namespace b2n
