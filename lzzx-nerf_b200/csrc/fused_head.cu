@@ -1103,8 +1103,8 @@ int head_forward_on_model(const b2n_model *m, const float *xyzs, const float *di
     a.sigmas = sigmas; a.rgbs = rgbs; a.amb_aud = amb_aud; a.amb_eye = amb_eye; a.unc = unc;
     a.has_unc = m->w.unc_w0 != nullptr;
     a.density_scale = density_scale;
-    // a frame that shares the GPU with other frames in flight (head_ctas > 0): at most head_ctas CTAs, grid-strided tiles; alone: all SMs, balanced shares
-    a.sched = head_ctas ? 2 : 0;
+    // a frame that shares the GPU with other frames in flight (head_ctas > 0): at most head_ctas CTAs, grid-strided tiles; a frame alone: all SMs, balanced shares
+    a.sched = (head_ctas || saved) ? 2 : 0;      // training: the grid-strided walk measured 2 % faster per step (neighbouring tiles run at the same time on different SMs and share the L2)
     a.max_ctas = head_ctas;
     if (const char *e = getenv("B2N_HEAD_SCHED")) a.sched = atoi(e);            // A/B overrides
     if (const char *e = getenv("B2N_HEAD_CTAS")) a.max_ctas = (uint32_t)atoi(e);

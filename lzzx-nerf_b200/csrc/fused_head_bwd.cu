@@ -143,9 +143,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) k_head_backward(const __grid_co
     auto mma_done = [&]() { mbar_wait(bar, phase); phase ^= 1u; fence_after_sync(); };
     auto publish = [&]() { fence_before_sync(); fence_proxy_async(); sync_wg(); };
 
-    // balanced contiguous share of the tiles per CTA (see cta_tile_share in fused_head.cu), warpgroups round-robin inside it
-    const uint32_t tile_lo = (uint32_t)(((uint64_t)blockIdx.x * n_tiles) / gridDim.x), tile_hi = (uint32_t)(((uint64_t)(blockIdx.x + 1) * n_tiles) / gridDim.x);
-    for (uint32_t tile = tile_lo + wg; tile < tile_hi; tile += BW_WGS) {
+    for (uint32_t tile = blockIdx.x * BW_WGS + wg; tile < n_tiles; tile += gridDim.x * BW_WGS) {
         const size_t m = (size_t)tile * HG_TILE + t;
         const bool live = m < a.M;
         const size_t tile_row0 = (size_t)tile * HG_TILE;
