@@ -123,8 +123,8 @@ class _FusedHead(torch.autograd.Function):
 _SIDE_STREAMS = {}
 
 
-def _side_stream(dev):
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+def _side_stream(dev, which=0):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), which)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
     return _SIDE_STREAMS[key]
@@ -369,11 +369,17 @@ class _FusedHeadAudio(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, model, x, d, auds, ind_code, eye, n_head, *params):
-        auds = auds.contiguous()
-        aw = model.audio_weights_struct()
-        enc_a = torch.empty(1, 32, dtype=torch.float32, device=auds.device)
-        lib().call("b2n_audio_encode", ctypes.byref(aw), auds.data_ptr(), auds.shape[2], enc_a.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    def forward(ctx, model, x, d, auds, ind_code, eye, n_head, ahead, *params):
+        if ahead is not None:                                  # audio_encode_ahead: already running (or done) on its side stream
+            aw, auds, enc_a, side = ahead
+            cur = torch.cuda.current_stream(auds.device)
+            cur.wait_stream(side)
+            enc_a.record_stream(cur)
+        else:
+            auds = auds.contiguous()
+            aw = model.audio_weights_struct()
+            enc_a = torch.empty(1, 32, dtype=torch.float32, device=auds.device)
+            lib().call("b2n_audio_encode", ctypes.byref(aw), auds.data_ptr(), auds.shape[2], enc_a.data_ptr(), torch.cuda.current_stream().cuda_stream)
         sig, rgb, aud, eye_att, unc, saved = model.forward_train_fused(x, d, enc_a, ind_code, eye)
         ctx.model, ctx.saved_acts, ctx.with_unc = model, saved, "hu" in saved
         ctx.audio = (aw, auds)
@@ -386,13 +392,27 @@ class _FusedHeadAudio(torch.autograd.Function):
     @custom_bwd(device_type="cuda")
     def backward(ctx, g_sig, g_rgb, g_aud, g_eye, g_unc):
         _, d_ind, head, audio = _head_backward(ctx, g_sig, g_rgb, g_aud, g_eye, g_unc, audio=ctx.audio)
-        return (None, None, None, None, d_ind, None, None, *head, *audio)
+        return (None, None, None, None, d_ind, None, None, None, *head, *audio)
 
 
-def fused_head_audio_train(model, x, d, auds, ind_code, eye):
+def audio_encode_ahead(model, auds, cur):
+    """Start encode_audio(auds) on a side stream forked from `cur` (the audio code does not depend on the step's rays: it runs beside the marcher).
+    Returns the handle fused_head_audio_train(ahead=...) joins."""
+    dev = auds.device
+    auds = auds.contiguous()
+    aw = model.audio_weights_struct()
+    side = _side_stream(dev, 2)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        enc_a = torch.empty(1, 32, dtype=torch.float32, device=dev)
+        lib().call("b2n_audio_encode", ctypes.byref(aw), auds.data_ptr(), auds.shape[2], enc_a.data_ptr(), side.cuda_stream)
+    return aw, auds, enc_a, side
+
+
+def fused_head_audio_train(model, x, d, auds, ind_code, eye, ahead=None):
     """encode_audio(auds) -> forward(x, d, enc_a, ind_code, eye) in a training step, both directions on the fused kernels (att > 0)."""
     hp = head_parameters(model)
-    sig, rgb, aud, eye_att, unc = _FusedHeadAudio.apply(model, x, d, auds, ind_code.view(-1), eye, len(hp), *hp, *audio_parameters(model))
+    sig, rgb, aud, eye_att, unc = _FusedHeadAudio.apply(model, x, d, auds, ind_code.view(-1), eye, len(hp), ahead, *hp, *audio_parameters(model))
     return sig, rgb, aud[:, None], eye_att[:, None], unc[:, None, None]
 
 
