@@ -39,6 +39,11 @@ template <typename T> inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
 // SM count of the current device (cached); grids for grid-stride kernels are sized in multiples of it
 int sm_count();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: remembered per (device, kernel) and raised when a launch asks for more,
+// so a process that drives several GPUs configures each of them (a process-wide `static bool` would configure only the first).  0 = ok.
+int ensure_dynamic_smem_impl(const void *kernel, size_t bytes);
+template <typename K> inline int ensure_dynamic_smem(K kernel, size_t bytes) { return ensure_dynamic_smem_impl(reinterpret_cast<const void *>(kernel), bytes); }
+#define B2N_SMEM(kernel, bytes) do { if (int rc__ = b2n::ensure_dynamic_smem(kernel, bytes)) return rc__; } while (0)
 // library-internal device scratch (grow-only, per device); never exposed to the caller
 void *scratch(size_t bytes, int slot);
 

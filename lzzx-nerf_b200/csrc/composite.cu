@@ -368,10 +368,9 @@ static int launch_train_fwd(const char *what, const float *sigmas, const float *
     B2N_REQUIRE(sigmas && rgbs && deltas && rays && ws && depth && image, "%s: null pointer", what);
     B2N_REQUIRE((NA < 1 || (amb0 && a0s)) && (NA < 2 || (amb1 && a1s)) && (!UNC || (unc && us)), "%s: null pointer", what);
     if (N == 0) return 0;
-    static bool attr_done = false;
     const size_t smem = Stage<NA, UNC>::BYTES;
     auto kern = k_comp_train_fwd<AMB, NA, UNC>;
-    if (!attr_done) { B2N_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    B2N_SMEM(kern, smem);
     kern<<<ceil_div<uint32_t>(N, CT_THREADS), CT_THREADS, smem, as_stream(stream)>>>(sigmas, rgbs, amb0, amb1, unc, deltas, rays, M, N, T_thresh,
                                                                                      ws, a0s, a1s, us, depth, image);
     return check_launch(what);
@@ -386,10 +385,9 @@ static int launch_train_bwd(const char *what, const float *g_ws, const float *g_
     B2N_REQUIRE((NA < 1 || (g_a0 && ga0)) && (NA < 2 || (g_a1 && ga1)) && (!UNC || (g_u && unc && us && gu)) && (AMB != 2 || (amb0 && a0s)),
                 "%s: null pointer", what);
     if (N == 0) return 0;
-    static bool attr_done = false;
     const size_t smem = Stage<NA, UNC>::BYTES;
     auto kern = k_comp_train_bwd<AMB, NA, UNC>;
-    if (!attr_done) { B2N_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    B2N_SMEM(kern, smem);
     kern<<<ceil_div<uint32_t>(N, CT_THREADS), CT_THREADS, smem, as_stream(stream)>>>(g_ws, g_a0, g_a1, g_u, g_img, sigmas, rgbs, amb0, unc, deltas, rays,
                                                                                      ws, a0s, us, image, M, N, T_thresh, gs, grgb, ga0, ga1, gu);
     return check_launch(what);

@@ -1,6 +1,8 @@
 // core.cu — library plumbing: error string, launch counter, SM count, internal scratch.
 #include "common.cuh"
+#include <map>
 #include <mutex>
+#include <utility>
 #include <string.h>
 
 namespace b2n {
@@ -25,6 +27,21 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+int ensure_dynamic_smem_impl(const void *kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return 0;           // the default limit needs no opt-in
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> configured;
+    int dev = 0;
+    B2N_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &have = configured[{dev, kernel}];
+    if (have < bytes) {
+        B2N_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return 0;
 }
 
 // Grow-only per-device scratch slots for the entry points that keep the reference's argument lists (no workspace parameter).  Growth happens only when a call

@@ -116,8 +116,7 @@ static int sh_launch(const float *inputs, float *outputs, uint32_t B, uint32_t D
     const uint32_t ctas = ceil_div<uint32_t>(B, SH_ROWS);
     if (dy_dx) {
         const size_t smem = sizeof(float) * 4 * SH_ROWS * LD;
-        static bool attr = false;
-        if (!attr) { B2N_CUDA(cudaFuncSetAttribute(k_sh_fwd<DEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        B2N_SMEM((k_sh_fwd<DEG, true>), smem);
         k_sh_fwd<DEG, true><<<ctas, SH_ROWS, smem, st>>>(sh_consts(), inputs, outputs, B, D, dy_dx);
     } else {
         k_sh_fwd<DEG, false><<<ctas, SH_ROWS, sizeof(float) * SH_ROWS * LD, st>>>(sh_consts(), inputs, outputs, B, D, nullptr);

@@ -388,8 +388,7 @@ extern "C" int b2n_audio_encode_smooth(const b2n_audio_weights *w, const float *
     B2N_REQUIRE(li == 1, "audio_encode: window length %u does not reduce to 1 after four stride-2 convolutions", L);
     AudioArgs a = {*w, auds, L, enc_a, lips_state, lambda, (float)(1.0 - (double)lambda)};
     const size_t smem = sizeof(float) * ((size_t)w->dim_in * Lw + 1024 + AW_TOTAL);       // input slice + ping / pong + the weight cache (121 KB)
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(k_audio_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    B2N_SMEM(k_audio_encode, smem);
     k_audio_encode<<<AU_FRAMES, AU_THREADS, smem, as_stream(stream)>>>(a);
     return check_launch("audio_encode");
 }
@@ -407,8 +406,7 @@ extern "C" int b2n_audio_backward(const b2n_audio_weights *w, const float *auds,
     B2N_REQUIRE(li == 1, "audio_backward: window length %u does not reduce to 1 after four stride-2 convolutions", L);
     AudioBwdArgs a = {*w, *g, auds, L, d_enc_a};
     const size_t smem = sizeof(float) * ((size_t)w->dim_in * Lw + 256 + 128 + 128 + 64 + 64 + 512 + 512);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(k_audio_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    B2N_SMEM(k_audio_backward, smem);
     k_audio_backward<<<AU_FRAMES, AU_THREADS, smem, as_stream(stream)>>>(a);
     return check_launch("audio_backward");
 }

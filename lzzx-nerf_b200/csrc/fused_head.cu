@@ -8,15 +8,18 @@
 // Numerics follow the reference under autocast(fp16): GEMM operands and activations are fp16, accumulation fp32
 // (TMEM), exp / norm / softplus in fp32, sigmoid in fp16.
 //
-// Organisation (B200):
-//   * persistent CTA per SM, 512 threads = 4 warpgroups; each warpgroup owns one 128-sample tile at a time, its own
-//     128 TMEM columns and two 16 KB operand buffers (X, H).  The four tiles desynchronise and overlap gather,
-//     tensor and epilogue work on the SM.
-//   * all weights (fp16, pre-swizzled K-major SWIZZLE_128B image, 70 KB) are brought in once per CTA by one TMA bulk
-//     copy and stay resident; every layer is a tcgen05.mma (M=128 samples, N=16..112, K=16 per instruction) issued by
-//     one thread per warpgroup with the accumulator in TMEM; epilogues read TMEM with tcgen05.ld (thread == sample
-//     row), apply the activation and write the next layer's fp16 operand straight back to shared memory.
-//   * the gather (144 table reads per sample) reads the fp32 tables through L1/L2 with paired corner loads.
+// Organisation (B200) — two kernels share the gather, the weight image and the layer arithmetic:
+//   * k_head_forward<SAVE, QUAD> (training forward with kept activations; inference when unc_net is evaluated): persistent CTA per SM, 384 threads =
+//     3 warpgroups; a warpgroup owns one 128-sample tile at a time, 160 TMEM columns and three 16 KB SWIZZLE_128B operand tiles (two feature tiles,
+//     double-buffered, and one hidden-activation tile); epilogues read TMEM with tcgen05.ld (thread == sample row), apply the activation and write
+//     the next layer's fp16 operand to shared memory.
+//   * k_head_infer4<QUAD> (inference): 512 threads = 4 warpgroups, 128 TMEM columns each; the hidden activations never leave tensor memory — the
+//     epilogue writes the next layer's A operand back with tcgen05.st and the layer is a TMEM-A tcgen05.mma (see the comment at the kernel).
+//   * all weights (fp16, pre-swizzled K-major SWIZZLE_128B image, 70 KB) are brought in once per CTA by one TMA bulk copy and stay resident; every
+//     layer is a tcgen05.mma (M=128 samples, N=16..144, K=16 per instruction) issued by one thread per warpgroup, accumulator in TMEM, completion
+//     through tcgen05.commit -> mbarrier.
+//   * the gather reads ONE 16-byte corner quad per (level, plane) cell from the quad image (36 LDG.128 per sample), six trips of the NEXT tile's
+//     gather in flight underneath the CURRENT tile's MMA phases.
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc5.cuh"
@@ -874,15 +877,11 @@ size_t head4_smem_bytes() { return 1024 + HW_BYTES + (size_t)H4_WGS * 2 * HG_TIL
 size_t head_smem_bytes() { return 1024 + HW_BYTES + (size_t)HG_WGS * 3 * HG_TILE_BYTES + sizeof(HeadSmem); }
 
 int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save, bool quad) {
-    static bool attr = false;
     const size_t smem = head_smem_bytes();
-    if (!attr) {
-        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B2N_CUDA(cudaFuncSetAttribute(k_head_forward<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    B2N_SMEM((k_head_forward<false, false>), smem);
+    B2N_SMEM((k_head_forward<true, false>), smem);
+    B2N_SMEM((k_head_forward<false, true>), smem);
+    B2N_SMEM((k_head_forward<true, true>), smem);
     const uint32_t tiles = ceil_div<uint32_t>(a.M, HG_TILE);
     uint32_t sms = (uint32_t)sm_count();
     if (a.max_ctas > 0 && a.max_ctas < sms) sms = a.max_ctas;
@@ -891,8 +890,8 @@ int launch_head_forward(const HeadArgs &a, cudaStream_t st, bool save, bool quad
     const bool wg4 = !(wg4_env && wg4_env[0] == '0');
     if (!save && !a.has_unc && wg4) {
         const size_t smem4 = head4_smem_bytes();
-        B2N_CUDA(cudaFuncSetAttribute(k_head_infer4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-        B2N_CUDA(cudaFuncSetAttribute(k_head_infer4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        B2N_SMEM(k_head_infer4<false>, smem4);
+        B2N_SMEM(k_head_infer4<true>, smem4);
         uint32_t c4 = ceil_div<uint32_t>(tiles, H4_WGS);
         if (c4 > sms) c4 = sms;
         if (c4 == 0) return 0;

@@ -377,8 +377,7 @@ extern "C" int b2n_head_backward(const b2n_model *m, uint32_t M, const float *en
     a.sigmas = sigmas; a.amb_aud = amb_aud; a.g_sigma = g_sigma; a.g_rgb = g_rgb; a.g_aud = g_aud; a.g_eye = g_eye; a.g_unc = g_unc;
     a.has_unc = has_unc;
     const size_t smem = 1024 + HT_BYTES + (size_t)BW_WGS * 2 * HG_TILE_BYTES + sizeof(BwdSmem);
-    static bool attr = false;
-    if (!attr) { B2N_CUDA(cudaFuncSetAttribute(k_head_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    B2N_SMEM(k_head_backward, smem);
     uint32_t ctas = ceil_div<uint32_t>(ceil_div<uint32_t>(M, HG_TILE), BW_WGS);
     const uint32_t sms = (uint32_t)sm_count();
     if (ctas > sms) ctas = sms;

@@ -613,7 +613,7 @@ extern "C" int b2n_torso_backward(const b2n_torso_weights *w, const float *bg_co
     uint32_t ctas = 3u * (uint32_t)sm_count();
     if (ctas > tiles) ctas = tiles;
     const size_t dyn = sizeof(float) * (TS_H + TS_ENC + 2) * TS_THREADS;
-    B2N_CUDA(cudaFuncSetAttribute(k_torso_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));      // (per device: set on every call, it is cheap)
+    B2N_SMEM(k_torso_backward, dyn);
     k_torso_backward<<<ctas, TS_THREADS, dyn, as_stream(stream)>>>(b);
     return check_launch("torso_backward");
 }

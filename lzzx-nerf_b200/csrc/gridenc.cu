@@ -630,10 +630,9 @@ static uint32_t largest_level_entries(const int32_t *offsets, uint32_t L, cudaSt
 template <uint32_t D, uint32_t C>
 static int launch_bwd_priv(const float *grad, const float *inputs, const int32_t *offsets, float *gtab, uint32_t B, uint32_t L, float S, uint32_t H,
                            uint32_t gridtype, bool ac, uint32_t smem_floats, cudaStream_t st) {
-    static size_t smem_set = 0;
     const size_t smem = sizeof(float) * (size_t)smem_floats;
     auto kern = k_grid_bwd_priv<D, C>;
-    if (smem > 48 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    B2N_SMEM(kern, smem);
     uint32_t slices = 3u * (uint32_t)sm_count() / L;          // three 512-thread CTAs per SM (64 KB of shared memory each for the tri-plane levels)
     if (const char *e = getenv("B2N_GRID_BWD_SLICES")) slices = (uint32_t)atoi(e);
     const uint32_t cap = ceil_div<uint32_t>(B, 2048);           // at least two rounds of the CTA per slice
@@ -795,8 +794,7 @@ int b2n_triplane_grid_backward(const float *grad_planes, const float *xyz, const
     if (fixed_point && mx != 0 && (size_t)mx * sizeof(int2) <= 200 * 1024) {
         // fixed-point privatisation: 8 bytes per slot, one 1024-thread CTA per SM
         const size_t smem = sizeof(int2) * (size_t)mx;
-        static size_t smem_set = 0;
-        if (smem > 32 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(k_triplane_bwd_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+        B2N_SMEM(k_triplane_bwd_fix, smem);
         uint32_t slices = 2u * (uint32_t)sm_count() / (3u * L);        // two waves of (slice, level, plane) CTAs
         if (const char *e = getenv("B2N_GRID_BWD_SLICES")) slices = (uint32_t)atoi(e);
         const uint32_t cap = ceil_div<uint32_t>(M, 4096);
@@ -817,8 +815,7 @@ int b2n_triplane_grid_backward(const float *grad_planes, const float *xyz, const
     }
     uint32_t fl = (mx != 0 && (size_t)mx * sizeof(float) <= 160 * 1024) ? mx : 0;       // 0: every level scatters straight to global memory
     const size_t smem = sizeof(float) * (size_t)fl;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) { B2N_CUDA(cudaFuncSetAttribute(k_triplane_bwd_priv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    B2N_SMEM(k_triplane_bwd_priv, smem);
     uint32_t slices = 3u * (uint32_t)sm_count() / (3u * L);
     if (const char *e = getenv("B2N_GRID_BWD_SLICES")) slices = (uint32_t)atoi(e);
     const uint32_t cap = ceil_div<uint32_t>(M, 2048);

@@ -7,7 +7,8 @@
 //           + sf * lambda_amb * mean_n (aud_sum * (1 - face))                                                                    (:318-324)
 //           + sf * lambda_amb * mean_n (eye_sum / max_steps * aud_sum.detach() * face)                                           (:326-331)
 // with H2(a) = -a log2 a - (1 - a) log2 (1 - a).  The reference builds this from ~60 elementwise / reduction kernels over 65 536 rays and autograd
-// replays as many backwards; here: one single-CTA pass for the softmax statistics, one pass for the loss, one for all five gradients.
+// replays as many backwards; here: a 64-CTA pass for the partial softmax statistics (folded by every CTA of the next two kernels), one pass for the loss,
+// one for all five gradients.
 // step_factor is read from the device so a CUDA graph of the step can be replayed while it ramps.
 #include "common.cuh"
 

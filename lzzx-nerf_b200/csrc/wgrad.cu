@@ -515,16 +515,14 @@ static int wgrad_launch(const void *dy, const void *x, uint32_t M, uint32_t out_
     B2N_REQUIRE(((uintptr_t)dy & 1) == 0 && ((uintptr_t)x & 1) == 0, "linear_wgrad: operands must be 2-byte aligned");
     if (M == 0) return 0;
     uint32_t ctas_per_sm = 3;           // 66 KB of operand buffers + 34 registers: three resident CTAs per SM hide the per-chunk load latency
-    static bool attr = false;
-    if (!attr) { B2N_CUDA(cudaFuncSetAttribute(k_linear_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM)); attr = true; }
+    B2N_SMEM(k_linear_wgrad, WG_SMEM);
     if (const char *g = getenv("B2N_WGRAD_CTAS_PER_SM")) ctas_per_sm = (uint32_t)atoi(g);
     const uint32_t n_chunks = ceil_div<uint32_t>(M, WG_CHUNK);
     uint32_t ctas = ctas_per_sm * (uint32_t)sm_count();
     if (ctas > n_chunks) ctas = n_chunks;
     const uint32_t va = vec_width(dy, out_dim), vb = vec_width(x, in_dim);
     if (va == 8 && vb == 8 && !getenv("B2N_WGRAD_SIMPLE")) {              // 16-byte aligned operands: cp.async ring, one CTA per SM
-        static bool attr_p = false;
-        if (!attr_p) { B2N_CUDA(cudaFuncSetAttribute(k_linear_wgrad_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WP_SMEM)); attr_p = true; }
+        B2N_SMEM(k_linear_wgrad_pipe, WP_SMEM);
         uint32_t g = (uint32_t)sm_count();
         if (g > n_chunks) g = n_chunks;
         k_linear_wgrad_pipe<<<g, WP_THREADS, WP_SMEM, as_stream(stream)>>>((const __half *)dy, (const __half *)x, M, out_dim, in_dim, dw, replicas, rstride);
@@ -549,8 +547,7 @@ extern "C" int b2n_linear_wgrad_batch(const b2n_wgrad_job *jobs, uint32_t n_jobs
         B2N_REQUIRE(replicas == 1 || replica_stride >= q.out_dim * q.in_dim, "linear_wgrad_batch: replica stride smaller than matrix %u", i);
         J.j[i] = q;
     }
-    static bool attr = false;
-    if (!attr) { B2N_CUDA(cudaFuncSetAttribute(k_linear_wgrad_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM)); attr = true; }
+    B2N_SMEM(k_linear_wgrad_multi, WM_SMEM);
     const uint32_t n_chunks = ceil_div<uint32_t>(M, WG_CHUNK);
     uint32_t g = (uint32_t)sm_count();
     if (g > n_chunks) g = n_chunks;
