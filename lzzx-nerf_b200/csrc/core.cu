@@ -30,7 +30,7 @@ int sm_count() {
 }
 
 int ensure_dynamic_smem_impl(const void *kernel, size_t bytes) {
-    if (bytes <= 48 * 1024) return 0;           // the default limit needs no opt-in
+    // (no shortcut for small sizes: static + dynamic shared memory together may exceed the 48 KB default even when the dynamic part alone does not)
     static std::mutex mu;
     static std::map<std::pair<int, const void *>, size_t> configured;
     int dev = 0;
