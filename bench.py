@@ -161,7 +161,7 @@ def run_reference_arm(args, rank):
                                "subset of the frame's rows and scaled by rows"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
@@ -478,7 +478,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "e2e_rays_in_float_out": e2e_rays,
         "gpu_launches": gpu_launches,
         "clocks": clocks,
-        "roofline": {"kernel": "k_head_forward (fused tri-plane gather + 7 tcgen05 layers)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "roofline": {"kernel": "k_head_infer4 (fused tri-plane gather + 7 tcgen05 layers, activations in tensor memory)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": pk_src + " (bf16 burst: the launches are timed alone)",
                      "how": f"average launch duration from CUDA events on the launching stream (5 back-to-back repeats per launch) for each of the "
                             f"{head_launches} head launches of {min(args.steps, 8)} frames, separate un-graphed pass of the same frames; "
@@ -505,10 +505,30 @@ def run_gpu_arm(args, rank, world, local_rank):
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{rows} rows of one 512x512 frame at an even stride of {ROW_STRIDE} ({rows * HW} rays, {ns} samples, x{ROW_STRIDE} extrapolation), "
                                           f"mean of 2 after 1 warm-up, pure-PyTorch fp32 (oracle/torch_port.py)"}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when the first communicator is made), so
+    file descriptor 1 is pointed at stderr for the whole run and the JSON line alone goes to the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
