@@ -17,27 +17,34 @@
 // threads walk their ray out of shared memory, and the backward writes its per-sample gradients back through
 // the same staging buffer with bulk stores — so HBM sees each algorithmic byte exactly once.  Foreign `rays` orderings (the reference's atomic allocation)
 // take the direct global-memory path of the same template.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc5.cuh"
 
 namespace b2n {
 
 constexpr int CT_THREADS = 128;
-constexpr int CT_CAP = 2048;            // staged samples per CTA (128 rays x 16 steps)
+constexpr int CT_CAP_DEFAULT = 1024;    // samples staged per PASS (runtime `cap`): 37 KB for the triplane variant -> six CTAs per SM.  A CTA whose 128 rays hold more
+                                        // samples takes several passes over groups of consecutive rows (the reservation used to be the worst case, 128 rays x 16 steps
+                                        // = 74 KB, three CTAs per SM, while the average tile needs half of it: ncu showed 12 latency-bound warps per SM)
 
 constexpr int CT_PAD = 4;               // floats of slack per staged array (a span keeps its source's 16-byte phase)
 
 template <int NA, bool UNC> struct Stage {
     // floats per staged sample: sigma 1, deltas 2, rgb 3, ambient NA, unc
     static constexpr int FLOATS = 6 + NA + (UNC ? 1 : 0);
-    static constexpr size_t BYTES = sizeof(float) * ((size_t)FLOATS * CT_CAP + 6 * CT_PAD);
+    static size_t bytes(uint32_t cap) { return sizeof(float) * ((size_t)FLOATS * cap + 6 * CT_PAD); }
 };
+static uint32_t stage_cap() {           // B2N_COMP_CAP: measurement switch
+    static const uint32_t cap = [] { const char *e = getenv("B2N_COMP_CAP"); const int v = e ? atoi(e) : 0; return (uint32_t)((v >= 64 && v <= 4096) ? (v & ~3) : CT_CAP_DEFAULT); }();
+    return cap;
+}
 
 // exp(-sigma*delta) exactly as nvcc emits __expf(-s*d) for the reference: (s*d) * -log2(e) -> ex2.approx
 __device__ __forceinline__ float alpha_of(float sigma, float delta) { return __fsub_rn(1.0f, __expf(-__fmul_rn(sigma, delta))); }
 
 // CTA-wide: decide whether the valid segments of this CTA's rows tile [lo, lo+total) in row order.
-// Returns true (uniformly) if so and total <= CT_CAP; fills lo/total.
+// Returns true (uniformly) if so and total > 0; fills lo / total / slot (= samples of the CTA's earlier rows).
 __device__ __forceinline__ bool cta_tiling(bool valid, uint32_t off, uint32_t num, uint32_t &lo, uint32_t &total, uint32_t &slot) {
     __shared__ uint32_t s_w[CT_THREADS / 32];
     __shared__ uint32_t s_lo;
@@ -57,7 +64,29 @@ __device__ __forceinline__ bool cta_tiling(bool valid, uint32_t off, uint32_t nu
     __syncthreads();
     lo = s_lo; total = tot; slot = before;
     const bool ok = !valid || (off == lo + before);
-    return __syncthreads_and(ok) && tot <= CT_CAP && tot > 0;
+    return __syncthreads_and(ok) && tot > 0;
+}
+
+// The next group of consecutive rows whose samples [base, end) fit `cap` staged samples; returns end (uniform over the CTA).  end == base: the row that starts
+// at `base` alone is longer than the staging capacity.
+__device__ __forceinline__ uint32_t group_end(bool valid, uint32_t slot, uint32_t cnt, uint32_t base, uint32_t total, uint32_t cap) {
+    __shared__ uint32_t s_end;
+    if (threadIdx.x == 0) s_end = total;
+    __syncthreads();
+    if (valid && slot >= base && slot + cnt > base + cap) atomicMin(&s_end, slot);
+    __syncthreads();
+    const uint32_t e = s_end;
+    __syncthreads();                           // (the next call resets s_end)
+    return e;
+}
+// end of the single over-long row that starts at `base` (uniform)
+__device__ __forceinline__ uint32_t long_row_end(bool mine, uint32_t slot, uint32_t cnt) {
+    __shared__ uint32_t s_next;
+    if (mine) s_next = slot + cnt;
+    __syncthreads();
+    const uint32_t e = s_next;
+    __syncthreads();
+    return e;
 }
 
 // A staged span: `count` floats of global memory mirrored in shared memory AT THE SAME 16-BYTE PHASE, so its interior moves as one TMA
@@ -127,7 +156,7 @@ template <int AMB, int NA, bool UNC>
 __global__ void __launch_bounds__(CT_THREADS) k_comp_train_fwd(
         const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ amb0,
         const float *__restrict__ amb1, const float *__restrict__ unc, const float *__restrict__ deltas,
-        const int32_t *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
+        const int32_t *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh, uint32_t cap,
         float *__restrict__ weights_sum, float *__restrict__ amb0_sum, float *__restrict__ amb1_sum,
         float *__restrict__ unc_sum, float *__restrict__ depth, float *__restrict__ image) {
     extern __shared__ __align__(16) float sm[];
@@ -138,57 +167,88 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_fwd(
     __shared__ __align__(8) uint64_t s_bar;
     if (threadIdx.x == 0) { tc5::mbar_init(&s_bar, 1); tc5::fence_mbar_init(); }
     uint32_t lo, total, slot;
-    const bool staged = cta_tiling(valid, off, num, lo, total, slot);       // (its barriers also publish the mbarrier init)
+    const bool tiled = cta_tiling(valid, off, num, lo, total, slot);        // (its barriers also publish the mbarrier init)
     float ws = 0, a0 = 0, a1 = 0, u = 0, d = 0, r = 0, g = 0, b = 0;
-    if (staged) {
-        float *b_sg = sm, *b_dl = b_sg + CT_CAP + CT_PAD, *b_rgb = b_dl + 2 * CT_CAP + CT_PAD, *b_a0 = b_rgb + 3 * CT_CAP + CT_PAD;
-        float *b_a1 = b_a0 + (NA >= 1 ? CT_CAP + CT_PAD : 0), *b_u = b_a1 + (NA >= 2 ? CT_CAP + CT_PAD : 0);
-        const Span p_sg = span_of(b_sg, sigmas + lo, total), p_dl = span_of(b_dl, deltas + 2 * (size_t)lo, 2 * total);
-        const Span p_rgb = span_of(b_rgb, rgbs + 3 * (size_t)lo, 3 * total);
-        const Span p_a0 = NA >= 1 ? span_of(b_a0, amb0 + lo, total) : Span{b_a0, 0, 0, 0};
-        const Span p_a1 = NA >= 2 ? span_of(b_a1, amb1 + lo, total) : Span{b_a1, 0, 0, 0};
-        const Span p_u = UNC ? span_of(b_u, unc + lo, total) : Span{b_u, 0, 0, 0};
-        if (threadIdx.x == 0) tc5::mbar_expect_tx(&s_bar, 4u * (p_sg.body + p_dl.body + p_rgb.body + p_a0.body + p_a1.body + p_u.body));
-        span_load(p_sg, sigmas + lo, &s_bar);
-        span_load(p_dl, deltas + 2 * (size_t)lo, &s_bar);
-        span_load(p_rgb, rgbs + 3 * (size_t)lo, &s_bar);
-        if (NA >= 1) span_load(p_a0, amb0 + lo, &s_bar);
-        if (NA >= 2) span_load(p_a1, amb1 + lo, &s_bar);
-        if (UNC) span_load(p_u, unc + lo, &s_bar);
-        __syncthreads();                       // edge floats
-        tc5::mbar_wait(&s_bar, 0);             // bulk interior
-        if (valid) {
-            const uint32_t o = off - lo;
-            train_fwd_ray<AMB, NA, UNC>(p_sg.s + o, p_rgb.s + 3 * o, p_a0.s + o, p_a1.s + o, p_u.s + o, p_dl.s + 2 * o, num, T_thresh, ws, a0, a1, u, d, r, g, b);
-        }
-    } else if (total > 0 && total <= (uint32_t)CT_CAP) {
-        // Foreign row order (the reference's atomic allocation, raymarching.cu:446-454: consecutive rows own unrelated segments).  A thread walking its ray
-        // straight out of global memory touches one sector per sample and array; instead every warp copies the segments of its 32 rays into the staging
-        // arrays one ray at a time — a segment is contiguous, so a copy is one or two coalesced loads per array — at the slots an exclusive scan of the
-        // counts assigns, and the rays are then walked out of shared memory like in the tiled case.
-        float *b_sg = sm, *b_dl = b_sg + CT_CAP + CT_PAD, *b_rgb = b_dl + 2 * CT_CAP + CT_PAD, *b_a0 = b_rgb + 3 * CT_CAP + CT_PAD;
-        float *b_a1 = b_a0 + (NA >= 1 ? CT_CAP + CT_PAD : 0), *b_u = b_a1 + (NA >= 2 ? CT_CAP + CT_PAD : 0);
-        const uint32_t lane = threadIdx.x & 31u;
-        const uint32_t cnt = valid ? num : 0u;
-#pragma unroll 1
-        for (uint32_t j = 0; j < 32; j++) {
-            const uint32_t nj = __shfl_sync(0xffffffffu, cnt, j);
-            if (nj == 0) continue;
-            const uint32_t oj = __shfl_sync(0xffffffffu, off, j), sj = __shfl_sync(0xffffffffu, slot, j);
-            for (uint32_t e = lane; e < nj; e += 32) {
-                b_sg[sj + e] = __ldcs(sigmas + oj + e);
-                if (NA >= 1) b_a0[sj + e] = __ldcs(amb0 + oj + e);
-                if (NA >= 2) b_a1[sj + e] = __ldcs(amb1 + oj + e);
-                if (UNC) b_u[sj + e] = __ldcs(unc + oj + e);
-            }
-            for (uint32_t e = lane; e < 2 * nj; e += 32) b_dl[2 * sj + e] = __ldcs(deltas + 2 * (size_t)oj + e);
-            for (uint32_t e = lane; e < 3 * nj; e += 32) b_rgb[3 * sj + e] = __ldcs(rgbs + 3 * (size_t)oj + e);
-        }
-        __syncwarp();                          // a warp only reads what it staged itself
-        if (valid) train_fwd_ray<AMB, NA, UNC>(b_sg + slot, b_rgb + 3 * slot, b_a0 + slot, b_a1 + slot, b_u + slot, b_dl + 2 * slot, num, T_thresh, ws, a0, a1, u, d, r, g, b);
-    } else if (valid) {
+    float *b_sg = sm, *b_dl = b_sg + cap + CT_PAD, *b_rgb = b_dl + 2 * cap + CT_PAD, *b_a0 = b_rgb + 3 * cap + CT_PAD;
+    float *b_a1 = b_a0 + (NA >= 1 ? cap + CT_PAD : 0), *b_u = b_a1 + (NA >= 2 ? cap + CT_PAD : 0);
+    const uint32_t cnt = valid ? num : 0u;
+    auto walk_global = [&]() {
         train_fwd_ray<AMB, NA, UNC>(sigmas + off, rgbs + 3 * (size_t)off, NA >= 1 ? amb0 + off : nullptr, NA >= 2 ? amb1 + off : nullptr,
                                     UNC ? unc + off : nullptr, deltas + 2 * (size_t)off, num, T_thresh, ws, a0, a1, u, d, r, g, b);
+    };
+    // groups of consecutive rows whose samples fit the staging buffers, one pass each (`slot` = samples of the CTA's earlier rows, in row order)
+    uint32_t bar_phase = 0;
+    for (uint32_t base = 0; base < total;) {
+        const uint32_t end = group_end(valid, slot, cnt, base, total, cap);
+        if (end == base) {                     // one ray longer than the staging capacity: straight out of global memory
+            const bool mine = valid && slot == base;
+            if (mine) walk_global();
+            base = long_row_end(mine, slot, cnt);
+            continue;
+        }
+        const bool in_group = valid && slot >= base && slot < end;
+        const uint32_t gcnt = end - base;
+        if (tiled) {
+            // the rows' segments tile [lo, lo + total) in row order (b2n_march_rays_train's allocation): the group is ONE contiguous range per array -> TMA bulk copies
+            const size_t g0 = (size_t)lo + base;
+            const Span p_sg = span_of(b_sg, sigmas + g0, gcnt), p_dl = span_of(b_dl, deltas + 2 * g0, 2 * gcnt), p_rgb = span_of(b_rgb, rgbs + 3 * g0, 3 * gcnt);
+            const Span p_a0 = NA >= 1 ? span_of(b_a0, amb0 + g0, gcnt) : Span{b_a0, 0, 0, 0};
+            const Span p_a1 = NA >= 2 ? span_of(b_a1, amb1 + g0, gcnt) : Span{b_a1, 0, 0, 0};
+            const Span p_u = UNC ? span_of(b_u, unc + g0, gcnt) : Span{b_u, 0, 0, 0};
+            if (threadIdx.x == 0) tc5::mbar_expect_tx(&s_bar, 4u * (p_sg.body + p_dl.body + p_rgb.body + p_a0.body + p_a1.body + p_u.body));
+            span_load(p_sg, sigmas + g0, &s_bar);
+            span_load(p_dl, deltas + 2 * g0, &s_bar);
+            span_load(p_rgb, rgbs + 3 * g0, &s_bar);
+            if (NA >= 1) span_load(p_a0, amb0 + g0, &s_bar);
+            if (NA >= 2) span_load(p_a1, amb1 + g0, &s_bar);
+            if (UNC) span_load(p_u, unc + g0, &s_bar);
+            __syncthreads();                       // edge floats
+            tc5::mbar_wait(&s_bar, bar_phase);     // bulk interior
+            bar_phase ^= 1u;
+            if (in_group) {
+                const uint32_t o = slot - base;
+                train_fwd_ray<AMB, NA, UNC>(p_sg.s + o, p_rgb.s + 3 * o, p_a0.s + o, p_a1.s + o, p_u.s + o, p_dl.s + 2 * o, num, T_thresh, ws, a0, a1, u, d, r, g, b);
+            }
+        } else {
+            // Foreign row order (the reference's atomic allocation, raymarching.cu:446-454: consecutive rows own unrelated segments).  A thread walking its ray
+            // straight out of global memory touches one sector per sample and array; instead every warp gathers the samples of its rays of this group into the
+            // staging arrays, at the slots the exclusive scan of the counts assigns, and the rays are then walked out of shared memory like in the tiled case.
+            // Sample-parallel: lane = one staged sample of the warp's rays of this group; its ray is found by a binary search over the lanes' slots
+            // (5 shuffles), then the nine floats of the sample are loaded — consecutive lanes read consecutive addresses inside a segment, every lane is
+            // busy and all loads of a round are independent (copying ray by ray kept 8 of 32 lanes busy on one dependent load -> store chain per ray).
+            const uint32_t lane = threadIdx.x & 31u;
+            const uint32_t w_lo = max(__shfl_sync(0xffffffffu, slot, 0), base), w_hi = min(__shfl_sync(0xffffffffu, slot + cnt, 31), end);
+#pragma unroll 1
+            for (uint32_t i0 = w_lo; i0 < w_hi; i0 += 32) {
+                const bool act = i0 + lane < w_hi;
+                const uint32_t i = act ? i0 + lane : w_hi - 1;
+                uint32_t j = 0;
+#pragma unroll
+                for (uint32_t step = 16; step; step >>= 1) {
+                    const uint32_t sj = __shfl_sync(0xffffffffu, slot, (j + step) & 31u);
+                    if (sj <= i) j += step;                      // slots ascend over the lanes; rows without samples share their successor's slot
+                }
+                const size_t src = (size_t)__shfl_sync(0xffffffffu, off, j) + (i - __shfl_sync(0xffffffffu, slot, j));
+                if (act) {
+                    const uint32_t dst = i - base;
+                    const float v_sg = __ldcs(sigmas + src), v_d0 = __ldcs(deltas + 2 * src), v_d1 = __ldcs(deltas + 2 * src + 1);
+                    const float v_r = __ldcs(rgbs + 3 * src), v_g = __ldcs(rgbs + 3 * src + 1), v_b = __ldcs(rgbs + 3 * src + 2);
+                    const float v_a0 = NA >= 1 ? __ldcs(amb0 + src) : 0.0f, v_a1 = NA >= 2 ? __ldcs(amb1 + src) : 0.0f, v_u = UNC ? __ldcs(unc + src) : 0.0f;
+                    b_sg[dst] = v_sg; b_dl[2 * dst] = v_d0; b_dl[2 * dst + 1] = v_d1;
+                    b_rgb[3 * dst] = v_r; b_rgb[3 * dst + 1] = v_g; b_rgb[3 * dst + 2] = v_b;
+                    if (NA >= 1) b_a0[dst] = v_a0;
+                    if (NA >= 2) b_a1[dst] = v_a1;
+                    if (UNC) b_u[dst] = v_u;
+                }
+            }
+            __syncwarp();                          // a warp only reads what it staged itself
+            if (in_group) {
+                const uint32_t o = slot - base;
+                train_fwd_ray<AMB, NA, UNC>(b_sg + o, b_rgb + 3 * o, b_a0 + o, b_a1 + o, b_u + o, b_dl + 2 * o, num, T_thresh, ws, a0, a1, u, d, r, g, b);
+            }
+        }
+        __syncthreads();                           // the next pass overwrites the staging buffers
+        base = end;
     }
     if (n >= N) return;
     weights_sum[idx] = ws;
@@ -255,7 +315,7 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_bwd(
         const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ amb0,
         const float *__restrict__ unc, const float *__restrict__ deltas, const int32_t *__restrict__ rays,
         const float *__restrict__ weights_sum, const float *__restrict__ amb0_sum, const float *__restrict__ unc_sum,
-        const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
+        const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh, uint32_t cap,
         float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs, float *__restrict__ grad_a0,
         float *__restrict__ grad_a1, float *__restrict__ grad_u) {
     extern __shared__ __align__(16) float sm[];
@@ -266,7 +326,7 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_bwd(
     __shared__ __align__(8) uint64_t s_bar;
     if (threadIdx.x == 0) { tc5::mbar_init(&s_bar, 1); tc5::fence_mbar_init(); }
     uint32_t lo, total, slot;
-    const bool staged = cta_tiling(valid, off, num, lo, total, slot);
+    const bool tiled = cta_tiling(valid, off, num, lo, total, slot);
     RayGrads q = {};
     if (valid) {
         q.gws = g_ws[idx];
@@ -278,40 +338,62 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_bwd(
         q.wsF = weights_sum[idx];
         q.rF = image[3 * (size_t)idx]; q.gF = image[3 * (size_t)idx + 1]; q.bF = image[3 * (size_t)idx + 2];
     }
-    if (staged) {
-        // the a0 span doubles as grad_a0 staging (input only when AMB == 2), a1 is output-only (grad_a1 = per-ray constant), u doubles as grad_u
-        float *b_sg = sm, *b_dl = b_sg + CT_CAP + CT_PAD, *b_rgb = b_dl + 2 * CT_CAP + CT_PAD, *b_a0 = b_rgb + 3 * CT_CAP + CT_PAD;
-        float *b_a1 = b_a0 + (NA >= 1 ? CT_CAP + CT_PAD : 0), *b_u = b_a1 + (NA >= 2 ? CT_CAP + CT_PAD : 0);
-        const Span p_sg = span_of(b_sg, sigmas + lo, total), p_dl = span_of(b_dl, deltas + 2 * (size_t)lo, 2 * total);
-        const Span p_rgb = span_of(b_rgb, rgbs + 3 * (size_t)lo, 3 * total);
-        const Span p_a0 = NA >= 1 ? span_of(b_a0, AMB == 2 ? amb0 + lo : grad_a0 + lo, total) : Span{b_a0, 0, 0, 0};
-        const Span p_a1 = NA >= 2 ? span_of(b_a1, grad_a1 + lo, total) : Span{b_a1, 0, 0, 0};
-        const Span p_u = UNC ? span_of(b_u, unc + lo, total) : Span{b_u, 0, 0, 0};
+    auto walk_global = [&]() {
+        train_bwd_ray<AMB, NA, UNC, false>(sigmas + off, rgbs + 3 * (size_t)off, AMB == 2 ? amb0 + off : nullptr, UNC ? unc + off : nullptr,
+                                           deltas + 2 * (size_t)off, num, T_thresh, q, grad_sigmas + off, grad_rgbs + 3 * (size_t)off,
+                                           NA >= 1 ? grad_a0 + off : nullptr, NA >= 2 ? grad_a1 + off : nullptr, UNC ? grad_u + off : nullptr);
+    };
+    if (!tiled) {                              // foreign row order: gradients go straight to global memory (the caller pre-zeroes them)
+        if (valid) walk_global();
+        return;
+    }
+    // the a0 span doubles as grad_a0 staging (input only when AMB == 2), a1 is output-only (grad_a1 = per-ray constant), u doubles as grad_u
+    float *b_sg = sm, *b_dl = b_sg + cap + CT_PAD, *b_rgb = b_dl + 2 * cap + CT_PAD, *b_a0 = b_rgb + 3 * cap + CT_PAD;
+    float *b_a1 = b_a0 + (NA >= 1 ? cap + CT_PAD : 0), *b_u = b_a1 + (NA >= 2 ? cap + CT_PAD : 0);
+    const uint32_t cnt = valid ? num : 0u;
+    uint32_t bar_phase = 0;
+    for (uint32_t base = 0; base < total;) {   // groups of consecutive rows that fit the staging buffers (see the forward kernel)
+        const uint32_t end = group_end(valid, slot, cnt, base, total, cap);
+        if (end == base) {
+            const bool mine = valid && slot == base;
+            if (mine) {
+                // the staged path rewrites its whole range, zeros after the early stop included; the direct path relies on pre-zeroed outputs like the reference
+                walk_global();
+            }
+            base = long_row_end(mine, slot, cnt);
+            continue;
+        }
+        const bool in_group = valid && slot >= base && slot < end;
+        const uint32_t gcnt = end - base;
+        const size_t g0 = (size_t)lo + base;
+        const Span p_sg = span_of(b_sg, sigmas + g0, gcnt), p_dl = span_of(b_dl, deltas + 2 * g0, 2 * gcnt), p_rgb = span_of(b_rgb, rgbs + 3 * g0, 3 * gcnt);
+        const Span p_a0 = NA >= 1 ? span_of(b_a0, AMB == 2 ? amb0 + g0 : grad_a0 + g0, gcnt) : Span{b_a0, 0, 0, 0};
+        const Span p_a1 = NA >= 2 ? span_of(b_a1, grad_a1 + g0, gcnt) : Span{b_a1, 0, 0, 0};
+        const Span p_u = UNC ? span_of(b_u, unc + g0, gcnt) : Span{b_u, 0, 0, 0};
         if (threadIdx.x == 0) tc5::mbar_expect_tx(&s_bar, 4u * (p_sg.body + p_dl.body + p_rgb.body + (AMB == 2 ? p_a0.body : 0u) + p_u.body));
-        span_load(p_sg, sigmas + lo, &s_bar);
-        span_load(p_dl, deltas + 2 * (size_t)lo, &s_bar);
-        span_load(p_rgb, rgbs + 3 * (size_t)lo, &s_bar);
-        if (AMB == 2) span_load(p_a0, amb0 + lo, &s_bar);
-        if (UNC) span_load(p_u, unc + lo, &s_bar);
+        span_load(p_sg, sigmas + g0, &s_bar);
+        span_load(p_dl, deltas + 2 * g0, &s_bar);
+        span_load(p_rgb, rgbs + 3 * g0, &s_bar);
+        if (AMB == 2) span_load(p_a0, amb0 + g0, &s_bar);
+        if (UNC) span_load(p_u, unc + g0, &s_bar);
         __syncthreads();
-        tc5::mbar_wait(&s_bar, 0);
-        if (valid) {
-            const uint32_t o = off - lo;
+        tc5::mbar_wait(&s_bar, bar_phase);
+        bar_phase ^= 1u;
+        if (in_group) {
+            const uint32_t o = slot - base;
             train_bwd_ray<AMB, NA, UNC, true>(p_sg.s + o, p_rgb.s + 3 * o, p_a0.s + o, p_u.s + o, p_dl.s + 2 * o, num, T_thresh, q,
                                               p_sg.s + o, p_rgb.s + 3 * o, p_a0.s + o, p_a1.s + o, p_u.s + o);
         }
         tc5::fence_proxy_async();              // this thread's shared-memory writes -> visible to the bulk-store (async) proxy
         __syncthreads();
-        span_store_any(p_sg, grad_sigmas + lo);
-        span_store_any(p_rgb, grad_rgbs + 3 * (size_t)lo);
-        if (NA >= 1) span_store_any(p_a0, grad_a0 + lo);
-        if (NA >= 2) span_store_any(p_a1, grad_a1 + lo);
-        if (UNC) span_store_any(p_u, grad_u + lo);
+        span_store_any(p_sg, grad_sigmas + g0);
+        span_store_any(p_rgb, grad_rgbs + 3 * g0);
+        if (NA >= 1) span_store_any(p_a0, grad_a0 + g0);
+        if (NA >= 2) span_store_any(p_a1, grad_a1 + g0);
+        if (UNC) span_store_any(p_u, grad_u + g0);
         if (threadIdx.x == 0) { tc5::bulk_commit(); tc5::bulk_wait_read0(); }     // shared memory must outlive the bulk reads
-    } else if (valid) {
-        train_bwd_ray<AMB, NA, UNC, false>(sigmas + off, rgbs + 3 * (size_t)off, AMB == 2 ? amb0 + off : nullptr, UNC ? unc + off : nullptr,
-                                           deltas + 2 * (size_t)off, num, T_thresh, q, grad_sigmas + off, grad_rgbs + 3 * (size_t)off,
-                                           NA >= 1 ? grad_a0 + off : nullptr, NA >= 2 ? grad_a1 + off : nullptr, UNC ? grad_u + off : nullptr);
+        __syncthreads();                       // ... and the next pass overwrites it
+        base = end;
     }
 }
 
@@ -368,10 +450,11 @@ static int launch_train_fwd(const char *what, const float *sigmas, const float *
     B2N_REQUIRE(sigmas && rgbs && deltas && rays && ws && depth && image, "%s: null pointer", what);
     B2N_REQUIRE((NA < 1 || (amb0 && a0s)) && (NA < 2 || (amb1 && a1s)) && (!UNC || (unc && us)), "%s: null pointer", what);
     if (N == 0) return 0;
-    const size_t smem = Stage<NA, UNC>::BYTES;
+    const uint32_t cap = stage_cap();
+    const size_t smem = Stage<NA, UNC>::bytes(cap);
     auto kern = k_comp_train_fwd<AMB, NA, UNC>;
     B2N_SMEM(kern, smem);
-    kern<<<ceil_div<uint32_t>(N, CT_THREADS), CT_THREADS, smem, as_stream(stream)>>>(sigmas, rgbs, amb0, amb1, unc, deltas, rays, M, N, T_thresh,
+    kern<<<ceil_div<uint32_t>(N, CT_THREADS), CT_THREADS, smem, as_stream(stream)>>>(sigmas, rgbs, amb0, amb1, unc, deltas, rays, M, N, T_thresh, cap,
                                                                                      ws, a0s, a1s, us, depth, image);
     return check_launch(what);
 }
@@ -385,11 +468,12 @@ static int launch_train_bwd(const char *what, const float *g_ws, const float *g_
     B2N_REQUIRE((NA < 1 || (g_a0 && ga0)) && (NA < 2 || (g_a1 && ga1)) && (!UNC || (g_u && unc && us && gu)) && (AMB != 2 || (amb0 && a0s)),
                 "%s: null pointer", what);
     if (N == 0) return 0;
-    const size_t smem = Stage<NA, UNC>::BYTES;
+    const uint32_t cap = stage_cap();
+    const size_t smem = Stage<NA, UNC>::bytes(cap);
     auto kern = k_comp_train_bwd<AMB, NA, UNC>;
     B2N_SMEM(kern, smem);
     kern<<<ceil_div<uint32_t>(N, CT_THREADS), CT_THREADS, smem, as_stream(stream)>>>(g_ws, g_a0, g_a1, g_u, g_img, sigmas, rgbs, amb0, unc, deltas, rays,
-                                                                                     ws, a0s, us, image, M, N, T_thresh, gs, grgb, ga0, ga1, gu);
+                                                                                     ws, a0s, us, image, M, N, T_thresh, cap, gs, grgb, ga0, ga1, gu);
     return check_launch(what);
 }
 
