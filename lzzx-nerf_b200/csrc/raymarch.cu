@@ -365,11 +365,14 @@ __device__ __forceinline__ void march_train_offsets(uint32_t N, const int32_t *_
     }
 }
 
-// pass 2 (t_cache present).  The samples of a CTA's 128 consecutive rays form one contiguous slot range [s_base, s_base + total): every thread turns the
-// cached t values of its ray (one contiguous t_cache row) into samples inside a shared-memory tile laid out like the output, and the tile leaves as full
-// contiguous lines of xyzs / dirs / deltas — instead of one thread walking its ray with 4-byte stores at a 12-byte stride.  Same expressions as DdaRay::probe
-// for an occupied cell: bit-identical samples.
+// pass 2 (t_cache present; max_steps <= 64).  The samples of a CTA's 128 consecutive rays form one contiguous slot range [s_base, s_base + total).  The pass is
+// SAMPLE-parallel: every ray first marks its slots in a byte map (slot -> ray of the CTA), then thread = slot: it looks up its ray, reads the cached parameter t
+// of the sample (neighbouring slots of a ray are neighbouring floats of one t_cache row), evaluates position / step and writes them into a shared-memory tile
+// laid out like the output (stride-3 / stride-2 floats over the threads: conflict-free), and the tile leaves as aligned 16-byte stores.  All lanes work and all
+// loads of a round are independent — the earlier thread-per-ray version walked rays of 0..16 samples side by side (half the lanes idle, scattered st.shared).
+// Same expressions as DdaRay::probe for an occupied cell: bit-identical samples.
 constexpr uint32_t MW_TILE = 512;                 // slots staged per round (16 KB of shared memory)
+constexpr uint32_t MW_MAX_STEPS = 64;             // = mt_cached()'s bound: the slot map of a CTA is 128 x 64 bytes
 __global__ void __launch_bounds__(MT_THREADS) k_march_train_emit(
         const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
         float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas,
@@ -377,15 +380,17 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_emit(
     __shared__ uint32_t red[MT_THREADS / 32];
     __shared__ uint32_t s_base, s_keep, s_total;
     __shared__ __align__(16) float s_xyz[MW_TILE * 3 + 4], s_dir[MW_TILE * 3 + 4], s_del[MW_TILE * 2 + 4];
+    __shared__ uint8_t s_owner[MT_THREADS * MW_MAX_STEPS];
+    __shared__ uint32_t s_first[MT_THREADS];                // first slot of the ray (relative to s_base)
+    __shared__ float s_od[MT_THREADS][6];
     uint32_t off, num;
     march_train_offsets(N, rays, counter, cta_totals, red, s_base, off, num);
     const uint32_t n = blockIdx.x * MT_THREADS + threadIdx.x;
-    float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 0.0f};
     if (n < N) {
         rays[3 * (size_t)n + 1] = (int32_t)off;
         if (num) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) { o[c] = rays_o[3 * (size_t)n + c]; d[c] = rays_d[3 * (size_t)n + c]; }
+            for (int c = 0; c < 3; c++) { s_od[threadIdx.x][c] = rays_o[3 * (size_t)n + c]; s_od[threadIdx.x][3 + c] = rays_d[3 * (size_t)n + c]; }
         }
     }
     if (threadIdx.x == 0) s_keep = 0xffffffffu;
@@ -394,13 +399,14 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_emit(
     const uint32_t a = off - s_base;
     if (num > 0 && off + num > M) atomicMin(&s_keep, a);
     if (threadIdx.x == MT_THREADS - 1) s_total = a + num;
+    s_first[threadIdx.x] = a;
     __syncthreads();
     const uint32_t total = min(s_total, s_keep);
+    for (uint32_t k = 0; k < num && a + k < total; k++) s_owner[a + k] = (uint8_t)threadIdx.x;
     DdaRay q;                                              // only the step rule is used
     q.dx = q.dy = q.dz = 1.0f;
     q.init_common(bound, dt_gamma, max_steps, C, H, 0.0f);
-    const float *tc = t_cache + (size_t)n * max_steps;
-    const bool vec4 = (max_steps & 3u) == 0;               // rows are 16-byte aligned: read them four parameters at a time
+    const float *tc = t_cache + (size_t)blockIdx.x * MT_THREADS * max_steps;
     // the tile keeps the 16-byte phase of its destination, so it leaves as aligned 16-byte stores (a round advances every array by a multiple of 16 bytes)
     const uint32_t ph_x = (uint32_t)((reinterpret_cast<uintptr_t>(xyzs + 3 * (size_t)s_base) >> 2) & 3), ph_d = (uint32_t)((reinterpret_cast<uintptr_t>(dirs + 3 * (size_t)s_base) >> 2) & 3),
                    ph_l = (uint32_t)((reinterpret_cast<uintptr_t>(deltas + 2 * (size_t)s_base) >> 2) & 3);
@@ -409,32 +415,25 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_emit(
         if (threadIdx.x < head) dst[threadIdx.x] = src[phase + threadIdx.x];
         float4 *d4 = reinterpret_cast<float4 *>(dst + head);
         const float4 *s4 = reinterpret_cast<const float4 *>(src + phase + head);
-        for (uint32_t v = threadIdx.x; v < nv; v += MT_THREADS) d4[v] = s4[v];
+        for (uint32_t v = threadIdx.x; v < nv; v += MT_THREADS) __stcs(d4 + v, s4[v]);
         if (threadIdx.x < tail) dst[head + 4 * nv + threadIdx.x] = src[phase + head + 4 * nv + threadIdx.x];
     };
+    __syncthreads();                                       // slot map complete
     for (uint32_t j0 = 0; j0 < total; j0 += MW_TILE) {
         const uint32_t j1 = min(j0 + MW_TILE, total);
-        auto put = [&](uint32_t sl, float tk) {
+#pragma unroll 4
+        for (uint32_t sl = j0 + threadIdx.x; sl < j1; sl += MT_THREADS) {
+            const uint32_t r = s_owner[sl];
+            const float tk = __ldcs(tc + r * max_steps + (sl - s_first[r]));
             const float dt = q.step_of(tk);
             const uint32_t j = sl - j0;
             float *px = s_xyz + ph_x + 3 * j, *pd = s_dir + ph_d + 3 * j, *pl = s_del + ph_l + 2 * j;
-            px[0] = clampf(__fmaf_rn(tk, d[0], o[0]), -bound, bound);
-            px[1] = clampf(__fmaf_rn(tk, d[1], o[1]), -bound, bound);
-            px[2] = clampf(__fmaf_rn(tk, d[2], o[2]), -bound, bound);
-            pd[0] = d[0]; pd[1] = d[1]; pd[2] = d[2];
+            const float d0 = s_od[r][3], d1 = s_od[r][4], d2 = s_od[r][5];
+            px[0] = clampf(__fmaf_rn(tk, d0, s_od[r][0]), -bound, bound);
+            px[1] = clampf(__fmaf_rn(tk, d1, s_od[r][1]), -bound, bound);
+            px[2] = clampf(__fmaf_rn(tk, d2, s_od[r][2]), -bound, bound);
+            pd[0] = d0; pd[1] = d1; pd[2] = d2;
             pl[0] = dt; pl[1] = __fadd_rn(tk, dt);
-        };
-        const uint32_t lo = max(a, j0), hi = min(a + num, j1);
-        if (vec4) {
-#pragma unroll 1
-            for (uint32_t k4 = (lo - a) >> 2; lo < hi && 4 * k4 < hi - a; k4++) {
-                const float4 v = __ldcs(reinterpret_cast<const float4 *>(tc) + k4);
-                const float tq[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (uint32_t c = 0; c < 4; c++) { const uint32_t sl = a + 4 * k4 + c; if (sl >= lo && sl < hi) put(sl, tq[c]); }
-            }
-        } else {
-            for (uint32_t sl = lo; sl < hi; sl++) put(sl, __ldcs(tc + (sl - a)));
         }
         __syncthreads();
         const uint32_t cnt = j1 - j0;
@@ -644,7 +643,7 @@ int b2n_morton3D_dilation(const float *grid, uint32_t C, uint32_t H, float *grid
 
 // workspace layout: [box OCC_BOX_FLOATS floats | cta totals (ctas + 1) int32 | t cache N * max_steps floats (only when max_steps <= 64)]
 static inline size_t mt_align(size_t v) { return (v + 255) & ~(size_t)255; }
-static inline bool mt_cached(uint32_t N, uint32_t max_steps) { return max_steps <= 64 && (uint64_t)max_steps * N <= (64ull << 20); }
+static inline bool mt_cached(uint32_t N, uint32_t max_steps) { return max_steps <= MW_MAX_STEPS && (uint64_t)max_steps * N <= (64ull << 20); }
 
 uint64_t b2n_march_rays_train_workspace_bytes(uint32_t N, uint32_t max_steps) {
     const uint32_t ctas = ceil_div<uint32_t>(N ? N : 1, MT_THREADS);
