@@ -126,11 +126,15 @@ __device__ __forceinline__ uint32_t warp_append(bool keep, int32_t *counter) {
 // true in exactly one thread block of the grid: the one that finishes last (all other blocks' writes are visible to it)
 __device__ __forceinline__ bool last_block_done(int32_t *ticket) {
     __shared__ int s_last;
-    __threadfence();
+    // the block's writes are ordered before the barrier (CTA scope); ONE device-scope fence by the thread that takes the ticket then orders them — cumulatively —
+    // before the ticket (the grid-barrier pattern of cooperative groups).  A fence in every thread made each of them wait for its own outstanding stores.
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int32_t)gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1) == (int32_t)gridDim.x - 1);
+        if (s_last) __threadfence();
+    }
     __syncthreads();
-    if (s_last) __threadfence();
     return s_last != 0;
 }
 

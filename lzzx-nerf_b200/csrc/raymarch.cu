@@ -208,9 +208,8 @@ __global__ void __launch_bounds__(256) k_occ_box(const uint8_t *__restrict__ gri
     }
     if (!finalize) return;                        // the consumer reduces the partial boxes itself (k_frame_init)
     int32_t *ticket = reinterpret_cast<int32_t *>(parts + 6 * OCC_PARTS + 6);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int32_t)gridDim.x - 1);
+    __syncthreads();                              // (one cumulative device-scope fence by the ticket taker, see last_block_done in fused_frame.cu)
+    if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(ticket, 1) == (int32_t)gridDim.x - 1); }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -314,9 +313,8 @@ __global__ void __launch_bounds__(MT_THREADS) k_march_train_count(
     }
     // the last CTA to finish turns the group totals into slot offsets: prefix[g] = counter snapshot + samples of all groups before g  (prefix = cta_totals + groups + 1)
     __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int32_t)gridDim.x - 1);
+    __syncthreads();                              // (one cumulative device-scope fence by the ticket taker, see last_block_done in fused_frame.cu)
+    if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(ticket, 1) == (int32_t)gridDim.x - 1); }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
