@@ -36,7 +36,7 @@ template <int NA, bool UNC> struct Stage {
     static size_t bytes(uint32_t cap) { return sizeof(float) * ((size_t)FLOATS * cap + 6 * CT_PAD); }
 };
 static uint32_t stage_cap() {           // B2N_COMP_CAP: measurement switch
-    static const uint32_t cap = [] { const char *e = getenv("B2N_COMP_CAP"); const int v = e ? atoi(e) : 0; return (uint32_t)((v >= 64 && v <= 4096) ? (v & ~3) : CT_CAP_DEFAULT); }();
+    static const uint32_t cap = [] { const char *e = getenv("B2N_COMP_CAP"); const int v = e ? atoi(e) : 0; return (uint32_t)((v >= 8 && v <= 4096) ? (v & ~3) : CT_CAP_DEFAULT); }();
     return cap;
 }
 

@@ -497,3 +497,33 @@ def test_four_warpgroup_tmem_head_kernel_equals_three_warpgroup_kernel(monkeypat
     for a_, b_, name in zip(outs[0], outs[1], ("sigma", "rgb", "aud", "eye", "unc") * 2):
         assert torch.equal(a_, b_), (name, float((a_ - b_).abs().max()))
     assert bool(torch.isfinite(outs[0][0]).all()) and float(outs[0][1].std()) > 1e-3
+
+
+@pytest.mark.parametrize("wg4", ["1", "0"])
+def test_head_tile_schedules_give_identical_outputs(monkeypatch, wg4):
+    """The tile -> CTA mapping of the head kernels (balanced contiguous shares for a frame alone, grid-strided walk on a capped grid for frames in flight, the spread
+    variant) only changes which SM evaluates a tile: every output bit for bit, full launches, device-side n_valid (short launches) and a capped grid."""
+    m = _model(6, 1.0, True)
+    x, d = _samples(200007, 33)
+    enc_a = torch.randn(1, 32, device="cuda") * 0.5; c = m.individual_codes[1:2].detach(); e = torch.tensor([[0.3]], device="cuda")
+    m.pack()
+    monkeypatch.setenv("B2N_HEAD_WG4", wg4)
+    ref = None
+    for sched, ctas in (("0", None), ("1", None), ("2", None), ("2", "74"), ("0", "37"), ("2", "5")):
+        monkeypatch.setenv("B2N_HEAD_SCHED", sched)
+        if ctas is None:
+            monkeypatch.delenv("B2N_HEAD_CTAS", raising=False)
+        else:
+            monkeypatch.setenv("B2N_HEAD_CTAS", ctas)
+        outs = [t.clone() for t in m(x, d, enc_a, c, e)]
+        for nv in (1, 127, 129, 40000, 200007):
+            nvt = torch.tensor([nv], dtype=torch.int32, device="cuda")
+            o2 = m(x, d, enc_a, c, e, n_valid=nvt, out=tuple(torch.full_like(t, -3.0) for t in outs[:5]))
+            outs += [t.clone() for t in o2]
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = outs
+            assert bool((ref[5][1:] == -3.0).all()) and bool((ref[5][:1] != -3.0).all())      # n_valid = 1: only the first row is written
+        else:
+            for k, (a_, b_) in enumerate(zip(ref, outs)):
+                assert torch.equal(a_, b_), (sched, ctas, k, float((a_ - b_).abs().max()))

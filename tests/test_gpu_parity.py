@@ -260,6 +260,21 @@ def test_composite_train_fwd_bwd(rm, ref, variant, layout, T_thresh):
         assert torch.equal(a, b.grad)
 
 
+@pytest.mark.parametrize("cap", ["64", "8"])
+def test_composite_train_small_staging_capacity(cap):
+    """The training composites stage `cap` samples per pass (default 1024) and take several passes over groups of consecutive rows when a CTA's 128 rays hold
+    more; a ray longer than the capacity is walked straight out of global memory.  cap = 64: every CTA of test_composite_train_fwd_bwd takes ~10 passes;
+    cap = 8: rays of 9..16 samples take the long-row path.  The capacity is read once per process (B2N_COMP_CAP), so the cases run in a child process."""
+    import os, subprocess, sys
+    if os.environ.get("B2N_COMP_CAP"):
+        pytest.skip("already the child process")
+    env = dict(os.environ, B2N_COMP_CAP=cap)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k", "test_composite_train_fwd_bwd", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
+
+
 @pytest.mark.parametrize("variant", ["rgb", "plain", "sigma", "uncertainty", "triplane"])
 def test_composite_inference_loop(rm, ref, variant):
     """Three chained (march, composite) iterations with growing n_step, compaction between them — the renderer.py:503-545 loop."""
