@@ -12,11 +12,11 @@
 // operation order, so results are bit-identical to the reference kernels on the same GPU (same MUFU.EX2).
 // What changes is data movement: a CTA owns 128 consecutive rows of `rays`; when their sample segments tile
 // one contiguous range (always true for b2n_march_rays_train's deterministic allocation) the CTA stages that
-// range through shared memory with TMA bulk copies (cp.async.bulk: one thread puts the CTA's whole 70 KB in
-// flight, three CTAs per SM keep > 200 KB outstanding per SM — the latency x bandwidth product HBM3e needs),
+// range through shared memory with TMA bulk copies (cp.async.bulk: one thread puts up to 37 KB per pass in flight, six CTAs per SM keep
+// > 200 KB outstanding per SM — the latency x bandwidth product HBM3e needs; tiles with more than 1024 samples take several passes),
 // threads walk their ray out of shared memory, and the backward writes its per-sample gradients back through
 // the same staging buffer with bulk stores — so HBM sees each algorithmic byte exactly once.  Foreign `rays` orderings (the reference's atomic allocation)
-// take the direct global-memory path of the same template.
+// are gathered into the same staging buffers sample-parallel per warp (forward); the backward then takes the direct global-memory path of the same template.
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc5.cuh"
