@@ -219,7 +219,55 @@ def head_kernel_profile(model, renderer, frames, auds, n_frames, repeats=5):
     return total_ms, launches, samples
 
 
-def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536, eager=False, fused_head=True):
+def train_kernel_breakdown(step_fn, batches, m_buf, n_rays):
+    """Per-kernel durations of ONE replayed training step (CUPTI kernel records via torch.profiler — CUDA events cannot be recorded inside a replayed graph) with
+    the algorithmic work of each of the big kernels, so the step's time can be read against HBM / tensor peaks.  Explanatory: the step time itself is the
+    event-timed figure above."""
+    from torch.profiler import profile, ProfilerActivity
+    pk, _ = peaks()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for s in range(2):
+            b = batches[s % 4]
+            step_fn(b[0], b[1], b[2], b[3], index=1 + s, face_mask=b[4])
+        torch.cuda.synchronize()
+    ev = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+    starts = [i for i, e in enumerate(ev) if "k_near_far" in e.name]
+    ev = ev[starts[-1]:] if starts else ev
+    t0, t1 = ev[0].time_range.start, max(e.time_range.end for e in ev)
+    dur = {}
+    for e in ev:
+        name = e.name.split("(")[0].replace("void ", "").replace("b2n::", "")
+        dur[name] = dur.get(name, 0.0) + (e.time_range.end - e.time_range.start)
+    M = m_buf
+    # algorithmic work per sample of the 327 k-sample buffer (DESIGN §4.3): bytes the kernel has to move at least, FLOPs of the layers it evaluates
+    work = {
+        "k_head_forward<true, true>": dict(flop=2 * 24368 * M, bytes=(24 + 1088 + 28) * M, note="coordinates in, 1088 B of kept fp16 activations + outputs out per sample"),
+        "k_head_backward": dict(flop=2 * 2 * 24368 * M, bytes=(744 + 1000 + 144) * M, note="kept activations in, fp16 layer gradients + fp32 table-gradient planes out"),
+        "k_linear_wgrad_multi": dict(flop=2 * 24368 * M, bytes=2132 * M, note="every (dY, X) operand pair once"),
+        "k_triplane_bwd_fix": dict(bytes=(144 + 12) * M, reds=144 * M, note="144 table reductions per sample"),
+        "k_march_train_count<1>": dict(bytes=40 * n_rays, note="instruction-bound DDA (DESIGN §4.5)"),
+        "k_march_train_emit": dict(bytes=12 * n_rays + 32 * M),
+        "k_comp_train_fwd<1, 2, true>": dict(bytes=36 * M + 44 * n_rays),
+        "k_comp_train_bwd<1, 2, true>": dict(bytes=64 * M + 72 * n_rays),
+    }
+    rows = []
+    for name, us in sorted(dur.items(), key=lambda kv: -kv[1]):
+        row = {"kernel": name, "us": round(us, 1)}
+        w = work.get(name)
+        if w:
+            row["frac_of_hbm"] = round(w["bytes"] / (us * 1e-6) / 1e9 / pk["hbm_gbs"], 3)
+            if "flop" in w:
+                row["frac_of_bf16_burst"] = round(w["flop"] / (us * 1e-6) / 1e12 / pk["bf16_tflops"], 3)
+            if "note" in w:
+                row["note"] = w["note"]
+        rows.append(row)
+        if len(rows) >= 14:
+            break
+    return {"how": "CUPTI kernel records of one replayed step (torch.profiler); branches of the graph overlap, so the rows add up to more than the span",
+            "span_us": round(t1 - t0, 1), "kernel_sum_us": round(sum(dur.values()), 1), "launches": len(ev), "rows": rows}
+
+
+def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536, eager=False, fused_head=True, kernel_breakdown=False):
     """BASELINE configs[2]/[4]: data-parallel training step, 65 536 rays per GPU, synthetic audio window (AudioNet + AudioAttNet), grid backward,
     AdamW; gradients all-reduced once per step over the flat buffer when world > 1.  Returns a dict (rays/s over all ranks)."""
     from b2nerf import scene
@@ -256,8 +304,14 @@ def train_bench(dev, rank, world, bitfield, barrier, steps, warmup, n_rays=65536
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    kernels = None
+    if kernel_breakdown and not eager and rank == 0:
+        try:
+            kernels = train_kernel_breakdown(step_fn, batches, int(m_buf), n_rays)
+        except Exception as e:      # explanatory leg only: never fail the line for it
+            kernels = {"error": f"{type(e).__name__}: {e}"}
     return {"metric": "train_rays_per_sec", "value": world * steps * n_rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": n_rays,
-            "samples_per_step_buffer": int(m_buf), "loss": float(loss), "grad_allreduce_bytes": tr.grads.nbytes() if world > 1 else 0, "steps_timed": steps,
+            "kernels": kernels, "samples_per_step_buffer": int(m_buf), "loss": float(loss), "grad_allreduce_bytes": tr.grads.nbytes() if world > 1 else 0, "steps_timed": steps,
             "grad_allreduce": "none (1 GPU)" if world == 1 else ("one two-shot kernel per rank over NVLink peer memory (csrc/peer_allreduce.cu), inside the step's graph"
                                                               if tr.grads.peer is not None else "ncclAllReduce of the flat buffer inside the step's graph"),
             "objective": "TrainerUtil.py:238-363 head branch: uncertainty-weighted MSE + loss_u + static-uncertainty + entropy(1e-4) + masked / ramped ambient terms, "
@@ -431,7 +485,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     train_info = None
     if not args.no_train:
         train_info = train_bench(dev, rank, world, bitfield, barrier, steps=max(64, args.steps * 32), warmup=max(args.warmup, 18), eager=args.train_eager,
-                                 fused_head=not args.train_unfused)
+                                 fused_head=not args.train_unfused, kernel_breakdown=(world == 1 and not args.no_kernels))
     if rank != 0:
         return
     torso_info = None

@@ -16,7 +16,7 @@
 // > 200 KB outstanding per SM — the latency x bandwidth product HBM3e needs; tiles with more than 1024 samples take several passes),
 // threads walk their ray out of shared memory, and the backward writes its per-sample gradients back through
 // the same staging buffer with bulk stores — so HBM sees each algorithmic byte exactly once.  Foreign `rays` orderings (the reference's atomic allocation)
-// are gathered into the same staging buffers sample-parallel per warp (forward); the backward then takes the direct global-memory path of the same template.
+// are gathered into the same staging buffers sample-parallel per warp, forward and backward (the backward scatters its gradients back the same way).
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc5.cuh"
@@ -343,10 +343,6 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_bwd(
                                            deltas + 2 * (size_t)off, num, T_thresh, q, grad_sigmas + off, grad_rgbs + 3 * (size_t)off,
                                            NA >= 1 ? grad_a0 + off : nullptr, NA >= 2 ? grad_a1 + off : nullptr, UNC ? grad_u + off : nullptr);
     };
-    if (!tiled) {                              // foreign row order: gradients go straight to global memory (the caller pre-zeroes them)
-        if (valid) walk_global();
-        return;
-    }
     // the a0 span doubles as grad_a0 staging (input only when AMB == 2), a1 is output-only (grad_a1 = per-ray constant), u doubles as grad_u
     float *b_sg = sm, *b_dl = b_sg + cap + CT_PAD, *b_rgb = b_dl + 2 * cap + CT_PAD, *b_a0 = b_rgb + 3 * cap + CT_PAD;
     float *b_a1 = b_a0 + (NA >= 1 ? cap + CT_PAD : 0), *b_u = b_a1 + (NA >= 2 ? cap + CT_PAD : 0);
@@ -365,6 +361,61 @@ __global__ void __launch_bounds__(CT_THREADS) k_comp_train_bwd(
         }
         const bool in_group = valid && slot >= base && slot < end;
         const uint32_t gcnt = end - base;
+        if (!tiled) {
+            // foreign row order (see the forward kernel): the warp gathers the samples of its rays of this group sample-parallel, the rays are walked in shared
+            // memory (gradients overwrite the inputs in place, zeros after the early stop), and the gradients are scattered back the same way.
+            const uint32_t lane = threadIdx.x & 31u;
+            const uint32_t w_lo = max(__shfl_sync(0xffffffffu, slot, 0), base), w_hi = min(__shfl_sync(0xffffffffu, slot + cnt, 31), end);
+            auto source_of = [&](uint32_t i) -> size_t {         // global sample index of staged sample i (all lanes call it)
+                uint32_t j = 0;
+#pragma unroll
+                for (uint32_t step = 16; step; step >>= 1) {
+                    const uint32_t sj = __shfl_sync(0xffffffffu, slot, (j + step) & 31u);
+                    if (sj <= i) j += step;
+                }
+                return (size_t)__shfl_sync(0xffffffffu, off, j) + (i - __shfl_sync(0xffffffffu, slot, j));
+            };
+#pragma unroll 1
+            for (uint32_t i0 = w_lo; i0 < w_hi; i0 += 32) {
+                const bool act = i0 + lane < w_hi;
+                const uint32_t i = act ? i0 + lane : w_hi - 1;
+                const size_t src = source_of(i);
+                if (act) {
+                    const uint32_t dst = i - base;
+                    const float v_sg = __ldcs(sigmas + src), v_d0 = __ldcs(deltas + 2 * src), v_d1 = __ldcs(deltas + 2 * src + 1);
+                    const float v_r = __ldcs(rgbs + 3 * src), v_g = __ldcs(rgbs + 3 * src + 1), v_b = __ldcs(rgbs + 3 * src + 2);
+                    const float v_a0 = AMB == 2 ? __ldcs(amb0 + src) : 0.0f, v_u = UNC ? __ldcs(unc + src) : 0.0f;
+                    b_sg[dst] = v_sg; b_dl[2 * dst] = v_d0; b_dl[2 * dst + 1] = v_d1;
+                    b_rgb[3 * dst] = v_r; b_rgb[3 * dst + 1] = v_g; b_rgb[3 * dst + 2] = v_b;
+                    if (AMB == 2) b_a0[dst] = v_a0;
+                    if (UNC) b_u[dst] = v_u;
+                }
+            }
+            __syncwarp();                          // a warp only reads what it staged itself
+            if (in_group) {
+                const uint32_t o = slot - base;
+                train_bwd_ray<AMB, NA, UNC, true>(b_sg + o, b_rgb + 3 * o, b_a0 + o, b_u + o, b_dl + 2 * o, num, T_thresh, q,
+                                                  b_sg + o, b_rgb + 3 * o, b_a0 + o, b_a1 + o, b_u + o);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (uint32_t i0 = w_lo; i0 < w_hi; i0 += 32) {
+                const bool act = i0 + lane < w_hi;
+                const uint32_t i = act ? i0 + lane : w_hi - 1;
+                const size_t src = source_of(i);
+                if (act) {
+                    const uint32_t dst = i - base;
+                    __stcs(grad_sigmas + src, b_sg[dst]);
+                    __stcs(grad_rgbs + 3 * src, b_rgb[3 * dst]); __stcs(grad_rgbs + 3 * src + 1, b_rgb[3 * dst + 1]); __stcs(grad_rgbs + 3 * src + 2, b_rgb[3 * dst + 2]);
+                    if (NA >= 1) __stcs(grad_a0 + src, b_a0[dst]);
+                    if (NA >= 2) __stcs(grad_a1 + src, b_a1[dst]);
+                    if (UNC) __stcs(grad_u + src, b_u[dst]);
+                }
+            }
+            __syncthreads();                       // the next pass overwrites the staging buffers
+            base = end;
+            continue;
+        }
         const size_t g0 = (size_t)lo + base;
         const Span p_sg = span_of(b_sg, sigmas + g0, gcnt), p_dl = span_of(b_dl, deltas + 2 * g0, 2 * gcnt), p_rgb = span_of(b_rgb, rgbs + 3 * g0, 3 * gcnt);
         const Span p_a0 = NA >= 1 ? span_of(b_a0, AMB == 2 ? amb0 + g0 : grad_a0 + g0, gcnt) : Span{b_a0, 0, 0, 0};

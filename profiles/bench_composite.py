@@ -30,3 +30,5 @@ local = (win.float() + torch.rand(N, device=dev) * 4096).argsort()
 rays_loc = rays[local].contiguous()
 f = lambda: rb.composite_rays_train_triplane_forward(sig, rgb, aud, eye, unc, dl, rays_loc, M, N, 1e-4, ws, a0, a1, us, dep, img)
 t = timeit(f, reps=3); print(f"  fwd scrambled(4096) {t * 1e6:.1f} us  {(36 * M + 44 * N) / t / 1e9 / HBM:.3f} of HBM")
+f = lambda: rb.composite_rays_train_triplane_backward(g_ws, g_a0, g_a1, g_u, g_img, sig, rgb, aud, eye, unc, dl, rays_loc, ws, a0, a1, us, img, M, N, 1e-4, gs, grgb, ga0, ga1, gu)
+t = timeit(f, reps=3); print(f"  bwd scrambled(4096) {t * 1e6:.1f} us  {((36 + 28) * M + 72 * N) / t / 1e9 / HBM:.3f} of HBM")
