@@ -388,16 +388,20 @@ class HeadModel(nn.Module):
     # ---- whole-frame inference (renderer.py:406-570) ----------------------------------------------------------------------
     @torch.no_grad()
     def render_frame(self, rays_o, rays_d, enc_a, ind_code=None, eye=None, bg_color=None, dt_gamma=1.0 / 256, max_steps=16, min_near=0.05,
-                     T_thresh=1e-4, density_scale=1.0, out=None, head_ctas=0):
-        """run_cuda_for_inference without host syncs: returns image [N,3] (clamped, background-blended), weights_sum [N], depth [N]."""
+                     T_thresh=1e-4, density_scale=1.0, out=None, head_ctas=0, workspace=None, aux=None):
+        """run_cuda_for_inference without host syncs: returns image [N,3] (clamped, background-blended), weights_sum [N], depth [N].
+        workspace: a caller-owned uint8 buffer of b2n_render_frame_workspace_bytes(N) — frames rendered concurrently on several streams need one each (default: one
+        per model, i.e. calls must be stream-ordered); aux = (weights_sum [N], depth [N]) output buffers to reuse."""
         rays_o, rays_d = rays_o.float().contiguous().view(-1, 3), rays_d.float().contiguous().view(-1, 3)
         N, dev = rays_o.shape[0], rays_o.device
         L = lib()
-        need = int(L.raw("b2n_render_frame_workspace_bytes")(N))
-        if getattr(self, "_ws", None) is None or self._ws.numel() < need or self._ws.device != dev:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        if workspace is None:
+            need = int(L.raw("b2n_render_frame_workspace_bytes")(N))
+            if getattr(self, "_ws", None) is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            workspace = self._ws
         image = out if out is not None else torch.empty(N, 3, device=dev)
-        ws, depth = torch.empty(N, device=dev), torch.empty(N, device=dev)
+        ws, depth = aux if aux is not None else (torch.empty(N, device=dev), torch.empty(N, device=dev))
         cfg = _RenderCfgC(self.bound, dt_gamma, min_near, T_thresh, density_scale, max_steps, self.cascade, self.grid_size,
                           (ctypes.c_float * 6)(*[float(v) for v in self.aabb_infer.tolist()]) if not hasattr(self, "_aabb_host") else self._aabb_host, int(head_ctas))
         f = lambda t: None if t is None else t.detach().float().contiguous().view(-1)
@@ -405,7 +409,7 @@ class HeadModel(nn.Module):
         self._keep = (enc_a, ind_code, eye, bg, cfg)
         L.call("b2n_render_frame", self.handle, ctypes.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(), N, self.density_bitfield.data_ptr(),
                enc_a.data_ptr(), None if ind_code is None else ind_code.data_ptr(), None if eye is None else eye.data_ptr(),
-               None if bg is None else bg.data_ptr(), self._ws.data_ptr(), image.data_ptr(), ws.data_ptr(), depth.data_ptr(),
+               None if bg is None else bg.data_ptr(), workspace.data_ptr(), image.data_ptr(), ws.data_ptr(), depth.data_ptr(),
                torch.cuda.current_stream().cuda_stream)
         return image, ws, depth
 

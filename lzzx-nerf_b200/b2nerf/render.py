@@ -113,7 +113,12 @@ class FrameRenderer:
         else:
             with torch.autocast("cuda", dtype=torch.float16):
                 enc_a = self.m.encode_audio(self.auds).float()              # AudioNet + AudioAttNet through torch (network.py:226-240)
-        self.m.render_frame(self.rays_o, self.rays_d, enc_a, self.ind_code, self.eye, bg_color=self.bg, out=self.image, head_ctas=self.head_ctas, **self.kw)
+        # eager frames use this renderer's own loop workspace and output buffers: several renderers may run concurrently on their own streams
+        if getattr(self, "_eager_ws", None) is None:
+            from ._lib import lib as _lib
+            self._eager_ws = torch.empty(int(_lib().raw("b2n_render_frame_workspace_bytes")(self.N)), dtype=torch.uint8, device=self.dev)
+        self.m.render_frame(self.rays_o, self.rays_d, enc_a, self.ind_code, self.eye, bg_color=self.bg, out=self.image, head_ctas=self.head_ctas,
+                            workspace=self._eager_ws, aux=(self.ws, self.depth), **self.kw)
 
     @torch.no_grad()
     def _build_loop_graph(self):
@@ -178,7 +183,7 @@ class FrameRenderer:
         """Loop iterations the last frame executed (synchronises)."""
         import ctypes
         from ._lib import lib
-        ws = self._graph_ws if self.loop_graph is not None else self.m._ws
+        ws = self._graph_ws if self.loop_graph is not None else self._eager_ws
         it = ctypes.c_int32()
         lib().call("b2n_frame_iterations", ws.data_ptr(), self.N, ctypes.byref(it), torch.cuda.current_stream(self.dev).cuda_stream)
         return int(it.value)

@@ -38,7 +38,7 @@ print(f"wall {wall:.1f} us for 48 frames = {wall / 48:.1f} us per frame; kernel 
 for n, v in busy.most_common(12):
     print(f"  {n:40s} x{cnt[n]:5d}  sum {v:9.1f} us  = {v / 48:7.1f} us per frame  ({100 * v / wall:5.1f} % of wall)")
 # union of head-kernel intervals: fraction of wall time with at least one head kernel running
-iv = sorted((a, b) for n, a, b in ks if n.startswith("k_head_forward"))
+iv = sorted((a, b) for n, a, b in ks if n.startswith("k_head_"))
 u, cur_a, cur_b = 0.0, None, None
 for a, b in iv:
     if cur_b is None or a > cur_b:
@@ -48,3 +48,23 @@ for a, b in iv:
         cur_b = max(cur_b, b)
 if cur_b is not None: u += cur_b - cur_a
 print(f"time with >= 1 head kernel running: {u:.1f} us = {100 * u / wall:.1f} % of wall")
+
+
+def coverage(pred):
+    """time with k = 0, 1, 2, ... kernels matching pred running"""
+    pts = []
+    for n, a, b in ks:
+        if pred(n):
+            pts.append((a, 1)); pts.append((b, -1))
+    pts.sort()
+    hist, level, last = collections.Counter(), 0, t0
+    for t, d in pts:
+        hist[level] += t - last
+        level += d; last = t
+    hist[level] += t1 - last
+    return hist
+
+for label, pred in (("head kernels", lambda n: n.startswith("k_head_")), ("any kernel", lambda n: True),
+                    ("non-head kernels", lambda n: not n.startswith("k_head_"))):
+    h = coverage(pred)
+    print(label + " concurrently running: " + ", ".join(f"{k}: {100 * v / wall:.1f} %" for k, v in sorted(h.items())))
