@@ -44,7 +44,7 @@ constexpr uint32_t FR_THREADS = 128;
 // The march kernel runs NEXT TO another frame's head kernel, whose one CTA per SM leaves 4096 of the 65 536 registers (384 threads x 160) and ~5 KB of shared
 // memory: a 128-thread CTA at 61 -> 64 registers does not fit (8192), a 64-thread CTA does — with 128 threads the march of one frame could only start in the
 // tail of another frame's head launch.  (The composite kernel is 32 registers x 128 threads = 4096: it already fits.)
-constexpr uint32_t FM_THREADS = 64;
+constexpr uint32_t FM_THREADS = 128;
 constexpr uint32_t FR_MAX_ITERS = 64;
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -123,6 +123,27 @@ __device__ __forceinline__ uint32_t warp_append(bool keep, int32_t *counter) {
     base = __shfl_sync(0xffffffffu, base, 0);
     return base + __popc(ballot & ((1u << lane) - 1u));
 }
+// The same with ONE atomic per thread block: the block's kept rays stay adjacent in the list, in thread order.  The lists are scrambled at the granularity of the
+// appending unit (the order in which the atomics arrive), and the network kernel's tiles of 128 samples gather from the tables with far better locality when the
+// rays of a tile are neighbouring pixels.
+template <uint32_t THREADS>
+__device__ __forceinline__ uint32_t block_append(bool keep, int32_t *counter) {
+    __shared__ uint32_t s_cnt[THREADS / 32], s_base;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, keep), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_cnt[warp] = (uint32_t)__popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < THREADS / 32; q++) tot += s_cnt[q];
+        s_base = tot ? (uint32_t)atomicAdd(counter, (int32_t)tot) : 0u;
+    }
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < THREADS / 32; q++) if (q < warp) before += s_cnt[q];
+    return s_base + before + __popc(ballot & ((1u << lane) - 1u));
+}
 // true in exactly one thread block of the grid: the one that finishes last (all other blocks' writes are visible to it)
 __device__ __forceinline__ bool last_block_done(int32_t *ticket) {
     __shared__ int s_last;
@@ -142,7 +163,10 @@ __device__ __forceinline__ bool last_block_done(int32_t *ticket) {
 // reference's composite would see delta == 0 in their first slot, add nothing and drop them, raymarching.cu:2193, 2235) — they are
 // dropped HERE, so the head network only evaluates slots of rays that still contribute: the surviving ray ids and their n_step slots are
 // written compacted (alive_mid / xyzs / dirs / deltas); slots a ray did not fill are zero (the reference's torch.zeros, raymarching.py:384).
-__global__ void __launch_bounds__(FM_THREADS) k_frame_march(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+// Held to 64 registers (no spills), 1024 resident threads per SM: a mid-frame launch has ~100 k live rays, which must fit ONE wave of the 148 SMs — at 96 registers
+// (640 threads per SM) the last CTAs ran as a second wave and doubled the latency-bound kernel's critical path (3570 -> 3785 frames/s; 768 / 1280 / 1536 threads
+// per SM: 3682 / 3752 / 3646).  128-thread CTAs with one list append per CTA (block_append): 3785 -> 3940 (64 / 256 / 512 threads: 3915 / 3900 / 3855).
+__global__ void __launch_bounds__(FM_THREADS, 8) k_frame_march(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
                                                              float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, FrameWs w) {
     const FrameCtrl c = w.ctrl[0];
     if (c.done) return;
@@ -163,7 +187,7 @@ __global__ void __launch_bounds__(FM_THREADS) k_frame_march(const float *__restr
         });
     }
     const bool has = valid && step > 0;
-    const uint32_t p = warp_append(has, &w.counters[0]);
+    const uint32_t p = block_append<FM_THREADS>(has, &w.counters[0]);
     // The warp's surviving rays own the contiguous slot range [p0 n_step, (p0 + cnt) n_step): the 8 floats of a slot are staged through a 1 KB per-warp tile
     // (the kernel must fit beside another frame's head CTA, which leaves ~7 KB of shared memory per SM) and leave as full 128-byte lines instead of
     // 4-byte stores at a 12 n_step-byte stride.
@@ -254,7 +278,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_frame_composite(float T_thresh, 
         w.image[3 * (size_t)idx] = r; w.image[3 * (size_t)idx + 1] = g; w.image[3 * (size_t)idx + 2] = b;
         w.aud_sum[idx] = a0; w.eye_sum[idx] = a1; w.unc_sum[idx] = u;
     }
-    const uint32_t p = warp_append(survive, &w.counters[1]);
+    const uint32_t p = block_append<FR_THREADS>(survive, &w.counters[1]);
     if (survive) w.alive[c.buf ^ 1][p] = idx;
     if (last_block_done(&w.counters[3])) {
         if (threadIdx.x == 0) {
