@@ -87,6 +87,9 @@ typedef struct {
     uint32_t head_ctas;   /* 0: the frame has the GPU to itself — each network launch uses every SM (lowest latency).  > 0: frames from other streams
                            * are in flight beside this one — a network launch takes at most head_ctas SMs (about half of them is best on B200), so two
                            * frames' network launches run side by side and the small march / composite launches never queue behind a full-GPU kernel. */
+    uint32_t image_width; /* 0: no assumption about the rays.  W > 0: the N rays are the pixels of an image of width W in row-major order (N = H * W; W % 16 == 0,
+                           * H % 8 == 0, else ignored) — the frame then walks them in 8 x 16 pixel tiles, which keeps the samples of a network tile close
+                           * together in space.  Per-ray results do not depend on the order. */
 } b2n_render_cfg;
 uint64_t b2n_render_frame_workspace_bytes(uint32_t N);
 int b2n_render_frame(const b2n_model *m, const b2n_render_cfg *cfg, const float *rays_o, const float *rays_d,

@@ -142,7 +142,7 @@ class _AudioWeightsC(ctypes.Structure):     # mirrors b2n_audio_weights
 class _RenderCfgC(ctypes.Structure):        # mirrors b2n_render_cfg
     _fields_ = [("bound", ctypes.c_float), ("dt_gamma", ctypes.c_float), ("min_near", ctypes.c_float), ("T_thresh", ctypes.c_float),
                 ("density_scale", ctypes.c_float), ("max_steps", ctypes.c_uint32), ("cascade", ctypes.c_uint32), ("grid_size", ctypes.c_uint32),
-                ("aabb", ctypes.c_float * 6), ("head_ctas", ctypes.c_uint32)]
+                ("aabb", ctypes.c_float * 6), ("head_ctas", ctypes.c_uint32), ("image_width", ctypes.c_uint32)]
 
 
 class HeadModel(nn.Module):
@@ -388,7 +388,7 @@ class HeadModel(nn.Module):
     # ---- whole-frame inference (renderer.py:406-570) ----------------------------------------------------------------------
     @torch.no_grad()
     def render_frame(self, rays_o, rays_d, enc_a, ind_code=None, eye=None, bg_color=None, dt_gamma=1.0 / 256, max_steps=16, min_near=0.05,
-                     T_thresh=1e-4, density_scale=1.0, out=None, head_ctas=0, workspace=None, aux=None):
+                     T_thresh=1e-4, density_scale=1.0, out=None, head_ctas=0, workspace=None, aux=None, image_width=0):
         """run_cuda_for_inference without host syncs: returns image [N,3] (clamped, background-blended), weights_sum [N], depth [N].
         workspace: a caller-owned uint8 buffer of b2n_render_frame_workspace_bytes(N) — frames rendered concurrently on several streams need one each (default: one
         per model, i.e. calls must be stream-ordered); aux = (weights_sum [N], depth [N]) output buffers to reuse."""
@@ -403,7 +403,7 @@ class HeadModel(nn.Module):
         image = out if out is not None else torch.empty(N, 3, device=dev)
         ws, depth = aux if aux is not None else (torch.empty(N, device=dev), torch.empty(N, device=dev))
         cfg = _RenderCfgC(self.bound, dt_gamma, min_near, T_thresh, density_scale, max_steps, self.cascade, self.grid_size,
-                          (ctypes.c_float * 6)(*[float(v) for v in self.aabb_infer.tolist()]) if not hasattr(self, "_aabb_host") else self._aabb_host, int(head_ctas))
+                          (ctypes.c_float * 6)(*[float(v) for v in self.aabb_infer.tolist()]) if not hasattr(self, "_aabb_host") else self._aabb_host, int(head_ctas), int(image_width))
         f = lambda t: None if t is None else t.detach().float().contiguous().view(-1)
         enc_a, ind_code, eye, bg = f(enc_a), f(ind_code), f(eye), f(bg_color)
         self._keep = (enc_a, ind_code, eye, bg, cfg)

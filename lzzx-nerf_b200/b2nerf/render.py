@@ -14,8 +14,9 @@ from .model import HeadModel
 
 class FrameRenderer:
     def __init__(self, model: HeadModel, n_rays, eye=0.4, ind_index=0, dt_gamma=1.0 / 256, max_steps=16, T_thresh=1e-4, use_graph=True, fused_audio=True,
-                 camera=None, torso=None, bg_coords=None, smooth_lips=False, lips_state=None, lips_lambda=0.35, head_ctas=0):
-        """head_ctas: b2n_render_cfg.head_ctas — 0 when this renderer has the GPU to itself; FramePipeline sets it for its slots.
+                 camera=None, torso=None, bg_coords=None, smooth_lips=False, lips_state=None, lips_lambda=0.35, head_ctas=0, image_width=0):
+        """image_width: b2n_render_cfg.image_width — the rays handed to render_device / render_host are the row-major pixels of an image of this width (0: unknown;
+        taken from `camera` when that is given).  head_ctas: b2n_render_cfg.head_ctas — 0 when this renderer has the GPU to itself; FramePipeline sets it for its slots.
         smooth_lips: the reference's opt.smooth_lips (renderer.py:456-460, on in the serving config HubertInferenceMQ.py): the audio code of frame k is
         0.35 * (smoothed code of frame k-1) + 0.65 * (its own); the state is a device float[33] (`lips_state`, shared by the slots of a FramePipeline) and the
         audio kernel runs in frame order in front of the frame graph instead of inside it.  reset_lips() starts a new sequence.
@@ -25,6 +26,7 @@ class FrameRenderer:
         the per-ray bg_color buffer the head frame reads (renderer.py:572-631 then :559-561); set the head pose with set_torso_pose()."""
         self.m = model
         self.head_ctas = int(head_ctas)
+        self.image_width = int(camera[1]) if camera is not None else int(image_width)
         self.torso = torso
         self.camera = camera
         self.dev = next(model.parameters()).device
@@ -118,7 +120,7 @@ class FrameRenderer:
             from ._lib import lib as _lib
             self._eager_ws = torch.empty(int(_lib().raw("b2n_render_frame_workspace_bytes")(self.N)), dtype=torch.uint8, device=self.dev)
         self.m.render_frame(self.rays_o, self.rays_d, enc_a, self.ind_code, self.eye, bg_color=self.bg, out=self.image, head_ctas=self.head_ctas,
-                            workspace=self._eager_ws, aux=(self.ws, self.depth), **self.kw)
+                            workspace=self._eager_ws, aux=(self.ws, self.depth), image_width=self.image_width, **self.kw)
 
     @torch.no_grad()
     def _build_loop_graph(self):
@@ -128,7 +130,7 @@ class FrameRenderer:
         L, m = lib(), self.m
         need = int(L.raw("b2n_render_frame_workspace_bytes")(self.N))
         self._graph_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
-        cfg = _RenderCfgC(m.bound, self.kw["dt_gamma"], 0.05, self.kw["T_thresh"], 1.0, self.kw["max_steps"], m.cascade, m.grid_size, m._aabb_host, self.head_ctas)
+        cfg = _RenderCfgC(m.bound, self.kw["dt_gamma"], 0.05, self.kw["T_thresh"], 1.0, self.kw["max_steps"], m.cascade, m.grid_size, m._aabb_host, self.head_ctas, self.image_width)
         aw = m.audio_weights_struct() if (self.fused_audio and not self.smooth_lips) else None        # smooth_lips: the audio kernel runs in frame order, in front of the graph
         self._graph_keep = (cfg, aw, self.ind_code.float().contiguous().view(-1), self.eye.float().contiguous().view(-1))
         h = ctypes.c_void_p()

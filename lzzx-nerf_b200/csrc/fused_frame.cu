@@ -15,6 +15,7 @@
 //     step += n_step; loop while step < max_steps and n_alive > 0             renderer.py:503
 // Per-ray arithmetic is the same code as the per-op kernels (dda.cuh, composite order), so images match the op-by-op
 // path bit for bit given the same network outputs.
+#include <stdlib.h>
 #include "common.cuh"
 #include "dda.cuh"
 #include "fused_head.cuh"
@@ -41,9 +42,8 @@ struct FrameWs {            // carved out of the caller's workspace
 };
 
 constexpr uint32_t FR_THREADS = 128;
-// The march kernel runs NEXT TO another frame's head kernel, whose one CTA per SM leaves 4096 of the 65 536 registers (384 threads x 160) and ~5 KB of shared
-// memory: a 128-thread CTA at 61 -> 64 registers does not fit (8192), a 64-thread CTA does — with 128 threads the march of one frame could only start in the
-// tail of another frame's head launch.  (The composite kernel is 32 registers x 128 threads = 4096: it already fits.)
+// (With the four-warpgroup head kernel nothing co-resides on an SM that runs a head CTA any more — 512 threads x 125 registers — so the march CTA is sized for
+// coherent list appends and one-wave launches, see k_frame_march.)
 constexpr uint32_t FM_THREADS = 128;
 constexpr uint32_t FR_MAX_ITERS = 64;
 
@@ -74,7 +74,7 @@ static size_t carve(FrameWs *w, uint8_t *base, uint32_t N) {
 // probing up to the box entry, so the first march iteration starts where the samples are instead of walking ~35 empty cells per ray.
 __global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ rays_o, const float *__restrict__ rays_d, uint32_t N, float min_near,
                                                      float a0, float a1, float a2, float a3, float a4, float a5, uint32_t max_steps, float bound, float dt_gamma,
-                                                     uint32_t C, uint32_t H, int clip, FrameWs w) {
+                                                     uint32_t C, uint32_t H, int clip, uint32_t tile_w, FrameWs w) {
     __shared__ float bx[6];
     if (threadIdx.x < 6 * 32) {                   // warp a reduces component a of the partial boxes
         const uint32_t a = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,7 +102,14 @@ __global__ void __launch_bounds__(256) k_frame_init(const float *__restrict__ ra
         w.nears[n] = tn; w.fars[n] = tf; w.rays_t[n] = t;
         w.ws[n] = 0.0f; w.depth[n] = 0.0f; w.aud_sum[n] = 0.0f; w.eye_sum[n] = 0.0f; w.unc_sum[n] = 0.0f;
         w.image[3 * n] = 0.0f; w.image[3 * n + 1] = 0.0f; w.image[3 * n + 2] = 0.0f;
-        w.alive[0][n] = (int32_t)n;
+        // first alive list: identity, or — when the caller says the rays are the pixels of an image of width tile_w (row-major) — 8 x 16 pixel tiles, so that a
+        // network tile of 128 samples is a compact patch of the image instead of a 128-pixel strip of one row (the tri-plane cells it gathers are shared in both directions)
+        uint32_t slot = n;
+        if (tile_w) {
+            const uint32_t row = n / tile_w, col = n - row * tile_w;
+            slot = ((row >> 3) * (tile_w >> 4) + (col >> 4)) * 128u + ((row & 7u) << 4) + (col & 15u);
+        }
+        w.alive[0][slot] = (int32_t)n;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         FrameCtrl c = {};
@@ -367,8 +374,12 @@ static int enqueue_init(const FramePlan &p, cudaStream_t st) {
     }
     const uint32_t sms = (uint32_t)sm_count();
     uint32_t g = ceil_div<uint32_t>(p.N, 256); if (g > sms * 8) g = sms * 8;
+    // image-shaped ray sets: width from the pose stage, else from the caller's hint; whole 8 x 16 tiles only
+    uint32_t tile_w = p.io.pose ? p.io.W : p.cfg.image_width;
+    if (tile_w == 0 || (tile_w & 15u) || p.N % tile_w != 0 || ((p.N / tile_w) & 7u)) tile_w = 0;
+    if (const char *e = getenv("B2N_FRAME_TILES")) { if (e[0] == '0') tile_w = 0; }      // A/B
     k_frame_init<<<g, 256, 0, st>>>(p.rays_o, p.rays_d, p.N, p.cfg.min_near, p.cfg.aabb[0], p.cfg.aabb[1], p.cfg.aabb[2], p.cfg.aabb[3], p.cfg.aabb[4], p.cfg.aabb[5],
-                                    p.cfg.max_steps, p.cfg.bound, p.cfg.dt_gamma, p.cfg.cascade, H, clip, p.w);
+                                    p.cfg.max_steps, p.cfg.bound, p.cfg.dt_gamma, p.cfg.cascade, H, clip, tile_w, p.w);
     return check_launch("render_frame(init)");
 }
 // one loop iteration: march (+ drop rays without samples) -> fused head -> composite (+ survivor list, next control block)
