@@ -527,3 +527,23 @@ def test_head_tile_schedules_give_identical_outputs(monkeypatch, wg4):
         else:
             for k, (a_, b_) in enumerate(zip(ref, outs)):
                 assert torch.equal(a_, b_), (sched, ctas, k, float((a_ - b_).abs().max()))
+
+
+def test_tiled_first_ray_order_renders_the_same_image():
+    """b2n_render_cfg.image_width only changes the ORDER in which an image-shaped frame walks its rays (8 x 16 pixel tiles instead of rows): every pixel bit for bit,
+    WHILE-graph and eager path; a width that does not tile (not a multiple of 16) is ignored."""
+    from b2nerf.render import FrameRenderer
+    m = _model(seed=7)
+    m.density_bitfield.copy_(torch.from_numpy(scene.bitfield_from_grid(scene.density_grid())).cuda())
+    H, W = 96, 160
+    j, i = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    o, d = scene.rays_for_pixels(scene.camera_pose(2), H, W, i.ravel(), j.ravel())
+    rays_o, rays_d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    auds = torch.from_numpy(scene.audio_window(2)).cuda()
+    ref = FrameRenderer(m, H * W, use_graph=True, image_width=0).render_device(rays_o, rays_d, auds).clone()
+    for use_graph in (True, False):
+        for width in (W, W - 8):          # 152 is not a multiple of 16 -> ignored (and H * W % 152 != 0)
+            img = FrameRenderer(m, H * W, use_graph=use_graph, image_width=width).render_device(rays_o, rays_d, auds).clone()
+            torch.cuda.synchronize()
+            assert torch.equal(img, ref), (use_graph, width)
+    assert 0.0 < float(ref.mean()) < 1.0
