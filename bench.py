@@ -589,7 +589,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b2nerf", choices=["b2nerf", "reference"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=5, help="frames in flight per GPU (independent frames on separate streams; 1 = strictly one after another)")
+    ap.add_argument("--in-flight", type=int, default=8, help="frames in flight per GPU (independent frames on separate streams; 1 = strictly one after another)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline leg (N = 1)")

@@ -282,9 +282,9 @@ class FramePipeline:
         if self.smooth and kw.get("lips_state") is None:                 # ONE smoothing state for the whole frame sequence
             kw["lips_state"] = torch.zeros(33, device=next(model.parameters()).device)
         if self.depth >= 2 and "head_ctas" not in kw:
-            # several frames share the GPU: each frame's network launches take half of the SMs, so two of them run side by side and the small march /
-            # composite launches of the other frames find free SMs (3397 -> 3550 frames/s at depth 5 on B200; 60..100 of 148 SMs all within 1.5 %)
-            kw["head_ctas"] = torch.cuda.get_device_properties(next(model.parameters()).device).multi_processor_count // 2
+            # several frames share the GPU: each frame's network launches take 40 % of the SMs, so two of them run side by side and the small march /
+            # composite launches of the other frames find free SMs (3397 -> 3550 frames/s at depth 5 on B200 when introduced; 50..100 of 148 SMs are within 2 %)
+            kw["head_ctas"] = max(1, int(round(0.4 * torch.cuda.get_device_properties(next(model.parameters()).device).multi_processor_count)))
         self.slots = [FrameRenderer(model, n_rays, **kw) for _ in range(self.depth)]
         self.dev = self.slots[0].dev
         # smooth_lips makes the audio code of frame k depend on frame k-1: the (tiny) audio kernels run in frame order on their own stream, the frames
